@@ -1,0 +1,232 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden
+
+TEST INFRASTRUCTURE.  The reference (timlod/onset-fingerprinting) has no tests and ships no
+data, so the only way to pin the oracle is to run the reference itself on seeded synthetic
+input (onset_fingerprinting_b200/synth.py) and commit what it returned.  The reference is
+imported from /root/reference through oracle/ref_harness.py (librosa / loopmate stubbed, DLL
+compiled by `make -C oracle ref`).  Inputs are NOT stored: tests regenerate them from the same
+seeds (a sha1 of the input is stored to detect generator drift).
+
+Recorded environment: see 'env' in each file (numpy/scipy versions, numpy SIMD dispatch --
+float32 log10/power results depend on it).
+"""
+from __future__ import annotations
+
+import hashlib
+import io
+import contextlib
+import sys
+from pathlib import Path
+
+import numpy as np
+import scipy
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import ref_harness as rh  # noqa: E402
+from onset_fingerprinting_b200 import synth  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+DETECT_CASES = {
+    # name: (synth kwargs, detect kwargs)
+    "default3": (dict(seconds=3.0, seed=1), dict()),
+    "realtime3": (dict(seconds=2.5, seed=2),
+                  dict(hipass_freq=0, fast_ar=(0.3, 800), slow_ar=(8000, 8000), on_threshold=0.45,
+                       off_threshold=0.45)),
+    "manual_b100": (dict(seconds=2.0, seed=3), dict(block_size=100, on_threshold=1.8, off_threshold=1.2)),
+    "b256_partial": (dict(seconds=2.0, seed=4), dict(block_size=256, hipass_freq=1000.0, cooldown=4000)),
+    "mesh16": (dict(seconds=1.5, seed=5, sensors=synth.SENSORS_16MESH, medium="drumhead"), dict(block_size=64)),
+}
+
+FIX_OPTS = {
+    "defaults": dict(),
+    "d1_abs": dict(d=1, take_abs=True),
+    "up_zero": dict(onset_direction="up", zero_left=True, normalization_cutoff=20, onset_tolerance=108,
+                    filter_size=7, shift_onsets=40),
+    "d1_down": dict(d=1, onset_direction="down", onset_tolerance=50),
+    "abs150": dict(take_abs=True, onset_tolerance=150, d=1, filter_size=7),
+}
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def env():
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        np.show_config()
+    simd = [ln.strip() for ln in buf.getvalue().splitlines() if "AVX" in ln or "SSE" in ln]
+    return f"numpy {np.__version__}; scipy {scipy.__version__}; simd {' '.join(simd)[:400]}"
+
+
+def gen_detect(det):
+    for name, (skw, dkw) in DETECT_CASES.items():
+        x, hits = synth.drum_recording(**skw)
+        ch, on, rel = det.detect_onsets_amplitude(x, sr=96000, **dkw)
+        np.savez_compressed(
+            OUT / f"detect_{name}.npz", channels=np.asarray(ch, np.int32), onsets=np.asarray(on, np.int64),
+            rel_sub=rel[::16].astype(np.float32), rel_shape=np.asarray(rel.shape), x_sha=sha(x), env=env(),
+            arrival=hits["arrival"])
+        print(name, x.shape, len(ch), "onsets")
+
+
+def gen_stream(det):
+    """AmplitudeOnsetDetector block by block (realtime/audio.py:39-52 settings), no warm-up."""
+    x, _ = synth.drum_recording(seconds=1.5, seed=7, first_hit=20000)
+    od = det.AmplitudeOnsetDetector(3, 128, hipass_freq=0, fast_ar=(0.3, 800), slow_ar=(8000, 8000),
+                                    on_threshold=0.45, off_threshold=0.45, cooldown=1323, sr=96000)
+    blocks, chans, deltas, rels = [], [], [], []
+    for b, i in enumerate(range(0, len(x) - 127, 128)):
+        c, d, r = od(x[i:i + 128])
+        if b % 8 == 0:
+            rels.append(r[::16].copy())
+        for cc, dd in zip(c, d):
+            blocks.append(b); chans.append(cc); deltas.append(dd)
+    np.savez_compressed(OUT / "stream_realtime.npz", blocks=np.asarray(blocks, np.int32),
+                        channels=np.asarray(chans, np.int32), deltas=np.asarray(deltas, np.int32),
+                        rel_sub=np.asarray(rels, np.float32), x_sha=sha(x), env=env())
+    print("stream", len(blocks), "onsets")
+
+
+def gen_kernels(det):
+    """Known answers for the two DLL kernels, find_onset_groups and cross_correlation_lag."""
+    rng = np.random.default_rng(11)
+    xb = (rng.uniform(-70, 0, (4, 64, 5))).astype(np.float32)
+    ar = det.AREnvelopeFollower(np.full((64, 5), -70, np.float32), 3, 383)
+    ar_out = np.stack([ar(b).copy() for b in xb])
+    mm = det.MinMaxEnvelopeFollower(np.array([[0, 10]] * 5).T, alpha_min=1e-4, alpha_max=1e-5, minmin=2)
+    xm = rng.uniform(0, 30, (4, 64, 5)).astype(np.float32)
+    xm[1, :10] = 1.0
+    mm_out = np.stack([np.stack([v.copy() for v in mm(b)]) for b in xm])
+    bw = det.ButterworthFilter(2000, 3, 4, 96000, "high")
+    xf = rng.standard_normal((3, 500, 3)).astype(np.float32)
+    hp_out = np.stack([bw(b) for b in xf])
+    # cross_correlation_lag on random signals / options
+    cc_in, cc_out = [], []
+    for t in range(400):
+        n = int(rng.integers(60, 400))
+        a = rng.standard_normal(n).astype(np.float32)
+        b = np.roll(a, int(rng.integers(-40, 40))) + 0.3 * rng.standard_normal(n).astype(np.float32)
+        tol = int(rng.choice([30, 50, 64, 108]))
+        cut = int(rng.choice([10, 20]))
+        o0 = int(rng.integers(0, n))
+        o1 = int(rng.integers(0, n))
+        d = int(rng.integers(0, 2))
+        ab = bool(rng.integers(0, 2))
+        use_legal = bool(t % 5 == 0)
+        l0, l1 = sorted(rng.integers(-20, 80, 2).tolist())
+        r = det.cross_correlation_lag(a, b, onsets=None if use_legal else (o0, o1),
+                                      legal_lags=(l0, l1) if use_legal else None, d=d,
+                                      normalization_cutoff=cut, onset_tolerance=tol, take_abs=ab)
+        cc_in.append((t, n, tol, cut, o0, o1, d, int(ab), int(use_legal), l0, l1))
+        cc_out.append(-(2**31) if r is None else int(r))
+    # find_onset_groups
+    g1 = det.find_onset_groups([100, 130, 90, 5000, 5010, 5020, 9000], [0, 1, 2, 0, 1, 2, 0], 1000, 3)
+    g2 = det.find_onset_groups([100, 130, 90, 5000, 5010, 5020, 9000, 9010, 9020], [0, 1, 2, 0, 1, 2, 2, 1, 0],
+                               1000, 3, close_channel=2)
+    np.savez_compressed(OUT / "kernels.npz", ar_in=xb, ar_out=ar_out, mm_in=xm, mm_out=mm_out, hp_in=xf,
+                        hp_out=hp_out, hp_b=bw.b, hp_a=bw.a, cc_params=np.asarray(cc_in, np.int64),
+                        cc_out=np.asarray(cc_out, np.int64), groups1=g1, groups2=g2, env=env())
+    print("kernels ok; cc None count", sum(1 for v in cc_out if v == -(2**31)))
+
+
+def gen_fix(det):
+    for tag, skw, dkw in (("3ch", dict(seconds=3.0, seed=21), dict()),
+                          ("16ch", dict(seconds=2.0, seed=22, sensors=synth.SENSORS_16MESH, medium="drumhead"),
+                           dict())):
+        x, _ = synth.drum_recording(**skw)
+        ch, on, _ = det.detect_onsets_amplitude(x, sr=96000, **dkw)
+        groups = det.find_onset_groups(on, ch, 1000 if tag == "3ch" else 1500, x.shape[1])
+        out = {"groups": groups, "x_sha": sha(x), "env": env()}
+        for name, kw in FIX_OPTS.items():
+            fixed = np.zeros_like(groups)
+            raised = np.zeros(len(groups), np.int32)
+            for j in range(len(groups)):  # per group: the reference can raise
+                try:
+                    fixed[j] = det.fix_onsets(x, groups[j:j + 1], **kw)[0]
+                except ValueError:
+                    raised[j] = 1
+                    fixed[j] = groups[j]
+            out[f"fixed_{name}"] = fixed
+            out[f"raised_{name}"] = raised
+            print(tag, name, "moved", float((fixed != groups + kw.get("shift_onsets", 0)).mean()), "raised",
+                  int(raised.sum()))
+        np.savez_compressed(OUT / f"fix_{tag}.npz", **out)
+
+
+def gen_locate(ml):
+    rng = np.random.default_rng(31)
+    for tag, sensors, medium in (("air3", synth.SENSORS_3MIC, "air"),
+                                 ("drumhead3", [(0.9, 0, 0), (0.9, 120, 0), (0.5, 240, 0)], "drumhead")):
+        m = ml.Multilaterate3D(sensors, sr=96000, medium=medium)
+        locs = synth.sensor_xyz(sensors)
+        c = synth.speed_cm_s(medium)
+        n = 1500
+        onsets = np.zeros((n, 3), np.int64)
+        res = np.full((n, 2), np.nan)
+        for h in range(n):
+            rr = 0.95 * 17.78 * np.sqrt(rng.uniform())
+            ang = rng.uniform(0, 2 * np.pi)
+            p = np.array([rr * np.cos(ang), rr * np.sin(ang), 0.0])
+            dist = np.sqrt(((locs - p) ** 2).sum(1))
+            onsets[h] = 100000 * (h + 1) + np.round(dist / c * 96000) + rng.integers(-3, 4, 3)
+            m.ongoing = []
+            r = None
+            with contextlib.redirect_stdout(io.StringIO()):
+                for s in np.argsort(onsets[h], kind="stable"):
+                    r = m.locate(int(s), int(onsets[h, s]))
+            if r is not None:
+                res[h] = r
+        S = len(sensors)
+        maps = np.full((S, S) + m.lag_maps[0][1].shape, np.nan, np.float32)
+        mx = np.full((S, S), np.nan, np.float32)
+        mn = np.full((S, S), np.nan, np.float32)
+        for i in range(S):
+            for j in range(S):
+                if i != j:
+                    maps[i, j] = m.lag_maps[i][j]; mx[i, j] = m.max_lags[i][j]; mn[i, j] = m.min_lags[i][j]
+        np.savez_compressed(OUT / f"locate_{tag}.npz", onsets=onsets, xy=res, maps=maps, max_lags=mx, min_lags=mn,
+                            max_max=np.asarray(m.max_max_lags, np.float32), c=m.c, radius=m.radius,
+                            sensor_locs=np.asarray(m.sensor_locs), sensors=np.asarray(sensors, np.float64),
+                            medium=medium, env=env())
+        print(tag, "located", int(np.isfinite(res[:, 0]).sum()), "of", n)
+
+
+def gen_online_cc():
+    """c/test.py:5-46 workload (shortened): stream two noisy sines through online_cc."""
+    occ = rh.load_online_cc()
+    n, bs = 256, 64
+    cc = occ.CrossCorrelation(n, bs)
+    ns = n * 40
+    rng = np.random.default_rng(0)
+    t = np.linspace(0, 10 * ns / (n * 10000), ns)
+    a = (np.sin(2 * np.pi * t * 300) + 0.01 * rng.random(ns)).astype(np.float32)
+    b = (np.sin(2 * np.pi * t * 300 + 0.5) + 0.01 * rng.random(ns)).astype(np.float32)
+    frames = []
+    for k, i in enumerate(range(0, ns - bs + 1, bs)):
+        out = cc.update(a[i:i + bs], b[i:i + bs])
+        if k in (3, 10, 50, ns // bs - 1):
+            frames.append(out.copy())
+    np.savez_compressed(OUT / "online_cc.npz", a=a, b=b, frames=np.asarray(frames), frame_idx=np.asarray(
+        [3, 10, 50, ns // bs - 1]), n=n, block=bs, env=env())
+    print("online_cc ok")
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    det, ml = rh.load_reference()
+    gen_detect(det)
+    gen_stream(det)
+    gen_kernels(det)
+    gen_fix(det)
+    gen_locate(ml)
+    gen_online_cc()
+
+
+if __name__ == "__main__":
+    main()
