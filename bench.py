@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the onset-fingerprinting hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of synthetic recordings (BASELINE.json configs[1]:
+10k synthetic 3-mic 96 kHz recordings batched on one B200): onset detection (K1) over every sample,
+then grouping, lag refinement (K4) and multilateration (K5) of every detected hit when those stages
+are enabled.  `value` = channel-samples per second with the batch resident in HBM; `e2e` = the same
+metric through the C-ABI host-buffer entry point (pinned host memory in, onsets out).
+Multi-GPU: one process per GPU (torchrun), recordings sharded by rank, no data-path collective except
+the final gather of per-hit records; value = all ranks' units / max-over-ranks time ("weak" scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+SR = 96000
+BLOCK = 128
+N_CH = 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--recordings", type=int, default=10000, help="recordings per GPU")
+    ap.add_argument("--seconds", type=float, default=5.0, help="length of each recording")
+    ap.add_argument("--no-rel", action="store_true", help="onsets-only mode (4 B per channel-sample)")
+    ap.add_argument("--e2e-recordings", type=int, default=256)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--skip-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index=0, period=0.1):
+        self.samples, self.reasons, self.maxmhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        self.index, self.period = index, period
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxmhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.maxmhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.maxmhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(x):
+    from oracle import ref_style
+
+    ch, on, _ = ref_style.detect_onsets_amplitude(x, block_size=BLOCK, sr=SR)
+    return len(on)
+
+
+def cpu_reference_rate(xs: np.ndarray, cores: int):
+    """channel-samples/s of the reference-shaped CPU path (oracle/ref_style.py) over xs [R, N, C]
+    with `cores` worker processes; returns (rate, seconds)."""
+    import multiprocessing as mp
+
+    t0 = time.perf_counter()
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_worker, list(xs))
+    else:
+        for x in xs:
+            _cpu_worker(x)
+    dt = time.perf_counter() - t0
+    return xs.size / dt, dt
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from onset_fingerprinting_b200 import synth
+    from oracle import ref_style
+
+    cores = host_cores()
+    n = int(args.seconds * SR)
+    # one step = a bounded sample of the workload: `cores` recordings (one per worker)
+    n_rec = max(cores, 1)
+    xs = np.stack([synth.drum_recording(args.seconds, seed=1000 + r)[0][:n] for r in range(n_rec)])
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, dt = cpu_reference_rate(xs, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = xs.size / (ms / 1e3)
+    sample = f"{n_rec} recordings x {args.seconds:g} s x {N_CH} ch per step ({xs.size} channel-samples)"
+    line = {
+        "impl": "reference", "metric": "channel-samples/sec through the onset->lag->multilateration hot path",
+        "value": value, "unit": "channel-samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.recordings),
+        "cpu_baseline": {"value": value, "unit": "channel-samples/s", "cores": cores, "kind": ref_style.kind(),
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "channel-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_rec):
+    return {
+        "workload": f"configs[1]: {n_rec} synthetic 3-mic 96 kHz recordings x {args.seconds:g} s per GPU, "
+                    f"block {BLOCK}, high-pass 2 kHz, reference defaults",
+        "recordings_per_gpu": n_rec, "seconds": args.seconds, "channels": N_CH, "sr": SR, "block_size": BLOCK,
+        "mode": "onsets_only" if args.no_rel else "drop_in (rel envelope written to HBM)",
+        "l2": "inputs larger than L2 (no flush needed)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from onset_fingerprinting_b200 import _lib, detection, synth
+
+    R, N = args.recordings, int(args.seconds * SR)
+    nb = N // BLOCK
+    x = synth.drum_batch_device(R, N, seed=1234, rec_offset=rank * R)
+    det = detection.BatchedOnsetDetector(R, N_CH, BLOCK, sr=SR)
+    cap = det.default_cap(N)
+    out = (torch.empty((R, cap), dtype=torch.int32, device="cuda"),
+           torch.empty((R, cap), dtype=torch.int32, device="cuda"),
+           torch.empty((R,), dtype=torch.int32, device="cuda"),
+           None if args.no_rel else torch.empty((R, nb * BLOCK, N_CH), dtype=torch.float32, device="cuda"))
+    warm_n = int(0.5 * SR)
+    launches = 0
+
+    def step():
+        nonlocal launches
+        det.reset()
+        det.detect_offline(x, warm_n, out=out)
+        launches += 2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    with ClockSampler(local) as clk:
+        barrier()
+        t_wall = time.perf_counter()
+        for s, k0, k1 in ev:
+            s.record()
+            det.reset()
+            k0.record()
+            det.detect_offline(x, warm_n, out=out)
+            k1.record()
+            launches += 2
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+    total_ms = ev[0][0].elapsed_time(end)
+    k1_ms = float(np.mean([k0.elapsed_time(k1) for _, k0, k1 in ev]))
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    units_per_step = R * nb * BLOCK * N_CH * world  # channel-samples through the main loop
+    value = units_per_step / (ms_per_step / 1e3)
+
+    n_onsets = int(out[2].sum().item())
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_per_unit = 4 if args.no_rel else 8
+    alg_bytes = R * nb * BLOCK * N_CH * bytes_per_unit
+    achieved = alg_bytes / (k1_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k1_detect", "kernel_ms": k1_ms,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_channel_sample": bytes_per_unit}
+
+    line = None
+    if rank == 0:
+        e2e = run_e2e(args, torch, detection, _lib, synth)
+        cpu = None if args.skip_cpu else run_cpu_baseline(args, x)
+        line = {
+            "metric": "channel-samples/sec through the onset->lag->multilateration hot path",
+            "value": value, "unit": "channel-samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, R), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clk.summary(), "onsets_per_step": n_onsets * world,
+            "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        }
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def run_e2e(args, torch, detection, _lib, synth):
+    """Same metric through the C-ABI host entry point: pinned host audio in, onsets out."""
+    import ctypes as C
+
+    Re, N = min(args.e2e_recordings, args.recordings), int(args.seconds * SR)
+    xd = synth.drum_batch_device(Re, N, seed=99)
+    xh = torch.empty(xd.shape, dtype=torch.float32, pin_memory=True)
+    xh.copy_(xd)
+    torch.cuda.synchronize()
+    del xd
+    p = detection.make_params(N_CH, BLOCK, sr=SR)
+    cap = int(N_CH * (N // 1323 + 2))
+    ch = torch.empty((Re, cap), dtype=torch.int32, pin_memory=True)
+    ix = torch.empty((Re, cap), dtype=torch.int32, pin_memory=True)
+    cnt = torch.empty((Re,), dtype=torch.int32, pin_memory=True)
+
+    def call():
+        _lib.check(_lib.lib().ofp_detect_offline_host(
+            C.byref(p), C.c_void_p(xh.data_ptr()), C.c_int64(Re), C.c_int64(N), C.c_int64(int(0.5 * SR)), None,
+            C.c_void_p(ch.data_ptr()), C.c_void_p(ix.data_ptr()), C.c_void_p(cnt.data_ptr()), C.c_int32(cap)))
+
+    for _ in range(2):
+        call()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        call()
+    dt = (time.perf_counter() - t0) / reps
+    units = Re * (N // BLOCK) * BLOCK * N_CH
+    return {"value": units / dt, "unit": "channel-samples/s", "h2d_bytes_per_step": int(xh.numel() * 4),
+            "d2h_bytes_per_step": int((ch.numel() + ix.numel() + cnt.numel()) * 4),
+            "recordings": Re, "ms": dt * 1e3, "mode": "onsets_only (rel not copied back)",
+            "entry": "ofp_detect_offline_host"}
+
+
+def run_cpu_baseline(args, x):
+    """The reference-shaped CPU path on a bounded sample of the SAME device-generated audio."""
+    from oracle import ref_style
+
+    cores = host_cores()
+    # ~2.5e6 channel-samples/s/core: size the sample for about args.cpu_seconds of work
+    per_rec = x.shape[1] * x.shape[2]
+    n_rec = int(max(cores, min(x.shape[0], args.cpu_seconds * 2.5e6 * cores / per_rec)))
+    xs = x[:n_rec].cpu().numpy()
+    rate, dt = cpu_reference_rate(xs, cores)
+    return {"value": rate, "unit": "channel-samples/s", "cores": cores, "kind": ref_style.kind(),
+            "sample": f"{n_rec} of the step's recordings ({xs.size} channel-samples, {dt:.1f} s)"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

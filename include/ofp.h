@@ -1,0 +1,126 @@
+/*
+ * ofp.h -- C ABI of libofp.so, the B200 (sm_100a) implementation of onset-fingerprinting's
+ * data-parallel hot path.  This is the drop-in boundary: every entry point below replaces a
+ * native interface or a Python hot loop of the reference (file:line under
+ * /root/reference/onset_fingerprinting/ given per function).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Pointers named *_dev are DEVICE pointers owned by
+ *     the caller (e.g. torch allocations); *_host are host pointers.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no hidden
+ *     synchronisation, except the *_host convenience entry points which synchronise before
+ *     returning because they hand results back in host memory.
+ *   - return value: 0 on success, a negative OFP_E* code otherwise; ofp_last_error() gives a
+ *     thread-local message.  The reference's ctypes DLL has no error reporting at all
+ *     (detection.py:520-538 sets argtypes only), so this is an extension, not a change.
+ *   - the library allocates nothing persistent except the opaque ofp_detector / ofp_ccstream
+ *     handles.  A handle must not be used from two streams concurrently (the reference's
+ *     follower objects are equally stateful and not thread safe).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     OFP_ECUDA.
+ */
+#ifndef OFP_H
+#define OFP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFP_OK 0
+#define OFP_EINVAL (-1)  /* bad argument */
+#define OFP_ECUDA (-2)   /* CUDA runtime / driver error, see ofp_last_error() */
+#define OFP_ENOMEM (-3)
+#define OFP_EUNSUPPORTED (-4)
+
+const char *ofp_last_error(void);
+/* "libofp <version> sm_100a" */
+const char *ofp_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  amplitude onset detector
+ *     replaces AmplitudeOnsetDetector (detection.py:595-840) and the three ctypes calls it
+ *     makes per block into envelope_follower.so (ar_envelope x2, minmax_envelope;
+ *     envelope_follower.c:6-57), plus ButterworthFilter (detection.py:487-501).
+ * ------------------------------------------------------------------------------------- */
+
+/* AmplitudeOnsetDetector.__init__ arguments after the host-side conversions the reference
+ * performs (detection.py:493-496, 514-515, 553-555, 683-712). */
+typedef struct ofp_detector_params {
+    int32_t n_channels;   /* n_signals, 1..32 */
+    int32_t block_size;   /* block_size */
+    int32_t use_hp;       /* hipass_freq != 0 */
+    int32_t manual;       /* on_threshold > 1: absolute thresholds, min/max tracker unused */
+    int32_t cooldown;     /* samples */
+    float b[5], a[5];     /* float32(scipy.signal.butter(4, hipass_freq, 'high', fs=sr)) */
+    float floor_db;       /* floor */
+    float fast_att, fast_rel, slow_att, slow_rel; /* float32(1/attack), float32(1/release) */
+    float on_thr, off_thr;                        /* on_threshold, off_threshold */
+    float alpha_min, alpha_max, minmin;           /* 1e-4, 1e-5, 2 in the reference */
+} ofp_detector_params;
+
+typedef struct ofp_detector ofp_detector;
+
+/* One detector per stream/recording: n_streams independent AmplitudeOnsetDetector states
+ * (filter delay line, both followers, min/max, FSM) resident in device memory. */
+int ofp_detector_create(ofp_detector **out, int64_t n_streams, const ofp_detector_params *p);
+int ofp_detector_destroy(ofp_detector *det);
+/* Back to the state right after __init__. */
+int ofp_detector_reset(ofp_detector *det, void *stream);
+/* Copy one field of the per-lane state out of / into the detector (checkpoint, inspection):
+ * fields 0..3 z[0..3], 4 yf, 5 ys, 6 min, 7 max, 8 prev (float32); 9 state, 10 debounce (int32).
+ * buf_dev: device buffer of n_streams*n_channels 32-bit words, lane = stream*C + channel. */
+int ofp_detector_get_state(ofp_detector *det, int field, void *buf_dev, void *stream);
+int ofp_detector_set_state(ofp_detector *det, int field, const void *buf_dev, void *stream);
+
+/* detect_onsets_amplitude (detection.py:19-86) for a batch of recordings.
+ *   x_dev      [R, n_samples, C] float32, recording r starts at x_dev + r*rec_stride (elements)
+ *   warm_n     samples of warm-up (init_minmax_tracker, detection.py:70,827-840); 0 = none
+ *   rel_dev    NULL (onsets only) or [R, n_blocks*B, C] float32, recording stride rel_stride
+ *   on_channel_dev, on_sample_dev  [R, cap] int32: onsets of recording r in the reference's
+ *              order (block-major, channel ascending); on_count_dev [R] int32 is the number
+ *              found (may exceed cap; only the first cap are stored)
+ * R must equal the detector's n_streams.  State is carried in `det` (continue with another
+ * call or with ofp_detect_block). */
+int ofp_detect_offline(ofp_detector *det, const float *x_dev, int64_t n_samples, int64_t rec_stride,
+                       int64_t warm_n, float *rel_dev, int64_t rel_stride, int32_t *on_channel_dev,
+                       int32_t *on_sample_dev, int32_t *on_count_dev, int32_t cap, void *stream);
+
+/* AmplitudeOnsetDetector.__call__ (detection.py:727-798) for n_streams concurrent streams:
+ *   x_dev [S, B, C]; rel_dev NULL or [S, B, C]; ch_dev/delta_dev [S, C] int32; count_dev [S]. */
+int ofp_detect_block(ofp_detector *det, const float *x_dev, float *rel_dev, int32_t *ch_dev,
+                     int32_t *delta_dev, int32_t *count_dev, void *stream);
+
+/* AmplitudeOnsetDetector.init_minmax_tracker (detection.py:827-840): x_dev [S, n, C]. */
+int ofp_detect_warmup(ofp_detector *det, const float *x_dev, int64_t n_samples, int64_t rec_stride,
+                      void *stream);
+
+/* Host-buffer convenience (the reference-facing call: numpy in, numpy out).  Copies
+ * x_host -> device, runs ofp_detect_offline on a fresh detector, copies results back and
+ * synchronises.  rel_host may be NULL. */
+int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, int64_t n_rec,
+                            int64_t n_samples, int64_t warm_n, float *rel_host, int32_t *on_channel_host,
+                            int32_t *on_sample_host, int32_t *on_count_host, int32_t cap);
+
+/* Signature twins of the ctypes DLL (envelope_follower.c:6,27), device pointers.
+ *   ar_envelope:  x,y [num_samples, size]; y's last row is the carried state on entry.
+ *   minmax_envelope: x [n_samples, n_channels]; min/max [n_channels] in/out. */
+int ofp_ar_envelope(const float *x_dev, float *y_dev, float attack, float release, int size,
+                    int num_samples, void *stream);
+int ofp_minmax_envelope(const float *x_dev, float *min_dev, float *max_dev, float alpha_min,
+                        float alpha_max, float minmin, int n_samples, int n_channels, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Benchmark input: seeded synthetic multi-mic drum audio generated on the device
+ * (SURVEY.md section 8d signal model; not a reference function).  x_dev [R, N, C] float32;
+ * sensors_xyz_host [C, 3] cm (host); rec_offset = global index of recording 0 of this shard.
+ * ------------------------------------------------------------------------------------- */
+int ofp_synth_drum(float *x_dev, int64_t n_rec, int64_t n_samples, int32_t n_channels,
+                   const float *sensors_xyz_host, float c_cm_s, float sr, float noise, float radius_cm,
+                   int64_t first_hit, int64_t hit_period, uint64_t seed, int64_t rec_offset, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFP_H */

@@ -1,0 +1,574 @@
+// K1: batched multi-channel amplitude onset detector (sm_100a).
+//
+// Replaces AmplitudeOnsetDetector.__call__/init_minmax_tracker and detect_onsets_amplitude
+// (reference detection.py:19-86, 595-840) together with the three ctypes calls per block into
+// envelope_follower.so (envelope_follower.c:6-57) and scipy.signal.lfilter (detection.py:499-501).
+//
+// Design (DESIGN.md "K1"):
+//   * time is sequential per channel (non-linear recurrences), so parallelism = channel lanes.
+//     One lane per (recording, channel); a warp owns G = floor(32/C) whole recordings because the
+//     off-threshold logic couples the channels of a recording -> warp shuffles only.
+//   * one warp per CTA: 10k recordings x 3 ch = 1000 warps = 6.8 per SM; single-warp CTAs spread
+//     them 6/7 per SM instead of 4/8.
+//   * input [R, N, C] is staged by TMA: a 2-D tensor map over (N*C, R) with box (T*C, G) brings the
+//     next T samples of all G recordings of the warp with ONE cp.async.bulk.tensor per tile into a
+//     warp-private mbarrier ring.  T is chosen so that the row pitch T*C is 4 (mod 32) floats:
+//     the per-sample LDS of the 32 lanes is then (almost) bank-conflict free.
+//   * the rel envelope of the current block stays in shared memory: the thresholds of a block
+//     depend on the END-of-block min/max, so crossings are found by a second pass that
+//     only runs when the block maximum exceeded the on-threshold (once per hit).  rel is written to
+//     HBM from that buffer with coalesced 16-byte streaming stores.
+//   * arithmetic follows SURVEY Appendix A op for op: explicit __f*_rn intrinsics (never contracted
+//     to FMA), one double add inside the follower, log10/10**x evaluated in double and rounded once.
+#include "ofp_common.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+struct ofp_detector {
+    ofp_detector_params p;
+    int64_t n_streams;
+    int64_t n_lanes;
+    float *buf;  // 11 arrays of n_lanes 32-bit words
+};
+
+namespace ofp {
+
+struct DetState {
+    float *z0, *z1, *z2, *z3, *yf, *ys, *mn, *mx, *prev;
+    int32_t *state, *deb;
+};
+
+static DetState state_of(const ofp_detector *d) {
+    DetState s;
+    float *b = d->buf;
+    const int64_t n = d->n_lanes;
+    s.z0 = b; s.z1 = b + n; s.z2 = b + 2 * n; s.z3 = b + 3 * n;
+    s.yf = b + 4 * n; s.ys = b + 5 * n; s.mn = b + 6 * n; s.mx = b + 7 * n; s.prev = b + 8 * n;
+    s.state = reinterpret_cast<int32_t *>(b + 9 * n);
+    s.deb = reinterpret_cast<int32_t *>(b + 10 * n);
+    return s;
+}
+
+struct K1Args {
+    ofp_detector_params p;
+    float ia_min, ia_max;  // float(1.0 - (double)alpha), envelope_follower.c:31-32
+    DetState st;
+    const float *x;
+    int64_t n_samples, rec_stride;
+    int64_t warm_n;  // warm-up region [0, warm_n): HP over all of it, envelopes over full blocks
+    int64_t n_main;  // main region [0, n_main), n_main = n_blocks * B
+    float *rel;
+    int64_t rel_stride;
+    int32_t *on_ch, *on_idx, *on_cnt;
+    int32_t cap;
+    int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
+};
+
+// envelope_follower.c:15-22 (gcc: subss, cvtss2sd, addsd, cvtsd2ss, mulss, addss)
+__device__ __forceinline__ float ar_step(float y, float x, float att, float rel) {
+    const float t = __fsub_rn(x, y);
+    const float d = __double2float_rn(__dadd_rn(static_cast<double>(t), 1e-10));
+    const float coef = d > 0.0f ? att : rel;
+    return __fadd_rn(y, __fmul_rn(coef, d));
+}
+
+struct Lane {
+    float z0, z1, z2, z3, yf, ys, mn, mx, prev, bmax, bmin;
+    int32_t state, deb;
+};
+
+template <bool USE_HP>
+__device__ __forceinline__ float front(Lane &L, const K1Args &a, float x) {
+    float h = x;
+    if (USE_HP) {  // scipy lfilter, DF2T, float32, unfused (detection.py:499-501)
+        const float y = __fadd_rn(L.z0, __fmul_rn(a.p.b[0], x));
+        L.z0 = __fsub_rn(__fadd_rn(L.z1, __fmul_rn(x, a.p.b[1])), __fmul_rn(y, a.p.a[1]));
+        L.z1 = __fsub_rn(__fadd_rn(L.z2, __fmul_rn(x, a.p.b[2])), __fmul_rn(y, a.p.a[2]));
+        L.z2 = __fsub_rn(__fadd_rn(L.z3, __fmul_rn(x, a.p.b[3])), __fmul_rn(y, a.p.a[3]));
+        L.z3 = __fsub_rn(__fmul_rn(x, a.p.b[4]), __fmul_rn(y, a.p.a[4]));
+        h = y;
+    }
+    // detection.py:747-748
+    const float v = fabsf(__fadd_rn(h, 1e-10f));
+    const float l = __double2float_rn(log10(static_cast<double>(v)));
+    const float db = fmaxf(__fmul_rn(20.0f, l), a.p.floor_db);
+    // detection.py:751 (envelope_follower.c:6-25 twice)
+    L.yf = ar_step(L.yf, db, a.p.fast_att, a.p.fast_rel);
+    L.ys = ar_step(L.ys, db, a.p.slow_att, a.p.slow_rel);
+    // detection.py:753-754
+    const float q = __fdiv_rn(__fsub_rn(L.yf, L.ys), 20.0f);
+    float amp = __double2float_rn(exp10(static_cast<double>(q)));
+    amp = __fsub_rn(amp, 1e-10f);
+    return fminf(fmaxf(amp, 0.0f), -a.p.floor_db);
+}
+
+// envelope_follower.c:38-52
+__device__ __forceinline__ void minmax_step(Lane &L, const K1Args &a, float r) {
+    const float nm = __fadd_rn(__fmul_rn(L.mn, a.ia_min), __fmul_rn(r, a.p.alpha_min));
+    L.mn = r < a.p.minmin ? a.p.minmin : (r < L.mn ? r : nm);
+    const float nx = __fadd_rn(__fmul_rn(L.mx, a.ia_max), __fmul_rn(r, a.p.alpha_max));
+    L.mx = r > L.mx ? r : nx;
+}
+
+template <bool USE_HP, bool USE_TMA>
+__global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    float *stages = reinterpret_cast<float *>(smem + 128);
+    float *relbuf = stages + static_cast<size_t>(a.nst) * a.stage_floats;
+
+    const int lane = threadIdx.x;
+    const int C = a.p.n_channels, B = a.p.block_size, G = a.G, T = a.T, TC = a.TC;
+    const int g_raw = lane / C;
+    const bool in_group = g_raw < G;
+    const int g = in_group ? g_raw : 0;
+    const int c = in_group ? lane - g_raw * C : 0;
+    const int rec0 = blockIdx.x * G;
+    const int rec = rec0 + g;
+    const bool active = in_group && rec < a.R;
+    const int64_t lid = static_cast<int64_t>(rec) * C + c;
+    const unsigned rec_mask = (C == 32 ? 0xffffffffu : ((1u << C) - 1u)) << (g * C);
+    const unsigned lower_mask = rec_mask & ((1u << lane) - 1u);
+
+    Lane L;
+    if (active) {
+        L.z0 = a.st.z0[lid]; L.z1 = a.st.z1[lid]; L.z2 = a.st.z2[lid]; L.z3 = a.st.z3[lid];
+        L.yf = a.st.yf[lid]; L.ys = a.st.ys[lid]; L.mn = a.st.mn[lid]; L.mx = a.st.mx[lid];
+        L.prev = a.st.prev[lid]; L.state = a.st.state[lid]; L.deb = a.st.deb[lid];
+    } else {
+        L.z0 = L.z1 = L.z2 = L.z3 = 0.f; L.yf = L.ys = a.p.floor_db; L.mn = 0.f; L.mx = 10.f;
+        L.prev = 0.f; L.state = 0; L.deb = 0;
+    }
+    L.bmax = -INFINITY; L.bmin = INFINITY;
+
+    if (USE_TMA) {
+        if (lane == 0) {
+            for (int s = 0; s < a.nst; ++s) mbar_init(&bars[s], 1);
+            fence_mbar_init();
+            tma_prefetch_desc(&tmap);
+        }
+        __syncwarp();
+    }
+    const uint32_t box_bytes = static_cast<uint32_t>(G) * TC * 4u;
+    uint32_t it = 0;      // tiles consumed so far (ring position / parity)
+    int32_t cnt = 0;      // onsets emitted for this lane's recording
+    int64_t blk = 0;      // main-phase block index
+
+    float *rcol = relbuf + g * a.stride_rel + c;  // this lane's column of the block buffer
+
+    for (int phase = 0; phase < 2; ++phase) {
+        const int64_t len = phase == 0 ? a.warm_n : a.n_main;
+        if (len <= 0) continue;
+        const int64_t env_len = phase == 0 ? (len / B) * B : len;
+        const bool do_minmax = phase == 0 || !a.p.manual;
+        const int64_t ntiles = (len + T - 1) / T;
+        int kpos = 0;
+        if (USE_TMA && lane == 0) {
+            for (int p = 0; p < a.nst - 1 && p < ntiles; ++p) {
+                const int s = (it + p) % a.nst;
+                mbar_expect_tx(&bars[s], box_bytes);
+                tma_load_2d(stages + static_cast<size_t>(s) * a.stage_floats, &tmap, &bars[s], p * TC, rec0);
+            }
+        }
+        for (int64_t ti = 0; ti < ntiles; ++ti, ++it) {
+            int s = it % a.nst;
+            const int64_t t0 = ti * T;
+            if (USE_TMA) {
+                const int64_t nx = ti + a.nst - 1;
+                if (lane == 0 && nx < ntiles) {
+                    const int sn = (it + a.nst - 1) % a.nst;
+                    mbar_expect_tx(&bars[sn], box_bytes);
+                    tma_load_2d(stages + static_cast<size_t>(sn) * a.stage_floats, &tmap, &bars[sn],
+                                static_cast<int32_t>(nx * TC), rec0);
+                }
+                mbar_wait(&bars[s], (it / a.nst) & 1u);
+            } else {
+                // generic path (unaligned input): cooperative copy of the tile into stage 0
+                s = 0;
+                const int64_t row_elems = a.n_samples * C;
+                for (int idx = lane; idx < G * TC; idx += 32) {
+                    const int gi = idx / TC, e = idx - gi * TC;
+                    const int64_t col = t0 * C + e;
+                    float v = 0.f;
+                    if (rec0 + gi < a.R && col < row_elems) v = a.x[(rec0 + gi) * a.rec_stride + col];
+                    stages[idx] = v;
+                }
+                __syncwarp();
+            }
+            const float *sp = stages + static_cast<size_t>(s) * a.stage_floats + g * TC + c;
+            const int tl = static_cast<int>(min(static_cast<int64_t>(T), len - t0));
+            int j = 0;
+            while (j < tl) {
+                const int64_t t = t0 + j;
+                if (t < env_len) {
+                    const int seg = min(tl - j, B - kpos);
+                    const float *xp = sp + j * C;
+                    float *rp = rcol + kpos * C;
+#pragma unroll 4
+                    for (int i = 0; i < seg; ++i) {
+                        const float r = front<USE_HP>(L, a, xp[i * C]);
+                        if (do_minmax) minmax_step(L, a, r);
+                        L.bmax = fmaxf(L.bmax, r);
+                        L.bmin = fminf(L.bmin, r);
+                        if (in_group) rp[i * C] = r;
+                    }
+                    j += seg;
+                    kpos += seg;
+                    if (kpos == B) {
+                        kpos = 0;
+                        if (phase == 1) {
+                            // ---- block FSM, detection.py:759-792 ----
+                            const float last = rcol[(B - 1) * C];
+                            const float thr_on = a.p.manual ? a.p.on_thr
+                                                            : __fadd_rn(__fmul_rn(L.mx, a.p.on_thr), L.mn);
+                            const float thr_off = a.p.manual ? a.p.off_thr
+                                                             : __fadd_rn(__fmul_rn(L.mx, a.p.off_thr), L.mn);
+                            int oi = 0;
+                            bool hit = false;
+                            if (!L.state && L.deb < 1 && L.bmax > thr_on) {
+                                float before = L.prev;
+                                for (int k = 0; k < B; ++k) {
+                                    const float r = rcol[k * C];
+                                    if (r > thr_on && before < thr_on) { oi = k; hit = true; break; }
+                                    before = r;
+                                }
+                            }
+                            if (hit) { L.state = 1; L.deb = a.p.cooldown; }
+                            if (L.deb > 0) L.deb -= B;
+                            const unsigned hits = __ballot_sync(0xffffffffu, hit && active);
+                            int M = 0;  // max first-crossing index over the recording's channels (Q3)
+                            if (hits) {
+                                for (int jj = 0; jj < C; ++jj) M = max(M, __shfl_sync(0xffffffffu, oi, g * C + jj));
+                            }
+                            bool off = false;
+                            if (M == 0) off = L.bmin < thr_off;
+                            else {
+                                for (int k = M; k < B; ++k)
+                                    if (rcol[k * C] < thr_off) { off = true; break; }
+                            }
+                            if (off) L.state = 0;
+                            L.prev = last;
+                            if (hits) {
+                                const int pos = cnt + __popc(hits & lower_mask);
+                                if (hit && active && pos < a.cap) {
+                                    a.on_ch[static_cast<int64_t>(rec) * a.cap + pos] = c;
+                                    a.on_idx[static_cast<int64_t>(rec) * a.cap + pos] =
+                                        static_cast<int32_t>(blk * B + oi);
+                                }
+                                cnt += __popc(hits & rec_mask);
+                            }
+                            if (a.rel != nullptr) {
+                                __syncwarp();
+                                const int nBC = B * C;
+                                for (int gi = 0; gi < G; ++gi) {
+                                    if (rec0 + gi >= a.R) break;
+                                    float *dst = a.rel + (rec0 + gi) * a.rel_stride + blk * nBC;
+                                    const float *src = relbuf + gi * a.stride_rel;
+                                    if (a.rel_vec_ok) {
+                                        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                                        float4 *d4 = reinterpret_cast<float4 *>(dst);
+                                        for (int i = lane; i < nBC / 4; i += 32) __stcs(d4 + i, s4[i]);
+                                    } else {
+                                        for (int i = lane; i < nBC; i += 32) __stcs(dst + i, src[i]);
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                            ++blk;
+                        }
+                        L.bmax = -INFINITY; L.bmin = INFINITY;
+                    }
+                } else {
+                    // warm-up tail beyond the last full block: only the high-pass advances
+                    // (detection.py:828-829 filters the whole half second in one call)
+                    const int seg = tl - j;
+                    if (USE_HP) {
+                        const float *xp = sp + j * C;
+                        for (int i = 0; i < seg; ++i) {
+                            const float x = xp[i * C];
+                            const float y = __fadd_rn(L.z0, __fmul_rn(a.p.b[0], x));
+                            L.z0 = __fsub_rn(__fadd_rn(L.z1, __fmul_rn(x, a.p.b[1])), __fmul_rn(y, a.p.a[1]));
+                            L.z1 = __fsub_rn(__fadd_rn(L.z2, __fmul_rn(x, a.p.b[2])), __fmul_rn(y, a.p.a[2]));
+                            L.z2 = __fsub_rn(__fadd_rn(L.z3, __fmul_rn(x, a.p.b[3])), __fmul_rn(y, a.p.a[3]));
+                            L.z3 = __fsub_rn(__fmul_rn(x, a.p.b[4]), __fmul_rn(y, a.p.a[4]));
+                        }
+                    }
+                    j += seg;
+                }
+            }
+            __syncwarp();  // every lane is done with stage s before the producer refills it
+        }
+    }
+
+    if (active) {
+        a.st.z0[lid] = L.z0; a.st.z1[lid] = L.z1; a.st.z2[lid] = L.z2; a.st.z3[lid] = L.z3;
+        a.st.yf[lid] = L.yf; a.st.ys[lid] = L.ys; a.st.mn[lid] = L.mn; a.st.mx[lid] = L.mx;
+        a.st.prev[lid] = L.prev; a.st.state[lid] = L.state; a.st.deb[lid] = L.deb;
+        if (c == 0 && a.on_cnt != nullptr) a.on_cnt[rec] = cnt;
+    }
+}
+
+__global__ void k1_reset(DetState st, int64_t n, float floor_db) {
+    const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    st.z0[i] = st.z1[i] = st.z2[i] = st.z3[i] = 0.f;
+    st.yf[i] = st.ys[i] = floor_db;  // detection.py:697-702
+    st.mn[i] = 0.f; st.mx[i] = 10.f; // detection.py:703-708
+    st.prev[i] = 0.f; st.state[i] = 0; st.deb[i] = 0;  // detection.py:710-712
+}
+
+// Twins of the DLL entry points, one thread per channel (envelope_follower.c:6-57).
+__global__ void k_ar_envelope(const float *x, float *y, float att, float rel, int size, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    float yi = y[static_cast<int64_t>(n - 1) * size + i];
+    for (int j = 0; j < n; ++j) {
+        yi = ar_step(yi, x[static_cast<int64_t>(j) * size + i], att, rel);
+        y[static_cast<int64_t>(j) * size + i] = yi;
+    }
+}
+
+__global__ void k_minmax_envelope(const float *x, float *mnp, float *mxp, float a_min, float a_max,
+                                  float ia_min, float ia_max, float minmin, int n, int nch) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nch) return;
+    float mn = mnp[c], mx = mxp[c];
+    for (int i = 0; i < n; ++i) {
+        const float r = x[static_cast<int64_t>(i) * nch + c];
+        const float nm = __fadd_rn(__fmul_rn(mn, ia_min), __fmul_rn(r, a_min));
+        mn = r < minmin ? minmin : (r < mn ? r : nm);
+        const float nx = __fadd_rn(__fmul_rn(mx, ia_max), __fmul_rn(r, a_max));
+        mx = r > mx ? r : nx;
+    }
+    mnp[c] = mn; mxp[c] = mx;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// Tile length: T*C floats per recording row must be a multiple of 4 (16-byte TMA rows), at most 256
+// (TMA box limit) and, if possible, == roundup4(C) (mod 32) so that the G rows of a stage start in
+// distinct shared-memory banks.
+static int pick_tile(int C) {
+    const int forced = env_int("OFP_K1_TILE", 0);
+    if (forced > 0 && (forced * C) % 4 == 0 && forced * C <= 256) return forced;
+    const int want = ((C + 3) / 4 * 4) % 32;
+    const int tmax = std::min(64, 256 / C);
+    int best = 0;
+    for (int t = tmax; t >= 4; --t)
+        if ((t * C) % 4 == 0 && (t * C) % 32 == want) { best = t; break; }
+    if (!best)
+        for (int t = tmax; t >= 1; --t)
+            if ((t * C) % 4 == 0) { best = t; break; }
+    return best;
+}
+
+static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64_t rec_stride, int64_t warm_n,
+                     int64_t n_main, float *rel, int64_t rel_stride, int32_t *on_ch, int32_t *on_idx,
+                     int32_t *on_cnt, int32_t cap, cudaStream_t stream) {
+    const ofp_detector_params &p = det->p;
+    const int C = p.n_channels, B = p.block_size;
+    K1Args a;
+    memset(&a, 0, sizeof a);
+    a.p = p;
+    a.ia_min = static_cast<float>(1.0 - static_cast<double>(p.alpha_min));
+    a.ia_max = static_cast<float>(1.0 - static_cast<double>(p.alpha_max));
+    a.st = state_of(det);
+    a.x = x; a.n_samples = n_samples; a.rec_stride = rec_stride;
+    a.warm_n = std::min(warm_n, n_samples);
+    a.n_main = n_main;
+    a.rel = rel; a.rel_stride = rel_stride;
+    a.on_ch = on_ch; a.on_idx = on_idx; a.on_cnt = on_cnt; a.cap = cap;
+    a.R = static_cast<int32_t>(det->n_streams);
+    a.G = 32 / C;
+    a.T = pick_tile(C);
+    OFP_REQUIRE(a.T > 0, "no valid tile length for %d channels", C);
+    a.TC = a.T * C;
+    a.nst = std::max(2, std::min(8, env_int("OFP_K1_STAGES", 2)));
+    const int stage_bytes = (a.G * a.TC * 4 + 127) / 128 * 128;
+    a.stage_floats = stage_bytes / 4;
+    const int want = ((C + 3) / 4 * 4) % 32;
+    const int bc4 = (B * C + 3) / 4 * 4;
+    a.stride_rel = bc4 + ((want - bc4 % 32) + 32) % 32;
+    a.rel_vec_ok = rel != nullptr && (reinterpret_cast<uintptr_t>(rel) % 16 == 0) && (rel_stride % 4 == 0) &&
+                   ((B * C) % 4 == 0);
+    const size_t smem = 128 + static_cast<size_t>(a.nst) * stage_bytes + static_cast<size_t>(a.G) * a.stride_rel * 4;
+    OFP_REQUIRE(smem <= 227 * 1024, "block_size %d x %d channels needs %zu bytes of shared memory per warp (max 232448)",
+                B, C, smem);
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (a.R == 1 || rec_stride % 4 == 0) &&
+                        (n_samples * C < (1ll << 31)) && !env_int("OFP_K1_NO_TMA", 0);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (tma_ok) {
+        const uint64_t stride1 = a.R == 1 ? static_cast<uint64_t>((n_samples * C * 4 + 15) / 16 * 16)
+                                          : static_cast<uint64_t>(rec_stride) * 4;
+        int rc = encode_tmap_2d_f32(&tmap, x, static_cast<uint64_t>(n_samples) * C, static_cast<uint64_t>(a.R),
+                                    stride1, static_cast<uint32_t>(a.TC), static_cast<uint32_t>(a.G));
+        if (rc != OFP_OK) return rc;
+    }
+    const int grid = (a.R + a.G - 1) / a.G;
+    auto kern = p.use_hp ? (tma_ok ? k1_detect<true, true> : k1_detect<true, false>)
+                         : (tma_ok ? k1_detect<false, true> : k1_detect<false, false>);
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, 32, smem, stream>>>(tmap, a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+}  // namespace ofp
+
+using namespace ofp;
+
+extern "C" {
+
+int ofp_detector_create(ofp_detector **out, int64_t n_streams, const ofp_detector_params *p) {
+    OFP_REQUIRE(out && p, "null argument");
+    OFP_REQUIRE(n_streams > 0 && n_streams < (1ll << 31), "n_streams out of range");
+    OFP_REQUIRE(p->n_channels >= 1 && p->n_channels <= 32, "n_channels must be in 1..32 (got %d)", p->n_channels);
+    OFP_REQUIRE(p->block_size >= 1, "block_size must be positive");
+    ofp_detector *d = new ofp_detector;
+    d->p = *p;
+    d->n_streams = n_streams;
+    d->n_lanes = n_streams * p->n_channels;
+    d->buf = nullptr;
+    cudaError_t e = cudaMalloc(&d->buf, sizeof(float) * 11 * d->n_lanes);
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc detector state: %s", cudaGetErrorString(e));
+        delete d;
+        return e == cudaErrorMemoryAllocation ? OFP_ENOMEM : OFP_ECUDA;
+    }
+    *out = d;
+    return ofp_detector_reset(d, nullptr);
+}
+
+int ofp_detector_destroy(ofp_detector *det) {
+    if (!det) return OFP_OK;
+    cudaFree(det->buf);
+    delete det;
+    return OFP_OK;
+}
+
+int ofp_detector_reset(ofp_detector *det, void *stream) {
+    OFP_REQUIRE(det, "null detector");
+    const int64_t n = det->n_lanes;
+    k1_reset<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        state_of(det), n, det->p.floor_db);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_detector_get_state(ofp_detector *det, int field, void *buf_dev, void *stream) {
+    OFP_REQUIRE(det && buf_dev && field >= 0 && field <= 10, "bad argument");
+    OFP_CUDA_CHECK(cudaMemcpyAsync(buf_dev, det->buf + static_cast<int64_t>(field) * det->n_lanes,
+                                   sizeof(float) * det->n_lanes, cudaMemcpyDeviceToDevice,
+                                   static_cast<cudaStream_t>(stream)));
+    return OFP_OK;
+}
+
+int ofp_detector_set_state(ofp_detector *det, int field, const void *buf_dev, void *stream) {
+    OFP_REQUIRE(det && buf_dev && field >= 0 && field <= 10, "bad argument");
+    OFP_CUDA_CHECK(cudaMemcpyAsync(det->buf + static_cast<int64_t>(field) * det->n_lanes, buf_dev,
+                                   sizeof(float) * det->n_lanes, cudaMemcpyDeviceToDevice,
+                                   static_cast<cudaStream_t>(stream)));
+    return OFP_OK;
+}
+
+int ofp_detect_offline(ofp_detector *det, const float *x_dev, int64_t n_samples, int64_t rec_stride,
+                       int64_t warm_n, float *rel_dev, int64_t rel_stride, int32_t *on_channel_dev,
+                       int32_t *on_sample_dev, int32_t *on_count_dev, int32_t cap, void *stream) {
+    OFP_REQUIRE(det && x_dev, "null argument");
+    OFP_REQUIRE(n_samples >= 0 && warm_n >= 0 && cap >= 0, "negative size");
+    OFP_REQUIRE(cap == 0 || (on_channel_dev && on_sample_dev), "onset buffers missing");
+    const int64_t nb = n_samples / det->p.block_size;
+    OFP_REQUIRE(nb * det->p.block_size < (1ll << 31), "recording too long for int32 sample indices");
+    return launch_k1(det, x_dev, n_samples, rec_stride, warm_n, nb * det->p.block_size, rel_dev, rel_stride,
+                     on_channel_dev, on_sample_dev, on_count_dev, cap, static_cast<cudaStream_t>(stream));
+}
+
+int ofp_detect_block(ofp_detector *det, const float *x_dev, float *rel_dev, int32_t *ch_dev, int32_t *delta_dev,
+                     int32_t *count_dev, void *stream) {
+    OFP_REQUIRE(det && x_dev && ch_dev && delta_dev && count_dev, "null argument");
+    const int64_t bc = static_cast<int64_t>(det->p.block_size) * det->p.n_channels;
+    return launch_k1(det, x_dev, det->p.block_size, bc, 0, det->p.block_size, rel_dev, bc, ch_dev, delta_dev,
+                     count_dev, det->p.n_channels, static_cast<cudaStream_t>(stream));
+}
+
+int ofp_detect_warmup(ofp_detector *det, const float *x_dev, int64_t n_samples, int64_t rec_stride, void *stream) {
+    OFP_REQUIRE(det && x_dev, "null argument");
+    return launch_k1(det, x_dev, n_samples, rec_stride, n_samples, 0, nullptr, 0, nullptr, nullptr, nullptr, 0,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, int64_t n_rec, int64_t n_samples,
+                            int64_t warm_n, float *rel_host, int32_t *on_channel_host, int32_t *on_sample_host,
+                            int32_t *on_count_host, int32_t cap) {
+    OFP_REQUIRE(p && x_host && on_channel_host && on_sample_host && on_count_host, "null argument");
+    ofp_detector *det = nullptr;
+    int rc = ofp_detector_create(&det, n_rec, p);
+    if (rc != OFP_OK) return rc;
+    const int64_t C = p->n_channels, B = p->block_size;
+    const int64_t in_elems = n_rec * n_samples * C;
+    const int64_t rel_elems = n_rec * (n_samples / B) * B * C;
+    float *x_dev = nullptr, *rel_dev = nullptr;
+    int32_t *och = nullptr, *oix = nullptr, *ocn = nullptr;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(x_dev); cudaFree(rel_dev); cudaFree(och); cudaFree(oix); cudaFree(ocn);
+        if (st) cudaStreamDestroy(st);
+        ofp_detector_destroy(det);
+    };
+#define HOST_CHECK(expr)                                                                  \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            cleanup();                                                                    \
+            return OFP_ECUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+    HOST_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    HOST_CHECK(cudaMalloc(&x_dev, sizeof(float) * std::max<int64_t>(in_elems, 4)));
+    if (rel_host) HOST_CHECK(cudaMalloc(&rel_dev, sizeof(float) * std::max<int64_t>(rel_elems, 4)));
+    HOST_CHECK(cudaMalloc(&och, sizeof(int32_t) * std::max<int64_t>(n_rec * cap, 1)));
+    HOST_CHECK(cudaMalloc(&oix, sizeof(int32_t) * std::max<int64_t>(n_rec * cap, 1)));
+    HOST_CHECK(cudaMalloc(&ocn, sizeof(int32_t) * n_rec));
+    HOST_CHECK(cudaMemcpyAsync(x_dev, x_host, sizeof(float) * in_elems, cudaMemcpyHostToDevice, st));
+    rc = ofp_detect_offline(det, x_dev, n_samples, n_samples * C, warm_n, rel_dev, (n_samples / B) * B * C, och, oix,
+                            ocn, cap, st);
+    if (rc != OFP_OK) { cleanup(); return rc; }
+    if (rel_host)
+        HOST_CHECK(cudaMemcpyAsync(rel_host, rel_dev, sizeof(float) * rel_elems, cudaMemcpyDeviceToHost, st));
+    HOST_CHECK(cudaMemcpyAsync(on_channel_host, och, sizeof(int32_t) * n_rec * cap, cudaMemcpyDeviceToHost, st));
+    HOST_CHECK(cudaMemcpyAsync(on_sample_host, oix, sizeof(int32_t) * n_rec * cap, cudaMemcpyDeviceToHost, st));
+    HOST_CHECK(cudaMemcpyAsync(on_count_host, ocn, sizeof(int32_t) * n_rec, cudaMemcpyDeviceToHost, st));
+    HOST_CHECK(cudaStreamSynchronize(st));
+#undef HOST_CHECK
+    cleanup();
+    return OFP_OK;
+}
+
+int ofp_ar_envelope(const float *x_dev, float *y_dev, float attack, float release, int size, int num_samples,
+                    void *stream) {
+    OFP_REQUIRE(x_dev && y_dev && size > 0 && num_samples > 0, "bad argument");
+    k_ar_envelope<<<(size + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(x_dev, y_dev, attack, release,
+                                                                                      size, num_samples);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_minmax_envelope(const float *x_dev, float *min_dev, float *max_dev, float alpha_min, float alpha_max,
+                        float minmin, int n_samples, int n_channels, void *stream) {
+    OFP_REQUIRE(x_dev && min_dev && max_dev && n_samples >= 0 && n_channels > 0, "bad argument");
+    const float ia_min = static_cast<float>(1.0 - static_cast<double>(alpha_min));
+    const float ia_max = static_cast<float>(1.0 - static_cast<double>(alpha_max));
+    k_minmax_envelope<<<(n_channels + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_dev, min_dev, max_dev, alpha_min, alpha_max, ia_min, ia_max, minmin, n_samples, n_channels);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's ``detection.py`` call surface, running on libofp.so.
+
+Same names, argument meaning and return types as the reference
+(/root/reference/onset_fingerprinting/detection.py) so existing callers can switch imports;
+the arithmetic runs in the CUDA kernels behind include/ofp.h.  Inputs may be numpy arrays
+(copied to the device) or CUDA torch tensors (used in place).  Batched variants
+(``*_batch``) take ``[R, N, C]`` and return device tensors.
+
+There is no CPU fallback (BASELINE.json north_star): without the built library or without
+a CUDA device these raise ``OfpError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import DetectorParams, OfpError, check, ptr, stream_ptr
+
+
+def make_params(n_signals, block_size, floor=-70.0, hipass_freq=2000.0, fast_ar=(3.0, 383.0),
+                slow_ar=(2205.0, 2205.0), on_threshold=0.5, off_threshold=0.1, cooldown=1323,
+                sr=44100) -> DetectorParams:
+    """The host-side conversions of AmplitudeOnsetDetector.__init__ (detection.py:631-712):
+    float32 Butterworth coefficients, float32 reciprocals of attack/release, manual flag."""
+    p = DetectorParams()
+    p.n_channels, p.block_size = int(n_signals), int(block_size)
+    p.use_hp = int(hipass_freq != 0)
+    if p.use_hp:
+        from scipy import signal as sig
+
+        b, a = sig.butter(4, hipass_freq, btype="high", analog=False, output="ba", fs=sr)
+        for i in range(5):
+            p.b[i], p.a[i] = np.float32(b[i]), np.float32(a[i])
+    p.manual = int(on_threshold > 1)
+    p.cooldown = int(cooldown)
+    p.floor_db = floor
+    p.fast_att, p.fast_rel = np.float32(1 / fast_ar[0]), np.float32(1 / fast_ar[1])
+    p.slow_att, p.slow_rel = np.float32(1 / slow_ar[0]), np.float32(1 / slow_ar[1])
+    p.on_thr, p.off_thr = on_threshold, off_threshold
+    p.alpha_min, p.alpha_max, p.minmin = 1e-4, 1e-5, 2.0
+    return p
+
+
+def _to_dev(x, torch, dtype=None):
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.float32:
+            # the reference's ctypes ndpointer rejects anything but float32 (detection.py:520-526)
+            raise TypeError("audio must be float32")
+        return torch.from_numpy(np.ascontiguousarray(x)).cuda(non_blocking=True)
+    if not x.is_cuda:
+        x = x.cuda()
+    if x.dtype != torch.float32:
+        raise TypeError("audio must be float32")
+    return x.contiguous()
+
+
+class BatchedOnsetDetector:
+    """n_streams independent AmplitudeOnsetDetector states on the device (one ``ofp_detector``)."""
+
+    def __init__(self, n_streams: int, n_signals: int, block_size: int = 32, **kw):
+        self.torch = _lib.require_cuda()
+        self.params = make_params(n_signals, block_size, **kw)
+        self.n_streams, self.n_signals, self.block_size = int(n_streams), int(n_signals), int(block_size)
+        self._h = C.c_void_p()
+        check(_lib.lib().ofp_detector_create(C.byref(self._h), C.c_int64(self.n_streams), C.byref(self.params)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().ofp_detector_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def reset(self):
+        check(_lib.lib().ofp_detector_reset(self._h, stream_ptr()))
+
+    STATE_FIELDS = ["z0", "z1", "z2", "z3", "yf", "ys", "min", "max", "prev", "state", "debounce"]
+
+    def state(self) -> dict:
+        """Copy of the per-lane state as numpy arrays of shape [n_streams, n_signals]."""
+        torch = self.torch
+        out = {}
+        for i, name in enumerate(self.STATE_FIELDS):
+            t = torch.empty((self.n_streams, self.n_signals), dtype=torch.float32 if i < 9 else torch.int32,
+                            device="cuda")
+            check(_lib.lib().ofp_detector_get_state(self._h, i, ptr(t), stream_ptr()))
+            out[name] = t.cpu().numpy()
+        return out
+
+    def load_state(self, state: dict):
+        torch = self.torch
+        for i, name in enumerate(self.STATE_FIELDS):
+            t = torch.from_numpy(np.ascontiguousarray(state[name])).cuda()
+            check(_lib.lib().ofp_detector_set_state(self._h, i, ptr(t), stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    def warmup(self, x):
+        """init_minmax_tracker (detection.py:827-840) on x [S, n, C]."""
+        x = _to_dev(x, self.torch)
+        assert x.dim() == 3 and x.shape[0] == self.n_streams and x.shape[2] == self.n_signals
+        check(_lib.lib().ofp_detect_warmup(self._h, ptr(x), C.c_int64(x.shape[1]), C.c_int64(x.stride(0)),
+                                           stream_ptr()))
+
+    def process_block(self, x, return_rel=True):
+        """One [S, B, C] block for every stream -> (channels [S, C], deltas [S, C], counts [S], rel)."""
+        torch = self.torch
+        x = _to_dev(x, torch)
+        S, B, Cn = self.n_streams, self.block_size, self.n_signals
+        assert tuple(x.shape) == (S, B, Cn), f"expected {(S, B, Cn)}, got {tuple(x.shape)}"
+        ch = torch.empty((S, Cn), dtype=torch.int32, device="cuda")
+        dl = torch.empty((S, Cn), dtype=torch.int32, device="cuda")
+        cnt = torch.empty((S,), dtype=torch.int32, device="cuda")
+        rel = torch.empty((S, B, Cn), dtype=torch.float32, device="cuda") if return_rel else None
+        check(_lib.lib().ofp_detect_block(self._h, ptr(x), ptr(rel), ptr(ch), ptr(dl), ptr(cnt), stream_ptr()))
+        return ch, dl, cnt, rel
+
+    def default_cap(self, n_samples: int) -> int:
+        """Upper bound on onsets per recording: one per channel per cooldown (>= one block)."""
+        return int(self.n_signals * (n_samples // max(self.params.cooldown, self.block_size) + 2))
+
+    def detect_offline(self, x, warm_n: int, return_rel=True, cap: Optional[int] = None, out=None):
+        """Warm-up on x[:, :warm_n] then the block loop from sample 0 (detection.py:70-82).
+        Returns (channels [R, cap] int32, samples [R, cap] int32, counts [R] int32, rel [R, nb*B, C] | None).
+        ``out`` may hold preallocated (channels, samples, counts, rel) tensors."""
+        torch = self.torch
+        x = _to_dev(x, torch)
+        R, N, Cn = x.shape
+        assert R == self.n_streams and Cn == self.n_signals
+        B = self.block_size
+        nb = N // B
+        if out is not None:
+            ch, ix, cnt, rel = out
+            cap = ch.shape[1]
+        else:
+            if cap is None:
+                cap = self.default_cap(N)
+            ch = torch.empty((R, cap), dtype=torch.int32, device="cuda")
+            ix = torch.empty((R, cap), dtype=torch.int32, device="cuda")
+            cnt = torch.empty((R,), dtype=torch.int32, device="cuda")
+            rel = torch.empty((R, nb * B, Cn), dtype=torch.float32, device="cuda") if return_rel else None
+        check(_lib.lib().ofp_detect_offline(self._h, ptr(x), C.c_int64(N), C.c_int64(x.stride(0)), C.c_int64(warm_n),
+                                            ptr(rel), C.c_int64(nb * B * Cn), ptr(ch), ptr(ix), ptr(cnt),
+                                            C.c_int32(cap), stream_ptr()))
+        return ch, ix, cnt, rel
+
+
+def detect_onsets_amplitude_batch(x, block_size: int = 128, floor: float = -70.0, hipass_freq: float = 2000.0,
+                                  fast_ar=(3.0, 383.0), slow_ar=(2205.0, 2205.0), on_threshold=0.5,
+                                  off_threshold=0.1, cooldown: int = 1323, sr: int = 96000, return_rel=True,
+                                  cap: Optional[int] = None):
+    """detect_onsets_amplitude (detection.py:19-86) for a batch x [R, N, C] in one launch.
+    Returns device tensors (channels [R, cap], onsets [R, cap], counts [R], rel | None); the first
+    counts[r] entries of row r are recording r's onsets in the reference's order."""
+    torch = _lib.require_cuda()
+    x = _to_dev(x, torch)
+    det = BatchedOnsetDetector(x.shape[0], x.shape[2], block_size, floor=floor, hipass_freq=hipass_freq,
+                               fast_ar=fast_ar, slow_ar=slow_ar, on_threshold=on_threshold,
+                               off_threshold=off_threshold, cooldown=cooldown, sr=sr)
+    return det.detect_offline(x, int(0.5 * sr), return_rel=return_rel, cap=cap)
+
+
+def detect_onsets_amplitude(x: np.ndarray, block_size: int = 128, floor: float = -70.0,
+                            hipass_freq: float = 2000.0, fast_ar=(3.0, 383.0), slow_ar=(2205.0, 2205.0),
+                            on_threshold=0.5, off_threshold=0.1, cooldown: int = 1323, backtrack: bool = False,
+                            backtrack_buffer_size: int = 128, backtrack_smooth_size: int = 5, sr: int = 96000):
+    """Drop-in for detection.detect_onsets_amplitude (detection.py:19-86): x [N, C] float32 ->
+    (channels_flat, onsets_flat, rel[n_blocks*block_size, C])."""
+    if backtrack:
+        raise NotImplementedError("backtrack=True is not on the CUDA path yet")
+    ch, ix, cnt, rel = detect_onsets_amplitude_batch(
+        x[None], block_size, floor, hipass_freq, fast_ar, slow_ar, on_threshold, off_threshold, cooldown, sr, True)
+    k = int(cnt[0].item())
+    if k > ch.shape[1]:
+        raise OfpError(f"onset buffer overflow ({k} > {ch.shape[1]})")
+    return ch[0, :k].cpu().tolist(), ix[0, :k].cpu().tolist(), rel[0].cpu().numpy()
+
+
+def detect_onsets(x: np.ndarray, sr: int = 96000, method="amp"):
+    """detection.py:12-16."""
+    if method == "amp":
+        return detect_onsets_amplitude(x, sr=sr)
+    raise NotImplementedError("spectral method: see spectral.py")
+
+
+class AmplitudeOnsetDetector:
+    """Drop-in for detection.AmplitudeOnsetDetector (detection.py:595-840), one stream.
+
+    ``od(block[B, C]) -> (channels, deltas, relative_envelope)`` with numpy results like the
+    reference.  State lives on the device between calls."""
+
+    def __init__(self, n_signals: int, block_size: int = 32, floor: float = -70.0, hipass_freq: float = 2000.0,
+                 fast_ar=(3.0, 383.0), slow_ar=(2205.0, 2205.0), on_threshold: float = 0.5,
+                 off_threshold: float = 0.1, cooldown: int = 1323, backtrack: bool = False,
+                 backtrack_buffer_size: int = 80, backtrack_smooth_size: int = 5, sr: int = 44100):
+        if backtrack:
+            raise NotImplementedError("backtrack=True is not on the CUDA path yet")
+        self.n_signals, self.block_size = n_signals, block_size
+        self.floor, self.on_threshold, self.off_threshold = floor, on_threshold, off_threshold
+        self.manual = bool(on_threshold > 1)
+        self.cooldown, self.sr = cooldown, sr
+        self._det = BatchedOnsetDetector(1, n_signals, block_size, floor=floor, hipass_freq=hipass_freq,
+                                         fast_ar=fast_ar, slow_ar=slow_ar, on_threshold=on_threshold,
+                                         off_threshold=off_threshold, cooldown=cooldown, sr=sr)
+
+    def __call__(self, x):
+        ch, dl, cnt, rel = self._det.process_block(x[None] if x.ndim == 2 else x)
+        k = int(cnt[0].item())
+        return ch[0, :k].cpu().numpy().astype(np.int64), dl[0, :k].cpu().numpy().astype(np.int64), rel[0].cpu().numpy()
+
+    def init_minmax_tracker(self, x):
+        self._det.warmup(x[None] if x.ndim == 2 else x)
+
+
+class AREnvelopeFollower:
+    """detection.py:504-538 over ofp_ar_envelope (twin of envelope_follower.c:6-25)."""
+
+    def __init__(self, x0: np.ndarray, attack=3, release=383):
+        torch = _lib.require_cuda()
+        self.attack = np.float32(1 / attack)
+        self.release = np.float32(1 / release)
+        self.y = torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float32)).cuda()
+        self.n, self.size = x0.shape
+
+    def __call__(self, x):
+        torch = _lib.require_cuda()
+        xd = _to_dev(x, torch)
+        check(_lib.lib().ofp_ar_envelope(ptr(xd), ptr(self.y), C.c_float(self.attack), C.c_float(self.release),
+                                         C.c_int(self.size), C.c_int(self.n), stream_ptr()))
+        return self.y.cpu().numpy() if isinstance(x, np.ndarray) else self.y
+
+
+class MinMaxEnvelopeFollower:
+    """detection.py:541-592 over ofp_minmax_envelope (twin of envelope_follower.c:27-57)."""
+
+    def __init__(self, x0: np.ndarray, alpha_min=1e-5, alpha_max=1e-5, minmin=0.0):
+        torch = _lib.require_cuda()
+        self.alpha_min, self.alpha_max, self.minmin = np.float32(alpha_min), np.float32(alpha_max), np.float32(minmin)
+        self.min_val = torch.from_numpy(np.float32(np.min(x0, axis=0))).cuda()
+        self.max_val = torch.from_numpy(np.float32(np.max(x0, axis=0))).cuda()
+        self.n_channels = x0.shape[1]
+
+    def __call__(self, x):
+        torch = _lib.require_cuda()
+        xd = _to_dev(x, torch)
+        check(_lib.lib().ofp_minmax_envelope(ptr(xd), ptr(self.min_val), ptr(self.max_val), C.c_float(self.alpha_min),
+                                             C.c_float(self.alpha_max), C.c_float(self.minmin), C.c_int(len(x)),
+                                             C.c_int(self.n_channels), stream_ptr()))
+        if isinstance(x, np.ndarray):
+            return self.min_val.cpu().numpy(), self.max_val.cpu().numpy()
+        return self.min_val, self.max_val
+
+
+def find_onset_groups(onsets, channels, max_distance: int = 1000, min_channels: int = 3,
+                      close_channel: Optional[int] = None):
+    """detection.py:131-189.  Sequential scan over (onset, channel) in detection order; the work is
+    a few thousand integers per recording, so it stays on the host."""
+    if len(onsets) == 0:
+        raise ValueError("max() arg is an empty sequence")  # what the reference raises (line 158)
+    width = max(channels) + 1
+    rows, members = [], []
+
+    def close_group():
+        if len({ch for _, ch in members}) >= min_channels:
+            row = np.full((width,), -1, dtype=int)
+            for s, ch in members:
+                row[ch] = s
+            rows.append(row)
+
+    for s, ch in zip(onsets, channels):
+        if members and abs(s - members[0][0]) > max_distance:
+            close_group()
+            members = []
+        members.append((s, ch))
+    close_group()
+    if close_channel is not None:
+        rows = [r for r in rows if all(r[close_channel] <= r)]
+    return np.array(rows, dtype=int) if rows else None

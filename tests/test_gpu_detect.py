@@ -1,0 +1,150 @@
+"""K1 parity on the GPU: CUDA path (through the C ABI) vs the CPU oracle and the golden vectors
+the unmodified reference produced.  Bars: onset channel/sample lists bit-exact; envelope <= 1e-5
+relative (north_star); additionally the fraction of bit-identical envelope samples vs the oracle
+is reported and required to be > 99.99 % (both round log10/10**x once from double)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from onset_fingerprinting_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def rel_err(a, b):
+    return float((np.abs(a - b) / np.maximum(np.abs(b), 1e-6)).max())
+
+
+@pytest.fixture(scope="module")
+def det():
+    from onset_fingerprinting_b200 import detection
+
+    return detection
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+
+    return oracle
+
+
+@pytest.mark.parametrize("name", ["default3", "realtime3", "manual_b100", "b256_partial", "mesh16"])
+def test_offline_vs_golden_and_oracle(name, det, orc, golden_dir):
+    from oracle.make_golden import DETECT_CASES
+
+    g = np.load(golden_dir / f"detect_{name}.npz")
+    skw, dkw = DETECT_CASES[name]
+    x, _ = synth.drum_recording(**skw)
+    assert sha(x) == str(g["x_sha"])
+    ch, on, rel = det.detect_onsets_amplitude(x, sr=96000, **dkw)
+    # reference (golden)
+    assert ch == g["channels"].tolist()
+    assert on == g["onsets"].tolist()
+    assert rel.shape == tuple(g["rel_shape"])
+    assert rel_err(rel[::16], g["rel_sub"]) <= 1e-5
+    # oracle, full resolution
+    ch_o, on_o, rel_o = orc.detect_onsets_amplitude(x, sr=96000, **dkw)
+    assert ch == ch_o and on == on_o
+    assert rel_err(rel, rel_o) <= 1e-5
+    assert float((rel == rel_o).mean()) > 0.9999
+
+
+def test_streaming_blocks_vs_golden(det, golden_dir):
+    g = np.load(golden_dir / "stream_realtime.npz")
+    x, _ = synth.drum_recording(seconds=1.5, seed=7, first_hit=20000)
+    od = det.AmplitudeOnsetDetector(3, 128, hipass_freq=0, fast_ar=(0.3, 800), slow_ar=(8000, 8000),
+                                    on_threshold=0.45, off_threshold=0.45, cooldown=1323, sr=96000)
+    got, rels = [], []
+    for b, i in enumerate(range(0, len(x) - 127, 128)):
+        c, d, r = od(x[i:i + 128])
+        if b % 8 == 0:
+            rels.append(r[::16])
+        got += [(b, int(cc), int(dd)) for cc, dd in zip(c, d)]
+    assert got == list(zip(g["blocks"].tolist(), g["channels"].tolist(), g["deltas"].tolist()))
+    assert rel_err(np.asarray(rels), g["rel_sub"]) <= 1e-5
+
+
+def test_batch_matches_per_recording_oracle(det, orc):
+    """[R, N, C] batch in one launch == R independent oracle runs (ragged tail warp: R=13 -> 2 warps)."""
+    xs, _ = synth.drum_batch(13, seconds=1.2, seed=100)
+    ch, ix, cnt, rel = det.detect_onsets_amplitude_batch(xs, sr=96000)
+    ch, ix, cnt, rel = ch.cpu().numpy(), ix.cpu().numpy(), cnt.cpu().numpy(), rel.cpu().numpy()
+    for r in range(len(xs)):
+        c_o, o_o, rel_o = orc.detect_onsets_amplitude(xs[r], sr=96000)
+        k = cnt[r]
+        assert ch[r, :k].tolist() == c_o and ix[r, :k].tolist() == o_o
+        assert rel_err(rel[r], rel_o) <= 1e-5
+
+
+def test_onsets_only_mode_and_state_carry(det, orc):
+    """rel_dev = NULL gives the same onsets; two half-length calls == one call (state in the handle)."""
+    x, _ = synth.drum_recording(seconds=2.0, seed=9)
+    n = (len(x) // 256) * 256
+    x = x[:n]
+    d1 = det.BatchedOnsetDetector(1, 3, 128, sr=96000)
+    ch, ix, cnt, _ = d1.detect_offline(x[None], warm_n=48000, return_rel=False)
+    c_o, o_o, _ = orc.detect_onsets_amplitude(x, sr=96000)
+    k = int(cnt[0])
+    assert ch[0, :k].tolist() == c_o and ix[0, :k].tolist() == o_o
+    d2 = det.BatchedOnsetDetector(1, 3, 128, sr=96000)
+    h = n // 2
+    a = d2.detect_offline(x[None, :h], warm_n=48000, return_rel=False)
+    b = d2.detect_offline(x[None, h:], warm_n=0, return_rel=False)
+    ka, kb = int(a[2][0]), int(b[2][0])
+    joined = a[1][0, :ka].tolist() + [v + h for v in b[1][0, :kb].tolist()]
+    assert joined == o_o
+
+
+def test_unaligned_input_uses_generic_loader(det, orc):
+    """A view whose base is not 16-byte aligned cannot use TMA; results must not change."""
+    x, _ = synth.drum_recording(seconds=1.0, seed=12)
+    buf = torch.empty(x.size + 1, dtype=torch.float32, device="cuda")
+    view = buf[1:].view(1, *x.shape)
+    view.copy_(torch.from_numpy(x))
+    assert view.data_ptr() % 16 != 0
+    d = det.BatchedOnsetDetector(1, 3, 128, sr=96000)
+    ch, ix, cnt, rel = d.detect_offline(view, warm_n=48000)
+    c_o, o_o, rel_o = orc.detect_onsets_amplitude(x, sr=96000)
+    k = int(cnt[0])
+    assert ch[0, :k].tolist() == c_o and ix[0, :k].tolist() == o_o
+    assert rel_err(rel[0].cpu().numpy(), rel_o) <= 1e-5
+
+
+def test_dll_twins(det, golden_dir):
+    g = np.load(golden_dir / "kernels.npz")
+    ar = det.AREnvelopeFollower(np.full((64, 5), -70, np.float32), 3, 383)
+    for xb, ref in zip(g["ar_in"], g["ar_out"]):
+        assert np.array_equal(ar(np.ascontiguousarray(xb)), ref)
+    mm = det.MinMaxEnvelopeFollower(np.array([[0, 10]] * 5).T, alpha_min=1e-4, alpha_max=1e-5, minmin=2)
+    for xb, ref in zip(g["mm_in"], g["mm_out"]):
+        mn, mx = mm(np.ascontiguousarray(xb))
+        assert np.array_equal(mn, ref[0]) and np.array_equal(mx, ref[1])
+
+
+def test_host_buffer_entry_point(det, orc):
+    import ctypes as C
+
+    from onset_fingerprinting_b200 import _lib
+
+    xs, _ = synth.drum_batch(3, seconds=1.0, seed=40)
+    p = det.make_params(3, 128, sr=96000)
+    R, N, Cn = xs.shape
+    cap = 64
+    rel = np.empty((R, (N // 128) * 128, Cn), np.float32)
+    ch = np.empty((R, cap), np.int32); ix = np.empty((R, cap), np.int32); cnt = np.empty(R, np.int32)
+    _lib.check(_lib.lib().ofp_detect_offline_host(
+        C.byref(p), xs.ctypes.data_as(C.c_void_p), C.c_int64(R), C.c_int64(N), C.c_int64(48000),
+        rel.ctypes.data_as(C.c_void_p), ch.ctypes.data_as(C.c_void_p), ix.ctypes.data_as(C.c_void_p),
+        cnt.ctypes.data_as(C.c_void_p), C.c_int32(cap)))
+    for r in range(R):
+        c_o, o_o, rel_o = orc.detect_onsets_amplitude(xs[r], sr=96000)
+        assert ch[r, :cnt[r]].tolist() == c_o and ix[r, :cnt[r]].tolist() == o_o
+        assert rel_err(rel[r], rel_o) <= 1e-5
