@@ -21,6 +21,7 @@
 //   * arithmetic follows SURVEY Appendix A op for op: explicit __f*_rn intrinsics (never contracted
 //     to FMA), one double add inside the follower, log10/10**x evaluated in double and rounded once.
 #include "ofp_common.cuh"
+#include "k1_math.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -34,6 +35,9 @@ struct ofp_detector {
 };
 
 namespace ofp {
+
+// shared memory header: 128 B of mbarriers, then the log10 / 10**x tables
+constexpr int K1_SMEM_HEADER = 128 + (2 << OFP_LOG_N) * 8 + 32 * 8;
 
 struct DetState {
     float *z0, *z1, *z2, *z3, *yf, *ys, *mn, *mx, *prev;
@@ -66,10 +70,23 @@ struct K1Args {
     int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
 };
 
-// envelope_follower.c:15-22 (gcc: subss, cvtss2sd, addsd, cvtsd2ss, mulss, addss)
+// Rare paths (special inputs, results too close to a float32 rounding boundary): full-precision
+// libdevice routines, kept out of line so that the hot loop stays small in the instruction cache.
+__device__ __noinline__ double slow_log10(float v) { return log10(static_cast<double>(v)); }
+__device__ __noinline__ double slow_exp10(float q) { return exp10(static_cast<double>(q)); }
+__device__ __noinline__ float slow_ar_delta(float t) {
+    return __double2float_rn(__dadd_rn(static_cast<double>(t), 1e-10));
+}
+
+// envelope_follower.c:15-22 (gcc: subss, cvtss2sd, addsd, cvtsd2ss, mulss, addss).
+// d = float(double(t) + 1e-10) equals the float32 sum t + 1e-10f whenever t == 0 or |t| >= 2^-26
+// (verified over 2.7e8 random t, DESIGN.md "K1 arithmetic"); the double path is kept for the
+// remaining sliver (|t| < 2^-22), which needs the signal within 3e-8 dB of the envelope.
 __device__ __forceinline__ float ar_step(float y, float x, float att, float rel) {
     const float t = __fsub_rn(x, y);
-    const float d = __double2float_rn(__dadd_rn(static_cast<double>(t), 1e-10));
+    float d = __fadd_rn(t, 1e-10f);
+    if (__builtin_expect(fabsf(t) < 0x1p-22f && t != 0.0f, 0))
+        d = slow_ar_delta(t);
     const float coef = d > 0.0f ? att : rel;
     return __fadd_rn(y, __fmul_rn(coef, d));
 }
@@ -79,29 +96,46 @@ struct Lane {
     int32_t state, deb;
 };
 
-template <bool USE_HP>
-__device__ __forceinline__ float front(Lane &L, const K1Args &a, float x) {
-    float h = x;
-    if (USE_HP) {  // scipy lfilter, DF2T, float32, unfused (detection.py:499-501)
-        const float y = __fadd_rn(L.z0, __fmul_rn(a.p.b[0], x));
-        L.z0 = __fsub_rn(__fadd_rn(L.z1, __fmul_rn(x, a.p.b[1])), __fmul_rn(y, a.p.a[1]));
-        L.z1 = __fsub_rn(__fadd_rn(L.z2, __fmul_rn(x, a.p.b[2])), __fmul_rn(y, a.p.a[2]));
-        L.z2 = __fsub_rn(__fadd_rn(L.z3, __fmul_rn(x, a.p.b[3])), __fmul_rn(y, a.p.a[3]));
-        L.z3 = __fsub_rn(__fmul_rn(x, a.p.b[4]), __fmul_rn(y, a.p.a[4]));
-        h = y;
-    }
-    // detection.py:747-748
+// scipy lfilter, DF2T, float32, unfused (detection.py:499-501)
+__device__ __forceinline__ float hp_step(Lane &L, const K1Args &a, float x) {
+    const float y = __fadd_rn(L.z0, __fmul_rn(a.p.b[0], x));
+    L.z0 = __fsub_rn(__fadd_rn(L.z1, __fmul_rn(x, a.p.b[1])), __fmul_rn(y, a.p.a[1]));
+    L.z1 = __fsub_rn(__fadd_rn(L.z2, __fmul_rn(x, a.p.b[2])), __fmul_rn(y, a.p.a[2]));
+    L.z2 = __fsub_rn(__fadd_rn(L.z3, __fmul_rn(x, a.p.b[3])), __fmul_rn(y, a.p.a[3]));
+    L.z3 = __fsub_rn(__fmul_rn(x, a.p.b[4]), __fmul_rn(y, a.p.a[4]));
+    return y;
+}
+
+// detection.py:747-748: clip(20*log10(|h + 1e-10|), floor) in float32; log10 correctly rounded.
+// Returns the fast-path value; `redo` is set when the value must be recomputed by slow_log10
+// (special input, or the double result is too close to a float32 rounding boundary).
+__device__ __forceinline__ float db_of(double ld, float floor_db) {
+    return fmaxf(__fmul_rn(20.0f, __double2float_rn(ld)), floor_db);
+}
+__device__ __forceinline__ float to_db_fast(float h, float floor_db, const double *logtab, const MathConst &mc,
+                                            float &v_out, bool &redo) {
     const float v = fabsf(__fadd_rn(h, 1e-10f));
-    const float l = __double2float_rn(log10(static_cast<double>(v)));
-    const float db = fmaxf(__fmul_rn(20.0f, l), a.p.floor_db);
-    // detection.py:751 (envelope_follower.c:6-25 twice)
-    L.yf = ar_step(L.yf, db, a.p.fast_att, a.p.fast_rel);
-    L.ys = ar_step(L.ys, db, a.p.slow_att, a.p.slow_rel);
-    // detection.py:753-754
-    const float q = __fdiv_rn(__fsub_rn(L.yf, L.ys), 20.0f);
-    float amp = __double2float_rn(exp10(static_cast<double>(q)));
-    amp = __fsub_rn(amp, 1e-10f);
-    return fminf(fmaxf(amp, 0.0f), -a.p.floor_db);
+    const uint32_t ix = __float_as_uint(v);
+    const double ld = log10_core(ix, logtab, mc);
+    redo = ((ix - 0x00800000u) >= 0x7f000000u) | near_f32_midpoint(ld, 1u << 13);
+    v_out = v;
+    return db_of(ld, floor_db);
+}
+
+// detection.py:753-754: clip(10**(r/20) - 1e-10, 0, -floor) in float32; 10**x correctly rounded.
+__device__ __forceinline__ float amp_of(double ad, float floor_db) {
+    const float amp = __fsub_rn(__double2float_rn(ad), 1e-10f);
+    return fminf(fmaxf(amp, 0.0f), -floor_db);
+}
+__device__ __forceinline__ float to_amp_fast(float r, float floor_db, const double *exptab, const MathConst &mc,
+                                             float &q_out, bool &redo) {
+    // r / 20 correctly rounded without a division (exact: host harness over 4e8 values)
+    const float q0 = __fmul_rn(r, 0.05f);
+    const float q = __fmaf_rn(__fmaf_rn(-20.0f, q0, r), 0.05f, q0);
+    const double ad = exp10_core(q, exptab, mc);
+    redo = !(fabsf(q) < 30.0f) | near_f32_midpoint(ad, 1u << 8);
+    q_out = q;
+    return amp_of(ad, floor_db);
 }
 
 // envelope_follower.c:38-52
@@ -112,11 +146,68 @@ __device__ __forceinline__ void minmax_step(Lane &L, const K1Args &a, float r) {
     L.mx = r > L.mx ? r : nx;
 }
 
+// U consecutive samples of one lane, stage by stage so that the pointwise stages (dB, 10**x) of the
+// U samples are independent instruction streams between the short sequential recurrences.  The rare
+// slow paths are taken after a warp vote, outside the straight-line code.
+template <bool USE_HP, int U>
+__device__ __forceinline__ void chunk(Lane &L, const K1Args &a, const float *xp, float *rp, int C, bool do_minmax,
+                                      bool store, const double *logtab, const double *exptab, const MathConst &mc) {
+    float h[U], db[U], dr[U], amp[U], aux[U];
+    bool redo[U], any = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float x = xp[u * C];
+        h[u] = USE_HP ? hp_step(L, a, x) : x;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        db[u] = to_db_fast(h[u], a.p.floor_db, logtab, mc, aux[u], redo[u]);
+        any |= redo[u];
+    }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (redo[u]) db[u] = db_of(slow_log10(aux[u]), a.p.floor_db);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {  // detection.py:751 (envelope_follower.c:6-25 twice)
+        L.yf = ar_step(L.yf, db[u], a.p.fast_att, a.p.fast_rel);
+        L.ys = ar_step(L.ys, db[u], a.p.slow_att, a.p.slow_rel);
+        dr[u] = __fsub_rn(L.yf, L.ys);
+    }
+    any = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        amp[u] = to_amp_fast(dr[u], a.p.floor_db, exptab, mc, aux[u], redo[u]);
+        any |= redo[u];
+    }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (redo[u]) {
+                const float q = fabsf(aux[u]) < 30.0f ? aux[u] : __fdiv_rn(dr[u], 20.0f);
+                amp[u] = amp_of(slow_exp10(q), a.p.floor_db);
+            }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (do_minmax) minmax_step(L, a, amp[u]);
+        L.bmax = fmaxf(L.bmax, amp[u]);
+        L.bmin = fminf(L.bmin, amp[u]);
+        if (store) rp[u * C] = amp[u];
+    }
+}
+
+__device__ double g_logtab[2 << OFP_LOG_N];
+__device__ double g_exptab[32];
+
 template <bool USE_HP, bool USE_TMA>
 __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    float *stages = reinterpret_cast<float *>(smem + 128);
+    double *logtab = reinterpret_cast<double *>(smem + 128);
+    double *exptab = logtab + (2 << OFP_LOG_N);
+    float *stages = reinterpret_cast<float *>(smem + K1_SMEM_HEADER);
     float *relbuf = stages + static_cast<size_t>(a.nst) * a.stage_floats;
 
     const int lane = threadIdx.x;
@@ -132,6 +223,12 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
     const unsigned rec_mask = (C == 32 ? 0xffffffffu : ((1u << C) - 1u)) << (g * C);
     const unsigned lower_mask = rec_mask & ((1u << lane) - 1u);
 
+    MathConst mc = math_const();
+    {   // keep the constants in registers (opaque moves defeat re-materialisation as immediates)
+        double *m = reinterpret_cast<double *>(&mc);
+#pragma unroll
+        for (int i = 0; i < static_cast<int>(sizeof(MathConst) / 8); ++i) asm volatile("" : "+d"(m[i]));
+    }
     Lane L;
     if (active) {
         L.z0 = a.st.z0[lid]; L.z1 = a.st.z1[lid]; L.z2 = a.st.z2[lid]; L.z3 = a.st.z3[lid];
@@ -143,6 +240,9 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
     }
     L.bmax = -INFINITY; L.bmin = INFINITY;
 
+    for (int i = lane; i < (2 << OFP_LOG_N); i += 32) logtab[i] = g_logtab[i];
+    exptab[lane] = g_exptab[lane];
+    __syncwarp();
     if (USE_TMA) {
         if (lane == 0) {
             for (int s = 0; s < a.nst; ++s) mbar_init(&bars[s], 1);
@@ -206,14 +306,11 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
                     const int seg = min(tl - j, B - kpos);
                     const float *xp = sp + j * C;
                     float *rp = rcol + kpos * C;
-#pragma unroll 4
-                    for (int i = 0; i < seg; ++i) {
-                        const float r = front<USE_HP>(L, a, xp[i * C]);
-                        if (do_minmax) minmax_step(L, a, r);
-                        L.bmax = fmaxf(L.bmax, r);
-                        L.bmin = fminf(L.bmin, r);
-                        if (in_group) rp[i * C] = r;
-                    }
+                    int i = 0;
+                    for (; i + 4 <= seg; i += 4)
+                        chunk<USE_HP, 4>(L, a, xp + i * C, rp + i * C, C, do_minmax, in_group, logtab, exptab, mc);
+                    for (; i < seg; ++i)
+                        chunk<USE_HP, 1>(L, a, xp + i * C, rp + i * C, C, do_minmax, in_group, logtab, exptab, mc);
                     j += seg;
                     kpos += seg;
                     if (kpos == B) {
@@ -286,14 +383,7 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
                     const int seg = tl - j;
                     if (USE_HP) {
                         const float *xp = sp + j * C;
-                        for (int i = 0; i < seg; ++i) {
-                            const float x = xp[i * C];
-                            const float y = __fadd_rn(L.z0, __fmul_rn(a.p.b[0], x));
-                            L.z0 = __fsub_rn(__fadd_rn(L.z1, __fmul_rn(x, a.p.b[1])), __fmul_rn(y, a.p.a[1]));
-                            L.z1 = __fsub_rn(__fadd_rn(L.z2, __fmul_rn(x, a.p.b[2])), __fmul_rn(y, a.p.a[2]));
-                            L.z2 = __fsub_rn(__fadd_rn(L.z3, __fmul_rn(x, a.p.b[3])), __fmul_rn(y, a.p.a[3]));
-                            L.z3 = __fsub_rn(__fmul_rn(x, a.p.b[4]), __fmul_rn(y, a.p.a[4]));
-                        }
+                        for (int i = 0; i < seg; ++i) hp_step(L, a, xp[i * C]);
                     }
                     j += seg;
                 }
@@ -367,6 +457,15 @@ static int pick_tile(int C) {
     return best;
 }
 
+static int upload_tables() {
+    static bool done = false;
+    if (done) return OFP_OK;
+    OFP_CUDA_CHECK(cudaMemcpyToSymbol(g_logtab, OFP_LOGTAB_H, sizeof(OFP_LOGTAB_H)));
+    OFP_CUDA_CHECK(cudaMemcpyToSymbol(g_exptab, OFP_EXPTAB_H, sizeof(OFP_EXPTAB_H)));
+    done = true;
+    return OFP_OK;
+}
+
 static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64_t rec_stride, int64_t warm_n,
                      int64_t n_main, float *rel, int64_t rel_stride, int32_t *on_ch, int32_t *on_idx,
                      int32_t *on_cnt, int32_t cap, cudaStream_t stream) {
@@ -396,7 +495,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.stride_rel = bc4 + ((want - bc4 % 32) + 32) % 32;
     a.rel_vec_ok = rel != nullptr && (reinterpret_cast<uintptr_t>(rel) % 16 == 0) && (rel_stride % 4 == 0) &&
                    ((B * C) % 4 == 0);
-    const size_t smem = 128 + static_cast<size_t>(a.nst) * stage_bytes + static_cast<size_t>(a.G) * a.stride_rel * 4;
+    const size_t smem = K1_SMEM_HEADER + static_cast<size_t>(a.nst) * stage_bytes + static_cast<size_t>(a.G) * a.stride_rel * 4;
     OFP_REQUIRE(smem <= 227 * 1024, "block_size %d x %d channels needs %zu bytes of shared memory per warp (max 232448)",
                 B, C, smem);
     const bool tma_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (a.R == 1 || rec_stride % 4 == 0) &&
@@ -410,6 +509,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
                                     stride1, static_cast<uint32_t>(a.TC), static_cast<uint32_t>(a.G));
         if (rc != OFP_OK) return rc;
     }
+    { int rc = upload_tables(); if (rc != OFP_OK) return rc; }
     const int grid = (a.R + a.G - 1) / a.G;
     auto kern = p.use_hp ? (tma_ok ? k1_detect<true, true> : k1_detect<true, false>)
                          : (tma_ok ? k1_detect<false, true> : k1_detect<false, false>);
