@@ -70,6 +70,45 @@ struct K1Args {
     int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
 };
 
+// Per-kernel constants held in registers for the whole launch (a one-warp CTA has registers to
+// spare; re-loading them from the constant bank inside the recurrences costs LDC latency).
+struct Coef {
+    float b0, b1, b2, b3, b4, a1, a2, a3, a4;
+    float fa, fr, sa, sr;
+    float floor_db, ceil_amp;
+    float amin, amax, iamin, iamax, minmin;
+};
+__device__ __forceinline__ Coef load_coef(const K1Args &a) {
+    Coef k;
+    k.b0 = a.p.b[0]; k.b1 = a.p.b[1]; k.b2 = a.p.b[2]; k.b3 = a.p.b[3]; k.b4 = a.p.b[4];
+    k.a1 = a.p.a[1]; k.a2 = a.p.a[2]; k.a3 = a.p.a[3]; k.a4 = a.p.a[4];
+    k.fa = a.p.fast_att; k.fr = a.p.fast_rel; k.sa = a.p.slow_att; k.sr = a.p.slow_rel;
+    k.floor_db = a.p.floor_db; k.ceil_amp = -a.p.floor_db;
+    k.amin = a.p.alpha_min; k.amax = a.p.alpha_max; k.iamin = a.ia_min; k.iamax = a.ia_max;
+    k.minmin = a.p.minmin;
+    return k;
+}
+
+// Shared memory is addressed with explicit 32-bit shared-space addresses (no generic-pointer
+// window arithmetic in the hot loop).  The "memory" clobber keeps these ordered against the
+// mbarrier waits / warp syncs that publish the TMA tiles.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));  // tables are read-only after setup
+    return v;
+}
+__device__ __forceinline__ void lds_2f64(uint32_t addr, double &x, double &y) {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
+}
+
 // Rare paths (special inputs, results too close to a float32 rounding boundary): full-precision
 // libdevice routines, kept out of line so that the hot loop stays small in the instruction cache.
 __device__ __noinline__ double slow_log10(float v) { return log10(static_cast<double>(v)); }
@@ -85,8 +124,7 @@ __device__ __noinline__ float slow_ar_delta(float t) {
 __device__ __forceinline__ float ar_step(float y, float x, float att, float rel) {
     const float t = __fsub_rn(x, y);
     float d = __fadd_rn(t, 1e-10f);
-    if (__builtin_expect(fabsf(t) < 0x1p-22f && t != 0.0f, 0))
-        d = slow_ar_delta(t);
+    if (__builtin_expect(fabsf(t) < 0x1p-22f && t != 0.0f, 0)) d = slow_ar_delta(t);
     const float coef = d > 0.0f ? att : rel;
     return __fadd_rn(y, __fmul_rn(coef, d));
 }
@@ -97,88 +135,114 @@ struct Lane {
 };
 
 // scipy lfilter, DF2T, float32, unfused (detection.py:499-501)
-__device__ __forceinline__ float hp_step(Lane &L, const K1Args &a, float x) {
-    const float y = __fadd_rn(L.z0, __fmul_rn(a.p.b[0], x));
-    L.z0 = __fsub_rn(__fadd_rn(L.z1, __fmul_rn(x, a.p.b[1])), __fmul_rn(y, a.p.a[1]));
-    L.z1 = __fsub_rn(__fadd_rn(L.z2, __fmul_rn(x, a.p.b[2])), __fmul_rn(y, a.p.a[2]));
-    L.z2 = __fsub_rn(__fadd_rn(L.z3, __fmul_rn(x, a.p.b[3])), __fmul_rn(y, a.p.a[3]));
-    L.z3 = __fsub_rn(__fmul_rn(x, a.p.b[4]), __fmul_rn(y, a.p.a[4]));
+__device__ __forceinline__ float hp_step(Lane &L, const Coef &k, float x) {
+    const float y = __fadd_rn(L.z0, __fmul_rn(k.b0, x));
+    L.z0 = __fsub_rn(__fadd_rn(L.z1, __fmul_rn(x, k.b1)), __fmul_rn(y, k.a1));
+    L.z1 = __fsub_rn(__fadd_rn(L.z2, __fmul_rn(x, k.b2)), __fmul_rn(y, k.a2));
+    L.z2 = __fsub_rn(__fadd_rn(L.z3, __fmul_rn(x, k.b3)), __fmul_rn(y, k.a3));
+    L.z3 = __fsub_rn(__fmul_rn(x, k.b4), __fmul_rn(y, k.a4));
     return y;
 }
 
 // detection.py:747-748: clip(20*log10(|h + 1e-10|), floor) in float32; log10 correctly rounded.
-// Returns the fast-path value; `redo` is set when the value must be recomputed by slow_log10
-// (special input, or the double result is too close to a float32 rounding boundary).
 __device__ __forceinline__ float db_of(double ld, float floor_db) {
     return fmaxf(__fmul_rn(20.0f, __double2float_rn(ld)), floor_db);
 }
-__device__ __forceinline__ float to_db_fast(float h, float floor_db, const double *logtab, const MathConst &mc,
+// Fast path of k1_math.cuh:log10_core with the table in shared memory; `redo` is set when the value
+// must be recomputed by slow_log10 (special input, or too close to a float32 rounding boundary).
+__device__ __forceinline__ float to_db_fast(float h, float floor_db, uint32_t logtab, const MathConst &mc,
                                             float &v_out, bool &redo) {
     const float v = fabsf(__fadd_rn(h, 1e-10f));
     const uint32_t ix = __float_as_uint(v);
-    const double ld = log10_core(ix, logtab, mc);
+    const uint32_t tmp = ix - OFP_LOG_OFF;
+    const int32_t kexp = static_cast<int32_t>(tmp) >> 23;
+    const uint32_t ti = (tmp >> (23 - OFP_LOG_N - 4)) & (((1u << OFP_LOG_N) - 1u) << 4);  // byte offset
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double z = __hiloint2double(static_cast<int>((iz >> 3) + 0x38000000u), static_cast<int>(iz << 29));
+    double invc, logc;
+    lds_2f64(logtab + ti, invc, logc);
+    const double r = __fma_rn(z, invc, -1.0);
+    const double r2 = __dmul_rn(r, r);
+    const double p01 = __fma_rn(r, mc.a2, mc.a1);
+    const double p23 = __fma_rn(r, mc.a4, mc.a3);
+    const double pp = __fma_rn(r2, __fma_rn(r2, mc.a5, p23), p01);
+    const double base = __fma_rn(static_cast<double>(kexp), mc.log10_2, logc);
+    const double ld = __fma_rn(r, pp, base);
     redo = ((ix - 0x00800000u) >= 0x7f000000u) | near_f32_midpoint(ld, 1u << 13);
     v_out = v;
     return db_of(ld, floor_db);
 }
 
 // detection.py:753-754: clip(10**(r/20) - 1e-10, 0, -floor) in float32; 10**x correctly rounded.
-__device__ __forceinline__ float amp_of(double ad, float floor_db) {
+__device__ __forceinline__ float amp_of(double ad, float ceil_amp) {
     const float amp = __fsub_rn(__double2float_rn(ad), 1e-10f);
-    return fminf(fmaxf(amp, 0.0f), -floor_db);
+    return fminf(fmaxf(amp, 0.0f), ceil_amp);
 }
-__device__ __forceinline__ float to_amp_fast(float r, float floor_db, const double *exptab, const MathConst &mc,
+__device__ __forceinline__ float to_amp_fast(float r, float ceil_amp, uint32_t exptab, const MathConst &mc,
                                              float &q_out, bool &redo) {
     // r / 20 correctly rounded without a division (exact: host harness over 4e8 values)
     const float q0 = __fmul_rn(r, 0.05f);
     const float q = __fmaf_rn(__fmaf_rn(-20.0f, q0, r), 0.05f, q0);
-    const double ad = exp10_core(q, exptab, mc);
+    const double t = __dmul_rn(static_cast<double>(q), mc.log2_10);
+    const double kd0 = __fma_rn(t, 32.0, mc.shift);
+    const int32_t ki = __double2loint(kd0);
+    const double kd = __dsub_rn(kd0, mc.shift);
+    const double rr = __fma_rn(kd, -0.03125, t);
+    const double r2 = __dmul_rn(rr, rr);
+    const double p01 = __fma_rn(rr, mc.e2, mc.e1);
+    const double p23 = __fma_rn(rr, mc.e4, mc.e3);
+    const double pp = __fma_rn(r2, __fma_rn(r2, mc.e5, p23), p01);
+    const double sc = lds_f64(exptab + ((ki & 31) << 3));
+    const double y = __fma_rn(__dmul_rn(sc, rr), pp, sc);
+    const double ad = __hiloint2double(__double2hiint(y) + ((ki >> 5) << 20), __double2loint(y));
     redo = !(fabsf(q) < 30.0f) | near_f32_midpoint(ad, 1u << 8);
     q_out = q;
-    return amp_of(ad, floor_db);
+    return amp_of(ad, ceil_amp);
 }
 
 // envelope_follower.c:38-52
-__device__ __forceinline__ void minmax_step(Lane &L, const K1Args &a, float r) {
-    const float nm = __fadd_rn(__fmul_rn(L.mn, a.ia_min), __fmul_rn(r, a.p.alpha_min));
-    L.mn = r < a.p.minmin ? a.p.minmin : (r < L.mn ? r : nm);
-    const float nx = __fadd_rn(__fmul_rn(L.mx, a.ia_max), __fmul_rn(r, a.p.alpha_max));
+__device__ __forceinline__ void minmax_step(Lane &L, const Coef &k, float r) {
+    const float nm = __fadd_rn(__fmul_rn(L.mn, k.iamin), __fmul_rn(r, k.amin));
+    L.mn = r < k.minmin ? k.minmin : (r < L.mn ? r : nm);
+    const float nx = __fadd_rn(__fmul_rn(L.mx, k.iamax), __fmul_rn(r, k.amax));
     L.mx = r > L.mx ? r : nx;
 }
 
 // U consecutive samples of one lane, stage by stage so that the pointwise stages (dB, 10**x) of the
 // U samples are independent instruction streams between the short sequential recurrences.  The rare
 // slow paths are taken after a warp vote, outside the straight-line code.
+//   xs: shared address of the lane's first input sample, rs: of its first rel slot; step = 4*C bytes.
 template <bool USE_HP, int U>
-__device__ __forceinline__ void chunk(Lane &L, const K1Args &a, const float *xp, float *rp, int C, bool do_minmax,
-                                      bool store, const double *logtab, const double *exptab, const MathConst &mc) {
+__device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
+                                      bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
+                                      const MathConst &mc) {
     float h[U], db[U], dr[U], amp[U], aux[U];
     bool redo[U], any = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const float x = xp[u * C];
-        h[u] = USE_HP ? hp_step(L, a, x) : x;
+        const float x = lds_f32(xs + u * step);
+        h[u] = USE_HP ? hp_step(L, k, x) : x;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        db[u] = to_db_fast(h[u], a.p.floor_db, logtab, mc, aux[u], redo[u]);
+        db[u] = to_db_fast(h[u], k.floor_db, logtab, mc, aux[u], redo[u]);
         any |= redo[u];
     }
     if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (redo[u]) db[u] = db_of(slow_log10(aux[u]), a.p.floor_db);
+            if (redo[u]) db[u] = db_of(slow_log10(aux[u]), k.floor_db);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {  // detection.py:751 (envelope_follower.c:6-25 twice)
-        L.yf = ar_step(L.yf, db[u], a.p.fast_att, a.p.fast_rel);
-        L.ys = ar_step(L.ys, db[u], a.p.slow_att, a.p.slow_rel);
+        L.yf = ar_step(L.yf, db[u], k.fa, k.fr);
+        L.ys = ar_step(L.ys, db[u], k.sa, k.sr);
         dr[u] = __fsub_rn(L.yf, L.ys);
     }
     any = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        amp[u] = to_amp_fast(dr[u], a.p.floor_db, exptab, mc, aux[u], redo[u]);
+        amp[u] = to_amp_fast(dr[u], k.ceil_amp, exptab, mc, aux[u], redo[u]);
         any |= redo[u];
     }
     if (__any_sync(0xffffffffu, any)) {
@@ -186,20 +250,42 @@ __device__ __forceinline__ void chunk(Lane &L, const K1Args &a, const float *xp,
         for (int u = 0; u < U; ++u)
             if (redo[u]) {
                 const float q = fabsf(aux[u]) < 30.0f ? aux[u] : __fdiv_rn(dr[u], 20.0f);
-                amp[u] = amp_of(slow_exp10(q), a.p.floor_db);
+                amp[u] = amp_of(slow_exp10(q), k.ceil_amp);
             }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        if (do_minmax) minmax_step(L, a, amp[u]);
+        if (do_minmax) minmax_step(L, k, amp[u]);
         L.bmax = fmaxf(L.bmax, amp[u]);
         L.bmin = fminf(L.bmin, amp[u]);
-        if (store) rp[u * C] = amp[u];
+        if (store) sts_f32(rs + u * step, amp[u]);
     }
 }
 
 __device__ double g_logtab[2 << OFP_LOG_N];
 __device__ double g_exptab[32];
+
+// Round-trip the launch constants through shared memory with volatile loads.  To nvcc/ptxas the
+// reloaded values are opaque, so they stay in registers; otherwise they are re-materialised inside
+// the recurrences as constant-bank loads (LDC, ~30 cycles in a dependent chain) and 64-bit
+// immediates (2 UMOV each).  scratch: >= 256 bytes of shared memory not yet in use.
+__device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch) {
+    float *f = reinterpret_cast<float *>(&k);
+    double *m = reinterpret_cast<double *>(&mc);
+    constexpr int NF = sizeof(Coef) / 4, ND = sizeof(MathConst) / 8;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) sts_f32(scratch + 4 * i, f[i]);
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(scratch + 128 + 8 * i), "d"(m[i]) : "memory");
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NF; ++i) asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(f[i]) : "r"(scratch + 4 * i) : "memory");
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+        asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(m[i]) : "r"(scratch + 128 + 8 * i) : "memory");
+    __syncwarp();
+}
 
 template <bool USE_HP, bool USE_TMA>
 __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
@@ -223,12 +309,11 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
     const unsigned rec_mask = (C == 32 ? 0xffffffffu : ((1u << C) - 1u)) << (g * C);
     const unsigned lower_mask = rec_mask & ((1u << lane) - 1u);
 
+    Coef kf = load_coef(a);
+    const uint32_t logtab_s = smem_u32(logtab), exptab_s = smem_u32(exptab);
+    const uint32_t step = 4u * C;
     MathConst mc = math_const();
-    {   // keep the constants in registers (opaque moves defeat re-materialisation as immediates)
-        double *m = reinterpret_cast<double *>(&mc);
-#pragma unroll
-        for (int i = 0; i < static_cast<int>(sizeof(MathConst) / 8); ++i) asm volatile("" : "+d"(m[i]));
-    }
+    launder(kf, mc, smem_u32(relbuf));
     Lane L;
     if (active) {
         L.z0 = a.st.z0[lid]; L.z1 = a.st.z1[lid]; L.z2 = a.st.z2[lid]; L.z3 = a.st.z3[lid];
@@ -257,6 +342,8 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
     int64_t blk = 0;      // main-phase block index
 
     float *rcol = relbuf + g * a.stride_rel + c;  // this lane's column of the block buffer
+    const uint32_t rcol_s = smem_u32(rcol);
+    const uint32_t stage0_s = smem_u32(stages) + 4u * (g * TC + c);
 
     for (int phase = 0; phase < 2; ++phase) {
         const int64_t len = phase == 0 ? a.warm_n : a.n_main;
@@ -297,20 +384,22 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
                 }
                 __syncwarp();
             }
-            const float *sp = stages + static_cast<size_t>(s) * a.stage_floats + g * TC + c;
+            const uint32_t sp = stage0_s + 4u * static_cast<uint32_t>(s) * a.stage_floats;
             const int tl = static_cast<int>(min(static_cast<int64_t>(T), len - t0));
             int j = 0;
             while (j < tl) {
                 const int64_t t = t0 + j;
                 if (t < env_len) {
                     const int seg = min(tl - j, B - kpos);
-                    const float *xp = sp + j * C;
-                    float *rp = rcol + kpos * C;
+                    const uint32_t xp = sp + j * step;
+                    const uint32_t rp = rcol_s + kpos * step;
                     int i = 0;
                     for (; i + 4 <= seg; i += 4)
-                        chunk<USE_HP, 4>(L, a, xp + i * C, rp + i * C, C, do_minmax, in_group, logtab, exptab, mc);
+                        chunk<USE_HP, 4>(L, kf, xp + i * step, rp + i * step, step, do_minmax, in_group, logtab_s,
+                                         exptab_s, mc);
                     for (; i < seg; ++i)
-                        chunk<USE_HP, 1>(L, a, xp + i * C, rp + i * C, C, do_minmax, in_group, logtab, exptab, mc);
+                        chunk<USE_HP, 1>(L, kf, xp + i * step, rp + i * step, step, do_minmax, in_group, logtab_s,
+                                         exptab_s, mc);
                     j += seg;
                     kpos += seg;
                     if (kpos == B) {
@@ -382,8 +471,7 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
                     // (detection.py:828-829 filters the whole half second in one call)
                     const int seg = tl - j;
                     if (USE_HP) {
-                        const float *xp = sp + j * C;
-                        for (int i = 0; i < seg; ++i) hp_step(L, a, xp[i * C]);
+                        for (int i = 0; i < seg; ++i) hp_step(L, kf, lds_f32(sp + (j + i) * step));
                     }
                     j += seg;
                 }
