@@ -112,6 +112,78 @@ int ofp_minmax_envelope(const float *x_dev, float *min_dev, float *max_dev, floa
                         float alpha_max, float minmin, int n_samples, int n_channels, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K3  onset grouping -- replaces find_onset_groups (detection.py:131-189)
+ * ------------------------------------------------------------------------------------- */
+
+/* One sequential scan per recording over its onsets in detection order (the output of
+ * ofp_detect_offline).  groups_dev [R, max_groups, C] int32 (-1 = channel missing),
+ * n_groups_dev [R] (may exceed max_groups; only max_groups are stored).
+ * close_channel < 0 disables the close-channel filter (detection.py:184-185). */
+int ofp_group_onsets(const int32_t *on_channel_dev, const int32_t *on_sample_dev, const int32_t *on_count_dev,
+                     int32_t n_rec, int32_t cap, int32_t n_channels, int32_t max_distance, int32_t min_channels,
+                     int32_t close_channel, int32_t max_groups, int32_t *groups_dev, int32_t *n_groups_dev,
+                     void *stream);
+/* Flatten the per-recording groups into a hit list.  offsets_dev [R] int64 = exclusive prefix sum of
+ * min(n_groups, max_groups); hit_rec_dev [H] int32, hit_onsets_dev [H, C] int32. */
+int ofp_compact_groups(const int32_t *groups_dev, const int32_t *n_groups_dev, const int64_t *offsets_dev,
+                       int32_t n_rec, int32_t max_groups, int32_t n_channels, int32_t *hit_rec_dev,
+                       int32_t *hit_onsets_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  lag refinement -- replaces fix_onsets (detection.py:373-451) and, inside it,
+ *     cross_correlation_lag (195-268) and adjust_onset (299-352)
+ * ------------------------------------------------------------------------------------- */
+
+#define OFP_LAG_NONE INT32_MIN /* cross_correlation_lag returned None */
+#define OFP_FIX_OK 0
+#define OFP_FIX_DEGENERATE 1 /* section start < 0 or too short: the reference wraps / raises (Q6) */
+#define OFP_FIX_REF_CRASH 2  /* the reference raises ValueError in adjust_onset (Q10); onsets as of the failing pair */
+#define OFP_FIX_TOO_LONG 3   /* section longer than max_section */
+#define OFP_FIX_INCOMPLETE 4 /* a channel of the group is missing (-1) */
+
+/* fix_onsets for n_hits onset groups in one launch.
+ *   audio_dev [R, n_samples, C] float32 (recording stride rec_stride elements)
+ *   hit_rec_dev [H] int32 recording of each hit, or NULL (hit h lives in recording h)
+ *   onsets_dev [H, C] int32 sample index per channel
+ *   filter_size/d/direction(0 none,1 "up",2 "down")/take_abs/zero_left/cutoff/tol/shift: the keyword
+ *   arguments of fix_onsets; max_section: upper bound on (span + 2*(cutoff+tol)) in samples
+ *   out_onsets_dev [H, C]; out_lags_dev [H, C] or NULL (lag returned by cross_correlation_lag per
+ *   later channel, OFP_LAG_NONE elsewhere); out_status_dev [H] OFP_FIX_*. */
+int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                   const int32_t *hit_rec_dev, const int32_t *onsets_dev, int32_t n_hits, int32_t filter_size,
+                   int32_t d, int32_t direction, int32_t take_abs, int32_t zero_left, int32_t cutoff, int32_t tol,
+                   int32_t shift, int32_t max_section, int32_t *out_onsets_dev, int32_t *out_lags_dev,
+                   int32_t *out_status_dev, void *stream);
+int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section);
+
+/* cross_correlation_lag for n_pairs pairs of equal length n: x_dev, y_dev [P, n] float32;
+ * onsets_or_legal_dev [P, 2] = (onset_x, onset_y) or (legal_lo, legal_hi); lag_dev [P] (OFP_LAG_NONE = None). */
+int ofp_cross_correlation_lag(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, int32_t d,
+                              int32_t take_abs, int32_t use_legal_lags, int32_t cutoff, int32_t tol,
+                              const int32_t *onsets_or_legal_dev, int32_t *lag_dev, void *stream);
+/* adjust_onset: out_dev [P, 2] = (change of onset_x, change of onset_y); both OFP_LAG_NONE where the
+ * reference raises. */
+int ofp_adjust_onset(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, const int32_t *onsets_dev,
+                     const int32_t *new_lag_dev, int32_t *out_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K5  TDOA multilateration -- replaces Multilaterate3D.is_legal / is_legal_3d / trilaterate and
+ *     solve_trilateration_3d (multilateration.py:230-316, 397-426, 536-566); per-hit batch form
+ * ------------------------------------------------------------------------------------- */
+
+/* status per hit: 0 located, 1 lag beyond max_max_lags, 2 is_legal failed, 3 no seed cell,
+ * 4 solver did not converge (fsolve ier != 1), 5 invalid sensors.
+ *   sensor_xyz_dev [S, 3] float64 cm; lag_maps_dev [S, S, M, M] float32 (NaN = illegal), entry
+ *   [i][j] = Multilaterate3D.lag_maps[i][j]; max/min_lags_dev [S, S] float32; max_max_dev [S];
+ *   hit_sensors_dev [H, 3] int32 or NULL (sensors 0,1,2); hit_onsets_dev [H, onset_stride] int32,
+ *   the first three entries of a row are used; xy_dev [H, 2] float64 (NaN when not located). */
+int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                    int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                    const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                    double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
+                    int32_t onset_stride, int32_t n_hits, double *xy_dev, int32_t *status_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Benchmark input: seeded synthetic multi-mic drum audio generated on the device
  * (SURVEY.md section 8d signal model; not a reference function).  x_dev [R, N, C] float32;
  * sensors_xyz_host [C, 3] cm (host); rec_offset = global index of recording 0 of this shard.

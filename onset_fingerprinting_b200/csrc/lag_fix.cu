@@ -1,0 +1,620 @@
+// K3 (group_onsets) and K4 (lag_fix): onset groups -> bounded-lag cross-correlation -> adjusted onsets.
+//
+// Replaces find_onset_groups (reference detection.py:131-189), fix_onsets (373-451),
+// cross_correlation_lag (195-268) and adjust_onset (299-352).
+//
+// K4 design (DESIGN.md "K4"): one CTA per hit.  The audio section [a-look, b+look) x C is read from
+// HBM once (coalesced, straight from the [R, N, C] recording -- no materialised sections), median
+// filtered / differenced / rectified in shared memory, then the later channels are aligned one after
+// the other (the reference moves the reference onset between pairs, SURVEY Q6, so pairs are
+// sequential).  Per pair only the 2*tol lags of the legal window are evaluated (the reference
+// computes all 2n-1 and slices): one thread per 4 consecutive lags, double accumulation in index
+// order (bit-identical to the oracle's restatement), sliding register window so that each step is
+// 2 LDS.64 + 4 DFMA.  argmax / max / weighted sums are block reductions.
+#include "ofp_common.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace ofp {
+
+constexpr int LAG_NONE = INT32_MIN;
+constexpr int FIX_OK = 0, FIX_DEGENERATE = 1, FIX_REF_CRASH = 2, FIX_TOO_LONG = 3, FIX_INCOMPLETE = 4;
+constexpr int K4_THREADS = 256;
+constexpr int LPT = 4;  // lags per thread
+
+struct FixParams {
+    int32_t filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift;
+};
+
+struct K4Args {
+    const float *audio;
+    int64_t rec_stride, n_samples;
+    int32_t C, H, Lmax;
+    const int32_t *hit_rec;  // [H] recording of each hit (may be null: rec = hit)
+    const int32_t *onsets;   // [H, C]
+    FixParams fp;
+    int32_t *out_onsets;     // [H, C]
+    int32_t *out_lags;       // [H, C] (may be null)
+    int32_t *out_status;     // [H]
+};
+
+__device__ __forceinline__ void py_slice(int64_t &s, int64_t &e, int64_t len) {
+    if (s < 0) { s += len; if (s < 0) s = 0; } else if (s > len) s = len;
+    if (e < 0) { e += len; if (e < 0) e = 0; } else if (e > len) e = len;
+}
+
+// median of `size` values by rank counting (stable: equal values ranked by position)
+__device__ __forceinline__ float median_rank(const float *w, int size) {
+    const int want = size / 2;
+    float med = w[0];
+    for (int i = 0; i < size; ++i) {
+        int rank = 0;
+        for (int j = 0; j < size; ++j) rank += (w[j] < w[i]) || (w[j] == w[i] && j < i);
+        if (rank == want) med = w[i];
+    }
+    return med;
+}
+
+template <int SIZE>
+__device__ __forceinline__ float median_window(const float *src, int64_t L, int C, int64_t t, int c, int size) {
+    float w[SIZE > 0 ? SIZE : 16];
+    const int n = SIZE > 0 ? SIZE : size;
+    const int lo = n / 2;
+#pragma unroll
+    for (int j = 0; j < (SIZE > 0 ? SIZE : 16); ++j) {
+        if (j < n) {
+            int64_t q = t - lo + j;  // scipy mode='reflect': d c b a | a b c d | d c b a
+            if (L == 1) q = 0;
+            else {
+                const int64_t P = 2 * L;
+                q %= P; if (q < 0) q += P;
+                if (q >= L) q = P - 1 - q;
+            }
+            w[j] = src[q * C + c];
+        }
+    }
+    if (SIZE > 0) {
+        const int want = SIZE / 2;
+        float med = w[0];
+#pragma unroll
+        for (int i = 0; i < SIZE; ++i) {
+            int rank = 0;
+#pragma unroll
+            for (int j = 0; j < SIZE; ++j) rank += (w[j] < w[i]) || (w[j] == w[i] && j < i);
+            if (rank == want) med = w[i];
+        }
+        return med;
+    }
+    return median_rank(w, n);
+}
+
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    for (int i = 0; i < K4_THREADS / 32; ++i) r += scratch[i];
+    return r;
+}
+
+__device__ __forceinline__ float block_max(float v, float *scratch) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_down_sync(0xffffffffu, v, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float r = scratch[0];
+    for (int i = 1; i < K4_THREADS / 32; ++i) r = fmaxf(r, scratch[i]);
+    return r;
+}
+
+// Normalised cross-correlation over the window [ws, ws + nl) of np.correlate(x, y, "full") and its
+// argmax (detection.py:244-268).  xd, yd: the two signals as doubles in shared memory, length L.
+// Result (adj - argmax) is left in *s_lag after a __syncthreads().
+__device__ __forceinline__ void cc_argmax(const double *xd, const double *yd, int64_t L, int64_t ws, int64_t nl,
+                                          int64_t adj, int cutoff, float *best_v, int *best_w, int *s_lag) {
+    const int tid = threadIdx.x;
+        // ---- bounded-lag cross-correlation: LPT consecutive lags per thread ----
+        float bv = -INFINITY; int bw = INT32_MAX;
+        for (int64_t w0 = static_cast<int64_t>(tid) * LPT; w0 < nl; w0 += K4_THREADS * LPT) {
+            const int64_t m0 = ws + w0 - (L - 1);  // lag of the first of the LPT windows
+            double acc[LPT];
+            int64_t i0[LPT], i1[LPT];
+#pragma unroll
+            for (int u = 0; u < LPT; ++u) {
+                const int64_t m = m0 + u;
+                acc[u] = 0.0;
+                i0[u] = m < 0 ? -m : 0;
+                i1[u] = m > 0 ? L - m : L;
+                if (w0 + u >= nl) { i0[u] = 0; i1[u] = 0; }
+            }
+            // common body range [lo, hi): every active lag is valid there
+            int64_t lo = 0, hi = L;
+#pragma unroll
+            for (int u = 0; u < LPT; ++u) if (i1[u] > i0[u]) { lo = max(lo, i0[u]); hi = min(hi, i1[u]); }
+            if (hi < lo) hi = lo;
+            // heads (ascending i keeps the oracle's summation order)
+#pragma unroll
+            for (int u = 0; u < LPT; ++u)
+                for (int64_t i = i0[u]; i < min(lo, i1[u]); ++i) acc[u] = __fma_rn(xd[i + m0 + u], yd[i], acc[u]);
+            {
+                const bool full = (w0 + LPT <= nl);
+                if (full && lo < hi) {
+                    double x0 = xd[lo + m0], x1 = xd[lo + m0 + 1], x2 = xd[lo + m0 + 2];
+                    for (int64_t i = lo; i < hi; ++i) {
+                        const double yv = yd[i];
+                        const double x3 = xd[i + m0 + 3];
+                        acc[0] = __fma_rn(x0, yv, acc[0]);
+                        acc[1] = __fma_rn(x1, yv, acc[1]);
+                        acc[2] = __fma_rn(x2, yv, acc[2]);
+                        acc[3] = __fma_rn(x3, yv, acc[3]);
+                        x0 = x1; x1 = x2; x2 = x3;
+                    }
+                } else {
+                    for (int64_t i = lo; i < hi; ++i) {
+                        const double yv = yd[i];
+#pragma unroll
+                        for (int u = 0; u < LPT; ++u)
+                            if (w0 + u < nl) acc[u] = __fma_rn(xd[i + m0 + u], yv, acc[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < LPT; ++u)
+                for (int64_t i = max(hi, i0[u]); i < i1[u]; ++i) acc[u] = __fma_rn(xd[i + m0 + u], yd[i], acc[u]);
+#pragma unroll
+            for (int u = 0; u < LPT; ++u) {
+                if (w0 + u < nl) {
+                    const int64_t m = m0 + u;
+                    int64_t cnt = L - (m < 0 ? -m : m);  // detection.py:247-250
+                    if (cnt < cutoff) cnt = cutoff;
+                    const float v = __fdiv_rn(__double2float_rn(acc[u]), static_cast<float>(cnt));
+                    if (v > bv) { bv = v; bw = static_cast<int>(w0 + u); }  // first maximum wins
+                }
+            }
+        }
+        // block argmax: larger value, ties -> smaller window index (np.argmax)
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const int ow = __shfl_down_sync(0xffffffffu, bw, o);
+            if (ov > bv || (ov == bv && ow < bw)) { bv = ov; bw = ow; }
+        }
+        if ((tid & 31) == 0) { best_v[tid >> 5] = bv; best_w[tid >> 5] = bw; }
+        __syncthreads();
+        if (tid == 0) {
+            float v = best_v[0]; int w = best_w[0];
+            for (int k = 1; k < K4_THREADS / 32; ++k)
+                if (best_v[k] > v || (best_v[k] == v && best_w[k] < w)) { v = best_v[k]; w = best_w[k]; }
+            if (w == INT32_MAX) w = 0;  // all NaN / -inf: np.argmax returns 0
+            *s_lag = static_cast<int>(adj - w);
+        }
+        __syncthreads();
+}
+
+// The two exponentially weighted sums of adjust_onset (detection.py:310-342).  Returns false when the
+// reference would raise "operands could not be broadcast" (SURVEY Q10).  Uniform across the block.
+__device__ __forceinline__ bool adjust_sums(const double *xd, const double *yd, int64_t L, int64_t o0, int64_t o1,
+                                            int lag, float xmax, float ymax, double *red_d, double &da, double &db,
+                                            int64_t &ld_out) {
+    const int tid = threadIdx.x;
+        const int64_t ld = (o1 - o0) - lag, k = ld < 0 ? -ld : ld;
+        int64_t xs, xe, ys, ye;
+        if (ld < 0) {
+            xs = o0 + ld > 0 ? o0 + ld : 0; xe = o0 < L ? o0 : L;
+            ys = o1 < L ? o1 : L;           ye = o1 - ld < L ? o1 - ld : L;
+        } else {
+            xs = o0;                        xe = o0 + ld < L ? o0 + ld : L;
+            ys = o1 - ld > 0 ? o1 - ld : 0; ye = o1 < L ? o1 : L;
+        }
+        const int64_t lx = xe - xs, ly = ye - ys;
+        {   // Q10: the reference raises "operands could not be broadcast" here
+            const int64_t nx = lx > 0 ? lx : 0, ex = lx > 0 ? lx : (lx == 0 ? k : (k + lx > 0 ? k + lx : 0));
+            bool bad = nx != ex && nx != 1 && ex != 1;
+            if (ly != 0) {
+                const int64_t ny = ly > 0 ? ly : 0, ey = ly > 0 ? ly : (k + ly > 0 ? k + ly : 0);
+                bad = bad || (ny != ey && ny != 1 && ey != 1);
+            }
+            if (bad) return false;
+        }
+        const double stop = -2.718281828459045, step = k > 1 ? stop / static_cast<double>(k - 1) : 0.0;
+        double pa = 0.0, pb = 0.0;
+        for (int64_t i = tid; i < lx; i += K4_THREADS) {
+            const int64_t wi = k - lx + i;
+            pa += xd[xs + i] * exp((wi == k - 1 && k > 1) ? stop : static_cast<double>(wi) * step);
+        }
+        for (int64_t i = tid; i < ly; i += K4_THREADS) {
+            const int64_t wi = k - 1 - i;
+            pb += yd[ys + i] * exp((wi == k - 1 && k > 1) ? stop : static_cast<double>(wi) * step);
+        }
+        da = block_sum(pa, red_d);
+        db = block_sum(pb, red_d);
+        da = da / static_cast<double>(xmax);
+        db = ly != 0 ? db / static_cast<double>(ymax) : 0.0;
+        __syncthreads();
+        ld_out = ld;
+        return true;
+}
+
+__global__ void __launch_bounds__(K4_THREADS) k4_fix(const K4Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = a.C, tid = threadIdx.x, h = blockIdx.x;
+    const FixParams fp = a.fp;
+    double *xd = reinterpret_cast<double *>(smem_raw);
+    double *yd = xd + a.Lmax + 8;
+    float *bufA = reinterpret_cast<float *>(yd + a.Lmax + 8);
+    float *bufB = bufA + static_cast<size_t>(a.Lmax) * C;
+    __shared__ int64_t og[32], so[32];
+    __shared__ int idx[32];
+    __shared__ int64_t s_s0, s_L0;
+    __shared__ int s_status;
+    __shared__ double red_d[K4_THREADS / 32];
+    __shared__ float red_f[K4_THREADS / 32];
+    __shared__ float best_v[K4_THREADS / 32];
+    __shared__ int best_w[K4_THREADS / 32];
+    __shared__ int s_lag;
+
+    if (tid < C) og[tid] = static_cast<int64_t>(a.onsets[static_cast<int64_t>(h) * C + tid]);
+    __syncthreads();
+    const int look = fp.cutoff + fp.tol;  // detection.py:413
+    if (tid == 0) {
+        int st = FIX_OK;
+        for (int c = 0; c < C; ++c) {
+            if (og[c] < 0) st = FIX_INCOMPLETE;  // -1 = channel missing in this group
+            og[c] += fp.shift;                   // detection.py:414
+            idx[c] = c;
+        }
+        for (int i = 1; i < C; ++i) {            // np.argsort (stable for <= 16 elements)
+            const int v = idx[i];
+            int j = i - 1;
+            while (j >= 0 && og[idx[j]] > og[v]) { idx[j + 1] = idx[j]; --j; }
+            idx[j + 1] = v;
+        }
+        const int64_t s0 = og[idx[0]] - look;    // detection.py:419
+        int64_t s1 = og[idx[C - 1]] + look;
+        if (s1 > a.n_samples) s1 = a.n_samples;
+        const int64_t L0 = s1 - s0;
+        if (st == FIX_OK && (s0 < 0 || L0 - fp.d < 1)) st = FIX_DEGENERATE;
+        if (st == FIX_OK && L0 > a.Lmax) st = FIX_TOO_LONG;
+        s_s0 = s0; s_L0 = L0; s_status = st;
+    }
+    __syncthreads();
+    const int64_t s0 = s_s0, L0 = s_L0;
+    if (s_status != FIX_OK) {
+        if (tid < C) {
+            a.out_onsets[static_cast<int64_t>(h) * C + tid] = static_cast<int32_t>(og[tid]);
+            if (a.out_lags) a.out_lags[static_cast<int64_t>(h) * C + tid] = LAG_NONE;
+        }
+        if (tid == 0) a.out_status[h] = s_status;
+        return;
+    }
+    const int64_t rec = a.hit_rec ? a.hit_rec[h] : h;
+    const float *src = a.audio + rec * a.rec_stride + s0 * C;
+    for (int64_t e = tid; e < L0 * C; e += K4_THREADS) bufA[e] = src[e];
+    if (tid < C && a.out_lags) a.out_lags[static_cast<int64_t>(h) * C + tid] = LAG_NONE;
+    __syncthreads();
+    // median filter along time (detection.py:420-422)
+    for (int64_t e = tid; e < L0 * C; e += K4_THREADS) {
+        const int64_t t = e / C;
+        const int c = static_cast<int>(e - t * C);
+        float m;
+        switch (fp.filter_size) {
+            case 1: m = bufA[e]; break;
+            case 3: m = median_window<3>(bufA, L0, C, t, c, 3); break;
+            case 5: m = median_window<5>(bufA, L0, C, t, c, 5); break;
+            case 7: m = median_window<7>(bufA, L0, C, t, c, 7); break;
+            case 9: m = median_window<9>(bufA, L0, C, t, c, 9); break;
+            default: m = median_window<0>(bufA, L0, C, t, c, fp.filter_size); break;
+        }
+        bufB[e] = m;
+    }
+    __syncthreads();
+    float *sec = bufB, *other = bufA;
+    int64_t L = L0;
+    for (int r = 0; r < fp.d; ++r) {  // np.diff(., d, axis=0)
+        for (int64_t e = tid; e < (L - 1) * C; e += K4_THREADS) other[e] = __fsub_rn(sec[e + C], sec[e]);
+        __syncthreads();
+        float *tmp = sec; sec = other; other = tmp;
+        --L;
+    }
+    for (int64_t e = tid; e < L * C; e += K4_THREADS) {  // detection.py:423-428
+        float v = sec[e];
+        if (fp.direction == 1 && v < 0.f) v = 0.f;
+        if (fp.direction == 2 && v > 0.f) v = 0.f;
+        if (fp.take_abs) v = fabsf(v);
+        sec[e] = v;
+    }
+    if (tid < C) so[tid] = og[tid] - s0;  // detection.py:429
+    __syncthreads();
+
+    const int r = idx[0];
+    int status = FIX_OK;
+    for (int j = 1; j < C; ++j) {
+        const int ci = idx[j];
+        const int64_t o0 = so[r], o1 = so[ci];
+        if (fp.zero_left) {  // detection.py:435-437 (python slice x[:o] = 0)
+            int64_t b0 = 0, z0 = o0, b1 = 0, z1 = o1;
+            py_slice(b0, z0, L); py_slice(b1, z1, L);
+            for (int64_t t = tid; t < z0; t += K4_THREADS) sec[t * C + r] = 0.f;
+            for (int64_t t = tid; t < z1; t += K4_THREADS) sec[t * C + ci] = 0.f;
+            __syncthreads();
+        }
+        float xm = -INFINITY, ym = -INFINITY;
+        for (int64_t t = tid; t < L; t += K4_THREADS) {
+            const float xv = sec[t * C + r], yv = sec[t * C + ci];
+            xd[t] = static_cast<double>(xv); yd[t] = static_cast<double>(yv);
+            xm = fmaxf(xm, xv); ym = fmaxf(ym, yv);
+        }
+        const float xmax = block_max(xm, red_f);
+        const float ymax = block_max(ym, red_f);
+        __syncthreads();
+        // window of the full CC, detection.py:259-264
+        const int64_t cur = o1 - o0;
+        int64_t ws = L - cur - fp.tol, we = L - cur + fp.tol;
+        const int64_t adj = cur + fp.tol;
+        py_slice(ws, we, 2 * L - 1);
+        const int64_t nl = we - ws;
+        if (nl <= 0) continue;  // detection.py:265-266 -> None, no adjustment
+        cc_argmax(xd, yd, L, ws, nl, adj, fp.cutoff, best_v, best_w, &s_lag);
+        const int lag = s_lag;
+        if (tid == 0 && a.out_lags) a.out_lags[static_cast<int64_t>(h) * C + ci] = lag;
+        // ---- adjust_onset, detection.py:299-352 ----
+        double da, db;
+        int64_t ld;
+        if (!adjust_sums(xd, yd, L, o0, o1, lag, xmax, ymax, red_d, da, db, ld)) { status = FIX_REF_CRASH; break; }
+        if (tid == 0) {
+            int64_t ca, cb;
+            if (da > db && !(o0 + ld < 0)) { ca = ld; cb = 0; }
+            else { ca = 0; cb = -ld; }
+            og[r] += ca; og[ci] += cb;  // detection.py:447-450
+            so[r] += ca; so[ci] += cb;
+        }
+        __syncthreads();
+    }
+    if (tid < C) a.out_onsets[static_cast<int64_t>(h) * C + tid] = static_cast<int32_t>(og[tid]);
+    if (tid == 0) a.out_status[h] = status;
+}
+
+// Stand-alone twins of cross_correlation_lag (detection.py:195-268) and adjust_onset (299-352) for
+// P independent signal pairs of equal length n: x, y [P, n] float32.
+struct PairArgs {
+    const float *x, *y;
+    int32_t P, n, d, take_abs, use_legal, cutoff, tol;
+    const int32_t *onsets;  // [P, 2] (onset of x, onset of y) or legal lags (l0, l1) when use_legal
+    const int32_t *new_lag; // [P] (adjust only)
+    int32_t *out;           // cc: [P] lag; adjust: [P, 2]
+};
+
+__device__ __forceinline__ int64_t load_pair(const PairArgs &a, int p, double *xd, double *yd, float *tmp,
+                                             float *red_f, float &xmax, float &ymax) {
+    // np.diff(., d) then optional abs (detection.py:238-242); tmp: 2*n floats of scratch
+    const int tid = threadIdx.x;
+    float *tx = tmp, *ty = tmp + a.n;
+    for (int t = tid; t < a.n; t += K4_THREADS) {
+        tx[t] = a.x[static_cast<int64_t>(p) * a.n + t];
+        ty[t] = a.y[static_cast<int64_t>(p) * a.n + t];
+    }
+    __syncthreads();
+    int64_t L = a.n;
+    for (int r = 0; r < a.d; ++r) {
+        float nx[8], ny[8];  // n <= 8 * K4_THREADS
+        int cnt = 0;
+        for (int t = tid; t < L - 1; t += K4_THREADS, ++cnt) {
+            nx[cnt] = __fsub_rn(tx[t + 1], tx[t]);
+            ny[cnt] = __fsub_rn(ty[t + 1], ty[t]);
+        }
+        __syncthreads();
+        cnt = 0;
+        for (int t = tid; t < L - 1; t += K4_THREADS, ++cnt) { tx[t] = nx[cnt]; ty[t] = ny[cnt]; }
+        __syncthreads();
+        --L;
+    }
+    float xm = -INFINITY, ym = -INFINITY;
+    for (int t = tid; t < L; t += K4_THREADS) {
+        float xv = tx[t], yv = ty[t];
+        if (a.take_abs) { xv = fabsf(xv); yv = fabsf(yv); }
+        xd[t] = xv; yd[t] = yv;
+        xm = fmaxf(xm, xv); ym = fmaxf(ym, yv);
+    }
+    xmax = block_max(xm, red_f);
+    ymax = block_max(ym, red_f);
+    __syncthreads();
+    return L;
+}
+
+__global__ void __launch_bounds__(K4_THREADS) k4_cc_pairs(const PairArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *xd = reinterpret_cast<double *>(smem_raw);
+    double *yd = xd + a.n + 8;
+    float *tmp = reinterpret_cast<float *>(yd + a.n + 8);
+    __shared__ float red_f[K4_THREADS / 32], best_v[K4_THREADS / 32];
+    __shared__ int best_w[K4_THREADS / 32];
+    __shared__ int s_lag;
+    const int p = blockIdx.x;
+    float xmax, ymax;
+    const int64_t L = load_pair(a, p, xd, yd, tmp, red_f, xmax, ymax);
+    int64_t ws, we, adj;
+    if (a.use_legal) {  // detection.py:256-258
+        const int64_t l0 = a.onsets[2 * p], l1 = a.onsets[2 * p + 1];
+        ws = L - l1; we = L - l0; adj = l1;
+    } else {
+        const int64_t cur = static_cast<int64_t>(a.onsets[2 * p + 1]) - a.onsets[2 * p];
+        ws = L - cur - a.tol; we = L - cur + a.tol; adj = cur + a.tol;
+    }
+    py_slice(ws, we, 2 * L - 1);
+    if (we - ws <= 0 || L <= 0) { if (threadIdx.x == 0) a.out[p] = LAG_NONE; return; }
+    cc_argmax(xd, yd, L, ws, we - ws, adj, a.cutoff, best_v, best_w, &s_lag);
+    if (threadIdx.x == 0) a.out[p] = s_lag;
+}
+
+__global__ void __launch_bounds__(K4_THREADS) k4_adjust_pairs(const PairArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *xd = reinterpret_cast<double *>(smem_raw);
+    double *yd = xd + a.n + 8;
+    float *tmp = reinterpret_cast<float *>(yd + a.n + 8);
+    __shared__ float red_f[K4_THREADS / 32];
+    __shared__ double red_d[K4_THREADS / 32];
+    const int p = blockIdx.x;
+    float xmax, ymax;
+    const int64_t L = load_pair(a, p, xd, yd, tmp, red_f, xmax, ymax);
+    const int64_t o0 = a.onsets[2 * p], o1 = a.onsets[2 * p + 1];
+    double da, db;
+    int64_t ld;
+    const bool ok = adjust_sums(xd, yd, L, o0, o1, a.new_lag[p], xmax, ymax, red_d, da, db, ld);
+    if (threadIdx.x == 0) {
+        if (!ok) { a.out[2 * p] = LAG_NONE; a.out[2 * p + 1] = LAG_NONE; }  // reference raises ValueError
+        else if (da > db && !(o0 + ld < 0)) { a.out[2 * p] = static_cast<int32_t>(ld); a.out[2 * p + 1] = 0; }
+        else { a.out[2 * p] = 0; a.out[2 * p + 1] = static_cast<int32_t>(-ld); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: find_onset_groups (detection.py:131-189), one thread per recording (sequential scan).
+// ---------------------------------------------------------------------------------------------
+struct K3Args {
+    const int32_t *on_ch, *on_idx, *on_cnt;  // [R, cap], [R, cap], [R]
+    int32_t R, cap, C, max_distance, min_channels, close_channel, max_groups;
+    int32_t *groups;   // [R, max_groups, C], -1 = missing
+    int32_t *n_groups; // [R]
+};
+
+__global__ void k3_group(const K3Args a) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const int n = min(a.on_cnt[r], a.cap);
+    const int32_t *ch = a.on_ch + static_cast<int64_t>(r) * a.cap;
+    const int32_t *ix = a.on_idx + static_cast<int64_t>(r) * a.cap;
+    int32_t *out = a.groups + static_cast<int64_t>(r) * a.max_groups * a.C;
+    int32_t cur[32];
+    unsigned mask = 0;
+    int first = 0, ng = 0, members = 0;
+    auto flush = [&]() {
+        if (members > 0 && __popc(mask) >= a.min_channels) {
+            bool keep = true;
+            if (a.close_channel >= 0) {  // detection.py:184-185: all(x[close] <= x), -1 entries included
+                const int32_t cv = (mask >> a.close_channel) & 1u ? cur[a.close_channel] : -1;
+                for (int c = 0; c < a.C; ++c) {
+                    const int32_t v = (mask >> c) & 1u ? cur[c] : -1;
+                    if (!(cv <= v)) keep = false;
+                }
+            }
+            if (keep) {
+                if (ng < a.max_groups)
+                    for (int c = 0; c < a.C; ++c) out[ng * a.C + c] = (mask >> c) & 1u ? cur[c] : -1;
+                ++ng;
+            }
+        }
+    };
+    for (int i = 0; i < n; ++i) {
+        const int s = ix[i], c = ch[i];
+        if (members > 0 && abs(s - first) > a.max_distance) { flush(); mask = 0; members = 0; }
+        if (members == 0) first = s;
+        cur[c] = s;  // a later onset of the same channel overwrites (detection.py:171-172)
+        mask |= 1u << c;
+        ++members;
+    }
+    flush();
+    a.n_groups[r] = ng;
+}
+
+// Hit list from the per-recording groups: offsets = exclusive prefix sum of min(n_groups, max_groups).
+__global__ void k3_compact(const int32_t *groups, const int32_t *n_groups, const int64_t *offsets, int R,
+                           int max_groups, int C, int32_t *hit_rec, int32_t *hit_onsets) {
+    const int r = blockIdx.x;
+    if (r >= R) return;
+    const int ng = min(n_groups[r], max_groups);
+    const int64_t off = offsets[r];
+    for (int e = threadIdx.x; e < ng * C; e += blockDim.x)
+        hit_onsets[off * C + e] = groups[static_cast<int64_t>(r) * max_groups * C + e];
+    for (int g = threadIdx.x; g < ng; g += blockDim.x) hit_rec[off + g] = r;
+}
+
+}  // namespace ofp
+
+using namespace ofp;
+
+extern "C" {
+
+int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section) {
+    return static_cast<int>(2 * (max_section + 8) * sizeof(double) + 2 * static_cast<size_t>(max_section) * n_channels * sizeof(float));
+}
+
+int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                   const int32_t *hit_rec_dev, const int32_t *onsets_dev, int32_t n_hits, int32_t filter_size,
+                   int32_t d, int32_t direction, int32_t take_abs, int32_t zero_left, int32_t cutoff, int32_t tol,
+                   int32_t shift, int32_t max_section, int32_t *out_onsets_dev, int32_t *out_lags_dev,
+                   int32_t *out_status_dev, void *stream) {
+    OFP_REQUIRE(audio_dev && onsets_dev && out_onsets_dev && out_status_dev, "null argument");
+    OFP_REQUIRE(n_channels >= 2 && n_channels <= 32, "n_channels must be in 2..32");
+    OFP_REQUIRE(filter_size >= 1 && filter_size <= 15, "filter_size must be in 1..15");
+    OFP_REQUIRE(d >= 0 && cutoff >= 0 && tol >= 0 && direction >= 0 && direction <= 2, "bad option");
+    if (n_hits == 0) return OFP_OK;
+    K4Args a;
+    a.audio = audio_dev; a.rec_stride = rec_stride; a.n_samples = n_samples; a.C = n_channels; a.H = n_hits;
+    a.Lmax = max_section; a.hit_rec = hit_rec_dev; a.onsets = onsets_dev;
+    a.fp = FixParams{filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift};
+    a.out_onsets = out_onsets_dev; a.out_lags = out_lags_dev; a.out_status = out_status_dev;
+    const int smem = ofp_fix_onsets_smem_bytes(n_channels, max_section);
+    OFP_REQUIRE(smem <= 220 * 1024, "max_section %d x %d channels needs %d bytes of shared memory", max_section,
+                n_channels, smem);
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(k4_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k4_fix<<<n_hits, K4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+static int launch_pairs(bool adjust, const float *x, const float *y, int32_t P, int32_t n, int32_t d, int32_t take_abs,
+                        int32_t use_legal, int32_t cutoff, int32_t tol, const int32_t *onsets, const int32_t *new_lag,
+                        int32_t *out, void *stream) {
+    OFP_REQUIRE(x && y && onsets && out, "null argument");
+    OFP_REQUIRE(n >= 1 && n <= 8 * K4_THREADS, "signal length must be in 1..%d", 8 * K4_THREADS);
+    OFP_REQUIRE(d >= 0 && d < n, "bad difference order");
+    if (P == 0) return OFP_OK;
+    PairArgs a{x, y, P, n, d, take_abs, use_legal, cutoff, tol, onsets, new_lag, out};
+    const int smem = 2 * (n + 8) * sizeof(double) + 2 * n * sizeof(float);
+    if (adjust) k4_adjust_pairs<<<P, K4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    else k4_cc_pairs<<<P, K4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_cross_correlation_lag(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, int32_t d,
+                              int32_t take_abs, int32_t use_legal_lags, int32_t cutoff, int32_t tol,
+                              const int32_t *onsets_or_legal_dev, int32_t *lag_dev, void *stream) {
+    return launch_pairs(false, x_dev, y_dev, n_pairs, n, d, take_abs, use_legal_lags, cutoff, tol,
+                        onsets_or_legal_dev, nullptr, lag_dev, stream);
+}
+
+int ofp_adjust_onset(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, const int32_t *onsets_dev,
+                     const int32_t *new_lag_dev, int32_t *out_dev, void *stream) {
+    OFP_REQUIRE(new_lag_dev, "null argument");
+    return launch_pairs(true, x_dev, y_dev, n_pairs, n, 0, 0, 0, 0, 0, onsets_dev, new_lag_dev, out_dev, stream);
+}
+
+int ofp_group_onsets(const int32_t *on_channel_dev, const int32_t *on_sample_dev, const int32_t *on_count_dev,
+                     int32_t n_rec, int32_t cap, int32_t n_channels, int32_t max_distance, int32_t min_channels,
+                     int32_t close_channel, int32_t max_groups, int32_t *groups_dev, int32_t *n_groups_dev,
+                     void *stream) {
+    OFP_REQUIRE(on_channel_dev && on_sample_dev && on_count_dev && groups_dev && n_groups_dev, "null argument");
+    OFP_REQUIRE(n_channels >= 1 && n_channels <= 32, "n_channels must be in 1..32");
+    K3Args a{on_channel_dev, on_sample_dev, on_count_dev, n_rec, cap, n_channels, max_distance, min_channels,
+             close_channel, max_groups, groups_dev, n_groups_dev};
+    k3_group<<<(n_rec + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_compact_groups(const int32_t *groups_dev, const int32_t *n_groups_dev, const int64_t *offsets_dev,
+                       int32_t n_rec, int32_t max_groups, int32_t n_channels, int32_t *hit_rec_dev,
+                       int32_t *hit_onsets_dev, void *stream) {
+    OFP_REQUIRE(groups_dev && n_groups_dev && offsets_dev && hit_rec_dev && hit_onsets_dev, "null argument");
+    k3_compact<<<n_rec, 64, 0, static_cast<cudaStream_t>(stream)>>>(groups_dev, n_groups_dev, offsets_dev, n_rec,
+                                                                    max_groups, n_channels, hit_rec_dev,
+                                                                    hit_onsets_dev);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,376 @@
+// K5: per-hit TDOA multilateration (sm_100a), one thread per hit, IEEE double, no FMA contraction
+// (this file is compiled with -fmad=false).
+//
+// Replaces Multilaterate3D.is_legal / is_legal_3d / trilaterate and solve_trilateration_3d
+// (reference multilateration.py:230-316, 397-426, 536-566) in the per-hit batch form of
+// SURVEY.md Appendix D.  The solver is MINPACK hybrj for n = 2 exactly as
+// scipy.optimize.fsolve(xtol=0.01, maxfev=20, fprime=...) runs it (Appendix C): fsolve stops long
+// before convergence, so a generic Gauss-Newton cannot reproduce its output to 1e-4; replaying the
+// algorithm step for step does (bit-identical to scipy when squares are formed by multiplication).
+// The same restatement, written for the CPU, is oracle/oracle_c.c:orc_hybrj2.
+#include "ofp_common.cuh"
+
+namespace ofp {
+
+typedef struct { double xa, ya, za, xb, yb, zb, xo, yo, zo, da, db; } tri_problem;
+
+__device__ __forceinline__ double enorm2(double a, double b) {
+    /* MINPACK enorm rescales to avoid overflow; for the magnitudes met here (1e-12..1e4) it
+     * reduces to sqrt of the plain sum accumulated in order. */
+    return sqrt(a * a + b * b);
+}
+
+__device__ __forceinline__ void tri_f(const tri_problem *q, const double *x, double *f) {
+    /* multilateration.py:259-273, z = 0 */
+    double X = x[0], Y = x[1];
+    double dA = sqrt((X - q->xa) * (X - q->xa) + (Y - q->ya) * (Y - q->ya) + (0.0 - q->za) * (0.0 - q->za));
+    double dB = sqrt((X - q->xb) * (X - q->xb) + (Y - q->yb) * (Y - q->yb) + (0.0 - q->zb) * (0.0 - q->zb));
+    double dO = sqrt((X - q->xo) * (X - q->xo) + (Y - q->yo) * (Y - q->yo) + (0.0 - q->zo) * (0.0 - q->zo));
+    f[0] = dA - dO - q->da;
+    f[1] = dB - dO - q->db;
+}
+
+__device__ __forceinline__ void tri_j(const tri_problem *q, const double *x, double J[2][2]) {
+    /* multilateration.py:275-302 */
+    double X = x[0], Y = x[1];
+    double dA = sqrt((X - q->xa) * (X - q->xa) + (Y - q->ya) * (Y - q->ya) + (0.0 - q->za) * (0.0 - q->za));
+    double dB = sqrt((X - q->xb) * (X - q->xb) + (Y - q->yb) * (Y - q->yb) + (0.0 - q->zb) * (0.0 - q->zb));
+    double dO = sqrt((X - q->xo) * (X - q->xo) + (Y - q->yo) * (Y - q->yo) + (0.0 - q->zo) * (0.0 - q->zo));
+    J[0][0] = (X - q->xa) / dA - (X - q->xo) / dO;
+    J[0][1] = (Y - q->ya) / dA - (Y - q->yo) / dO;
+    J[1][0] = (X - q->xb) / dB - (X - q->xo) / dO;
+    J[1][1] = (Y - q->yb) / dB - (Y - q->yo) / dO;
+}
+
+#define HYB_EPS 2.220446049250313e-16
+#define HYB_GIANT 1.79769313486231570815e308
+
+/* returns ier (1 = converged); x in/out */
+__device__ int hybrj2(const tri_problem *q, double *x, double xtol, int maxfev, int *nfev_out) {
+    const double p1 = .1, p5 = .5, p001 = 1e-3, p0001 = 1e-4, factor = 100.0;
+    double fvec[2], a[2][2], diag[2] = {0, 0}, qtf[2], r11, r12, r22, Q[2][2];
+    double wa1[2], wa2[2], wa3[2], wa4[2];
+    double delta = 0, xnorm = 0, fnorm, pnorm, fnorm1, actred, prered, ratio, temp, sum;
+    int nfev, iter = 1, ncsuc = 0, ncfail = 0, nslow1 = 0, nslow2 = 0, jeval;
+    tri_f(q, x, fvec); nfev = 1;
+    fnorm = enorm2(fvec[0], fvec[1]);
+    int info = 0;
+    for (;;) { /* outer loop */
+        jeval = 1;
+        tri_j(q, x, a);
+        /* qrfac, no pivoting; column norms */
+        double acnorm[2], rdiag[2];
+        acnorm[0] = enorm2(a[0][0], a[1][0]);
+        acnorm[1] = enorm2(a[0][1], a[1][1]);
+        rdiag[0] = acnorm[0]; rdiag[1] = acnorm[1];
+        {   /* j = 0 */
+            double ajn = enorm2(a[0][0], a[1][0]);
+            if (ajn != 0.0) {
+                if (a[0][0] < 0.0) ajn = -ajn;
+                a[0][0] /= ajn; a[1][0] /= ajn;
+                a[0][0] += 1.0;
+                sum = a[0][0] * a[0][1] + a[1][0] * a[1][1];
+                temp = sum / a[0][0];
+                a[0][1] -= temp * a[0][0];
+                a[1][1] -= temp * a[1][0];
+                /* (rdiag[1] downdate is only used when pivoting) */
+            }
+            rdiag[0] = -ajn;
+            /* j = 1 */
+            ajn = fabs(a[1][1]); /* enorm of a single element */
+            if (ajn != 0.0) {
+                if (a[1][1] < 0.0) ajn = -ajn;
+                a[1][1] /= ajn;
+                a[1][1] += 1.0;
+            }
+            rdiag[1] = -ajn;
+        }
+        if (iter == 1) {
+            for (int j = 0; j < 2; ++j) { diag[j] = acnorm[j]; if (acnorm[j] == 0.0) diag[j] = 1.0; }
+            wa3[0] = diag[0] * x[0]; wa3[1] = diag[1] * x[1];
+            xnorm = enorm2(wa3[0], wa3[1]);
+            delta = factor * xnorm;
+            if (delta == 0.0) delta = factor;
+        }
+        /* qtf = Q^T fvec */
+        qtf[0] = fvec[0]; qtf[1] = fvec[1];
+        if (a[0][0] != 0.0) {
+            sum = a[0][0] * qtf[0] + a[1][0] * qtf[1];
+            temp = -sum / a[0][0];
+            qtf[0] += a[0][0] * temp; qtf[1] += a[1][0] * temp;
+        }
+        if (a[1][1] != 0.0) {
+            sum = a[1][1] * qtf[1];
+            temp = -sum / a[1][1];
+            qtf[1] += a[1][1] * temp;
+        }
+        /* copy R (upper triangle by rows) */
+        r11 = rdiag[0]; r12 = a[0][1]; r22 = rdiag[1];
+        /* qform: accumulate Q from the Householder vectors stored in the lower trapezoid */
+        Q[0][0] = a[0][0]; Q[1][0] = a[1][0]; Q[0][1] = 0.0; Q[1][1] = a[1][1];
+        for (int k = 1; k >= 0; --k) {
+            double w[2] = {0, 0};
+            for (int i = k; i < 2; ++i) { w[i] = Q[i][k]; Q[i][k] = 0.0; }
+            Q[k][k] = 1.0;
+            if (w[k] != 0.0) {
+                for (int j = k; j < 2; ++j) {
+                    sum = 0.0;
+                    for (int i = k; i < 2; ++i) sum += Q[i][j] * w[i];
+                    temp = sum / w[k];
+                    for (int i = k; i < 2; ++i) Q[i][j] -= temp * w[i];
+                }
+            }
+        }
+        for (int j = 0; j < 2; ++j) if (acnorm[j] > diag[j]) diag[j] = acnorm[j]; /* mode 1 rescale */
+
+        for (;;) { /* inner loop */
+            /* dogleg */
+            double px[2];
+            {
+                double t2 = r22, t1 = r11;
+                if (t2 == 0.0) { double l = fabs(r12) > fabs(r22) ? fabs(r12) : fabs(r22); t2 = HYB_EPS * l; if (t2 == 0.0) t2 = HYB_EPS; }
+                px[1] = (qtf[1] - 0.0) / t2;
+                if (t1 == 0.0) { double l = fabs(r11); t1 = HYB_EPS * l; if (t1 == 0.0) t1 = HYB_EPS; }
+                px[0] = (qtf[0] - r12 * px[1]) / t1;
+                double w2[2] = {diag[0] * px[0], diag[1] * px[1]};
+                double qnorm = enorm2(w2[0], w2[1]);
+                if (qnorm > delta) {
+                    double g[2];
+                    g[0] = (0.0 + r11 * qtf[0]) / diag[0];
+                    g[1] = ((0.0 + r12 * qtf[0]) + r22 * qtf[1]) / diag[1];
+                    double gnorm = enorm2(g[0], g[1]);
+                    double sgnorm = 0.0, alpha = delta / qnorm;
+                    if (gnorm != 0.0) {
+                        g[0] = (g[0] / gnorm) / diag[0];
+                        g[1] = (g[1] / gnorm) / diag[1];
+                        double s0 = (0.0 + r11 * g[0]) + r12 * g[1];
+                        double s1 = 0.0 + r22 * g[1];
+                        temp = enorm2(s0, s1);
+                        sgnorm = gnorm / temp / temp;
+                        alpha = 0.0;
+                        if (sgnorm < delta) {
+                            double bnorm = enorm2(qtf[0], qtf[1]);
+                            temp = bnorm / gnorm * (bnorm / qnorm) * (sgnorm / delta);
+                            double d1 = sgnorm / delta, d2 = temp - delta / qnorm, d3 = delta / qnorm,
+                                   d4 = sgnorm / delta;
+                            temp = temp - delta / qnorm * (d1 * d1) +
+                                   sqrt(d2 * d2 + (1.0 - d3 * d3) * (1.0 - d4 * d4));
+                            double d5 = sgnorm / delta;
+                            alpha = delta / qnorm * (1.0 - d5 * d5) / temp;
+                        }
+                    }
+                    temp = (1.0 - alpha) * (sgnorm < delta ? sgnorm : delta);
+                    px[0] = temp * g[0] + alpha * px[0];
+                    px[1] = temp * g[1] + alpha * px[1];
+                }
+            }
+            for (int j = 0; j < 2; ++j) {
+                wa1[j] = -px[j];
+                wa2[j] = x[j] + wa1[j];
+                wa3[j] = diag[j] * wa1[j];
+            }
+            pnorm = enorm2(wa3[0], wa3[1]);
+            if (iter == 1 && pnorm < delta) delta = pnorm;
+            tri_f(q, wa2, wa4); ++nfev;
+            fnorm1 = enorm2(wa4[0], wa4[1]);
+            actred = -1.0;
+            if (fnorm1 < fnorm) { double d = fnorm1 / fnorm; actred = 1.0 - d * d; }
+            /* predicted reduction: || qtf + R wa1 || */
+            wa3[0] = qtf[0] + ((0.0 + r11 * wa1[0]) + r12 * wa1[1]);
+            wa3[1] = qtf[1] + (0.0 + r22 * wa1[1]);
+            temp = enorm2(wa3[0], wa3[1]);
+            prered = 0.0;
+            if (temp < fnorm) { double d = temp / fnorm; prered = 1.0 - d * d; }
+            ratio = prered > 0.0 ? actred / prered : 0.0;
+            if (ratio < p1) { ncsuc = 0; ++ncfail; delta = p5 * delta; }
+            else {
+                ncfail = 0; ++ncsuc;
+                if (ratio >= p5 || ncsuc > 1) { double t = pnorm / p5; if (t > delta) delta = t; }
+                if (fabs(ratio - 1.0) <= p1) delta = pnorm / p5;
+            }
+            if (ratio >= p0001) {
+                for (int j = 0; j < 2; ++j) { x[j] = wa2[j]; wa2[j] = diag[j] * x[j]; fvec[j] = wa4[j]; }
+                xnorm = enorm2(wa2[0], wa2[1]);
+                fnorm = fnorm1;
+                ++iter;
+            }
+            ++nslow1; if (actred >= p001) nslow1 = 0;
+            if (jeval) ++nslow2;
+            if (actred >= p1) nslow2 = 0;
+            if (delta <= xtol * xnorm || fnorm == 0.0) info = 1;
+            if (info != 0) goto done;
+            if (nfev >= maxfev) info = 2;
+            { double t = p1 * delta; if (pnorm > t) t = pnorm; if (p1 * t <= HYB_EPS * xnorm) info = 3; }
+            if (nslow2 == 5) info = 4;
+            if (nslow1 == 10) info = 5;
+            if (info != 0) goto done;
+            if (ncfail == 2) break; /* re-evaluate the Jacobian */
+            /* rank-one (Broyden) update */
+            for (int j = 0; j < 2; ++j) {
+                sum = 0.0;
+                for (int i = 0; i < 2; ++i) sum += Q[i][j] * wa4[i];
+                wa2[j] = (sum - wa3[j]) / pnorm;
+                wa1[j] = diag[j] * (diag[j] * wa1[j] / pnorm);
+                if (ratio >= p0001) qtf[j] = sum;
+            }
+            /* r1updt(m=2,n=2): R + u v^T -> (Q1-rotations) upper-tri; u = wa1, v = wa2, w = wa3 */
+            {
+                double u0 = wa1[0], u1 = wa1[1], v0 = wa2[0], v1 = wa2[1], w0, w1, cs, sn, tau, cot, tn;
+                /* w starts as the last column of s: for n=2 jj points at r22 */
+                w1 = r22; w0 = 0.0;
+                /* rotate v into a multiple of e_n: j = n-1 = 0 */
+                if (v0 != 0.0) {
+                    if (fabs(v1) < fabs(v0)) {
+                        cot = v1 / v0; sn = p5 / sqrt(0.25 + 0.25 * (cot * cot)); cs = sn * cot;
+                        tau = 1.0; if (fabs(cs) * HYB_GIANT > 1.0) tau = 1.0 / cs;
+                    } else {
+                        tn = v0 / v1; cs = p5 / sqrt(0.25 + 0.25 * (tn * tn)); sn = cs * tn; tau = sn;
+                    }
+                    v1 = sn * v0 + cs * v1;
+                    v0 = tau;
+                    /* apply to s (row 0: r11, r12) and w */
+                    temp = cs * r11 - sn * w0; w0 = sn * r11 + cs * w0; r11 = temp;
+                    temp = cs * r12 - sn * w1; w1 = sn * r12 + cs * w1; r12 = temp;
+                }
+                /* add the spike from the rank-1 update to w */
+                w0 += v1 * u0; w1 += v1 * u1;
+                /* eliminate the spike: j = 0 */
+                int sing = 0;
+                if (w0 != 0.0) {
+                    if (fabs(r11) < fabs(w0)) {
+                        cot = r11 / w0; sn = p5 / sqrt(0.25 + 0.25 * (cot * cot)); cs = sn * cot;
+                        tau = 1.0; if (fabs(cs) * HYB_GIANT > 1.0) tau = 1.0 / cs;
+                    } else {
+                        tn = w0 / r11; cs = p5 / sqrt(0.25 + 0.25 * (tn * tn)); sn = cs * tn; tau = sn;
+                    }
+                    temp = cs * r11 + sn * w0; w0 = -sn * r11 + cs * w0; r11 = temp;
+                    temp = cs * r12 + sn * w1; w1 = -sn * r12 + cs * w1; r12 = temp;
+                    w0 = tau;
+                }
+                if (r11 == 0.0) sing = 1;
+                r22 = w1;
+                if (r22 == 0.0) sing = 1;
+                (void)sing;
+                /* r1mpyq on Q (2x2) and on qtf (1x2) with the stored rotations (v0, w0) */
+                double *rows[3] = {Q[0], Q[1], qtf};
+                for (int rr = 0; rr < 3; ++rr) {
+                    double *A = rows[rr];
+                    /* first set: j = n-2 = 0, from v */
+                    if (fabs(v0) > 1.0) { cs = 1.0 / v0; sn = sqrt(1.0 - cs * cs); }
+                    else { sn = v0; cs = sqrt(1.0 - sn * sn); }
+                    temp = cs * A[0] - sn * A[1]; A[1] = sn * A[0] + cs * A[1]; A[0] = temp;
+                    /* second set: from w */
+                    if (fabs(w0) > 1.0) { cs = 1.0 / w0; sn = sqrt(1.0 - cs * cs); }
+                    else { sn = w0; cs = sqrt(1.0 - sn * sn); }
+                    temp = cs * A[0] + sn * A[1]; A[1] = -sn * A[0] + cs * A[1]; A[0] = temp;
+                }
+            }
+            jeval = 0;
+        }
+    }
+done:
+    if (nfev_out) *nfev_out = nfev;
+    return info;
+}
+
+
+struct K5Args {
+    const double *locs;      // [S, 3] cm
+    const float *maps;       // [S, S, Hm, Hm] lag maps (NaN = illegal)
+    const float *max_lags, *min_lags, *max_max;  // [S,S], [S,S], [S]
+    int32_t S, Hm, H, n_per_hit;
+    double radius, samples_per_cm, sr, c_cm;
+    const int32_t *sensors;  // [H, 3] sensor index of each onset, or null: (0, 1, 2)
+    const int32_t *onsets;   // [H, onset_stride]; the first three entries are used
+    int32_t onset_stride;
+    double *xy;              // [H, 2], NaN when not located
+    int32_t *status;         // [H]
+};
+
+__global__ void k5_locate(const K5Args a) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= a.H) return;
+    const int S = a.S, Hm = a.Hm;
+    int sen[3]; long long on[3];
+    for (int i = 0; i < 3; ++i) {
+        sen[i] = a.sensors ? a.sensors[3 * h + i] : i;
+        on[i] = a.onsets[static_cast<int64_t>(h) * a.onset_stride + i];
+    }
+    // stable argsort of the three onsets
+    int ord[3] = {0, 1, 2};
+    for (int i = 1; i < 3; ++i) {
+        const int v = ord[i];
+        int j = i - 1;
+        while (j >= 0 && on[ord[j]] > on[v]) { ord[j + 1] = ord[j]; --j; }
+        ord[j + 1] = v;
+    }
+    int s0 = sen[ord[0]], s1 = sen[ord[1]], s2 = sen[ord[2]];
+    long long o0 = on[ord[0]], o1 = on[ord[1]], o2 = on[ord[2]];
+    const long long lag1 = o1 - o0, lag2 = o2 - o0;
+    double out[2] = {__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double(0x7ff8000000000000ll)};
+    int st = 0;
+    const bool valid = s0 >= 0 && s0 < S && s1 >= 0 && s1 < S && s2 >= 0 && s2 < S && s0 != s1 && s0 != s2;
+    if (!valid) st = 5;
+    // multilateration.py:439-441, 397-411 (float32 bounds compared with python ints -> exact in double)
+    if (st == 0 && (static_cast<double>(lag1) > static_cast<double>(a.max_max[s0]) ||
+                    static_cast<double>(lag2) > static_cast<double>(a.max_max[s0]))) st = 1;
+    if (st == 0 && !(static_cast<double>(a.min_lags[s0 * S + s1]) < static_cast<double>(lag1) &&
+                     static_cast<double>(lag1) < static_cast<double>(a.max_lags[s0 * S + s1]))) st = 2;
+    if (st == 0 && !(static_cast<double>(a.min_lags[s0 * S + s2]) < static_cast<double>(lag2) &&
+                     static_cast<double>(lag2) < static_cast<double>(a.max_lags[s0 * S + s2]))) st = 2;
+    if (st == 0) {
+        // is_legal_3d (multilateration.py:413-426): first cell, C-order flatten, unravelled "F"
+        const double tol = 1 * a.samples_per_cm;
+        const float *lm1 = a.maps + static_cast<int64_t>(s0 * S + s1) * Hm * Hm;
+        const float *lm2 = a.maps + static_cast<int64_t>(s0 * S + s2) * Hm * Hm;
+        const double l1lo = lag1 - tol, l1hi = lag1 + tol, l2lo = lag2 - tol, l2hi = lag2 + tol;
+        int kfound = 0;
+        for (int k = 0; k < Hm * Hm; ++k) {
+            const double m1 = lm1[k], m2 = lm2[k];
+            if (m1 < l1hi && m1 > l1lo && m2 < l2hi && m2 > l2lo) { kfound = k; break; }
+        }
+        const int ci = kfound % Hm, cj = kfound / Hm;
+        if (ci == 0 && cj == 0) st = 3;
+        else {
+            double x[2] = {ci - a.radius, cj - a.radius};
+            if (s1 == 1) { s1 = 0; s2 = 1; const long long t = o1; o1 = o2; o2 = t; }  // Q8, multilateration.py:542-544
+            tri_problem q;
+            q.xa = a.locs[3 * s1]; q.ya = a.locs[3 * s1 + 1]; q.za = a.locs[3 * s1 + 2];
+            q.xb = a.locs[3 * s2]; q.yb = a.locs[3 * s2 + 1]; q.zb = a.locs[3 * s2 + 2];
+            q.xo = a.locs[3 * s0]; q.yo = a.locs[3 * s0 + 1]; q.zo = a.locs[3 * s0 + 2];
+            q.da = static_cast<double>(o1 - o0) / a.sr * a.c_cm;  // multilateration.py:563-564
+            q.db = static_cast<double>(o2 - o0) / a.sr * a.c_cm;
+            const int ier = hybrj2(&q, x, 0.01, 20, nullptr);
+            if (ier == 1) { out[0] = x[0]; out[1] = x[1]; }
+            else st = 4;
+        }
+    }
+    a.xy[2 * static_cast<int64_t>(h)] = out[0];
+    a.xy[2 * static_cast<int64_t>(h) + 1] = out[1];
+    a.status[h] = st;
+}
+
+}  // namespace ofp
+
+using namespace ofp;
+
+extern "C" int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                               int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                               const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                               double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
+                               int32_t onset_stride, int32_t n_hits, double *xy_dev, int32_t *status_dev,
+                               void *stream) {
+    OFP_REQUIRE(sensor_xyz_dev && lag_maps_dev && max_lags_dev && min_lags_dev && max_max_dev && hit_onsets_dev &&
+                    xy_dev && status_dev, "null argument");
+    OFP_REQUIRE(n_sensors >= 3 && onset_stride >= 3, "need at least three sensors / onsets per hit");
+    if (n_hits == 0) return OFP_OK;
+    K5Args a;
+    a.locs = sensor_xyz_dev; a.maps = lag_maps_dev; a.max_lags = max_lags_dev; a.min_lags = min_lags_dev;
+    a.max_max = max_max_dev; a.S = n_sensors; a.Hm = map_size; a.H = n_hits; a.n_per_hit = 3;
+    a.radius = radius_cm; a.samples_per_cm = samples_per_cm; a.sr = sr; a.c_cm = c_cm_s;
+    a.sensors = hit_sensors_dev; a.onsets = hit_onsets_dev; a.onset_stride = onset_stride;
+    a.xy = xy_dev; a.status = status_dev;
+    k5_locate<<<(n_hits + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}

@@ -280,3 +280,128 @@ def find_onset_groups(onsets, channels, max_distance: int = 1000, min_channels: 
     if close_channel is not None:
         rows = [r for r in rows if all(r[close_channel] <= r)]
     return np.array(rows, dtype=int) if rows else None
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 / K4: grouping on the device, lag refinement
+# ------------------------------------------------------------------------------------------------
+LAG_NONE = -(2 ** 31)
+_DIRECTION = {None: 0, "up": 1, "down": 2}
+
+
+def find_onset_groups_batch(channels, onsets, counts, n_channels: int, max_distance: int = 1000,
+                            min_channels: int = 3, close_channel: Optional[int] = None,
+                            max_groups: Optional[int] = None):
+    """find_onset_groups for every recording of a batch on the device.
+    channels/onsets [R, cap] int32 and counts [R] int32 as returned by detect_onsets_amplitude_batch.
+    Returns (hit_rec [H] int32, hit_onsets [H, C] int32, n_groups [R] int32): the groups of all
+    recordings concatenated in recording order (rows may contain -1 for a missing channel)."""
+    torch = _lib.require_cuda()
+    R, cap = channels.shape
+    if max_groups is None:
+        max_groups = max(1, cap // max(min_channels, 1))
+    groups = torch.empty((R, max_groups, n_channels), dtype=torch.int32, device="cuda")
+    ng = torch.empty((R,), dtype=torch.int32, device="cuda")
+    check(_lib.lib().ofp_group_onsets(ptr(channels), ptr(onsets), ptr(counts), C.c_int32(R), C.c_int32(cap),
+                                      C.c_int32(n_channels), C.c_int32(max_distance), C.c_int32(min_channels),
+                                      C.c_int32(-1 if close_channel is None else close_channel),
+                                      C.c_int32(max_groups), ptr(groups), ptr(ng), stream_ptr()))
+    kept = torch.clamp(ng, max=max_groups).to(torch.int64)
+    offsets = torch.cumsum(kept, 0) - kept
+    H = int(kept.sum().item())
+    hit_rec = torch.empty((H,), dtype=torch.int32, device="cuda")
+    hit_on = torch.empty((H, n_channels), dtype=torch.int32, device="cuda")
+    if H:
+        check(_lib.lib().ofp_compact_groups(ptr(groups), ptr(ng), ptr(offsets), C.c_int32(R), C.c_int32(max_groups),
+                                            C.c_int32(n_channels), ptr(hit_rec), ptr(hit_on), stream_ptr()))
+    return hit_rec, hit_on, ng
+
+
+def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 0, onset_direction=None,
+                     take_abs: bool = False, zero_left: bool = False, normalization_cutoff: int = 10,
+                     onset_tolerance: int = 30, shift_onsets: int = 0, max_section: Optional[int] = None):
+    """fix_onsets (detection.py:373-451) for H onset groups in one launch.
+    audio [R, N, C] float32 (device or numpy); hit_rec [H] int32 or None (hit h in recording h);
+    hit_onsets [H, C] int32.  Returns (onsets [H, C], lags [H, C], status [H]) device tensors."""
+    torch = _lib.require_cuda()
+    audio = _to_dev(audio, torch)
+    R, N, Cn = audio.shape
+    hit_onsets = hit_onsets.to(device="cuda", dtype=torch.int32).contiguous()
+    H = hit_onsets.shape[0]
+    if hit_rec is not None:
+        hit_rec = hit_rec.to(device="cuda", dtype=torch.int32).contiguous()
+    look = normalization_cutoff + onset_tolerance
+    if max_section is None:
+        if H:
+            valid = hit_onsets.clamp(min=0)
+            span = int((valid.max(1).values - valid.min(1).values).max().item())
+        else:
+            span = 0
+        max_section = span + 2 * look + 1
+    out = torch.empty_like(hit_onsets)
+    lags = torch.empty_like(hit_onsets)
+    status = torch.empty((H,), dtype=torch.int32, device="cuda")
+    check(_lib.lib().ofp_fix_onsets(ptr(audio), C.c_int64(N), C.c_int64(audio.stride(0)), C.c_int32(Cn),
+                                    ptr(hit_rec), ptr(hit_onsets), C.c_int32(H), C.c_int32(filter_size),
+                                    C.c_int32(d), C.c_int32(_DIRECTION[onset_direction]), C.c_int32(bool(take_abs)),
+                                    C.c_int32(bool(zero_left)), C.c_int32(normalization_cutoff),
+                                    C.c_int32(onset_tolerance), C.c_int32(shift_onsets), C.c_int32(max_section),
+                                    ptr(out), ptr(lags), ptr(status), stream_ptr()))
+    return out, lags, status
+
+
+def fix_onsets(audio: np.ndarray, onsets: np.ndarray, filter_size: int = 5, d: int = 0, onset_direction=None,
+               take_abs: bool = False, zero_left: bool = False, normalization_cutoff: int = 10,
+               onset_tolerance: int = 30, shift_onsets: int = 0, return_status: bool = False):
+    """Drop-in for detection.fix_onsets (detection.py:373-451): audio [N, C], onsets [G, C] -> [G, C].
+    Where the reference raises (ValueError in adjust_onset; negative section start, Q6) this
+    raises ValueError too, unless return_status=True, in which case (onsets, status, lags) is returned
+    with the affected groups flagged."""
+    torch = _lib.require_cuda()
+    on = torch.from_numpy(np.ascontiguousarray(onsets).astype(np.int32))
+    rec = torch.zeros(len(onsets), dtype=torch.int32)
+    out, lags, status = fix_onsets_batch(audio[None], rec, on, filter_size, d, onset_direction, take_abs, zero_left,
+                                         normalization_cutoff, onset_tolerance, shift_onsets)
+    out, lags, status = out.cpu().numpy().astype(np.int64), lags.cpu().numpy(), status.cpu().numpy()
+    if return_status:
+        return out, status, lags
+    if (status != 0).any():
+        bad = np.nonzero(status)[0]
+        raise ValueError(f"fix_onsets: the reference raises on groups {bad.tolist()} (status {status[bad].tolist()})")
+    return out
+
+
+def cross_correlation_lag(x: np.ndarray, y: np.ndarray, onsets=None, legal_lags=None, d: int = 0,
+                          normalization_cutoff: int = 10, onset_tolerance: int = 50, take_abs: bool = False):
+    """Drop-in for detection.cross_correlation_lag (detection.py:195-268) -> int or None."""
+    torch = _lib.require_cuda()
+    xd = _to_dev(np.ascontiguousarray(x, dtype=np.float32)[None], torch)
+    yd = _to_dev(np.ascontiguousarray(y, dtype=np.float32)[None], torch)
+    use_legal = legal_lags is not None
+    pair = legal_lags if use_legal else (onsets if onsets is not None else None)
+    if pair is None:
+        raise UnboundLocalError("max_adjust")  # what the reference does without onsets / legal_lags
+    o = torch.tensor([[int(pair[0]), int(pair[1])]], dtype=torch.int32, device="cuda")
+    out = torch.empty((1,), dtype=torch.int32, device="cuda")
+    check(_lib.lib().ofp_cross_correlation_lag(ptr(xd), ptr(yd), C.c_int32(1), C.c_int32(xd.shape[1]), C.c_int32(d),
+                                               C.c_int32(bool(take_abs)), C.c_int32(use_legal),
+                                               C.c_int32(normalization_cutoff), C.c_int32(onset_tolerance), ptr(o),
+                                               ptr(out), stream_ptr()))
+    r = int(out.item())
+    return None if r == LAG_NONE else r
+
+
+def adjust_onset(onsets, x: np.ndarray, y: np.ndarray, new_lag: int):
+    """Drop-in for detection.adjust_onset (detection.py:299-352) -> (change_x, change_y)."""
+    torch = _lib.require_cuda()
+    xd = _to_dev(np.ascontiguousarray(x, dtype=np.float32)[None], torch)
+    yd = _to_dev(np.ascontiguousarray(y, dtype=np.float32)[None], torch)
+    o = torch.tensor([[int(onsets[0]), int(onsets[1])]], dtype=torch.int32, device="cuda")
+    nl = torch.tensor([int(new_lag)], dtype=torch.int32, device="cuda")
+    out = torch.empty((1, 2), dtype=torch.int32, device="cuda")
+    check(_lib.lib().ofp_adjust_onset(ptr(xd), ptr(yd), C.c_int32(1), C.c_int32(xd.shape[1]), ptr(o), ptr(nl),
+                                      ptr(out), stream_ptr()))
+    a, b = out[0].cpu().tolist()
+    if a == LAG_NONE:
+        raise ValueError("operands could not be broadcast together (adjust_onset, detection.py:335)")
+    return a, b
