@@ -332,12 +332,16 @@ def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 
         hit_rec = hit_rec.to(device="cuda", dtype=torch.int32).contiguous()
     look = normalization_cutoff + onset_tolerance
     if max_section is None:
+        span = 0
         if H:
-            valid = hit_onsets.clamp(min=0)
-            span = int((valid.max(1).values - valid.min(1).values).max().item())
-        else:
-            span = 0
+            complete = (hit_onsets >= 0).all(1)
+            if bool(complete.any()):
+                rows = hit_onsets[complete]
+                span = int((rows.max(1).values - rows.min(1).values).max().item())
         max_section = span + 2 * look + 1
+        # shared-memory budget of one CTA; longer sections are flagged OFP_FIX_TOO_LONG
+        budget = (200 * 1024 - 128) // (16 + 8 * Cn)
+        max_section = min(max_section, budget)
     out = torch.empty_like(hit_onsets)
     lags = torch.empty_like(hit_onsets)
     status = torch.empty((H,), dtype=torch.int32, device="cuda")
