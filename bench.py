@@ -199,21 +199,20 @@ def run_ours(args):
 
     R, N = args.recordings, int(args.seconds * SR)
     nb = N // BLOCK
+    from onset_fingerprinting_b200 import pipeline
+
     x = synth.drum_batch_device(R, N, seed=1234, rec_offset=rank * R)
-    det = detection.BatchedOnsetDetector(R, N_CH, BLOCK, sr=SR)
-    cap = det.default_cap(N)
-    out = (torch.empty((R, cap), dtype=torch.int32, device="cuda"),
-           torch.empty((R, cap), dtype=torch.int32, device="cuda"),
-           torch.empty((R,), dtype=torch.int32, device="cuda"),
-           None if args.no_rel else torch.empty((R, nb * BLOCK, N_CH), dtype=torch.float32, device="cuda"))
+    hp = pipeline.HotPath(R, N_CH, synth.SENSORS_3MIC, medium="air", sr=SR, block_size=BLOCK)
+    det = hp.det
     warm_n = int(0.5 * SR)
     launches = 0
+    LAUNCHES_PER_STEP = 6  # k1_reset, k1_detect, k3_group, k3_compact, k4_fix, k5_locate (+ torch cumsum/clamp)
+    last = {}
 
     def step():
         nonlocal launches
-        det.reset()
-        det.detect_offline(x, warm_n, out=out)
-        launches += 2
+        last["hits"] = hp.run(x, return_rel=not args.no_rel, warm_n=warm_n)
+        launches += LAUNCHES_PER_STEP
 
     def barrier():
         if dist is not None:
@@ -233,9 +232,13 @@ def run_ours(args):
             s.record()
             det.reset()
             k0.record()
-            det.detect_offline(x, warm_n, out=out)
+            ch_, ix_, cnt_, rel_ = det.detect_offline(x, warm_n, out=hp._out)
             k1.record()
-            launches += 2
+            hit_rec, hit_on, _ = detection.find_onset_groups_batch(ch_, ix_, cnt_, N_CH, **hp.group_kw)
+            fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on, max_section=1000 + 2 * 40 + 1)
+            xy, lstat = hp.ml.locate_batch(fixed)
+            last["hits"] = pipeline.HitBatch(hit_rec, hit_on, fixed, lags, fstat, xy, lstat, cnt_, rel_)
+            launches += LAUNCHES_PER_STEP
         end = torch.cuda.Event(enable_timing=True)
         end.record()
         barrier()
@@ -250,7 +253,16 @@ def run_ours(args):
     units_per_step = R * nb * BLOCK * N_CH * world  # channel-samples through the main loop
     value = units_per_step / (ms_per_step / 1e3)
 
-    n_onsets = int(out[2].sum().item())
+    hb = last["hits"]
+    n_onsets = int(hb.onset_counts.sum().item())
+    n_hits = int(hb.rec.shape[0])
+    n_located = int((hb.loc_status == 0).sum().item())
+    if dist is not None:
+        t = torch.tensor([n_onsets, n_hits, n_located], device="cuda")
+        dist.all_reduce(t)
+        n_onsets, n_hits, n_located = (int(v) for v in t.tolist())
+    else:
+        n_onsets, n_hits, n_located = n_onsets, n_hits, n_located
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -275,7 +287,9 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, R), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clk.summary(), "onsets_per_step": n_onsets * world,
+            "gpu_launches": launches, "clocks": clk.summary(), "onsets_per_step": n_onsets,
+            "hits_per_step": n_hits, "located_hits_per_step": n_located,
+            "localised_hits_per_sec": n_located / (ms_per_step / 1e3),
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
         }
     if dist is not None:
