@@ -209,9 +209,19 @@ def run_ours(args):
     LAUNCHES_PER_STEP = 6  # k1_reset, k1_detect, k3_group, k3_compact, k4_fix, k5_locate (+ torch cumsum/clamp)
     last = {}
 
+    def gather(hb):
+        """N > 1: every rank receives all per-hit records (the path's only collective)."""
+        if dist is not None:
+            from onset_fingerprinting_b200 import parallel
+
+            recs = parallel.pack_records(hb.rec, hb.fixed, hb.lags, hb.xy, hb.fix_status, hb.loc_status,
+                                         rec_offset=rank * R)
+            last["all_records"] = parallel.gather_records(recs)
+
     def step():
         nonlocal launches
         last["hits"] = hp.run(x, return_rel=not args.no_rel, warm_n=warm_n)
+        gather(last["hits"])
         launches += LAUNCHES_PER_STEP
 
     def barrier():
@@ -238,6 +248,7 @@ def run_ours(args):
             fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on, max_section=1000 + 2 * 40 + 1)
             xy, lstat = hp.ml.locate_batch(fixed)
             last["hits"] = pipeline.HitBatch(hit_rec, hit_on, fixed, lags, fstat, xy, lstat, cnt_, rel_)
+            gather(last["hits"])
             launches += LAUNCHES_PER_STEP
         end = torch.cuda.Event(enable_timing=True)
         end.record()

@@ -1,0 +1,56 @@
+"""Multi-GPU plumbing: one process per GPU, recordings / hits sharded by rank, no data-path
+collective; the only exchange is the gather of fixed-size per-hit records at the end
+(SURVEY.md section 8e).  The reference has no distributed code at all; this is the B200-box
+equivalent of running its notebooks on 8 machines and concatenating the result tables."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items for `rank`; sizes differ by at most one."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def pack_records(rec, fixed, lags, xy, fix_status, loc_status, rec_offset: int = 0) -> torch.Tensor:
+    """[H, 2C + 4] int64 records: global recording id, fix status, location status, C onsets, C lags,
+    then x and y bit-cast to int64."""
+    H, C = fixed.shape
+    out = torch.empty((H, 2 * C + 5), dtype=torch.int64, device=fixed.device)
+    out[:, 0] = rec.long() + rec_offset
+    out[:, 1] = fix_status.long()
+    out[:, 2] = loc_status.long()
+    out[:, 3:3 + C] = fixed.long()
+    out[:, 3 + C:3 + 2 * C] = lags.long()
+    out[:, 3 + 2 * C:] = xy.contiguous().view(torch.int64)
+    return out
+
+
+def unpack_records(records: torch.Tensor, n_channels: int) -> dict:
+    C = n_channels
+    return {
+        "rec": records[:, 0], "fix_status": records[:, 1], "loc_status": records[:, 2],
+        "fixed": records[:, 3:3 + C], "lags": records[:, 3 + C:3 + 2 * C],
+        "xy": records[:, 3 + 2 * C:].contiguous().view(torch.float64),
+    }
+
+
+def gather_records(records: torch.Tensor, group=None) -> torch.Tensor:
+    """All ranks receive every rank's records, concatenated in rank order.  One all_gather of the
+    counts, one all_gather of the padded record blocks (NCCL over NVLink on the box, gloo in tests)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return records
+    world = dist.get_world_size(group)
+    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c.item()) for c in counts]
+    width = records.shape[1]
+    padded = torch.zeros((max(max(counts), 1), width), dtype=records.dtype, device=records.device)
+    padded[: records.shape[0]] = records
+    blocks = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(blocks, padded, group=group)
+    return torch.cat([b[:c] for b, c in zip(blocks, counts)], 0)
