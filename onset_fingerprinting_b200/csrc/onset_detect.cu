@@ -488,6 +488,10 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
     }
 }
 
+}  // namespace ofp
+#include "onset_detect_ws.cuh"
+namespace ofp {
+
 __global__ void k1_reset(DetState st, int64_t n, float floor_db) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (i >= n) return;
@@ -531,17 +535,17 @@ static int env_int(const char *name, int dflt) {
 // Tile length: T*C floats per recording row must be a multiple of 4 (16-byte TMA rows), at most 256
 // (TMA box limit) and, if possible, == roundup4(C) (mod 32) so that the G rows of a stage start in
 // distinct shared-memory banks.
-static int pick_tile(int C) {
+static int pick_tile(int C, int tcap = 64, int multiple = 1) {
     const int forced = env_int("OFP_K1_TILE", 0);
-    if (forced > 0 && (forced * C) % 4 == 0 && forced * C <= 256) return forced;
+    if (forced > 0 && (forced * C) % 4 == 0 && forced * C <= 256 && forced % multiple == 0) return forced;
     const int want = ((C + 3) / 4 * 4) % 32;
-    const int tmax = std::min(64, 256 / C);
+    const int tmax = std::min(tcap, 256 / C);
     int best = 0;
     for (int t = tmax; t >= 4; --t)
-        if ((t * C) % 4 == 0 && (t * C) % 32 == want) { best = t; break; }
+        if (t % multiple == 0 && (t * C) % 4 == 0 && (t * C) % 32 == want) { best = t; break; }
     if (!best)
         for (int t = tmax; t >= 1; --t)
-            if ((t * C) % 4 == 0) { best = t; break; }
+            if (t % multiple == 0 && (t * C) % 4 == 0) { best = t; break; }
     return best;
 }
 
@@ -599,6 +603,40 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     }
     { int rc = upload_tables(); if (rc != OFP_OK) return rc; }
     const int grid = (a.R + a.G - 1) / a.G;
+    // ---- warp-specialised kernel (default): needs TMA-able input and a block size divisible by 4 ----
+    if (tma_ok && B % 4 == 0 && env_int("OFP_K1_WS", 1)) {
+        WsCfg w;
+        w.CH = B % 16 == 0 ? 16 : (B % 8 == 0 ? 8 : 4);
+        w.NDB = std::max(2, std::min(WS_MAX_NDB, env_int("OFP_K1_NDB", 3)));
+        w.NRS = B / w.CH + std::max(1, env_int("OFP_K1_SLACK", 1));
+        w.row = a.G * C;
+        K1Args b = a;
+        b.T = pick_tile(C, env_int("OFP_K1_WS_TILECAP", 16), 4);
+        if (b.T > 0 && w.NRS <= WS_MAX_NRS) {
+            b.TC = b.T * C;
+            b.nst = std::max(2, std::min(4, env_int("OFP_K1_STAGES", 2)));
+            const int sb = (b.G * b.TC * 4 + 127) / 128 * 128;
+            b.stage_floats = sb / 4;
+            w.off_x = WS_OFF_DATA;
+            w.off_db = w.off_x + b.nst * sb;
+            w.off_rel = (w.off_db + w.NDB * w.CH * w.row * 4 + 15) / 16 * 16;
+            const size_t smem_ws = static_cast<size_t>(w.off_rel) + static_cast<size_t>(w.NRS) * w.CH * w.row * 4;
+            if (smem_ws <= 227 * 1024 && smem_ws >= static_cast<size_t>(w.off_rel) + 3 * 512) {
+                CUtensorMap tm2;
+                const uint64_t stride1 = a.R == 1 ? static_cast<uint64_t>((n_samples * C * 4 + 15) / 16 * 16)
+                                                  : static_cast<uint64_t>(rec_stride) * 4;
+                int rc = encode_tmap_2d_f32(&tm2, x, static_cast<uint64_t>(n_samples) * C, static_cast<uint64_t>(a.R),
+                                            stride1, static_cast<uint32_t>(b.TC), static_cast<uint32_t>(b.G));
+                if (rc != OFP_OK) return rc;
+                auto kws = p.use_hp ? k1_detect_ws<true> : k1_detect_ws<false>;
+                OFP_CUDA_CHECK(cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(smem_ws)));
+                kws<<<grid, WS_THREADS, smem_ws, stream>>>(tm2, b, w);
+                OFP_CUDA_CHECK(cudaGetLastError());
+                return OFP_OK;
+            }
+        }
+    }
     auto kern = p.use_hp ? (tma_ok ? k1_detect<true, true> : k1_detect<true, false>)
                          : (tma_ok ? k1_detect<false, true> : k1_detect<false, false>);
     OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
