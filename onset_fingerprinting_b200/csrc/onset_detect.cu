@@ -200,6 +200,96 @@ __device__ __forceinline__ float to_amp_fast(float r, float ceil_amp, uint32_t e
     return amp_of(ad, ceil_amp);
 }
 
+// Step-major ("vertical") forms of to_db_fast / to_amp_fast for U independent samples: every
+// elementary operation is issued for all U samples before the next one, so the instruction stream
+// handed to ptxas is already interleaved.  (Written sample-major, ptxas keeps the U dependency
+// chains mostly back to back and the warp stalls on every dependent FP64 op -- ncu, profiles/.)
+template <int U>
+__device__ __forceinline__ void to_db_vec(const float (&h)[U], float floor_db, uint32_t logtab, const MathConst &mc,
+                                          float (&db)[U], float (&v_out)[U], uint32_t &redo_mask, int bit0) {
+    uint32_t ix[U], tmp[U], iz[U];
+    int32_t kexp[U];
+    double z[U], invc[U], logc[U], r[U], r2[U], p01[U], p23[U], pp[U], base[U], ld[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { v_out[u] = fabsf(__fadd_rn(h[u], 1e-10f)); ix[u] = __float_as_uint(v_out[u]); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) tmp[u] = ix[u] - OFP_LOG_OFF;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        lds_2f64(logtab + ((tmp[u] >> (23 - OFP_LOG_N - 4)) & (((1u << OFP_LOG_N) - 1u) << 4)), invc[u], logc[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { kexp[u] = static_cast<int32_t>(tmp[u]) >> 23; iz[u] = ix[u] - (tmp[u] & 0xff800000u); }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        z[u] = __hiloint2double(static_cast<int>((iz[u] >> 3) + 0x38000000u), static_cast<int>(iz[u] << 29));
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = __fma_rn(z[u], invc[u], -1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) base[u] = __fma_rn(static_cast<double>(kexp[u]), mc.log10_2, logc[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) r2[u] = __dmul_rn(r[u], r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p01[u] = __fma_rn(r[u], mc.a2, mc.a1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p23[u] = __fma_rn(r[u], mc.a4, mc.a3);
+#pragma unroll
+    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(r2[u], mc.a5, p23[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(r2[u], pp[u], p01[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) ld[u] = __fma_rn(r[u], pp[u], base[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool redo = ((ix[u] - 0x00800000u) >= 0x7f000000u) | near_f32_midpoint(ld[u], 1u << 13);
+        redo_mask |= (redo ? 1u : 0u) << (bit0 + u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) db[u] = db_of(ld[u], floor_db);
+}
+
+template <int U>
+__device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp, uint32_t exptab, const MathConst &mc,
+                                           float (&amp)[U], uint32_t &redo_mask, int bit0) {
+    float q0[U], q[U];
+    double t[U], kd0[U], kd[U], rr[U], r2[U], p01[U], p23[U], pp[U], sc[U], y[U], ad[U];
+    int32_t ki[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q0[u] = __fmul_rn(dr[u], 0.05f);
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = __fmaf_rn(__fmaf_rn(-20.0f, q0[u], dr[u]), 0.05f, q0[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) t[u] = __dmul_rn(static_cast<double>(q[u]), mc.log2_10);
+#pragma unroll
+    for (int u = 0; u < U; ++u) kd0[u] = __fma_rn(t[u], 32.0, mc.shift);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { ki[u] = __double2loint(kd0[u]); kd[u] = __dsub_rn(kd0[u], mc.shift); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) sc[u] = lds_f64(exptab + ((ki[u] & 31) << 3));
+#pragma unroll
+    for (int u = 0; u < U; ++u) rr[u] = __fma_rn(kd[u], -0.03125, t[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) r2[u] = __dmul_rn(rr[u], rr[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p01[u] = __fma_rn(rr[u], mc.e2, mc.e1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p23[u] = __fma_rn(rr[u], mc.e4, mc.e3);
+#pragma unroll
+    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(r2[u], mc.e5, p23[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(r2[u], pp[u], p01[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) y[u] = __fma_rn(__dmul_rn(sc[u], rr[u]), pp[u], sc[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) ad[u] = __hiloint2double(__double2hiint(y[u]) + ((ki[u] >> 5) << 20), __double2loint(y[u]));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool redo = !(fabsf(q[u]) < 30.0f) | near_f32_midpoint(ad[u], 1u << 8);
+        redo_mask |= (redo ? 1u : 0u) << (bit0 + u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) amp[u] = amp_of(ad[u], ceil_amp);
+}
+
 // envelope_follower.c:38-52
 __device__ __forceinline__ void minmax_step(Lane &L, const Coef &k, float r) {
     const float nm = __fadd_rn(__fmul_rn(L.mn, k.iamin), __fmul_rn(r, k.amin));
@@ -262,6 +352,46 @@ __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint3
     }
 }
 
+// Straight-line, branch-free form of chunk<> for U samples: one large basic block that ptxas can
+// software-pipeline (needs __launch_bounds__(32, 1): with a higher occupancy target ptxas keeps
+// the dependency chains back to back to save registers).  Every rare case is only FLAGGED:
+//   - dB / 10**x results that need the exact slow path (special input, float32 rounding boundary),
+//   - follower steps in the sliver 0 < |t| < 2^-22 where the float32 shortcut is not proven exact.
+// Returns true when this lane hit a flag; the caller then restores the lane state and re-runs the
+// samples through chunk<> (exact, with branches).
+template <bool USE_HP, int U>
+__device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
+                                           bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
+                                           const MathConst &mc) {
+    float h[U], db[U], dr[U], amp[U], aux[U];
+    uint32_t flags = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float x = lds_f32(xs + u * step);
+        h[u] = USE_HP ? hp_step(L, k, x) : x;
+    }
+    to_db_vec<U>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
+    bool sliver = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float t1 = __fsub_rn(db[u], L.yf), t2 = __fsub_rn(db[u], L.ys);
+        sliver |= (fabsf(t1) < 0x1p-22f && t1 != 0.0f) | (fabsf(t2) < 0x1p-22f && t2 != 0.0f);
+        const float d1 = __fadd_rn(t1, 1e-10f), d2 = __fadd_rn(t2, 1e-10f);
+        L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
+        L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
+        dr[u] = __fsub_rn(L.yf, L.ys);
+    }
+    to_amp_vec<U>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (do_minmax) minmax_step(L, k, amp[u]);
+        L.bmax = fmaxf(L.bmax, amp[u]);
+        L.bmin = fminf(L.bmin, amp[u]);
+        if (store) sts_f32(rs + u * step, amp[u]);
+    }
+    return sliver | (flags != 0);
+}
+
 __device__ double g_logtab[2 << OFP_LOG_N];
 __device__ double g_exptab[32];
 
@@ -287,8 +417,10 @@ __device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch
     __syncwarp();
 }
 
+constexpr int KU = 8;  // samples per straight-line chunk of the single-warp kernel
+
 template <bool USE_HP, bool USE_TMA>
-__global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
+__global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
     double *logtab = reinterpret_cast<double *>(smem + 128);
@@ -394,9 +526,17 @@ __global__ void __launch_bounds__(32) k1_detect(const __grid_constant__ CUtensor
                     const uint32_t xp = sp + j * step;
                     const uint32_t rp = rcol_s + kpos * step;
                     int i = 0;
-                    for (; i + 4 <= seg; i += 4)
-                        chunk<USE_HP, 4>(L, kf, xp + i * step, rp + i * step, step, do_minmax, in_group, logtab_s,
-                                         exptab_s, mc);
+                    for (; i + KU <= seg; i += KU) {
+                        const Lane saved = L;
+                        const bool bad = chunk_fast<USE_HP, KU>(L, kf, xp + i * step, rp + i * step, step, do_minmax,
+                                                                in_group, logtab_s, exptab_s, mc);
+                        if (__any_sync(0xffffffffu, bad)) {  // rare: exact re-run of these samples
+                            L = saved;
+                            for (int e = 0; e < KU; ++e)
+                                chunk<USE_HP, 1>(L, kf, xp + (i + e) * step, rp + (i + e) * step, step, do_minmax,
+                                                 in_group, logtab_s, exptab_s, mc);
+                        }
+                    }
                     for (; i < seg; ++i)
                         chunk<USE_HP, 1>(L, kf, xp + i * step, rp + i * step, step, do_minmax, in_group, logtab_s,
                                          exptab_s, mc);
@@ -535,17 +675,24 @@ static int env_int(const char *name, int dflt) {
 // Tile length: T*C floats per recording row must be a multiple of 4 (16-byte TMA rows), at most 256
 // (TMA box limit) and, if possible, == roundup4(C) (mod 32) so that the G rows of a stage start in
 // distinct shared-memory banks.
+// Tile length T (samples per TMA box row).  Constraints: T*C*4 bytes a multiple of 16 (TMA), T*C <= 256
+// (box limit), T a multiple of `multiple` (so that chunks never straddle tiles).  Among those, prefer
+// the T whose row pitch T*C spreads the G rows of a stage over the most shared-memory banks (the
+// per-sample LDS of a warp touches one word per lane: rows starting in the same bank conflict), then
+// the longest.
 static int pick_tile(int C, int tcap = 64, int multiple = 1) {
     const int forced = env_int("OFP_K1_TILE", 0);
     if (forced > 0 && (forced * C) % 4 == 0 && forced * C <= 256 && forced % multiple == 0) return forced;
-    const int want = ((C + 3) / 4 * 4) % 32;
+    const int G = 32 / C;
     const int tmax = std::min(tcap, 256 / C);
-    int best = 0;
-    for (int t = tmax; t >= 4; --t)
-        if (t % multiple == 0 && (t * C) % 4 == 0 && (t * C) % 32 == want) { best = t; break; }
-    if (!best)
-        for (int t = tmax; t >= 1; --t)
-            if (t % multiple == 0 && (t * C) % 4 == 0) { best = t; break; }
+    int best = 0, best_deg = 1 << 30;
+    for (int t = multiple; t <= tmax; t += multiple) {
+        if ((t * C) % 4 != 0) continue;
+        int count[32] = {0}, deg = 0;
+        for (int g = 0; g < G; ++g)
+            for (int c = 0; c < C; ++c) deg = std::max(deg, ++count[(g * t * C + c) % 32]);
+        if (deg < best_deg || (deg == best_deg && t > best)) { best = t; best_deg = deg; }
+    }
     return best;
 }
 
@@ -576,7 +723,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.on_ch = on_ch; a.on_idx = on_idx; a.on_cnt = on_cnt; a.cap = cap;
     a.R = static_cast<int32_t>(det->n_streams);
     a.G = 32 / C;
-    a.T = pick_tile(C);
+    a.T = pick_tile(C, env_int("OFP_K1_TILECAP", 48), (B % KU == 0) ? KU : 1);
     OFP_REQUIRE(a.T > 0, "no valid tile length for %d channels", C);
     a.TC = a.T * C;
     a.nst = std::max(2, std::min(8, env_int("OFP_K1_STAGES", 2)));
@@ -604,7 +751,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     { int rc = upload_tables(); if (rc != OFP_OK) return rc; }
     const int grid = (a.R + a.G - 1) / a.G;
     // ---- warp-specialised kernel (default): needs TMA-able input and a block size divisible by 4 ----
-    if (tma_ok && B % 4 == 0 && env_int("OFP_K1_WS", 1)) {
+    if (tma_ok && B % 4 == 0 && env_int("OFP_K1_WS", 0)) {
         WsCfg w;
         w.CH = B % 16 == 0 ? 16 : (B % 8 == 0 ? 8 : 4);
         w.NDB = std::max(2, std::min(WS_MAX_NDB, env_int("OFP_K1_NDB", 3)));

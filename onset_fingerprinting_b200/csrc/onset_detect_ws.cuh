@@ -42,17 +42,17 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(200000u)  // suspend-time hint (ns): sleep instead of spinning
             : "memory");
     } while (!done);
 }
 
 template <bool USE_HP>
-__global__ void __launch_bounds__(WS_THREADS) k1_detect_ws(const __grid_constant__ CUtensorMap tmap, const K1Args a,
+__global__ void __launch_bounds__(WS_THREADS, 7) k1_detect_ws(const __grid_constant__ CUtensorMap tmap, const K1Args a,
                                                            const WsCfg w) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -145,20 +145,21 @@ __global__ void __launch_bounds__(WS_THREADS) k1_detect_ws(const __grid_constant
                 for (; j + 4 <= tl && t0 + j < env_len; j += 4) {
                     if (kc == 0) mbar_wait_s(sbase + WS_OFF_DBEMPTY + 8u * slot, par);
                     float h[4], db[4], aux[4];
-                    bool redo[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float x = lds_f32(sp + (j + u) * step);
                         h[u] = USE_HP ? hp_step(L, kf, x) : x;
                     }
                     const uint32_t dst = sbase + w.off_db + (static_cast<uint32_t>(slot * CH + kc)) * rowb + 4u * li;
+                    uint32_t redo4 = 0;
+                    to_db_vec<4>(h, kf.floor_db, logtab_s, mc, db, aux, redo4, 0);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        db[u] = to_db_fast(h[u], kf.floor_db, logtab_s, mc, aux[u], redo[u]);
                         // a flagged sample leaves |h + 1e-10| in the ring; it is fixed up when the chunk closes
-                        if (redo[u]) { db[u] = aux[u]; fix_mask |= 1u << (kc + u); }
+                        if ((redo4 >> u) & 1u) db[u] = aux[u];
                         if (in_group) sts_f32(dst + u * rowb, db[u]);
                     }
+                    fix_mask |= redo4 << kc;
                     kc += 4;
                     if (kc == CH) {
                         if (__any_sync(0xffffffffu, fix_mask != 0)) {  // rare: exact log10 out of line
@@ -224,12 +225,16 @@ __global__ void __launch_bounds__(WS_THREADS) k1_detect_ws(const __grid_constant
             }
             uint32_t fix = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (i < CH) {
-                    float qq; bool redo;
-                    float amp = to_amp_fast(dr[i], kf.ceil_amp, exptab_s, mc, qq, redo);
-                    if (redo) { fix |= 1u << i; amp = dr[i]; }  // fixed up below from the follower difference
-                    if (in_group) sts_f32(dst + i * rowb, amp);
+            for (int i0 = 0; i0 < 16; i0 += 4) {
+                if (i0 < CH) {
+                    float d4[4] = {dr[i0], dr[i0 + 1], dr[i0 + 2], dr[i0 + 3]}, a4[4];
+                    to_amp_vec<4>(d4, kf.ceil_amp, exptab_s, mc, a4, fix, i0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        // a flagged sample leaves the follower difference in the ring; fixed up below
+                        const float v = (fix >> (i0 + u)) & 1u ? d4[u] : a4[u];
+                        if (in_group) sts_f32(dst + (i0 + u) * rowb, v);
+                    }
                 }
             }
             if (__any_sync(0xffffffffu, fix != 0)) {  // rare: exact 10**x out of line
