@@ -103,6 +103,18 @@ int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, i
                             int64_t n_samples, int64_t warm_n, float *rel_host, int32_t *on_channel_host,
                             int32_t *on_sample_host, int32_t *on_count_host, int32_t cap);
 
+/* backtrack_onsets (detection.py:800-825; C twin envelope_follower.c:59-85) for all onsets of a
+ * batch.  rel_dev [R, n_rows, C] is the relative envelope in time order.
+ *   streaming = 0: rel_dev is the whole output of ofp_detect_offline, on_sample_dev holds absolute
+ *                  samples and is rewritten in place;
+ *   streaming = 1: rel_dev holds the last n_rows rows ending with the current block (the reference's
+ *                  CircularArray), on_sample_dev holds deltas within that block.
+ * alpha = float32(2/(smooth+1)), tol = float32((1-alpha)**buffer_size) as in detection.py:722-725. */
+int ofp_backtrack_onsets(const float *rel_dev, int64_t rec_stride, int64_t n_rows, int32_t n_channels,
+                         int32_t block_size, int32_t buffer_size, float alpha, float tol, int32_t streaming,
+                         const int32_t *on_channel_dev, int32_t *on_sample_dev, const int32_t *on_count_dev,
+                         int32_t n_rec, int32_t cap, void *stream);
+
 /* Signature twins of the ctypes DLL (envelope_follower.c:6,27), device pointers.
  *   ar_envelope:  x,y [num_samples, size]; y's last row is the carried state on entry.
  *   minmax_envelope: x [n_samples, n_channels]; min/max [n_channels] in/out. */

@@ -667,6 +667,42 @@ __global__ void k_minmax_envelope(const float *x, float *mnp, float *mxp, float 
     mnp[c] = mn; mxp[c] = mx;
 }
 
+// backtrack_onsets (detection.py:800-825 == envelope_follower.c:59-85), one thread per onset.
+// hist: rel rows in time order, [R, n_rows, C].  The ring buffer of the reference holds the last N
+// rows ending with the last row of the onset's block; rows before the start of `hist` read as 0
+// (the reference's buffer starts uninitialised, np.empty).
+__global__ void k_backtrack(const float *hist, int64_t rec_stride, int64_t n_rows, int C, int B, int N, float alpha,
+                            float omba, float tol, int streaming, const int32_t *on_ch, int32_t *on_idx,
+                            const int32_t *on_cnt, int R, int cap) {
+    const int64_t gid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (gid >= static_cast<int64_t>(R) * cap) return;
+    const int r = static_cast<int>(gid / cap), k = static_cast<int>(gid % cap);
+    if (k >= min(on_cnt[r], cap)) return;
+    const int c = on_ch[gid];
+    const int64_t s = on_idx[gid];
+    // last row of the block the onset was detected in
+    const int64_t end_row = streaming ? n_rows - 1 : (s / B + 1) * B - 1;
+    int64_t delta = streaming ? s : s - (s / B) * B;
+    const float *col = hist + r * rec_stride + c;
+    auto at = [&](int64_t i) -> float {  // buffer[-i]
+        const int64_t row = end_row - i + 1;
+        return row >= 0 ? col[row * C] : 0.0f;
+    };
+    int64_t i = B - delta;
+    float cur = at(i);
+    i += 1;
+    float prev = at(i);
+    float ps = __fadd_rn(__fmul_rn(alpha, prev), __fmul_rn(omba, cur));
+    while (cur > ps && fabsf(__fsub_rn(ps, prev)) > tol && i + 1 < N) {
+        delta -= 1;
+        i += 1;
+        cur = ps;
+        prev = at(i);
+        ps = __fadd_rn(__fmul_rn(alpha, prev), __fmul_rn(omba, cur));
+    }
+    on_idx[gid] = static_cast<int32_t>(streaming ? delta : (s / B) * B + delta);
+}
+
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -921,6 +957,22 @@ int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, i
     HOST_CHECK(cudaStreamSynchronize(st));
 #undef HOST_CHECK
     cleanup();
+    return OFP_OK;
+}
+
+int ofp_backtrack_onsets(const float *rel_dev, int64_t rec_stride, int64_t n_rows, int32_t n_channels,
+                         int32_t block_size, int32_t buffer_size, float alpha, float tol, int32_t streaming,
+                         const int32_t *on_channel_dev, int32_t *on_sample_dev, const int32_t *on_count_dev,
+                         int32_t n_rec, int32_t cap, void *stream) {
+    OFP_REQUIRE(rel_dev && on_channel_dev && on_sample_dev && on_count_dev, "null argument");
+    OFP_REQUIRE(buffer_size >= block_size, "backtrack_buffer_size should be at least block_size");
+    if (n_rec == 0 || cap == 0) return OFP_OK;
+    const float omba = static_cast<float>(1.0 - static_cast<double>(alpha));
+    const int64_t total = static_cast<int64_t>(n_rec) * cap;
+    k_backtrack<<<static_cast<unsigned>((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        rel_dev, rec_stride, n_rows, n_channels, block_size, buffer_size, alpha, omba, tol, streaming, on_channel_dev,
+        on_sample_dev, on_count_dev, n_rec, cap);
+    OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;
 }
 

@@ -170,14 +170,35 @@ def detect_onsets_amplitude(x: np.ndarray, block_size: int = 128, floor: float =
                             backtrack_buffer_size: int = 128, backtrack_smooth_size: int = 5, sr: int = 96000):
     """Drop-in for detection.detect_onsets_amplitude (detection.py:19-86): x [N, C] float32 ->
     (channels_flat, onsets_flat, rel[n_blocks*block_size, C])."""
-    if backtrack:
-        raise NotImplementedError("backtrack=True is not on the CUDA path yet")
     ch, ix, cnt, rel = detect_onsets_amplitude_batch(
         x[None], block_size, floor, hipass_freq, fast_ar, slow_ar, on_threshold, off_threshold, cooldown, sr, True)
+    if backtrack:
+        backtrack_onsets_batch(rel, ch, ix, cnt, block_size, backtrack_buffer_size, backtrack_smooth_size)
     k = int(cnt[0].item())
     if k > ch.shape[1]:
         raise OfpError(f"onset buffer overflow ({k} > {ch.shape[1]})")
     return ch[0, :k].cpu().tolist(), ix[0, :k].cpu().tolist(), rel[0].cpu().numpy()
+
+
+def _backtrack_consts(buffer_size: int, smooth_size: int):
+    """detection.py:722-725."""
+    alpha = np.float32(2 / (smooth_size + 1))
+    tol = np.float32((1 - alpha) ** buffer_size)
+    return alpha, tol
+
+
+def backtrack_onsets_batch(rel, channels, samples, counts, block_size: int, buffer_size: int = 128,
+                           smooth_size: int = 5, streaming: bool = False):
+    """AmplitudeOnsetDetector.backtrack_onsets (detection.py:800-825) for every onset of a batch, in place
+    on `samples`.  rel [R, n_rows, C] device tensor (whole envelope, or the last rows when streaming)."""
+    assert block_size <= buffer_size, "backtrack_buffer_size should be at least block_size!"
+    alpha, tol = _backtrack_consts(buffer_size, smooth_size)
+    R, n_rows, Cn = rel.shape
+    check(_lib.lib().ofp_backtrack_onsets(ptr(rel), C.c_int64(rel.stride(0)), C.c_int64(n_rows), C.c_int32(Cn),
+                                          C.c_int32(block_size), C.c_int32(buffer_size), C.c_float(alpha),
+                                          C.c_float(tol), C.c_int32(int(streaming)), ptr(channels), ptr(samples),
+                                          ptr(counts), C.c_int32(R), C.c_int32(channels.shape[1]), stream_ptr()))
+    return samples
 
 
 def detect_onsets(x: np.ndarray, sr: int = 96000, method="amp"):
@@ -197,8 +218,11 @@ class AmplitudeOnsetDetector:
                  fast_ar=(3.0, 383.0), slow_ar=(2205.0, 2205.0), on_threshold: float = 0.5,
                  off_threshold: float = 0.1, cooldown: int = 1323, backtrack: bool = False,
                  backtrack_buffer_size: int = 80, backtrack_smooth_size: int = 5, sr: int = 44100):
+        self.backtrack = backtrack
+        self._bt = (backtrack_buffer_size, backtrack_smooth_size)
+        self._hist = None
         if backtrack:
-            raise NotImplementedError("backtrack=True is not on the CUDA path yet")
+            assert block_size <= backtrack_buffer_size, "backtrack_buffer_size should be at least block_size!"
         self.n_signals, self.block_size = n_signals, block_size
         self.floor, self.on_threshold, self.off_threshold = floor, on_threshold, off_threshold
         self.manual = bool(on_threshold > 1)
@@ -209,6 +233,13 @@ class AmplitudeOnsetDetector:
 
     def __call__(self, x):
         ch, dl, cnt, rel = self._det.process_block(x[None] if x.ndim == 2 else x)
+        if self.backtrack:
+            torch = self._det.torch
+            N = self._bt[0]
+            if self._hist is None:  # the reference's ring starts uninitialised; rows before the start read 0
+                self._hist = torch.zeros((1, N, self.n_signals), dtype=torch.float32, device="cuda")
+            self._hist = torch.cat([self._hist[:, self.block_size:], rel], 1).contiguous()
+            backtrack_onsets_batch(self._hist, ch, dl, cnt, self.block_size, N, self._bt[1], streaming=True)
         k = int(cnt[0].item())
         return ch[0, :k].cpu().numpy().astype(np.int64), dl[0, :k].cpu().numpy().astype(np.int64), rel[0].cpu().numpy()
 

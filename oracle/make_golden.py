@@ -75,6 +75,21 @@ def gen_detect(det):
         print(name, x.shape, len(ch), "onsets")
 
 
+def gen_backtrack(det):
+    """backtrack=True, offline and block by block (RingStub zero-initialised stands in for loopmate)."""
+    x, _ = synth.drum_recording(seconds=2.0, seed=8)
+    out = {"x_sha": sha(x), "env": env()}
+    for tag, kw in (("b128", dict(backtrack_buffer_size=128, backtrack_smooth_size=5)),
+                    ("b256s1", dict(backtrack_buffer_size=256, backtrack_smooth_size=1))):
+        ch, on, _ = det.detect_onsets_amplitude(x, sr=96000, backtrack=True, **kw)
+        out[f"ch_{tag}"] = np.asarray(ch, np.int32)
+        out[f"on_{tag}"] = np.asarray(on, np.int64)
+    ch0, on0, _ = det.detect_onsets_amplitude(x, sr=96000)
+    out["on_plain"] = np.asarray(on0, np.int64)
+    np.savez_compressed(OUT / "backtrack.npz", **out)
+    print("backtrack moved", int((out["on_b128"] != out["on_plain"]).sum()), "of", len(on0))
+
+
 def gen_stream(det):
     """AmplitudeOnsetDetector block by block (realtime/audio.py:39-52 settings), no warm-up."""
     x, _ = synth.drum_recording(seconds=1.5, seed=7, first_hit=20000)
@@ -222,6 +237,7 @@ def main():
     det, ml = rh.load_reference()
     gen_detect(det)
     gen_stream(det)
+    gen_backtrack(det)
     gen_kernels(det)
     gen_fix(det)
     gen_locate(ml)

@@ -148,3 +148,24 @@ def test_host_buffer_entry_point(det, orc):
         c_o, o_o, rel_o = orc.detect_onsets_amplitude(xs[r], sr=96000)
         assert ch[r, :cnt[r]].tolist() == c_o and ix[r, :cnt[r]].tolist() == o_o
         assert rel_err(rel[r], rel_o) <= 1e-5
+
+
+def test_backtrack_offline_and_streaming(det, golden_dir):
+    g = np.load(golden_dir / "backtrack.npz")
+    x, _ = synth.drum_recording(seconds=2.0, seed=8)
+    assert sha(x) == str(g["x_sha"])
+    ch, on, _ = det.detect_onsets_amplitude(x, sr=96000, backtrack=True, backtrack_buffer_size=128,
+                                            backtrack_smooth_size=5)
+    assert ch == g["ch_b128"].tolist() and on == g["on_b128"].tolist()
+    ch, on, _ = det.detect_onsets_amplitude(x, sr=96000, backtrack=True, backtrack_buffer_size=256,
+                                            backtrack_smooth_size=1)
+    assert on == g["on_b256s1"].tolist()
+    # block-by-block detector with the same settings and warm-up gives the same backtracked onsets
+    od = det.AmplitudeOnsetDetector(3, 128, sr=96000, backtrack=True, backtrack_buffer_size=256,
+                                    backtrack_smooth_size=1)
+    od.init_minmax_tracker(x[:48000])
+    got = []
+    for i in range(0, len(x) - 127, 128):
+        c, d, _ = od(x[i:i + 128])
+        got += [i + int(v) for v in d]
+    assert got == g["on_b256s1"].tolist()

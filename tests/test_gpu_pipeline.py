@@ -75,3 +75,50 @@ def test_pipeline_properties_large():
     # match a recomputation from the flat onset list
     per_rec = torch.zeros(R, dtype=torch.int64, device="cuda").index_add_(0, a.rec.long(), a.onsets.sum(1).long())
     assert int(per_rec.sum()) == int(a.onsets.sum())
+
+
+def test_realtime_block_api_matches_reference_semantics():
+    """BlockLocator.detect_hits == the reference's PlayRec.detect_hits loop restated with the oracle:
+    block detector -> sort -> streaming locate."""
+    from onset_fingerprinting_b200.realtime import audio as rt
+    from oracle import oracle as orc
+
+    x, truth = synth.drum_recording(seconds=2.0, seed=11, first_hit=30000)
+    conf = {"sensor_locations": synth.SENSORS_3MIC, "medium": "air", "c": None}
+    bl = rt.BlockLocator(conf)
+    od = orc.Detector(3, 128, **{k: v for k, v in rt.REALTIME_DETECTOR.items()})
+    mo = orc.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+    got, want, pending = [], [], []
+    for i in range(0, len(x) - 127, 128):
+        r = bl.detect_hits(x[i:i + 128])
+        if r is not None:
+            got.append((i // 128, r.x, r.y))
+        c, d, _ = od(x[i:i + 128])
+        for cc, dd in sorted(zip(c.tolist(), d.tolist()), key=lambda t: t[1]):
+            pending.append((int(cc), i + int(dd)))
+            if len(pending) == 3:  # hits are far apart: three detections complete a group
+                sens = [p[0] for p in pending]; ons = [p[1] for p in pending]
+                xy, st = mo.locate_hit(sens, ons)
+                if xy is not None:
+                    want.append((i // 128, xy[0], xy[1]))
+                pending = []
+    assert len(got) > 5
+    assert [g[0] for g in got] == [w[0] for w in want]
+    assert np.allclose([g[1:] for g in got], [w[1:] for w in want], rtol=1e-12)
+
+
+def test_stream_batch_equals_independent_detectors():
+    from onset_fingerprinting_b200.realtime import audio as rt
+    from oracle import oracle as orc
+
+    S = 37
+    xs, _ = synth.drum_batch(S, seconds=0.3, seed=900, first_hit=4000)
+    sb = rt.StreamBatch(S)
+    ods = [orc.Detector(3, 128, **rt.REALTIME_DETECTOR) for _ in range(S)]
+    for i in range(0, xs.shape[1] - 127, 128):
+        ch, dl, cnt, rel = sb.process(xs[:, i:i + 128], return_rel=True)
+        ch, dl, cnt, rel = ch.cpu().numpy(), dl.cpu().numpy(), cnt.cpu().numpy(), rel.cpu().numpy()
+        for s in range(S):
+            c, d, r = ods[s](xs[s, i:i + 128])
+            assert ch[s, :cnt[s]].tolist() == c.tolist() and dl[s, :cnt[s]].tolist() == d.tolist()
+            assert np.array_equal(rel[s], r)
