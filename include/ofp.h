@@ -196,6 +196,27 @@ int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, const float
                     int32_t onset_stride, int32_t n_hits, double *xy_dev, int32_t *status_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K2  spectral-flux onset features -- replaces RecAnalysis.fft / onset_strength
+ *     (realtime/recording.py:273-311) and the STFT half of detect_onsets_spectral (detection.py:96-110)
+ * ------------------------------------------------------------------------------------- */
+
+/* x_dev [R, n_samples, C] float32 -> flux_dev [R, n_frames] float32.  Per frame: channel mean, window,
+ * rFFT(n_fft), then mode 0: 10*log10(max(1e-10, |X|^2)) (optionally clamped at frame max - top_db),
+ * mode 1: |X| * weight[bin]; flux = mean over the n_fft/2+1 bins of max(0, S_j - S_{j-1}).
+ * center = 0: frame j = samples [(j+1)*hop - n_fft, (j+1)*hop) (n_frames = n_samples / hop);
+ * center = 1: frame j centred on j*hop, padded with zeros (reflect = 0) or by reflection (1).
+ * window_dev [n_fft], weight_dev [n_fft/2+1] or NULL. */
+int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                      int32_t n_fft, int32_t hop, int32_t center, int32_t reflect, int32_t mode, float top_db,
+                      const float *window_dev, const float *weight_dev, int32_t n_frames, float *flux_dev,
+                      void *stream);
+/* librosa.util.peak_pick (detection.py:113-121) per row of oe_dev [R, n_frames]: peaks_dev [R, cap],
+ * n_peaks_dev [R]. */
+int ofp_peak_pick(const float *oe_dev, int32_t n_rec, int32_t n_frames, int32_t pre_max, int32_t post_max,
+                  int32_t pre_avg, int32_t post_avg, float delta, int32_t wait, int32_t *peaks_dev,
+                  int32_t *n_peaks_dev, int32_t cap, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Benchmark input: seeded synthetic multi-mic drum audio generated on the device
  * (SURVEY.md section 8d signal model; not a reference function).  x_dev [R, N, C] float32;
  * sensors_xyz_host [C, 3] cm (host); rec_offset = global index of recording 0 of this shard.

@@ -1,0 +1,221 @@
+// K2: spectral-flux onset features (sm_100a).
+//
+// Replaces the per-hop numpy FFT of the reference's realtime analysis -- RecAnalysis.fft /
+// onset_strength (realtime/recording.py:273-311: hann(2048) * mean_c(audio[-2048:]) -> rfft ->
+// |.|^2 -> 10 log10(max(1e-10, .)) -> clamp at max-80 -> mean(max(0, s - s_prev))) -- and the STFT
+// front half of detect_onsets_spectral (detection.py:96-110: |stft(n_fft=256, hop=32)| x per-bin
+// weight -> mean(max(0, dD))).  librosa and loopmate are absent from the reference tree, so this
+// row is a restatement of their documented behaviour ("parity unpinned" for K2).
+//
+// One CTA walks F consecutive frames of one recording: the frame is gathered (channel mean on the
+// fly from the interleaved [R, N, C] audio; the 16x overlap between frames is served by L1/L2),
+// windowed, transformed by an in-shared-memory radix-2 Stockham FFT of n_fft/2 complex points plus
+// the real-input split, and reduced to one flux value against the previous frame's spectrum, which
+// never leaves shared memory.  FP32 throughout (the reference uses numpy's float32 FFT).
+#include "ofp_common.cuh"
+
+namespace ofp {
+
+constexpr int K2_THREADS = 256;
+
+struct K2Args {
+    const float *x;
+    int64_t rec_stride, n_samples;
+    int32_t C, n_fft, hop, n_frames, frames_per_cta;
+    int32_t center;      // 0: frame j = x[(j+1)*hop - n_fft : (j+1)*hop] (realtime); 1: centred on j*hop (librosa)
+    int32_t reflect;     // padding of a centred transform: 0 zeros, 1 reflect
+    int32_t mode;        // 0: log-power flux, 1: weighted magnitude flux
+    float top_db;        // mode 0: clamp at (frame max - top_db); <= 0 disables
+    const float *window; // [n_fft]
+    const float *weight; // [n_fft/2 + 1] or null (mode 1)
+    float *flux;         // [R, n_frames]
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__device__ __forceinline__ float k2_block_sum(float v, float *scratch) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int i = 0; i < K2_THREADS / 32; ++i) r += scratch[i];
+    return r;
+}
+__device__ __forceinline__ float k2_block_max(float v, float *scratch) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_down_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = scratch[0];
+    for (int i = 1; i < K2_THREADS / 32; ++i) r = fmaxf(r, scratch[i]);
+    return r;
+}
+
+__global__ void __launch_bounds__(K2_THREADS) k2_flux(const K2Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.n_fft, H = N / 2, tid = threadIdx.x;
+    float *win = reinterpret_cast<float *>(smem_raw);            // [N]
+    float2 *tw = reinterpret_cast<float2 *>(win + N);            // [H]: exp(-2 pi i k / N)
+    float2 *bufA = tw + H;                                        // [H]
+    float2 *bufB = bufA + H;                                      // [H]
+    float *prevS = reinterpret_cast<float *>(bufB + H);           // [H + 1]
+    float *curS = prevS + H + 1;                                  // [H + 1]
+    __shared__ float red[K2_THREADS / 32];
+
+    const int r = blockIdx.y;
+    const float *xr = a.x + static_cast<int64_t>(r) * a.rec_stride;
+    for (int i = tid; i < N; i += K2_THREADS) win[i] = a.window[i];
+    for (int k = tid; k < H; k += K2_THREADS) {
+        float s, c;
+        sincospif(-2.0f * static_cast<float>(k) / static_cast<float>(N), &s, &c);
+        tw[k] = make_float2(c, s);
+    }
+    const float invC = 1.0f / static_cast<float>(a.C);
+    const int j0 = blockIdx.x * a.frames_per_cta;
+    const int j1 = min(j0 + a.frames_per_cta, a.n_frames);
+    int log2h = 0;
+    while ((1 << log2h) < H) ++log2h;
+    __syncthreads();
+
+    for (int j = j0 - 1; j < j1; ++j) {  // frame j0-1 only seeds prevS
+        // ---- gather + window: z[n] = x[2n] + i x[2n+1] ----
+        const int64_t start = a.center ? static_cast<int64_t>(j) * a.hop - H
+                                       : static_cast<int64_t>(j + 1) * a.hop - N;
+        for (int n = tid; n < H; n += K2_THREADS) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int64_t t = start + 2 * n + e;
+                if (a.center && a.reflect) {  // numpy pad mode 'reflect' (no edge repeat)
+                    if (t < 0) t = -t;
+                    if (t >= a.n_samples) t = 2 * (a.n_samples - 1) - t;
+                }
+                float s = 0.f;
+                if (j >= 0 && t >= 0 && t < a.n_samples) {
+                    const float *p = xr + t * a.C;
+                    for (int c = 0; c < a.C; ++c) s += p[c];
+                    s = a.C > 1 ? s * invC : s;
+                }
+                v[e] = s * win[2 * n + e];
+            }
+            bufA[n] = make_float2(v[0], v[1]);
+        }
+        __syncthreads();
+        // ---- Stockham radix-2 FFT of H complex points (autosort, ping-pong) ----
+        float2 *src = bufA, *dst = bufB;
+        for (int s = 0; s < log2h; ++s) {
+            const int half = 1 << s;           // butterflies span `half` outputs
+            for (int i = tid; i < H / 2; i += K2_THREADS) {
+                const int k = i & (half - 1);  // position inside the sub-transform
+                const int blk = i >> s;
+                const float2 u = src[i], t = src[i + H / 2];
+                // twiddle exp(-2 pi i k / (2*half)) = tw[k * (N / (2*half)) ... with tw of size H over N]
+                const float2 w = tw[k * (H / half)];  // index k * N/(2*half): exp(-2 pi i k/(2 half))
+                const float2 tt = cmul(t, w);
+                const int o = (blk << (s + 1)) + k;
+                dst[o] = make_float2(u.x + tt.x, u.y + tt.y);
+                dst[o + half] = make_float2(u.x - tt.x, u.y - tt.y);
+            }
+            __syncthreads();
+            float2 *tmp = src; src = dst; dst = tmp;
+        }
+        // src now holds Z[k], k < H.  Real-input split: X[k], k = 0..H
+        float pmax = -INFINITY;
+        for (int k = tid; k <= H; k += K2_THREADS) {
+            const float2 zk = src[k & (H - 1)], zc = src[(H - k) & (H - 1)];
+            const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));   // (Z[k] + conj Z[H-k]) / 2
+            const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));  // (Z[k] - conj Z[H-k]) / 2i
+            const float2 w = k < H ? tw[k] : make_float2(-1.f, 0.f);
+            const float2 ow = cmul(o, w);
+            const float re = e.x + ow.x, im = e.y + ow.y;
+            const float p = re * re + im * im;
+            float sv;
+            if (a.mode == 0) sv = 10.0f * log10f(fmaxf(1e-10f, p));
+            else sv = sqrtf(p) * (a.weight ? a.weight[k] : 1.0f);
+            curS[k] = sv;
+            pmax = fmaxf(pmax, sv);
+        }
+        float lo = -INFINITY;
+        if (a.mode == 0 && a.top_db > 0.f) lo = k2_block_max(pmax, red) - a.top_db;
+        __syncthreads();
+        float acc = 0.f;
+        for (int k = tid; k <= H; k += K2_THREADS) {
+            const float s = fmaxf(curS[k], lo), sp = fmaxf(prevS[k], lo);
+            acc += fmaxf(0.f, s - sp);
+        }
+        const float total = k2_block_sum(acc, red);
+        if (tid == 0 && j >= j0) a.flux[static_cast<int64_t>(r) * a.n_frames + j] = total / static_cast<float>(H + 1);
+        __syncthreads();
+        float *t2 = prevS; prevS = curS; curS = t2;
+    }
+}
+
+// librosa.util.peak_pick restated (greedy, sequential; one thread per recording):
+// x[n] is a peak if x[n] == max(x[n-pre_max : n+post_max+1]) and x[n] >= mean(x[n-pre_avg : n+post_avg+1]) + delta
+// and n - last_peak > wait.
+__global__ void k2_peak_pick(const float *oe, int n_frames, int R, int pre_max, int post_max, int pre_avg,
+                             int post_avg, float delta, int wait, int32_t *peaks, int32_t *n_peaks, int cap) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float *x = oe + static_cast<int64_t>(r) * n_frames;
+    int cnt = 0;
+    int last = -(1 << 30);
+    for (int n = 0; n < n_frames; ++n) {
+        const int a0 = max(0, n - pre_max), a1 = min(n_frames, n + post_max + 1);
+        float mx = -INFINITY;
+        for (int i = a0; i < a1; ++i) mx = fmaxf(mx, x[i]);
+        if (x[n] != mx) continue;
+        const int b0 = max(0, n - pre_avg), b1 = min(n_frames, n + post_avg + 1);
+        float s = 0.f;
+        for (int i = b0; i < b1; ++i) s += x[i];
+        if (x[n] < s / static_cast<float>(b1 - b0) + delta) continue;
+        if (n - last <= wait) continue;
+        if (cnt < cap) peaks[static_cast<int64_t>(r) * cap + cnt] = n;
+        ++cnt;
+        last = n;
+    }
+    n_peaks[r] = cnt;
+}
+
+}  // namespace ofp
+
+using namespace ofp;
+
+extern "C" {
+
+int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                      int32_t n_fft, int32_t hop, int32_t center, int32_t reflect, int32_t mode, float top_db,
+                      const float *window_dev, const float *weight_dev, int32_t n_frames, float *flux_dev,
+                      void *stream) {
+    OFP_REQUIRE(x_dev && window_dev && flux_dev, "null argument");
+    OFP_REQUIRE(n_fft >= 64 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0, "n_fft must be a power of two in 64..8192");
+    OFP_REQUIRE(hop >= 1 && n_channels >= 1 && n_rec <= 65535, "bad argument");
+    if (n_frames <= 0 || n_rec == 0) return OFP_OK;
+    K2Args a;
+    a.x = x_dev; a.rec_stride = rec_stride; a.n_samples = n_samples; a.C = n_channels; a.n_fft = n_fft; a.hop = hop;
+    a.n_frames = n_frames; a.frames_per_cta = 64; a.center = center; a.reflect = reflect; a.mode = mode;
+    a.top_db = top_db; a.window = window_dev; a.weight = weight_dev; a.flux = flux_dev;
+    const int H = n_fft / 2;
+    const size_t smem = sizeof(float) * n_fft + sizeof(float2) * 3 * H + sizeof(float) * 2 * (H + 1) + 16;
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(k2_flux, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid((n_frames + a.frames_per_cta - 1) / a.frames_per_cta, static_cast<unsigned>(n_rec));
+    k2_flux<<<grid, K2_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_peak_pick(const float *oe_dev, int32_t n_rec, int32_t n_frames, int32_t pre_max, int32_t post_max,
+                  int32_t pre_avg, int32_t post_avg, float delta, int32_t wait, int32_t *peaks_dev,
+                  int32_t *n_peaks_dev, int32_t cap, void *stream) {
+    OFP_REQUIRE(oe_dev && peaks_dev && n_peaks_dev, "null argument");
+    if (n_rec == 0) return OFP_OK;
+    k2_peak_pick<<<(n_rec + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        oe_dev, n_frames, n_rec, pre_max, post_max, pre_avg, post_avg, delta, wait, peaks_dev, n_peaks_dev, cap);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+}  // extern "C"
