@@ -40,9 +40,15 @@ def parse():
     ap.add_argument("--recordings", type=int, default=10000, help="recordings per GPU")
     ap.add_argument("--seconds", type=float, default=5.0, help="length of each recording")
     ap.add_argument("--no-rel", action="store_true", help="onsets-only mode (4 B per channel-sample)")
-    ap.add_argument("--e2e-recordings", type=int, default=256)
+    ap.add_argument("--e2e-recordings", type=int, default=1536)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--workload", default="batch", choices=["batch", "hits16", "realtime"],
+                    help="batch = configs[1] (headline); hits16 = configs[2] (16-channel hit mining, K4+K5); "
+                         "realtime = configs[3] (4096 concurrent 128-sample block streams)")
+    ap.add_argument("--hits", type=int, default=1000000, help="hits16: number of hits (over all GPUs)")
+    ap.add_argument("--streams", type=int, default=4096, help="realtime: concurrent streams per GPU")
+    ap.add_argument("--blocks", type=int, default=1000, help="realtime: consecutive blocks")
     return ap.parse_args()
 
 
@@ -359,10 +365,132 @@ def run_cpu_baseline(args, x):
             "sample": f"{n_rec} of the step's recordings ({xs.size} channel-samples, {dt:.1f} s)"}
 
 
+def _peak():
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s"
+
+
+def run_hits16(args):
+    """configs[2]: 16-channel mesh hit mining -- K4 (lag refinement, tol 150 / cutoff 20 / d=1 / abs /
+    median 7 as in notebooks/refresh.org:1507-1509) + K5 on the first three arrivals; hits sharded by rank."""
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from onset_fingerprinting_b200 import detection, multilateration, parallel, synth
+
+    Cn, L, tol, cut = 16, 768, 150, 20
+    lo, hi = parallel.shard_range(args.hits, rank, world)
+    H = hi - lo
+    look = tol + cut
+    # one section per hit: a burst whose wavefront reaches the 16 mesh sensors between look and look+420
+    x = synth.drum_batch_device(H, L, sensors=synth.SENSORS_16MESH, medium="drumhead", seed=7, hit_period=10.0,
+                                first_hit=look + 4, tail_guard=0, rec_offset=lo)
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    onsets = (look + 4 + torch.randint(0, 400, (H, Cn), generator=g, device="cuda")).to(torch.int32)
+    ml = multilateration.Multilaterate3D(synth.SENSORS_16MESH, sr=SR, medium="drumhead")
+    kw = dict(filter_size=7, d=1, take_abs=True, normalization_cutoff=cut, onset_tolerance=tol, max_section=L)
+
+    def step():
+        fixed, lags, st = detection.fix_onsets_batch(x, None, onsets, **kw)
+        first3 = torch.argsort(fixed, 1, stable=True)[:, :3].to(torch.int32)
+        on3 = torch.gather(fixed, 1, first3.long())
+        xy, lst = ml.locate_batch(on3, first3)
+        return fixed, st, xy, lst
+
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1, ek = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), []
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fixed, lags, st = detection.fix_onsets_batch(x, None, onsets, **kw)
+            b.record()
+            ek.append((a, b))
+            first3 = torch.argsort(fixed, 1, stable=True)[:, :3].to(torch.int32)
+            xy, lst = ml.locate_batch(torch.gather(fixed, 1, first3.long()), first3)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ms /= args.steps
+    k4_ms = float(np.mean([a.elapsed_time(b) for a, b in ek]))
+    peak, src = _peak()
+    bytes_per_hit = 4 * Cn * L + 16 * Cn + 48
+    achieved = bytes_per_hit * H / (k4_ms / 1e3) / 1e9
+    ok = int((st == 0).sum().item()); loc = int((lst == 0).sum().item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "hits/sec through lag refinement + multilateration (16-channel hit mining)",
+            "value": args.hits / (ms / 1e3), "unit": "hits/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64 accumulate / f32 data", "data": "synthetic",
+            "config": {"workload": f"configs[2]: {args.hits} hits x 16 ch, section {L}, tol {tol}, cutoff {cut}, d=1, abs, "
+                                   "median 7; K5 on the first three arrivals", "l2": "48.6 GB of sections per 1M hits, larger than L2"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k4_fix", "kernel_ms": k4_ms, "peak_source": src,
+                         "algorithmic_bytes_per_hit": bytes_per_hit,
+                         "note": "K4 at 16 ch is FP64-issue bound (3.4 M double MACs per hit), not HBM bound"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": 2 * args.steps, "clocks": clk.summary(),
+            "fix_ok": ok, "located": loc}))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def run_realtime(args):
+    """configs[3]: S concurrent streams, one launch per 128-sample block; per-block latency and throughput."""
+    import torch
+
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    from onset_fingerprinting_b200 import synth
+    from onset_fingerprinting_b200.realtime import audio as rt
+
+    S, nblk = args.streams, args.blocks
+    x = synth.drum_batch_device(S, nblk * BLOCK, seed=3, first_hit=5000)
+    sb = rt.StreamBatch(S)
+    for b in range(min(20, nblk)):
+        sb.process(x[:, b * BLOCK:(b + 1) * BLOCK])
+    torch.cuda.synchronize()
+    lat = []
+    t0 = time.perf_counter()
+    for b in range(nblk):
+        t = time.perf_counter()
+        ch, dl, cnt, _ = sb.process(x[:, b * BLOCK:(b + 1) * BLOCK])
+        cnt_host = cnt.cpu()  # launch-to-result: the host has the counts
+        lat.append(time.perf_counter() - t)
+    total = time.perf_counter() - t0
+    lat = np.asarray(lat) * 1e6
+    print(json.dumps({
+        "metric": "channel-samples/sec, realtime block streams", "value": S * nblk * BLOCK * N_CH / total,
+        "unit": "channel-samples/s", "n_gpus": 1, "steps": nblk, "warmup": 20, "ms_per_step": 1e3 * total / nblk,
+        "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[3]: {S} concurrent 3-mic streams, {BLOCK}-sample blocks, realtime detector settings"},
+        "latency_us": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+                       "budget_us": 1e6 * BLOCK / SR},
+        "gpu_launches": nblk, "e2e": None, "cpu_baseline": None, "roofline": None}))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "hits16":
+        run_hits16(args)
+    elif args.workload == "realtime":
+        run_realtime(args)
     else:
         run_ours(args)
 

@@ -88,8 +88,9 @@ int ofp_detect_offline(ofp_detector *det, const float *x_dev, int64_t n_samples,
                        int32_t *on_sample_dev, int32_t *on_count_dev, int32_t cap, void *stream);
 
 /* AmplitudeOnsetDetector.__call__ (detection.py:727-798) for n_streams concurrent streams:
- *   x_dev [S, B, C]; rel_dev NULL or [S, B, C]; ch_dev/delta_dev [S, C] int32; count_dev [S]. */
-int ofp_detect_block(ofp_detector *det, const float *x_dev, float *rel_dev, int32_t *ch_dev,
+ *   x_dev [S, B, C] with stream s starting at x_dev + s*stream_stride (elements; B*C when dense);
+ *   rel_dev NULL or [S, B, C]; ch_dev/delta_dev [S, C] int32; count_dev [S]. */
+int ofp_detect_block(ofp_detector *det, const float *x_dev, int64_t stream_stride, float *rel_dev, int32_t *ch_dev,
                      int32_t *delta_dev, int32_t *count_dev, void *stream);
 
 /* AmplitudeOnsetDetector.init_minmax_tracker (detection.py:827-840): x_dev [S, n, C]. */
@@ -196,6 +197,17 @@ int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, const float
                     int32_t onset_stride, int32_t n_hits, double *xy_dev, int32_t *status_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Streaming cross-correlation -- twin of the CPython extension online_cc
+ *     (c/cross_corr.c:257-291: CrossCorrelation(n, block_size).update(a, b) -> float32[2n-1])
+ * ------------------------------------------------------------------------------------- */
+typedef struct ofp_ccstream ofp_ccstream;
+/* n_pairs independent stream pairs; rings start at zero like the reference's calloc'd buffers. */
+int ofp_ccstream_create(ofp_ccstream **out, int32_t n_pairs, int32_t n, int32_t block_size);
+int ofp_ccstream_destroy(ofp_ccstream *h);
+/* a_dev, b_dev [P, block_size] float32 -> out_dev [P, 2n-1]: np.correlate(last n of a, last n of b, "full"). */
+int ofp_ccstream_update(ofp_ccstream *h, const float *a_dev, const float *b_dev, float *out_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * K2  spectral-flux onset features -- replaces RecAnalysis.fft / onset_strength
  *     (realtime/recording.py:273-311) and the STFT half of detect_onsets_spectral (detection.py:96-110)
  * ------------------------------------------------------------------------------------- */
@@ -219,11 +231,13 @@ int ofp_peak_pick(const float *oe_dev, int32_t n_rec, int32_t n_frames, int32_t 
 /* ---------------------------------------------------------------------------------------
  * Benchmark input: seeded synthetic multi-mic drum audio generated on the device
  * (SURVEY.md section 8d signal model; not a reference function).  x_dev [R, N, C] float32;
- * sensors_xyz_host [C, 3] cm (host); rec_offset = global index of recording 0 of this shard.
+ * sensors_xyz_host [C, 3] cm (host); rec_offset = global index of recording 0 of this shard;
+ * a burst is only emitted if it starts at least tail_guard samples before the end.
  * ------------------------------------------------------------------------------------- */
 int ofp_synth_drum(float *x_dev, int64_t n_rec, int64_t n_samples, int32_t n_channels,
                    const float *sensors_xyz_host, float c_cm_s, float sr, float noise, float radius_cm,
-                   int64_t first_hit, int64_t hit_period, uint64_t seed, int64_t rec_offset, void *stream);
+                   int64_t first_hit, int64_t hit_period, int32_t tail_guard, uint64_t seed, int64_t rec_offset,
+                   void *stream);
 
 #ifdef __cplusplus
 }

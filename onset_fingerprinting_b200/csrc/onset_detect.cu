@@ -863,7 +863,7 @@ int ofp_detector_destroy(ofp_detector *det) {
 
 int ofp_detector_reset(ofp_detector *det, void *stream) {
     OFP_REQUIRE(det, "null detector");
-    const int64_t n = det->n_lanes;
+    const int64_t n = det->n_lanes;  // all allocated lanes, also when fewer streams are active
     k1_reset<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         state_of(det), n, det->p.floor_db);
     OFP_CUDA_CHECK(cudaGetLastError());
@@ -898,11 +898,12 @@ int ofp_detect_offline(ofp_detector *det, const float *x_dev, int64_t n_samples,
                      on_channel_dev, on_sample_dev, on_count_dev, cap, static_cast<cudaStream_t>(stream));
 }
 
-int ofp_detect_block(ofp_detector *det, const float *x_dev, float *rel_dev, int32_t *ch_dev, int32_t *delta_dev,
-                     int32_t *count_dev, void *stream) {
+int ofp_detect_block(ofp_detector *det, const float *x_dev, int64_t stream_stride, float *rel_dev, int32_t *ch_dev,
+                     int32_t *delta_dev, int32_t *count_dev, void *stream) {
     OFP_REQUIRE(det && x_dev && ch_dev && delta_dev && count_dev, "null argument");
     const int64_t bc = static_cast<int64_t>(det->p.block_size) * det->p.n_channels;
-    return launch_k1(det, x_dev, det->p.block_size, bc, 0, det->p.block_size, rel_dev, bc, ch_dev, delta_dev,
+    OFP_REQUIRE(stream_stride >= bc, "stream_stride smaller than one block");
+    return launch_k1(det, x_dev, det->p.block_size, stream_stride, 0, det->p.block_size, rel_dev, bc, ch_dev, delta_dev,
                      count_dev, det->p.n_channels, static_cast<cudaStream_t>(stream));
 }
 
@@ -916,19 +917,29 @@ int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, i
                             int64_t warm_n, float *rel_host, int32_t *on_channel_host, int32_t *on_sample_host,
                             int32_t *on_count_host, int32_t cap) {
     OFP_REQUIRE(p && x_host && on_channel_host && on_sample_host && on_count_host, "null argument");
-    ofp_detector *det = nullptr;
-    int rc = ofp_detector_create(&det, n_rec, p);
-    if (rc != OFP_OK) return rc;
+    OFP_REQUIRE(n_rec > 0 && n_samples >= 0, "bad size");
+    // Recordings are processed in chunks on two streams so that the host->device copy of chunk i+1
+    // overlaps the kernel and the result copies of chunk i (pinned host memory makes the copies async).
     const int64_t C = p->n_channels, B = p->block_size;
-    const int64_t in_elems = n_rec * n_samples * C;
-    const int64_t rel_elems = n_rec * (n_samples / B) * B * C;
-    float *x_dev = nullptr, *rel_dev = nullptr;
-    int32_t *och = nullptr, *oix = nullptr, *ocn = nullptr;
-    cudaStream_t st = nullptr;
+    int64_t chunk = env_int("OFP_HOST_CHUNK", 1024);
+    if (n_rec <= chunk + chunk / 2) chunk = n_rec;
+    const int64_t nchunks = (n_rec + chunk - 1) / chunk;
+    const int ns = nchunks > 1 ? 2 : 1;
+    const int64_t in_elems = chunk * n_samples * C;
+    const int64_t rel_row = (n_samples / B) * B * C;
+    struct Slot {
+        ofp_detector *det = nullptr;
+        float *x = nullptr, *rel = nullptr;
+        int32_t *och = nullptr, *oix = nullptr, *ocn = nullptr;
+        cudaStream_t st = nullptr;
+    } slot[2];
+    int rc = OFP_OK;
     auto cleanup = [&]() {
-        cudaFree(x_dev); cudaFree(rel_dev); cudaFree(och); cudaFree(oix); cudaFree(ocn);
-        if (st) cudaStreamDestroy(st);
-        ofp_detector_destroy(det);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(slot[i].x); cudaFree(slot[i].rel); cudaFree(slot[i].och); cudaFree(slot[i].oix); cudaFree(slot[i].ocn);
+            if (slot[i].st) cudaStreamDestroy(slot[i].st);
+            ofp_detector_destroy(slot[i].det);
+        }
     };
 #define HOST_CHECK(expr)                                                                  \
     do {                                                                                  \
@@ -939,22 +950,36 @@ int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, i
             return OFP_ECUDA;                                                             \
         }                                                                                 \
     } while (0)
-    HOST_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    HOST_CHECK(cudaMalloc(&x_dev, sizeof(float) * std::max<int64_t>(in_elems, 4)));
-    if (rel_host) HOST_CHECK(cudaMalloc(&rel_dev, sizeof(float) * std::max<int64_t>(rel_elems, 4)));
-    HOST_CHECK(cudaMalloc(&och, sizeof(int32_t) * std::max<int64_t>(n_rec * cap, 1)));
-    HOST_CHECK(cudaMalloc(&oix, sizeof(int32_t) * std::max<int64_t>(n_rec * cap, 1)));
-    HOST_CHECK(cudaMalloc(&ocn, sizeof(int32_t) * n_rec));
-    HOST_CHECK(cudaMemcpyAsync(x_dev, x_host, sizeof(float) * in_elems, cudaMemcpyHostToDevice, st));
-    rc = ofp_detect_offline(det, x_dev, n_samples, n_samples * C, warm_n, rel_dev, (n_samples / B) * B * C, och, oix,
-                            ocn, cap, st);
-    if (rc != OFP_OK) { cleanup(); return rc; }
-    if (rel_host)
-        HOST_CHECK(cudaMemcpyAsync(rel_host, rel_dev, sizeof(float) * rel_elems, cudaMemcpyDeviceToHost, st));
-    HOST_CHECK(cudaMemcpyAsync(on_channel_host, och, sizeof(int32_t) * n_rec * cap, cudaMemcpyDeviceToHost, st));
-    HOST_CHECK(cudaMemcpyAsync(on_sample_host, oix, sizeof(int32_t) * n_rec * cap, cudaMemcpyDeviceToHost, st));
-    HOST_CHECK(cudaMemcpyAsync(on_count_host, ocn, sizeof(int32_t) * n_rec, cudaMemcpyDeviceToHost, st));
-    HOST_CHECK(cudaStreamSynchronize(st));
+    for (int i = 0; i < ns; ++i) {
+        rc = ofp_detector_create(&slot[i].det, chunk, p);
+        if (rc != OFP_OK) { cleanup(); return rc; }
+        HOST_CHECK(cudaStreamCreateWithFlags(&slot[i].st, cudaStreamNonBlocking));
+        HOST_CHECK(cudaMalloc(&slot[i].x, sizeof(float) * std::max<int64_t>(in_elems, 4)));
+        if (rel_host) HOST_CHECK(cudaMalloc(&slot[i].rel, sizeof(float) * std::max<int64_t>(chunk * rel_row, 4)));
+        HOST_CHECK(cudaMalloc(&slot[i].och, sizeof(int32_t) * std::max<int64_t>(chunk * cap, 1)));
+        HOST_CHECK(cudaMalloc(&slot[i].oix, sizeof(int32_t) * std::max<int64_t>(chunk * cap, 1)));
+        HOST_CHECK(cudaMalloc(&slot[i].ocn, sizeof(int32_t) * chunk));
+    }
+    HOST_CHECK(cudaDeviceSynchronize());  // detector resets ran on the default stream
+    for (int64_t ci = 0; ci < nchunks; ++ci) {
+        Slot &sl = slot[ci % ns];
+        const int64_t r0 = ci * chunk, n = std::min(chunk, n_rec - r0);
+        HOST_CHECK(cudaMemcpyAsync(sl.x, x_host + r0 * n_samples * C, sizeof(float) * n * n_samples * C,
+                                   cudaMemcpyHostToDevice, sl.st));
+        sl.det->n_streams = n;  // the state arrays are sized for `chunk` recordings
+        rc = ofp_detector_reset(sl.det, sl.st);
+        if (rc == OFP_OK)
+            rc = ofp_detect_offline(sl.det, sl.x, n_samples, n_samples * C, warm_n, sl.rel, rel_row, sl.och, sl.oix,
+                                    sl.ocn, cap, sl.st);
+        if (rc != OFP_OK) { cleanup(); return rc; }
+        if (rel_host)
+            HOST_CHECK(cudaMemcpyAsync(rel_host + r0 * rel_row, sl.rel, sizeof(float) * n * rel_row,
+                                       cudaMemcpyDeviceToHost, sl.st));
+        HOST_CHECK(cudaMemcpyAsync(on_channel_host + r0 * cap, sl.och, sizeof(int32_t) * n * cap, cudaMemcpyDeviceToHost, sl.st));
+        HOST_CHECK(cudaMemcpyAsync(on_sample_host + r0 * cap, sl.oix, sizeof(int32_t) * n * cap, cudaMemcpyDeviceToHost, sl.st));
+        HOST_CHECK(cudaMemcpyAsync(on_count_host + r0, sl.ocn, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, sl.st));
+    }
+    for (int i = 0; i < ns; ++i) HOST_CHECK(cudaStreamSynchronize(slot[i].st));
 #undef HOST_CHECK
     cleanup();
     return OFP_OK;

@@ -14,7 +14,7 @@ struct SynthArgs {
     float sensors[32 * 3];
     float c_cm_s, sr, noise, radius;
     int64_t first_hit, hit_period;
-    int32_t burst_len;
+    int32_t burst_len, tail_guard;
     uint64_t seed;
     int64_t rec_offset;  // global index of recording 0 (multi-GPU shards draw different hits)
 };
@@ -50,7 +50,7 @@ __global__ void k_synth(const SynthArgs a) {
             const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
             const int64_t delay = static_cast<int64_t>(rintf(dist / a.c_cm_s * a.sr));
             const int64_t k = rel - hit * a.hit_period - delay;
-            if (k >= 0 && k < a.burst_len && a.first_hit + hit * a.hit_period + delay + a.burst_len + 2048 < a.N) {
+            if (k >= 0 && k < a.burst_len && a.first_hit + hit * a.hit_period + delay + a.tail_guard < a.N) {
                 const float t = static_cast<float>(k) / a.sr;
                 v += 0.5f * 10.0f / dist * expf(-400.0f * t) * sinf(6.2831853f * 900.0f * t);
             }
@@ -65,14 +65,14 @@ using namespace ofp;
 
 extern "C" int ofp_synth_drum(float *x_dev, int64_t n_rec, int64_t n_samples, int32_t n_channels,
                               const float *sensors_xyz_host, float c_cm_s, float sr, float noise, float radius_cm,
-                              int64_t first_hit, int64_t hit_period, uint64_t seed, int64_t rec_offset,
-                              void *stream) {
+                              int64_t first_hit, int64_t hit_period, int32_t tail_guard, uint64_t seed,
+                              int64_t rec_offset, void *stream) {
     OFP_REQUIRE(x_dev && sensors_xyz_host && n_channels >= 1 && n_channels <= 32, "bad argument");
     SynthArgs a;
     a.x = x_dev; a.R = n_rec; a.N = n_samples; a.C = n_channels;
     for (int i = 0; i < 3 * n_channels; ++i) a.sensors[i] = sensors_xyz_host[i];
     a.c_cm_s = c_cm_s; a.sr = sr; a.noise = noise; a.radius = radius_cm;
-    a.first_hit = first_hit; a.hit_period = hit_period; a.burst_len = 4096; a.seed = seed;
+    a.first_hit = first_hit; a.hit_period = hit_period; a.burst_len = 4096; a.tail_guard = tail_guard; a.seed = seed;
     a.rec_offset = rec_offset;
     const int blocks = sm_count() * 16;
     k_synth<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);

@@ -109,14 +109,19 @@ class BatchedOnsetDetector:
     def process_block(self, x, return_rel=True):
         """One [S, B, C] block for every stream -> (channels [S, C], deltas [S, C], counts [S], rel)."""
         torch = self.torch
-        x = _to_dev(x, torch)
         S, B, Cn = self.n_streams, self.block_size, self.n_signals
+        if not isinstance(x, np.ndarray) and x.is_cuda and x.dtype == torch.float32 and x.stride(2) == 1 \
+                and x.stride(1) == Cn:
+            pass  # a [S, B, C] window into longer per-stream buffers: used in place
+        else:
+            x = _to_dev(x, torch)
         assert tuple(x.shape) == (S, B, Cn), f"expected {(S, B, Cn)}, got {tuple(x.shape)}"
         ch = torch.empty((S, Cn), dtype=torch.int32, device="cuda")
         dl = torch.empty((S, Cn), dtype=torch.int32, device="cuda")
         cnt = torch.empty((S,), dtype=torch.int32, device="cuda")
         rel = torch.empty((S, B, Cn), dtype=torch.float32, device="cuda") if return_rel else None
-        check(_lib.lib().ofp_detect_block(self._h, ptr(x), ptr(rel), ptr(ch), ptr(dl), ptr(cnt), stream_ptr()))
+        check(_lib.lib().ofp_detect_block(self._h, ptr(x), C.c_int64(x.stride(0)), ptr(rel), ptr(ch), ptr(dl),
+                                          ptr(cnt), stream_ptr()))
         return ch, dl, cnt, rel
 
     def default_cap(self, n_samples: int) -> int:

@@ -101,7 +101,8 @@ def drum_batch(n_rec: int, seconds: float = 2.0, seed: int = 0, **kw):
 
 
 def drum_batch_device(n_rec: int, n_samples: int, sensors=SENSORS_3MIC, medium: str = "air", seed: int = 0,
-                      sr: int = SR, hit_period: float = 0.118, noise: float = 1e-4, rec_offset: int = 0, out=None):
+                      sr: int = SR, hit_period: float = 0.118, noise: float = 1e-4, rec_offset: int = 0, out=None,
+                      first_hit: int | None = None, tail_guard: int = 4096 + 2048):
     """Same signal model generated on the GPU (csrc/synth.cu): returns a CUDA tensor [R, N, C]."""
     import ctypes as C
 
@@ -114,6 +115,6 @@ def drum_batch_device(n_rec: int, n_samples: int, sensors=SENSORS_3MIC, medium: 
     _lib.check(_lib.lib().ofp_synth_drum(
         _lib.ptr(x), C.c_int64(n_rec), C.c_int64(n_samples), C.c_int32(n_ch),
         locs.ctypes.data_as(C.c_void_p), C.c_float(speed_cm_s(medium)), C.c_float(sr), C.c_float(noise),
-        C.c_float(DIAMETER / 2), C.c_int64(int(0.5 * sr) + 1000), C.c_int64(int(round(hit_period * sr))),
-        C.c_uint64(seed), C.c_int64(rec_offset), _lib.stream_ptr()))
+        C.c_float(DIAMETER / 2), C.c_int64(int(0.5 * sr) + 1000 if first_hit is None else first_hit),
+        C.c_int64(int(round(hit_period * sr))), C.c_int32(tail_guard), C.c_uint64(seed), C.c_int64(rec_offset), _lib.stream_ptr()))
     return x
