@@ -400,7 +400,7 @@ def run_hits16(args):
 
     def step():
         fixed, lags, st = detection.fix_onsets_batch(x, None, onsets, **kw)
-        first3 = torch.argsort(fixed, 1, stable=True)[:, :3].to(torch.int32)
+        first3 = torch.argsort(fixed, dim=1, stable=True)[:, :3].to(torch.int32)
         on3 = torch.gather(fixed, 1, first3.long())
         xy, lst = ml.locate_batch(on3, first3)
         return fixed, st, xy, lst
@@ -419,7 +419,7 @@ def run_hits16(args):
             fixed, lags, st = detection.fix_onsets_batch(x, None, onsets, **kw)
             b.record()
             ek.append((a, b))
-            first3 = torch.argsort(fixed, 1, stable=True)[:, :3].to(torch.int32)
+            first3 = torch.argsort(fixed, dim=1, stable=True)[:, :3].to(torch.int32)
             xy, lst = ml.locate_batch(torch.gather(fixed, 1, first3.long()), first3)
         e1.record()
         torch.cuda.synchronize()

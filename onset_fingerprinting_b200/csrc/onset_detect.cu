@@ -902,6 +902,7 @@ int ofp_detect_block(ofp_detector *det, const float *x_dev, int64_t stream_strid
                      int32_t *delta_dev, int32_t *count_dev, void *stream) {
     OFP_REQUIRE(det && x_dev && ch_dev && delta_dev && count_dev, "null argument");
     const int64_t bc = static_cast<int64_t>(det->p.block_size) * det->p.n_channels;
+    if (det->n_streams == 1) stream_stride = bc;  // a size-1 leading dimension carries no meaningful stride
     OFP_REQUIRE(stream_stride >= bc, "stream_stride smaller than one block");
     return launch_k1(det, x_dev, det->p.block_size, stream_stride, 0, det->p.block_size, rel_dev, bc, ch_dev, delta_dev,
                      count_dev, det->p.n_channels, static_cast<cudaStream_t>(stream));
