@@ -20,8 +20,11 @@ namespace ofp {
 
 constexpr int LAG_NONE = INT32_MIN;
 constexpr int FIX_OK = 0, FIX_DEGENERATE = 1, FIX_REF_CRASH = 2, FIX_TOO_LONG = 3, FIX_INCOMPLETE = 4;
-constexpr int K4_THREADS = 256;
-constexpr int LPT = 4;  // lags per thread
+constexpr int K4_THREADS = 128;
+// Lags per thread.  ODD on purpose: neighbouring lanes then read x at a stride of LPT doubles, and an
+// odd stride spreads the 32 lanes of an LDS.64 over all bank pairs (LPT = 4 gave 8-way conflicts).
+constexpr int LPT = 3;
+constexpr int CC_UN = 4;  // time steps per unrolled iteration
 
 struct FixParams {
     int32_t filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift;
@@ -64,12 +67,12 @@ __device__ __forceinline__ float median_window(const float *src, int64_t L, int 
 #pragma unroll
     for (int j = 0; j < (SIZE > 0 ? SIZE : 16); ++j) {
         if (j < n) {
-            int64_t q = t - lo + j;  // scipy mode='reflect': d c b a | a b c d | d c b a
-            if (L == 1) q = 0;
-            else {
-                const int64_t P = 2 * L;
+            int q = static_cast<int>(t) - lo + j;  // scipy mode='reflect': d c b a | a b c d | d c b a
+            const int Li = static_cast<int>(L);
+            if (q < 0 || q >= Li) {               // rare: only within size/2 samples of the section ends
+                const int P = 2 * Li;
                 q %= P; if (q < 0) q += P;
-                if (q >= L) q = P - 1 - q;
+                if (q >= Li) q = P - 1 - q;
             }
             w[j] = src[q * C + c];
         }
@@ -143,15 +146,32 @@ __device__ __forceinline__ void cc_argmax(const double *xd, const double *yd, in
             {
                 const bool full = (w0 + LPT <= nl);
                 if (full && lo < hi) {
-                    double x0 = xd[lo + m0], x1 = xd[lo + m0 + 1], x2 = xd[lo + m0 + 2];
-                    for (int64_t i = lo; i < hi; ++i) {
-                        const double yv = yd[i];
-                        const double x3 = xd[i + m0 + 3];
-                        acc[0] = __fma_rn(x0, yv, acc[0]);
-                        acc[1] = __fma_rn(x1, yv, acc[1]);
-                        acc[2] = __fma_rn(x2, yv, acc[2]);
-                        acc[3] = __fma_rn(x3, yv, acc[3]);
-                        x0 = x1; x1 = x2; x2 = x3;
+                    // sliding register window over x: per CC_UN time steps, CC_UN loads of y (broadcast) and
+                    // CC_UN of x feed CC_UN * LPT DFMA.  32-bit indices inside the loop.
+                    const double *xp = xd + (lo + m0), *yp = yd + lo;
+                    const int nbody = static_cast<int>(hi - lo);
+                    double xw[LPT - 1 + CC_UN];
+#pragma unroll
+                    for (int k = 0; k < LPT - 1; ++k) xw[k] = xp[k];
+                    int i = 0;
+                    for (; i + CC_UN <= nbody; i += CC_UN) {
+                        double yv[CC_UN];
+#pragma unroll
+                        for (int k = 0; k < CC_UN; ++k) { yv[k] = yp[i + k]; xw[LPT - 1 + k] = xp[i + LPT - 1 + k]; }
+#pragma unroll
+                        for (int k = 0; k < CC_UN; ++k)
+#pragma unroll
+                            for (int u = 0; u < LPT; ++u) acc[u] = __fma_rn(xw[k + u], yv[k], acc[u]);
+#pragma unroll
+                        for (int k = 0; k < LPT - 1; ++k) xw[k] = xw[k + CC_UN];
+                    }
+                    for (; i < nbody; ++i) {
+                        const double yv = yp[i];
+                        xw[LPT - 1] = xp[i + LPT - 1];
+#pragma unroll
+                        for (int u = 0; u < LPT; ++u) acc[u] = __fma_rn(xw[u], yv, acc[u]);
+#pragma unroll
+                        for (int k = 0; k < LPT - 1; ++k) xw[k] = xw[k + 1];
                     }
                 } else {
                     for (int64_t i = lo; i < hi; ++i) {
@@ -243,10 +263,9 @@ __global__ void __launch_bounds__(K4_THREADS) k4_fix(const K4Args a) {
     const int C = a.C, tid = threadIdx.x, h = blockIdx.x;
     const FixParams fp = a.fp;
     double *xd = reinterpret_cast<double *>(smem_raw);
-    double *yd = xd + a.Lmax + 8;
-    float *bufA = reinterpret_cast<float *>(yd + a.Lmax + 8);
-    float *bufB = bufA + static_cast<size_t>(a.Lmax) * C;
-    __shared__ int64_t og[32], so[32];
+    double *yd = xd + a.Lmax + 16;
+    float *bufA = reinterpret_cast<float *>(yd + a.Lmax + 16);
+    __shared__ int64_t og[32], so[32], zl[32];
     __shared__ int idx[32];
     __shared__ int64_t s_s0, s_L0;
     __shared__ int s_status;
@@ -292,58 +311,59 @@ __global__ void __launch_bounds__(K4_THREADS) k4_fix(const K4Args a) {
     }
     const int64_t rec = a.hit_rec ? a.hit_rec[h] : h;
     const float *src = a.audio + rec * a.rec_stride + s0 * C;
-    for (int64_t e = tid; e < L0 * C; e += K4_THREADS) bufA[e] = src[e];
     if (tid < C && a.out_lags) a.out_lags[static_cast<int64_t>(h) * C + tid] = LAG_NONE;
-    __syncthreads();
-    // median filter along time (detection.py:420-422)
+    // median filter along time (detection.py:420-422), read straight from the recording (the 7 rows
+    // around a sample are coalesced and L1-resident) into the only section buffer kept in shared memory
+    float *med = bufA;
     for (int64_t e = tid; e < L0 * C; e += K4_THREADS) {
         const int64_t t = e / C;
         const int c = static_cast<int>(e - t * C);
         float m;
         switch (fp.filter_size) {
-            case 1: m = bufA[e]; break;
-            case 3: m = median_window<3>(bufA, L0, C, t, c, 3); break;
-            case 5: m = median_window<5>(bufA, L0, C, t, c, 5); break;
-            case 7: m = median_window<7>(bufA, L0, C, t, c, 7); break;
-            case 9: m = median_window<9>(bufA, L0, C, t, c, 9); break;
-            default: m = median_window<0>(bufA, L0, C, t, c, fp.filter_size); break;
+            case 1: m = src[e]; break;
+            case 3: m = median_window<3>(src, L0, C, t, c, 3); break;
+            case 5: m = median_window<5>(src, L0, C, t, c, 5); break;
+            case 7: m = median_window<7>(src, L0, C, t, c, 7); break;
+            case 9: m = median_window<9>(src, L0, C, t, c, 9); break;
+            default: m = median_window<0>(src, L0, C, t, c, fp.filter_size); break;
         }
-        bufB[e] = m;
+        med[e] = m;
     }
+    const int64_t L = L0 - fp.d;
+    if (tid < C) { so[tid] = og[tid] - s0; zl[tid] = 0; }  // detection.py:429
     __syncthreads();
-    float *sec = bufB, *other = bufA;
-    int64_t L = L0;
-    for (int r = 0; r < fp.d; ++r) {  // np.diff(., d, axis=0)
-        for (int64_t e = tid; e < (L - 1) * C; e += K4_THREADS) other[e] = __fsub_rn(sec[e + C], sec[e]);
-        __syncthreads();
-        float *tmp = sec; sec = other; other = tmp;
-        --L;
-    }
-    for (int64_t e = tid; e < L * C; e += K4_THREADS) {  // detection.py:423-428
-        float v = sec[e];
+    // section value after np.diff(., d), direction mask, abs (detection.py:420-428) and the in-place
+    // zero_left prefixes (435-437), evaluated on the fly from the median-filtered samples
+    auto secval = [&](int64_t t, int c) -> float {
+        if (t < zl[c]) return 0.0f;
+        float w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = k <= fp.d ? med[(t + k) * C + c] : 0.0f;
+        for (int rr = 0; rr < fp.d; ++rr)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) w[k] = __fsub_rn(w[k + 1], w[k]);
+        float v = w[0];
         if (fp.direction == 1 && v < 0.f) v = 0.f;
         if (fp.direction == 2 && v > 0.f) v = 0.f;
         if (fp.take_abs) v = fabsf(v);
-        sec[e] = v;
-    }
-    if (tid < C) so[tid] = og[tid] - s0;  // detection.py:429
-    __syncthreads();
+        return v;
+    };
 
     const int r = idx[0];
     int status = FIX_OK;
     for (int j = 1; j < C; ++j) {
         const int ci = idx[j];
         const int64_t o0 = so[r], o1 = so[ci];
-        if (fp.zero_left) {  // detection.py:435-437 (python slice x[:o] = 0)
+        if (fp.zero_left) {  // detection.py:435-437 (python slice x[:o] = 0): prefixes only ever grow
             int64_t b0 = 0, z0 = o0, b1 = 0, z1 = o1;
             py_slice(b0, z0, L); py_slice(b1, z1, L);
-            for (int64_t t = tid; t < z0; t += K4_THREADS) sec[t * C + r] = 0.f;
-            for (int64_t t = tid; t < z1; t += K4_THREADS) sec[t * C + ci] = 0.f;
+            __syncthreads();
+            if (tid == 0) { zl[r] = max(zl[r], z0); zl[ci] = max(zl[ci], z1); }
             __syncthreads();
         }
         float xm = -INFINITY, ym = -INFINITY;
         for (int64_t t = tid; t < L; t += K4_THREADS) {
-            const float xv = sec[t * C + r], yv = sec[t * C + ci];
+            const float xv = secval(t, r), yv = secval(t, ci);
             xd[t] = static_cast<double>(xv); yd[t] = static_cast<double>(yv);
             xm = fmaxf(xm, xv); ym = fmaxf(ym, yv);
         }
@@ -427,8 +447,8 @@ __device__ __forceinline__ int64_t load_pair(const PairArgs &a, int p, double *x
 __global__ void __launch_bounds__(K4_THREADS) k4_cc_pairs(const PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *xd = reinterpret_cast<double *>(smem_raw);
-    double *yd = xd + a.n + 8;
-    float *tmp = reinterpret_cast<float *>(yd + a.n + 8);
+    double *yd = xd + a.n + 16;
+    float *tmp = reinterpret_cast<float *>(yd + a.n + 16);
     __shared__ float red_f[K4_THREADS / 32], best_v[K4_THREADS / 32];
     __shared__ int best_w[K4_THREADS / 32];
     __shared__ int s_lag;
@@ -452,8 +472,8 @@ __global__ void __launch_bounds__(K4_THREADS) k4_cc_pairs(const PairArgs a) {
 __global__ void __launch_bounds__(K4_THREADS) k4_adjust_pairs(const PairArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *xd = reinterpret_cast<double *>(smem_raw);
-    double *yd = xd + a.n + 8;
-    float *tmp = reinterpret_cast<float *>(yd + a.n + 8);
+    double *yd = xd + a.n + 16;
+    float *tmp = reinterpret_cast<float *>(yd + a.n + 16);
     __shared__ float red_f[K4_THREADS / 32];
     __shared__ double red_d[K4_THREADS / 32];
     const int p = blockIdx.x;
@@ -538,7 +558,7 @@ using namespace ofp;
 extern "C" {
 
 int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section) {
-    return static_cast<int>(2 * (max_section + 8) * sizeof(double) + 2 * static_cast<size_t>(max_section) * n_channels * sizeof(float));
+    return static_cast<int>(2 * (max_section + 16) * sizeof(double) + static_cast<size_t>(max_section) * n_channels * sizeof(float));
 }
 
 int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
@@ -549,7 +569,8 @@ int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride
     OFP_REQUIRE(audio_dev && onsets_dev && out_onsets_dev && out_status_dev, "null argument");
     OFP_REQUIRE(n_channels >= 2 && n_channels <= 32, "n_channels must be in 2..32");
     OFP_REQUIRE(filter_size >= 1 && filter_size <= 15, "filter_size must be in 1..15");
-    OFP_REQUIRE(d >= 0 && cutoff >= 0 && tol >= 0 && direction >= 0 && direction <= 2, "bad option");
+    OFP_REQUIRE(d >= 0 && d <= 3 && cutoff >= 0 && tol >= 0 && direction >= 0 && direction <= 2,
+                "bad option (difference order d must be 0..3)");
     if (n_hits == 0) return OFP_OK;
     K4Args a;
     a.audio = audio_dev; a.rec_stride = rec_stride; a.n_samples = n_samples; a.C = n_channels; a.H = n_hits;
@@ -573,7 +594,7 @@ static int launch_pairs(bool adjust, const float *x, const float *y, int32_t P, 
     OFP_REQUIRE(d >= 0 && d < n, "bad difference order");
     if (P == 0) return OFP_OK;
     PairArgs a{x, y, P, n, d, take_abs, use_legal, cutoff, tol, onsets, new_lag, out};
-    const int smem = 2 * (n + 8) * sizeof(double) + 2 * n * sizeof(float);
+    const int smem = 2 * (n + 16) * sizeof(double) + 2 * n * sizeof(float);
     if (adjust) k4_adjust_pairs<<<P, K4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
     else k4_cc_pairs<<<P, K4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
     OFP_CUDA_CHECK(cudaGetLastError());
