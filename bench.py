@@ -289,8 +289,15 @@ def run_ours(args):
     bytes_per_unit = 4 if args.no_rel else 8
     alg_bytes = R * nb * BLOCK * N_CH * bytes_per_unit
     achieved = alg_bytes / (k1_ms / 1e3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per launch, scaled from the committed ncu --set full capture of this kernel
+        tj = json.loads((ROOT / "profiles" / "r01_k1_traffic.json").read_text())
+        traffic = (tj["dram_read_bytes_per_input_sample"] * R * N_CH * (nb * BLOCK + warm_n)
+                   + (0 if args.no_rel else tj["dram_write_bytes_per_output_sample"] * R * N_CH * nb * BLOCK))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k1_detect", "kernel_ms": k1_ms,
+                "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel": "k1_detect", "kernel_ms": k1_ms,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_channel_sample": bytes_per_unit}
 
