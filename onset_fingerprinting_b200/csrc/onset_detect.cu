@@ -134,6 +134,18 @@ struct Lane {
     int32_t state, deb;
 };
 
+// Same recurrence when the numerator is symmetric (b0 == b4, b1 == b3 bit for bit, true for every
+// Butterworth high-pass): the two repeated products are formed once -- identical values, 2 FMUL less.
+__device__ __forceinline__ float hp_step_sym(Lane &L, const Coef &k, float x) {
+    const float m0 = __fmul_rn(k.b0, x), m1 = __fmul_rn(x, k.b1);
+    const float y = __fadd_rn(L.z0, m0);
+    L.z0 = __fsub_rn(__fadd_rn(L.z1, m1), __fmul_rn(y, k.a1));
+    L.z1 = __fsub_rn(__fadd_rn(L.z2, __fmul_rn(x, k.b2)), __fmul_rn(y, k.a2));
+    L.z2 = __fsub_rn(__fadd_rn(L.z3, m1), __fmul_rn(y, k.a3));
+    L.z3 = __fsub_rn(m0, __fmul_rn(y, k.a4));
+    return y;
+}
+
 // scipy lfilter, DF2T, float32, unfused (detection.py:499-501)
 __device__ __forceinline__ float hp_step(Lane &L, const Coef &k, float x) {
     const float y = __fadd_rn(L.z0, __fmul_rn(k.b0, x));
@@ -204,7 +216,7 @@ __device__ __forceinline__ float to_amp_fast(float r, float ceil_amp, uint32_t e
 // elementary operation is issued for all U samples before the next one, so the instruction stream
 // handed to ptxas is already interleaved.  (Written sample-major, ptxas keeps the U dependency
 // chains mostly back to back and the warp stalls on every dependent FP64 op -- ncu, profiles/.)
-template <int U>
+template <int U, bool MASK = true>
 __device__ __forceinline__ void to_db_vec(const float (&h)[U], float floor_db, uint32_t logtab, const MathConst &mc,
                                           float (&db)[U], float (&v_out)[U], uint32_t &redo_mask, int bit0) {
     uint32_t ix[U], tmp[U], iz[U];
@@ -241,13 +253,14 @@ __device__ __forceinline__ void to_db_vec(const float (&h)[U], float floor_db, u
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const bool redo = ((ix[u] - 0x00800000u) >= 0x7f000000u) | near_f32_midpoint(ld[u], 1u << 13);
-        redo_mask |= (redo ? 1u : 0u) << (bit0 + u);
+        if (MASK) redo_mask |= (redo ? 1u : 0u) << (bit0 + u);
+        else redo_mask |= redo;  // only "any sample flagged" is needed
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) db[u] = db_of(ld[u], floor_db);
 }
 
-template <int U>
+template <int U, bool MASK = true>
 __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp, uint32_t exptab, const MathConst &mc,
                                            float (&amp)[U], uint32_t &redo_mask, int bit0) {
     float q0[U], q[U];
@@ -284,7 +297,8 @@ __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp,
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const bool redo = !(fabsf(q[u]) < 30.0f) | near_f32_midpoint(ad[u], 1u << 8);
-        redo_mask |= (redo ? 1u : 0u) << (bit0 + u);
+        if (MASK) redo_mask |= (redo ? 1u : 0u) << (bit0 + u);
+        else redo_mask |= redo;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) amp[u] = amp_of(ad[u], ceil_amp);
@@ -359,7 +373,7 @@ __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint3
 //   - follower steps in the sliver 0 < |t| < 2^-22 where the float32 shortcut is not proven exact.
 // Returns true when this lane hit a flag; the caller then restores the lane state and re-runs the
 // samples through chunk<> (exact, with branches).
-template <bool USE_HP, int U>
+template <bool USE_HP, bool HP_SYM, int U>
 __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
                                            bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
                                            const MathConst &mc) {
@@ -368,20 +382,22 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const float x = lds_f32(xs + u * step);
-        h[u] = USE_HP ? hp_step(L, k, x) : x;
+        h[u] = USE_HP ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
     }
-    to_db_vec<U>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
+    to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
     bool sliver = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const float t1 = __fsub_rn(db[u], L.yf), t2 = __fsub_rn(db[u], L.ys);
-        sliver |= (fabsf(t1) < 0x1p-22f && t1 != 0.0f) | (fabsf(t2) < 0x1p-22f && t2 != 0.0f);
+        // 0 < |x - y| < 2^-22 needs min(|x|, |y|) < 2 (a difference of floats is a multiple of the smaller
+        // ulp): flag conservatively on the operands, the exact test runs in the re-run path
+        sliver |= (fabsf(db[u]) < 2.0f) | (fabsf(L.yf) < 2.0f) | (fabsf(L.ys) < 2.0f);
         const float d1 = __fadd_rn(t1, 1e-10f), d2 = __fadd_rn(t2, 1e-10f);
         L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
         L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
         dr[u] = __fsub_rn(L.yf, L.ys);
     }
-    to_amp_vec<U>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
+    to_amp_vec<U, false>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if (do_minmax) minmax_step(L, k, amp[u]);
@@ -419,7 +435,7 @@ __device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch
 
 constexpr int KU = 8;  // samples per straight-line chunk of the single-warp kernel
 
-template <bool USE_HP, bool USE_TMA>
+template <bool USE_HP, bool USE_TMA, bool HP_SYM>
 __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -528,7 +544,7 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                     int i = 0;
                     for (; i + KU <= seg; i += KU) {
                         const Lane saved = L;
-                        const bool bad = chunk_fast<USE_HP, KU>(L, kf, xp + i * step, rp + i * step, step, do_minmax,
+                        const bool bad = chunk_fast<USE_HP, HP_SYM, KU>(L, kf, xp + i * step, rp + i * step, step, do_minmax,
                                                                 in_group, logtab_s, exptab_s, mc);
                         if (__any_sync(0xffffffffu, bad)) {  // rare: exact re-run of these samples
                             L = saved;
@@ -820,8 +836,10 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
             }
         }
     }
-    auto kern = p.use_hp ? (tma_ok ? k1_detect<true, true> : k1_detect<true, false>)
-                         : (tma_ok ? k1_detect<false, true> : k1_detect<false, false>);
+    const bool sym = p.use_hp && memcmp(&p.b[0], &p.b[4], 4) == 0 && memcmp(&p.b[1], &p.b[3], 4) == 0;
+    auto kern = p.use_hp ? (tma_ok ? (sym ? k1_detect<true, true, true> : k1_detect<true, true, false>)
+                                   : (sym ? k1_detect<true, false, true> : k1_detect<true, false, false>))
+                         : (tma_ok ? k1_detect<false, true, false> : k1_detect<false, false, false>);
     OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, 32, smem, stream>>>(tmap, a);
     OFP_CUDA_CHECK(cudaGetLastError());

@@ -169,3 +169,18 @@ def test_backtrack_offline_and_streaming(det, golden_dir):
         c, d, _ = od(x[i:i + 128])
         got += [i + int(v) for v in d]
     assert got == g["on_b256s1"].tolist()
+
+
+def test_loud_clipped_signal_exercises_exact_paths(det, orc):
+    """Full-scale, clipped audio: dB values near 0 put the followers into the regime where the float32
+    shortcut of the follower step is not proven exact, so the kernel re-runs those chunks through its
+    exact path; plateaus at +-1.0 hit log10 inputs next to 1.  Results must still equal the oracle."""
+    x, _ = synth.drum_recording(seconds=1.2, seed=77)
+    x = np.clip(x * 6.0, -1.0, 1.0).astype(np.float32)
+    for kw in (dict(), dict(hipass_freq=0, fast_ar=(0.3, 800), slow_ar=(8000, 8000), on_threshold=0.45,
+                            off_threshold=0.45)):
+        ch, on, rel = det.detect_onsets_amplitude(x, sr=96000, **kw)
+        ch_o, on_o, rel_o = orc.detect_onsets_amplitude(x, sr=96000, **kw)
+        assert ch == ch_o and on == on_o
+        assert rel_err(rel, rel_o) <= 1e-5
+        assert float((rel == rel_o).mean()) > 0.9999
