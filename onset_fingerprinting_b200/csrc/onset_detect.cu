@@ -316,26 +316,32 @@ __device__ __forceinline__ void minmax_step(Lane &L, const Coef &k, float r) {
 // U samples are independent instruction streams between the short sequential recurrences.  The rare
 // slow paths are taken after a warp vote, outside the straight-line code.
 //   xs: shared address of the lane's first input sample, rs: of its first rel slot; step = 4*C bytes.
-template <bool USE_HP, int U>
+template <bool USE_HP, int U, bool FROM_DB = false>
 __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
                                       bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
-                                      const MathConst &mc) {
+                                      const MathConst &mc, uint32_t rstep = 0) {
     float h[U], db[U], dr[U], amp[U], aux[U];
     bool redo[U], any = false;
+    if (rstep == 0) rstep = step;
+    if (FROM_DB) {  // warp-specialised consumer: dB values come from the producer warp's ring
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float x = lds_f32(xs + u * step);
-        h[u] = USE_HP ? hp_step(L, k, x) : x;
-    }
+        for (int u = 0; u < U; ++u) db[u] = lds_f32(xs + u * step);
+    } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        db[u] = to_db_fast(h[u], k.floor_db, logtab, mc, aux[u], redo[u]);
-        any |= redo[u];
-    }
-    if (__any_sync(0xffffffffu, any)) {
+        for (int u = 0; u < U; ++u) {
+            const float x = lds_f32(xs + u * step);
+            h[u] = USE_HP ? hp_step(L, k, x) : x;
+        }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (redo[u]) db[u] = db_of(slow_log10(aux[u]), k.floor_db);
+        for (int u = 0; u < U; ++u) {
+            db[u] = to_db_fast(h[u], k.floor_db, logtab, mc, aux[u], redo[u]);
+            any |= redo[u];
+        }
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (redo[u]) db[u] = db_of(slow_log10(aux[u]), k.floor_db);
+        }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {  // detection.py:751 (envelope_follower.c:6-25 twice)
@@ -362,7 +368,7 @@ __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint3
         if (do_minmax) minmax_step(L, k, amp[u]);
         L.bmax = fmaxf(L.bmax, amp[u]);
         L.bmin = fminf(L.bmin, amp[u]);
-        if (store) sts_f32(rs + u * step, amp[u]);
+        if (store) sts_f32(rs + u * rstep, amp[u]);
     }
 }
 
@@ -373,18 +379,24 @@ __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint3
 //   - follower steps in the sliver 0 < |t| < 2^-22 where the float32 shortcut is not proven exact.
 // Returns true when this lane hit a flag; the caller then restores the lane state and re-runs the
 // samples through chunk<> (exact, with branches).
-template <bool USE_HP, bool HP_SYM, int U>
+template <bool USE_HP, bool HP_SYM, int U, bool FROM_DB = false>
 __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
                                            bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
-                                           const MathConst &mc) {
+                                           const MathConst &mc, uint32_t rstep = 0) {
     float h[U], db[U], dr[U], amp[U], aux[U];
     uint32_t flags = 0;
+    if (rstep == 0) rstep = step;
+    if (FROM_DB) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float x = lds_f32(xs + u * step);
-        h[u] = USE_HP ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
+        for (int u = 0; u < U; ++u) db[u] = lds_f32(xs + u * step);
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float x = lds_f32(xs + u * step);
+            h[u] = USE_HP ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
+        }
+        to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
     }
-    to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
     bool sliver = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -403,7 +415,7 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
         if (do_minmax) minmax_step(L, k, amp[u]);
         L.bmax = fmaxf(L.bmax, amp[u]);
         L.bmin = fminf(L.bmin, amp[u]);
-        if (store) sts_f32(rs + u * step, amp[u]);
+        if (store) sts_f32(rs + u * rstep, amp[u]);
     }
     return sliver | (flags != 0);
 }
@@ -431,6 +443,72 @@ __device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch
     for (int i = 0; i < ND; ++i)
         asm volatile("ld.volatile.shared.f64 %0, [%1];" : "=d"(m[i]) : "r"(scratch + 128 + 8 * i) : "memory");
     __syncwarp();
+}
+
+// End of a block (main phase): the reference's threshold FSM (detection.py:759-792) on the block held
+// in shared memory (rcol = this lane's column, element k at rcol[k * C]), onset compaction in the
+// reference's order, and the coalesced copy of the block's rel envelope to HBM.
+__device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float *rcol, const float *relbuf, int lane,
+                                          int g, int c, int rec, int rec0, bool active, unsigned rec_mask,
+                                          unsigned lower_mask, int32_t &cnt, int64_t blk) {
+    const int C = a.p.n_channels, B = a.p.block_size, G = a.G;
+    // ---- block FSM, detection.py:759-792 ----
+    const float last = rcol[(B - 1) * C];
+    const float thr_on = a.p.manual ? a.p.on_thr
+                                    : __fadd_rn(__fmul_rn(L.mx, a.p.on_thr), L.mn);
+    const float thr_off = a.p.manual ? a.p.off_thr
+                                     : __fadd_rn(__fmul_rn(L.mx, a.p.off_thr), L.mn);
+    int oi = 0;
+    bool hit = false;
+    if (!L.state && L.deb < 1 && L.bmax > thr_on) {
+        float before = L.prev;
+        for (int k = 0; k < B; ++k) {
+            const float r = rcol[k * C];
+            if (r > thr_on && before < thr_on) { oi = k; hit = true; break; }
+            before = r;
+        }
+    }
+    if (hit) { L.state = 1; L.deb = a.p.cooldown; }
+    if (L.deb > 0) L.deb -= B;
+    const unsigned hits = __ballot_sync(0xffffffffu, hit && active);
+    int M = 0;  // max first-crossing index over the recording's channels (Q3)
+    if (hits) {
+        for (int jj = 0; jj < C; ++jj) M = max(M, __shfl_sync(0xffffffffu, oi, g * C + jj));
+    }
+    bool off = false;
+    if (M == 0) off = L.bmin < thr_off;
+    else {
+        for (int k = M; k < B; ++k)
+            if (rcol[k * C] < thr_off) { off = true; break; }
+    }
+    if (off) L.state = 0;
+    L.prev = last;
+    if (hits) {
+        const int pos = cnt + __popc(hits & lower_mask);
+        if (hit && active && pos < a.cap) {
+            a.on_ch[static_cast<int64_t>(rec) * a.cap + pos] = c;
+            a.on_idx[static_cast<int64_t>(rec) * a.cap + pos] =
+                static_cast<int32_t>(blk * B + oi);
+        }
+        cnt += __popc(hits & rec_mask);
+    }
+    if (a.rel != nullptr) {
+        __syncwarp();
+        const int nBC = B * C;
+        for (int gi = 0; gi < G; ++gi) {
+            if (rec0 + gi >= a.R) break;
+            float *dst = a.rel + (rec0 + gi) * a.rel_stride + blk * nBC;
+            const float *src = relbuf + gi * a.stride_rel;
+            if (a.rel_vec_ok) {
+                const float4 *s4 = reinterpret_cast<const float4 *>(src);
+                float4 *d4 = reinterpret_cast<float4 *>(dst);
+                for (int i = lane; i < nBC / 4; i += 32) __stcs(d4 + i, s4[i]);
+            } else {
+                for (int i = lane; i < nBC; i += 32) __stcs(dst + i, src[i]);
+            }
+        }
+        __syncwarp();
+    }
 }
 
 constexpr int KU = 8;  // samples per straight-line chunk of the single-warp kernel
@@ -561,63 +639,7 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                     if (kpos == B) {
                         kpos = 0;
                         if (phase == 1) {
-                            // ---- block FSM, detection.py:759-792 ----
-                            const float last = rcol[(B - 1) * C];
-                            const float thr_on = a.p.manual ? a.p.on_thr
-                                                            : __fadd_rn(__fmul_rn(L.mx, a.p.on_thr), L.mn);
-                            const float thr_off = a.p.manual ? a.p.off_thr
-                                                             : __fadd_rn(__fmul_rn(L.mx, a.p.off_thr), L.mn);
-                            int oi = 0;
-                            bool hit = false;
-                            if (!L.state && L.deb < 1 && L.bmax > thr_on) {
-                                float before = L.prev;
-                                for (int k = 0; k < B; ++k) {
-                                    const float r = rcol[k * C];
-                                    if (r > thr_on && before < thr_on) { oi = k; hit = true; break; }
-                                    before = r;
-                                }
-                            }
-                            if (hit) { L.state = 1; L.deb = a.p.cooldown; }
-                            if (L.deb > 0) L.deb -= B;
-                            const unsigned hits = __ballot_sync(0xffffffffu, hit && active);
-                            int M = 0;  // max first-crossing index over the recording's channels (Q3)
-                            if (hits) {
-                                for (int jj = 0; jj < C; ++jj) M = max(M, __shfl_sync(0xffffffffu, oi, g * C + jj));
-                            }
-                            bool off = false;
-                            if (M == 0) off = L.bmin < thr_off;
-                            else {
-                                for (int k = M; k < B; ++k)
-                                    if (rcol[k * C] < thr_off) { off = true; break; }
-                            }
-                            if (off) L.state = 0;
-                            L.prev = last;
-                            if (hits) {
-                                const int pos = cnt + __popc(hits & lower_mask);
-                                if (hit && active && pos < a.cap) {
-                                    a.on_ch[static_cast<int64_t>(rec) * a.cap + pos] = c;
-                                    a.on_idx[static_cast<int64_t>(rec) * a.cap + pos] =
-                                        static_cast<int32_t>(blk * B + oi);
-                                }
-                                cnt += __popc(hits & rec_mask);
-                            }
-                            if (a.rel != nullptr) {
-                                __syncwarp();
-                                const int nBC = B * C;
-                                for (int gi = 0; gi < G; ++gi) {
-                                    if (rec0 + gi >= a.R) break;
-                                    float *dst = a.rel + (rec0 + gi) * a.rel_stride + blk * nBC;
-                                    const float *src = relbuf + gi * a.stride_rel;
-                                    if (a.rel_vec_ok) {
-                                        const float4 *s4 = reinterpret_cast<const float4 *>(src);
-                                        float4 *d4 = reinterpret_cast<float4 *>(dst);
-                                        for (int i = lane; i < nBC / 4; i += 32) __stcs(d4 + i, s4[i]);
-                                    } else {
-                                        for (int i = lane; i < nBC; i += 32) __stcs(dst + i, src[i]);
-                                    }
-                                }
-                                __syncwarp();
-                            }
+                            block_end(L, a, rcol, relbuf, lane, g, c, rec, rec0, active, rec_mask, lower_mask, cnt, blk);
                             ++blk;
                         }
                         L.bmax = -INFINITY; L.bmin = INFINITY;
