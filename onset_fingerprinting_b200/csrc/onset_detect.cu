@@ -379,9 +379,9 @@ __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint3
 //   - follower steps in the sliver 0 < |t| < 2^-22 where the float32 shortcut is not proven exact.
 // Returns true when this lane hit a flag; the caller then restores the lane state and re-runs the
 // samples through chunk<> (exact, with branches).
-template <bool USE_HP, bool HP_SYM, int U, bool FROM_DB = false>
+template <bool USE_HP, bool HP_SYM, int U, bool DO_MM, bool FROM_DB = false>
 __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
-                                           bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
+                                           bool store, uint32_t logtab, uint32_t exptab,
                                            const MathConst &mc, uint32_t rstep = 0) {
     float h[U], db[U], dr[U], amp[U], aux[U];
     uint32_t flags = 0;
@@ -412,7 +412,7 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
     to_amp_vec<U, false>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        if (do_minmax) minmax_step(L, k, amp[u]);
+        if (DO_MM) minmax_step(L, k, amp[u]);
         L.bmax = fmaxf(L.bmax, amp[u]);
         L.bmin = fminf(L.bmin, amp[u]);
         if (store) sts_f32(rs + u * rstep, amp[u]);
@@ -446,14 +446,16 @@ __device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch
 }
 
 // End of a block (main phase): the reference's threshold FSM (detection.py:759-792) on the block held
-// in shared memory (rcol = this lane's column, element k at rcol[k * C]), onset compaction in the
-// reference's order, and the coalesced copy of the block's rel envelope to HBM.
+// in shared memory, onset compaction in the reference's order, and the coalesced copy of the block's
+// rel envelope to HBM.  The block lives in a ring of NR rows per recording starting at row r0
+// (rcol = this lane's column of row 0; NR == B, r0 == 0 for a plain block buffer).
 __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float *rcol, const float *relbuf, int lane,
                                           int g, int c, int rec, int rec0, bool active, unsigned rec_mask,
-                                          unsigned lower_mask, int32_t &cnt, int64_t blk) {
+                                          unsigned lower_mask, int32_t &cnt, int64_t blk, int r0, int NR) {
     const int C = a.p.n_channels, B = a.p.block_size, G = a.G;
+    auto row = [&](int k) { const int i = r0 + k; return (i >= NR ? i - NR : i) * C; };
     // ---- block FSM, detection.py:759-792 ----
-    const float last = rcol[(B - 1) * C];
+    const float last = rcol[row(B - 1)];
     const float thr_on = a.p.manual ? a.p.on_thr
                                     : __fadd_rn(__fmul_rn(L.mx, a.p.on_thr), L.mn);
     const float thr_off = a.p.manual ? a.p.off_thr
@@ -463,7 +465,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     if (!L.state && L.deb < 1 && L.bmax > thr_on) {
         float before = L.prev;
         for (int k = 0; k < B; ++k) {
-            const float r = rcol[k * C];
+            const float r = rcol[row(k)];
             if (r > thr_on && before < thr_on) { oi = k; hit = true; break; }
             before = r;
         }
@@ -479,7 +481,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     if (M == 0) off = L.bmin < thr_off;
     else {
         for (int k = M; k < B; ++k)
-            if (rcol[k * C] < thr_off) { off = true; break; }
+            if (rcol[row(k)] < thr_off) { off = true; break; }
     }
     if (off) L.state = 0;
     L.prev = last;
@@ -495,16 +497,19 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     if (a.rel != nullptr) {
         __syncwarp();
         const int nBC = B * C;
+        const int n1 = min(B, NR - r0) * C;  // elements before the ring wraps
         for (int gi = 0; gi < G; ++gi) {
             if (rec0 + gi >= a.R) break;
             float *dst = a.rel + (rec0 + gi) * a.rel_stride + blk * nBC;
             const float *src = relbuf + gi * a.stride_rel;
             if (a.rel_vec_ok) {
+                // n1 and r0 * C are multiples of 4 whenever the ring is used (chunks of 8 rows)
                 const float4 *s4 = reinterpret_cast<const float4 *>(src);
                 float4 *d4 = reinterpret_cast<float4 *>(dst);
-                for (int i = lane; i < nBC / 4; i += 32) __stcs(d4 + i, s4[i]);
+                const int q1 = n1 / 4, q0 = r0 * C / 4;
+                for (int i = lane; i < nBC / 4; i += 32) __stcs(d4 + i, s4[i < q1 ? q0 + i : i - q1]);
             } else {
-                for (int i = lane; i < nBC; i += 32) __stcs(dst + i, src[i]);
+                for (int i = lane; i < nBC; i += 32) __stcs(dst + i, src[i < n1 ? r0 * C + i : i - n1]);
             }
         }
         __syncwarp();
@@ -622,8 +627,12 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                     int i = 0;
                     for (; i + KU <= seg; i += KU) {
                         const Lane saved = L;
-                        const bool bad = chunk_fast<USE_HP, HP_SYM, KU>(L, kf, xp + i * step, rp + i * step, step, do_minmax,
-                                                                in_group, logtab_s, exptab_s, mc);
+                        // the min/max trackers only rest in the main phase of manual-threshold detectors
+                        const bool bad = do_minmax
+                            ? chunk_fast<USE_HP, HP_SYM, KU, true>(L, kf, xp + i * step, rp + i * step, step, in_group,
+                                                                   logtab_s, exptab_s, mc)
+                            : chunk_fast<USE_HP, HP_SYM, KU, false>(L, kf, xp + i * step, rp + i * step, step, in_group,
+                                                                    logtab_s, exptab_s, mc);
                         if (__any_sync(0xffffffffu, bad)) {  // rare: exact re-run of these samples
                             L = saved;
                             for (int e = 0; e < KU; ++e)
@@ -639,7 +648,7 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                     if (kpos == B) {
                         kpos = 0;
                         if (phase == 1) {
-                            block_end(L, a, rcol, relbuf, lane, g, c, rec, rec0, active, rec_mask, lower_mask, cnt, blk);
+                            block_end(L, a, rcol, relbuf, lane, g, c, rec, rec0, active, rec_mask, lower_mask, cnt, blk, 0, B);
                             ++blk;
                         }
                         L.bmax = -INFINITY; L.bmin = INFINITY;
@@ -668,6 +677,7 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
 
 }  // namespace ofp
 #include "onset_detect_ws.cuh"
+#include "onset_detect_pipe.cuh"
 namespace ofp {
 
 __global__ void k1_reset(DetState st, int64_t n, float floor_db) {
@@ -803,16 +813,21 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.nst = std::max(2, std::min(8, env_int("OFP_K1_STAGES", 2)));
     const int stage_bytes = (a.G * a.TC * 4 + 127) / 128 * 128;
     a.stage_floats = stage_bytes / 4;
+    // software-pipelined kernel (opt-in, OFP_K1_PIPE=1; measured 8 % slower than k1_detect at the same
+    // issue rate, DESIGN.md "K1 experiments"): needs TMA-able input and whole chunks per block and tile;
+    // its envelope buffer is a ring of B + PU rows
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (a.R == 1 || rec_stride % 4 == 0) &&
+                        (n_samples * C < (1ll << 31)) && !env_int("OFP_K1_NO_TMA", 0);
+    const bool pipe = tma_ok && B % PU == 0 && a.T % PU == 0 && env_int("OFP_K1_PIPE", 0) && !env_int("OFP_K1_WS", 0);
+    const int NR = pipe ? B + PU : B;
     const int want = ((C + 3) / 4 * 4) % 32;
-    const int bc4 = (B * C + 3) / 4 * 4;
+    const int bc4 = (NR * C + 3) / 4 * 4;
     a.stride_rel = bc4 + ((want - bc4 % 32) + 32) % 32;
     a.rel_vec_ok = rel != nullptr && (reinterpret_cast<uintptr_t>(rel) % 16 == 0) && (rel_stride % 4 == 0) &&
                    ((B * C) % 4 == 0);
     const size_t smem = K1_SMEM_HEADER + static_cast<size_t>(a.nst) * stage_bytes + static_cast<size_t>(a.G) * a.stride_rel * 4;
     OFP_REQUIRE(smem <= 227 * 1024, "block_size %d x %d channels needs %zu bytes of shared memory per warp (max 232448)",
                 B, C, smem);
-    const bool tma_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (a.R == 1 || rec_stride % 4 == 0) &&
-                        (n_samples * C < (1ll << 31)) && !env_int("OFP_K1_NO_TMA", 0);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     if (tma_ok) {
@@ -859,6 +874,15 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
         }
     }
     const bool sym = p.use_hp && memcmp(&p.b[0], &p.b[4], 4) == 0 && memcmp(&p.b[1], &p.b[3], 4) == 0;
+    if (pipe) {
+        auto kp = p.use_hp ? (sym ? (p.manual ? k1_pipe<true, true, true> : k1_pipe<true, true, false>)
+                                  : (p.manual ? k1_pipe<true, false, true> : k1_pipe<true, false, false>))
+                           : (p.manual ? k1_pipe<false, false, true> : k1_pipe<false, false, false>);
+        OFP_CUDA_CHECK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kp<<<grid, 32, smem, stream>>>(tmap, a, NR);
+        OFP_CUDA_CHECK(cudaGetLastError());
+        return OFP_OK;
+    }
     auto kern = p.use_hp ? (tma_ok ? (sym ? k1_detect<true, true, true> : k1_detect<true, true, false>)
                                    : (sym ? k1_detect<true, false, true> : k1_detect<true, false, false>))
                          : (tma_ok ? k1_detect<false, true, false> : k1_detect<false, false, false>);
