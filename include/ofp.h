@@ -167,6 +167,14 @@ int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride
                    int32_t d, int32_t direction, int32_t take_abs, int32_t zero_left, int32_t cutoff, int32_t tol,
                    int32_t shift, int32_t max_section, int32_t *out_onsets_dev, int32_t *out_lags_dev,
                    int32_t *out_status_dev, void *stream);
+/* Same with flags: bit 0 = every section runs to the END of its recording instead of stopping
+ * lookaround samples after the last onset -- the section Multilaterate3D.locate cuts from its ring
+ * buffer (multilateration.py:457-466: rec_audio[-i - 1:]). */
+int ofp_fix_onsets_ex(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                      const int32_t *hit_rec_dev, const int32_t *onsets_dev, int32_t n_hits, int32_t filter_size,
+                      int32_t d, int32_t direction, int32_t take_abs, int32_t zero_left, int32_t cutoff,
+                      int32_t tol, int32_t shift, int32_t max_section, int32_t flags, int32_t *out_onsets_dev,
+                      int32_t *out_lags_dev, int32_t *out_status_dev, void *stream);
 int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section);
 
 /* cross_correlation_lag for n_pairs pairs of equal length n: x_dev, y_dev [P, n] float32;
@@ -195,6 +203,37 @@ int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, const float
                     const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
                     double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
                     int32_t onset_stride, int32_t n_hits, double *xy_dev, int32_t *status_dev, void *stream);
+
+/* solve_trilateration / solve_trilateration_3d (multilateration.py:170-316) with explicit seeds:
+ * scipy.optimize.fsolve(xtol, maxfev, fprime) = MINPACK hybrj for n = 2, one problem per row.
+ *   problems_dev [P, 11] float64 = sensor_a xyz, sensor_b xyz, sensor_origin xyz, delta_d_a, delta_d_b
+ *   (z = 0 for the 2-D form); seeds_dev [P, 2]; xy_dev [P, 2] = fsolve's root (also when not
+ *   converged); ier_dev [P] (1 = converged, the reference returns None otherwise); nfev_dev [P] or NULL. */
+int ofp_solve_trilateration(const double *problems_dev, const double *seeds_dev, int32_t n_problems, double xtol,
+                            int32_t maxfev, double *xy_dev, int32_t *ier_dev, int32_t *nfev_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Helper twins around the detector / lag path (csrc/onset_tools.cu)
+ * ------------------------------------------------------------------------------------- */
+
+/* ButterworthFilter.__call__ (detection.py:487-501) = scipy.signal.lfilter(b, a, x, axis=0, zi): direct
+ * form II transposed in float32.  b_host, a_host [order+1] float32 (a[0] == 1); x_dev, y_dev
+ * [n_samples, n_channels]; zi_dev [order, n_channels] carried state, updated in place. */
+int ofp_lfilter(const float *b_host, const float *a_host, int32_t order, const float *x_dev, float *y_dev,
+                float *zi_dev, int32_t n_samples, int32_t n_channels, void *stream);
+/* filter_data (detection.py:355-370): direction 1 = "up" (zero where the first difference is negative),
+ * 2 = "down"; x_dev, out_dev [n_samples, n_channels], out of place. */
+int ofp_filter_data(const float *x_dev, float *out_dev, int64_t n_samples, int32_t n_channels, int32_t direction,
+                    void *stream);
+/* detect_onset_region (detection.py:454-484) for n_signals rows of audio_dev [n_signals, len]:
+ * out_dev [n_signals] = start of the loud region around onsets_dev[i]. */
+int ofp_detect_onset_region(const float *audio_dev, int32_t n_signals, int64_t len, const int32_t *onsets_dev,
+                            int32_t n, int32_t median_filter_size, float threshold_factor, int32_t *out_dev,
+                            void *stream);
+/* np.correlate(x, y, "full") as find_lag / find_lag_multi use it (multilateration.py:878-899):
+ * x_dev, y_dev [P, n] -> out_dev [P, 2n-1] (double accumulation, rounded once). */
+int ofp_correlate_full(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, float *out_dev,
+                       void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Streaming cross-correlation -- twin of the CPython extension online_cc

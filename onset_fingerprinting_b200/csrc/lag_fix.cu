@@ -28,6 +28,7 @@ constexpr int CC_UN = 4;  // time steps per unrolled iteration
 
 struct FixParams {
     int32_t filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift;
+    int32_t to_end;  // section runs to the end of the recording (streaming ring, multilateration.py:457-466)
 };
 
 struct K4Args {
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_fix(const K4Args a) {
         }
         const int64_t s0 = og[idx[0]] - look;    // detection.py:419
         int64_t s1 = og[idx[C - 1]] + look;
-        if (s1 > a.n_samples) s1 = a.n_samples;
+        if (s1 > a.n_samples || fp.to_end) s1 = a.n_samples;
         const int64_t L0 = s1 - s0;
         if (st == FIX_OK && (s0 < 0 || L0 - fp.d < 1)) st = FIX_DEGENERATE;
         if (st == FIX_OK && L0 > a.Lmax) st = FIX_TOO_LONG;
@@ -566,6 +567,16 @@ int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride
                    int32_t d, int32_t direction, int32_t take_abs, int32_t zero_left, int32_t cutoff, int32_t tol,
                    int32_t shift, int32_t max_section, int32_t *out_onsets_dev, int32_t *out_lags_dev,
                    int32_t *out_status_dev, void *stream) {
+    return ofp_fix_onsets_ex(audio_dev, n_samples, rec_stride, n_channels, hit_rec_dev, onsets_dev, n_hits,
+                             filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift, max_section, 0,
+                             out_onsets_dev, out_lags_dev, out_status_dev, stream);
+}
+
+int ofp_fix_onsets_ex(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                      const int32_t *hit_rec_dev, const int32_t *onsets_dev, int32_t n_hits, int32_t filter_size,
+                      int32_t d, int32_t direction, int32_t take_abs, int32_t zero_left, int32_t cutoff,
+                      int32_t tol, int32_t shift, int32_t max_section, int32_t flags, int32_t *out_onsets_dev,
+                      int32_t *out_lags_dev, int32_t *out_status_dev, void *stream) {
     OFP_REQUIRE(audio_dev && onsets_dev && out_onsets_dev && out_status_dev, "null argument");
     OFP_REQUIRE(n_channels >= 2 && n_channels <= 32, "n_channels must be in 2..32");
     OFP_REQUIRE(filter_size >= 1 && filter_size <= 15, "filter_size must be in 1..15");
@@ -575,7 +586,7 @@ int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride
     K4Args a;
     a.audio = audio_dev; a.rec_stride = rec_stride; a.n_samples = n_samples; a.C = n_channels; a.H = n_hits;
     a.Lmax = max_section; a.hit_rec = hit_rec_dev; a.onsets = onsets_dev;
-    a.fp = FixParams{filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift};
+    a.fp = FixParams{filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift, flags & 1};
     a.out_onsets = out_onsets_dev; a.out_lags = out_lags_dev; a.out_status = out_status_dev;
     const int smem = ofp_fix_onsets_smem_bytes(n_channels, max_section);
     OFP_REQUIRE(smem <= 220 * 1024, "max_section %d x %d channels needs %d bytes of shared memory", max_section,

@@ -350,9 +350,39 @@ __global__ void k5_locate(const K5Args a) {
     a.status[h] = st;
 }
 
+// solve_trilateration / solve_trilateration_3d (multilateration.py:170-316) with an explicit seed, one
+// thread per problem: prob [P, 11] = (sensor_a xyz, sensor_b xyz, sensor_origin xyz, delta_d_a, delta_d_b).
+__global__ void k5_solve(const double *prob, const double *seed, int P, double xtol, int maxfev, double *xy,
+                         int32_t *ier_out, int32_t *nfev_out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double *v = prob + 11 * static_cast<int64_t>(p);
+    tri_problem q;
+    q.xa = v[0]; q.ya = v[1]; q.za = v[2]; q.xb = v[3]; q.yb = v[4]; q.zb = v[5];
+    q.xo = v[6]; q.yo = v[7]; q.zo = v[8]; q.da = v[9]; q.db = v[10];
+    double x[2] = {seed[2 * p], seed[2 * p + 1]};
+    int nfev = 0;
+    const int ier = hybrj2(&q, x, xtol, maxfev, &nfev);
+    xy[2 * static_cast<int64_t>(p)] = x[0];
+    xy[2 * static_cast<int64_t>(p) + 1] = x[1];
+    ier_out[p] = ier;
+    if (nfev_out) nfev_out[p] = nfev;
+}
+
 }  // namespace ofp
 
 using namespace ofp;
+
+extern "C" int ofp_solve_trilateration(const double *problems_dev, const double *seeds_dev, int32_t n_problems,
+                                       double xtol, int32_t maxfev, double *xy_dev, int32_t *ier_dev,
+                                       int32_t *nfev_dev, void *stream) {
+    OFP_REQUIRE(problems_dev && seeds_dev && xy_dev && ier_dev, "null argument");
+    if (n_problems == 0) return OFP_OK;
+    k5_solve<<<(n_problems + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        problems_dev, seeds_dev, n_problems, xtol, maxfev, xy_dev, ier_dev, nfev_dev);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
 
 extern "C" int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
                                int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,

@@ -1,0 +1,216 @@
+// Small device twins of the helper functions around the detector / lag path (sm_100a):
+//   ofp_lfilter              ButterworthFilter.__call__ = scipy.signal.lfilter(b, a, x, axis=0, zi)  (detection.py:487-501)
+//   ofp_filter_data          filter_data                                                        (detection.py:355-370)
+//   ofp_detect_onset_region  detect_onset_region                                                (detection.py:454-484)
+//   ofp_correlate_full       np.correlate(a, b, "full") as used by find_lag / find_lag_multi     (multilateration.py:878-899)
+// None of them is on the throughput-critical path (they are per-call helpers of a few hundred
+// samples); they exist so that the whole detection.py / multilateration.py surface runs on the device.
+#include "ofp_common.cuh"
+
+namespace ofp {
+
+constexpr int LF_MAX_ORDER = 8;
+
+struct LfArgs {
+    float b[LF_MAX_ORDER + 1], a[LF_MAX_ORDER + 1];
+    int32_t order, n, C;
+    const float *x;
+    float *y, *zi;
+};
+
+// scipy's float_filt (direct form II transposed), float32, evaluated left to right without
+// contraction: y = z0 + b0*x; z[i] = (z[i+1] + x*b[i+1]) - y*a[i+1]; z[last] = x*b[last] - y*a[last].
+__global__ void k_lfilter(const LfArgs q) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= q.C) return;
+    float z[LF_MAX_ORDER];
+#pragma unroll
+    for (int i = 0; i < LF_MAX_ORDER; ++i) z[i] = i < q.order ? q.zi[i * q.C + c] : 0.f;
+    for (int t = 0; t < q.n; ++t) {
+        const float x = q.x[static_cast<int64_t>(t) * q.C + c];
+        const float y = q.order > 0 ? __fadd_rn(z[0], __fmul_rn(q.b[0], x)) : __fmul_rn(q.b[0], x);
+#pragma unroll
+        for (int i = 0; i < LF_MAX_ORDER; ++i) {
+            if (i < q.order - 1)
+                z[i] = __fsub_rn(__fadd_rn(z[i + 1], __fmul_rn(x, q.b[i + 1])), __fmul_rn(y, q.a[i + 1]));
+            else if (i == q.order - 1)
+                z[i] = __fsub_rn(__fmul_rn(x, q.b[i + 1]), __fmul_rn(y, q.a[i + 1]));
+        }
+        q.y[static_cast<int64_t>(t) * q.C + c] = y;
+    }
+#pragma unroll
+    for (int i = 0; i < LF_MAX_ORDER; ++i)
+        if (i < q.order) q.zi[i * q.C + c] = z[i];
+}
+
+// filter_data: diff = x[t] - x[t-1] (0 for the first row); "up" zeroes samples with diff < 0,
+// "down" those with diff > 0.  Out of place (the reference masks with the diff of the ORIGINAL x).
+__global__ void k_filter_data(const float *x, float *out, int64_t n, int C, int direction) {
+    const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (e >= n * C) return;
+    const float v = x[e];
+    const float diff = e >= C ? __fsub_rn(v, x[e - C]) : 0.f;
+    const bool kill = direction == 1 ? diff < 0.f : diff > 0.f;
+    out[e] = kill ? 0.f : v;
+}
+
+// detect_onset_region, one warp-sized block per signal.  audio [P, len] float32.
+//   region = audio[start:end], start = max(onset - n/2, 0), end = min(onset + n/2, len)
+//   filtered = scipy.signal.medfilt(|region|, ks) (zero padded)
+//   binary = filtered > factor * max(filtered)        (float32, numpy >= 2 scalar rules)
+//   binary_opening(binary, ones(5)) = erosion then dilation with border value 0
+//   -> start + index of the first True (0 if none)
+__global__ void k_onset_region(const float *audio, int64_t len, const int32_t *onsets, int32_t n, int32_t ks,
+                               float factor, int32_t *out) {
+    extern __shared__ float sm[];
+    const int p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int64_t on = onsets[p];
+    int64_t s = on - n / 2, e = on + n / 2;
+    // python slicing of audio[start:end] with start clamped at 0 and end at len
+    if (s < 0) s = 0;
+    if (e > len) e = len;
+    if (e < 0) { e += len; if (e < 0) e = 0; }
+    if (s > len) s = len;
+    const int m = e > s ? static_cast<int>(e - s) : 0;
+    float *a = sm, *f = sm + m;
+    unsigned char *b0 = reinterpret_cast<unsigned char *>(f + m), *b1 = b0 + m;
+    const float *src = audio + static_cast<int64_t>(p) * len + s;
+    for (int i = tid; i < m; i += nt) a[i] = fabsf(src[i]);
+    __syncthreads();
+    const int half = ks / 2;
+    float mx = -INFINITY;
+    for (int i = tid; i < m; i += nt) {
+        // median of ks values (zeros outside) by rank counting
+        float med = 0.f;
+        for (int u = 0; u < ks; ++u) {
+            const int iu = i - half + u;
+            const float vu = (iu >= 0 && iu < m) ? a[iu] : 0.f;
+            int rank = 0;
+            for (int w = 0; w < ks; ++w) {
+                const int iw = i - half + w;
+                const float vw = (iw >= 0 && iw < m) ? a[iw] : 0.f;
+                rank += (vw < vu) || (vw == vu && w < u);
+            }
+            if (rank == half) med = vu;
+        }
+        f[i] = med;
+        mx = fmaxf(mx, med);
+    }
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    float gm = -INFINITY;
+    for (int w = 0; w < (nt + 31) / 32; ++w) gm = fmaxf(gm, red[w]);
+    const float thr = __fmul_rn(factor, gm);
+    for (int i = tid; i < m; i += nt) b0[i] = f[i] > thr;
+    __syncthreads();
+    for (int i = tid; i < m; i += nt) {  // erosion, structure ones(5), outside = 0
+        bool all = true;
+        for (int k = -2; k <= 2; ++k) all = all && (i + k >= 0 && i + k < m && b0[i + k]);
+        b1[i] = all;
+    }
+    __syncthreads();
+    int first = INT32_MAX;
+    for (int i = tid; i < m; i += nt) {  // dilation
+        bool any = false;
+        for (int k = -2; k <= 2; ++k) any = any || (i + k >= 0 && i + k < m && b1[i + k]);
+        if (any) first = min(first, i);
+    }
+    __shared__ int redi[32];
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_down_sync(0xffffffffu, first, o));
+    if ((tid & 31) == 0) redi[tid >> 5] = first;
+    __syncthreads();
+    if (tid == 0) {
+        int g = INT32_MAX;
+        for (int w = 0; w < (nt + 31) / 32; ++w) g = min(g, redi[w]);
+        out[p] = static_cast<int32_t>(s + (g == INT32_MAX ? 0 : g));
+    }
+}
+
+// np.correlate(x, y, "full")[k] = sum_i x[i + k - (n-1)] * y[i], double accumulation in index order,
+// rounded once to float32.  x, y [P, n]; out [P, 2n-1].
+__global__ void k_correlate_full(const float *x, const float *y, int n, float *out) {
+    extern __shared__ float sm[];
+    float *xs = sm, *ys = sm + n;
+    const int p = blockIdx.x;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        xs[i] = x[static_cast<int64_t>(p) * n + i];
+        ys[i] = y[static_cast<int64_t>(p) * n + i];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * n - 1; k += blockDim.x) {
+        const int m = k - (n - 1);
+        const int i0 = m < 0 ? -m : 0, i1 = m > 0 ? n - m : n;
+        double acc = 0.0;
+        for (int i = i0; i < i1; ++i) acc = __fma_rn(static_cast<double>(xs[i + m]), static_cast<double>(ys[i]), acc);
+        out[static_cast<int64_t>(p) * (2 * n - 1) + k] = __double2float_rn(acc);
+    }
+}
+
+}  // namespace ofp
+
+using namespace ofp;
+
+extern "C" {
+
+int ofp_lfilter(const float *b_host, const float *a_host, int32_t order, const float *x_dev, float *y_dev,
+                float *zi_dev, int32_t n_samples, int32_t n_channels, void *stream) {
+    OFP_REQUIRE(b_host && a_host && x_dev && y_dev && zi_dev, "null argument");
+    OFP_REQUIRE(order >= 1 && order <= LF_MAX_ORDER, "filter order must be in 1..%d", LF_MAX_ORDER);
+    OFP_REQUIRE(n_samples >= 0 && n_channels >= 1, "bad size");
+    OFP_REQUIRE(a_host[0] == 1.0f, "a[0] must be 1 (scipy.signal.butter output)");
+    if (n_samples == 0) return OFP_OK;
+    LfArgs q;
+    for (int i = 0; i <= LF_MAX_ORDER; ++i) {
+        q.b[i] = i <= order ? b_host[i] : 0.f;
+        q.a[i] = i <= order ? a_host[i] : 0.f;
+    }
+    q.order = order; q.n = n_samples; q.C = n_channels; q.x = x_dev; q.y = y_dev; q.zi = zi_dev;
+    k_lfilter<<<(n_channels + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(q);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_filter_data(const float *x_dev, float *out_dev, int64_t n_samples, int32_t n_channels, int32_t direction,
+                    void *stream) {
+    OFP_REQUIRE(x_dev && out_dev && x_dev != out_dev, "null or aliased argument");
+    OFP_REQUIRE(direction == 1 || direction == 2, "direction must be 1 (\"up\") or 2 (\"down\")");
+    const int64_t total = n_samples * n_channels;
+    if (total <= 0) return OFP_OK;
+    k_filter_data<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x_dev, out_dev, n_samples, n_channels, direction);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_detect_onset_region(const float *audio_dev, int32_t n_signals, int64_t len, const int32_t *onsets_dev,
+                            int32_t n, int32_t median_filter_size, float threshold_factor, int32_t *out_dev,
+                            void *stream) {
+    OFP_REQUIRE(audio_dev && onsets_dev && out_dev, "null argument");
+    OFP_REQUIRE(n >= 0 && n <= 8192, "n must be in 0..8192");
+    OFP_REQUIRE(median_filter_size >= 1 && median_filter_size % 2 == 1 && median_filter_size <= 31,
+                "kernel_size must be odd and <= 31");
+    if (n_signals == 0) return OFP_OK;
+    const int m = n + 2;
+    const size_t smem = static_cast<size_t>(m) * (2 * sizeof(float) + 2);
+    k_onset_region<<<n_signals, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        audio_dev, len, onsets_dev, n, median_filter_size, threshold_factor, out_dev);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_correlate_full(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, float *out_dev,
+                       void *stream) {
+    OFP_REQUIRE(x_dev && y_dev && out_dev, "null argument");
+    OFP_REQUIRE(n >= 1 && n <= 24 * 1024, "signal length must be in 1..24576");
+    if (n_pairs == 0) return OFP_OK;
+    const size_t smem = 2 * static_cast<size_t>(n) * sizeof(float);
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(k_correlate_full, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    k_correlate_full<<<n_pairs, 256, smem, static_cast<cudaStream_t>(stream)>>>(x_dev, y_dev, n, out_dev);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+}  // extern "C"

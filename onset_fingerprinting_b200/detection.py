@@ -210,7 +210,14 @@ def detect_onsets(x: np.ndarray, sr: int = 96000, method="amp"):
     """detection.py:12-16."""
     if method == "amp":
         return detect_onsets_amplitude(x, sr=sr)
-    raise NotImplementedError("spectral method: see spectral.py")
+    return detect_onsets_spectral(x, sr=sr)
+
+
+def detect_onsets_spectral(x: np.ndarray, n_fft: int = 256, hop: int = 32, sr: int = 96000, return_oe: bool = False):
+    """detection.py:89-128 (K2: csrc/spectral_flux.cu, see spectral.py for the librosa restatement)."""
+    from . import spectral
+
+    return spectral.detect_onsets_spectral(x, n_fft=n_fft, hop=hop, sr=sr, return_oe=return_oe)
 
 
 class AmplitudeOnsetDetector:
@@ -232,6 +239,7 @@ class AmplitudeOnsetDetector:
         self.floor, self.on_threshold, self.off_threshold = floor, on_threshold, off_threshold
         self.manual = bool(on_threshold > 1)
         self.cooldown, self.sr = cooldown, sr
+        self._hipass, self._fast_ar, self._slow_ar = hipass_freq, fast_ar, slow_ar
         self._det = BatchedOnsetDetector(1, n_signals, block_size, floor=floor, hipass_freq=hipass_freq,
                                          fast_ar=fast_ar, slow_ar=slow_ar, on_threshold=on_threshold,
                                          off_threshold=off_threshold, cooldown=cooldown, sr=sr)
@@ -251,15 +259,114 @@ class AmplitudeOnsetDetector:
     def init_minmax_tracker(self, x):
         self._det.warmup(x[None] if x.ndim == 2 else x)
 
+    def backtrack_onsets(self, channels, deltas):
+        """detection.py:800-825 on the detector's envelope history (the last backtrack_buffer_size rows
+        ending with the block passed to the latest call)."""
+        if self._hist is None:
+            raise AttributeError("backtrack_onsets needs backtrack=True and at least one processed block")
+        torch = self._det.torch
+        k = len(channels)
+        ch = torch.zeros((1, self.n_signals), dtype=torch.int32, device="cuda")
+        dl = torch.zeros((1, self.n_signals), dtype=torch.int32, device="cuda")
+        ch[0, :k] = torch.as_tensor(np.asarray(channels, np.int32))
+        dl[0, :k] = torch.as_tensor(np.asarray(deltas, np.int32))
+        cnt = torch.tensor([k], dtype=torch.int32, device="cuda")
+        backtrack_onsets_batch(self._hist, ch, dl, cnt, self.block_size, self._bt[0], self._bt[1], streaming=True)
+        return dl[0, :k].cpu().numpy().astype(np.int64)
+
+    def init(self, x):
+        """detection.py:842-888: calibrate per-channel thresholds and noise level on a take x [N, C] that
+        holds silence and full-level playing.  The envelope followers run through ofp_ar_envelope and
+        the high-pass through ofp_lfilter; the statistics (median / max / running maximum) are torch
+        reductions on the device.  Like the reference it does not touch the min/max trackers __call__
+        uses; it sets mins, maxs, on_threshold, off_threshold, noise_max and leaves the followers
+        settled at the start of x."""
+        torch = self._det.torch
+        p = self._det.params
+        xd = _to_dev(np.ascontiguousarray(x, dtype=np.float32), torch)
+        st = self._det.state()
+        hp = None
+        if p.use_hp:  # the detector's own filter, state carried over (detection.py:852-853)
+            hp = ButterworthFilter(self._hipass, self.n_signals, 4, self.sr, "high")
+            hp.zi = torch.from_numpy(np.concatenate([st[f"z{i}"] for i in range(4)], 0)).cuda()
+            xd = hp(xd)
+        xd = 20 * torch.log10(torch.abs(xd + 1e-10))
+        B, sr = self.block_size, self.sr
+        fast = AREnvelopeFollower(torch.from_numpy(st["yf"]).expand(B, -1), self._fast_ar[0], self._fast_ar[1])
+        slow = AREnvelopeFollower(torch.from_numpy(st["ys"]).expand(B, -1), self._slow_ar[0], self._slow_ar[1])
+
+        def run(block):
+            # whole blocks only: with a shorter trailing block the reference's C follower reads past the
+            # end of its input (num_samples is fixed at block_size, detection.py:533-538)
+            if block.shape[0] != B:
+                return torch.zeros_like(block)
+            block = block.contiguous()
+            return fast(block).clone() - slow(block)
+
+        for i in range(int(0.1 * sr), int(0.5 * sr), B):
+            run(xd[i:i + B])
+        rel = torch.zeros_like(xd)
+        for i in range(0, len(xd), B):
+            rel[i:i + B] = run(xd[i:i + B])
+        self.mins = torch.quantile(rel[:sr], 0.5, dim=0).cpu().numpy()
+        self.maxs = rel.max(0).values.cpu().numpy()
+        self.on_threshold = self.maxs * self.on_threshold + self.mins
+        self.off_threshold = self.maxs * self.off_threshold + self.mins
+        w = int(sr * 0.01)
+        pad_l, pad_r = w // 2, w - 1 - w // 2
+        mf = torch.nn.functional.max_pool1d(
+            torch.nn.functional.pad(rel.T[None], (pad_l, pad_r), mode="reflect"), w, stride=1)[0].T
+        self.noise_max = torch.quantile(mf, 0.5, dim=0).cpu().numpy()
+        xr = torch.flip(xd[:sr], dims=(0,)).contiguous()
+        for i in range(0, sr, B):
+            run(xr[i:i + B])
+        # hand the settled filter / follower state back to the detector __call__ uses
+        if hp is not None:
+            zi = hp.zi.cpu().numpy()
+            for i in range(4):
+                st[f"z{i}"] = zi[i:i + 1].copy()
+        st["yf"], st["ys"] = fast.y[-1:].cpu().numpy(), slow.y[-1:].cpu().numpy()
+        self._det.load_state(st)
+
+
+class ButterworthFilter:
+    """detection.py:487-501: Butterworth filter applied to n signals in parallel, state carried between
+    calls.  The coefficients come from scipy.signal.butter on the host exactly as in the reference
+    (cast to float32); the filtering is ofp_lfilter (scipy's float32 direct form II transposed)."""
+
+    def __init__(self, cutoff, n, order=2, sr=44100, btype="high"):
+        from scipy import signal as sig
+
+        torch = _lib.require_cuda()
+        b, a = sig.butter(order, cutoff, btype=btype, analog=False, output="ba", fs=sr)
+        self.b, self.a = np.float32(b), np.float32(a)
+        self.order = len(self.b) - 1  # band filters double the order
+        self.zi = torch.zeros((self.order, n), dtype=torch.float32, device="cuda")
+        self.n = n
+
+    def __call__(self, x):
+        torch = _lib.require_cuda()
+        xd = _to_dev(x, torch)
+        assert xd.dim() == 2 and xd.shape[1] == self.n
+        y = torch.empty_like(xd)
+        b = (C.c_float * (self.order + 1))(*self.b.tolist())
+        a = (C.c_float * (self.order + 1))(*self.a.tolist())
+        check(_lib.lib().ofp_lfilter(b, a, C.c_int32(self.order), ptr(xd), ptr(y), ptr(self.zi),
+                                     C.c_int32(xd.shape[0]), C.c_int32(self.n), stream_ptr()))
+        return y.cpu().numpy() if isinstance(x, np.ndarray) else y
+
 
 class AREnvelopeFollower:
     """detection.py:504-538 over ofp_ar_envelope (twin of envelope_follower.c:6-25)."""
 
-    def __init__(self, x0: np.ndarray, attack=3, release=383):
+    def __init__(self, x0, attack=3, release=383):
         torch = _lib.require_cuda()
         self.attack = np.float32(1 / attack)
         self.release = np.float32(1 / release)
-        self.y = torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float32)).cuda()
+        if isinstance(x0, np.ndarray):
+            self.y = torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float32)).cuda()
+        else:
+            self.y = x0.to(device="cuda", dtype=torch.float32).contiguous().clone()
         self.n, self.size = x0.shape
 
     def __call__(self, x):
@@ -355,10 +462,13 @@ def find_onset_groups_batch(channels, onsets, counts, n_channels: int, max_dista
 
 def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 0, onset_direction=None,
                      take_abs: bool = False, zero_left: bool = False, normalization_cutoff: int = 10,
-                     onset_tolerance: int = 30, shift_onsets: int = 0, max_section: Optional[int] = None):
+                     onset_tolerance: int = 30, shift_onsets: int = 0, max_section: Optional[int] = None,
+                     to_end: bool = False):
     """fix_onsets (detection.py:373-451) for H onset groups in one launch.
     audio [R, N, C] float32 (device or numpy); hit_rec [H] int32 or None (hit h in recording h);
-    hit_onsets [H, C] int32.  Returns (onsets [H, C], lags [H, C], status [H]) device tensors."""
+    hit_onsets [H, C] int32.  Returns (onsets [H, C], lags [H, C], status [H]) device tensors.
+    to_end: sections run to the end of the recording (the ring-buffer sections of
+    Multilaterate3D.locate, multilateration.py:457-466)."""
     torch = _lib.require_cuda()
     audio = _to_dev(audio, torch)
     R, N, Cn = audio.shape
@@ -374,19 +484,20 @@ def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 
             if bool(complete.any()):
                 rows = hit_onsets[complete]
                 span = int((rows.max(1).values - rows.min(1).values).max().item())
-        max_section = span + 2 * look + 1
+        max_section = N if to_end else span + 2 * look + 1
         # shared-memory budget of one CTA; longer sections are flagged OFP_FIX_TOO_LONG
         budget = (200 * 1024 - 128) // (16 + 8 * Cn)
         max_section = min(max_section, budget)
     out = torch.empty_like(hit_onsets)
     lags = torch.empty_like(hit_onsets)
     status = torch.empty((H,), dtype=torch.int32, device="cuda")
-    check(_lib.lib().ofp_fix_onsets(ptr(audio), C.c_int64(N), C.c_int64(audio.stride(0)), C.c_int32(Cn),
-                                    ptr(hit_rec), ptr(hit_onsets), C.c_int32(H), C.c_int32(filter_size),
-                                    C.c_int32(d), C.c_int32(_DIRECTION[onset_direction]), C.c_int32(bool(take_abs)),
-                                    C.c_int32(bool(zero_left)), C.c_int32(normalization_cutoff),
-                                    C.c_int32(onset_tolerance), C.c_int32(shift_onsets), C.c_int32(max_section),
-                                    ptr(out), ptr(lags), ptr(status), stream_ptr()))
+    check(_lib.lib().ofp_fix_onsets_ex(ptr(audio), C.c_int64(N), C.c_int64(audio.stride(0)), C.c_int32(Cn),
+                                       ptr(hit_rec), ptr(hit_onsets), C.c_int32(H), C.c_int32(filter_size),
+                                       C.c_int32(d), C.c_int32(_DIRECTION[onset_direction]),
+                                       C.c_int32(bool(take_abs)), C.c_int32(bool(zero_left)),
+                                       C.c_int32(normalization_cutoff), C.c_int32(onset_tolerance),
+                                       C.c_int32(shift_onsets), C.c_int32(max_section), C.c_int32(int(to_end)),
+                                       ptr(out), ptr(lags), ptr(status), stream_ptr()))
     return out, lags, status
 
 
@@ -445,3 +556,57 @@ def adjust_onset(onsets, x: np.ndarray, y: np.ndarray, new_lag: int):
     if a == LAG_NONE:
         raise ValueError("operands could not be broadcast together (adjust_onset, detection.py:335)")
     return a, b
+
+
+def adjust_onset_rel(onsets, relx: np.ndarray, rely: np.ndarray, new_lag: int):
+    """detection.py:271-296: move the onset whose relative envelope rises more towards the target lag.
+    Four envelope reads and one comparison per pair -- host arithmetic on whatever array type the
+    envelopes are (numpy, or device tensors straight from detect_onsets_amplitude_batch)."""
+    oa, ob = onsets[0], onsets[1]
+    lag_diff = (ob - oa) - new_lag
+    da = relx[oa + lag_diff] - relx[oa]
+    db = rely[ob - lag_diff] - rely[ob]
+    if da > db:
+        oa += lag_diff
+    else:
+        ob -= lag_diff
+    return oa, ob
+
+
+def filter_data(x, direction: str):
+    """detection.py:355-370: zero the samples whose first difference (along axis 0) has the wrong sign,
+    in place, and return x (numpy array or device tensor, [N] or [N, C])."""
+    if direction not in ("up", "down"):
+        raise RuntimeError(f"Unknown onset direction {direction=}!")
+    torch = _lib.require_cuda()
+    is_np = isinstance(x, np.ndarray)
+    xd = _to_dev(x, torch)
+    n = xd.shape[0]
+    cn = int(xd.numel() // max(n, 1))
+    out = torch.empty_like(xd)
+    check(_lib.lib().ofp_filter_data(ptr(xd), ptr(out), C.c_int64(n), C.c_int32(cn),
+                                     C.c_int32(_DIRECTION[direction]), stream_ptr()))
+    if is_np:
+        x[...] = out.cpu().numpy()
+    else:
+        x.copy_(out)
+    return x
+
+
+def detect_onset_region_batch(audio, detected_onsets, n: int = 256, median_filter_size: int = 5,
+                              threshold_factor: float = 0.5):
+    """detect_onset_region for P signals at once: audio [P, len], detected_onsets [P] -> int32 [P] tensor."""
+    torch = _lib.require_cuda()
+    ad = _to_dev(audio, torch)
+    on = torch.as_tensor(np.asarray(detected_onsets, np.int32)).to(device="cuda", dtype=torch.int32).contiguous()
+    out = torch.empty_like(on)
+    check(_lib.lib().ofp_detect_onset_region(ptr(ad), C.c_int32(ad.shape[0]), C.c_int64(ad.shape[1]), ptr(on),
+                                             C.c_int32(n), C.c_int32(median_filter_size),
+                                             C.c_float(threshold_factor), ptr(out), stream_ptr()))
+    return out
+
+
+def detect_onset_region(audio, detected_onset, n=256, median_filter_size=5, threshold_factor=0.5):
+    """detection.py:454-484: start of the loud part around a detected onset in a 1-D signal."""
+    a = np.ascontiguousarray(audio, dtype=np.float32)[None] if isinstance(audio, np.ndarray) else audio[None]
+    return int(detect_onset_region_batch(a, [int(detected_onset)], n, median_filter_size, threshold_factor)[0].item())

@@ -115,22 +115,119 @@ def lag_map_3d(mic_a, mic_b, d=DIAMETER, sr=96000, scale=1, medium=MEDIUM, tol=1
     return _lag_map(mic_a, mic_b, int(np.round(d, 1) * scale) // 2, tol, scale, c, sr)
 
 
-def find_lag(a: np.ndarray, b: np.ndarray):
-    """multilateration.py:878-886: argmax of the full cross-correlation, evaluated by K4's CC kernel
-    with the legal window covering every lag and the contribution normaliser disabled (cutoff > n)."""
-    from . import detection
+def correlate_full(a, b):
+    """np.correlate(a, b, "full") on the device (ofp_correlate_full): a, b [n] or [P, n] float32 ->
+    float32 [2n-1] / [P, 2n-1] (numpy in, numpy out; tensors in, tensor out)."""
+    from .detection import _to_dev
 
-    n = len(a)
-    # full window: cc[n - l1 : n - l0] with l1 = n, l0 = -(n - 1); cutoff huge -> constant divisor
-    r = detection.cross_correlation_lag(a, b, legal_lags=(-(n - 1), n), normalization_cutoff=1 << 30)
-    # cross_correlation_lag returns l1 - argmax = n - argmax; find_lag returns argmax - (n - 1)
-    return (n - r) - (n - 1)
+    torch = _lib.require_cuda()
+    is_np = isinstance(a, np.ndarray)
+    ad = _to_dev(np.ascontiguousarray(a, dtype=np.float32) if is_np else a, torch)
+    bd = _to_dev(np.ascontiguousarray(b, dtype=np.float32) if isinstance(b, np.ndarray) else b, torch)
+    one = ad.dim() == 1
+    if one:
+        ad, bd = ad[None], bd[None]
+    assert ad.shape == bd.shape, "np.correlate twin: equal lengths only"
+    P, n = ad.shape
+    out = torch.empty((P, 2 * n - 1), dtype=torch.float32, device="cuda")
+    check(_lib.lib().ofp_correlate_full(ptr(ad), ptr(bd), C.c_int32(P), C.c_int32(n), ptr(out), stream_ptr()))
+    out = out[0] if one else out
+    return out.cpu().numpy() if is_np else out
+
+
+def find_lag(a: np.ndarray, b: np.ndarray):
+    """multilateration.py:878-886: argmax of the full cross-correlation (first maximum) minus len(a) - 1."""
+    cc = correlate_full(np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32))
+    return int(np.argmax(cc) - (len(a) - 1))
+
+
+def find_lag_multi(a, b, top_n=3):
+    """multilateration.py:889-899: the top_n peaks of the full cross-correlation (lags, squared heights).
+    The correlation runs on the device; peak picking over the 2n-1 values is scipy's find_peaks as in
+    the reference."""
+    from scipy.signal import find_peaks
+
+    cc = correlate_full(np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32))
+    peaks, _ = find_peaks(cc)
+    peaks = peaks[np.argsort(-cc[peaks])][:top_n]
+    return peaks - len(a) + 1, cc[peaks] ** 2
+
+
+def solve_trilateration_batch(sensor_a, sensor_b, sensor_origin, delta_d_a, delta_d_b, initial_guess,
+                              xtol: float = 0.01, maxfev: int = 20):
+    """P trilateration problems in one launch (ofp_solve_trilateration = MINPACK hybrj as fsolve runs it).
+    sensor_* [P, 2|3] (or one sensor for all), delta_d_* [P], initial_guess [P, 2] ->
+    (xy [P, 2] float64, ier [P] int32) device tensors; ier == 1 where the reference returns a root."""
+    torch = _lib.require_cuda()
+    g = np.atleast_2d(np.asarray(initial_guess, np.float64))
+    P = g.shape[0]
+    prob = np.zeros((P, 11), np.float64)
+    for k, sensor in enumerate((sensor_a, sensor_b, sensor_origin)):
+        v = np.atleast_2d(np.asarray(sensor, np.float64))
+        prob[:, 3 * k:3 * k + v.shape[1]] = v
+    prob[:, 9] = np.asarray(delta_d_a, np.float64)
+    prob[:, 10] = np.asarray(delta_d_b, np.float64)
+    pd = torch.from_numpy(prob).cuda()
+    gd = torch.from_numpy(np.ascontiguousarray(g)).cuda()
+    xy = torch.empty((P, 2), dtype=torch.float64, device="cuda")
+    ier = torch.empty((P,), dtype=torch.int32, device="cuda")
+    check(_lib.lib().ofp_solve_trilateration(ptr(pd), ptr(gd), C.c_int32(P), C.c_double(xtol), C.c_int32(maxfev),
+                                             ptr(xy), ptr(ier), None, stream_ptr()))
+    return xy, ier
+
+
+def solve_trilateration(sensor_a, sensor_b, sensor_origin, delta_d_a, delta_d_b, initial_guess):
+    """multilateration.py:170-227 (2-D): tuple (x, y) or None when fsolve does not report convergence."""
+    xy, ier = solve_trilateration_batch(sensor_a, sensor_b, sensor_origin, delta_d_a, delta_d_b, initial_guess)
+    if int(ier[0].item()) != 1:
+        return None
+    return tuple(xy[0].cpu().tolist())
 
 
 def solve_trilateration_3d(sensor_a, sensor_b, sensor_origin, delta_d_a, delta_d_b, initial_guess):
-    """multilateration.py:230-316 through K5 (a one-hit launch with an explicit seed is not exposed by
-    the C ABI; the batched path seeds from the lag maps as Multilaterate3D.locate does)."""
-    raise NotImplementedError("use Multilaterate3D.locate / locate_batch; the seed comes from the lag maps")
+    """multilateration.py:230-316: sensors in 3-D, source on the z = 0 plane."""
+    return solve_trilateration(sensor_a, sensor_b, sensor_origin, delta_d_a, delta_d_b, initial_guess)
+
+
+def sound_intensity_at_source(strike_location, strike_force=STRIKE_FORCE, diameter=DIAMETER) -> float:
+    """multilateration.py:1004-1008 (placeholder in the reference too)."""
+    return strike_force
+
+
+def vec_sub(a, b):
+    """multilateration.py:1011-1015."""
+    x = a[0] - b[0].reshape(-1)
+    y = a[1] - b[1].reshape(-1)
+    z = np.full_like(x, a[2] - b[2], dtype=float)
+    return np.vstack((x, y, z)).T
+
+
+def attenuate_intensity(source_loc, mic_loc, reflectivity, intensity_at_source):
+    """multilateration.py:1018-1041: 1/r law with an angle term towards the drumhead normal."""
+    direction = vec_sub(mic_loc, source_loc)
+    distance = np.linalg.norm(direction, axis=-1)
+    direction /= np.linalg.norm(direction, axis=-1, keepdims=True)
+    thetas = np.arccos(np.dot(direction, np.array([0.0, 0.0, 1.0])))
+    A = intensity_at_source * (1 + reflectivity * (1 - np.abs(np.cos(thetas)))) / distance
+    return A, np.degrees(thetas)
+
+
+def lag_intensity_map(mic_a, mic_b, reflectivity: float = 0.5, d: int = DIAMETER, sr: int = 96000,
+                      scale: float = 1, medium: str = MEDIUM):
+    """multilateration.py:1044-1101: lag map plus the two intensity maps (dB) of a microphone pair;
+    one-off geometry set-up on the host like lag_map_2d/3d."""
+    r = int(np.round(d, 1) * scale) // 2
+    i, j = np.meshgrid(range(-r, r + 1), range(-r, r + 1))
+    c = speed_of_sound(100 * scale, medium=medium)
+
+    def at_mic(mic):
+        A, _ = attenuate_intensity((i, j, 0), np.array(mic), reflectivity, 1)
+        return A.reshape(i.shape)
+
+    la = np.sqrt((i - mic_a[0]) ** 2 + (j - mic_a[1]) ** 2 + (0 - mic_a[2]) ** 2) / c
+    lb = np.sqrt((i - mic_b[0]) ** 2 + (j - mic_b[1]) ** 2 + (0 - mic_b[2]) ** 2) / c
+    return (np.round((la - lb) * sr).astype(np.float32), (10 * np.log10(at_mic(mic_a))).astype(np.float32),
+            (10 * np.log10(at_mic(mic_b))).astype(np.float32))
 
 
 class Multilaterate3D:
@@ -218,21 +315,59 @@ class Multilaterate3D:
         return np.unravel_index(np.argmax(legal > 0), legal.shape, "F")
 
     def trilaterate(self, group, initial_guess=None):
-        """multilateration.py:536-575: legality + seed + solve of one complete group on the GPU.
-        The seed is recomputed from the lag maps exactly as locate() derives it (line 511-516)."""
-        sensors, onsets = list(group[0]), list(group[1])
-        xy, st = self.locate_batch(np.asarray([onsets[:3]], np.int32), np.asarray([sensors[:3]], np.int32))
-        if int(st[0].item()) != 0:
-            return None
-        x, y = xy[0].cpu().tolist()
-        return (x, y)
+        """multilateration.py:536-575.  With a seed: the reference's sensor rewrite (Q8, in place on the
+        caller's lists like the reference) and one solve.  Without: legality + seed + solve of a
+        complete group in one K5 launch, the seed derived from the lag maps as locate() does (511-516)."""
+        sensors, onsets = group[0], group[1]
+        if initial_guess is None:
+            xy, st = self.locate_batch(np.asarray([list(onsets)[:3]], np.int32), np.asarray([list(sensors)[:3]], np.int32))
+            if int(st[0].item()) != 0:
+                return None
+            return tuple(xy[0].cpu().tolist())
+        if sensors[1] == 1:
+            sensors[1:] = [0, 1]
+            onsets[1:] = onsets[2:0:-1]
+        d_a1, d_b1 = onsets[1] - onsets[0], onsets[2] - onsets[0]
+        return solve_trilateration_3d(self.sensor_locs[sensors[1]], self.sensor_locs[sensors[2]],
+                                      self.sensor_locs[sensors[0]], d_a1 / self.sr * self.c, d_b1 / self.sr * self.c,
+                                      initial_guess)
+
+    def _refine_pair(self, rec_audio, first_sensor, sensor_index, last_onset, onset_index):
+        """The ring-buffer refinement of locate (multilateration.py:457-501): median 5 -> first
+        difference -> falling flanks only -> bounded-lag cross-correlation (tol 50, cutoff 10) ->
+        adjust_onset, on the section from lookaround + 1 samples before the group's first onset to the
+        newest sample.  One K4 launch on the two columns.  Returns (new_lag | None, change_first, change_new)."""
+        from . import detection
+
+        torch = self.torch
+        i = rec_audio.counter - last_onset + lookaround
+        section = rec_audio[-i - 1:]
+        if isinstance(section, np.ndarray):
+            section = torch.from_numpy(np.ascontiguousarray(section[:, [first_sensor, sensor_index]], np.float32)).cuda()
+        else:
+            section = section[:, [first_sensor, sensor_index]].to(device="cuda", dtype=torch.float32)
+        section = section.contiguous()[None]
+        on = torch.tensor([[lookaround, lookaround + (onset_index - last_onset)]], dtype=torch.int32)
+        out, lags, st = detection.fix_onsets_batch(section, None, on, filter_size=5, d=1, onset_direction="down",
+                                                   take_abs=True, normalization_cutoff=NORM_CUTOFF,
+                                                   onset_tolerance=ONSET_TOL, to_end=True)
+        code = int(st[0].item())
+        if code == 2:
+            raise ValueError("operands could not be broadcast together (adjust_onset, detection.py:335)")
+        if code != 0:
+            return None, 0, 0
+        lag = int(lags[0, 1].item())
+        if lag == detection.LAG_NONE:
+            return None, 0, 0
+        o = out[0].cpu().tolist()
+        return lag, o[0] - lookaround, o[1] - (lookaround + (onset_index - last_onset))
 
     def locate(self, sensor_index: int, onset_index: int, rec_audio=None):
         """multilateration.py:428-534, streaming contract: feed detections one at a time, get (x, y)
-        in cm when a third legal sensor completes a group, else None."""
-        if rec_audio is not None:
-            raise NotImplementedError("ring-buffer CC refinement (multilateration.py:457-501) is the next "
-                                      "row of the scope table (SURVEY 8f rank 1)")
+        in cm when a third legal sensor completes a group, else None.  rec_audio: a ring of the most
+        recent audio rows (``counter`` = rows written so far, ``ring[-k:]`` = last k rows in time
+        order; realtime.audio.DeviceRing or loopmate's CircularArray) enables the cross-correlation
+        refinement of each new pair."""
         new_groups = []
         for group in self.ongoing:
             lag = onset_index - group[1][0]
@@ -244,15 +379,20 @@ class Multilaterate3D:
                 sensor_index, onset_index = inter
                 lag = -lag
             if sensor_index not in group[0]:
+                if rec_audio is not None:
+                    new_lag, co, cn = self._refine_pair(rec_audio, group[0][0], sensor_index, group[1][0], onset_index)
+                    if new_lag is not None:
+                        lag = new_lag
+                        group[1][0] += co
+                        onset_index += cn
                 if self.is_legal(group[0][0], sensor_index, lag):
                     group = (group[0] + [sensor_index], group[1] + [onset_index])
                     if len(group[0]) == 3:
                         if group[0][0] == group[0][1]:
                             break
-                        xy, st = self.locate_batch(np.asarray([group[1]], np.int32), np.asarray([group[0]], np.int32))
-                        code = int(st[0].item())
-                        if code != 3:  # a seed cell exists (multilateration.py:512)
-                            res = tuple(xy[0].cpu().tolist()) if code == 0 else None
+                        res = self.is_legal_3d(group)
+                        if res != (0, 0):
+                            res = self.trilaterate(group, initial_guess=np.array(res) - self.radius)
                             if res is not None:
                                 new_groups = remove_seed(new_groups, group)
                             self.ongoing = new_groups
@@ -263,3 +403,112 @@ class Multilaterate3D:
         new_groups.append(([sensor_index], [onset_index]))
         self.ongoing = new_groups
         return None
+
+
+class Multilaterate:
+    """multilateration.py:578-733: the 2-D (sensors on the drumhead plane) streaming locator.  Set-up
+    as in the reference (cm lag maps on the host); the solve is ofp_solve_trilateration."""
+
+    def __init__(self, sensor_locations, drum_diameter: float = DIAMETER, medium: str = "drumhead", sr: int = 44100):
+        _lib.require_cuda()
+        self.radius = drum_diameter / 2
+        self.sensor_locs = [polar_to_cartesian(x[0] * self.radius, x[1]) for x in sensor_locations]
+        self.medium, self.sr = medium, sr
+        self.samples_per_cm = sr / speed_of_sound(100, medium=medium)
+        S = len(self.sensor_locs)
+        self.lag_maps = [{} for _ in range(S)]
+        self.max_lags = [{} for _ in range(S)]
+        self.min_lags = [{} for _ in range(S)]
+        for i in range(S):
+            for j in range(S):
+                if i == j:
+                    continue
+                lm = lag_map_2d(self.sensor_locs[j], self.sensor_locs[i], d=drum_diameter, sr=sr, scale=1,
+                                medium=medium, tol=2)
+                lm[lm < -self.samples_per_cm * 1] = np.nan
+                self.lag_maps[i][j] = lm
+                self.max_lags[i][j] = np.nanmax(lm)
+                self.min_lags[i][j] = np.nanmin(lm)
+        self.max_max_lags = [np.nanmax(list(d.values())) for d in self.max_lags]
+        self.ongoing = []
+
+    is_legal = Multilaterate3D.is_legal
+    is_legal_3d = Multilaterate3D.is_legal_3d
+
+    def locate(self, sensor_index: int, onset_index: int):
+        """multilateration.py:679-713."""
+        new_groups = []
+        for group in self.ongoing:
+            lag = onset_index - group[1][0]
+            if sensor_index not in group[0]:
+                if self.is_legal(group[0][0], sensor_index, lag):
+                    group = (group[0] + [sensor_index], group[1] + [onset_index])
+                    if len(group[0]) == 3:
+                        res = self.is_legal_3d(group)
+                        if res != (0, 0):
+                            res = self.trilaterate(group, np.array(res) - self.radius)
+                            self.ongoing = new_groups
+                            return res
+                    new_groups.append(group)
+            if lag <= self.max_max_lags[group[0][0]]:
+                new_groups.append(group)
+        new_groups.append(([sensor_index], [onset_index]))
+        self.ongoing = new_groups
+        return None
+
+    def trilaterate(self, group, initial_guess):
+        """multilateration.py:715-733 -> (relative radius, angle in degrees) or None."""
+        sensors, onsets = group[0], group[1]
+        c = speed_of_sound(100, medium=self.medium)
+        res = solve_trilateration(self.sensor_locs[sensors[1]], self.sensor_locs[sensors[2]],
+                                  self.sensor_locs[sensors[0]], (onsets[1] - onsets[0]) * c / self.sr,
+                                  (onsets[2] - onsets[0]) * c / self.sr, initial_guess)
+        return None if res is None else cartesian_to_polar(*res, self.radius)
+
+
+class MultilateratePaired:
+    """multilateration.py:736-875: neighbour-pair lag maps at `scale` resolution; locate() solves from
+    two lags, locate_cc() votes the lag maps with cross-correlation lags found on the device."""
+
+    def __init__(self, sensor_locations, drum_diameter: float = DIAMETER, scale: float = 10,
+                 medium: str = "drumhead", sr: int = 44100):
+        _lib.require_cuda()
+        self.radius = int(np.round(drum_diameter * scale / 2, 1))
+        self.sensor_locs = [polar_to_cartesian(x[0] * self.radius, x[1]) for x in sensor_locations]
+        self.scale, self.medium, self.sr = scale, medium, sr
+        S = len(self.sensor_locs)
+        self.lag_maps = [{} for _ in range(S)]
+        for i in range(S):
+            for k in (-1, 1):
+                j = (i + k) % S
+                self.lag_maps[i][j] = lag_map_2d(self.sensor_locs[i], self.sensor_locs[j], d=drum_diameter, sr=sr,
+                                                 scale=scale, medium="drumhead")
+        self.res = np.zeros_like(self.lag_maps[0][1])
+
+    def locate(self, lags, i: int):
+        """multilateration.py:801-832."""
+        S = len(self.sensor_locs)
+        sensor_a, sensor_b, sensor_origin = self.sensor_locs[(i - 1) % S], self.sensor_locs[(i + 1) % S], self.sensor_locs[i]
+        c = speed_of_sound(100 * self.scale, medium=self.medium)
+        d_a1, d_b1 = lags[0] * c / self.sr, lags[1] * c / self.sr
+        wa, wb, wo = abs(d_a1) / self.radius, abs(d_b1) / self.radius, abs(d_a1 + d_b1) / (2 * self.radius)
+        guess = np.array([sensor_a[0] * wa + sensor_b[0] * wb + sensor_origin[0] * wo,
+                          sensor_a[1] * wa + sensor_b[1] * wb + sensor_origin[1] * wo])
+        x, y = solve_trilateration(sensor_a, sensor_b, sensor_origin, d_a1, d_b1, guess)
+        return cartesian_to_polar(x, y, self.radius)
+
+    def locate_cc(self, x: np.ndarray, onset_idx: int, i: int, tol: int = 2, left: int = 0, right: int = 256):
+        """multilateration.py:834-875: both neighbour lags in one correlation launch, then the map vote."""
+        js = list(self.lag_maps[i])
+        seg = np.ascontiguousarray(x[onset_idx - left:onset_idx + right], np.float32)
+        a = np.stack([seg[:, i]] * len(js))
+        b = np.stack([seg[:, j] for j in js])
+        cc = correlate_full(a, b)
+        self.res[:] = 0
+        for row, j in zip(cc, js):
+            lag = int(np.argmax(row)) - (seg.shape[0] - 1)
+            self.res += (self.lag_maps[i][j] < lag + tol) & (self.lag_maps[i][j] > lag - tol)
+        coord = np.unravel_index(np.argmax(self.res), self.res.shape)
+        px = coord[1] - (self.res.shape[1] - 1) / 2
+        py = (self.res.shape[0] - 1) / 2 - coord[0]
+        return cartesian_to_polar(px, py, self.radius)

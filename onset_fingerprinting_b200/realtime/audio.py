@@ -20,13 +20,53 @@ REALTIME_DETECTOR = dict(hipass_freq=0, fast_ar=(0.3, 800), slow_ar=(8000, 8000)
                          off_threshold=0.45, cooldown=1323, sr=config.SR)
 
 
+class DeviceRing:
+    """The most recent `n_rows` audio rows on the device -- the part of loopmate's CircularArray
+    (package absent from the reference tree) that Multilaterate3D.locate uses (multilateration.py:462-466):
+    ``write(block)``, ``counter`` (rows written so far), ``N`` and ``ring[-k:]`` (last k rows, time order).
+    Rows before the first write read as zero."""
+
+    def __init__(self, n_rows: int, n_channels: int):
+        from .. import _lib
+
+        self.torch = _lib.require_cuda()
+        self.N = int(n_rows)
+        self.data = self.torch.zeros((2 * self.N, n_channels), dtype=self.torch.float32, device="cuda")
+        self.counter = 0
+        self.write_counter = 0
+        self._pos = 0  # rows [pos, pos + N) of the doubled buffer are the ring in time order
+
+    def write(self, block):
+        torch = self.torch
+        b = torch.as_tensor(block, dtype=torch.float32).to("cuda")
+        n = b.shape[0]
+        if n >= self.N:
+            self.data[: self.N] = b[-self.N:]
+            self._pos = 0
+        else:
+            if self._pos + self.N + n > 2 * self.N:  # slide the window back to the start
+                self.data[: self.N] = self.data[self._pos:self._pos + self.N].clone()
+                self._pos = 0
+            self.data[self._pos + self.N:self._pos + self.N + n] = b
+            self._pos += n
+        self.counter += n
+        self.write_counter += n
+
+    def __getitem__(self, item):
+        return self.data[self._pos:self._pos + self.N][item]
+
+
 class BlockLocator:
     def __init__(self, ml_conf: dict, n_channels: int = config.N_CHANNELS, blocksize: int = config.BLOCKSIZE,
-                 detector_kw: dict | None = None):
+                 detector_kw: dict | None = None, ring_rows: int | None = None):
+        """ring_rows: keep that many recent audio rows and let locate() refine every new sensor pair by
+        cross-correlation on them, as the reference's callback does with its recording buffer
+        (realtime/audio.py:69, 102)."""
         kw = dict(REALTIME_DETECTOR)
         kw.update(detector_kw or {})
         self.current_index = 0
         self.blocksize = blocksize
+        self.rec_audio = DeviceRing(ring_rows, n_channels) if ring_rows else None
         self.od = detection.AmplitudeOnsetDetector(n_channels, blocksize, backtrack=False, **kw)
         self.m = multilateration.Multilaterate3D(sensor_locations=ml_conf["sensor_locations"], sr=kw["sr"],
                                                  medium=ml_conf["medium"], c=ml_conf.get("c"))
@@ -34,12 +74,14 @@ class BlockLocator:
     def detect_hits(self, audio: np.ndarray):
         """realtime/audio.py:62-74.  Advances current_index by the block length like the callback does
         (realtime/audio.py:120)."""
+        if self.rec_audio is not None:
+            self.rec_audio.write(audio)  # the callback writes before it detects (realtime/audio.py:102-106)
         c, d, _ = self.od(audio)
         res = None
         if len(c) > 0:
             d = [self.current_index + int(x) for x in d]
             for i in np.argsort(d):
-                got = self.m.locate(int(c[i]), d[i])
+                got = self.m.locate(int(c[i]), d[i], self.rec_audio)
                 if got is not None:
                     res = Location(got[0], got[1], self.m.radius)
                     break

@@ -232,9 +232,166 @@ def gen_online_cc():
     print("online_cc ok")
 
 
+def tools_inputs():
+    """Seeded inputs of the helper-surface fixtures (shared by the generator and the tests)."""
+    rng = np.random.default_rng(77)
+    d = {}
+    d["fd_x"] = rng.standard_normal((200, 3)).astype(np.float32)
+    sig, ons = [], []
+    for k in range(24):
+        n = 700
+        x = 0.01 * rng.standard_normal(n)
+        o = int(rng.integers(20, 680)) if k % 6 else int(rng.choice([3, 695]))
+        t = np.arange(n - o)
+        x[o:] += rng.uniform(0.2, 1.0) * np.exp(-t / rng.uniform(30, 200)) * np.sin(2 * np.pi * t / rng.uniform(8, 40))
+        sig.append(x.astype(np.float32)); ons.append(o + int(rng.integers(-10, 30)))
+    d["or_x"], d["or_on"] = np.stack(sig), np.asarray(ons, np.int64)
+    d["rel_x"] = rng.uniform(0, 3, (30, 400)).astype(np.float32)
+    d["rel_y"] = rng.uniform(0, 3, (30, 400)).astype(np.float32)
+    d["rel_on"] = np.stack([rng.integers(120, 200, 30), rng.integers(200, 280, 30)], 1).astype(np.int64)
+    d["rel_lag"] = (d["rel_on"][:, 1] - d["rel_on"][:, 0] + rng.integers(-40, 40, 30)).astype(np.int64)
+    d["bw_x"] = rng.standard_normal((3, 300, 4)).astype(np.float32)
+    a = rng.standard_normal((40, 256)).astype(np.float32)
+    sh = rng.integers(-60, 60, 40)
+    d["fl_a"] = a
+    d["fl_b"] = np.stack([np.roll(a[k], int(sh[k])) for k in range(40)]) + 0.2 * rng.standard_normal((40, 256)).astype(np.float32)
+    d["fl_b"] = d["fl_b"].astype(np.float32)
+    # 2-D trilateration problems: sensors on the rim, deltas from a true point plus noise, seed near it
+    P = 200
+    ang = rng.uniform(0, 2 * np.pi, (P, 3))
+    sens = 16.0 * np.stack([np.cos(ang), np.sin(ang)], -1)           # [P, 3 sensors, 2]
+    rr, th = 15.0 * np.sqrt(rng.uniform(size=P)), rng.uniform(0, 2 * np.pi, P)
+    pt = np.stack([rr * np.cos(th), rr * np.sin(th)], -1)
+    dist = np.sqrt(((sens - pt[:, None]) ** 2).sum(-1))
+    d["tri_sens"] = sens
+    d["tri_da"] = dist[:, 0] - dist[:, 2] + rng.normal(0, 0.05, P)
+    d["tri_db"] = dist[:, 1] - dist[:, 2] + rng.normal(0, 0.05, P)
+    d["tri_seed"] = pt + rng.normal(0, 2.0, (P, 2))
+    d["init_x"], _ = synth.drum_recording(seconds=2.0, seed=9)
+    return d
+
+
+MESH3 = [(0.9, 0.0), (0.9, 120.0), (0.9, 240.0)]
+MESH4 = [(0.9, 0.0), (0.9, 90.0), (0.9, 180.0), (0.9, 270.0)]
+
+
+def mesh2d_onsets(sensors2d, n, seed, sr=96000):
+    """Onset triples of n random strikes for planar sensors (drumhead medium)."""
+    rng = np.random.default_rng(seed)
+    r = 17.78
+    locs = np.asarray([(s[0] * r * np.cos(np.radians(s[1])), s[0] * r * np.sin(np.radians(s[1]))) for s in sensors2d])
+    rr, th = 0.9 * r * np.sqrt(rng.uniform(size=n)), rng.uniform(0, 2 * np.pi, n)
+    pt = np.stack([rr * np.cos(th), rr * np.sin(th)], -1)
+    dist = np.sqrt(((locs[None] - pt[:, None]) ** 2).sum(-1))
+    return (100000 * (np.arange(n)[:, None] + 1) + np.round(dist / 8200.0 * sr) + rng.integers(-2, 3, dist.shape)).astype(np.int64)
+
+
+def gen_tools(det, ml):
+    """Helper surface of detection.py / multilateration.py."""
+    d = tools_inputs()
+    out = {"env": env()}
+    for direction in ("up", "down"):
+        out[f"fd_{direction}"] = det.filter_data(d["fd_x"].copy(), direction)
+    out["or_a"] = np.asarray([det.detect_onset_region(x, int(o)) for x, o in zip(d["or_x"], d["or_on"])], np.int64)
+    out["or_b"] = np.asarray([det.detect_onset_region(x, int(o), n=128, median_filter_size=7, threshold_factor=0.3)
+                              for x, o in zip(d["or_x"], d["or_on"])], np.int64)
+    out["rel_out"] = np.asarray([det.adjust_onset_rel(list(o), x, y, int(l)) for o, x, y, l in
+                                 zip(d["rel_on"], d["rel_x"], d["rel_y"], d["rel_lag"])], np.int64)
+    for tag, args in (("lo2", (3000, 4, 2, 96000, "low")), ("hi3", (500, 4, 3, 96000, "high"))):
+        bw = det.ButterworthFilter(*args)
+        out[f"bw_{tag}"] = np.stack([bw(b) for b in d["bw_x"]])
+    out["fl"] = np.asarray([ml.find_lag(a, b) for a, b in zip(d["fl_a"], d["fl_b"])], np.int64)
+    flm = [ml.find_lag_multi(a, b, 3) for a, b in zip(d["fl_a"][:12], d["fl_b"][:12])]
+    out["flm_lags"] = np.asarray([np.pad(l, (0, 3 - len(l)), constant_values=-9999) for l, _ in flm], np.int64)
+    out["flm_vals"] = np.asarray([np.pad(v, (0, 3 - len(v))) for _, v in flm], np.float64)
+    tri = np.full((len(d["tri_da"]), 2), np.nan)
+    for k in range(len(tri)):
+        r = ml.solve_trilateration(tuple(d["tri_sens"][k, 0]), tuple(d["tri_sens"][k, 1]), tuple(d["tri_sens"][k, 2]),
+                                   d["tri_da"][k], d["tri_db"][k], d["tri_seed"][k])
+        if r is not None:
+            tri[k] = r
+    out["tri_xy"] = tri
+    print("solve_trilateration converged", int(np.isfinite(tri[:, 0]).sum()), "of", len(tri))
+    # Multilaterate (2-D) streaming locate
+    m2 = ml.Multilaterate(MESH3, sr=96000, medium="drumhead")
+    on = mesh2d_onsets(MESH3, 300, 41)
+    res = np.full((len(on), 2), np.nan)
+    for h in range(len(on)):
+        m2.ongoing = []
+        r = None
+        for s in np.argsort(on[h], kind="stable"):
+            r = m2.locate(int(s), int(on[h, s]))
+        if r is not None:
+            res[h] = r
+    out["m2_onsets"], out["m2_res"] = on, res
+    print("Multilaterate located", int(np.isfinite(res[:, 0]).sum()), "of", len(on))
+    # MultilateratePaired
+    mp = ml.MultilateratePaired(MESH4, scale=10, sr=96000)
+    rng = np.random.default_rng(43)
+    lags = rng.integers(-150, 150, (60, 2))
+    ii = rng.integers(0, 4, 60)
+    pres = np.full((60, 2), np.nan)
+    for k in range(60):
+        try:
+            pres[k] = mp.locate([int(lags[k, 0]), int(lags[k, 1])], int(ii[k]))
+        except TypeError:  # solve_trilateration returned None and the reference unpacks it (multilateration.py:828)
+            pass
+    out["mp_lags"], out["mp_i"], out["mp_res"] = lags, ii, pres
+    xcc = rng.standard_normal((20, 600, 4)).astype(np.float32)
+    for k in range(20):  # delayed copies so that the vote has a clear winner
+        for c in range(1, 4):
+            xcc[k, :, c] = np.roll(xcc[k, :, 0], int(rng.integers(-80, 80))) + 0.1 * xcc[k, :, c]
+    out["mp_cc_x"] = xcc
+    out["mp_cc"] = np.asarray([mp.locate_cc(xcc[k], 200, int(k % 4)) for k in range(20)], np.float64)
+    lm, sa, sb = ml.lag_intensity_map((10.0, 5.0, 8.0), (-12.0, 3.0, 6.0), reflectivity=0.5, sr=96000)
+    out["lim_lag"], out["lim_a"], out["lim_b"] = lm, sa, sb
+    # AmplitudeOnsetDetector.init
+    od = det.AmplitudeOnsetDetector(3, 128, sr=96000)
+    with contextlib.redirect_stdout(io.StringIO()):
+        od.init(d["init_x"])
+    out["init_mins"], out["init_maxs"] = od.mins, od.maxs
+    out["init_on"], out["init_off"], out["init_noise"] = od.on_threshold, od.off_threshold, od.noise_max
+    np.savez_compressed(OUT / "tools.npz", **out)
+    print("tools ok")
+
+
+STREAM_CC = dict(seconds=2.5, seed=12)
+
+
+def gen_stream_cc(det, ml):
+    """PlayRec.detect_hits with the ring-buffer refinement (realtime/audio.py:62-74, 102;
+    multilateration.py:457-501): detector blocks -> locate(sensor, onset, rec_audio)."""
+    x, _ = synth.drum_recording(**STREAM_CC)
+    od = det.AmplitudeOnsetDetector(3, 128, hipass_freq=0, fast_ar=(0.3, 800), slow_ar=(8000, 8000),
+                                    on_threshold=0.45, off_threshold=0.45, cooldown=1323, sr=96000)
+    m = ml.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+    ring = rh.RingStub(np.zeros((4096, 3), np.float32))
+    rows, cur = [], 0
+    with contextlib.redirect_stdout(io.StringIO()):
+        for b, i in enumerate(range(0, len(x) - 127, 128)):
+            blk = x[i:i + 128]
+            ring.write(blk)
+            c, dl, _ = od(blk)
+            if len(c) > 0:
+                dd = [cur + int(v) for v in dl]
+                for k in np.argsort(dd):
+                    res = m.locate(int(c[k]), dd[k], ring)
+                    rows.append((b, int(c[k]), dd[k], np.nan if res is None else res[0], np.nan if res is None else res[1]))
+                    if res is not None:
+                        break
+            cur += 128
+    rows = np.asarray(rows, np.float64)
+    np.savez_compressed(OUT / "stream_cc.npz", rows=rows, x_sha=sha(x), env=env())
+    print("stream_cc: detections", len(rows), "located", int(np.isfinite(rows[:, 3]).sum()))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     det, ml = rh.load_reference()
+    if "tools" in sys.argv:  # only the helper-surface fixtures
+        gen_tools(det, ml)
+        gen_stream_cc(det, ml)
+        return
     gen_detect(det)
     gen_stream(det)
     gen_backtrack(det)
@@ -242,6 +399,8 @@ def main():
     gen_fix(det)
     gen_locate(ml)
     gen_online_cc()
+    gen_tools(det, ml)
+    gen_stream_cc(det, ml)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,189 @@
+"""Helper surface of detection.py / multilateration.py on the GPU (SURVEY 8a rows a3, a4, a9, a12, a13,
+8f rank 1) against what the unmodified reference returned (tests/golden/tools.npz, stream_cc.npz) and
+against the numpy restatements in oracle/oracle.py."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from onset_fingerprinting_b200 import synth
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(golden_dir / "tools.npz")
+
+
+@pytest.fixture(scope="module")
+def inp():
+    from oracle.make_golden import tools_inputs
+
+    return tools_inputs()
+
+
+@pytest.fixture(scope="module")
+def det():
+    from onset_fingerprinting_b200 import detection
+
+    return detection
+
+
+@pytest.fixture(scope="module")
+def ml():
+    from onset_fingerprinting_b200 import multilateration
+
+    return multilateration
+
+
+def test_filter_data_in_place(det, gold, inp):
+    for d in ("up", "down"):
+        x = inp["fd_x"].copy()
+        r = det.filter_data(x, d)
+        assert r is x and np.array_equal(x, gold[f"fd_{d}"])
+    with pytest.raises(RuntimeError):
+        det.filter_data(inp["fd_x"].copy(), "sideways")
+
+
+def test_detect_onset_region(det, gold, inp):
+    a = [det.detect_onset_region(x, int(o)) for x, o in zip(inp["or_x"], inp["or_on"])]
+    assert a == gold["or_a"].tolist()
+    b = det.detect_onset_region_batch(inp["or_x"], inp["or_on"], n=128, median_filter_size=7, threshold_factor=0.3)
+    assert b.cpu().tolist() == gold["or_b"].tolist()
+
+
+def test_adjust_onset_rel(det, gold, inp):
+    got = [det.adjust_onset_rel(list(o), x, y, int(l)) for o, x, y, l in
+           zip(inp["rel_on"], inp["rel_x"], inp["rel_y"], inp["rel_lag"])]
+    assert np.array_equal(np.asarray(got), gold["rel_out"])
+
+
+@pytest.mark.parametrize("tag,args", [("lo2", (3000, 4, 2, 96000, "low")), ("hi3", (500, 4, 3, 96000, "high"))])
+def test_butterworth_filter_streaming(det, gold, inp, tag, args):
+    bw = det.ButterworthFilter(*args)
+    for k, blk in enumerate(inp["bw_x"]):
+        assert np.array_equal(bw(blk), gold[f"bw_{tag}"][k])  # float32 DF2T, bit for bit
+
+
+def test_butterworth_matches_detector_highpass(det, golden_dir):
+    g = np.load(golden_dir / "kernels.npz")
+    bw = det.ButterworthFilter(2000, 3, 4, 96000, "high")
+    for k, blk in enumerate(g["hp_in"]):
+        assert np.array_equal(bw(blk), g["hp_out"][k])
+
+
+def test_find_lag_and_multi(ml, gold, inp):
+    from oracle import oracle as orc
+
+    got = [ml.find_lag(a, b) for a, b in zip(inp["fl_a"], inp["fl_b"])]
+    assert got == gold["fl"].tolist()
+    cc = ml.correlate_full(inp["fl_a"][:3], inp["fl_b"][:3])
+    for k in range(3):
+        assert np.array_equal(cc[k], orc.correlate_full(inp["fl_a"][k], inp["fl_b"][k]))
+    for k in range(12):
+        lags, vals = ml.find_lag_multi(inp["fl_a"][k], inp["fl_b"][k], 3)
+        n = len(lags)
+        assert lags.tolist() == gold["flm_lags"][k][:n].tolist()
+        assert np.allclose(vals, gold["flm_vals"][k][:n], rtol=1e-5)
+
+
+def test_solve_trilateration_2d(ml, gold, inp):
+    want = gold["tri_xy"]
+    xy, ier = ml.solve_trilateration_batch(inp["tri_sens"][:, 0], inp["tri_sens"][:, 1], inp["tri_sens"][:, 2],
+                                           inp["tri_da"], inp["tri_db"], inp["tri_seed"])
+    xy, ier = xy.cpu().numpy(), ier.cpu().numpy()
+    conv = np.isfinite(want[:, 0])
+    assert np.array_equal(ier == 1, conv)  # same None set as fsolve
+    err = np.abs(xy[conv] - want[conv]) / np.maximum(np.abs(want[conv]), 1e-3)
+    assert err.max() <= 1e-9  # north_star: 1e-4
+    k = int(np.nonzero(conv)[0][0])
+    one = ml.solve_trilateration(tuple(inp["tri_sens"][k, 0]), tuple(inp["tri_sens"][k, 1]),
+                                 tuple(inp["tri_sens"][k, 2]), inp["tri_da"][k], inp["tri_db"][k], inp["tri_seed"][k])
+    assert np.allclose(one, want[k], rtol=1e-9)
+    if (~conv).any():
+        k = int(np.nonzero(~conv)[0][0])
+        assert ml.solve_trilateration(tuple(inp["tri_sens"][k, 0]), tuple(inp["tri_sens"][k, 1]),
+                                      tuple(inp["tri_sens"][k, 2]), inp["tri_da"][k], inp["tri_db"][k],
+                                      inp["tri_seed"][k]) is None
+
+
+def test_multilaterate_2d_streaming(ml, gold):
+    from oracle.make_golden import MESH3
+
+    m = ml.Multilaterate(MESH3, sr=96000, medium="drumhead")
+    on, want = gold["m2_onsets"], gold["m2_res"]
+    for h in range(len(on)):
+        m.ongoing = []
+        r = None
+        for s in np.argsort(on[h], kind="stable"):
+            r = m.locate(int(s), int(on[h, s]))
+        if np.isfinite(want[h, 0]):
+            assert r is not None and np.allclose(r, want[h], rtol=1e-9, atol=1e-9), h
+        else:
+            assert r is None, h
+
+
+def test_multilaterate_paired(ml, gold):
+    from oracle.make_golden import MESH4
+
+    mp = ml.MultilateratePaired(MESH4, scale=10, sr=96000)
+    for k, (lg, i) in enumerate(zip(gold["mp_lags"], gold["mp_i"])):
+        want = gold["mp_res"][k]
+        if np.isfinite(want[0]):
+            assert np.allclose(mp.locate([int(lg[0]), int(lg[1])], int(i)), want, rtol=1e-9, atol=1e-9)
+        else:
+            with pytest.raises(TypeError):  # the reference unpacks None (multilateration.py:828)
+                mp.locate([int(lg[0]), int(lg[1])], int(i))
+    got = np.asarray([mp.locate_cc(gold["mp_cc_x"][k], 200, int(k % 4)) for k in range(20)])
+    assert np.allclose(got, gold["mp_cc"], rtol=1e-12)
+
+
+def test_lag_intensity_map(ml, gold):
+    lm, sa, sb = ml.lag_intensity_map((10.0, 5.0, 8.0), (-12.0, 3.0, 6.0), reflectivity=0.5, sr=96000)
+    assert np.array_equal(lm, gold["lim_lag"])
+    assert np.allclose(sa, gold["lim_a"], rtol=1e-6) and np.allclose(sb, gold["lim_b"], rtol=1e-6)
+
+
+def test_detector_init_calibration(det, gold, inp):
+    od = det.AmplitudeOnsetDetector(3, 128, sr=96000)
+    od.init(inp["init_x"])
+    # dB envelopes: float32 log10 differs from numpy's by a few ulp -> absolute 1e-3 dB
+    for name, attr in (("init_mins", "mins"), ("init_maxs", "maxs"), ("init_on", "on_threshold"),
+                       ("init_off", "off_threshold"), ("init_noise", "noise_max")):
+        assert np.allclose(getattr(od, attr), gold[name], atol=1e-3, rtol=1e-5), name
+
+
+def test_streaming_locate_with_ring_refinement(golden_dir):
+    """PlayRec.detect_hits with rec_audio: every detection's locate() result, block by block."""
+    from oracle.make_golden import STREAM_CC
+    from onset_fingerprinting_b200 import detection, multilateration
+    from onset_fingerprinting_b200.realtime.audio import DeviceRing
+
+    g = np.load(golden_dir / "stream_cc.npz")["rows"]
+    x, _ = synth.drum_recording(**STREAM_CC)
+    od = detection.AmplitudeOnsetDetector(3, 128, hipass_freq=0, fast_ar=(0.3, 800), slow_ar=(8000, 8000),
+                                          on_threshold=0.45, off_threshold=0.45, cooldown=1323, sr=96000)
+    m = multilateration.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+    ring = DeviceRing(4096, 3)
+    rows, cur = [], 0
+    for b, i in enumerate(range(0, len(x) - 127, 128)):
+        blk = x[i:i + 128]
+        ring.write(blk)
+        c, dl, _ = od(blk)
+        if len(c) > 0:
+            dd = [cur + int(v) for v in dl]
+            for k in np.argsort(dd):
+                res = m.locate(int(c[k]), dd[k], ring)
+                rows.append((b, int(c[k]), dd[k], np.nan if res is None else res[0], np.nan if res is None else res[1]))
+                if res is not None:
+                    break
+        cur += 128
+    rows = np.asarray(rows, np.float64)
+    assert rows.shape == g.shape
+    assert np.array_equal(rows[:, :3], g[:, :3])
+    assert np.array_equal(np.isfinite(rows[:, 3]), np.isfinite(g[:, 3]))
+    ok = np.isfinite(g[:, 3])
+    assert np.allclose(rows[ok, 3:], g[ok, 3:], rtol=1e-9, atol=1e-9)
