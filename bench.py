@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--recordings", type=int, default=10000, help="recordings per GPU")
     ap.add_argument("--seconds", type=float, default=5.0, help="length of each recording")
     ap.add_argument("--no-rel", action="store_true", help="onsets-only mode (4 B per channel-sample)")
-    ap.add_argument("--e2e-recordings", type=int, default=1536)
+    ap.add_argument("--e2e-recordings", type=int, default=3072)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--workload", default="batch", choices=["batch", "hits16", "realtime"],

@@ -427,10 +427,13 @@ __device__ double g_exptab[32];
 // reloaded values are opaque, so they stay in registers; otherwise they are re-materialised inside
 // the recurrences as constant-bank loads (LDC, ~30 cycles in a dependent chain) and 64-bit
 // immediates (2 UMOV each).  scratch: >= 256 bytes of shared memory not yet in use.
+#ifndef OFP_LAUNDER_COEF
+#define OFP_LAUNDER_COEF 0
+#endif
 __device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch) {
     float *f = reinterpret_cast<float *>(&k);
     double *m = reinterpret_cast<double *>(&mc);
-    constexpr int NF = sizeof(Coef) / 4, ND = sizeof(MathConst) / 8;
+    constexpr int NF = OFP_LAUNDER_COEF ? sizeof(Coef) / 4 : 0, ND = sizeof(MathConst) / 8;
 #pragma unroll
     for (int i = 0; i < NF; ++i) sts_f32(scratch + 4 * i, f[i]);
 #pragma unroll
