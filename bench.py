@@ -439,6 +439,12 @@ def run_hits16(args):
     bytes_per_hit = 4 * Cn * L + 16 * Cn + 48
     achieved = bytes_per_hit * H / (k4_ms / 1e3) / 1e9
     ok = int((st == 0).sum().item()); loc = int((lst == 0).sum().item())
+    import ctypes as C
+    from onset_fingerprinting_b200 import _lib
+    cs = (C.c_uint64 * 4)()
+    _lib.check(_lib.lib().ofp_cc_screen_stats(cs, 1))
+    screen = {"pairs": int(cs[0]), "single_survivor": int(cs[1]), "few_survivors_exact": int(cs[2]),
+              "exact_all_lags": int(cs[3])}
     if rank == 0:
         print(json.dumps({
             "metric": "hits/sec through lag refinement + multilateration (16-channel hit mining)",
@@ -452,7 +458,7 @@ def run_hits16(args):
                          "algorithmic_bytes_per_hit": bytes_per_hit,
                          "note": "K4 at 16 ch is FP64-issue bound (3.4 M double MACs per hit), not HBM bound"},
             "cpu_baseline": None, "e2e": None, "gpu_launches": 2 * args.steps, "clocks": clk.summary(),
-            "fix_ok": ok, "located": loc}))
+            "fix_ok": ok, "located": loc, "cc_screening": screen}))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
 

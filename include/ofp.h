@@ -176,6 +176,11 @@ int ofp_fix_onsets_ex(const float *audio_dev, int64_t n_samples, int64_t rec_str
                       int32_t tol, int32_t shift, int32_t max_section, int32_t flags, int32_t *out_onsets_dev,
                       int32_t *out_lags_dev, int32_t *out_status_dev, void *stream);
 int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section);
+/* Statistics of the float32 lag-window screening inside K4 (csrc/lag_fix.cu:cc_argmax_screen) since
+ * the last reset (synchronises the device): stats4_host[0] pairs screened, [1] decided by a single
+ * surviving lag, [2] decided by exact recomputation of <= 32 survivors, [3] handed to the exact
+ * all-lags path.  The result is identical in every case; this only tells where the time goes. */
+int ofp_cc_screen_stats(uint64_t *stats4_host, int32_t reset);
 
 /* cross_correlation_lag for n_pairs pairs of equal length n: x_dev, y_dev [P, n] float32;
  * onsets_or_legal_dev [P, 2] = (onset_x, onset_y) or (legal_lo, legal_hi); lag_dev [P] (OFP_LAG_NONE = None). */
@@ -234,6 +239,17 @@ int ofp_detect_onset_region(const float *audio_dev, int32_t n_signals, int64_t l
  * x_dev, y_dev [P, n] -> out_dev [P, 2n-1] (double accumulation, rounded once). */
 int ofp_correlate_full(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, float *out_dev,
                        void *stream);
+
+/* Onset-window extraction -- FrameExtractor / FastFrameExtractor (data.py:55-192):
+ * frames_dev [H, C, F] = sliding_window_view(audio, F, axis=0)[start], start = min over the hit's
+ * onsets (use_min_onset) or each channel's own onset, minus (pre_samples - shift[h]); negative starts
+ * wrap like numpy indexing, out-of-range ones set status_dev[h] = 1 (numpy raises IndexError).
+ *   audio_dev [R, n_samples, C]; hit_rec_dev [H] or NULL (recording 0); onsets_dev [H, C];
+ *   shifts_dev [H] or NULL (the random augmentation shift of max_shift). */
+int ofp_extract_frames(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                       const int32_t *hit_rec_dev, const int32_t *onsets_dev, const int32_t *shifts_dev,
+                       int32_t n_hits, int32_t frame_length, int32_t pre_samples, int32_t use_min_onset,
+                       float *frames_dev, int32_t *status_dev, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Streaming cross-correlation -- twin of the CPython extension online_cc

@@ -14,6 +14,7 @@
 #include "ofp_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace ofp {
@@ -41,6 +42,7 @@ struct K4Args {
     int32_t *out_onsets;     // [H, C]
     int32_t *out_lags;       // [H, C] (may be null)
     int32_t *out_status;     // [H]
+    int32_t screen;          // float32 screening of the lag window (OFP_K4_SCREEN, default on)
 };
 
 __device__ __forceinline__ void py_slice(int64_t &s, int64_t &e, int64_t len) {
@@ -215,6 +217,184 @@ __device__ __forceinline__ void cc_argmax(const double *xd, const double *yd, in
         __syncthreads();
 }
 
+// ---- float32 screening of the lag window ---------------------------------------------------------
+// The result of cross_correlation_lag is an argmax, so the exact (double, index-order) sums are only
+// needed for lags that can still win.  Pass 1 evaluates every lag of the window with float32 FMAs
+// (LPF lags per thread, the x window sliding through registers; threads split (lag group, time
+// segment)), pass 2 bounds each value rigorously:
+//     |v32[w] - V[w]| <= delta[w] = (n + 8) * 2^-24 * ||x|| * ||y|| / cnt[w] + 2^-21 * |v32[w]|
+// (V = the oracle's float32(double sum) / cnt; float32 recursive summation error <= n u sum|x_i y_i|,
+// Cauchy-Schwarz; the last term covers the roundings of both quotients) and keeps the lags with
+// v32 + delta >= max_w (v32 - delta).  The true first maximum is always among them.  One survivor
+// (the usual case) IS the answer; a handful are recomputed exactly, one thread each, and compared
+// with np.argmax's tie rule; more than CAND_CAP, or non-finite data, falls back to cc_argmax.
+constexpr int LPF = 9;       // lags per thread (odd: conflict-free x reads across lanes)
+constexpr int CCF_UN = 8;    // time steps per unrolled iteration
+constexpr int XPAD = 16;     // zeros on both sides of the float copy of x
+constexpr int CAND_CAP = 32;
+
+// screening statistics since the last reset: pairs screened, decided by one survivor, decided by an exact
+// recomputation of a few survivors, handed to the exact path
+__device__ unsigned long long g_cc_stats[4];
+
+struct CcScratch {
+    float *xf;     // [L + 2 * XPAD], xf[XPAD + i] = x[i]
+    float *yf;     // [L]
+    float *part;   // [K4_THREADS * LPF] partial sums, then v32[w]
+    int *cand;     // [CAND_CAP + 1]: count, then window indices
+    double *red_d; // block reduction scratch
+    float *red_f;
+};
+
+__device__ __forceinline__ double cc_exact_one(const double *xd, const double *yd, int64_t L, int64_t m) {
+    const int64_t i0 = m < 0 ? -m : 0, i1 = m > 0 ? L - m : L;
+    double acc = 0.0;
+    for (int64_t i = i0; i < i1; ++i) acc = __fma_rn(xd[i + m], yd[i], acc);
+    return acc;
+}
+
+// Returns false when the screening is inconclusive (caller runs cc_argmax).  Uniform across the block.
+__device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double *yd, int64_t L, int64_t ws, int64_t nl,
+                                                 int64_t adj, int cutoff, const CcScratch &sc, float *best_v,
+                                                 int *best_w, int *s_lag) {
+    const int tid = threadIdx.x;
+    if (nl > K4_THREADS * LPF || L < 64) return false;
+    // float copies and the norms
+    double sx = 0.0, sy = 0.0;
+    for (int64_t i = tid; i < L + 2 * XPAD; i += K4_THREADS) {
+        const int64_t k = i - XPAD;
+        const double xv = (k >= 0 && k < L) ? xd[k] : 0.0;
+        sc.xf[i] = static_cast<float>(xv);
+        sx += xv * xv;
+        if (i < L) { const double yv = yd[i]; sc.yf[i] = static_cast<float>(yv); sy += yv * yv; }
+    }
+    sx = block_sum(sx, sc.red_d);
+    sy = block_sum(sy, sc.red_d);
+    const double S = sqrt(sx) * sqrt(sy);
+    if (!(S < 1e30)) return false;  // inf / NaN in the section: exact path
+    if (S == 0.0) {                 // one signal is all zero: every sum is 0, np.argmax returns index 0
+        if (tid == 0) *s_lag = static_cast<int>(adj);
+        __syncthreads();
+        return true;
+    }
+    if (tid == 0) sc.cand[0] = 0;
+    // pass 1: thread = (lag group g, time segment s)
+    const int NG = static_cast<int>((nl + LPF - 1) / LPF);
+    const int NS = K4_THREADS / NG;  // >= 1
+    const int g = tid % NG, seg = tid / NG;
+    float acc[LPF];
+#pragma unroll
+    for (int u = 0; u < LPF; ++u) acc[u] = 0.f;
+    if (seg < NS) {
+        const int64_t m0 = ws + static_cast<int64_t>(g) * LPF - (L - 1);  // lag of the group's first window
+        const int64_t m1 = m0 + LPF - 1;
+        // union of the valid index ranges of the group's lags; outside its own range a lag reads zeros
+        int64_t lo = m1 < 0 ? -m1 : 0, hi = m0 > 0 ? L - m0 : L;
+        if (lo < 0) lo = 0;
+        if (hi > L) hi = L;
+        if (hi < lo) hi = lo;
+        // reads stay inside [-(LPF-1), L + LPF - 1) of x: covered by XPAD
+        const int64_t len = hi - lo, per = (len + NS - 1) / NS;
+        const int64_t i0 = lo + seg * per, i1 = min(hi, i0 + per);
+        if (i1 > i0) {
+            const float *xp = sc.xf + XPAD + i0 + m0, *yp = sc.yf + i0;
+            const int n = static_cast<int>(i1 - i0);
+            float xw[LPF - 1 + CCF_UN];
+#pragma unroll
+            for (int k = 0; k < LPF - 1; ++k) xw[k] = xp[k];
+            int i = 0;
+            for (; i + CCF_UN <= n; i += CCF_UN) {
+                float yv[CCF_UN];
+#pragma unroll
+                for (int k = 0; k < CCF_UN; ++k) { yv[k] = yp[i + k]; xw[LPF - 1 + k] = xp[i + LPF - 1 + k]; }
+#pragma unroll
+                for (int k = 0; k < CCF_UN; ++k)
+#pragma unroll
+                    for (int u = 0; u < LPF; ++u) acc[u] = fmaf(xw[k + u], yv[k], acc[u]);
+#pragma unroll
+                for (int k = 0; k < LPF - 1; ++k) xw[k] = xw[k + CCF_UN];
+            }
+            for (; i < n; ++i) {
+                const float yv = yp[i];
+                xw[LPF - 1] = xp[i + LPF - 1];
+#pragma unroll
+                for (int u = 0; u < LPF; ++u) acc[u] = fmaf(xw[u], yv, acc[u]);
+#pragma unroll
+                for (int k = 0; k < LPF - 1; ++k) xw[k] = xw[k + 1];
+            }
+        }
+    }
+    __syncthreads();  // xf / yf reads done; part aliases nothing else
+    if (seg < NS) {
+#pragma unroll
+        for (int u = 0; u < LPF; ++u) sc.part[(seg * NG + g) * LPF + u] = acc[u];
+    }
+    __syncthreads();
+    // pass 2: v32, bounds, candidates
+    const float Ef = static_cast<float>(S * (static_cast<double>(L + 8) * 5.9604644775390625e-08) * 1.0001);
+    auto eval = [&](int64_t w, float &v, float &d) {
+        const int gg = static_cast<int>(w / LPF), u = static_cast<int>(w - static_cast<int64_t>(gg) * LPF);
+        float a = 0.f;
+        for (int q = 0; q < NS; ++q) a += sc.part[(q * NG + gg) * LPF + u];
+        const int64_t m = ws + w - (L - 1);
+        int64_t cnt = L - (m < 0 ? -m : m);
+        if (cnt < cutoff) cnt = cutoff;
+        const float c = static_cast<float>(cnt);
+        v = a / c;
+        d = Ef / c * 1.0001f + fabsf(v) * 4.76837158203125e-07f;
+    };
+    float lowmax = -INFINITY;
+    for (int64_t w = tid; w < nl; w += K4_THREADS) {
+        float v, d;
+        eval(w, v, d);
+        lowmax = fmaxf(lowmax, v - d);
+    }
+    lowmax = block_max(lowmax, sc.red_f);
+    __syncthreads();
+    for (int64_t w = tid; w < nl; w += K4_THREADS) {
+        float v, d;
+        eval(w, v, d);
+        if (v + d >= lowmax) {
+            const int k = atomicAdd(&sc.cand[0], 1);
+            if (k < CAND_CAP) sc.cand[1 + k] = static_cast<int>(w);
+        }
+    }
+    __syncthreads();
+    const int nc = sc.cand[0];
+    if (tid == 0) {
+        atomicAdd(&g_cc_stats[0], 1ull);
+        atomicAdd(&g_cc_stats[nc == 1 ? 1 : (nc >= 1 && nc <= CAND_CAP ? 2 : 3)], 1ull);
+    }
+    if (nc < 1 || nc > CAND_CAP) return false;  // NaNs (no candidate) or a flat window: exact path
+    if (nc == 1) {
+        if (tid == 0) *s_lag = static_cast<int>(adj - sc.cand[1]);
+        __syncthreads();
+        return true;
+    }
+    // exact values of the survivors, one thread each, then np.argmax's rule (first maximum)
+    float bv = -INFINITY;
+    int bw = INT32_MAX;
+    if (tid < nc) {
+        const int w = sc.cand[1 + tid];
+        const int64_t m = ws + w - (L - 1);
+        int64_t cnt = L - (m < 0 ? -m : m);
+        if (cnt < cutoff) cnt = cutoff;
+        bv = __fdiv_rn(__double2float_rn(cc_exact_one(xd, yd, L, m)), static_cast<float>(cnt));
+        bw = w;
+        if (!(bv == bv)) { bv = -INFINITY; bw = INT32_MAX; }  // unreachable for finite data
+    }
+    if (tid < 32) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const int ow = __shfl_down_sync(0xffffffffu, bw, o);
+            if (ov > bv || (ov == bv && ow < bw)) { bv = ov; bw = ow; }
+        }
+        if (tid == 0) *s_lag = static_cast<int>(adj - (bw == INT32_MAX ? 0 : bw));
+    }
+    __syncthreads();
+    return true;
+}
+
 // The two exponentially weighted sums of adjust_onset (detection.py:310-342).  Returns false when the
 // reference would raise "operands could not be broadcast" (SURVEY Q10).  Uniform across the block.
 __device__ __forceinline__ bool adjust_sums(const double *xd, const double *yd, int64_t L, int64_t o0, int64_t o1,
@@ -266,6 +446,11 @@ __global__ void __launch_bounds__(K4_THREADS) k4_fix(const K4Args a) {
     double *xd = reinterpret_cast<double *>(smem_raw);
     double *yd = xd + a.Lmax + 16;
     float *bufA = reinterpret_cast<float *>(yd + a.Lmax + 16);
+    CcScratch sc;
+    sc.xf = bufA + static_cast<size_t>(a.Lmax) * C;
+    sc.yf = sc.xf + a.Lmax + 2 * XPAD;
+    sc.part = sc.yf + a.Lmax + 16;
+    sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * LPF);
     __shared__ int64_t og[32], so[32], zl[32];
     __shared__ int idx[32];
     __shared__ int64_t s_s0, s_L0;
@@ -275,6 +460,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_fix(const K4Args a) {
     __shared__ float best_v[K4_THREADS / 32];
     __shared__ int best_w[K4_THREADS / 32];
     __shared__ int s_lag;
+    sc.red_d = red_d; sc.red_f = red_f;
 
     if (tid < C) og[tid] = static_cast<int64_t>(a.onsets[static_cast<int64_t>(h) * C + tid]);
     __syncthreads();
@@ -378,7 +564,8 @@ __global__ void __launch_bounds__(K4_THREADS) k4_fix(const K4Args a) {
         py_slice(ws, we, 2 * L - 1);
         const int64_t nl = we - ws;
         if (nl <= 0) continue;  // detection.py:265-266 -> None, no adjustment
-        cc_argmax(xd, yd, L, ws, nl, adj, fp.cutoff, best_v, best_w, &s_lag);
+        if (!a.screen || !cc_argmax_screen(xd, yd, L, ws, nl, adj, fp.cutoff, sc, best_v, best_w, &s_lag))
+            cc_argmax(xd, yd, L, ws, nl, adj, fp.cutoff, best_v, best_w, &s_lag);
         const int lag = s_lag;
         if (tid == 0 && a.out_lags) a.out_lags[static_cast<int64_t>(h) * C + ci] = lag;
         // ---- adjust_onset, detection.py:299-352 ----
@@ -406,6 +593,7 @@ struct PairArgs {
     const int32_t *onsets;  // [P, 2] (onset of x, onset of y) or legal lags (l0, l1) when use_legal
     const int32_t *new_lag; // [P] (adjust only)
     int32_t *out;           // cc: [P] lag; adjust: [P, 2]
+    int32_t screen;
 };
 
 __device__ __forceinline__ int64_t load_pair(const PairArgs &a, int p, double *xd, double *yd, float *tmp,
@@ -466,7 +654,15 @@ __global__ void __launch_bounds__(K4_THREADS) k4_cc_pairs(const PairArgs a) {
     }
     py_slice(ws, we, 2 * L - 1);
     if (we - ws <= 0 || L <= 0) { if (threadIdx.x == 0) a.out[p] = LAG_NONE; return; }
-    cc_argmax(xd, yd, L, ws, we - ws, adj, a.cutoff, best_v, best_w, &s_lag);
+    __shared__ double red_d[K4_THREADS / 32];
+    CcScratch sc;
+    sc.xf = tmp + 2 * a.n;
+    sc.yf = sc.xf + a.n + 2 * XPAD;
+    sc.part = sc.yf + a.n + 16;
+    sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * LPF);
+    sc.red_d = red_d; sc.red_f = red_f;
+    if (!a.screen || !cc_argmax_screen(xd, yd, L, ws, we - ws, adj, a.cutoff, sc, best_v, best_w, &s_lag))
+        cc_argmax(xd, yd, L, ws, we - ws, adj, a.cutoff, best_v, best_w, &s_lag);
     if (threadIdx.x == 0) a.out[p] = s_lag;
 }
 
@@ -558,8 +754,20 @@ using namespace ofp;
 
 extern "C" {
 
+int ofp_cc_screen_stats(uint64_t *stats4_host, int32_t reset) {
+    OFP_REQUIRE(stats4_host, "null argument");
+    OFP_CUDA_CHECK(cudaMemcpyFromSymbol(stats4_host, g_cc_stats, 4 * sizeof(uint64_t)));
+    if (reset) {
+        const uint64_t z[4] = {0, 0, 0, 0};
+        OFP_CUDA_CHECK(cudaMemcpyToSymbol(g_cc_stats, z, sizeof z));
+    }
+    return OFP_OK;
+}
+
 int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section) {
-    return static_cast<int>(2 * (max_section + 16) * sizeof(double) + static_cast<size_t>(max_section) * n_channels * sizeof(float));
+    const size_t cc = (static_cast<size_t>(max_section) + 2 * XPAD + max_section + 16 + K4_THREADS * LPF) * sizeof(float) +
+                      (CAND_CAP + 1) * sizeof(int);
+    return static_cast<int>(2 * (max_section + 16) * sizeof(double) + static_cast<size_t>(max_section) * n_channels * sizeof(float) + cc);
 }
 
 int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
@@ -588,6 +796,7 @@ int ofp_fix_onsets_ex(const float *audio_dev, int64_t n_samples, int64_t rec_str
     a.Lmax = max_section; a.hit_rec = hit_rec_dev; a.onsets = onsets_dev;
     a.fp = FixParams{filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift, flags & 1};
     a.out_onsets = out_onsets_dev; a.out_lags = out_lags_dev; a.out_status = out_status_dev;
+    { const char *e = getenv("OFP_K4_SCREEN"); a.screen = e ? atoi(e) : 1; }
     const int smem = ofp_fix_onsets_smem_bytes(n_channels, max_section);
     OFP_REQUIRE(smem <= 220 * 1024, "max_section %d x %d channels needs %d bytes of shared memory", max_section,
                 n_channels, smem);
@@ -604,8 +813,11 @@ static int launch_pairs(bool adjust, const float *x, const float *y, int32_t P, 
     OFP_REQUIRE(n >= 1 && n <= 8 * K4_THREADS, "signal length must be in 1..%d", 8 * K4_THREADS);
     OFP_REQUIRE(d >= 0 && d < n, "bad difference order");
     if (P == 0) return OFP_OK;
-    PairArgs a{x, y, P, n, d, take_abs, use_legal, cutoff, tol, onsets, new_lag, out};
-    const int smem = 2 * (n + 16) * sizeof(double) + 2 * n * sizeof(float);
+    const char *e = getenv("OFP_K4_SCREEN");
+    PairArgs a{x, y, P, n, d, take_abs, use_legal, cutoff, tol, onsets, new_lag, out, e ? atoi(e) : 1};
+    const int smem = 2 * (n + 16) * sizeof(double) + 2 * n * sizeof(float) +
+                     (static_cast<size_t>(n) + 2 * XPAD + n + 16 + K4_THREADS * LPF) * sizeof(float) +
+                     (CAND_CAP + 1) * sizeof(int);
     if (adjust) k4_adjust_pairs<<<P, K4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
     else k4_cc_pairs<<<P, K4_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
     OFP_CUDA_CHECK(cudaGetLastError());

@@ -214,3 +214,93 @@ int ofp_correlate_full(const float *x_dev, const float *y_dev, int32_t n_pairs, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Onset-window extraction (data.py:55-192 FrameExtractor / FastFrameExtractor): the gather
+// sliding_window_view(audio, F, axis=0)[start] -> [C, F] per hit, fused after K4 so that the
+// [hits, C, F] training windows are cut on the device from the resident recordings.
+// One CTA per hit: the F x C block is contiguous in the time-major recording (coalesced read),
+// transposed through shared memory, written as C contiguous rows of F samples.
+// ---------------------------------------------------------------------------------------------
+namespace ofp {
+
+struct FrameArgs {
+    const float *audio;
+    int64_t n_samples, rec_stride;
+    int32_t C, H, F, pre, use_min;
+    const int32_t *hit_rec, *onsets, *shifts;  // [H] or null, [H, C], [H] or null
+    float *out;                                // [H, C, F]
+    int32_t *status;                           // [H]: 0 ok, 1 index out of range (numpy raises IndexError)
+};
+
+__global__ void k_extract_frames(const FrameArgs a) {
+    extern __shared__ float sm[];
+    const int h = blockIdx.x, C = a.C, F = a.F;
+    const int64_t rec = a.hit_rec ? a.hit_rec[h] : 0;
+    const float *src = a.audio + rec * a.rec_stride;
+    const int64_t nwin = a.n_samples - F + 1;  // rows of the sliding-window view
+    const int32_t off = a.pre - (a.shifts ? a.shifts[h] : 0);
+    __shared__ int64_t start[32];
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        int64_t o;
+        if (a.use_min) {
+            o = a.onsets[static_cast<int64_t>(h) * C];
+            for (int c = 1; c < C; ++c) o = min(o, static_cast<int64_t>(a.onsets[static_cast<int64_t>(h) * C + c]));
+        } else {
+            o = a.onsets[static_cast<int64_t>(h) * C + threadIdx.x];
+        }
+        int64_t s = o - off;
+        if (s < 0) s += nwin;  // numpy's negative indexing into the view
+        if (s < 0 || s >= nwin) { s = 0; bad = 1; }
+        start[threadIdx.x] = s;
+    }
+    __syncthreads();
+    float *dst = a.out + static_cast<int64_t>(h) * C * F;
+    if (bad) {
+        for (int e = threadIdx.x; e < C * F; e += blockDim.x) dst[e] = 0.f;
+        if (threadIdx.x == 0) a.status[h] = 1;
+        return;
+    }
+    if (a.use_min) {
+        const float *p = src + start[0] * C;
+        for (int e = threadIdx.x; e < C * F; e += blockDim.x) {  // e = t * C + c
+            const int t = e / C, c = e - t * C;
+            sm[c * (F + 1) + t] = p[e];
+        }
+    } else {
+        for (int e = threadIdx.x; e < C * F; e += blockDim.x) {
+            const int t = e / C, c = e - t * C;
+            sm[c * (F + 1) + t] = src[(start[c] + t) * C + c];
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < C * F; e += blockDim.x) {  // e = c * F + t
+        const int c = e / F, t = e - c * F;
+        dst[e] = sm[c * (F + 1) + t];
+    }
+    if (threadIdx.x == 0) a.status[h] = 0;
+}
+
+}  // namespace ofp
+
+extern "C" int ofp_extract_frames(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                                  const int32_t *hit_rec_dev, const int32_t *onsets_dev, const int32_t *shifts_dev,
+                                  int32_t n_hits, int32_t frame_length, int32_t pre_samples, int32_t use_min_onset,
+                                  float *frames_dev, int32_t *status_dev, void *stream) {
+    OFP_REQUIRE(audio_dev && onsets_dev && frames_dev && status_dev, "null argument");
+    OFP_REQUIRE(n_channels >= 1 && n_channels <= 32, "n_channels must be in 1..32");
+    OFP_REQUIRE(frame_length >= 1 && frame_length <= n_samples, "frame_length must be in 1..n_samples");
+    if (n_hits == 0) return OFP_OK;
+    const size_t smem = static_cast<size_t>(n_channels) * (frame_length + 1) * sizeof(float);
+    OFP_REQUIRE(smem <= 200 * 1024, "frame of %d x %d samples does not fit shared memory", frame_length, n_channels);
+    ofp::FrameArgs a{audio_dev, n_samples, rec_stride, n_channels, n_hits, frame_length, pre_samples, use_min_onset,
+                     hit_rec_dev, onsets_dev, shifts_dev, frames_dev, status_dev};
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(ofp::k_extract_frames, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    ofp::k_extract_frames<<<n_hits, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}

@@ -1,0 +1,156 @@
+"""Device mirror of the window-extraction part of the reference's ``data.py``.
+
+``FrameExtractor`` / ``FastFrameExtractor`` (data.py:55-192) cut a fixed-length window per onset
+group out of a recording; ``MCPOSD`` (233-327) holds such windows with their strike positions;
+``batch_cc`` (226-230) is the row-wise full cross-correlation the CC models feed on.  Here the
+windows are gathered by ``ofp_extract_frames`` straight from recordings resident in HBM -- e.g. the
+``[R, N, C]`` batch K1/K4 just processed (``extract_frames_batch``) -- so the offline dataset build
+(BASELINE config 2, "data.py path") never copies audio back to the host.
+
+File formats (wav + json, ``from_file``) and the augmentation pipeline are host-side and out of
+scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .detection import _to_dev
+
+
+def extract_frames_batch(audio, hit_rec, hit_onsets, frame_length: int, pre_samples: int = 0, shifts=None,
+                         use_min_onset: bool = True):
+    """Windows for H hits of a batch: audio [R, N, C] float32 (device or numpy), hit_rec [H] int32 or
+    None (all in recording 0), hit_onsets [H, C] int32 -> frames [H, C, frame_length] float32 CUDA tensor.
+    Raises IndexError where numpy's ``view[start]`` would."""
+    torch = _lib.require_cuda()
+    audio = _to_dev(audio, torch)
+    R, N, Cn = audio.shape
+    on = torch.as_tensor(hit_onsets).to(device="cuda", dtype=torch.int32).contiguous()
+    H = on.shape[0]
+    rec = None if hit_rec is None else torch.as_tensor(hit_rec).to(device="cuda", dtype=torch.int32).contiguous()
+    sh = None if shifts is None else torch.as_tensor(shifts).to(device="cuda", dtype=torch.int32).contiguous()
+    out = torch.empty((H, Cn, frame_length), dtype=torch.float32, device="cuda")
+    status = torch.empty((H,), dtype=torch.int32, device="cuda")
+    check(_lib.lib().ofp_extract_frames(ptr(audio), C.c_int64(N), C.c_int64(audio.stride(0)), C.c_int32(Cn), ptr(rec),
+                                        ptr(on), ptr(sh), C.c_int32(H), C.c_int32(frame_length),
+                                        C.c_int32(pre_samples), C.c_int32(int(use_min_onset)), ptr(out), ptr(status),
+                                        stream_ptr()))
+    if H and bool((status != 0).any()):
+        bad = int(torch.nonzero(status)[0].item())
+        raise IndexError(f"index out of bounds for the sliding-window view (hit {bad})")
+    return out
+
+
+class FrameExtractor:
+    """data.py:55-120: ``fe(audio[N(, C)], onsets[O(, C)]) -> frames`` as a numpy array of shape
+    [O, C, F] (2-D audio) or [O, F] (1-D audio)."""
+
+    def __init__(self, frame_length: int, pre_samples: int, max_shift: int = 0, add_pre_samples: bool = False,
+                 use_min_onset: bool = True):
+        self.frame_length = frame_length + (pre_samples if add_pre_samples else 0)
+        self.pre_samples = pre_samples
+        self.max_shift = max_shift
+        self.use_min_onset = use_min_onset
+
+    def __call__(self, audio: np.ndarray, onsets: np.ndarray) -> np.ndarray:
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+        onsets = np.asarray(onsets)
+        shifts = None
+        if self.max_shift:
+            shifts = np.random.randint(-self.max_shift, self.max_shift + 1, len(onsets)).astype(np.int32)
+        one_d = audio.ndim == 1
+        a3 = audio[None, :, None] if one_d else audio[None]
+        on2 = onsets.reshape(len(onsets), -1)
+        out = extract_frames_batch(a3, None, on2, self.frame_length, self.pre_samples, shifts,
+                                   use_min_onset=self.use_min_onset or one_d)
+        out = out.cpu().numpy()
+        return out[:, 0, :] if one_d else out
+
+
+class FastFrameExtractor:
+    """data.py:123-192: holds the recording on the device and returns the window tensor; 2-D onsets
+    always use the minimum of each group."""
+
+    def __init__(self, audio, onsets, frame_length: int, pre_samples: int, max_shift: int = 0,
+                 add_pre_samples: bool = False, device=None):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.frame_length = frame_length + (pre_samples if add_pre_samples else 0)
+        self.pre_samples, self.max_shift = pre_samples, max_shift
+        audio = np.ascontiguousarray(audio, dtype=np.float32) if isinstance(audio, np.ndarray) else audio
+        self._one_d = audio.ndim == 1
+        a = _to_dev(audio, torch)
+        self.audio = (a[None, :, None] if self._one_d else a[None]).contiguous()
+        on = torch.as_tensor(np.asarray(onsets)).to("cuda")
+        self.onsets = (on.min(1).values if on.dim() == 2 else on).to(torch.int32)[:, None].contiguous()
+        if not max_shift:
+            self.frames = self._cut(None)
+
+    def _cut(self, shifts):
+        on = self.onsets.expand(-1, self.audio.shape[2]).contiguous()
+        out = extract_frames_batch(self.audio, None, on, self.frame_length, self.pre_samples, shifts)
+        return out[:, 0, :] if self._one_d else out
+
+    def __call__(self):
+        if self.max_shift:
+            shifts = self.torch.randint(-self.max_shift, self.max_shift + 1, (len(self.onsets),), device="cuda",
+                                        dtype=self.torch.int32)
+            return self._cut(shifts)
+        return self.frames
+
+
+def batch_cc(a, b):
+    """data.py:226-230: full cross-correlation of every row pair, [n, L] x [n, L] -> [n, 2L-1]
+    (``F.conv1d`` with padding L-1 == np.correlate(a_i, b_i, "full")), on ofp_correlate_full."""
+    from .multilateration import correlate_full
+
+    return correlate_full(a, b)
+
+
+class MCPOSD:
+    """data.py:233-327 without the file reader: multi-channel windows ``x [O, C, F]`` and positions
+    ``y [O, 2]`` as device tensors; ``ds[0] -> (x, y)`` (the reference's batch_size=None contract)."""
+
+    def __init__(self, data, onsets, sound_positions, frame_length: int = 256, pre_samples: int = 0,
+                 max_shift: int = 0, n_extractions: int = 1, device=None, channels=None):
+        torch = _lib.require_cuda()
+        if channels is not None:
+            data = data[:, channels]
+        self.data = data
+        self.frame_extractor = FastFrameExtractor(data, onsets, frame_length, pre_samples, max_shift)
+        pos = np.asarray(sound_positions, dtype=np.float32)
+        if n_extractions == 1 and max_shift == 0:
+            self.y = torch.from_numpy(pos).cuda()
+            self.x = self.frame_extractor()
+            self.straight = True
+        else:
+            self.y = torch.from_numpy(np.concatenate([pos] * n_extractions)).cuda()
+            self.straight = False
+        self.n_extractions = n_extractions
+
+    def __getitem__(self, index):
+        if self.straight:
+            return self.x, self.y
+        torch = self.frame_extractor.torch
+        return torch.cat([self.frame_extractor() for _ in range(self.n_extractions)]), self.y
+
+    def __len__(self):
+        return 1
+
+    @classmethod
+    def from_xy(cls, x, y):
+        ds = cls.__new__(cls)
+        ds.x, ds.y, ds.straight = x, y, True
+        return ds
+
+    def split(self, r: float = 0.8):
+        import torch
+
+        n = len(self.y)
+        idx = torch.randperm(n, device=self.y.device)
+        k = int(n * r)
+        return self.from_xy(self.x[idx[:k]], self.y[idx[:k]]), self.from_xy(self.x[idx[k:]], self.y[idx[k:]])

@@ -385,8 +385,42 @@ def gen_stream_cc(det, ml):
     print("stream_cc: detections", len(rows), "located", int(np.isfinite(rows[:, 3]).sum()))
 
 
+def frames_inputs():
+    rng = np.random.default_rng(55)
+    x, _ = synth.drum_recording(seconds=1.0, seed=14)
+    on = np.sort(rng.integers(2000, len(x) - 3000, 40))[:, None] + rng.integers(0, 60, (40, 3))
+    return x, on.astype(np.int64)
+
+
+def gen_frames():
+    """data.py window extraction."""
+    import torch
+
+    data = rh.load_reference_data()
+    x, on = frames_inputs()
+    out = {"env": env(), "x_sha": sha(x)}
+    out["fe_min"] = data.FrameExtractor(256, 16)(x, on)
+    out["fe_each"] = data.FrameExtractor(128, 8, add_pre_samples=True, use_min_onset=False)(x, on)
+    out["fe_1d"] = data.FrameExtractor(200, 0)(x[:, 1].copy(), on[:, 1])
+    np.random.seed(5)
+    out["fe_shift"] = data.FrameExtractor(256, 32, max_shift=10)(x, on)
+    out["ffe_sha"] = sha(data.FastFrameExtractor(x, on, 256, 16)().numpy())
+    a = torch.tensor(x[1000:1256].T.copy())
+    b = torch.tensor(x[1010:1266].T.copy())
+    out["bcc"] = data.batch_cc(a, b).numpy()
+    pos = np.random.default_rng(1).uniform(-1, 1, (40, 2))
+    ds = data.MCPOSD(x, on, pos, 256, 16)
+    xx, yy = ds[0]
+    out["ds_x_sha"], out["ds_y"] = sha(xx.numpy()), yy.numpy()
+    np.savez_compressed(OUT / "frames.npz", **out)
+    print("frames ok", out["fe_min"].shape, out["fe_each"].shape, out["bcc"].shape)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "frames" in sys.argv:
+        gen_frames()
+        return
     det, ml = rh.load_reference()
     if "tools" in sys.argv:  # only the helper-surface fixtures
         gen_tools(det, ml)
@@ -401,6 +435,7 @@ def main():
     gen_online_cc()
     gen_tools(det, ml)
     gen_stream_cc(det, ml)
+    gen_frames()
 
 
 if __name__ == "__main__":

@@ -102,3 +102,34 @@ def load_online_cc():
     import online_cc  # noqa: E402
 
     return online_cc
+
+
+class _AnyModule(types.ModuleType):
+    """Stub whose every attribute is a do-nothing callable class (audiomentations, soundfile ... are
+    absent; data.py builds a module-level AUGMENTATIONS list at import time)."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+
+        class _Dummy:
+            def __init__(self, *a, **k):
+                pass
+
+            def __call__(self, *a, **k):
+                raise RuntimeError(f"{self.__class__.__name__} is a stub")
+
+        _Dummy.__name__ = name
+        return _Dummy
+
+
+def load_reference_data():
+    """The reference's data.py (FrameExtractor, FastFrameExtractor, batch_cc, MCPOSD) with its absent
+    third-party imports stubbed; none of the stubbed packages is touched by those four."""
+    load_reference()
+    for name in ("audiomentations", "soundfile"):
+        if name not in sys.modules:
+            sys.modules[name] = _AnyModule(name)
+    import onset_fingerprinting.data as data  # noqa: E402
+
+    return data
