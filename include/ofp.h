@@ -209,6 +209,24 @@ int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, const float
                     double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
                     int32_t onset_stride, int32_t n_hits, double *xy_dev, int32_t *status_dev, void *stream);
 
+/* Streaming locate for n_streams concurrent realtime streams: what PlayRec.detect_hits does per block
+ * (realtime/audio.py:62-74) with Multilaterate3D.locate's group state machine
+ * (multilateration.py:428-534, rec_audio = None) kept per stream in device memory.
+ *   geometry arguments as in ofp_locate_hits; det_*_dev = ofp_detect_block's output for this block
+ *   ([S, C], [S, C], [S]); current_index = sample index of the block start;
+ *   state_*_dev: the `ongoing` lists (sizes from ofp_stream_locate_state_bytes, zero-initialised by
+ *   the caller = empty lists); xy_dev [S, 2] (NaN when nothing located), found_dev [S]: 1 located,
+ *   0 nothing, -1 a group list or group outgrew its slot (16 groups x 4 members) and was truncated. */
+int ofp_stream_locate_state_bytes(int32_t n_streams, int64_t *count_bytes, int64_t *len_bytes,
+                                  int64_t *sensor_bytes, int64_t *onset_bytes);
+int ofp_stream_locate(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                      int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                      const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                      double c_cm_s, int32_t n_streams, int32_t n_channels, const int32_t *det_channel_dev,
+                      const int32_t *det_delta_dev, const int32_t *det_count_dev, int64_t current_index,
+                      int32_t *state_count_dev, int32_t *state_len_dev, int32_t *state_sensor_dev,
+                      int64_t *state_onset_dev, double *xy_dev, int32_t *found_dev, void *stream);
+
 /* solve_trilateration / solve_trilateration_3d (multilateration.py:170-316) with explicit seeds:
  * scipy.optimize.fsolve(xtol, maxfev, fprime) = MINPACK hybrj for n = 2, one problem per row.
  *   problems_dev [P, 11] float64 = sensor_a xyz, sensor_b xyz, sensor_origin xyz, delta_d_a, delta_d_b

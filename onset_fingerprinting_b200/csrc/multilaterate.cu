@@ -350,6 +350,150 @@ __global__ void k5_locate(const K5Args a) {
     a.status[h] = st;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming locate for many concurrent streams: PlayRec.detect_hits + Multilaterate3D.locate
+// (realtime/audio.py:62-74, multilateration.py:428-534 with rec_audio = None), one thread per stream.
+// Each stream keeps its `ongoing` list of onset groups in device memory; a block's detections (K1's
+// per-block output) are taken in sample order and fed through the reference's group state machine
+// statement by statement -- including its quirks: the in-place swap when an onset lies before a
+// group's first one (which also replaces the detection for the rest of the loop), the extended
+// group being appended twice, `break` on a repeated first sensor, and every group after a solve
+// being dropped.  A block stops at its first located hit like detect_hits does.
+// ---------------------------------------------------------------------------------------------
+constexpr int SL_GMAX = 16;  // groups kept per stream
+constexpr int SL_LEN = 4;    // members kept per group (the reference solves at exactly three)
+
+struct SlArgs {
+    K5Args geo;               // lag maps, bounds, sensor positions (hit fields unused)
+    int32_t n_streams, C;
+    const int32_t *det_ch, *det_delta, *det_cnt;  // [S, C], [S, C], [S]: K1's per-block output
+    int64_t current_index;    // sample index of the block start
+    int32_t *g_count;         // [S]
+    int32_t *g_len;           // [S, GMAX]
+    int32_t *g_sensor;        // [S, GMAX, LEN]
+    int64_t *g_onset;         // [S, GMAX, LEN]
+    double *xy;               // [S, 2]
+    int32_t *found;           // [S]: 1 located, 0 nothing, -1 state overflow (groups or members dropped)
+};
+
+struct SlGroup { int len; int s[SL_LEN]; long long o[SL_LEN]; };
+
+__device__ __forceinline__ bool sl_is_legal(const K5Args &a, int first, int later, long long lag) {
+    const double l = static_cast<double>(lag);
+    return static_cast<double>(a.min_lags[first * a.S + later]) < l && l < static_cast<double>(a.max_lags[first * a.S + later]);
+}
+
+__global__ void k5_stream_locate(const SlArgs a) {
+    const int st = blockIdx.x * blockDim.x + threadIdx.x;
+    if (st >= a.n_streams) return;
+    const K5Args &geo = a.geo;
+    const int S = geo.S, Hm = geo.Hm;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    double out[2] = {nan, nan};
+    int found = 0;
+    bool overflow = false;
+    // detections of this block in sample order (np.argsort on <= C values: stable insertion sort)
+    const int nd = min(a.det_cnt[st], a.C);
+    int ord[32];
+    for (int i = 0; i < nd; ++i) {
+        int j = i - 1;
+        const int v = a.det_delta[static_cast<int64_t>(st) * a.C + i];
+        while (j >= 0 && a.det_delta[static_cast<int64_t>(st) * a.C + ord[j]] > v) { ord[j + 1] = ord[j]; --j; }
+        ord[j + 1] = i;
+    }
+    int32_t *gl = a.g_len + static_cast<int64_t>(st) * SL_GMAX;
+    int32_t *gs = a.g_sensor + static_cast<int64_t>(st) * SL_GMAX * SL_LEN;
+    int64_t *go = a.g_onset + static_cast<int64_t>(st) * SL_GMAX * SL_LEN;
+    int ng = a.g_count[st];
+    for (int di = 0; di < nd && !found; ++di) {
+        int sensor = a.det_ch[static_cast<int64_t>(st) * a.C + ord[di]];
+        long long onset = a.current_index + a.det_delta[static_cast<int64_t>(st) * a.C + ord[di]];
+        // ---- Multilaterate3D.locate(sensor, onset) ----
+        SlGroup ngp[SL_GMAX];  // new_groups
+        int nn = 0;
+        auto push = [&](const SlGroup &g) { if (nn < SL_GMAX) ngp[nn++] = g; else overflow = true; };
+        bool returned = false, broke = false;
+        for (int gi = 0; gi < ng && !returned && !broke; ++gi) {
+            SlGroup g;
+            g.len = gl[gi];
+            for (int k = 0; k < SL_LEN; ++k) { g.s[k] = gs[gi * SL_LEN + k]; g.o[k] = go[gi * SL_LEN + k]; }
+            long long lag = onset - g.o[0];
+            if (static_cast<double>(lag) > static_cast<double>(geo.max_max[g.s[0]])) continue;
+            if (lag < 0) {  // multilateration.py:443-449
+                const int ts = g.s[0]; const long long to = g.o[0];
+                g.s[0] = sensor; g.o[0] = onset;
+                sensor = ts; onset = to;
+                lag = -lag;
+            }
+            bool member = false;
+            for (int k = 0; k < g.len; ++k) member = member || g.s[k] == sensor;
+            if (!member) {
+                if (sl_is_legal(geo, g.s[0], sensor, lag)) {
+                    if (g.len < SL_LEN) { g.s[g.len] = sensor; g.o[g.len] = onset; ++g.len; }
+                    else overflow = true;
+                    if (g.len == 3) {
+                        if (g.s[0] == g.s[1]) { broke = true; break; }
+                        // is_legal_3d (multilateration.py:413-426)
+                        const double tol = 1 * geo.samples_per_cm;
+                        const long long lag1 = g.o[1] - g.o[0], lag2 = g.o[2] - g.o[0];
+                        const float *lm1 = geo.maps + static_cast<int64_t>(g.s[0] * S + g.s[1]) * Hm * Hm;
+                        const float *lm2 = geo.maps + static_cast<int64_t>(g.s[0] * S + g.s[2]) * Hm * Hm;
+                        const double l1lo = lag1 - tol, l1hi = lag1 + tol, l2lo = lag2 - tol, l2hi = lag2 + tol;
+                        int kf = 0;
+                        for (int k = 0; k < Hm * Hm; ++k) {
+                            const double m1 = lm1[k], m2 = lm2[k];
+                            if (m1 < l1hi && m1 > l1lo && m2 < l2hi && m2 > l2lo) { kf = k; break; }
+                        }
+                        const int ci = kf % Hm, cj = kf / Hm;
+                        if (!(ci == 0 && cj == 0)) {
+                            // trilaterate (multilateration.py:536-575) incl. the sensor rewrite (Q8)
+                            int s0 = g.s[0], s1 = g.s[1], s2 = g.s[2];
+                            long long o0 = g.o[0], o1 = g.o[1], o2 = g.o[2];
+                            if (s1 == 1) { s1 = 0; s2 = 1; const long long t = o1; o1 = o2; o2 = t; }
+                            double x[2] = {ci - geo.radius, cj - geo.radius};
+                            tri_problem q;
+                            q.xa = geo.locs[3 * s1]; q.ya = geo.locs[3 * s1 + 1]; q.za = geo.locs[3 * s1 + 2];
+                            q.xb = geo.locs[3 * s2]; q.yb = geo.locs[3 * s2 + 1]; q.zb = geo.locs[3 * s2 + 2];
+                            q.xo = geo.locs[3 * s0]; q.yo = geo.locs[3 * s0 + 1]; q.zo = geo.locs[3 * s0 + 2];
+                            q.da = static_cast<double>(o1 - o0) / geo.sr * geo.c_cm;
+                            q.db = static_cast<double>(o2 - o0) / geo.sr * geo.c_cm;
+                            const int ier = hybrj2(&q, x, 0.01, 20, nullptr);
+                            if (ier == 1) {
+                                out[0] = x[0]; out[1] = x[1]; found = 1;
+                                // remove_seed (multilateration.py:160-167): same first sensor and onset
+                                int w = 0;
+                                for (int r = 0; r < nn; ++r)
+                                    if (!(ngp[r].s[0] == g.s[0] && ngp[r].o[0] == g.o[0])) ngp[w++] = ngp[r];
+                                nn = w;
+                            }
+                            returned = true;  // self.ongoing = new_groups; return res
+                            break;
+                        }
+                    }
+                    push(g);
+                }
+            }
+            if (static_cast<double>(lag) <= static_cast<double>(geo.max_max[g.s[0]])) push(g);
+        }
+        if (!returned) {
+            SlGroup single;
+            single.len = 1;
+            for (int k = 0; k < SL_LEN; ++k) { single.s[k] = -1; single.o[k] = 0; }
+            single.s[0] = sensor; single.o[0] = onset;
+            push(single);
+        }
+        ng = nn;
+        for (int gi = 0; gi < ng; ++gi) {
+            gl[gi] = ngp[gi].len;
+            for (int k = 0; k < SL_LEN; ++k) { gs[gi * SL_LEN + k] = ngp[gi].s[k]; go[gi * SL_LEN + k] = ngp[gi].o[k]; }
+        }
+    }
+    a.g_count[st] = ng;
+    a.xy[2 * static_cast<int64_t>(st)] = out[0];
+    a.xy[2 * static_cast<int64_t>(st) + 1] = out[1];
+    a.found[st] = found ? 1 : (overflow ? -1 : 0);
+}
+
 // solve_trilateration / solve_trilateration_3d (multilateration.py:170-316) with an explicit seed, one
 // thread per problem: prob [P, 11] = (sensor_a xyz, sensor_b xyz, sensor_origin xyz, delta_d_a, delta_d_b).
 __global__ void k5_solve(const double *prob, const double *seed, int P, double xtol, int maxfev, double *xy,
@@ -372,6 +516,43 @@ __global__ void k5_solve(const double *prob, const double *seed, int P, double x
 }  // namespace ofp
 
 using namespace ofp;
+
+extern "C" int ofp_stream_locate_state_bytes(int32_t n_streams, int64_t *count_bytes, int64_t *len_bytes,
+                                             int64_t *sensor_bytes, int64_t *onset_bytes) {
+    OFP_REQUIRE(count_bytes && len_bytes && sensor_bytes && onset_bytes, "null argument");
+    *count_bytes = 4ll * n_streams;
+    *len_bytes = 4ll * n_streams * SL_GMAX;
+    *sensor_bytes = 4ll * n_streams * SL_GMAX * SL_LEN;
+    *onset_bytes = 8ll * n_streams * SL_GMAX * SL_LEN;
+    return OFP_OK;
+}
+
+extern "C" int ofp_stream_locate(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                                 int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                                 const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                                 double c_cm_s, int32_t n_streams, int32_t n_channels, const int32_t *det_channel_dev,
+                                 const int32_t *det_delta_dev, const int32_t *det_count_dev, int64_t current_index,
+                                 int32_t *state_count_dev, int32_t *state_len_dev, int32_t *state_sensor_dev,
+                                 int64_t *state_onset_dev, double *xy_dev, int32_t *found_dev, void *stream) {
+    OFP_REQUIRE(sensor_xyz_dev && lag_maps_dev && max_lags_dev && min_lags_dev && max_max_dev && det_channel_dev &&
+                    det_delta_dev && det_count_dev && state_count_dev && state_len_dev && state_sensor_dev &&
+                    state_onset_dev && xy_dev && found_dev, "null argument");
+    OFP_REQUIRE(n_sensors >= 3 && n_channels >= 1 && n_channels <= 32, "bad sensor / channel count");
+    if (n_streams == 0) return OFP_OK;
+    SlArgs a;
+    a.geo.locs = sensor_xyz_dev; a.geo.maps = lag_maps_dev; a.geo.max_lags = max_lags_dev;
+    a.geo.min_lags = min_lags_dev; a.geo.max_max = max_max_dev; a.geo.S = n_sensors; a.geo.Hm = map_size;
+    a.geo.H = 0; a.geo.n_per_hit = 3; a.geo.radius = radius_cm; a.geo.samples_per_cm = samples_per_cm;
+    a.geo.sr = sr; a.geo.c_cm = c_cm_s; a.geo.sensors = nullptr; a.geo.onsets = nullptr; a.geo.onset_stride = 0;
+    a.geo.xy = nullptr; a.geo.status = nullptr;
+    a.n_streams = n_streams; a.C = n_channels; a.det_ch = det_channel_dev; a.det_delta = det_delta_dev;
+    a.det_cnt = det_count_dev; a.current_index = current_index; a.g_count = state_count_dev;
+    a.g_len = state_len_dev; a.g_sensor = state_sensor_dev; a.g_onset = state_onset_dev; a.xy = xy_dev;
+    a.found = found_dev;
+    k5_stream_locate<<<(n_streams + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
 
 extern "C" int ofp_solve_trilateration(const double *problems_dev, const double *seeds_dev, int32_t n_problems,
                                        double xtol, int32_t maxfev, double *xy_dev, int32_t *ier_dev,

@@ -101,3 +101,60 @@ class StreamBatch:
     def process(self, blocks, return_rel: bool = False):
         """blocks [S, B, C] (device tensor or numpy) -> (channels [S, C], deltas [S, C], counts [S], rel)."""
         return self.det.process_block(blocks, return_rel=return_rel)
+
+
+class StreamLocatorBatch:
+    """detect_hits for S concurrent streams on the device: ``StreamBatch`` (K1, one launch per block)
+    followed by ``ofp_stream_locate`` (one thread per stream runs Multilaterate3D.locate's group state
+    machine on the block's detections).  BASELINE config 4: 4096 streams x 3 mics x 128-sample blocks,
+    two launches per block, nothing returns to the host but the located positions."""
+
+    def __init__(self, n_streams: int, ml_conf: dict, n_channels: int = config.N_CHANNELS,
+                 blocksize: int = config.BLOCKSIZE, detector_kw: dict | None = None):
+        import ctypes as C
+
+        from .. import _lib
+
+        kw = dict(REALTIME_DETECTOR)
+        kw.update(detector_kw or {})
+        self.torch = torch = _lib.require_cuda()
+        self.S, self.C, self.blocksize = n_streams, n_channels, blocksize
+        self.det = detection.BatchedOnsetDetector(n_streams, n_channels, blocksize, **kw)
+        self.m = multilateration.Multilaterate3D(sensor_locations=ml_conf["sensor_locations"], sr=kw["sr"],
+                                                 medium=ml_conf["medium"], c=ml_conf.get("c"))
+        sizes = [C.c_int64() for _ in range(4)]
+        _lib.check(_lib.lib().ofp_stream_locate_state_bytes(C.c_int32(n_streams), *[C.byref(v) for v in sizes]))
+        self._state = [torch.zeros((v.value,), dtype=torch.uint8, device="cuda") for v in sizes]
+        self.current_index = 0
+
+    def reset(self):
+        for t in self._state:
+            t.zero_()
+        self.det.reset()
+        self.current_index = 0
+
+    def locate_detections(self, ch, delta, cnt):
+        """Feed one block's detections (ofp_detect_block's output) to every stream's state machine.
+        Returns (xy [S, 2] float64, found [S] int32)."""
+        import ctypes as C
+
+        from .. import _lib
+        from .._lib import ptr, stream_ptr
+
+        torch, m = self.torch, self.m
+        xy = torch.empty((self.S, 2), dtype=torch.float64, device="cuda")
+        found = torch.empty((self.S,), dtype=torch.int32, device="cuda")
+        _lib.check(_lib.lib().ofp_stream_locate(
+            ptr(m._locs), C.c_int32(m._S), ptr(m._maps), C.c_int32(m._M), ptr(m._mx), ptr(m._mn), ptr(m._mm),
+            C.c_double(m.radius), C.c_double(m.samples_per_cm), C.c_double(m.sr), C.c_double(m.c),
+            C.c_int32(self.S), C.c_int32(self.C), ptr(ch), ptr(delta), ptr(cnt), C.c_int64(self.current_index),
+            ptr(self._state[0]), ptr(self._state[1]), ptr(self._state[2]), ptr(self._state[3]), ptr(xy), ptr(found),
+            stream_ptr()))
+        return xy, found
+
+    def detect_hits(self, blocks):
+        """blocks [S, B, C] -> (xy [S, 2] cm (NaN = no hit), found [S]); advances every stream by one block."""
+        ch, dl, cnt, _ = self.det.process_block(blocks, return_rel=False)
+        xy, found = self.locate_detections(ch, dl, cnt)
+        self.current_index += self.blocksize
+        return xy, found

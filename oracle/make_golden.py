@@ -416,8 +416,72 @@ def gen_frames():
     print("frames ok", out["fe_min"].shape, out["fe_each"].shape, out["bcc"].shape)
 
 
+def stream_fsm_events(seed=91, n_streams=48, n_blocks=60):
+    """Per-block detection lists for the group state machine: mostly plausible hits (three sensors
+    within the legal lags), plus out-of-order onsets, repeated sensors, stray single detections and
+    lags just outside the legal range -- everything locate()'s branches react to."""
+    rng = np.random.default_rng(seed)
+    locs = synth.sensor_xyz(synth.SENSORS_3MIC)
+    c = synth.speed_cm_s("air")
+    ev = np.full((n_streams, n_blocks, 3, 2), -1, np.int64)  # (channel, delta) per slot, -1 = none
+    cnt = np.zeros((n_streams, n_blocks), np.int64)
+    for s in range(n_streams):
+        for b in range(n_blocks):
+            kind = rng.uniform()
+            dets = []
+            if kind < 0.45:      # a hit: all three sensors in this block
+                rr, ang = 0.9 * 17.78 * np.sqrt(rng.uniform()), rng.uniform(0, 2 * np.pi)
+                p = np.array([rr * np.cos(ang), rr * np.sin(ang), 0.0])
+                d = np.round(np.sqrt(((locs - p) ** 2).sum(1)) / c * 96000).astype(int)
+                base = int(rng.integers(0, 128 - (d.max() - d.min()) - 1)) if d.max() - d.min() < 120 else 0
+                dets = [(k, base + int(d[k] - d.min()) + int(rng.integers(-2, 3))) for k in range(3)]
+                dets = [(k, min(max(v, 0), 127)) for k, v in dets]
+                if rng.uniform() < 0.2:
+                    dets = dets[: int(rng.integers(1, 3))]  # one sensor missed it
+            elif kind < 0.6:     # stray detections
+                for k in rng.permutation(3)[: int(rng.integers(1, 3))]:
+                    dets.append((int(k), int(rng.integers(0, 128))))
+            elif kind < 0.65:    # the same sensor twice cannot happen within a block; leave empty
+                dets = []
+            np.random.default_rng(seed + s * 1000 + b).shuffle(dets)  # K1 reports in channel order, keep both
+            dets.sort(key=lambda t: t[0])
+            for i, (k, v) in enumerate(dets):
+                ev[s, b, i] = (k, v)
+            cnt[s, b] = len(dets)
+    return ev, cnt
+
+
+def gen_stream_fsm(ml):
+    """Multilaterate3D.locate fed block by block as PlayRec.detect_hits does (no rec_audio)."""
+    ev, cnt = stream_fsm_events()
+    S, NB = cnt.shape
+    res = np.full((S, NB, 2), np.nan)
+    glen = np.zeros((S, NB), np.int64)
+    for s in range(S):
+        m = ml.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+        cur = 0
+        with contextlib.redirect_stdout(io.StringIO()):
+            for b in range(NB):
+                k = int(cnt[s, b])
+                c = ev[s, b, :k, 0]
+                d = [cur + int(v) for v in ev[s, b, :k, 1]]
+                if k:
+                    for i in np.argsort(d):
+                        r = m.locate(int(c[i]), d[i])
+                        if r is not None:
+                            res[s, b] = r
+                            break
+                glen[s, b] = len(m.ongoing)
+                cur += 128
+    np.savez_compressed(OUT / "stream_fsm.npz", res=res, n_groups=glen, env=env())
+    print("stream_fsm: located", int(np.isfinite(res[..., 0]).sum()), "of", int((cnt == 3).sum()), "full blocks")
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "fsm" in sys.argv:
+        gen_stream_fsm(rh.load_reference()[1])
+        return
     if "frames" in sys.argv:
         gen_frames()
         return
@@ -436,6 +500,7 @@ def main():
     gen_tools(det, ml)
     gen_stream_cc(det, ml)
     gen_frames()
+    gen_stream_fsm(ml)
 
 
 if __name__ == "__main__":

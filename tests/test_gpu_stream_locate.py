@@ -1,0 +1,67 @@
+"""Batched streaming locate (SURVEY 8f rank 1 / BASELINE config 4): one thread per stream runs
+Multilaterate3D.locate's group state machine.  Golden: the unmodified reference fed the same per-block
+detections stream by stream (tests/golden/stream_fsm.npz: located positions and the length of
+`ongoing` after every block)."""
+import numpy as np
+import pytest
+
+from onset_fingerprinting_b200 import synth
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ML_CONF = {"sensor_locations": synth.SENSORS_3MIC, "medium": "air", "c": None}
+
+
+def test_group_state_machine_vs_reference(golden_dir):
+    from oracle.make_golden import stream_fsm_events
+    from onset_fingerprinting_b200.realtime.audio import StreamLocatorBatch
+
+    g = np.load(golden_dir / "stream_fsm.npz")
+    ev, cnt = stream_fsm_events()
+    S, NB = cnt.shape
+    sl = StreamLocatorBatch(S, ML_CONF)
+    n_loc = 0
+    for b in range(NB):
+        ch = torch.from_numpy(ev[:, b, :, 0].astype(np.int32)).cuda()
+        dl = torch.from_numpy(ev[:, b, :, 1].astype(np.int32)).cuda()
+        c = torch.from_numpy(cnt[:, b].astype(np.int32)).cuda()
+        xy, found = sl.locate_detections(ch, dl, c)
+        sl.current_index += 128
+        xy, found = xy.cpu().numpy(), found.cpu().numpy()
+        want = g["res"][:, b]
+        ok = np.isfinite(want[:, 0])
+        assert np.array_equal(found == 1, ok), b
+        assert (found >= 0).all()
+        assert np.allclose(xy[ok], want[ok], rtol=1e-9, atol=1e-9)
+        n_groups = sl._state[0].view(torch.int32).cpu().numpy()
+        assert np.array_equal(n_groups, g["n_groups"][:, b]), b
+        n_loc += int(ok.sum())
+    assert n_loc > 900
+
+
+def test_detect_hits_batch_matches_single_stream_locator():
+    """K1 + state machine for a batch of streams == BlockLocator (the single-stream mirror of
+    PlayRec.detect_hits) run on each stream separately."""
+    from onset_fingerprinting_b200.realtime.audio import BlockLocator, StreamLocatorBatch
+
+    S, nblk = 5, 600
+    xs, _ = synth.drum_batch(S, seconds=nblk * 128 / 96000, seed=77, first_hit=9000)
+    xs = xs[:, : nblk * 128]
+    sl = StreamLocatorBatch(S, ML_CONF)
+    xd = torch.from_numpy(xs).cuda()
+    got = {}
+    for b in range(nblk):
+        xy, found = sl.detect_hits(xd[:, b * 128:(b + 1) * 128])
+        f = found.cpu().numpy()
+        for s in np.nonzero(f == 1)[0]:
+            got[(int(s), b)] = xy[s].cpu().numpy()
+    assert len(got) > 10
+    for s in range(S):
+        bl = BlockLocator(ML_CONF)
+        for b in range(nblk):
+            r = bl.detect_hits(xs[s, b * 128:(b + 1) * 128])
+            if r is None:
+                assert (s, b) not in got
+            else:
+                assert np.array_equal(got[(s, b)], np.asarray([r.x, r.y]))
