@@ -10,8 +10,11 @@ import ctypes as C
 import re
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libofp.so"
+# OFP_LIB selects another build of the same ABI (A/B runs of kernel variants); default: the in-tree library
+LIB_PATH = Path(os.environ["OFP_LIB"]).resolve() if os.environ.get("OFP_LIB") else PKG / "libofp.so"
 HEADER = PKG.parent / "include" / "ofp.h"
 
 _lib = None
