@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--e2e-recordings", type=int, default=3072)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--workload", default="batch", choices=["batch", "hits16", "realtime"],
+    ap.add_argument("--workload", default="batch", choices=["batch", "hits16", "realtime", "spectral"],
                     help="batch = configs[1] (headline); hits16 = configs[2] (16-channel hit mining, K4+K5); "
                          "realtime = configs[3] (4096 concurrent 128-sample block streams)")
     ap.add_argument("--hits", type=int, default=1000000, help="hits16: number of hits (over all GPUs)")
@@ -445,6 +445,11 @@ def run_hits16(args):
     _lib.check(_lib.lib().ofp_cc_screen_stats(cs, 1))
     screen = {"pairs": int(cs[0]), "single_survivor": int(cs[1]), "few_survivors_exact": int(cs[2]),
               "exact_all_lags": int(cs[3])}
+    cpu = e2e = None
+    if rank == 0 and not args.skip_cpu:
+        cpu = hits16_cpu_baseline(x, onsets, kw, args.cpu_seconds)
+    if rank == 0:
+        e2e = hits16_e2e(torch, detection, ml, x, onsets, kw)
     if rank == 0:
         print(json.dumps({
             "metric": "hits/sec through lag refinement + multilateration (16-channel hit mining)",
@@ -456,9 +461,128 @@ def run_hits16(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "k4_fix", "kernel_ms": k4_ms, "peak_source": src,
                          "algorithmic_bytes_per_hit": bytes_per_hit,
-                         "note": "K4 at 16 ch is FP64-issue bound (3.4 M double MACs per hit), not HBM bound"},
-            "cpu_baseline": None, "e2e": None, "gpu_launches": 2 * args.steps, "clocks": clk.summary(),
+                         "note": "K4 at 16 ch is instruction bound (median filter, section preparation, float32 "
+                                 "lag screening = 41 % of the instructions, reductions), not HBM bound"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clk.summary(),
             "fix_ok": ok, "located": loc, "cc_screening": screen}))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def _fix_worker(job):
+    from oracle import oracle as orc
+
+    xs, on, kw = job
+    n = 0
+    for k in range(len(xs)):
+        orc.fix_onsets(xs[k], on[k:k + 1], filter_size=kw["filter_size"], d=kw["d"], take_abs=kw["take_abs"],
+                       normalization_cutoff=kw["normalization_cutoff"], onset_tolerance=kw["onset_tolerance"])
+        n += 1
+    return n
+
+
+def hits16_cpu_baseline(x, onsets, kw, budget_s):
+    """The oracle's C port of fix_onsets (the reference's numpy fix_onsets runs ~0.3 ms/hit at 3 ch and
+    cannot be imported on the GPU box) over a bounded sample of the step's hits on all host cores."""
+    import multiprocessing as mp
+
+    cores = host_cores()
+    n = int(min(x.shape[0], max(cores * 8, 400 * cores * budget_s / 15.0)))
+    xs, on = x[:n].cpu().numpy(), onsets[:n].cpu().numpy().astype(np.int64)
+    jobs = [(xs[i::cores], on[i::cores], kw) for i in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        done = sum(pool.map(_fix_worker, jobs))
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "hits/s", "cores": cores, "kind": "port",
+            "sample": f"{done} of the step's hits, lag refinement only (oracle_c.c:orc_fix_group), {dt:.1f} s"}
+
+
+def hits16_e2e(torch, detection, ml, x, onsets, kw, n=40000):
+    """Same metric with the sections in pinned host memory: copy in, K4 + K5, results back."""
+    n = min(n, x.shape[0])
+    xh = torch.empty((n,) + tuple(x.shape[1:]), dtype=torch.float32, pin_memory=True)
+    xh.copy_(x[:n])
+    oh = torch.empty((n, onsets.shape[1]), dtype=torch.int32, pin_memory=True)
+    oh.copy_(onsets[:n])
+    torch.cuda.synchronize()
+
+    def call():
+        xd = xh.cuda(non_blocking=True)
+        od = oh.cuda(non_blocking=True)
+        fixed, lags, st = detection.fix_onsets_batch(xd, None, od, **kw)
+        first3 = torch.argsort(fixed, dim=1, stable=True)[:, :3].to(torch.int32)
+        xy, lst = ml.locate_batch(torch.gather(fixed, 1, first3.long()), first3)
+        return fixed.cpu(), xy.cpu(), lst.cpu()
+
+    call()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        call()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": n / dt, "unit": "hits/s", "h2d_bytes_per_step": int(xh.numel() * 4 + oh.numel() * 4),
+            "d2h_bytes_per_step": int(n * (onsets.shape[1] * 4 + 16 + 4)), "hits": n, "ms": dt * 1e3}
+
+
+def run_spectral(args):
+    """configs[4], feature half: spectral-flux onset strength (2048-point Hann rFFT every 128 samples of the
+    channel mean, recording.py:273-311) over the configs[1] batch; K2 = csrc/spectral_flux.cu."""
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from onset_fingerprinting_b200 import spectral, synth
+    from oracle import spectral_np
+
+    R, N = args.recordings, int(args.seconds * SR)
+    x = synth.drum_batch_device(R, N, seed=1234, rec_offset=rank * R)
+    for _ in range(args.warmup):
+        flux = spectral.spectral_flux_batch(x, 2048, 128)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            flux = spectral.spectral_flux_batch(x, 2048, 128)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ms /= args.steps
+    frames = R * (N // 128)
+    flops = frames * 5.0 * 2048 * 11  # 5 N log2 N per frame
+    peak, src = _peak()
+    alg_bytes = R * N * N_CH * 4 + frames * 4
+    cpu = None
+    if rank == 0 and not args.skip_cpu:
+        xs = x[0, : 96000].cpu().numpy()
+        t0 = time.perf_counter()
+        spectral_np.onset_strength(xs)
+        dt = time.perf_counter() - t0
+        cpu = {"value": xs.shape[0] / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+               "sample": f"1 s of one recording, numpy rfft per hop (oracle/spectral_np.py), {dt:.2f} s"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "samples/sec through the spectral-flux onset-strength feature", "value": world * R * N / (ms / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[4] (features): {R} recordings x {args.seconds:g} s, 2048-point rFFT, hop 128, "
+                                   "3-channel mean", "l2": "inputs larger than L2"},
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_bytes / (ms / 1e3) / 1e9 / peak, "traffic": None, "kernel": "k2_flux",
+                         "kernel_ms": ms, "peak_source": src,
+                         "note": f"FP32-compute bound: {flops / (ms / 1e3) / 1e12:.1f} TFLOP/s of FFT arithmetic"},
+            "cpu_baseline": cpu, "e2e": None, "gpu_launches": args.steps, "clocks": clk.summary(),
+            "frames_per_step": frames}))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
 
@@ -511,6 +635,8 @@ def main():
         run_hits16(args)
     elif args.workload == "realtime":
         run_realtime(args)
+    elif args.workload == "spectral":
+        run_spectral(args)
     else:
         run_ours(args)
 

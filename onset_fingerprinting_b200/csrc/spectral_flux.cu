@@ -14,6 +14,8 @@
 // never leaves shared memory.  FP32 throughout (the reference uses numpy's float32 FFT).
 #include "ofp_common.cuh"
 
+#include <algorithm>
+
 namespace ofp {
 
 constexpr int K2_THREADS = 256;
@@ -54,6 +56,12 @@ __device__ __forceinline__ float k2_block_max(float v, float *scratch) {
     return r;
 }
 
+// Twiddle exp(-2 pi i m / N) for m < N from the half-circle table tw[k], k < N/2.
+__device__ __forceinline__ float2 tw_full(const float2 *tw, int m, int H) {
+    const float2 w = tw[m & (H - 1)];
+    return m >= H ? make_float2(-w.x, -w.y) : w;
+}
+
 __global__ void __launch_bounds__(K2_THREADS) k2_flux(const K2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.n_fft, H = N / 2, tid = threadIdx.x;
@@ -63,6 +71,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_flux(const K2Args a) {
     float2 *bufB = bufA + H;                                      // [H]
     float *prevS = reinterpret_cast<float *>(bufB + H);           // [H + 1]
     float *curS = prevS + H + 1;                                  // [H + 1]
+    float *mono = curS + H + 1;                                   // [frames_per_cta * hop + N]: channel mean
     __shared__ float red[K2_THREADS / 32];
 
     const int r = blockIdx.y;
@@ -76,48 +85,68 @@ __global__ void __launch_bounds__(K2_THREADS) k2_flux(const K2Args a) {
     const float invC = 1.0f / static_cast<float>(a.C);
     const int j0 = blockIdx.x * a.frames_per_cta;
     const int j1 = min(j0 + a.frames_per_cta, a.n_frames);
-    int log2h = 0;
-    while ((1 << log2h) < H) ++log2h;
+    // ---- channel mean of every sample this CTA's frames touch, once (the frames overlap N/hop-fold) ----
+    // frame j starts at fs(j); the buffer covers frames j0-1 (seed of the previous spectrum) .. j1-1
+    const int64_t fs0 = a.center ? static_cast<int64_t>(j0 - 1) * a.hop - H : static_cast<int64_t>(j0) * a.hop - N;
+    const int span = (j1 - j0) * a.hop + N;
+    for (int i = tid; i < span; i += K2_THREADS) {
+        int64_t t = fs0 + i;
+        if (a.center && a.reflect) {  // numpy pad mode 'reflect' (no edge repeat)
+            if (t < 0) t = -t;
+            if (t >= a.n_samples) t = 2 * (a.n_samples - 1) - t;
+        }
+        float sv = 0.f;
+        if (t >= 0 && t < a.n_samples) {
+            const float *p = xr + t * a.C;
+            for (int c = 0; c < a.C; ++c) sv += p[c];
+            sv = a.C > 1 ? sv * invC : sv;
+        }
+        mono[i] = sv;
+    }
     __syncthreads();
 
     for (int j = j0 - 1; j < j1; ++j) {  // frame j0-1 only seeds prevS
-        // ---- gather + window: z[n] = x[2n] + i x[2n+1] ----
-        const int64_t start = a.center ? static_cast<int64_t>(j) * a.hop - H
-                                       : static_cast<int64_t>(j + 1) * a.hop - N;
-        for (int n = tid; n < H; n += K2_THREADS) {
-            float v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int64_t t = start + 2 * n + e;
-                if (a.center && a.reflect) {  // numpy pad mode 'reflect' (no edge repeat)
-                    if (t < 0) t = -t;
-                    if (t >= a.n_samples) t = 2 * (a.n_samples - 1) - t;
-                }
-                float s = 0.f;
-                if (j >= 0 && t >= 0 && t < a.n_samples) {
-                    const float *p = xr + t * a.C;
-                    for (int c = 0; c < a.C; ++c) s += p[c];
-                    s = a.C > 1 ? s * invC : s;
-                }
-                v[e] = s * win[2 * n + e];
-            }
-            bufA[n] = make_float2(v[0], v[1]);
+        if (j < 0) {  // before the recording: the spectrum of silence
+            const float s0 = a.mode == 0 ? 10.0f * log10f(1e-10f) : 0.0f;
+            for (int k = tid; k <= H; k += K2_THREADS) prevS[k] = s0;
+            __syncthreads();
+            continue;
         }
+        // ---- window: z[n] = x[2n] + i x[2n+1] ----
+        const float *fr = mono + static_cast<int64_t>(j - (j0 - 1)) * a.hop;
+        for (int n = tid; n < H; n += K2_THREADS)
+            bufA[n] = make_float2(fr[2 * n] * win[2 * n], fr[2 * n + 1] * win[2 * n + 1]);
         __syncthreads();
-        // ---- Stockham radix-2 FFT of H complex points (autosort, ping-pong) ----
+        // ---- Stockham autosort FFT of H complex points: radix-4 passes, one radix-2 pass if log2 H is odd ----
         float2 *src = bufA, *dst = bufB;
-        for (int s = 0; s < log2h; ++s) {
-            const int half = 1 << s;           // butterflies span `half` outputs
+        int L = 1;
+        for (; L * 4 <= H; L *= 4) {
+            const int q = H / 4, tstep = N / (4 * L);  // W_{4L}^{k} = exp(-2 pi i k tstep / N)
+            for (int i = tid; i < q; i += K2_THREADS) {
+                const int k = i & (L - 1);
+                const float2 v0 = src[i];
+                float2 v1 = src[i + q], v2 = src[i + 2 * q], v3 = src[i + 3 * q];
+                if (L > 1) {
+                    v1 = cmul(v1, tw_full(tw, k * tstep, H));
+                    v2 = cmul(v2, tw_full(tw, 2 * k * tstep, H));
+                    v3 = cmul(v3, tw_full(tw, 3 * k * tstep, H));
+                }
+                const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+                const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+                const int o = ((i - k) << 2) + k;
+                dst[o] = make_float2(s02.x + s13.x, s02.y + s13.y);
+                dst[o + L] = make_float2(d02.x + d13.y, d02.y - d13.x);      // d02 - i d13
+                dst[o + 2 * L] = make_float2(s02.x - s13.x, s02.y - s13.y);
+                dst[o + 3 * L] = make_float2(d02.x - d13.y, d02.y + d13.x);  // d02 + i d13
+            }
+            __syncthreads();
+            float2 *tmp = src; src = dst; dst = tmp;
+        }
+        if (L < H) {  // remaining radix-2 pass (L == H / 2)
             for (int i = tid; i < H / 2; i += K2_THREADS) {
-                const int k = i & (half - 1);  // position inside the sub-transform
-                const int blk = i >> s;
-                const float2 u = src[i], t = src[i + H / 2];
-                // twiddle exp(-2 pi i k / (2*half)) = tw[k * (N / (2*half)) ... with tw of size H over N]
-                const float2 w = tw[k * (H / half)];  // index k * N/(2*half): exp(-2 pi i k/(2 half))
-                const float2 tt = cmul(t, w);
-                const int o = (blk << (s + 1)) + k;
-                dst[o] = make_float2(u.x + tt.x, u.y + tt.y);
-                dst[o + half] = make_float2(u.x - tt.x, u.y - tt.y);
+                const float2 u = src[i], t = cmul(src[i + H / 2], tw_full(tw, i * (N / (2 * L)), H));
+                dst[i] = make_float2(u.x + t.x, u.y + t.y);
+                dst[i + L] = make_float2(u.x - t.x, u.y - t.y);
             }
             __syncthreads();
             float2 *tmp = src; src = dst; dst = tmp;
@@ -196,10 +225,17 @@ int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int6
     if (n_frames <= 0 || n_rec == 0) return OFP_OK;
     K2Args a;
     a.x = x_dev; a.rec_stride = rec_stride; a.n_samples = n_samples; a.C = n_channels; a.n_fft = n_fft; a.hop = hop;
-    a.n_frames = n_frames; a.frames_per_cta = 64; a.center = center; a.reflect = reflect; a.mode = mode;
+    a.n_frames = n_frames; a.center = center; a.reflect = reflect; a.mode = mode;
     a.top_db = top_db; a.window = window_dev; a.weight = weight_dev; a.flux = flux_dev;
     const int H = n_fft / 2;
-    const size_t smem = sizeof(float) * n_fft + sizeof(float2) * 3 * H + sizeof(float) * 2 * (H + 1) + 16;
+    // frames per CTA: enough that the shared channel-mean buffer is read ~1.5x instead of n_fft/hop-fold,
+    // few enough that 3 CTAs fit an SM and the grid keeps every SM busy
+    int fpc = std::max(8, std::min(64, (3 * n_fft / 2 + hop - 1) / hop));
+    const size_t fixed = sizeof(float) * n_fft + sizeof(float2) * 3 * H + sizeof(float) * 2 * (H + 1) + 16;
+    while (fpc > 1 && fixed + sizeof(float) * (static_cast<size_t>(fpc) * hop + n_fft) > 220 * 1024) fpc /= 2;
+    a.frames_per_cta = fpc;
+    const size_t smem = fixed + sizeof(float) * (static_cast<size_t>(fpc) * hop + n_fft);
+    OFP_REQUIRE(smem <= 227 * 1024, "n_fft %d with hop %d needs %zu bytes of shared memory", n_fft, hop, smem);
     OFP_CUDA_CHECK(cudaFuncSetAttribute(k2_flux, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     dim3 grid((n_frames + a.frames_per_cta - 1) / a.frames_per_cta, static_cast<unsigned>(n_rec));
     k2_flux<<<grid, K2_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
