@@ -15,6 +15,7 @@
 #include "ofp_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ofp {
 
@@ -182,6 +183,10 @@ __global__ void __launch_bounds__(K2_THREADS) k2_flux(const K2Args a) {
     }
 }
 
+}  // namespace ofp
+#include "spectral_flux_warp.cuh"
+namespace ofp {
+
 // librosa.util.peak_pick restated (greedy, sequential; one thread per recording):
 // x[n] is a peak if x[n] == max(x[n-pre_max : n+post_max+1]) and x[n] >= mean(x[n-pre_avg : n+post_avg+1]) + delta
 // and n - last_peak > wait.
@@ -228,6 +233,18 @@ int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int6
     a.n_frames = n_frames; a.center = center; a.reflect = reflect; a.mode = mode;
     a.top_db = top_db; a.window = window_dev; a.weight = weight_dev; a.flux = flux_dev;
     const int H = n_fft / 2;
+    // 2048-point fast path (the realtime / config-5 shape): one warp per frame, transform in registers
+    const size_t smem_w = sizeof(K2WSmem) + sizeof(float) * (static_cast<size_t>(K2W_WARPS * K2W_FRAMES) * hop + n_fft);
+    static const bool force_generic = getenv("OFP_K2_GENERIC") != nullptr;
+    if (n_fft == 2 * K2W_H && hop % 2 == 0 && smem_w <= 113 * 1024 && !force_generic) {
+        auto kern = mode == 0 ? k2_flux_warp<0> : k2_flux_warp<1>;
+        OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_w)));
+        const int fpc = K2W_WARPS * K2W_FRAMES;
+        dim3 grid((n_frames + fpc - 1) / fpc, static_cast<unsigned>(n_rec));
+        kern<<<grid, K2W_WARPS * 32, smem_w, static_cast<cudaStream_t>(stream)>>>(a);
+        OFP_CUDA_CHECK(cudaGetLastError());
+        return OFP_OK;
+    }
     // frames per CTA: enough that the shared channel-mean buffer is read ~1.5x instead of n_fft/hop-fold,
     // few enough that 3 CTAs fit an SM and the grid keeps every SM busy
     int fpc = std::max(8, std::min(64, (3 * n_fft / 2 + hop - 1) / hop));

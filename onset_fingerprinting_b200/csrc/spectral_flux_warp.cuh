@@ -1,0 +1,215 @@
+// K2, 2048-point fast path: one WARP per frame, the transform lives in registers.
+//
+// The 2048 real samples of a frame are packed into 1024 complex points z[n] = x[2n] + i x[2n+1] and
+// transformed by the four-step factorisation 1024 = 32 x 32 with n = n1 + 32 n2, k = 32 k1 + k2:
+//   step 1  lane n1 holds z[n1 + 32 n2], n2 = 0..31 (conflict-free 8-byte shared loads of the staged
+//           channel mean times the window) and runs a 32-point DFT over n2 in registers;
+//   step 2  Y[n1][k2] *= W_1024^(n1 k2)   (table T[k2][n1], conflict-free);
+//   step 3  transpose through a padded warp-private shared tile (the only exchange, __syncwarp only),
+//           lane k2 runs a 32-point DFT over n1 -> Z[32 k1 + k2] in register k1.
+// The real-input split needs Z[k] and Z[1024 - k]: bin 32 k1 + k2 pairs with register 31 - k1 of lane
+// 32 - k2, i.e. one warp shuffle per word (lane 0 pairs with its own registers).  Log-power / magnitude,
+// the frame maximum, the rectified difference against the previous frame and the mean over the bins
+// are register + shuffle work; the previous spectrum stays in registers because a warp walks
+// K2W_FRAMES consecutive frames.  No block-wide barrier inside the frame loop.
+#pragma once
+
+namespace ofp {
+
+constexpr int K2W_WARPS = 4;     // warps per CTA
+constexpr int K2W_FRAMES = 16;   // consecutive frames per warp (+1 seed frame)
+constexpr int K2W_H = 1024;      // complex points
+constexpr int K2W_PAD = 33;      // row stride (float2) of the transpose tile
+
+__host__ __device__ constexpr int brev5(int v) {
+    return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+}
+
+// d * W_32^m, m = 0..15 (compile-time m after unrolling: the branches fold away)
+__device__ __forceinline__ float2 mul_w32(float2 d, int m) {
+    constexpr float R = 0.70710678118654752f;
+    // cos(2 pi m / 32), sin(2 pi m / 32)
+    constexpr float CS[16] = {1.0f, 0.98078528040323044f, 0.92387953251128676f, 0.83146961230254524f,
+                              0.70710678118654752f, 0.55557023301960222f, 0.38268343236508977f,
+                              0.19509032201612827f, 0.0f, -0.19509032201612827f, -0.38268343236508977f,
+                              -0.55557023301960222f, -0.70710678118654752f, -0.83146961230254524f,
+                              -0.92387953251128676f, -0.98078528040323044f};
+    constexpr float SN[16] = {0.0f, 0.19509032201612827f, 0.38268343236508977f, 0.55557023301960222f,
+                              0.70710678118654752f, 0.83146961230254524f, 0.92387953251128676f,
+                              0.98078528040323044f, 1.0f, 0.98078528040323044f, 0.92387953251128676f,
+                              0.83146961230254524f, 0.70710678118654752f, 0.55557023301960222f,
+                              0.38268343236508977f, 0.19509032201612827f};
+    if (m == 0) return d;
+    if (m == 8) return make_float2(d.y, -d.x);                       // -i
+    if (m == 4) return make_float2((d.x + d.y) * R, (d.y - d.x) * R);   // (1 - i) / sqrt 2
+    if (m == 12) return make_float2((d.y - d.x) * R, -(d.x + d.y) * R); // (-1 - i) / sqrt 2
+    const float c = CS[m], s = SN[m];                                // W = c - i s
+    return make_float2(fmaf(d.y, s, d.x * c), fmaf(-d.x, s, d.y * c));
+}
+
+// In-place radix-2 decimation-in-frequency DFT of 32 points held in registers.
+// Result X[k] sits in v[brev5(k)].
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+#pragma unroll
+    for (int len = 32; len >= 2; len >>= 1) {
+        const int half = len >> 1, tstep = 32 / len;
+#pragma unroll
+        for (int b = 0; b < 32; b += len) {
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float2 p = v[b + i], q = v[b + i + half];
+                v[b + i] = make_float2(p.x + q.x, p.y + q.y);
+                v[b + i + half] = mul_w32(make_float2(p.x - q.x, p.y - q.y), i * tstep);
+            }
+        }
+    }
+}
+
+struct K2WSmem {
+    float2 win2[K2W_H];                   // window pairs (w[2n], w[2n+1])
+    float2 T[32 * 32];                    // T[k2][n1] = exp(-2 pi i n1 k2 / 1024)
+    float2 T2[32 * 32];                   // T2[k1][l] = exp(-2 pi i (32 k1 + l) / 2048)
+    float2 tile[K2W_WARPS][32 * K2W_PAD]; // warp-private transpose tiles
+    // followed by the channel-mean buffer: float mono[K2W_WARPS * K2W_FRAMES * hop + 2048]
+};
+
+// bin value from Z[k] and its partner Z[1024 - k]
+template <int MODE>
+__device__ __forceinline__ float k2w_bin(float2 zk, float2 zc, float2 w, float wt) {
+    const float ex = zk.x + zc.x, ey = zk.y - zc.y;  // 2 e
+    const float ox = zk.y + zc.y, oy = zc.x - zk.x;  // 2 o
+    const float re = 0.5f * (ex + (ox * w.x - oy * w.y));
+    const float im = 0.5f * (ey + (ox * w.y + oy * w.x));
+    const float p = re * re + im * im;
+    if (MODE == 0) return 3.0102999566398120f * __log2f(fmaxf(1e-10f, p));  // 10 log10 p
+    return sqrtf(p) * wt;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(K2W_WARPS * 32, 2) k2_flux_warp(const K2Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    K2WSmem &sm = *reinterpret_cast<K2WSmem *>(smem_raw);
+    float *mono = reinterpret_cast<float *>(smem_raw + sizeof(K2WSmem));
+    constexpr int N = 2 * K2W_H, H = K2W_H, NT = K2W_WARPS * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const int r = blockIdx.y;
+    const float *xr = a.x + static_cast<int64_t>(r) * a.rec_stride;
+    for (int i = tid; i < H; i += NT) {
+        sm.win2[i] = make_float2(a.window[2 * i], a.window[2 * i + 1]);
+        const int k2 = i >> 5, n1 = i & 31;
+        float s, c;
+        sincospif(-2.0f * static_cast<float>((n1 * k2) & (H - 1)) / static_cast<float>(H), &s, &c);
+        sm.T[i] = make_float2(c, s);
+        sincospif(-2.0f * static_cast<float>(i) / static_cast<float>(N), &s, &c);
+        sm.T2[i] = make_float2(c, s);
+    }
+    const int j0 = blockIdx.x * (K2W_WARPS * K2W_FRAMES);
+    const int j1 = min(j0 + K2W_WARPS * K2W_FRAMES, a.n_frames);
+    // channel mean of every sample the CTA's frames touch (frames j0-1 .. j1-1), once
+    const int64_t fs0 = a.center ? static_cast<int64_t>(j0 - 1) * a.hop - H : static_cast<int64_t>(j0) * a.hop - N;
+    const int span = (j1 - j0) * a.hop + N;
+    const float invC = 1.0f / static_cast<float>(a.C);
+    for (int i = tid; i < span; i += NT) {
+        int64_t t = fs0 + i;
+        if (a.center && a.reflect) {
+            if (t < 0) t = -t;
+            if (t >= a.n_samples) t = 2 * (a.n_samples - 1) - t;
+        }
+        float sv = 0.f;
+        if (t >= 0 && t < a.n_samples) {
+            const float *p = xr + t * a.C;
+            for (int c = 0; c < a.C; ++c) sv += p[c];
+            sv = a.C > 1 ? sv * invC : sv;
+        }
+        mono[i] = sv;
+    }
+    __syncthreads();
+
+    const int jw0 = j0 + warp * K2W_FRAMES;
+    const int jw1 = min(jw0 + K2W_FRAMES, j1);
+    if (jw0 >= jw1) return;
+    float2 *tile = sm.tile[warp];
+    const int partner = (32 - lane) & 31;
+    const bool l0 = lane == 0;
+
+    float prevS[33], curS[33];
+    for (int j = jw0 - 1; j < jw1; ++j) {
+        if (j < 0) {
+            const float s0 = MODE == 0 ? 3.0102999566398120f * __log2f(1e-10f) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 33; ++k) prevS[k] = s0;
+            continue;
+        }
+        float2 v[32];
+        {   // ---- step 1: windowed load, DFT over n2 ----
+            const float2 *fr2 = reinterpret_cast<const float2 *>(mono + static_cast<int64_t>(j - (j0 - 1)) * a.hop);
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const float2 x2 = fr2[lane + 32 * n2], w2 = sm.win2[lane + 32 * n2];
+                v[n2] = make_float2(x2.x * w2.x, x2.y * w2.y);
+            }
+            fft32(v);
+            // ---- step 2 + transpose: tile[k2][n1] = Y[n1][k2] W^(n1 k2) ----
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) {
+                float2 y = v[brev5(k2)];
+                if (k2 > 0) y = cmul(y, sm.T[k2 * 32 + lane]);
+                tile[k2 * K2W_PAD + lane] = y;
+            }
+            __syncwarp();
+            // ---- step 3: lane = k2, DFT over n1 ----
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[n1] = tile[lane * K2W_PAD + n1];
+            __syncwarp();
+            fft32(v);
+        }
+        // ---- real-input split + per-bin value; Z[32 k1 + lane] = v[brev5(k1)] ----
+        float pmax = -INFINITY;
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+            const int m = 31 - k1;
+            const float2 za = v[brev5(k1)], zb = v[brev5(m)];
+            float2 pa, pb;
+            pa.x = __shfl_sync(0xffffffffu, zb.x, partner);
+            pa.y = __shfl_sync(0xffffffffu, zb.y, partner);
+            pb.x = __shfl_sync(0xffffffffu, za.x, partner);
+            pb.y = __shfl_sync(0xffffffffu, za.y, partner);
+            if (l0) {
+                pa = v[brev5((32 - k1) & 31)];
+                pb = v[brev5(k1 + 1)];
+            }
+            const int ka = 32 * k1 + lane, kb = 32 * m + lane;
+            const float wa = (MODE == 1 && a.weight) ? a.weight[ka] : 1.0f;
+            const float wb = (MODE == 1 && a.weight) ? a.weight[kb] : 1.0f;
+            curS[k1] = k2w_bin<MODE>(za, pa, sm.T2[ka], wa);
+            curS[m] = k2w_bin<MODE>(zb, pb, sm.T2[kb], wb);
+            pmax = fmaxf(pmax, fmaxf(curS[k1], curS[m]));
+        }
+        {   // Nyquist bin (lane 0 only): X[1024] = Re Z[0] - Im Z[0]
+            const float ny = v[0].x - v[0].y, p = ny * ny;
+            float sv;
+            if (MODE == 0) sv = 3.0102999566398120f * __log2f(fmaxf(1e-10f, p));
+            else sv = sqrtf(p) * (a.weight ? a.weight[H] : 1.0f);
+            curS[32] = sv;
+            if (l0) pmax = fmaxf(pmax, sv);
+        }
+        float lo = -INFINITY;
+        if (MODE == 0 && a.top_db > 0.f) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+            lo = pmax - a.top_db;
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc += fmaxf(0.f, fmaxf(curS[k], lo) - fmaxf(prevS[k], lo));
+        if (l0) acc += fmaxf(0.f, fmaxf(curS[32], lo) - fmaxf(prevS[32], lo));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (l0 && j >= jw0) a.flux[static_cast<int64_t>(r) * a.n_frames + j] = acc / static_cast<float>(H + 1);
+#pragma unroll
+        for (int k = 0; k < 33; ++k) prevS[k] = curS[k];
+    }
+}
+
+}  // namespace ofp
