@@ -16,8 +16,17 @@
 
 namespace ofp {
 
-constexpr int K2W_WARPS = 4;     // warps per CTA
-constexpr int K2W_FRAMES = 16;   // consecutive frames per warp (+1 seed frame)
+#ifndef OFP_K2W_WARPS
+#define OFP_K2W_WARPS 4
+#endif
+#ifndef OFP_K2W_FRAMES
+#define OFP_K2W_FRAMES 16
+#endif
+#ifndef OFP_K2W_MINCTA
+#define OFP_K2W_MINCTA 2
+#endif
+constexpr int K2W_WARPS = OFP_K2W_WARPS;     // warps per CTA
+constexpr int K2W_FRAMES = OFP_K2W_FRAMES;   // consecutive frames per warp (+1 seed frame)
 constexpr int K2W_H = 1024;      // complex points
 constexpr int K2W_PAD = 33;      // row stride (float2) of the transpose tile
 
@@ -85,8 +94,68 @@ __device__ __forceinline__ float k2w_bin(float2 zk, float2 zc, float2 w, float w
     return sqrtf(p) * wt;
 }
 
+
+// Channel mean of samples [fs0, fs0 + span) of one recording into shared memory (zeros outside the
+// recording, numpy 'reflect' padding for a centred transform).  3-channel audio, the configs[1..4]
+// shape, is read as three 16-byte loads per four samples with a batch of loads in flight per thread.
+template <int NT>
+__device__ __forceinline__ void k2_fill_mono(const K2Args &a, const float *__restrict__ xr, int64_t fs0, int span,
+                                             float *mono, int tid) {
+    const float invC = 1.0f / static_cast<float>(a.C);
+    auto scalar = [&](int i) {
+        int64_t t = fs0 + i;
+        if (a.center && a.reflect) {
+            if (t < 0) t = -t;
+            if (t >= a.n_samples) t = 2 * (a.n_samples - 1) - t;
+        }
+        float sv = 0.f;
+        if (t >= 0 && t < a.n_samples) {
+            const float *p = xr + t * a.C;
+            for (int c = 0; c < a.C; ++c) sv += __ldg(p + c);
+            sv = a.C > 1 ? sv * invC : sv;
+        }
+        mono[i] = sv;
+    };
+    const bool vec3 = a.C == 3 && (reinterpret_cast<uintptr_t>(xr + fs0 * 3) & 15) == 0;
+    if (!vec3) {
+        for (int i = tid; i < span; i += NT) scalar(i);
+        return;
+    }
+    constexpr int U = 4;
+    const int groups = span >> 2;  // four samples = 12 floats = 3 float4
+    for (int g0 = 0; g0 < groups; g0 += NT * U) {
+        float4 q[U][3];
+        bool in[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int g = g0 + u * NT + tid;
+            const int64_t t = fs0 + 4 * static_cast<int64_t>(g);
+            in[u] = g < groups && t >= 0 && t + 4 <= a.n_samples;
+            if (in[u]) {
+                const float4 *p = reinterpret_cast<const float4 *>(xr + t * 3);
+                q[u][0] = __ldg(p); q[u][1] = __ldg(p + 1); q[u][2] = __ldg(p + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int g = g0 + u * NT + tid;
+            if (in[u]) {
+                float4 m;  // same summation order as the scalar path: ((c0 + c1) + c2) * (1/3)
+                m.x = ((q[u][0].x + q[u][0].y) + q[u][0].z) * invC;
+                m.y = ((q[u][0].w + q[u][1].x) + q[u][1].y) * invC;
+                m.z = ((q[u][1].z + q[u][1].w) + q[u][2].x) * invC;
+                m.w = ((q[u][2].y + q[u][2].z) + q[u][2].w) * invC;
+                *reinterpret_cast<float4 *>(mono + 4 * g) = m;
+            } else if (g < groups) {
+                for (int e = 0; e < 4; ++e) scalar(4 * g + e);
+            }
+        }
+    }
+    for (int i = (groups << 2) + tid; i < span; i += NT) scalar(i);
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(K2W_WARPS * 32, 2) k2_flux_warp(const K2Args a) {
+__global__ void __launch_bounds__(K2W_WARPS * 32, OFP_K2W_MINCTA) k2_flux_warp(const K2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K2WSmem &sm = *reinterpret_cast<K2WSmem *>(smem_raw);
     float *mono = reinterpret_cast<float *>(smem_raw + sizeof(K2WSmem));
@@ -109,21 +178,7 @@ __global__ void __launch_bounds__(K2W_WARPS * 32, 2) k2_flux_warp(const K2Args a
     // channel mean of every sample the CTA's frames touch (frames j0-1 .. j1-1), once
     const int64_t fs0 = a.center ? static_cast<int64_t>(j0 - 1) * a.hop - H : static_cast<int64_t>(j0) * a.hop - N;
     const int span = (j1 - j0) * a.hop + N;
-    const float invC = 1.0f / static_cast<float>(a.C);
-    for (int i = tid; i < span; i += NT) {
-        int64_t t = fs0 + i;
-        if (a.center && a.reflect) {
-            if (t < 0) t = -t;
-            if (t >= a.n_samples) t = 2 * (a.n_samples - 1) - t;
-        }
-        float sv = 0.f;
-        if (t >= 0 && t < a.n_samples) {
-            const float *p = xr + t * a.C;
-            for (int c = 0; c < a.C; ++c) sv += p[c];
-            sv = a.C > 1 ? sv * invC : sv;
-        }
-        mono[i] = sv;
-    }
+    k2_fill_mono<NT>(a, xr, fs0, span, mono, tid);
     __syncthreads();
 
     const int jw0 = j0 + warp * K2W_FRAMES;
