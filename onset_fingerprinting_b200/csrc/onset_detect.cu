@@ -68,6 +68,7 @@ struct K1Args {
     int32_t *on_ch, *on_idx, *on_cnt;
     int32_t cap;
     int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
+    int32_t floor_skip;  // OFP_K1_FLOOR_SKIP=0 disables the below-floor short-cut (A/B runs)
 };
 
 // Per-kernel constants held in registers for the whole launch (a one-warp CTA has registers to
@@ -75,7 +76,7 @@ struct K1Args {
 struct Coef {
     float b0, b1, b2, b3, b4, a1, a2, a3, a4;
     float fa, fr, sa, sr;
-    float floor_db, ceil_amp;
+    float floor_db, ceil_amp, vfloor;
     float amin, amax, iamin, iamax, minmin;
 };
 __device__ __forceinline__ Coef load_coef(const K1Args &a) {
@@ -84,6 +85,9 @@ __device__ __forceinline__ Coef load_coef(const K1Args &a) {
     k.a1 = a.p.a[1]; k.a2 = a.p.a[2]; k.a3 = a.p.a[3]; k.a4 = a.p.a[4];
     k.fa = a.p.fast_att; k.fr = a.p.fast_rel; k.sa = a.p.slow_att; k.sr = a.p.slow_rel;
     k.floor_db = a.p.floor_db; k.ceil_amp = -a.p.floor_db;
+    // |h + 1e-10| below vfloor => 20*log10(.) rounds below the floor => the clipped dB value IS the floor
+    // (4e-6 relative margin = 4.5 float32 ulps of the floor in dB, DESIGN.md "K1 arithmetic" (iv))
+    k.vfloor = a.floor_skip ? static_cast<float>(exp10(static_cast<double>(a.p.floor_db) / 20.0) * (1.0 - 4e-6)) : 0.0f;
     k.amin = a.p.alpha_min; k.amax = a.p.alpha_max; k.iamin = a.ia_min; k.iamax = a.ia_max;
     k.minmin = a.p.minmin;
     return k;
@@ -395,7 +399,16 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
             const float x = lds_f32(xs + u * step);
             h[u] = USE_HP ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
         }
-        to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
+        // exact short-cut (iv): a chunk whose samples all sit below the floor needs no logarithm
+        float vmax = 0.0f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) vmax = fmaxf(vmax, fabsf(__fadd_rn(h[u], 1e-10f)));
+        if (__all_sync(0xffffffffu, vmax < k.vfloor)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) db[u] = k.floor_db;
+        } else {
+            to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
+        }
     }
     bool sliver = false;
 #pragma unroll
@@ -802,6 +815,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.p = p;
     a.ia_min = static_cast<float>(1.0 - static_cast<double>(p.alpha_min));
     a.ia_max = static_cast<float>(1.0 - static_cast<double>(p.alpha_max));
+    a.floor_skip = env_int("OFP_K1_FLOOR_SKIP", 1);
     a.st = state_of(det);
     a.x = x; a.n_samples = n_samples; a.rec_stride = rec_stride;
     a.warm_n = std::min(warm_n, n_samples);
