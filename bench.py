@@ -43,9 +43,10 @@ def parse():
     ap.add_argument("--e2e-recordings", type=int, default=3072)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--workload", default="batch", choices=["batch", "hits16", "realtime", "spectral"],
+    ap.add_argument("--workload", default="batch", choices=["batch", "hits16", "realtime", "spectral", "cnn"],
                     help="batch = configs[1] (headline); hits16 = configs[2] (16-channel hit mining, K4+K5); "
                          "realtime = configs[3] (4096 concurrent 128-sample block streams)")
+    ap.add_argument("--windows", type=int, default=1000000, help="cnn: onset windows per GPU")
     ap.add_argument("--hits", type=int, default=1000000, help="hits16: number of hits (over all GPUs)")
     ap.add_argument("--streams", type=int, default=4096, help="realtime: concurrent streams per GPU")
     ap.add_argument("--blocks", type=int, default=1000, help="realtime: consecutive blocks")
@@ -587,6 +588,82 @@ def run_spectral(args):
         dist.barrier(); dist.destroy_process_group()
 
 
+def run_cnn(args):
+    """configs[4], classifier half: model.CNN inference (model.py:52-120, reference defaults: 3 x 256 windows,
+    Conv1d 3->8->16 k=3 + SiLU, Linear 4096->2) on --windows onset windows per GPU; K6 = csrc/cnn_infer.cu."""
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from onset_fingerprinting_b200 import model
+
+    torch.manual_seed(7)
+    m = model.CNN(256, 2).cuda()
+    n = args.windows
+    g = torch.Generator(device="cuda"); g.manual_seed(100 + rank)
+    x = torch.randn((n, 3, 256), device="cuda", generator=g) * 0.1
+    for _ in range(args.warmup):
+        y = m(x)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            y = m(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ms /= args.steps
+    macs = 256 * (8 * 3 * 3 + 16 * 8 * 3) + 2 * 4096
+    peak, src = _peak()
+    alg_bytes = n * (3 * 256 * 4 + 2 * 4)
+    cpu = e2e = None
+    if rank == 0 and not args.skip_cpu:
+        # the reference runs this network through stock torch modules; same modules on the host cores
+        mc = torch.nn.Sequential(m.conv_layers, torch.nn.Flatten(1), m.fc).cpu().eval()
+        xs = x[:50000].cpu()
+        with torch.no_grad():
+            mc(xs[:1000])
+            t0 = time.perf_counter(); mc(xs); dt = time.perf_counter() - t0
+        cpu = {"value": xs.shape[0] / dt, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{xs.shape[0]} windows through torch.nn modules on the host (model.py:112-117), {dt:.2f} s"}
+        m.cuda()
+    if rank == 0:
+        ne = min(n, 200000)
+        xh = torch.empty((ne, 3, 256), dtype=torch.float32, pin_memory=True); xh.copy_(x[:ne])
+        torch.cuda.synchronize()
+        m(xh.cuda(non_blocking=True)).cpu()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            m(xh.cuda(non_blocking=True)).cpu()
+        dt = (time.perf_counter() - t0) / 3
+        e2e = {"value": ne / dt, "unit": "windows/s", "h2d_bytes_per_step": int(xh.numel() * 4),
+               "d2h_bytes_per_step": int(ne * 8), "windows": ne, "ms": dt * 1e3}
+        print(json.dumps({
+            "metric": "onset windows/sec through model.CNN inference", "value": world * n / (ms / 1e3),
+            "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[4] (classifier): {n} windows x 3 ch x 256 samples per GPU, CNN [8, 16] k=3 SiLU "
+                                   "+ Linear 4096->2, random-init weights", "l2": "inputs larger than L2"},
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg_bytes / (ms / 1e3) / 1e9 / peak, "traffic": None, "kernel": "k6_cnn",
+                         "kernel_ms": ms, "peak_source": src,
+                         "note": f"FP32-FMA bound: {2 * macs * n / (ms / 1e3) / 1e12:.1f} TFLOP/s on the CUDA cores "
+                                 f"({macs} MAC per window)"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clk.summary()}))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def run_realtime(args):
     """configs[3]: S concurrent streams; per 128-sample block one K1 launch (detector) and one
     ofp_stream_locate launch (Multilaterate3D.locate's group state machine, one thread per stream).
@@ -637,6 +714,8 @@ def main():
         run_realtime(args)
     elif args.workload == "spectral":
         run_spectral(args)
+    elif args.workload == "cnn":
+        run_cnn(args)
     else:
         run_ours(args)
 

@@ -302,6 +302,25 @@ int ofp_peak_pick(const float *oe_dev, int32_t n_rec, int32_t n_frames, int32_t 
                   int32_t *n_peaks_dev, int32_t cap, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K6  onset-window network inference -- replaces model.CNN.forward in eval mode (model.py:52-120):
+ *     n_layers x [Conv1d(kernel_size, padding; stride 1, dilation 1, groups 1) + activation],
+ *     flatten (channel-major), Dropout = identity, Linear(flat, out_size).
+ * ------------------------------------------------------------------------------------- */
+
+/* Size of the packed parameter buffer and of the flattened feature vector for an architecture. */
+int ofp_cnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
+                        int32_t kernel_size, int32_t padding, int32_t out_size, int64_t *n_params_out,
+                        int32_t *flat_out);
+/* x_dev [n_windows, channels, input_size] float32 (window w at x_dev + w*win_stride elements, the layout
+ * FrameExtractor returns, data.py:55-120) -> out_dev [n_windows, out_size] float32.
+ * params_dev, packed float32: per conv layer l the weight transposed to [c_in][k][c_out_padded] followed by
+ * the bias [c_out_padded] (c_out padded to a multiple of 8 with zeros), then fc.weight [out_size][flat]
+ * and fc.bias [out_size].  activation: 0 SiLU (the reference default), 1 ReLU, 2 tanh, 3 identity. */
+int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
+                    int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
+                    int32_t activation, const float *params_dev, int32_t out_size, float *out_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Benchmark input: seeded synthetic multi-mic drum audio generated on the device
  * (SURVEY.md section 8d signal model; not a reference function).  x_dev [R, N, C] float32;
  * sensors_xyz_host [C, 3] cm (host); rec_offset = global index of recording 0 of this shard;

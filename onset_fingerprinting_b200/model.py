@@ -1,0 +1,103 @@
+"""Onset-window network inference on the GPU (K6, csrc/cnn_infer.cu).
+
+Mirrors ``model.CNN`` of the reference (model.py:52-120) for inference: the constructor takes the same
+arguments and builds the same ``conv_layers`` / ``fc`` parameter containers, so a checkpoint of the
+reference model loads with ``load_state_dict`` unchanged; ``forward`` runs the fused CUDA kernel
+(Conv1d + activation stack -> flatten -> Linear, one warp per window) instead of cuDNN/cuBLAS calls.
+Training (LightningModule hooks, optimisers, plots; model.py:122-165) is out of scope, and so are the
+options the reference leaves off by default (batch_norm, pool, dilation != 1, groups != 1): they raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+_ACT = {nn.SiLU: 0, nn.ReLU: 1, nn.Tanh: 2, nn.Identity: 3}
+
+
+class CNN(nn.Module):
+    def __init__(self, input_size: int, output_size: int, channels: int = 3, layer_sizes: list[int] = [8, 16],
+                 kernel_size: int = 3, dropout_rate: float = 0.5, loss=None, batch_norm=False, pool=False,
+                 padding=1, dilation=1, groups=1, lr=1e-3, activation=nn.SiLU) -> None:
+        super().__init__()
+        if batch_norm or pool or dilation != 1 or groups != 1:
+            raise NotImplementedError("K6 covers the reference defaults: no batch_norm / pool, dilation = groups = 1")
+        if activation not in _ACT:
+            raise NotImplementedError(f"activation {activation} (supported: {[a.__name__ for a in _ACT]})")
+        self.input_size, self.output_size, self.channels = input_size, output_size, channels
+        self.layer_sizes, self.kernel_size, self.padding = list(layer_sizes), kernel_size, padding
+        self.act = _ACT[activation]
+        self.conv_layers = nn.Sequential()  # same names as the reference: conv1, act1, conv2, ...
+        cur, length = channels, input_size
+        for i, size in enumerate(self.layer_sizes):
+            self.conv_layers.add_module(f"conv{i + 1}", nn.Conv1d(cur, size, kernel_size, padding=padding))
+            self.conv_layers.add_module(f"act{i + 1}", activation())
+            length = length + 2 * padding - (kernel_size - 1)
+            cur = size
+        self.dropout = nn.Dropout(dropout_rate)
+        self.fc = nn.Linear(cur * length, output_size)
+        self.flat = cur * length
+        self._packed = None
+        self.eval()
+
+    # ---- parameter packing (include/ofp.h: ofp_cnn_forward) ----
+    def pack(self) -> torch.Tensor:
+        parts = []
+        for i in range(len(self.layer_sizes)):
+            conv = getattr(self.conv_layers, f"conv{i + 1}")
+            w = conv.weight.detach().float().cpu()  # [cout, cin, ks]
+            b = conv.bias.detach().float().cpu() if conv.bias is not None else torch.zeros(w.shape[0])
+            cout = w.shape[0]
+            cp = (cout + 7) // 8 * 8
+            wt = torch.zeros((w.shape[1], w.shape[2], cp))
+            wt[:, :, :cout] = w.permute(1, 2, 0)
+            bp = torch.zeros(cp)
+            bp[:cout] = b
+            parts += [wt.reshape(-1), bp]
+        parts += [self.fc.weight.detach().float().cpu().reshape(-1), self.fc.bias.detach().float().cpu()]
+        packed = torch.cat(parts).contiguous()
+        n = C.c_int64(0)
+        sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
+        check(_lib.lib().ofp_cnn_param_count(C.c_int32(self.channels), C.c_int32(self.input_size),
+                                             C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
+                                             C.c_int32(self.padding), C.c_int32(self.output_size), C.byref(n), None))
+        assert n.value == packed.numel(), (n.value, packed.numel())
+        self._packed = packed.cuda()
+        return self._packed
+
+    def load_state_dict(self, *args, **kw):
+        out = super().load_state_dict(*args, **kw)
+        self._packed = None
+        return out
+
+    @torch.no_grad()
+    def forward(self, x) -> torch.Tensor:
+        """x [B, channels, input_size] float32 (device tensor or numpy) -> [B, output_size] device tensor."""
+        _lib.require_cuda()
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        x = x.cuda().float()
+        if x.dim() != 3 or x.shape[1] != self.channels or x.shape[2] != self.input_size:
+            raise ValueError(f"expected [B, {self.channels}, {self.input_size}], got {tuple(x.shape)}")
+        if x.stride(2) != 1 or x.stride(1) != self.input_size:
+            x = x.contiguous()
+        if self._packed is None:
+            self.pack()
+        out = torch.empty((x.shape[0], self.output_size), dtype=torch.float32, device="cuda")
+        sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
+        check(_lib.lib().ofp_cnn_forward(ptr(x), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)),
+                                         C.c_int32(self.channels), C.c_int32(self.input_size),
+                                         C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
+                                         C.c_int32(self.padding), C.c_int32(self.act), ptr(self._packed),
+                                         C.c_int32(self.output_size), ptr(out), stream_ptr()))
+        return out
+
+    def call_np(self, x: np.ndarray) -> np.ndarray:
+        """numpy in, numpy out (the shape FCNN.call_np has in the reference, calibration.py:463-560)."""
+        return self.forward(x).cpu().numpy()
