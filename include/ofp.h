@@ -209,6 +209,26 @@ int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, const float
                     double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
                     int32_t onset_stride, int32_t n_hits, double *xy_dev, int32_t *status_dev, void *stream);
 
+/* Model bypass of trilaterate (multilateration.py:553-557: res = self.model.call_np((d_a1, d_b1)) * 100).
+ * ofp_locate_hits_lags runs the same legality / seed-cell checks as ofp_locate_hits but, instead of solving,
+ * writes the two lags the reference hands to the model (after its sensor rewrite, Q8) to pair_lags_dev [H, 2]
+ * float32; status as above (never 4), xy_dev is left NaN.  ofp_fcnn_forward evaluates calibration.FCNN
+ * (calibration.py:463-560) in eval mode on rows x_dev [n_rows, widths[0]]: n_layers Linear layers of widths
+ * widths_host[0..n_layers] (<= 32), each hidden one followed by the BatchNorm1d inference affine and the
+ * activation (0 ReLU, 1 tanh, 2 sigmoid, 3 SiLU, 4 identity).  params_dev per layer: W [out][in], b [out],
+ * scale [out], shift [out] (scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale;
+ * 1 and 0 without batch norm).  Rows with status_dev[r] != 0 are skipped (status_dev may be NULL).  Outputs are
+ * multiplied by out_scale and written to out_f32_dev and/or out_f64_dev [n_rows, widths[n_layers]]. */
+int ofp_locate_hits_lags(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                         int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                         const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                         double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
+                         int32_t onset_stride, int32_t n_hits, float *pair_lags_dev, double *xy_dev,
+                         int32_t *status_dev, void *stream);
+int ofp_fcnn_forward(const float *x_dev, int64_t n_rows, int32_t n_layers, const int32_t *widths_host,
+                     int32_t activation, const float *params_dev, const int32_t *status_dev, float out_scale,
+                     float *out_f32_dev, double *out_f64_dev, void *stream);
+
 /* Streaming locate for n_streams concurrent realtime streams: what PlayRec.detect_hits does per block
  * (realtime/audio.py:62-74) with Multilaterate3D.locate's group state machine
  * (multilateration.py:428-534, rec_audio = None) kept per stream in device memory.

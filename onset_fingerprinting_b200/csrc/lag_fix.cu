@@ -21,7 +21,13 @@ namespace ofp {
 
 constexpr int LAG_NONE = INT32_MIN;
 constexpr int FIX_OK = 0, FIX_DEGENERATE = 1, FIX_REF_CRASH = 2, FIX_TOO_LONG = 3, FIX_INCOMPLETE = 4;
-constexpr int K4_THREADS = 128;
+#ifndef OFP_K4_THREADS
+#define OFP_K4_THREADS 192
+#endif
+#ifndef OFP_K4_MINCTA
+#define OFP_K4_MINCTA 3
+#endif
+constexpr int K4_THREADS = OFP_K4_THREADS;
 // Lags per thread.  ODD on purpose: neighbouring lanes then read x at a stride of LPT doubles, and an
 // odd stride spreads the 32 lanes of an LDS.64 over all bank pairs (LPT = 4 gave 8-way conflicts).
 constexpr int LPT = 3;
@@ -439,7 +445,7 @@ __device__ __forceinline__ bool adjust_sums(const double *xd, const double *yd, 
         return true;
 }
 
-__global__ void __launch_bounds__(K4_THREADS) k4_fix(const K4Args a) {
+__global__ void __launch_bounds__(K4_THREADS, OFP_K4_MINCTA) k4_fix(const K4Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = a.C, tid = threadIdx.x, h = blockIdx.x;
     const FixParams fp = a.fp;

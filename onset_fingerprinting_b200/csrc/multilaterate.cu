@@ -285,6 +285,8 @@ struct K5Args {
     int32_t onset_stride;
     double *xy;              // [H, 2], NaN when not located
     int32_t *status;         // [H]
+    float *pair_lags = nullptr;  // [H, 2] or null.  Non-null: no solve; the two lags trilaterate() would hand to
+                                 // Multilaterate3D.model (multilateration.py:553-557) are written instead
 };
 
 __global__ void k5_locate(const K5Args a) {
@@ -334,6 +336,14 @@ __global__ void k5_locate(const K5Args a) {
         else {
             double x[2] = {ci - a.radius, cj - a.radius};
             if (s1 == 1) { s1 = 0; s2 = 1; const long long t = o1; o1 = o2; o2 = t; }  // Q8, multilateration.py:542-544
+            if (a.pair_lags != nullptr) {  // model bypass: the network sees (d_a1, d_b1) as float32
+                a.pair_lags[2 * static_cast<int64_t>(h)] = static_cast<float>(o1 - o0);
+                a.pair_lags[2 * static_cast<int64_t>(h) + 1] = static_cast<float>(o2 - o0);
+                a.xy[2 * static_cast<int64_t>(h)] = out[0];
+                a.xy[2 * static_cast<int64_t>(h) + 1] = out[1];
+                a.status[h] = 0;
+                return;
+            }
             tri_problem q;
             q.xa = a.locs[3 * s1]; q.ya = a.locs[3 * s1 + 1]; q.za = a.locs[3 * s1 + 2];
             q.xb = a.locs[3 * s2]; q.yb = a.locs[3 * s2 + 1]; q.zb = a.locs[3 * s2 + 2];
@@ -581,6 +591,119 @@ extern "C" int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, 
     a.radius = radius_cm; a.samples_per_cm = samples_per_cm; a.sr = sr; a.c_cm = c_cm_s;
     a.sensors = hit_sensors_dev; a.onsets = hit_onsets_dev; a.onset_stride = onset_stride;
     a.xy = xy_dev; a.status = status_dev;
+    k5_locate<<<(n_hits + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model bypass of trilaterate (multilateration.py:553-557): res = model.call_np((d_a1, d_b1)) * 100 with
+// model = calibration.FCNN (calibration.py:463-560) in eval mode: [Linear -> BatchNorm1d (running
+// statistics) -> activation] x n_hidden -> Linear.  One thread per row, activations in registers,
+// parameters in shared memory.  BatchNorm is applied as the per-feature affine (scale, shift) it is
+// at inference; packed per layer: W [out][in], b [out], scale [out], shift [out].
+// ---------------------------------------------------------------------------------------------
+namespace ofp {
+constexpr int FC_MAXW = 32;   // widest layer
+constexpr int FC_MAXL = 8;    // layers incl. the output layer
+struct FcArgs {
+    const float *x;  // [n, in]
+    int64_t n;
+    int32_t n_layers, act;
+    int32_t width[FC_MAXL + 1];  // in, hidden..., out
+    int32_t off[FC_MAXL];        // float offset of layer l's block
+    int32_t n_params;
+    const float *params;
+    const int32_t *status;       // optional: rows with status != 0 are skipped
+    float out_scale;
+    float *out_f32;              // [n, out] or null
+    double *out_f64;             // [n, out] or null (rows skipped keep their content)
+};
+
+__global__ void __launch_bounds__(128) k5_fcnn(const FcArgs a) {
+    extern __shared__ float fc_prm[];
+    for (int i = threadIdx.x; i < a.n_params; i += blockDim.x) fc_prm[i] = a.params[i];
+    __syncthreads();
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    if (a.status != nullptr && a.status[r] != 0) return;
+    float h[FC_MAXW], g[FC_MAXW];
+    const int win = a.width[0];
+    for (int i = 0; i < FC_MAXW; ++i) h[i] = i < win ? a.x[r * win + i] : 0.f;
+    for (int l = 0; l < a.n_layers; ++l) {
+        const int ni = a.width[l], no = a.width[l + 1];
+        const float *W = fc_prm + a.off[l], *b = W + no * ni, *sc = b + no, *sh = sc + no;
+        const bool last = l == a.n_layers - 1;
+#pragma unroll
+        for (int o = 0; o < FC_MAXW; ++o) {
+            float v = 0.f;
+            if (o < no) {
+#pragma unroll
+                for (int i = 0; i < FC_MAXW; ++i)
+                    if (i < ni) v = fmaf(W[o * ni + i], h[i], v);
+                v += b[o];
+                if (!last) {
+                    v = fmaf(v, sc[o], sh[o]);
+                    if (a.act == 0) v = fmaxf(v, 0.f);
+                    else if (a.act == 1) v = tanhf(v);
+                    else if (a.act == 2) v = 1.0f / (1.0f + expf(-v));
+                    else if (a.act == 3) v = v / (1.0f + expf(-v));
+                }
+            }
+            g[o] = v;
+        }
+#pragma unroll
+        for (int o = 0; o < FC_MAXW; ++o) h[o] = g[o];
+    }
+    const int nout = a.width[a.n_layers];
+#pragma unroll
+    for (int o = 0; o < FC_MAXW; ++o) {
+        if (o < nout) {
+            if (a.out_f32) a.out_f32[r * nout + o] = h[o] * a.out_scale;
+            if (a.out_f64) a.out_f64[r * nout + o] = static_cast<double>(h[o] * a.out_scale);
+        }
+    }
+}
+}  // namespace ofp
+
+extern "C" int ofp_fcnn_forward(const float *x_dev, int64_t n_rows, int32_t n_layers, const int32_t *widths_host,
+                                int32_t activation, const float *params_dev, const int32_t *status_dev,
+                                float out_scale, float *out_f32_dev, double *out_f64_dev, void *stream) {
+    OFP_REQUIRE(x_dev && widths_host && params_dev && (out_f32_dev || out_f64_dev), "null argument");
+    OFP_REQUIRE(n_layers >= 1 && n_layers <= FC_MAXL, "1..%d layers supported", FC_MAXL);
+    OFP_REQUIRE(activation >= 0 && activation <= 4, "activation: 0 ReLU, 1 tanh, 2 sigmoid, 3 SiLU, 4 identity");
+    if (n_rows == 0) return OFP_OK;
+    FcArgs a{};
+    a.x = x_dev; a.n = n_rows; a.n_layers = n_layers; a.act = activation; a.params = params_dev;
+    a.status = status_dev; a.out_scale = out_scale; a.out_f32 = out_f32_dev; a.out_f64 = out_f64_dev;
+    int off = 0;
+    for (int l = 0; l <= n_layers; ++l) {
+        OFP_REQUIRE(widths_host[l] >= 1 && widths_host[l] <= FC_MAXW, "layer widths 1..%d supported", FC_MAXW);
+        a.width[l] = widths_host[l];
+        if (l < n_layers) { a.off[l] = off; off += widths_host[l + 1] * widths_host[l] + 3 * widths_host[l + 1]; }
+    }
+    a.n_params = off;
+    k5_fcnn<<<static_cast<unsigned>((n_rows + 127) / 128), 128, off * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+extern "C" int ofp_locate_hits_lags(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                                    int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                                    const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                                    double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
+                                    int32_t onset_stride, int32_t n_hits, float *pair_lags_dev, double *xy_dev,
+                                    int32_t *status_dev, void *stream) {
+    OFP_REQUIRE(sensor_xyz_dev && lag_maps_dev && max_lags_dev && min_lags_dev && max_max_dev && hit_onsets_dev &&
+                    xy_dev && status_dev && pair_lags_dev, "null argument");
+    OFP_REQUIRE(n_sensors >= 3 && onset_stride >= 3, "need at least three sensors / onsets per hit");
+    if (n_hits == 0) return OFP_OK;
+    K5Args a;
+    a.locs = sensor_xyz_dev; a.maps = lag_maps_dev; a.max_lags = max_lags_dev; a.min_lags = min_lags_dev;
+    a.max_max = max_max_dev; a.S = n_sensors; a.Hm = map_size; a.H = n_hits; a.n_per_hit = 3;
+    a.radius = radius_cm; a.samples_per_cm = samples_per_cm; a.sr = sr; a.c_cm = c_cm_s;
+    a.sensors = hit_sensors_dev; a.onsets = hit_onsets_dev; a.onset_stride = onset_stride;
+    a.xy = xy_dev; a.status = status_dev; a.pair_lags = pair_lags_dev;
     k5_locate<<<(n_hits + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
     OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;

@@ -235,12 +235,11 @@ class Multilaterate3D:
 
     def __init__(self, sensor_locations, drum_diameter: float = DIAMETER, medium: str = "drumhead", sr: int = 44100,
                  c: Optional[float] = None, model=None):
-        if model is not None:
-            raise NotImplementedError("FCNN bypass (multilateration.py:555-557) is outside the hot-path scope")
         self.torch = _lib.require_cuda()
         torch = self.torch
         self.c = speed_of_sound(100, medium=medium) if c is None else c * 100
-        self.model = None
+        # multilateration.py:350, 553-557: an optional network that maps the two lags straight to (x, y) in m
+        self.model = model
         self.radius = drum_diameter / 2
         self.sensor_locs = [spherical_to_cartesian(x[0] * self.radius, x[1], x[2]) for x in sensor_locations]
         self.medium, self.sr = medium, sr
@@ -293,6 +292,17 @@ class Multilaterate3D:
         H = onsets.shape[0]
         xy = torch.empty((H, 2), dtype=torch.float64, device="cuda")
         st = torch.empty((H,), dtype=torch.int32, device="cuda")
+        if self.model is not None:
+            # same legality / seed checks, then res = model((d_a1, d_b1)) * 100 (multilateration.py:553-557)
+            lags = torch.zeros((H, 2), dtype=torch.float32, device="cuda")
+            check(_lib.lib().ofp_locate_hits_lags(ptr(self._locs), C.c_int32(self._S), ptr(self._maps),
+                                                  C.c_int32(self._M), ptr(self._mx), ptr(self._mn), ptr(self._mm),
+                                                  C.c_double(self.radius), C.c_double(self.samples_per_cm),
+                                                  C.c_double(self.sr), C.c_double(self.c), ptr(sensors), ptr(onsets),
+                                                  C.c_int32(onsets.stride(0)), C.c_int32(H), ptr(lags), ptr(xy),
+                                                  ptr(st), stream_ptr()))
+            self.model.forward_device(lags, status=st, out_scale=100.0, out_f64=xy)
+            return xy, st
         check(_lib.lib().ofp_locate_hits(ptr(self._locs), C.c_int32(self._S), ptr(self._maps), C.c_int32(self._M),
                                          ptr(self._mx), ptr(self._mn), ptr(self._mm), C.c_double(self.radius),
                                          C.c_double(self.samples_per_cm), C.c_double(self.sr), C.c_double(self.c),
@@ -328,6 +338,8 @@ class Multilaterate3D:
             sensors[1:] = [0, 1]
             onsets[1:] = onsets[2:0:-1]
         d_a1, d_b1 = onsets[1] - onsets[0], onsets[2] - onsets[0]
+        if self.model is not None:
+            return self.model.call_np((d_a1, d_b1)) * 100
         return solve_trilateration_3d(self.sensor_locs[sensors[1]], self.sensor_locs[sensors[2]],
                                       self.sensor_locs[sensors[0]], d_a1 / self.sr * self.c, d_b1 / self.sr * self.c,
                                       initial_guess)

@@ -67,3 +67,59 @@ def test_unsupported_options_raise():
         model.CNN(256, 2, batch_norm=True)
     with pytest.raises(NotImplementedError):
         model.CNN(256, 2, pool=True)
+
+
+def _fcnn_reference(m, x):
+    with torch.no_grad():
+        return m.network(x)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(hidden_layers=[16, 32, 8, 4], activation=torch.nn.Tanh),
+                                dict(batch_norm=False, activation=torch.nn.SiLU), dict(bias=False, eye_init=True)])
+def test_fcnn_forward_matches_torch(kw):
+    """calibration.FCNN (calibration.py:463-560) in eval mode; BatchNorm with non-trivial running statistics.
+    float32 on both sides, BatchNorm folded to scale/shift here: 1e-5 relative to the output scale."""
+    from onset_fingerprinting_b200 import calibration
+
+    torch.manual_seed(3)
+    m = calibration.FCNN(2, 2, **kw)
+    for mod in m.network:
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.5); mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.normal_(1, 0.2); mod.bias.data.normal_(0, 0.2)
+    m = m.cuda().eval()
+    x = (torch.randn(5000, 2, device="cuda") * 60).round()
+    got, want = m(x), _fcnn_reference(m, x)
+    assert float((got - want).abs().max()) <= 1e-5 * max(1.0, float(want.abs().max()))
+    one = m.call_np((12.0, -7.0))
+    assert np.allclose(one, _fcnn_reference(m, torch.tensor([[12.0, -7.0]], device="cuda")).cpu().numpy()[0], rtol=1e-5, atol=1e-6)
+
+
+def test_multilaterate3d_model_bypass():
+    """Multilaterate3D(model=FCNN): trilaterate returns model((d_a1, d_b1)) * 100 (multilateration.py:553-557)
+    after the same legality checks; the batched path must agree with the per-hit one and with the solver
+    path on which hits are located at all (status 4 = solver failure cannot occur with a model)."""
+    from onset_fingerprinting_b200 import calibration
+    from onset_fingerprinting_b200 import multilateration as ml
+
+    torch.manual_seed(4)
+    net = calibration.FCNN(2, 2).cuda()
+    sensors = [(0.9, 140, 75), (0.9, 10, 55), (0.5, 100, 15)]
+    a = ml.Multilaterate3D(sensors, sr=96000, medium="air")
+    b = ml.Multilaterate3D(sensors, sr=96000, medium="air", model=net)
+    rng = np.random.default_rng(0)
+    base = rng.integers(1000, 100000, size=(2000, 1))
+    on = np.concatenate([base + rng.integers(0, 60, size=(2000, 2)), base], axis=1).astype(np.int32)  # close mic first
+    xy_a, st_a = a.locate_batch(on)
+    xy_b, st_b = b.locate_batch(on)
+    st_a, st_b = st_a.cpu().numpy(), st_b.cpu().numpy()
+    assert ((st_a == 0) | (st_a == 4)).sum() == (st_b == 0).sum()
+    assert np.array_equal(st_b[st_a != 4], st_a[st_a != 4])
+    ok = np.nonzero(st_b == 0)[0]
+    assert len(ok) > 100
+    xy_b = xy_b.cpu().numpy()
+    assert np.isnan(xy_b[st_b != 0]).all()
+    for h in ok[:50]:
+        order = np.argsort(on[h], kind="stable")
+        got = b.trilaterate(([int(s) for s in order], [int(on[h][s]) for s in order]), initial_guess=np.zeros(2))
+        assert np.allclose(got, xy_b[h], rtol=1e-6, atol=1e-6)
