@@ -87,6 +87,15 @@ int ofp_detect_offline(ofp_detector *det, const float *x_dev, int64_t n_samples,
                        int64_t warm_n, float *rel_dev, int64_t rel_stride, int32_t *on_channel_dev,
                        int32_t *on_sample_dev, int32_t *on_count_dev, int32_t cap, void *stream);
 
+/* Continue ofp_detect_offline on the NEXT n_samples (whole blocks) of every recording from the state the
+ * previous call left in `det` -- the block loop of detect_onsets_amplitude (detection.py:74-84) resumed at
+ * block `first_block`.  x_dev / rel_dev hold only this segment ([R, n_samples, C]); onset sample indices are
+ * global (first_block * B + ...), and detections are appended after the on_count_dev[r] entries already in
+ * on_channel_dev / on_sample_dev (on_count_dev is read and updated). */
+int ofp_detect_continue(ofp_detector *det, const float *x_dev, int64_t n_samples, int64_t rec_stride,
+                        int64_t first_block, float *rel_dev, int64_t rel_stride, int32_t *on_channel_dev,
+                        int32_t *on_sample_dev, int32_t *on_count_dev, int32_t cap, void *stream);
+
 /* AmplitudeOnsetDetector.__call__ (detection.py:727-798) for n_streams concurrent streams:
  *   x_dev [S, B, C] with stream s starting at x_dev + s*stream_stride (elements; B*C when dense);
  *   rel_dev NULL or [S, B, C]; ch_dev/delta_dev [S, C] int32; count_dev [S]. */
@@ -97,9 +106,14 @@ int ofp_detect_block(ofp_detector *det, const float *x_dev, int64_t stream_strid
 int ofp_detect_warmup(ofp_detector *det, const float *x_dev, int64_t n_samples, int64_t rec_stride,
                       void *stream);
 
-/* Host-buffer convenience (the reference-facing call: numpy in, numpy out).  Copies
- * x_host -> device, runs ofp_detect_offline on a fresh detector, copies results back and
- * synchronises.  rel_host may be NULL. */
+/* Host-buffer convenience (the reference-facing call: numpy in, numpy out).  Streams x_host to the device
+ * in time segments of all recordings (copy of segment s+1 overlapping the kernel of segment s, which
+ * continues from the detector state of segment s-1), copies results back and synchronises.  Same results as
+ * ofp_detect_offline on the whole batch.  rel_host may be NULL; pinned host memory makes the copies
+ * asynchronous.  The two staging segments, streams and events are kept for the next call (allocating and
+ * freeing multi-GB buffers costs more than the pipeline); ofp_host_release() frees them.  Calls are
+ * serialised by a mutex. */
+int ofp_host_release(void);
 int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, int64_t n_rec,
                             int64_t n_samples, int64_t warm_n, float *rel_host, int32_t *on_channel_host,
                             int32_t *on_sample_host, int32_t *on_count_host, int32_t cap);

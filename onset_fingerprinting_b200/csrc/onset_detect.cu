@@ -21,6 +21,9 @@
 //   * arithmetic follows SURVEY Appendix A op for op: explicit __f*_rn intrinsics (never contracted
 //     to FMA), one double add inside the follower, log10/10**x evaluated in double and rounded once.
 #include "ofp_common.cuh"
+
+#include <chrono>
+#include <mutex>
 #include "k1_math.cuh"
 
 #include <algorithm>
@@ -69,6 +72,8 @@ struct K1Args {
     int32_t cap;
     int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
     int32_t floor_skip;  // OFP_K1_FLOOR_SKIP=0 disables the below-floor short-cut (A/B runs)
+    int32_t cnt_in;      // continue: the per-recording onset counts in on_cnt are the starting fill levels
+    int64_t blk0;        // continue: global index of the first block of this call (x / rel start there)
 };
 
 // Per-kernel constants held in registers for the whole launch (a one-warp CTA has registers to
@@ -516,7 +521,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
         const int n1 = min(B, NR - r0) * C;  // elements before the ring wraps
         for (int gi = 0; gi < G; ++gi) {
             if (rec0 + gi >= a.R) break;
-            float *dst = a.rel + (rec0 + gi) * a.rel_stride + blk * nBC;
+            float *dst = a.rel + (rec0 + gi) * a.rel_stride + (blk - a.blk0) * nBC;
             const float *src = relbuf + gi * a.stride_rel;
             if (a.rel_vec_ok) {
                 // n1 and r0 * C are multiples of 4 whenever the ring is used (chunks of 8 rows)
@@ -585,8 +590,8 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     }
     const uint32_t box_bytes = static_cast<uint32_t>(G) * TC * 4u;
     uint32_t it = 0;      // tiles consumed so far (ring position / parity)
-    int32_t cnt = 0;      // onsets emitted for this lane's recording
-    int64_t blk = 0;      // main-phase block index
+    int32_t cnt = (a.cnt_in && active) ? a.on_cnt[rec] : 0;  // onsets emitted for this lane's recording
+    int64_t blk = a.blk0;  // main-phase block index (global; a.blk0 != 0 when a recording is fed in segments)
 
     float *rcol = relbuf + g * a.stride_rel + c;  // this lane's column of the block buffer
     const uint32_t rcol_s = smem_u32(rcol);
@@ -807,7 +812,7 @@ static int upload_tables() {
 
 static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64_t rec_stride, int64_t warm_n,
                      int64_t n_main, float *rel, int64_t rel_stride, int32_t *on_ch, int32_t *on_idx,
-                     int32_t *on_cnt, int32_t cap, cudaStream_t stream) {
+                     int32_t *on_cnt, int32_t cap, cudaStream_t stream, int64_t blk0 = 0, bool cnt_in = false) {
     const ofp_detector_params &p = det->p;
     const int C = p.n_channels, B = p.block_size;
     K1Args a;
@@ -816,6 +821,8 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.ia_min = static_cast<float>(1.0 - static_cast<double>(p.alpha_min));
     a.ia_max = static_cast<float>(1.0 - static_cast<double>(p.alpha_max));
     a.floor_skip = env_int("OFP_K1_FLOOR_SKIP", 1);
+    a.blk0 = blk0; a.cnt_in = cnt_in ? 1 : 0;
+    const bool plain = blk0 == 0 && !cnt_in;  // the opt-in experimental kernels only know whole recordings
     a.st = state_of(det);
     a.x = x; a.n_samples = n_samples; a.rec_stride = rec_stride;
     a.warm_n = std::min(warm_n, n_samples);
@@ -835,7 +842,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     // its envelope buffer is a ring of B + PU rows
     const bool tma_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (a.R == 1 || rec_stride % 4 == 0) &&
                         (n_samples * C < (1ll << 31)) && !env_int("OFP_K1_NO_TMA", 0);
-    const bool pipe = tma_ok && B % PU == 0 && a.T % PU == 0 && env_int("OFP_K1_PIPE", 0) && !env_int("OFP_K1_WS", 0);
+    const bool pipe = plain && tma_ok && B % PU == 0 && a.T % PU == 0 && env_int("OFP_K1_PIPE", 0) && !env_int("OFP_K1_WS", 0);
     const int NR = pipe ? B + PU : B;
     const int want = ((C + 3) / 4 * 4) % 32;
     const int bc4 = (NR * C + 3) / 4 * 4;
@@ -857,7 +864,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     { int rc = upload_tables(); if (rc != OFP_OK) return rc; }
     const int grid = (a.R + a.G - 1) / a.G;
     // ---- warp-specialised kernel (default): needs TMA-able input and a block size divisible by 4 ----
-    if (tma_ok && B % 4 == 0 && env_int("OFP_K1_WS", 0)) {
+    if (plain && tma_ok && B % 4 == 0 && env_int("OFP_K1_WS", 0)) {
         WsCfg w;
         w.CH = B % 16 == 0 ? 16 : (B % 8 == 0 ? 8 : 4);
         w.NDB = std::max(2, std::min(WS_MAX_NDB, env_int("OFP_K1_NDB", 3)));
@@ -909,11 +916,35 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     return OFP_OK;
 }
 
+struct HostCache {
+    float *x[2] = {nullptr, nullptr}, *rel[2] = {nullptr, nullptr};
+    size_t x_cap[2] = {0, 0}, rel_cap[2] = {0, 0};
+    int32_t *och = nullptr, *oix = nullptr, *ocn = nullptr;
+    size_t och_cap = 0, oix_cap = 0, ocn_cap = 0;
+    cudaStream_t copy = nullptr, comp = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+};
+static HostCache g_host_cache;
+
 }  // namespace ofp
 
 using namespace ofp;
 
 extern "C" {
+
+int ofp_host_release(void) {
+    HostCache &c = g_host_cache;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c.x[i]); cudaFree(c.rel[i]);
+        if (c.copied[i]) cudaEventDestroy(c.copied[i]);
+        if (c.done[i]) cudaEventDestroy(c.done[i]);
+    }
+    cudaFree(c.och); cudaFree(c.oix); cudaFree(c.ocn);
+    if (c.copy) cudaStreamDestroy(c.copy);
+    if (c.comp) cudaStreamDestroy(c.comp);
+    c = HostCache();
+    return OFP_OK;
+}
 
 int ofp_detector_create(ofp_detector **out, int64_t n_streams, const ofp_detector_params *p) {
     OFP_REQUIRE(out && p, "null argument");
@@ -979,6 +1010,19 @@ int ofp_detect_offline(ofp_detector *det, const float *x_dev, int64_t n_samples,
                      on_channel_dev, on_sample_dev, on_count_dev, cap, static_cast<cudaStream_t>(stream));
 }
 
+int ofp_detect_continue(ofp_detector *det, const float *x_dev, int64_t n_samples, int64_t rec_stride,
+                        int64_t first_block, float *rel_dev, int64_t rel_stride, int32_t *on_channel_dev,
+                        int32_t *on_sample_dev, int32_t *on_count_dev, int32_t cap, void *stream) {
+    OFP_REQUIRE(det && x_dev && on_channel_dev && on_sample_dev && on_count_dev, "null argument");
+    OFP_REQUIRE(n_samples >= 0 && first_block >= 0 && cap >= 0, "negative size");
+    OFP_REQUIRE(n_samples % det->p.block_size == 0, "a continuation must be whole blocks");
+    OFP_REQUIRE((first_block + n_samples / det->p.block_size) * det->p.block_size < (1ll << 31),
+                "recording too long for int32 sample indices");
+    if (n_samples == 0) return OFP_OK;
+    return launch_k1(det, x_dev, n_samples, rec_stride, 0, n_samples, rel_dev, rel_stride, on_channel_dev,
+                     on_sample_dev, on_count_dev, cap, static_cast<cudaStream_t>(stream), first_block, true);
+}
+
 int ofp_detect_block(ofp_detector *det, const float *x_dev, int64_t stream_stride, float *rel_dev, int32_t *ch_dev,
                      int32_t *delta_dev, int32_t *count_dev, void *stream) {
     OFP_REQUIRE(det && x_dev && ch_dev && delta_dev && count_dev, "null argument");
@@ -999,30 +1043,27 @@ int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, i
                             int64_t warm_n, float *rel_host, int32_t *on_channel_host, int32_t *on_sample_host,
                             int32_t *on_count_host, int32_t cap) {
     OFP_REQUIRE(p && x_host && on_channel_host && on_sample_host && on_count_host, "null argument");
-    OFP_REQUIRE(n_rec > 0 && n_samples >= 0, "bad size");
-    // Recordings are processed in chunks on two streams so that the host->device copy of chunk i+1
-    // overlaps the kernel and the result copies of chunk i (pinned host memory makes the copies async).
+    OFP_REQUIRE(n_rec > 0 && n_samples >= 0 && warm_n >= 0, "bad size");
+    // The batch is fed in TIME segments of all recordings at once (2-D copies out of the [R, N, C] host
+    // array), double buffered: the copy of segment s+1 overlaps the kernel of segment s, which continues
+    // from the detector state segment s-1 left behind (ofp_detect_continue).  Every launch therefore keeps
+    // all recordings' lanes busy and the wall time is the host->device transfer plus one segment's kernel.
+    // Batches too large for one detector go through the same pipeline in chunks of recordings.
     const int64_t C = p->n_channels, B = p->block_size;
-    int64_t chunk = env_int("OFP_HOST_CHUNK", 1024);
-    if (n_rec <= chunk + chunk / 2) chunk = n_rec;
-    const int64_t nchunks = (n_rec + chunk - 1) / chunk;
-    const int ns = nchunks > 1 ? 2 : 1;
-    const int64_t in_elems = chunk * n_samples * C;
-    const int64_t rel_row = (n_samples / B) * B * C;
-    struct Slot {
-        ofp_detector *det = nullptr;
-        float *x = nullptr, *rel = nullptr;
-        int32_t *och = nullptr, *oix = nullptr, *ocn = nullptr;
-        cudaStream_t st = nullptr;
-    } slot[2];
-    int rc = OFP_OK;
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; ++i) {
-            cudaFree(slot[i].x); cudaFree(slot[i].rel); cudaFree(slot[i].och); cudaFree(slot[i].oix); cudaFree(slot[i].ocn);
-            if (slot[i].st) cudaStreamDestroy(slot[i].st);
-            ofp_detector_destroy(slot[i].det);
-        }
-    };
+    const int64_t n_main = (n_samples / B) * B;
+    const int64_t rel_row = n_main * C;
+    int64_t seg = std::max<int64_t>(env_int("OFP_HOST_SEGMENT", 49152), std::min(warm_n, n_samples));
+    seg = (seg + B - 1) / B * B;
+    if (seg % 4) seg *= 4;  // 16-byte rows for the TMA path
+    const int64_t chunk = std::min<int64_t>(n_rec, env_int("OFP_HOST_CHUNK", 8192));
+    const int64_t seg_alloc = std::min(seg + B, std::max<int64_t>(n_samples, 1));  // + an absorbed partial block
+    // Staging buffers, streams and events are kept between calls (cudaMalloc / cudaFree of multi-GB buffers
+    // cost more than the whole pipeline); ofp_host_release() frees them.  One call at a time.
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    HostCache &cx = g_host_cache;
+    ofp_detector *det = nullptr;
+    auto cleanup = [&]() { ofp_detector_destroy(det); };
 #define HOST_CHECK(expr)                                                                  \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \
@@ -1032,38 +1073,79 @@ int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, i
             return OFP_ECUDA;                                                             \
         }                                                                                 \
     } while (0)
-    for (int i = 0; i < ns; ++i) {
-        rc = ofp_detector_create(&slot[i].det, chunk, p);
-        if (rc != OFP_OK) { cleanup(); return rc; }
-        HOST_CHECK(cudaStreamCreateWithFlags(&slot[i].st, cudaStreamNonBlocking));
-        HOST_CHECK(cudaMalloc(&slot[i].x, sizeof(float) * std::max<int64_t>(in_elems, 4)));
-        if (rel_host) HOST_CHECK(cudaMalloc(&slot[i].rel, sizeof(float) * std::max<int64_t>(chunk * rel_row, 4)));
-        HOST_CHECK(cudaMalloc(&slot[i].och, sizeof(int32_t) * std::max<int64_t>(chunk * cap, 1)));
-        HOST_CHECK(cudaMalloc(&slot[i].oix, sizeof(int32_t) * std::max<int64_t>(chunk * cap, 1)));
-        HOST_CHECK(cudaMalloc(&slot[i].ocn, sizeof(int32_t) * chunk));
+    const bool trace = env_int("OFP_HOST_TRACE", 0) != 0;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
+    int rc = ofp_detector_create(&det, chunk, p);
+    if (rc != OFP_OK) { cleanup(); return rc; }
+    if (!cx.copy) HOST_CHECK(cudaStreamCreateWithFlags(&cx.copy, cudaStreamNonBlocking));
+    if (!cx.comp) HOST_CHECK(cudaStreamCreateWithFlags(&cx.comp, cudaStreamNonBlocking));
+    auto ensure = [&](void **ptr, size_t &cap, size_t need) -> cudaError_t {
+        if (need <= cap) return cudaSuccess;
+        cudaFree(*ptr); *ptr = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(ptr, need);
+        if (e == cudaSuccess) cap = need;
+        return e;
+    };
+    const size_t seg_bytes = sizeof(float) * static_cast<size_t>(std::max<int64_t>(chunk * ((seg_alloc + B) * C + 4), 4));
+    for (int i = 0; i < 2; ++i) {
+        HOST_CHECK(ensure(reinterpret_cast<void **>(&cx.x[i]), cx.x_cap[i], seg_bytes));
+        if (rel_host) HOST_CHECK(ensure(reinterpret_cast<void **>(&cx.rel[i]), cx.rel_cap[i], seg_bytes));
+        if (!cx.copied[i]) HOST_CHECK(cudaEventCreateWithFlags(&cx.copied[i], cudaEventDisableTiming));
+        if (!cx.done[i]) HOST_CHECK(cudaEventCreateWithFlags(&cx.done[i], cudaEventDisableTiming));
     }
-    HOST_CHECK(cudaDeviceSynchronize());  // detector resets ran on the default stream
-    for (int64_t ci = 0; ci < nchunks; ++ci) {
-        Slot &sl = slot[ci % ns];
-        const int64_t r0 = ci * chunk, n = std::min(chunk, n_rec - r0);
-        HOST_CHECK(cudaMemcpyAsync(sl.x, x_host + r0 * n_samples * C, sizeof(float) * n * n_samples * C,
-                                   cudaMemcpyHostToDevice, sl.st));
-        sl.det->n_streams = n;  // the state arrays are sized for `chunk` recordings
-        rc = ofp_detector_reset(sl.det, sl.st);
-        if (rc == OFP_OK)
-            rc = ofp_detect_offline(sl.det, sl.x, n_samples, n_samples * C, warm_n, sl.rel, rel_row, sl.och, sl.oix,
-                                    sl.ocn, cap, sl.st);
+    const size_t on_bytes = sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(chunk * cap, 1));
+    HOST_CHECK(ensure(reinterpret_cast<void **>(&cx.och), cx.och_cap, on_bytes));
+    HOST_CHECK(ensure(reinterpret_cast<void **>(&cx.oix), cx.oix_cap, on_bytes));
+    HOST_CHECK(ensure(reinterpret_cast<void **>(&cx.ocn), cx.ocn_cap, sizeof(int32_t) * static_cast<size_t>(chunk)));
+    HOST_CHECK(cudaDeviceSynchronize());  // the detector's first reset ran on the default stream
+    const size_t host_pitch = sizeof(float) * n_samples * C;
+    const double t_setup = now();
+    int64_t use = 0;  // buffer uses so far (parity = slot)
+    for (int64_t r0 = 0; r0 < n_rec; r0 += chunk) {
+        const int64_t n = std::min(chunk, n_rec - r0);
+        det->n_streams = n;  // the state arrays are sized for `chunk` recordings
+        rc = ofp_detector_reset(det, cx.comp);
         if (rc != OFP_OK) { cleanup(); return rc; }
-        if (rel_host)
-            HOST_CHECK(cudaMemcpyAsync(rel_host + r0 * rel_row, sl.rel, sizeof(float) * n * rel_row,
-                                       cudaMemcpyDeviceToHost, sl.st));
-        HOST_CHECK(cudaMemcpyAsync(on_channel_host + r0 * cap, sl.och, sizeof(int32_t) * n * cap, cudaMemcpyDeviceToHost, sl.st));
-        HOST_CHECK(cudaMemcpyAsync(on_sample_host + r0 * cap, sl.oix, sizeof(int32_t) * n * cap, cudaMemcpyDeviceToHost, sl.st));
-        HOST_CHECK(cudaMemcpyAsync(on_count_host + r0, sl.ocn, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, sl.st));
+        if (n_samples == 0) HOST_CHECK(cudaMemsetAsync(cx.ocn, 0, sizeof(int32_t) * n, cx.comp));
+        for (int64_t t0 = 0; t0 < n_samples; ++use) {
+            const int slot = static_cast<int>(use & 1);
+            // the last segment carries the trailing partial block (only the warm-up's high-pass reads it)
+            int64_t len = std::min(seg, n_samples - t0);
+            if (t0 + len < n_samples && n_samples - (t0 + len) < B) len = n_samples - t0;
+            if (use >= 2) HOST_CHECK(cudaStreamWaitEvent(cx.copy, cx.done[slot], 0));
+            const int64_t pitch = (len * C + 3) / 4 * 4;  // device row stride in floats (16-byte rows: TMA path)
+            HOST_CHECK(cudaMemcpy2DAsync(cx.x[slot], sizeof(float) * pitch, x_host + r0 * n_samples * C + t0 * C,
+                                         host_pitch, sizeof(float) * len * C, n, cudaMemcpyHostToDevice, cx.copy));
+            HOST_CHECK(cudaEventRecord(cx.copied[slot], cx.copy));
+            HOST_CHECK(cudaStreamWaitEvent(cx.comp, cx.copied[slot], 0));
+            const int64_t blocks = len / B;
+            if (t0 == 0)
+                rc = ofp_detect_offline(det, cx.x[slot], len, pitch, warm_n, cx.rel[slot], blocks * B * C, cx.och,
+                                        cx.oix, cx.ocn, cap, cx.comp);
+            else
+                rc = ofp_detect_continue(det, cx.x[slot], blocks * B, pitch, t0 / B, cx.rel[slot], blocks * B * C,
+                                         cx.och, cx.oix, cx.ocn, cap, cx.comp);
+            if (rc != OFP_OK) { cleanup(); return rc; }
+            if (rel_host && blocks > 0)
+                HOST_CHECK(cudaMemcpy2DAsync(rel_host + r0 * rel_row + t0 * C, sizeof(float) * rel_row, cx.rel[slot],
+                                             sizeof(float) * blocks * B * C, sizeof(float) * blocks * B * C, n,
+                                             cudaMemcpyDeviceToHost, cx.comp));
+            HOST_CHECK(cudaEventRecord(cx.done[slot], cx.comp));
+            t0 += len;
+        }
+        HOST_CHECK(cudaMemcpyAsync(on_channel_host + r0 * cap, cx.och, sizeof(int32_t) * n * cap, cudaMemcpyDeviceToHost, cx.comp));
+        HOST_CHECK(cudaMemcpyAsync(on_sample_host + r0 * cap, cx.oix, sizeof(int32_t) * n * cap, cudaMemcpyDeviceToHost, cx.comp));
+        HOST_CHECK(cudaMemcpyAsync(on_count_host + r0, cx.ocn, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, cx.comp));
+        HOST_CHECK(cudaStreamSynchronize(cx.comp));  // och / oix / ocn are reused by the next chunk
     }
-    for (int i = 0; i < ns; ++i) HOST_CHECK(cudaStreamSynchronize(slot[i].st));
+    HOST_CHECK(cudaStreamSynchronize(cx.copy));
 #undef HOST_CHECK
+    const double t_done = now();
     cleanup();
+    if (trace)
+        fprintf(stderr, "[ofp_detect_offline_host] setup %.1f ms, pipeline %.1f ms, cleanup %.1f ms (segment %lld samples)\n",
+                t_setup - t_start, t_done - t_setup, now() - t_done, static_cast<long long>(seg));
     return OFP_OK;
 }
 

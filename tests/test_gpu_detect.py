@@ -164,6 +164,39 @@ def test_host_buffer_entry_point(det, orc):
         assert rel_err(rel[r], rel_o) <= 1e-5
 
 
+def test_host_entry_time_segments_equal_one_shot(det, monkeypatch):
+    """ofp_detect_offline_host feeds the batch in time segments (ofp_detect_continue); whatever the segment
+    length, onsets and envelope must be bit-identical to one ofp_detect_offline launch over the whole batch.
+    Recording length deliberately not a multiple of the block size."""
+    import ctypes as C
+
+    from onset_fingerprinting_b200 import _lib
+
+    xs, _ = synth.drum_batch(5, seconds=1.3, seed=41)
+    xs = np.ascontiguousarray(xs[:, : xs.shape[1] - 51])
+    R, N, Cn = xs.shape
+    assert N % 128 != 0
+    d = det.BatchedOnsetDetector(R, 3, 128, sr=96000)
+    ch0, ix0, cnt0, rel0 = d.detect_offline(torch.from_numpy(xs).cuda(), warm_n=48000)
+    ch0, ix0, cnt0, rel0 = ch0.cpu().numpy(), ix0.cpu().numpy(), cnt0.cpu().numpy(), rel0.cpu().numpy()
+    p = det.make_params(3, 128, sr=96000)
+    cap = ch0.shape[1]
+    for seg, chunk in ((48000, 8192), (50048, 8192), (1 << 20, 8192), (48000, 2)):
+        monkeypatch.setenv("OFP_HOST_SEGMENT", str(seg))
+        monkeypatch.setenv("OFP_HOST_CHUNK", str(chunk))
+        rel = np.full((R, (N // 128) * 128, Cn), np.nan, np.float32)
+        ch = np.empty((R, cap), np.int32); ix = np.empty((R, cap), np.int32); cnt = np.empty(R, np.int32)
+        _lib.check(_lib.lib().ofp_detect_offline_host(
+            C.byref(p), xs.ctypes.data_as(C.c_void_p), C.c_int64(R), C.c_int64(N), C.c_int64(48000),
+            rel.ctypes.data_as(C.c_void_p), ch.ctypes.data_as(C.c_void_p), ix.ctypes.data_as(C.c_void_p),
+            cnt.ctypes.data_as(C.c_void_p), C.c_int32(cap)))
+        assert np.array_equal(cnt, cnt0), (seg, chunk)
+        for r in range(R):
+            assert np.array_equal(ch[r, :cnt[r]], ch0[r, :cnt[r]]) and np.array_equal(ix[r, :cnt[r]], ix0[r, :cnt[r]])
+        assert np.array_equal(rel, rel0), (seg, chunk)
+    assert int(cnt0.sum()) >= 5 * 6  # the batch does contain hits
+
+
 def test_backtrack_offline_and_streaming(det, golden_dir):
     g = np.load(golden_dir / "backtrack.npz")
     x, _ = synth.drum_recording(seconds=2.0, seed=8)
