@@ -657,8 +657,8 @@ def run_cnn(args):
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes / (ms / 1e3) / 1e9 / peak, "traffic": None, "kernel": "k6_cnn",
                          "kernel_ms": ms, "peak_source": src,
-                         "note": f"FP32-FMA bound: {2 * macs * n / (ms / 1e3) / 1e12:.1f} TFLOP/s on the CUDA cores "
-                                 f"({macs} MAC per window)"},
+                         "note": f"compute bound: {2 * macs * n / (ms / 1e3) / 1e12:.1f} TFLOP/s ({macs} MAC per window; conv2 as "
+                                 "3xTF32 mma.sync on the tensor cores, conv1 / SiLU / Linear on the FP32 pipe)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clk.summary()}))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

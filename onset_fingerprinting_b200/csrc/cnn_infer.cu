@@ -15,6 +15,7 @@
 #include "ofp_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace ofp {
@@ -38,7 +39,12 @@ struct K6Args {
 
 template <int ACT>
 __device__ __forceinline__ float k6_act(float v) {
-    if (ACT == 0) return __fdividef(v, 1.0f + __expf(-v));  // SiLU (2 ulp division, ex2.approx)
+    if (ACT == 0) {  // SiLU = v / (1 + 2^(-v log2 e)): ex2.approx + rcp.approx, 5 instructions (rel. error ~2e-7)
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        return v * r;
+    }
     if (ACT == 1) return fmaxf(v, 0.0f);                    // ReLU
     if (ACT == 2) return tanhf(v);
     return v;
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 2) k6_cnn(const K6Args a) {
 }
 
 }  // namespace ofp
+#include "cnn_infer_tc.cuh"
 
 using namespace ofp;
 
@@ -258,6 +265,26 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
     const int P = max_len <= 64 ? 2 : (max_len <= 128 ? 4 : 8);
     // odd multiple-of-nothing row stride is fine (all accesses are 32 consecutive words); room for the halo
     a.row_stride = 32 * P + 2 * padding + kernel_size + 1;
+    // Tensor-core path for the reference's default shape: [C0 -> 8 -> 16], k = 3, padding 1, SiLU, <= 4 outputs
+    static const bool no_tc = getenv("OFP_K6_NO_TC") != nullptr;
+    if (!no_tc && n_layers == 2 && kernel_size == 3 && padding == 1 && activation == 0 && out_size <= 4 &&
+        layer_sizes_host[0] == K6T_C1 && layer_sizes_host[1] == K6T_C2 && input_size % 16 == 0 && channels <= 8) {
+        const int n_w1 = channels * 24 + 8;
+        const size_t smem_tc = sizeof(float) * (((n_w1 + 3) & ~3) + static_cast<size_t>(out_size) * K6T_C2 * K6T_FCS +
+                                                static_cast<size_t>(K6_WARPS) * (channels + K6T_C1) * a.row_stride);
+        if (smem_tc <= 112 * 1024) {
+            auto kt = P == 2 ? k6_cnn_tc<2> : (P == 4 ? k6_cnn_tc<4> : k6_cnn_tc<8>);
+            OFP_CUDA_CHECK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_tc)));
+            int per_sm = 0;
+            OFP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, K6_WARPS * 32, smem_tc));
+            per_sm = std::max(per_sm, 1);
+            const int64_t want = (n_windows + K6_WARPS - 1) / K6_WARPS;
+            const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
+            kt<<<grid, K6_WARPS * 32, smem_tc, static_cast<cudaStream_t>(stream)>>>(a);
+            OFP_CUDA_CHECK(cudaGetLastError());
+            return OFP_OK;
+        }
+    }
     // shared memory: staged parameters + two activation buffers per warp.  4 warps with the Linear weights
     // staged and fused (2 CTAs per SM) when that fits, else 4 / 2 / 1 warps and the Linear read through L1.
     int warps = K6_WARPS;
