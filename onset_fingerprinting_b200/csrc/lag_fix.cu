@@ -68,6 +68,34 @@ __device__ __forceinline__ float median_rank(const float *w, int size) {
     return med;
 }
 
+// Median of SIZE values through an optimal sorting network (3 / 9 / 16 / 25 compare-exchanges for
+// 3 / 5 / 7 / 9 inputs, each validated with the 0-1 principle): 2 FMNMX per exchange instead of SIZE^2 rank
+// comparisons.  Any correct selection returns the same VALUE as scipy's median_filter; NaNs (for which
+// fminf / fmaxf are not an ordering) are detected by the caller and sent through rank counting.
+__device__ __forceinline__ void cswap(float &a, float &b) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo; b = hi;
+}
+template <int SIZE>
+__device__ __forceinline__ float median_network(float (&w)[SIZE > 0 ? SIZE : 16]) {
+#define CS(i, j) cswap(w[i], w[j])
+    if (SIZE == 3) { CS(0, 2); CS(0, 1); CS(1, 2); return w[1]; }
+    if (SIZE == 5) { CS(0, 3); CS(1, 4); CS(0, 2); CS(1, 3); CS(0, 1); CS(2, 4); CS(1, 2); CS(3, 4); CS(2, 3); return w[2]; }
+    if (SIZE == 7) {
+        CS(0, 6); CS(2, 3); CS(4, 5); CS(0, 2); CS(1, 4); CS(3, 6); CS(0, 1); CS(2, 5); CS(3, 4); CS(1, 2); CS(4, 6);
+        CS(2, 3); CS(4, 5); CS(1, 2); CS(3, 4); CS(5, 6);
+        return w[3];
+    }
+    if (SIZE == 9) {
+        CS(0, 3); CS(1, 7); CS(2, 5); CS(4, 8); CS(0, 7); CS(2, 4); CS(3, 8); CS(5, 6); CS(0, 2); CS(1, 3); CS(4, 5);
+        CS(7, 8); CS(1, 4); CS(3, 6); CS(5, 7); CS(0, 1); CS(2, 4); CS(3, 5); CS(6, 8); CS(2, 3); CS(4, 5); CS(6, 7);
+        CS(1, 2); CS(3, 4); CS(5, 6);
+        return w[4];
+    }
+#undef CS
+    return w[0];
+}
+
 template <int SIZE>
 __device__ __forceinline__ float median_window(const float *src, int64_t L, int C, int64_t t, int c, int size) {
     float w[SIZE > 0 ? SIZE : 16];
@@ -85,6 +113,12 @@ __device__ __forceinline__ float median_window(const float *src, int64_t L, int 
             }
             w[j] = src[q * C + c];
         }
+    }
+    if (SIZE == 3 || SIZE == 5 || SIZE == 7 || SIZE == 9) {
+        float chk = 0.f;
+#pragma unroll
+        for (int j = 0; j < (SIZE > 0 ? SIZE : 1); ++j) chk += w[j];
+        if (chk == chk) return median_network<SIZE>(w);  // no NaN (inf - inf also lands in the rank path)
     }
     if (SIZE > 0) {
         const int want = SIZE / 2;
@@ -110,6 +144,34 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
     double r = 0.0;
     for (int i = 0; i < K4_THREADS / 32; ++i) r += scratch[i];
     return r;
+}
+
+// two sums / two maxima with one pair of barriers (same per-value summation order as block_sum / block_max)
+__device__ __forceinline__ void block_sum2(double &a, double &b, double *scratch) {
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { scratch[warp] = a; scratch[K4_THREADS / 32 + warp] = b; }
+    __syncthreads();
+    double ra = 0.0, rb = 0.0;
+    for (int i = 0; i < K4_THREADS / 32; ++i) { ra += scratch[i]; rb += scratch[K4_THREADS / 32 + i]; }
+    a = ra; b = rb;
+}
+__device__ __forceinline__ void block_max2(float &a, float &b, float *scratch) {
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmaxf(a, __shfl_down_sync(0xffffffffu, a, o));
+        b = fmaxf(b, __shfl_down_sync(0xffffffffu, b, o));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { scratch[warp] = a; scratch[K4_THREADS / 32 + warp] = b; }
+    __syncthreads();
+    float ra = scratch[0], rb = scratch[K4_THREADS / 32];
+    for (int i = 1; i < K4_THREADS / 32; ++i) { ra = fmaxf(ra, scratch[i]); rb = fmaxf(rb, scratch[K4_THREADS / 32 + i]); }
+    a = ra; b = rb;
 }
 
 __device__ __forceinline__ float block_max(float v, float *scratch) {
@@ -274,8 +336,7 @@ __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double 
         sx += xv * xv;
         if (i < L) { const double yv = yd[i]; sc.yf[i] = static_cast<float>(yv); sy += yv * yv; }
     }
-    sx = block_sum(sx, sc.red_d);
-    sy = block_sum(sy, sc.red_d);
+    block_sum2(sx, sy, sc.red_d);
     const double S = sqrt(sx) * sqrt(sy);
     if (!(S < 1e30)) return false;  // inf / NaN in the section: exact path
     if (S == 0.0) {                 // one signal is all zero: every sum is 0, np.argmax returns index 0
@@ -338,26 +399,27 @@ __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double 
     __syncthreads();
     // pass 2: v32, bounds, candidates
     const float Ef = static_cast<float>(S * (static_cast<double>(L + 8) * 5.9604644775390625e-08) * 1.0001);
-    auto eval = [&](int64_t w, float &v, float &d) {
-        const int gg = static_cast<int>(w / LPF), u = static_cast<int>(w - static_cast<int64_t>(gg) * LPF);
+    const int m_first = static_cast<int>(ws - (L - 1)), Lw = static_cast<int>(L), nlw = static_cast<int>(nl);
+    auto eval = [&](int w, float &v, float &d) {
+        const int gg = w / LPF, u = w - gg * LPF;
         float a = 0.f;
         for (int q = 0; q < NS; ++q) a += sc.part[(q * NG + gg) * LPF + u];
-        const int64_t m = ws + w - (L - 1);
-        int64_t cnt = L - (m < 0 ? -m : m);
+        const int m = m_first + w;
+        int cnt = Lw - (m < 0 ? -m : m);
         if (cnt < cutoff) cnt = cutoff;
         const float c = static_cast<float>(cnt);
         v = a / c;
         d = Ef / c * 1.0001f + fabsf(v) * 4.76837158203125e-07f;
     };
     float lowmax = -INFINITY;
-    for (int64_t w = tid; w < nl; w += K4_THREADS) {
+    for (int w = tid; w < nlw; w += K4_THREADS) {
         float v, d;
         eval(w, v, d);
         lowmax = fmaxf(lowmax, v - d);
     }
     lowmax = block_max(lowmax, sc.red_f);
     __syncthreads();
-    for (int64_t w = tid; w < nl; w += K4_THREADS) {
+    for (int w = tid; w < nlw; w += K4_THREADS) {
         float v, d;
         eval(w, v, d);
         if (v + d >= lowmax) {
@@ -436,8 +498,8 @@ __device__ __forceinline__ bool adjust_sums(const double *xd, const double *yd, 
             const int64_t wi = k - 1 - i;
             pb += yd[ys + i] * exp((wi == k - 1 && k > 1) ? stop : static_cast<double>(wi) * step);
         }
-        da = block_sum(pa, red_d);
-        db = block_sum(pb, red_d);
+        block_sum2(pa, pb, red_d);
+        da = pa; db = pb;
         da = da / static_cast<double>(xmax);
         db = ly != 0 ? db / static_cast<double>(ymax) : 0.0;
         __syncthreads();
@@ -461,8 +523,8 @@ __global__ void __launch_bounds__(K4_THREADS, OFP_K4_MINCTA) k4_fix(const K4Args
     __shared__ int idx[32];
     __shared__ int64_t s_s0, s_L0;
     __shared__ int s_status;
-    __shared__ double red_d[K4_THREADS / 32];
-    __shared__ float red_f[K4_THREADS / 32];
+    __shared__ double red_d[2 * (K4_THREADS / 32)];
+    __shared__ float red_f[2 * (K4_THREADS / 32)];
     __shared__ float best_v[K4_THREADS / 32];
     __shared__ int best_w[K4_THREADS / 32];
     __shared__ int s_lag;
@@ -508,9 +570,13 @@ __global__ void __launch_bounds__(K4_THREADS, OFP_K4_MINCTA) k4_fix(const K4Args
     // median filter along time (detection.py:420-422), read straight from the recording (the 7 rows
     // around a sample are coalesced and L1-resident) into the only section buffer kept in shared memory
     float *med = bufA;
-    for (int64_t e = tid; e < L0 * C; e += K4_THREADS) {
-        const int64_t t = e / C;
-        const int c = static_cast<int>(e - t * C);
+    const int n_el = static_cast<int>(L0) * C, dt_el = K4_THREADS / C, dc_el = K4_THREADS % C;
+    int t_el = tid / C, c_el = tid % C;  // (sample, channel) of element e, advanced without a division
+    for (int e = tid; e < n_el; e += K4_THREADS) {
+        const int64_t t = t_el;
+        const int c = c_el;
+        t_el += dt_el; c_el += dc_el;
+        if (c_el >= C) { c_el -= C; ++t_el; }
         float m;
         switch (fp.filter_size) {
             case 1: m = src[e]; break;
@@ -560,8 +626,8 @@ __global__ void __launch_bounds__(K4_THREADS, OFP_K4_MINCTA) k4_fix(const K4Args
             xd[t] = static_cast<double>(xv); yd[t] = static_cast<double>(yv);
             xm = fmaxf(xm, xv); ym = fmaxf(ym, yv);
         }
-        const float xmax = block_max(xm, red_f);
-        const float ymax = block_max(ym, red_f);
+        block_max2(xm, ym, red_f);
+        const float xmax = xm, ymax = ym;
         __syncthreads();
         // window of the full CC, detection.py:259-264
         const int64_t cur = o1 - o0;
@@ -660,7 +726,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_cc_pairs(const PairArgs a) {
     }
     py_slice(ws, we, 2 * L - 1);
     if (we - ws <= 0 || L <= 0) { if (threadIdx.x == 0) a.out[p] = LAG_NONE; return; }
-    __shared__ double red_d[K4_THREADS / 32];
+    __shared__ double red_d[2 * (K4_THREADS / 32)];
     CcScratch sc;
     sc.xf = tmp + 2 * a.n;
     sc.yf = sc.xf + a.n + 2 * XPAD;
@@ -678,7 +744,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_adjust_pairs(const PairArgs a) 
     double *yd = xd + a.n + 16;
     float *tmp = reinterpret_cast<float *>(yd + a.n + 16);
     __shared__ float red_f[K4_THREADS / 32];
-    __shared__ double red_d[K4_THREADS / 32];
+    __shared__ double red_d[2 * (K4_THREADS / 32)];
     const int p = blockIdx.x;
     float xmax, ymax;
     const int64_t L = load_pair(a, p, xd, yd, tmp, red_f, xmax, ymax);
