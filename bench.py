@@ -223,7 +223,12 @@ def run_ours(args):
 
             recs = parallel.pack_records(hb.rec, hb.fixed, hb.lags, hb.xy, hb.fix_status, hb.loc_status,
                                          rec_offset=rank * R)
-            last["all_records"] = parallel.gather_records(recs)
+            # fixed-capacity blocks: no host round trip for counts inside the step (H is already on the host)
+            cap_h = last.setdefault("gather_capacity", int(recs.shape[0] * 1.05) + 1024)
+            if recs.shape[0] <= cap_h:
+                last["all_records"] = parallel.gather_records_padded(recs, cap_h)
+            else:
+                last["all_records"] = parallel.gather_records(recs)
 
     def step():
         nonlocal launches
@@ -303,8 +308,8 @@ def run_ours(args):
                 "algorithmic_bytes_per_channel_sample": bytes_per_unit}
 
     line = None
+    e2e = run_e2e(args, torch, detection, _lib, synth, dist, world, rank)  # every rank feeds its own GPU
     if rank == 0:
-        e2e = run_e2e(args, torch, detection, _lib, synth)
         cpu = None if args.skip_cpu else run_cpu_baseline(args, x)
         line = {
             "metric": "channel-samples/sec through the onset->lag->multilateration hot path",
@@ -324,12 +329,14 @@ def run_ours(args):
         print(json.dumps(line))
 
 
-def run_e2e(args, torch, detection, _lib, synth):
-    """Same metric through the C-ABI host entry point: pinned host audio in, onsets out."""
+def run_e2e(args, torch, detection, _lib, synth, dist=None, world=1, rank=0):
+    """Same metric through the C-ABI host entry point: pinned host audio in, onsets out.  With N ranks every
+    rank pushes its own recordings through its own GPU at the same time; value = all ranks' units over the
+    slowest rank's wall time."""
     import ctypes as C
 
     Re, N = min(args.e2e_recordings, args.recordings), int(args.seconds * SR)
-    xd = synth.drum_batch_device(Re, N, seed=99)
+    xd = synth.drum_batch_device(Re, N, seed=99, rec_offset=rank * Re)
     xh = torch.empty(xd.shape, dtype=torch.float32, pin_memory=True)
     xh.copy_(xd)
     torch.cuda.synchronize()
@@ -348,15 +355,21 @@ def run_e2e(args, torch, detection, _lib, synth):
     for _ in range(2):
         call()
     reps = 3
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
         call()
     dt = (time.perf_counter() - t0) / reps
-    units = Re * (N // BLOCK) * BLOCK * N_CH
-    return {"value": units / dt, "unit": "channel-samples/s", "h2d_bytes_per_step": int(xh.numel() * 4),
-            "d2h_bytes_per_step": int((ch.numel() + ix.numel() + cnt.numel()) * 4),
-            "recordings": Re, "ms": dt * 1e3, "mode": "onsets_only (rel not copied back)",
-            "entry": "ofp_detect_offline_host"}
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    units = world * Re * (N // BLOCK) * BLOCK * N_CH
+    return {"value": units / dt, "unit": "channel-samples/s", "h2d_bytes_per_step": int(world * xh.numel() * 4),
+            "d2h_bytes_per_step": int(world * (ch.numel() + ix.numel() + cnt.numel()) * 4),
+            "recordings": world * Re, "ms": dt * 1e3, "mode": "onsets_only (rel not copied back)",
+            "entry": "ofp_detect_offline_host (one call per rank, concurrently)"}
 
 
 def run_cpu_baseline(args, x):

@@ -54,3 +54,27 @@ def gather_records(records: torch.Tensor, group=None) -> torch.Tensor:
     blocks = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(blocks, padded, group=group)
     return torch.cat([b[:c] for b, c in zip(blocks, counts)], 0)
+
+
+def gather_records_padded(records: torch.Tensor, capacity: int, group=None):
+    """Sync-free variant for a hot loop: every rank contributes a block padded to a fixed `capacity` rows, so
+    neither the counts nor the payload need a host round trip.  Returns (blocks [world, capacity, width],
+    counts [world] int64, both on the device); `compact_gathered` turns them into the concatenated table when
+    a consumer needs it.  records.shape[0] must not exceed capacity (checked by the caller, who knows H)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    width = records.shape[1]
+    padded = torch.zeros((capacity, width), dtype=records.dtype, device=records.device)
+    padded[: records.shape[0]] = records
+    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
+    if world == 1:
+        return padded[None], n
+    blocks = torch.empty((world, capacity, width), dtype=records.dtype, device=records.device)
+    counts = torch.empty((world,), dtype=torch.int64, device=records.device)
+    dist.all_gather(list(blocks.unbind(0)), padded, group=group)
+    dist.all_gather(list(counts.split(1)), n, group=group)
+    return blocks, counts
+
+
+def compact_gathered(blocks: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """Concatenate the valid rows of `gather_records_padded`'s result in rank order (host sync on counts)."""
+    return torch.cat([blocks[r, : int(c)] for r, c in enumerate(counts.tolist())], 0)

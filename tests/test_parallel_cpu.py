@@ -39,6 +39,10 @@ def _worker(rank, world, port, out):
     ok &= torch.equal(torch.nan_to_num(d["xy"][lo:lo + H]), torch.nan_to_num(xy))
     ok &= bool(torch.isnan(d["xy"][lo, 0]))
     ok &= int(d["rec"][lo]) == 100 * rank and int(d["loc_status"][lo]) == rank
+    # the sync-free fixed-capacity form used inside the bench step gives the same table
+    blocks, counts = parallel.gather_records_padded(mine, capacity=16)
+    ok &= counts.tolist() == [5 + 2 * r for r in range(world)]
+    ok &= torch.equal(parallel.compact_gathered(blocks, counts), everything)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
