@@ -7,8 +7,8 @@ windows are gathered by ``ofp_extract_frames`` straight from recordings resident
 ``[R, N, C]`` batch K1/K4 just processed (``extract_frames_batch``) -- so the offline dataset build
 (BASELINE config 2, "data.py path") never copies audio back to the host.
 
-File formats (wav + json, ``from_file``) and the augmentation pipeline are host-side and out of
-scope.
+The wav + json session files are read and written by ``posd.py`` (``MCPOSD.from_file`` goes through it);
+the augmentation pipeline is host-side and out of scope.
 """
 from __future__ import annotations
 
@@ -140,6 +140,15 @@ class MCPOSD:
 
     def __len__(self):
         return 1
+
+    @classmethod
+    def from_file(cls, folder, name: str, frame_length: int = 256, pre_samples: int = 0, max_shift: int = 0,
+                  n_extractions: int = 1, channels=None):
+        """data.py:285-311: ``<folder>/<name>.wav`` + ``<name>.json`` (POSD session, posd.py)."""
+        from . import posd
+
+        data, _, onsets, positions, _ = posd.read_session(folder, name)
+        return cls(data, onsets, positions, frame_length, pre_samples, max_shift, n_extractions, channels=channels)
 
     @classmethod
     def from_xy(cls, x, y):

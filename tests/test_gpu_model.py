@@ -123,3 +123,27 @@ def test_multilaterate3d_model_bypass():
         order = np.argsort(on[h], kind="stable")
         got = b.trilaterate(([int(s) for s in order], [int(on[h][s]) for s in order]), initial_guess=np.zeros(2))
         assert np.allclose(got, xy_b[h], rtol=1e-6, atol=1e-6)
+
+
+def test_session_file_to_windows_to_network(tmp_path):
+    """The dataset tail of configs[1]/[4]: hot path results -> POSD session on disk (posd.py) -> MCPOSD.from_file
+    (data.py:285-311) -> windows on the device -> CNN inference; the windows equal a direct numpy slice."""
+    from onset_fingerprinting_b200 import data, model, pipeline, posd, synth
+
+    xs, _ = synth.drum_batch(1, seconds=2.0, seed=21)
+    hb = pipeline.HotPath(1, 3, synth.SENSORS_3MIC, medium="air", sr=96000).run(torch.from_numpy(xs).cuda())
+    ok = (hb.loc_status == 0).cpu().numpy()
+    assert ok.sum() >= 5
+    fixed, xy = hb.fixed.cpu().numpy()[ok], hb.xy.cpu().numpy()[ok]
+    posd.write_session(tmp_path, "take1", xs[0], 96000, fixed, xy, synth.SENSORS_3MIC, meta={"instrument": "snare"})
+    ds = data.MCPOSD.from_file(tmp_path, "take1", frame_length=256, pre_samples=16)
+    x, y = ds[0]
+    assert tuple(x.shape) == (int(ok.sum()), 3, 256) and tuple(y.shape) == (int(ok.sum()), 2)
+    start = fixed.min(1) - 16
+    want = np.stack([xs[0][s:s + 256].T for s in start])
+    assert np.array_equal(x.cpu().numpy(), want)
+    assert np.allclose(y.cpu().numpy(), xy.astype(np.float32))
+    torch.manual_seed(5)
+    net = model.CNN(256, 2).cuda()
+    out = net(x)
+    assert tuple(out.shape) == (int(ok.sum()), 2) and bool(torch.isfinite(out).all())
