@@ -93,13 +93,18 @@ struct PairArgs {
     int32_t screen;
 };
 
-namespace t64 { constexpr int K4_THREADS = 64, K4_MINCTA = 8;
+#ifndef OFP_K4_SMALL_LPF
+#define OFP_K4_SMALL_LPF 9
+#endif
+// lags per thread in the float32 screening (tunable per CTA size; measured 1 / 3 / 5 / 9 on 3-channel hits:
+// 8.13-8.18 ms for 380 k hits, no difference -- those hits are barrier / latency bound, scripts/ncu_lines.py)
+namespace t64 { constexpr int K4_THREADS = 64, K4_MINCTA = 8, K4_LPF = OFP_K4_SMALL_LPF;
 #include "lag_fix_body.cuh"
 }
-namespace t128 { constexpr int K4_THREADS = 128, K4_MINCTA = 4;
+namespace t128 { constexpr int K4_THREADS = 128, K4_MINCTA = 4, K4_LPF = OFP_K4_SMALL_LPF;
 #include "lag_fix_body.cuh"
 }
-namespace t192 { constexpr int K4_THREADS = K4_MAX_THREADS, K4_MINCTA = OFP_K4_MINCTA;
+namespace t192 { constexpr int K4_THREADS = K4_MAX_THREADS, K4_MINCTA = OFP_K4_MINCTA, K4_LPF = LPF;
 #include "lag_fix_body.cuh"
 }
 

@@ -249,7 +249,7 @@ __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double 
                                                  int64_t adj, int cutoff, const CcScratch &sc, float *best_v,
                                                  int *best_w, int *s_lag) {
     const int tid = threadIdx.x;
-    if (nl > K4_THREADS * LPF || L < 64) return false;
+    if (nl > K4_THREADS * K4_LPF || L < 64) return false;
     // float copies and the norms
     double sx = 0.0, sy = 0.0;
     for (int64_t i = tid; i < L + 2 * XPAD; i += K4_THREADS) {
@@ -269,64 +269,64 @@ __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double 
     }
     if (tid == 0) sc.cand[0] = 0;
     // pass 1: thread = (lag group g, time segment s)
-    const int NG = static_cast<int>((nl + LPF - 1) / LPF);
+    const int NG = static_cast<int>((nl + K4_LPF - 1) / K4_LPF);
     const int NS = K4_THREADS / NG;  // >= 1
     const int g = tid % NG, seg = tid / NG;
-    float acc[LPF];
+    float acc[K4_LPF];
 #pragma unroll
-    for (int u = 0; u < LPF; ++u) acc[u] = 0.f;
+    for (int u = 0; u < K4_LPF; ++u) acc[u] = 0.f;
     if (seg < NS) {
-        const int64_t m0 = ws + static_cast<int64_t>(g) * LPF - (L - 1);  // lag of the group's first window
-        const int64_t m1 = m0 + LPF - 1;
+        const int64_t m0 = ws + static_cast<int64_t>(g) * K4_LPF - (L - 1);  // lag of the group's first window
+        const int64_t m1 = m0 + K4_LPF - 1;
         // union of the valid index ranges of the group's lags; outside its own range a lag reads zeros
         int64_t lo = m1 < 0 ? -m1 : 0, hi = m0 > 0 ? L - m0 : L;
         if (lo < 0) lo = 0;
         if (hi > L) hi = L;
         if (hi < lo) hi = lo;
-        // reads stay inside [-(LPF-1), L + LPF - 1) of x: covered by XPAD
+        // reads stay inside [-(K4_LPF-1), L + K4_LPF - 1) of x: covered by XPAD
         const int64_t len = hi - lo, per = (len + NS - 1) / NS;
         const int64_t i0 = lo + seg * per, i1 = min(hi, i0 + per);
         if (i1 > i0) {
             const float *xp = sc.xf + XPAD + i0 + m0, *yp = sc.yf + i0;
             const int n = static_cast<int>(i1 - i0);
-            float xw[LPF - 1 + CCF_UN];
+            float xw[K4_LPF - 1 + CCF_UN];
 #pragma unroll
-            for (int k = 0; k < LPF - 1; ++k) xw[k] = xp[k];
+            for (int k = 0; k < K4_LPF - 1; ++k) xw[k] = xp[k];
             int i = 0;
             for (; i + CCF_UN <= n; i += CCF_UN) {
                 float yv[CCF_UN];
 #pragma unroll
-                for (int k = 0; k < CCF_UN; ++k) { yv[k] = yp[i + k]; xw[LPF - 1 + k] = xp[i + LPF - 1 + k]; }
+                for (int k = 0; k < CCF_UN; ++k) { yv[k] = yp[i + k]; xw[K4_LPF - 1 + k] = xp[i + K4_LPF - 1 + k]; }
 #pragma unroll
                 for (int k = 0; k < CCF_UN; ++k)
 #pragma unroll
-                    for (int u = 0; u < LPF; ++u) acc[u] = fmaf(xw[k + u], yv[k], acc[u]);
+                    for (int u = 0; u < K4_LPF; ++u) acc[u] = fmaf(xw[k + u], yv[k], acc[u]);
 #pragma unroll
-                for (int k = 0; k < LPF - 1; ++k) xw[k] = xw[k + CCF_UN];
+                for (int k = 0; k < K4_LPF - 1; ++k) xw[k] = xw[k + CCF_UN];
             }
             for (; i < n; ++i) {
                 const float yv = yp[i];
-                xw[LPF - 1] = xp[i + LPF - 1];
+                xw[K4_LPF - 1] = xp[i + K4_LPF - 1];
 #pragma unroll
-                for (int u = 0; u < LPF; ++u) acc[u] = fmaf(xw[u], yv, acc[u]);
+                for (int u = 0; u < K4_LPF; ++u) acc[u] = fmaf(xw[u], yv, acc[u]);
 #pragma unroll
-                for (int k = 0; k < LPF - 1; ++k) xw[k] = xw[k + 1];
+                for (int k = 0; k < K4_LPF - 1; ++k) xw[k] = xw[k + 1];
             }
         }
     }
     __syncthreads();  // xf / yf reads done; part aliases nothing else
     if (seg < NS) {
 #pragma unroll
-        for (int u = 0; u < LPF; ++u) sc.part[(seg * NG + g) * LPF + u] = acc[u];
+        for (int u = 0; u < K4_LPF; ++u) sc.part[(seg * NG + g) * K4_LPF + u] = acc[u];
     }
     __syncthreads();
     // pass 2: v32, bounds, candidates
     const float Ef = static_cast<float>(S * (static_cast<double>(L + 8) * 5.9604644775390625e-08) * 1.0001);
     const int m_first = static_cast<int>(ws - (L - 1)), Lw = static_cast<int>(L), nlw = static_cast<int>(nl);
     auto eval = [&](int w, float &v, float &d) {
-        const int gg = w / LPF, u = w - gg * LPF;
+        const int gg = w / K4_LPF, u = w - gg * K4_LPF;
         float a = 0.f;
-        for (int q = 0; q < NS; ++q) a += sc.part[(q * NG + gg) * LPF + u];
+        for (int q = 0; q < NS; ++q) a += sc.part[(q * NG + gg) * K4_LPF + u];
         const int m = m_first + w;
         int cnt = Lw - (m < 0 ? -m : m);
         if (cnt < cutoff) cnt = cutoff;
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
     sc.xf = bufA + static_cast<size_t>(a.Lmax) * C;
     sc.yf = sc.xf + a.Lmax + 2 * XPAD;
     sc.part = sc.yf + a.Lmax + 16;
-    sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * LPF);
+    sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * K4_LPF);
     __shared__ int64_t og[32], so[32], zl[32];
     __shared__ int idx[32];
     __shared__ int64_t s_s0, s_L0;
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(K4_THREADS) k4_cc_pairs(const PairArgs a) {
     sc.xf = tmp + 2 * a.n;
     sc.yf = sc.xf + a.n + 2 * XPAD;
     sc.part = sc.yf + a.n + 16;
-    sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * LPF);
+    sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * K4_LPF);
     sc.red_d = red_d; sc.red_f = red_f;
     if (!a.screen || !cc_argmax_screen(xd, yd, L, ws, we - ws, adj, a.cutoff, sc, best_v, best_w, &s_lag))
         cc_argmax(xd, yd, L, ws, we - ws, adj, a.cutoff, best_v, best_w, &s_lag);
