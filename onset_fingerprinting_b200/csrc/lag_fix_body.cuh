@@ -86,6 +86,37 @@ __device__ __forceinline__ float median_window(const float *src, int64_t L, int 
     return median_rank(w, n);
 }
 
+// K4_RUN consecutive samples of one channel per thread: the SIZE + K4_RUN - 1 samples the windows share are
+// loaded once (10 loads for four 7-point medians instead of 28) and are all in flight together.
+constexpr int K4_RUN = 4;
+template <int SIZE>
+__device__ __forceinline__ void median_run(const float *src, int Li, int C, int t0, int c, float *med) {
+    constexpr int NW = SIZE + K4_RUN - 1, lo = SIZE / 2;
+    float w[NW];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        int q = t0 - lo + j;  // scipy mode='reflect': d c b a | a b c d | d c b a
+        if (q < 0 || q >= Li) {
+            const int P = 2 * Li;
+            q %= P; if (q < 0) q += P;
+            if (q >= Li) q = P - 1 - q;
+        }
+        w[j] = src[q * C + c];
+    }
+    float chk = 0.f;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) chk += w[j];
+    const bool finite = chk == chk;  // a NaN anywhere in the run (or inf - inf): rank counting, as in median_window
+#pragma unroll
+    for (int k = 0; k < K4_RUN; ++k) {
+        if (t0 + k >= Li) break;
+        float v[SIZE];
+#pragma unroll
+        for (int j = 0; j < SIZE; ++j) v[j] = w[k + j];
+        med[(t0 + k) * C + c] = finite ? median_network<SIZE>(v) : median_rank(v, SIZE);
+    }
+}
+
 __device__ __forceinline__ double block_sum(double v, double *scratch) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -493,23 +524,29 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
     // median filter along time (detection.py:420-422), read straight from the recording (the 7 rows
     // around a sample are coalesced and L1-resident) into the only section buffer kept in shared memory
     float *med = bufA;
-    const int n_el = static_cast<int>(L0) * C, dt_el = K4_THREADS / C, dc_el = K4_THREADS % C;
-    int t_el = tid / C, c_el = tid % C;  // (sample, channel) of element e, advanced without a division
-    for (int e = tid; e < n_el; e += K4_THREADS) {
-        const int64_t t = t_el;
-        const int c = c_el;
-        t_el += dt_el; c_el += dc_el;
-        if (c_el >= C) { c_el -= C; ++t_el; }
-        float m;
-        switch (fp.filter_size) {
-            case 1: m = src[e]; break;
-            case 3: m = median_window<3>(src, L0, C, t, c, 3); break;
-            case 5: m = median_window<5>(src, L0, C, t, c, 5); break;
-            case 7: m = median_window<7>(src, L0, C, t, c, 7); break;
-            case 9: m = median_window<9>(src, L0, C, t, c, 9); break;
-            default: m = median_window<0>(src, L0, C, t, c, fp.filter_size); break;
+    const int n_el = static_cast<int>(L0) * C;
+    if (fp.filter_size == 3 || fp.filter_size == 5 || fp.filter_size == 7 || fp.filter_size == 9) {
+        // runs of K4_RUN samples of one channel per thread (lanes across channels, then across runs)
+        const int Li = static_cast<int>(L0), n_runs = (Li + K4_RUN - 1) / K4_RUN * C;
+        for (int r = tid; r < n_runs; r += K4_THREADS) {
+            const int tr = r / C, c = r - tr * C, t0 = tr * K4_RUN;
+            switch (fp.filter_size) {
+                case 3: median_run<3>(src, Li, C, t0, c, med); break;
+                case 5: median_run<5>(src, Li, C, t0, c, med); break;
+                case 7: median_run<7>(src, Li, C, t0, c, med); break;
+                default: median_run<9>(src, Li, C, t0, c, med); break;
+            }
         }
-        med[e] = m;
+    } else {
+        const int dt_el = K4_THREADS / C, dc_el = K4_THREADS % C;
+        int t_el = tid / C, c_el = tid % C;  // (sample, channel) of element e, advanced without a division
+        for (int e = tid; e < n_el; e += K4_THREADS) {
+            const int64_t t = t_el;
+            const int c = c_el;
+            t_el += dt_el; c_el += dc_el;
+            if (c_el >= C) { c_el -= C; ++t_el; }
+            med[e] = fp.filter_size == 1 ? src[e] : median_window<0>(src, L0, C, t, c, fp.filter_size);
+        }
     }
     const int64_t L = L0 - fp.d;
     if (tid < C) { so[tid] = og[tid] - s0; zl[tid] = 0; }  // detection.py:429
