@@ -278,19 +278,25 @@ __device__ __forceinline__ double cc_exact_one(const double *xd, const double *y
 // Returns false when the screening is inconclusive (caller runs cc_argmax).  Uniform across the block.
 __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double *yd, int64_t L, int64_t ws, int64_t nl,
                                                  int64_t adj, int cutoff, const CcScratch &sc, float *best_v,
-                                                 int *best_w, int *s_lag) {
+                                                 int *best_w, int *s_lag, bool &xf_valid, double &sx_cache) {
     const int tid = threadIdx.x;
     if (nl > K4_THREADS * K4_LPF || L < 64) return false;
     // float copies and the norms
+    // (xf_valid: xd is still the signal of an earlier call, its float copy and norm are kept)
+    const bool x_fresh = !xf_valid;
+    xf_valid = true;
     double sx = 0.0, sy = 0.0;
     for (int64_t i = tid; i < L + 2 * XPAD; i += K4_THREADS) {
-        const int64_t k = i - XPAD;
-        const double xv = (k >= 0 && k < L) ? xd[k] : 0.0;
-        sc.xf[i] = static_cast<float>(xv);
-        sx += xv * xv;
+        if (x_fresh) {
+            const int64_t k = i - XPAD;
+            const double xv = (k >= 0 && k < L) ? xd[k] : 0.0;
+            sc.xf[i] = static_cast<float>(xv);
+            sx += xv * xv;
+        }
         if (i < L) { const double yv = yd[i]; sc.yf[i] = static_cast<float>(yv); sy += yv * yv; }
     }
     block_sum2(sx, sy, sc.red_d);
+    if (x_fresh) sx_cache = sx; else sx = sx_cache;
     const double S = sqrt(sx) * sqrt(sy);
     if (!(S < 1e30)) return false;  // inf / NaN in the section: exact path
     if (S == 0.0) {                 // one signal is all zero: every sum is 0, np.argmax returns index 0
@@ -570,6 +576,10 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
 
     const int r = idx[0];
     int status = FIX_OK;
+    int64_t x_zl = -1;
+    float xmax_c = 0.f;
+    double sx_c = 0.0;
+    bool xf_valid = false;  // the screening's float copy / norm of xd
     for (int j = 1; j < C; ++j) {
         const int ci = idx[j];
         const int64_t o0 = so[r], o1 = so[ci];
@@ -580,14 +590,24 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
             if (tid == 0) { zl[r] = max(zl[r], z0); zl[ci] = max(zl[ci], z1); }
             __syncthreads();
         }
+        // the reference channel's signal only changes when its zero_left prefix grew: keep xd, its float copy,
+        // norm and maximum across pairs otherwise (so[r] moves, but it only selects the window)
+        const bool x_fresh = zl[r] != x_zl;
+        x_zl = zl[r];
         float xm = -INFINITY, ym = -INFINITY;
         for (int64_t t = tid; t < L; t += K4_THREADS) {
-            const float xv = secval(t, r), yv = secval(t, ci);
-            xd[t] = static_cast<double>(xv); yd[t] = static_cast<double>(yv);
-            xm = fmaxf(xm, xv); ym = fmaxf(ym, yv);
+            const float yv = secval(t, ci);
+            yd[t] = static_cast<double>(yv);
+            ym = fmaxf(ym, yv);
+            if (x_fresh) {
+                const float xv = secval(t, r);
+                xd[t] = static_cast<double>(xv);
+                xm = fmaxf(xm, xv);
+            }
         }
         block_max2(xm, ym, red_f);
-        const float xmax = xm, ymax = ym;
+        if (x_fresh) { xmax_c = xm; xf_valid = false; }
+        const float xmax = xmax_c, ymax = ym;
         __syncthreads();
         // window of the full CC, detection.py:259-264
         const int64_t cur = o1 - o0;
@@ -596,7 +616,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
         py_slice(ws, we, 2 * L - 1);
         const int64_t nl = we - ws;
         if (nl <= 0) continue;  // detection.py:265-266 -> None, no adjustment
-        if (!a.screen || !cc_argmax_screen(xd, yd, L, ws, nl, adj, fp.cutoff, sc, best_v, best_w, &s_lag))
+        if (!a.screen || !cc_argmax_screen(xd, yd, L, ws, nl, adj, fp.cutoff, sc, best_v, best_w, &s_lag, xf_valid, sx_c))
             cc_argmax(xd, yd, L, ws, nl, adj, fp.cutoff, best_v, best_w, &s_lag);
         const int lag = s_lag;
         if (tid == 0 && a.out_lags) a.out_lags[static_cast<int64_t>(h) * C + ci] = lag;
@@ -683,7 +703,9 @@ __global__ void __launch_bounds__(K4_THREADS) k4_cc_pairs(const PairArgs a) {
     sc.part = sc.yf + a.n + 16;
     sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * K4_LPF);
     sc.red_d = red_d; sc.red_f = red_f;
-    if (!a.screen || !cc_argmax_screen(xd, yd, L, ws, we - ws, adj, a.cutoff, sc, best_v, best_w, &s_lag))
+    double sx_unused = 0.0;
+    bool xf_valid = false;
+    if (!a.screen || !cc_argmax_screen(xd, yd, L, ws, we - ws, adj, a.cutoff, sc, best_v, best_w, &s_lag, xf_valid, sx_unused))
         cc_argmax(xd, yd, L, ws, we - ws, adj, a.cutoff, best_v, best_w, &s_lag);
     if (threadIdx.x == 0) a.out[p] = s_lag;
 }
