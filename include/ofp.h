@@ -336,6 +336,40 @@ int ofp_peak_pick(const float *oe_dev, int32_t n_rec, int32_t n_frames, int32_t 
                   int32_t *n_peaks_dev, int32_t cap, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Realtime session -- PlayRec's per-block callback (realtime/audio.py:62-122: detector -> locate per
+ * 128-sample block) for n_streams concurrent streams as one replayed CUDA graph per block.
+ * ------------------------------------------------------------------------------------- */
+
+/* ofp_stream_locate with the block's start index kept in device memory (*current_index_dev, advanced by
+ * `advance` samples after the block): the form a CUDA graph can replay. */
+int ofp_stream_locate_dev(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                          int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                          const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                          double c_cm_s, int32_t n_streams, int32_t n_channels, const int32_t *det_channel_dev,
+                          const int32_t *det_delta_dev, const int32_t *det_count_dev, int64_t *current_index_dev,
+                          int32_t advance, int32_t *state_count_dev, int32_t *state_len_dev,
+                          int32_t *state_sensor_dev, int64_t *state_onset_dev, double *xy_dev, int32_t *found_dev,
+                          void *stream);
+
+typedef struct ofp_rt ofp_rt;
+/* The session owns the detector, the locate state, a staging buffer and pinned result buffers; the geometry
+ * arrays (as in ofp_locate_hits) stay owned by the caller and must outlive it.  use_graph = 0 issues the same
+ * launches eagerly (A/B). */
+int ofp_rt_create(ofp_rt **out, int32_t n_streams, const ofp_detector_params *p, const double *sensor_xyz_dev,
+                  int32_t n_sensors, const float *lag_maps_dev, int32_t map_size, const float *max_lags_dev,
+                  const float *min_lags_dev, const float *max_max_dev, double radius_cm, double samples_per_cm,
+                  double sr, double c_cm_s, int32_t use_graph);
+int ofp_rt_reset(ofp_rt *rt);
+int ofp_rt_destroy(ofp_rt *rt);
+/* One block for every stream: blocks [S, B, C] float32 in host (blocks_on_host = 1, pinned for an asynchronous
+ * copy) or device memory, stream s at blocks + s*stream_stride elements (0 = dense).  Returns when the results
+ * are on the host: xy_host [S, 2] float64 (NaN = nothing located), found_host [S] (1 located, 0 nothing,
+ * -1 a group list overflowed); either may be NULL (read them through ofp_rt_results instead). */
+int ofp_rt_step(ofp_rt *rt, const float *blocks, int32_t blocks_on_host, int64_t stream_stride, double *xy_host,
+                int32_t *found_host);
+int ofp_rt_results(ofp_rt *rt, const double **xy_host, const int32_t **found_host);
+
+/* ---------------------------------------------------------------------------------------
  * K6  onset-window network inference -- replaces model.CNN.forward in eval mode (model.py:52-120):
  *     n_layers x [Conv1d(kernel_size, padding; stride 1, dilation 1, groups 1) + activation],
  *     flatten (channel-major), Dropout = identity, Linear(flat, out_size).

@@ -378,6 +378,7 @@ struct SlArgs {
     int32_t n_streams, C;
     const int32_t *det_ch, *det_delta, *det_cnt;  // [S, C], [S, C], [S]: K1's per-block output
     int64_t current_index;    // sample index of the block start
+    const int64_t *current_index_dev = nullptr;  // when set: read from device memory instead (graph replay)
     int32_t *g_count;         // [S]
     int32_t *g_len;           // [S, GMAX]
     int32_t *g_sensor;        // [S, GMAX, LEN]
@@ -398,6 +399,7 @@ __global__ void k5_stream_locate(const SlArgs a) {
     if (st >= a.n_streams) return;
     const K5Args &geo = a.geo;
     const int S = geo.S, Hm = geo.Hm;
+    const long long cur_index = a.current_index_dev ? *a.current_index_dev : a.current_index;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     double out[2] = {nan, nan};
     int found = 0;
@@ -417,7 +419,7 @@ __global__ void k5_stream_locate(const SlArgs a) {
     int ng = a.g_count[st];
     for (int di = 0; di < nd && !found; ++di) {
         int sensor = a.det_ch[static_cast<int64_t>(st) * a.C + ord[di]];
-        long long onset = a.current_index + a.det_delta[static_cast<int64_t>(st) * a.C + ord[di]];
+        long long onset = cur_index + a.det_delta[static_cast<int64_t>(st) * a.C + ord[di]];
         // ---- Multilaterate3D.locate(sensor, onset) ----
         SlGroup ngp[SL_GMAX];  // new_groups
         int nn = 0;
@@ -560,6 +562,39 @@ extern "C" int ofp_stream_locate(const double *sensor_xyz_dev, int32_t n_sensors
     a.g_len = state_len_dev; a.g_sensor = state_sensor_dev; a.g_onset = state_onset_dev; a.xy = xy_dev;
     a.found = found_dev;
     k5_stream_locate<<<(n_streams + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+__global__ void k_advance_index(int64_t *idx, int64_t by) { *idx += by; }
+
+// ofp_stream_locate with the block's start index read from device memory and advanced by `advance` samples
+// afterwards: the form a CUDA graph can replay (kernel arguments are baked into a captured graph).
+extern "C" int ofp_stream_locate_dev(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                                     int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                                     const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                                     double c_cm_s, int32_t n_streams, int32_t n_channels,
+                                     const int32_t *det_channel_dev, const int32_t *det_delta_dev,
+                                     const int32_t *det_count_dev, int64_t *current_index_dev, int32_t advance,
+                                     int32_t *state_count_dev, int32_t *state_len_dev, int32_t *state_sensor_dev,
+                                     int64_t *state_onset_dev, double *xy_dev, int32_t *found_dev, void *stream) {
+    OFP_REQUIRE(sensor_xyz_dev && lag_maps_dev && max_lags_dev && min_lags_dev && max_max_dev && det_channel_dev &&
+                    det_delta_dev && det_count_dev && state_count_dev && state_len_dev && state_sensor_dev &&
+                    state_onset_dev && xy_dev && found_dev && current_index_dev, "null argument");
+    OFP_REQUIRE(n_sensors >= 3 && n_channels >= 1 && n_channels <= 32, "bad sensor / channel count");
+    if (n_streams == 0) return OFP_OK;
+    SlArgs a;
+    a.geo.locs = sensor_xyz_dev; a.geo.maps = lag_maps_dev; a.geo.max_lags = max_lags_dev;
+    a.geo.min_lags = min_lags_dev; a.geo.max_max = max_max_dev; a.geo.S = n_sensors; a.geo.Hm = map_size;
+    a.geo.H = 0; a.geo.n_per_hit = 3; a.geo.radius = radius_cm; a.geo.samples_per_cm = samples_per_cm;
+    a.geo.sr = sr; a.geo.c_cm = c_cm_s; a.geo.sensors = nullptr; a.geo.onsets = nullptr; a.geo.onset_stride = 0;
+    a.geo.xy = nullptr; a.geo.status = nullptr;
+    a.n_streams = n_streams; a.C = n_channels; a.det_ch = det_channel_dev; a.det_delta = det_delta_dev;
+    a.det_cnt = det_count_dev; a.current_index = 0; a.current_index_dev = current_index_dev;
+    a.g_count = state_count_dev; a.g_len = state_len_dev; a.g_sensor = state_sensor_dev; a.g_onset = state_onset_dev;
+    a.xy = xy_dev; a.found = found_dev;
+    k5_stream_locate<<<(n_streams + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    k_advance_index<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(current_index_dev, advance);
     OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;
 }

@@ -158,3 +158,69 @@ class StreamLocatorBatch:
         xy, found = self.locate_detections(ch, dl, cnt)
         self.current_index += self.blocksize
         return xy, found
+
+
+class RealtimeSession:
+    """``StreamLocatorBatch.detect_hits`` as one replayed CUDA graph per block (csrc/realtime.cu): the native
+    session owns the detector, the locate state machines, the staging and result buffers; a step is one
+    asynchronous copy of the block, one ``cudaGraphLaunch`` and one stream synchronisation, and returns
+    ``(xy [S, 2] float64, found [S] int32)`` as numpy arrays on the host.  Same results as
+    ``StreamLocatorBatch`` block by block (tests/test_gpu_stream_locate.py)."""
+
+    def __init__(self, n_streams: int, ml_conf: dict, n_channels: int = config.N_CHANNELS,
+                 blocksize: int = config.BLOCKSIZE, detector_kw: dict | None = None, use_graph: bool = True):
+        import ctypes as C
+
+        from .. import _lib
+        from .._lib import ptr
+
+        kw = dict(REALTIME_DETECTOR)
+        kw.update(detector_kw or {})
+        self.torch = _lib.require_cuda()
+        self.S, self.C, self.blocksize = n_streams, n_channels, blocksize
+        self.m = m = multilateration.Multilaterate3D(sensor_locations=ml_conf["sensor_locations"], sr=kw["sr"],
+                                                     medium=ml_conf["medium"], c=ml_conf.get("c"))
+        self._params = detection.make_params(n_channels, blocksize, **kw)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().ofp_rt_create(C.byref(self._h), C.c_int32(n_streams), C.byref(self._params), ptr(m._locs),
+                                            C.c_int32(m._S), ptr(m._maps), C.c_int32(m._M), ptr(m._mx), ptr(m._mn),
+                                            ptr(m._mm), C.c_double(m.radius), C.c_double(m.samples_per_cm),
+                                            C.c_double(m.sr), C.c_double(m.c), C.c_int32(int(use_graph))))
+        self.xy = np.empty((n_streams, 2), np.float64)
+        self.found = np.empty((n_streams,), np.int32)
+        self.current_index = 0
+
+    def reset(self):
+        from .. import _lib
+
+        _lib.check(_lib.lib().ofp_rt_reset(self._h))
+        self.current_index = 0
+
+    def detect_hits(self, blocks):
+        """blocks [S, B, C] float32: a device tensor (may be a window into longer per-stream buffers) or a
+        C-contiguous numpy array / pinned host tensor."""
+        import ctypes as C
+
+        from .. import _lib
+
+        if isinstance(blocks, np.ndarray):
+            assert blocks.dtype == np.float32 and blocks.flags.c_contiguous and blocks.shape == (self.S, self.blocksize, self.C)
+            p, on_host, stride = blocks.ctypes.data_as(C.c_void_p), 1, 0
+        else:
+            assert blocks.dtype == self.torch.float32 and tuple(blocks.shape) == (self.S, self.blocksize, self.C)
+            assert blocks.stride(2) == 1 and blocks.stride(1) == self.C
+            p, on_host, stride = C.c_void_p(blocks.data_ptr()), int(not blocks.is_cuda), blocks.stride(0)
+        _lib.check(_lib.lib().ofp_rt_step(self._h, p, C.c_int32(on_host), C.c_int64(stride),
+                                          self.xy.ctypes.data_as(C.c_void_p), self.found.ctypes.data_as(C.c_void_p)))
+        self.current_index += self.blocksize
+        return self.xy, self.found
+
+    def __del__(self):
+        try:
+            from .. import _lib
+
+            if self._h:
+                _lib.lib().ofp_rt_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

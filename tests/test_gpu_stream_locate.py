@@ -65,3 +65,29 @@ def test_detect_hits_batch_matches_single_stream_locator():
                 assert (s, b) not in got
             else:
                 assert np.array_equal(got[(s, b)], np.asarray([r.x, r.y]))
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_realtime_session_graph_equals_python_path(use_graph):
+    """The native session (csrc/realtime.cu: one replayed CUDA graph per block) gives, block by block, exactly
+    what StreamLocatorBatch.detect_hits gives; device windows, numpy blocks and a reset in between."""
+    from onset_fingerprinting_b200.realtime.audio import RealtimeSession, StreamLocatorBatch
+
+    S, nblk = 37, 500
+    xs, _ = synth.drum_batch(S, seconds=nblk * 128 / 96000, seed=78, first_hit=9000)
+    xs = np.ascontiguousarray(xs[:, : nblk * 128])
+    xd = torch.from_numpy(xs).cuda()
+    sl = StreamLocatorBatch(S, ML_CONF)
+    rs = RealtimeSession(S, ML_CONF, use_graph=use_graph)
+    for attempt in range(2):
+        n_loc = 0
+        for b in range(nblk):
+            want_xy, want_f = sl.detect_hits(xd[:, b * 128:(b + 1) * 128])
+            blk = xd[:, b * 128:(b + 1) * 128] if b % 2 else np.ascontiguousarray(xs[:, b * 128:(b + 1) * 128])
+            xy, f = rs.detect_hits(blk)
+            want_xy, want_f = want_xy.cpu().numpy(), want_f.cpu().numpy()
+            assert np.array_equal(f, want_f), (attempt, b)
+            assert np.array_equal(np.isnan(xy), np.isnan(want_xy)) and np.array_equal(np.nan_to_num(xy), np.nan_to_num(want_xy))
+            n_loc += int((f == 1).sum())
+        assert n_loc >= S  # every stream locates at least one hit on average
+        sl.reset(); rs.reset()
