@@ -231,7 +231,7 @@ def run_ours(args):
             # fixed-capacity blocks: no host round trip for counts inside the step (H is already on the host)
             cap_h = last.setdefault("gather_capacity", int(recs.shape[0] * 1.05) + 1024)
             if recs.shape[0] <= cap_h:
-                last["all_records"] = parallel.gather_records_padded(recs, cap_h)
+                last["all_records"] = parallel.gather_records_padded(recs, cap_h, work=last.setdefault("gather_work", {}))
             else:
                 last["all_records"] = parallel.gather_records(recs)
 

@@ -56,22 +56,36 @@ def gather_records(records: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([b[:c] for b, c in zip(blocks, counts)], 0)
 
 
-def gather_records_padded(records: torch.Tensor, capacity: int, group=None):
+def gather_records_padded(records: torch.Tensor, capacity: int, group=None, work: dict | None = None):
     """Sync-free variant for a hot loop: every rank contributes a block padded to a fixed `capacity` rows, so
     neither the counts nor the payload need a host round trip.  Returns (blocks [world, capacity, width],
-    counts [world] int64, both on the device); `compact_gathered` turns them into the concatenated table when
-    a consumer needs it.  records.shape[0] must not exceed capacity (checked by the caller, who knows H)."""
+    counts [world] int64, both on the device; rows past a rank's count are unspecified); `compact_gathered`
+    turns them into the concatenated table when a consumer needs it.  records.shape[0] must not exceed
+    capacity (checked by the caller, who knows H).  `work` keeps the send / receive buffers between calls."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     width = records.shape[1]
-    padded = torch.zeros((capacity, width), dtype=records.dtype, device=records.device)
-    padded[: records.shape[0]] = records
-    n = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
+    work = {} if work is None else work
+    key = (capacity, width, records.dtype, records.device, world)
+    if work.get("key") != key:
+        work.clear()
+        work["key"] = key
+        work["send"] = torch.empty((capacity, width), dtype=records.dtype, device=records.device)
+        work["blocks"] = torch.empty((world, capacity, width), dtype=records.dtype, device=records.device)
+        work["counts"] = torch.empty((world,), dtype=torch.int64, device=records.device)
+        work["n"] = torch.empty((1,), dtype=torch.int64, device=records.device)
+    send, blocks, counts, n = work["send"], work["blocks"], work["counts"], work["n"]
+    send[: records.shape[0]] = records
+    n.fill_(records.shape[0])
     if world == 1:
-        return padded[None], n
-    blocks = torch.empty((world, capacity, width), dtype=records.dtype, device=records.device)
-    counts = torch.empty((world,), dtype=torch.int64, device=records.device)
-    dist.all_gather(list(blocks.unbind(0)), padded, group=group)
-    dist.all_gather(list(counts.split(1)), n, group=group)
+        blocks[0] = send
+        counts.copy_(n)
+        return blocks, counts
+    try:
+        dist.all_gather_into_tensor(blocks.view(world * capacity, width), send, group=group)
+        dist.all_gather_into_tensor(counts, n, group=group)
+    except (RuntimeError, NotImplementedError):  # a backend without the flat collective
+        dist.all_gather(list(blocks.unbind(0)), send, group=group)
+        dist.all_gather(list(counts.split(1)), n, group=group)
     return blocks, counts
 
 
