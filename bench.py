@@ -282,7 +282,7 @@ def run_ours(args):
             s_post.wait_event(k1_done[i])
             ch_, ix_, cnt_, rel_ = k1_out.pop(i)
             hit_rec, hit_on, _ = detection.find_onset_groups_batch(ch_, ix_, cnt_, N_CH, **hp.group_kw)
-            fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on, max_section=1000 + 2 * 40 + 1)
+            fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on)
             xy, lstat = hp.ml.locate_batch(fixed)
             last["hits"] = pipeline.HitBatch(hit_rec, hit_on, fixed, lags, fstat, xy, lstat, cnt_, rel_)
             gather(last["hits"])

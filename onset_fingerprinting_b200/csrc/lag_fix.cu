@@ -101,7 +101,10 @@ struct PairArgs {
 namespace t64 { constexpr int K4_THREADS = 64, K4_MINCTA = 8, K4_LPF = OFP_K4_SMALL_LPF;
 #include "lag_fix_body.cuh"
 }
-namespace t128 { constexpr int K4_THREADS = 128, K4_MINCTA = 4, K4_LPF = OFP_K4_SMALL_LPF;
+#ifndef OFP_K4_T128_MINCTA
+#define OFP_K4_T128_MINCTA 8
+#endif
+namespace t128 { constexpr int K4_THREADS = 128, K4_MINCTA = OFP_K4_T128_MINCTA, K4_LPF = OFP_K4_SMALL_LPF;
 #include "lag_fix_body.cuh"
 }
 namespace t192 { constexpr int K4_THREADS = K4_MAX_THREADS, K4_MINCTA = OFP_K4_MINCTA, K4_LPF = LPF;

@@ -479,11 +479,9 @@ def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 
     look = normalization_cutoff + onset_tolerance
     if max_section is None:
         span = 0
-        if H:
-            complete = (hit_onsets >= 0).all(1)
-            if bool(complete.any()):
-                rows = hit_onsets[complete]
-                span = int((rows.max(1).values - rows.min(1).values).max().item())
+        if H:  # largest onset spread over the complete groups: one small reduction, one host round trip
+            mn, mx = hit_onsets.min(1).values, hit_onsets.max(1).values
+            span = int(torch.where(mn >= 0, mx - mn, torch.zeros_like(mx)).max().item())
         max_section = N if to_end else span + 2 * look + 1
         # shared-memory budget of one CTA; longer sections are flagged OFP_FIX_TOO_LONG
         budget = (200 * 1024 - 128) // (16 + 8 * Cn)

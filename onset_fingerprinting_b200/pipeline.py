@@ -59,9 +59,8 @@ class HotPath:
         self.det.reset()
         ch, ix, cnt, rel = self.det.detect_offline(x, warm_n, out=self._out)
         hit_rec, hit_on, _ = detection.find_onset_groups_batch(ch, ix, cnt, C, **self.group_kw)
-        # fix_onsets needs every channel of a group (the reference indexes audio with the -1 otherwise)
-        look = self.fix_kw.get("normalization_cutoff", 10) + self.fix_kw.get("onset_tolerance", 30)
-        max_section = self.group_kw["max_distance"] + 2 * look + 1
-        fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on, max_section=max_section, **self.fix_kw)
+        # sections are sized by the largest onset spread actually present (one tiny reduction + host round
+        # trip): the shared memory of a K4 CTA -- and with it how many hits an SM works on -- follows it
+        fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on, **self.fix_kw)
         xy, lstat = self.ml.locate_batch(fixed)
         return HitBatch(hit_rec, hit_on, fixed, lags, fstat, xy, lstat, cnt, rel)
