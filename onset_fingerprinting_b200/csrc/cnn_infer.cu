@@ -266,7 +266,7 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
     // odd multiple-of-nothing row stride is fine (all accesses are 32 consecutive words); room for the halo
     a.row_stride = 32 * P + 2 * padding + kernel_size + 1;
     // Tensor-core path for the reference's default shape: [C0 -> 8 -> 16], k = 3, padding 1, SiLU, <= 4 outputs
-    static const bool no_tc = getenv("OFP_K6_NO_TC") != nullptr;
+    const bool no_tc = getenv("OFP_K6_NO_TC") != nullptr;  // read per call: tests compare both kernels in one process
     if (!no_tc && n_layers == 2 && kernel_size == 3 && padding == 1 && activation == 0 && out_size <= 4 &&
         layer_sizes_host[0] == K6T_C1 && layer_sizes_host[1] == K6T_C2 && input_size % 16 == 0 && channels <= 8) {
         const int n_w1 = channels * 24 + 8;

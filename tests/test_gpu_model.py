@@ -147,3 +147,24 @@ def test_session_file_to_windows_to_network(tmp_path):
     net = model.CNN(256, 2).cuda()
     out = net(x)
     assert tuple(out.shape) == (int(ok.sum()), 2) and bool(torch.isfinite(out).all())
+
+
+def test_cnn_large_batch_properties(monkeypatch):
+    """200 k windows (beyond what the torch reference is run on here): the tensor-core path and the generic FP32
+    kernel agree to float32 accuracy, the result does not depend on the batch a window travels in, and it is
+    deterministic."""
+    from onset_fingerprinting_b200 import model
+
+    torch.manual_seed(11)
+    net = model.CNN(256, 2).cuda()
+    x = torch.randn(200_000, 3, 256, device="cuda") * 0.2
+    y_tc = net(x)
+    assert torch.equal(y_tc, net(x))
+    monkeypatch.setenv("OFP_K6_NO_TC", "1")
+    y_fp = net(x)
+    monkeypatch.delenv("OFP_K6_NO_TC")
+    scale = float(y_fp.abs().max())
+    assert float((y_tc - y_fp).abs().max()) <= 1e-4 * scale
+    perm = torch.randperm(x.shape[0], device="cuda")
+    assert torch.equal(net(x[perm]), y_tc[perm])
+    assert torch.equal(net(x[1234:1234 + 777]), y_tc[1234:1234 + 777])

@@ -57,3 +57,28 @@ def test_detect_onsets_spectral_restatement():
     assert len(peaks) >= 5
     assert all(np.abs(arr - p).min() < 300 for p in peaks)
     assert peaks.tolist() == peaks_o.tolist()
+
+
+def test_flux_properties_large_batch():
+    """BASELINE-size properties the numpy restatement is too slow to check: per-recording independence of the
+    batch, determinism, hop-shift equivariance (delaying a recording by k hops delays its flux by k frames
+    once the 2048-sample window no longer sees the inserted silence boundary differently), silence -> 0."""
+    from onset_fingerprinting_b200 import spectral
+
+    R, N, hop = 64, 96000, 128
+    x = synth.drum_batch_device(R, N, seed=77)
+    f = spectral.spectral_flux_batch(x, 2048, hop)
+    assert tuple(f.shape) == (R, N // hop) and bool(torch.isfinite(f).all())
+    assert torch.equal(f, spectral.spectral_flux_batch(x, 2048, hop))
+    assert torch.equal(spectral.spectral_flux_batch(x[5:9].contiguous(), 2048, hop), f[5:9])
+    k = 37
+    xs = torch.zeros_like(x)
+    xs[:, k * hop:] = x[:, : N - k * hop]
+    fs = spectral.spectral_flux_batch(xs, 2048, hop)
+    # frame j of the delayed signal sees the same 2048 samples as frame j - k of the original wherever both windows
+    # lie inside the recording or inside leading zeros; the synthetic recordings start with 0.5 s of noise, so compare
+    # bitwise only where the original frame index is past the zero padding of the original (j - k >= 16)
+    a, b = fs[:, k + 16:], f[:, 16: N // hop - k]
+    assert torch.equal(a, b)
+    z = spectral.spectral_flux_batch(torch.zeros(2, 8192, 3, device="cuda"), 2048, hop)
+    assert float(z.abs().max()) == 0.0
