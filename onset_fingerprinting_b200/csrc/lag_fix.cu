@@ -98,7 +98,13 @@ struct PairArgs {
 #endif
 // lags per thread in the float32 screening (tunable per CTA size; measured 1 / 3 / 5 / 9 on 3-channel hits:
 // 8.13-8.18 ms for 380 k hits, no difference -- those hits are barrier / latency bound, scripts/ncu_lines.py)
-namespace t64 { constexpr int K4_THREADS = 64, K4_MINCTA = 8, K4_LPF = OFP_K4_SMALL_LPF;
+namespace t32 { constexpr int K4_THREADS = 32, K4_MINCTA = 32, K4_LPF = OFP_K4_SMALL_LPF;
+#include "lag_fix_body.cuh"
+}
+#ifndef OFP_K4_T64_MINCTA
+#define OFP_K4_T64_MINCTA 16
+#endif
+namespace t64 { constexpr int K4_THREADS = 64, K4_MINCTA = OFP_K4_T64_MINCTA, K4_LPF = OFP_K4_SMALL_LPF;
 #include "lag_fix_body.cuh"
 }
 #ifndef OFP_K4_T128_MINCTA
@@ -188,10 +194,14 @@ int ofp_cc_screen_stats(uint64_t *stats4_host, int32_t reset) {
     return OFP_OK;
 }
 
-int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section) {
-    const size_t cc = (static_cast<size_t>(max_section) + 2 * XPAD + max_section + 16 + K4_MAX_THREADS * LPF) * sizeof(float) +
+static int fix_smem_bytes(int32_t n_channels, int32_t max_section, int threads) {
+    const size_t cc = (static_cast<size_t>(max_section) + 2 * XPAD + max_section + 16 + threads * LPF) * sizeof(float) +
                       (CAND_CAP + 1) * sizeof(int);
     return static_cast<int>(2 * (max_section + 16) * sizeof(double) + static_cast<size_t>(max_section) * n_channels * sizeof(float) + cc);
+}
+// upper bound over the CTA sizes a launch may pick
+int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section) {
+    return fix_smem_bytes(n_channels, max_section, K4_MAX_THREADS);
 }
 
 int ofp_fix_onsets(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
@@ -221,15 +231,22 @@ int ofp_fix_onsets_ex(const float *audio_dev, int64_t n_samples, int64_t rec_str
     a.fp = FixParams{filter_size, d, direction, take_abs, zero_left, cutoff, tol, shift, flags & 1};
     a.out_onsets = out_onsets_dev; a.out_lags = out_lags_dev; a.out_status = out_status_dev;
     { const char *e = getenv("OFP_K4_SCREEN"); a.screen = e ? atoi(e) : 1; }
-    const int smem = ofp_fix_onsets_smem_bytes(n_channels, max_section);
+    // CTA size by the work a hit carries: 16-channel sections feed 192 threads; a 3-channel hit (60-lag windows
+    // over ~300 samples) is barrier / latency bound and runs best as ONE WARP per hit at 32 CTAs per SM
+    // (380 k hits: 8.0 ms with 128 threads and the worst-case section size, 5.7 / 4.2 / 3.1 ms with 128 / 64 / 32
+    // threads once the section is sized by the data).  The float32 screening needs 2 tol lags <= 9 per thread.
+    // OFP_K4_SMALL forces the size used below the 192-thread threshold (A/B runs).
+    static const int small = getenv("OFP_K4_SMALL") ? atoi(getenv("OFP_K4_SMALL")) : 0;
+    const int64_t work = static_cast<int64_t>(n_channels) * max_section;
+    int threads = work >= 4096 ? K4_MAX_THREADS : (work > 1536 ? 64 : 32);
+    if (small > 0 && threads != K4_MAX_THREADS) threads = small <= 32 ? 32 : (small <= 64 ? 64 : 128);
+    while (threads < 128 && 2 * tol > threads * LPF) threads *= 2;
+    if (threads > 128) threads = K4_MAX_THREADS;
+    auto kern = threads == K4_MAX_THREADS ? t192::k4_fix
+                                          : (threads == 32 ? t32::k4_fix : (threads == 64 ? t64::k4_fix : t128::k4_fix));
+    const int smem = fix_smem_bytes(n_channels, max_section, threads);  // the partial-sum buffer follows the CTA size
     OFP_REQUIRE(smem <= 220 * 1024, "max_section %d x %d channels needs %d bytes of shared memory", max_section,
                 n_channels, smem);
-    // CTA size by the work a hit carries: 16-channel sections feed 192 threads, 3-channel ones (60-lag windows
-    // over ~200 samples) only 64-128.  OFP_K4_SMALL overrides the small size for A/B runs.
-    static const int small = getenv("OFP_K4_SMALL") ? atoi(getenv("OFP_K4_SMALL")) : 128;
-    const int64_t work = static_cast<int64_t>(n_channels) * max_section;
-    const int threads = work >= 4096 ? K4_MAX_THREADS : (small <= 64 ? 64 : 128);
-    auto kern = threads == K4_MAX_THREADS ? t192::k4_fix : (threads == 64 ? t64::k4_fix : t128::k4_fix);
     OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kern<<<n_hits, threads, smem, static_cast<cudaStream_t>(stream)>>>(a);
     OFP_CUDA_CHECK(cudaGetLastError());

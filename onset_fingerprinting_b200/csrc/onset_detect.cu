@@ -537,7 +537,10 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     }
 }
 
-constexpr int KU = 8;  // samples per straight-line chunk of the single-warp kernel
+#ifndef OFP_K1_KU
+#define OFP_K1_KU 8
+#endif
+constexpr int KU = OFP_K1_KU;  // samples per straight-line chunk of the single-warp kernel
 
 template <bool USE_HP, bool USE_TMA, bool HP_SYM>
 __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {

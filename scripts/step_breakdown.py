@@ -19,7 +19,7 @@ for rep in range(3):
     det.reset(); ev[1].record(); wall.append(time.perf_counter())
     ch, ix, cnt, rel = det.detect_offline(x, 48000, out=hp._out); ev[2].record(); wall.append(time.perf_counter())
     hit_rec, hit_on, _ = detection.find_onset_groups_batch(ch, ix, cnt, 3, **hp.group_kw); ev[3].record(); wall.append(time.perf_counter())
-    ms = None if os.environ.get("AUTO_SECTION") else 1081
+    ms = 1081 if os.environ.get("FIXED_SECTION") else None  # None: sized by the largest onset spread (pipeline default)
     fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on, max_section=ms); ev[4].record(); wall.append(time.perf_counter())
     xy, lstat = hp.ml.locate_batch(fixed); ev[5].record(); wall.append(time.perf_counter())
     torch.cuda.synchronize()
