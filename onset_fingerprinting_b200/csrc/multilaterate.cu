@@ -289,7 +289,10 @@ struct K5Args {
                                  // Multilaterate3D.model (multilateration.py:553-557) are written instead
 };
 
-__global__ void k5_locate(const K5Args a) {
+#ifndef OFP_K5_MINCTA
+#define OFP_K5_MINCTA 8
+#endif
+__global__ void __launch_bounds__(128, OFP_K5_MINCTA) k5_locate(const K5Args a) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= a.H) return;
     const int S = a.S, Hm = a.Hm;
