@@ -168,3 +168,18 @@ def test_cnn_large_batch_properties(monkeypatch):
     perm = torch.randperm(x.shape[0], device="cuda")
     assert torch.equal(net(x[perm]), y_tc[perm])
     assert torch.equal(net(x[1234:1234 + 777]), y_tc[1234:1234 + 777])
+
+
+def test_chunked_host_pipeline_equals_direct_call():
+    """hostpipe.run_chunked (uploads overlapped with compute on two streams, pinned results) returns exactly
+    what one call on the whole batch returns; ragged last chunk, buffer reuse."""
+    from onset_fingerprinting_b200 import hostpipe, model
+
+    torch.manual_seed(2)
+    net = model.CNN(256, 2).cuda()
+    xh = torch.randn(1003, 3, 256).pin_memory()
+    want = net(xh.cuda()).cpu()
+    (got,) = hostpipe.run_chunked([xh], net, chunk=128)
+    assert torch.equal(got, want)
+    (again,) = hostpipe.run_chunked([xh], net, chunk=400, outs=(got,))
+    assert again.data_ptr() == got.data_ptr() and torch.equal(again, want)
