@@ -77,23 +77,19 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
 struct K2WSmem {
     float2 win2[K2W_H];                   // window pairs (w[2n], w[2n+1])
     float2 T[32 * 32];                    // T[k2][n1] = exp(-2 pi i n1 k2 / 1024)
-    float2 T2[32 * 32];                   // T2[k1][l] = exp(-2 pi i (32 k1 + l) / 2048)
+    float2 T2[16 * 32];                   // T2[k1][l] = exp(-2 pi i (32 k1 + l) / 2048), k1 < 16 (lower half of the bins)
     float2 tile[K2W_WARPS][32 * K2W_PAD]; // warp-private transpose tiles
     // followed by the channel-mean buffer: float mono[K2W_WARPS * K2W_FRAMES * hop + 2048]
 };
 
-// bin value from Z[k] and its partner Z[1024 - k]
+// Per-bin value from FOUR TIMES the power 4|X|^2 (the split below never forms X/2): mode 0 works on
+// s' = 10 log10(max(4e-10, 4 p)) = s + 6.02 dB -- the constant cancels in the frame difference and in the top_db
+// clamp; mode 1 on sqrt(4 p) * (weight / 2).
 template <int MODE>
-__device__ __forceinline__ float k2w_bin(float2 zk, float2 zc, float2 w, float wt) {
-    const float ex = zk.x + zc.x, ey = zk.y - zc.y;  // 2 e
-    const float ox = zk.y + zc.y, oy = zc.x - zk.x;  // 2 o
-    const float re = 0.5f * (ex + (ox * w.x - oy * w.y));
-    const float im = 0.5f * (ey + (ox * w.y + oy * w.x));
-    const float p = re * re + im * im;
-    if (MODE == 0) return 3.0102999566398120f * __log2f(fmaxf(1e-10f, p));  // 10 log10 p
-    return sqrtf(p) * wt;
+__device__ __forceinline__ float k2w_val(float p4, float half_wt) {
+    if (MODE == 0) return 3.0102999566398120f * __log2f(fmaxf(4e-10f, p4));
+    return sqrtf(p4) * half_wt;
 }
-
 
 // Channel mean of samples [fs0, fs0 + span) of one recording into shared memory (zeros outside the
 // recording, numpy 'reflect' padding for a centred transform).  3-channel audio, the configs[1..4]
@@ -154,7 +150,7 @@ __device__ __forceinline__ void k2_fill_mono(const K2Args &a, const float *__res
     for (int i = (groups << 2) + tid; i < span; i += NT) scalar(i);
 }
 
-template <int MODE>
+template <int MODE, bool TOPDB>
 __global__ void __launch_bounds__(K2W_WARPS * 32, OFP_K2W_MINCTA) k2_flux_warp(const K2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     K2WSmem &sm = *reinterpret_cast<K2WSmem *>(smem_raw);
@@ -170,8 +166,10 @@ __global__ void __launch_bounds__(K2W_WARPS * 32, OFP_K2W_MINCTA) k2_flux_warp(c
         float s, c;
         sincospif(-2.0f * static_cast<float>((n1 * k2) & (H - 1)) / static_cast<float>(H), &s, &c);
         sm.T[i] = make_float2(c, s);
-        sincospif(-2.0f * static_cast<float>(i) / static_cast<float>(N), &s, &c);
-        sm.T2[i] = make_float2(c, s);
+        if (i < 16 * 32) {
+            sincospif(-2.0f * static_cast<float>(i) / static_cast<float>(N), &s, &c);
+            sm.T2[i] = make_float2(c, s);
+        }
     }
     const int j0 = blockIdx.x * (K2W_WARPS * K2W_FRAMES);
     const int j1 = min(j0 + K2W_WARPS * K2W_FRAMES, a.n_frames);
@@ -191,7 +189,7 @@ __global__ void __launch_bounds__(K2W_WARPS * 32, OFP_K2W_MINCTA) k2_flux_warp(c
     float prevS[33], curS[33];
     for (int j = jw0 - 1; j < jw1; ++j) {
         if (j < 0) {
-            const float s0 = MODE == 0 ? 3.0102999566398120f * __log2f(1e-10f) : 0.0f;
+            const float s0 = MODE == 0 ? 3.0102999566398120f * __log2f(4e-10f) : 0.0f;
 #pragma unroll
             for (int k = 0; k < 33; ++k) prevS[k] = s0;
             continue;
@@ -219,46 +217,50 @@ __global__ void __launch_bounds__(K2W_WARPS * 32, OFP_K2W_MINCTA) k2_flux_warp(c
             __syncwarp();
             fft32(v);
         }
-        // ---- real-input split + per-bin value; Z[32 k1 + lane] = v[brev5(k1)] ----
+        // ---- real-input split, a PAIR of bins per step; Z[32 k1 + lane] = v[brev5(k1)] ----
+        // With E2 = Z[k] + conj Z[H-k], O2 = (Z[k] - conj Z[H-k]) / i and T = W^k O2:
+        //   2 X[k] = E2 + T,   2 X[H-k] = conj(E2 - T)
+        // so one evaluation of (E2, T) gives bins k and H - k.  A lane owns k = 32 k1 + lane for k1 < 16 (its
+        // lower 16 registers) together with their mirrors H - k, whose Z values are the upper registers of lane
+        // 32 - lane: one shuffle per word of the upper half only.  Lane 0 mirrors onto its own registers
+        // (k1 = 0 pairs bin 0 with the Nyquist bin) and also owns the self-paired bin H/2.
         float pmax = -INFINITY;
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {
-            const int m = 31 - k1;
-            const float2 za = v[brev5(k1)], zb = v[brev5(m)];
-            float2 pa, pb;
-            pa.x = __shfl_sync(0xffffffffu, zb.x, partner);
-            pa.y = __shfl_sync(0xffffffffu, zb.y, partner);
-            pb.x = __shfl_sync(0xffffffffu, za.x, partner);
-            pb.y = __shfl_sync(0xffffffffu, za.y, partner);
-            if (l0) {
-                pa = v[brev5((32 - k1) & 31)];
-                pb = v[brev5(k1 + 1)];
-            }
-            const int ka = 32 * k1 + lane, kb = 32 * m + lane;
-            const float wa = (MODE == 1 && a.weight) ? a.weight[ka] : 1.0f;
-            const float wb = (MODE == 1 && a.weight) ? a.weight[kb] : 1.0f;
-            curS[k1] = k2w_bin<MODE>(za, pa, sm.T2[ka], wa);
-            curS[m] = k2w_bin<MODE>(zb, pb, sm.T2[kb], wb);
-            pmax = fmaxf(pmax, fmaxf(curS[k1], curS[m]));
+            const float2 za = v[brev5(k1)], up = v[brev5(31 - k1)];
+            float2 pa;
+            pa.x = __shfl_sync(0xffffffffu, up.x, partner);
+            pa.y = __shfl_sync(0xffffffffu, up.y, partner);
+            if (l0) pa = v[brev5((32 - k1) & 31)];
+            const int ka = 32 * k1 + lane;
+            const float2 w = sm.T2[ka];
+            const float ex = za.x + pa.x, ey = za.y - pa.y, ox = za.y + pa.y, oy = pa.x - za.x;
+            const float tx = ox * w.x - oy * w.y, ty = ox * w.y + oy * w.x;
+            const float rx = ex + tx, ry = ey + ty, qx = ex - tx, qy = ey - ty;
+            const float ha = (MODE == 1) ? 0.5f * (a.weight ? a.weight[ka] : 1.0f) : 0.f;
+            const float hb = (MODE == 1) ? 0.5f * (a.weight ? a.weight[H - ka] : 1.0f) : 0.f;
+            curS[k1] = k2w_val<MODE>(rx * rx + ry * ry, ha);        // bin k
+            curS[16 + k1] = k2w_val<MODE>(qx * qx + qy * qy, hb);   // bin H - k
+            if (TOPDB) pmax = fmaxf(pmax, fmaxf(curS[k1], curS[16 + k1]));
         }
-        {   // Nyquist bin (lane 0 only): X[1024] = Re Z[0] - Im Z[0]
-            const float ny = v[0].x - v[0].y, p = ny * ny;
-            float sv;
-            if (MODE == 0) sv = 3.0102999566398120f * __log2f(fmaxf(1e-10f, p));
-            else sv = sqrtf(p) * (a.weight ? a.weight[H] : 1.0f);
-            curS[32] = sv;
-            if (l0) pmax = fmaxf(pmax, sv);
-        }
-        float lo = -INFINITY;
-        if (MODE == 0 && a.top_db > 0.f) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
-            lo = pmax - a.top_db;
+        {   // bin H/2 = conj Z[H/2] (lane 0, register 16)
+            const float2 zh = v[brev5(16)];
+            curS[32] = k2w_val<MODE>(4.0f * (zh.x * zh.x + zh.y * zh.y), (MODE == 1) ? 0.5f * (a.weight ? a.weight[H / 2] : 1.0f) : 0.f);
+            if (TOPDB && l0) pmax = fmaxf(pmax, curS[32]);
         }
         float acc = 0.f;
+        if (TOPDB) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) acc += fmaxf(0.f, fmaxf(curS[k], lo) - fmaxf(prevS[k], lo));
-        if (l0) acc += fmaxf(0.f, fmaxf(curS[32], lo) - fmaxf(prevS[32], lo));
+            for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+            const float lo = pmax - a.top_db;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc += fmaxf(0.f, fmaxf(curS[k], lo) - fmaxf(prevS[k], lo));
+            if (l0) acc += fmaxf(0.f, fmaxf(curS[32], lo) - fmaxf(prevS[32], lo));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc += fmaxf(0.f, curS[k] - prevS[k]);
+            if (l0) acc += fmaxf(0.f, curS[32] - prevS[32]);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (l0 && j >= jw0) a.flux[static_cast<int64_t>(r) * a.n_frames + j] = acc / static_cast<float>(H + 1);
