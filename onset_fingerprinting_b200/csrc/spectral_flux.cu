@@ -235,7 +235,7 @@ int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int6
     const int H = n_fft / 2;
     // 2048-point fast path (the realtime / config-5 shape): one warp per frame, transform in registers
     const size_t smem_w = sizeof(K2WSmem) + sizeof(float) * (static_cast<size_t>(K2W_WARPS * K2W_FRAMES) * hop + n_fft);
-    static const bool force_generic = getenv("OFP_K2_GENERIC") != nullptr;
+    const bool force_generic = getenv("OFP_K2_GENERIC") != nullptr;  // read per call: tests compare both kernels
     if (n_fft == 2 * K2W_H && hop % 2 == 0 && smem_w <= (227 * 1024) / OFP_K2W_MINCTA && !force_generic) {
         auto kern = mode == 0 ? (top_db > 0.f ? k2_flux_warp<0, true> : k2_flux_warp<0, false>) : k2_flux_warp<1, false>;
         OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_w)));

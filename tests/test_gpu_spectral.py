@@ -82,3 +82,32 @@ def test_flux_properties_large_batch():
     assert torch.equal(a, b)
     z = spectral.spectral_flux_batch(torch.zeros(2, 8192, 3, device="cuda"), 2048, hop)
     assert float(z.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+def test_warp_kernel_equals_generic_kernel_2048(channels, monkeypatch):
+    """The 2048-point warp-per-frame kernel against the generic Stockham kernel (validated against the numpy
+    restatement at other sizes) over the option space: channel counts (the 3-channel vector staging and its
+    scalar fallback), centred / reflected framing, both modes, top_db, hops, lengths that are no multiple of
+    anything, a strided batch view.  Same float32 FFT noise floor as the oracle comparison."""
+    from onset_fingerprinting_b200 import spectral
+
+    rng = np.random.default_rng(channels)
+    N = 30011
+    x = torch.from_numpy((rng.standard_normal((3, N, channels)) * 0.05).astype(np.float32)).cuda()
+    x[1, 9000:9400] += 0.8  # a loud burst: large dynamic range between bins
+    w = (0.5 + rng.random(1025)).astype(np.float32)
+    cases = [dict(center=False), dict(center=False, top_db=60.0), dict(center=True), dict(center=True, reflect=True),
+             dict(center=True, mode="magnitude", weight=w), dict(center=False, mode="magnitude")]
+    for hop in (128, 256, 130):
+        for kw in cases:
+            got = spectral.spectral_flux_batch(x, 2048, hop, **kw)
+            monkeypatch.setenv("OFP_K2_GENERIC", "1")
+            want = spectral.spectral_flux_batch(x, 2048, hop, **kw)
+            monkeypatch.delenv("OFP_K2_GENERIC")
+            assert got.shape == want.shape
+            tol = 3e-3 if kw.get("mode") != "magnitude" else 1e-4 * float(want.abs().max()) + 1e-6
+            assert torch.allclose(got, want, rtol=2e-3, atol=tol), (channels, hop, kw.keys(), float((got - want).abs().max()))
+    # a batch that is a strided view (every other recording of a larger buffer)
+    big = torch.from_numpy((rng.standard_normal((6, N, channels)) * 0.05).astype(np.float32)).cuda()
+    assert torch.equal(spectral.spectral_flux_batch(big[::2], 2048, 128), spectral.spectral_flux_batch(big[::2].contiguous(), 2048, 128))
