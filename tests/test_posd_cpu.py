@@ -58,3 +58,31 @@ def test_reads_pcm_files(tmp_path, bits):
     a, got_sr = posd.read_wav(tmp_path / "p.wav")
     assert got_sr == sr and a.shape == (n, c)
     assert np.allclose(a.reshape(-1), v / float(1 << (bits - 1)), atol=1e-7)
+
+
+def test_spec_example_session(tmp_path):
+    """The example session of the POSD draft (notebooks/dataset_spec_draft.org:333-397): its hits parse into the
+    table the reference's parse_hits builds (conditions unwrapped), and a file written from it reads back."""
+    example = {
+        "meta": {"channels": {"SP": {"location": [0.95, 0], "coordinate_system": "polar"},
+                              "OP": {"location": [0.95, 30], "coordinate_system": "polar"}},
+                 "instrument": "snare", "manufacturer": "sonor", "model": "BG SDW 2.0", "size": "13x5.75",
+                 "head_top": "ambassador", "head_bottom": "ambassador_ss", "rim": "triple-flange", "tuning": "low",
+                 "player": "rodrigo", "context": "full kit"},
+        "hits": [
+            {"i": 0, "zone": "center", "onset_start": [0, 2, 3], "velocity": 0.0, "isolated": True, "pitch": 220,
+             "conditions": {"wires": "on"}},
+            {"i": 1, "zone": "center", "onset_start": [48000, 4805, 47900], "velocity": 1.0, "isolated": True,
+             "pitch": 220, "conditions": {"wires": "on"}},
+            {"i": 2, "zone": "edge", "onset_start": [96000, 96000, 96000], "velocity": 0.0, "isolated": True,
+             "pitch": 219, "conditions": {"wires": "off"}},
+        ],
+    }
+    df = posd.parse_hits(example["hits"])
+    assert list(df.columns) == ["i", "zone", "onset_start", "velocity", "isolated", "pitch", "wires"]
+    assert list(df["wires"]) == ["on", "on", "off"] and df["onset_start"][1] == [48000, 4805, 47900]
+    (tmp_path / "session1.json").write_text(json.dumps(example))
+    posd.write_wav(tmp_path / "session1.wav", np.zeros((100, 3), np.float32), 48000)
+    audio, sr, onsets, loc, meta = posd.read_session(tmp_path, "session1")
+    assert sr == 48000 and audio.shape == (100, 3) and onsets.tolist() == [h["onset_start"] for h in example["hits"]]
+    assert np.isnan(loc).all() and meta["channels"]["OP"]["location"] == [0.95, 30]
