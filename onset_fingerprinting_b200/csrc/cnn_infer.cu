@@ -271,16 +271,16 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
         layer_sizes_host[0] == K6T_C1 && layer_sizes_host[1] == K6T_C2 && input_size % 16 == 0 && channels <= 8) {
         const int n_w1 = channels * 24 + 8;
         const size_t smem_tc = sizeof(float) * (((n_w1 + 3) & ~3) + static_cast<size_t>(out_size) * K6T_C2 * K6T_FCS +
-                                                static_cast<size_t>(K6_WARPS) * (channels + K6T_C1) * a.row_stride);
-        if (smem_tc <= 112 * 1024) {
+                                                static_cast<size_t>(K6T_WARPS) * (channels + K6T_C1) * a.row_stride);
+        if (smem_tc <= (226 * 1024) / OFP_K6T_MINCTA) {
             auto kt = P == 2 ? k6_cnn_tc<2> : (P == 4 ? k6_cnn_tc<4> : k6_cnn_tc<8>);
             OFP_CUDA_CHECK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_tc)));
             int per_sm = 0;
-            OFP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, K6_WARPS * 32, smem_tc));
+            OFP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kt, K6T_WARPS * 32, smem_tc));
             per_sm = std::max(per_sm, 1);
-            const int64_t want = (n_windows + K6_WARPS - 1) / K6_WARPS;
+            const int64_t want = (n_windows + K6T_WARPS - 1) / K6T_WARPS;
             const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
-            kt<<<grid, K6_WARPS * 32, smem_tc, static_cast<cudaStream_t>(stream)>>>(a);
+            kt<<<grid, K6T_WARPS * 32, smem_tc, static_cast<cudaStream_t>(stream)>>>(a);
             OFP_CUDA_CHECK(cudaGetLastError());
             return OFP_OK;
         }

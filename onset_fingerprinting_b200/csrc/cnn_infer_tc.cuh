@@ -20,7 +20,14 @@
 
 namespace ofp {
 
+#ifndef OFP_K6T_WARPS
+#define OFP_K6T_WARPS 16
+#endif
 constexpr int K6T_C1 = 8, K6T_C2 = 16, K6T_FCS = 260;  // channels, fc channel stride in shared memory
+#ifndef OFP_K6T_MINCTA
+#define OFP_K6T_MINCTA 1
+#endif
+constexpr int K6T_WARPS = OFP_K6T_WARPS;            // warps per CTA of the tensor-core kernel
 
 __device__ __forceinline__ uint32_t tf32_hi(float v) {
     uint32_t r;
@@ -40,7 +47,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 
 // shared memory: [conv1 wT + bias | fc weights [out][16][260] | per warp: input rows (C0 x RS), h1 rows (8 x RS)]
 template <int P>
-__global__ void __launch_bounds__(K6_WARPS * 32, 2) k6_cnn_tc(const K6Args a) {
+__global__ void __launch_bounds__(K6T_WARPS * 32, OFP_K6T_MINCTA) k6_cnn_tc(const K6Args a) {
     extern __shared__ __align__(16) float k6_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     const int RS = a.row_stride, W = a.W, C0 = a.C0;
@@ -82,11 +89,14 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 2) k6_cnn_tc(const K6Args a) {
         for (int c = 0; c < C0; ++c)
             for (int t = lane; t < W; t += 32) inb[c * RS + 1 + t] = __ldg(xw + c * W + t);
         __syncwarp();
-        {   // ---- conv1 + SiLU on the FP32 pipe: 8 channels x P positions per lane ----
-            float acc[8][P];
+        // ---- conv1 + SiLU on the FP32 pipe: two passes of 4 channels x P positions per lane (32 accumulators:
+        // the kernel then fits 168 registers = 12 warps per SM instead of 8) ----
+#pragma unroll 1
+        for (int ob = 0; ob < 8; ob += 4) {
+            float acc[4][P];
 #pragma unroll
-            for (int o = 0; o < 8; ++o) {
-                const float b = w1[C0 * 24 + o];
+            for (int o = 0; o < 4; ++o) {
+                const float b = w1[C0 * 24 + ob + o];
 #pragma unroll
                 for (int p = 0; p < P; ++p) acc[o][p] = b;
             }
@@ -94,22 +104,21 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 2) k6_cnn_tc(const K6Args a) {
                 const float *row = inb + ic * RS + lane;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const float4 wa = *reinterpret_cast<const float4 *>(w1 + (ic * 3 + k) * 8);
-                    const float4 wb = *reinterpret_cast<const float4 *>(w1 + (ic * 3 + k) * 8 + 4);
-                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                    const float4 wa = *reinterpret_cast<const float4 *>(w1 + (ic * 3 + k) * 8 + ob);
+                    const float wv[4] = {wa.x, wa.y, wa.z, wa.w};
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         const float xin = row[32 * p + k];
 #pragma unroll
-                        for (int o = 0; o < 8; ++o) acc[o][p] = fmaf(wv[o], xin, acc[o][p]);
+                        for (int o = 0; o < 4; ++o) acc[o][p] = fmaf(wv[o], xin, acc[o][p]);
                     }
                 }
             }
 #pragma unroll
-            for (int o = 0; o < 8; ++o)
+            for (int o = 0; o < 4; ++o)
 #pragma unroll
                 for (int p = 0; p < P; ++p)
-                    if (lane + 32 * p < W) h1[o * RS + 1 + lane + 32 * p] = k6_act<0>(acc[o][p]);
+                    if (lane + 32 * p < W) h1[(ob + o) * RS + 1 + lane + 32 * p] = k6_act<0>(acc[o][p]);
         }
         __syncwarp();
         // ---- conv2 on the tensor cores, SiLU, Linear ----
