@@ -52,6 +52,7 @@ struct K4Args {
     int32_t *out_lags;       // [H, C] (may be null)
     int32_t *out_status;     // [H]
     int32_t screen;          // float32 screening of the lag window (OFP_K4_SCREEN, default on)
+    int32_t columns;         // column mode: shared memory holds two channel columns instead of the [L, C] section
 };
 // ---- float32 screening of the lag window ---------------------------------------------------------
 // The result of cross_correlation_lag is an argmax, so the exact (double, index-order) sums are only
@@ -194,10 +195,11 @@ int ofp_cc_screen_stats(uint64_t *stats4_host, int32_t reset) {
     return OFP_OK;
 }
 
-static int fix_smem_bytes(int32_t n_channels, int32_t max_section, int threads) {
+static int fix_smem_bytes(int32_t n_channels, int32_t max_section, int threads, bool columns = false) {
     const size_t cc = (static_cast<size_t>(max_section) + 2 * XPAD + max_section + 16 + threads * LPF) * sizeof(float) +
                       (CAND_CAP + 1) * sizeof(int);
-    return static_cast<int>(2 * (max_section + 16) * sizeof(double) + static_cast<size_t>(max_section) * n_channels * sizeof(float) + cc);
+    return static_cast<int>(2 * (max_section + 16) * sizeof(double) +
+                            static_cast<size_t>(max_section) * (columns ? 2 : n_channels) * sizeof(float) + cc);
 }
 // upper bound over the CTA sizes a launch may pick
 int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section) {
@@ -238,13 +240,22 @@ int ofp_fix_onsets_ex(const float *audio_dev, int64_t n_samples, int64_t rec_str
     // OFP_K4_SMALL forces the size used below the 192-thread threshold (A/B runs).
     static const int small = getenv("OFP_K4_SMALL") ? atoi(getenv("OFP_K4_SMALL")) : 0;
     const int64_t work = static_cast<int64_t>(n_channels) * max_section;
+    // Column mode: shared memory holds two channel columns instead of the [L, C] section; the later channel of
+    // each pair is median filtered from the L1-resident section when its pair comes up.  It lifts the 3-hits-per-SM
+    // cap of 16-channel sections (49 KB each) but measured no faster (2.03e6 vs 2.09e6 hits/s: the per-pair column
+    // reads are uncoalesced and 16-channel hits are not occupancy bound), so it is only taken when the full
+    // section does not fit shared memory at all (e.g. 32 channels x 1500 samples).  OFP_K4_COLUMNS=0/1 and
+    // OFP_K4_COL_THREADS override (A/B).
+    const char *ec = getenv("OFP_K4_COLUMNS");
+    a.columns = ec ? atoi(ec) : (fix_smem_bytes(n_channels, max_section, K4_MAX_THREADS) > 200 * 1024 ? 1 : 0);
     int threads = work >= 4096 ? K4_MAX_THREADS : (work > 1536 ? 64 : 32);
+    if (a.columns && work >= 4096) threads = getenv("OFP_K4_COL_THREADS") ? atoi(getenv("OFP_K4_COL_THREADS")) : 128;
     if (small > 0 && threads != K4_MAX_THREADS) threads = small <= 32 ? 32 : (small <= 64 ? 64 : 128);
     while (threads < 128 && 2 * tol > threads * LPF) threads *= 2;
     if (threads > 128) threads = K4_MAX_THREADS;
     auto kern = threads == K4_MAX_THREADS ? t192::k4_fix
                                           : (threads == 32 ? t32::k4_fix : (threads == 64 ? t64::k4_fix : t128::k4_fix));
-    const int smem = fix_smem_bytes(n_channels, max_section, threads);  // the partial-sum buffer follows the CTA size
+    const int smem = fix_smem_bytes(n_channels, max_section, threads, a.columns != 0);  // partial sums follow the CTA size
     OFP_REQUIRE(smem <= 220 * 1024, "max_section %d x %d channels needs %d bytes of shared memory", max_section,
                 n_channels, smem);
     OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

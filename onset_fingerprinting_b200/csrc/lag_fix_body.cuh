@@ -90,7 +90,8 @@ __device__ __forceinline__ float median_window(const float *src, int64_t L, int 
 // loaded once (10 loads for four 7-point medians instead of 28) and are all in flight together.
 constexpr int K4_RUN = 4;
 template <int SIZE>
-__device__ __forceinline__ void median_run(const float *src, int Li, int C, int t0, int c, float *med) {
+__device__ __forceinline__ void median_run(const float *src, int Li, int C, int t0, int c, float *med, int ostride,
+                                           int ooff) {
     constexpr int NW = SIZE + K4_RUN - 1, lo = SIZE / 2;
     float w[NW];
 #pragma unroll
@@ -113,7 +114,7 @@ __device__ __forceinline__ void median_run(const float *src, int Li, int C, int 
         float v[SIZE];
 #pragma unroll
         for (int j = 0; j < SIZE; ++j) v[j] = w[k + j];
-        med[(t0 + k) * C + c] = finite ? median_network<SIZE>(v) : median_rank(v, SIZE);
+        med[(t0 + k) * ostride + ooff] = finite ? median_network<SIZE>(v) : median_rank(v, SIZE);
     }
 }
 
@@ -467,6 +468,26 @@ __device__ __forceinline__ bool adjust_sums(const double *xd, const double *yd, 
         return true;
 }
 
+// Median-filtered samples of ONE channel of the section into col[0 .. Li) (column mode, see k4_fix).
+__device__ __forceinline__ void median_column(const float *src, int Li, int C, int c, int size, float *col) {
+    const int tid = threadIdx.x;
+    if (size == 3 || size == 5 || size == 7 || size == 9) {
+        const int n_runs = (Li + K4_RUN - 1) / K4_RUN;
+        for (int r = tid; r < n_runs; r += K4_THREADS) {
+            const int t0 = r * K4_RUN;
+            switch (size) {
+                case 3: median_run<3>(src, Li, C, t0, c, col, 1, 0); break;
+                case 5: median_run<5>(src, Li, C, t0, c, col, 1, 0); break;
+                case 7: median_run<7>(src, Li, C, t0, c, col, 1, 0); break;
+                default: median_run<9>(src, Li, C, t0, c, col, 1, 0); break;
+            }
+        }
+    } else {
+        for (int t = tid; t < Li; t += K4_THREADS)
+            col[t] = size == 1 ? src[t * C + c] : median_window<0>(src, Li, C, t, c, size);
+    }
+}
+
 __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = a.C, tid = threadIdx.x, h = blockIdx.x;
@@ -475,7 +496,11 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
     double *yd = xd + a.Lmax + 16;
     float *bufA = reinterpret_cast<float *>(yd + a.Lmax + 16);
     CcScratch sc;
-    sc.xf = bufA + static_cast<size_t>(a.Lmax) * C;
+    // section storage: every channel's median-filtered samples [Lmax, C] -- or, in column mode (a.columns:
+    // many-channel hits, where that buffer alone would cap an SM at 3 hits), only the reference channel's and
+    // the current later channel's columns, the latter re-filtered from the L1-resident section once per pair
+    const bool columns = a.columns != 0;
+    sc.xf = bufA + static_cast<size_t>(a.Lmax) * (columns ? 2 : C);
     sc.yf = sc.xf + a.Lmax + 2 * XPAD;
     sc.part = sc.yf + a.Lmax + 16;
     sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * K4_LPF);
@@ -530,17 +555,20 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
     // median filter along time (detection.py:420-422), read straight from the recording (the 7 rows
     // around a sample are coalesced and L1-resident) into the only section buffer kept in shared memory
     float *med = bufA;
+    float *colx = bufA, *coly = bufA + a.Lmax;  // column mode
     const int n_el = static_cast<int>(L0) * C;
-    if (fp.filter_size == 3 || fp.filter_size == 5 || fp.filter_size == 7 || fp.filter_size == 9) {
+    if (columns) {
+        median_column(src, static_cast<int>(L0), C, idx[0], fp.filter_size, colx);  // the reference channel, once
+    } else if (fp.filter_size == 3 || fp.filter_size == 5 || fp.filter_size == 7 || fp.filter_size == 9) {
         // runs of K4_RUN samples of one channel per thread (lanes across channels, then across runs)
         const int Li = static_cast<int>(L0), n_runs = (Li + K4_RUN - 1) / K4_RUN * C;
         for (int r = tid; r < n_runs; r += K4_THREADS) {
             const int tr = r / C, c = r - tr * C, t0 = tr * K4_RUN;
             switch (fp.filter_size) {
-                case 3: median_run<3>(src, Li, C, t0, c, med); break;
-                case 5: median_run<5>(src, Li, C, t0, c, med); break;
-                case 7: median_run<7>(src, Li, C, t0, c, med); break;
-                default: median_run<9>(src, Li, C, t0, c, med); break;
+                case 3: median_run<3>(src, Li, C, t0, c, med, C, c); break;
+                case 5: median_run<5>(src, Li, C, t0, c, med, C, c); break;
+                case 7: median_run<7>(src, Li, C, t0, c, med, C, c); break;
+                default: median_run<9>(src, Li, C, t0, c, med, C, c); break;
             }
         }
     } else {
@@ -559,11 +587,13 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
     __syncthreads();
     // section value after np.diff(., d), direction mask, abs (detection.py:420-428) and the in-place
     // zero_left prefixes (435-437), evaluated on the fly from the median-filtered samples
+    const int ref_ch = idx[0];
     auto secval = [&](int64_t t, int c) -> float {
         if (t < zl[c]) return 0.0f;
         float w[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) w[k] = k <= fp.d ? med[(t + k) * C + c] : 0.0f;
+        for (int k = 0; k < 4; ++k)
+            w[k] = k <= fp.d ? (columns ? (c == ref_ch ? colx : coly)[t + k] : med[(t + k) * C + c]) : 0.0f;
         for (int rr = 0; rr < fp.d; ++rr)
 #pragma unroll
             for (int k = 0; k < 3; ++k) w[k] = __fsub_rn(w[k + 1], w[k]);
@@ -594,6 +624,10 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
         // norm and maximum across pairs otherwise (so[r] moves, but it only selects the window)
         const bool x_fresh = zl[r] != x_zl;
         x_zl = zl[r];
+        if (columns) {  // this pair's later channel, median filtered straight from the (L1-resident) section
+            median_column(src, static_cast<int>(L0), C, ci, fp.filter_size, coly);
+            __syncthreads();
+        }
         float xm = -INFINITY, ym = -INFINITY;
         for (int64_t t = tid; t < L; t += K4_THREADS) {
             const float yv = secval(t, ci);

@@ -483,8 +483,9 @@ def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 
             mn, mx = hit_onsets.min(1).values, hit_onsets.max(1).values
             span = int(torch.where(mn >= 0, mx - mn, torch.zeros_like(mx)).max().item())
         max_section = N if to_end else span + 2 * look + 1
-        # shared-memory budget of one CTA; longer sections are flagged OFP_FIX_TOO_LONG
-        budget = (200 * 1024 - 128) // (16 + 8 * Cn)
+        # shared-memory budget of one CTA; longer sections are flagged OFP_FIX_TOO_LONG.  When the [L, C] section
+        # does not fit, the kernel keeps two channel columns instead (column mode): 16 + 8 + 8 + 8 B per sample.
+        budget = max((200 * 1024 - 128) // (16 + 8 * Cn), (200 * 1024 - 16 * 1024) // 40)
         max_section = min(max_section, budget)
     out = torch.empty_like(hit_onsets)
     lags = torch.empty_like(hit_onsets)

@@ -93,6 +93,41 @@ def test_fix_onsets_golden(tag, det, orc, golden_dir):
         assert np.array_equal(fixed, f_o) and np.array_equal(status, st_o) and np.array_equal(lags, lags_o), name
 
 
+@pytest.mark.parametrize("tag", ["3ch", "16ch"])
+def test_fix_onsets_column_mode_golden(tag, det, golden_dir, monkeypatch):
+    """K4's column mode (two channel columns in shared memory instead of the whole [L, C] section; taken on its
+    own when a section does not fit) must reproduce the reference's golden results for every option set."""
+    from oracle.make_golden import FIX_OPTS
+
+    g = np.load(golden_dir / f"fix_{tag}.npz")
+    skw = dict(seconds=3.0, seed=21) if tag == "3ch" else dict(seconds=2.0, seed=22, sensors=synth.SENSORS_16MESH,
+                                                                  medium="drumhead")
+    x, _ = synth.drum_recording(**skw)
+    groups = g["groups"]
+    for name, kw in FIX_OPTS.items():
+        want = det.fix_onsets(x, groups, return_status=True, **kw)
+        monkeypatch.setenv("OFP_K4_COLUMNS", "1")
+        got = det.fix_onsets(x, groups, return_status=True, **kw)
+        monkeypatch.delenv("OFP_K4_COLUMNS")
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), name
+        ok = g[f"raised_{name}"] == 0
+        assert np.array_equal(got[0][ok], g[f"fixed_{name}"][ok]), name
+
+
+def test_fix_onsets_oversized_sections_fall_into_column_mode(det, orc):
+    """24 channels x 2600-sample sections (250 KB as [L, C]) only fit a CTA's shared memory as columns."""
+    sensors = [(0.9, 15.0 * i, 0.0) for i in range(24)]
+    x, truth = synth.drum_recording(seconds=1.2, seed=31, sensors=sensors, medium="drumhead")
+    arr = truth["arrival"][:3]
+    fixed, status, lags = det.fix_onsets(x, arr, return_status=True, onset_tolerance=1000, normalization_cutoff=20,
+                                         filter_size=5, d=1, take_abs=True)
+    f_o, st_o, lags_o = orc.fix_onsets(x, arr, return_status=True, onset_tolerance=1000, normalization_cutoff=20,
+                                       filter_size=5, d=1, take_abs=True)
+    assert np.array_equal(status, st_o) and np.array_equal(fixed, f_o) and np.array_equal(lags, lags_o)
+    assert (status == 0).any()
+
+
 def test_fix_onsets_edge_cases(det, orc):
     """Sections at the start of a recording (negative start, Q6), a missing channel, an empty CC window."""
     x, _ = synth.drum_recording(seconds=1.0, seed=5)
