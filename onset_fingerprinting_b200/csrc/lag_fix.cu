@@ -199,7 +199,7 @@ static int fix_smem_bytes(int32_t n_channels, int32_t max_section, int threads, 
     const size_t cc = (static_cast<size_t>(max_section) + 2 * XPAD + max_section + 16 + threads * LPF) * sizeof(float) +
                       (CAND_CAP + 1) * sizeof(int);
     return static_cast<int>(2 * (max_section + 16) * sizeof(double) +
-                            static_cast<size_t>(max_section) * (columns ? 2 : n_channels) * sizeof(float) + cc);
+                            static_cast<size_t>(max_section | 1) * (columns ? 2 : n_channels) * sizeof(float) + cc);
 }
 // upper bound over the CTA sizes a launch may pick
 int ofp_fix_onsets_smem_bytes(int32_t n_channels, int32_t max_section) {

@@ -298,9 +298,11 @@ __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double 
     }
     block_sum2(sx, sy, sc.red_d);
     if (x_fresh) sx_cache = sx; else sx = sx_cache;
-    const double S = sqrt(sx) * sqrt(sy);
-    if (!(S < 1e30)) return false;  // inf / NaN in the section: exact path
-    if (S == 0.0) {                 // one signal is all zero: every sum is 0, np.argmax returns index 0
+    // ||x|| ||y|| as ONE square root (two double square roots per thread per pair were 2.5 % of the kernel's
+    // samples); it only enters the error bound, where the 1.0001 factor below covers its rounding
+    const double S = sqrt(sx * sy);
+    if (!(sx < 1e30 && sy < 1e30)) return false;  // inf / NaN in the section: exact path
+    if (sx == 0.0 || sy == 0.0) {   // one signal is all zero: every sum is 0, np.argmax returns index 0
         if (tid == 0) *s_lag = static_cast<int>(adj);
         __syncthreads();
         return true;
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
     // many-channel hits, where that buffer alone would cap an SM at 3 hits), only the reference channel's and
     // the current later channel's columns, the latter re-filtered from the L1-resident section once per pair
     const bool columns = a.columns != 0;
-    sc.xf = bufA + static_cast<size_t>(a.Lmax) * (columns ? 2 : C);
+    sc.xf = bufA + static_cast<size_t>(a.Lmax | 1) * (columns ? 2 : C);
     sc.yf = sc.xf + a.Lmax + 2 * XPAD;
     sc.part = sc.yf + a.Lmax + 16;
     sc.cand = reinterpret_cast<int *>(sc.part + K4_THREADS * K4_LPF);
@@ -554,7 +556,8 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
     if (tid < C && a.out_lags) a.out_lags[static_cast<int64_t>(h) * C + tid] = LAG_NONE;
     // median filter along time (detection.py:420-422), read straight from the recording (the 7 rows
     // around a sample are coalesced and L1-resident) into the only section buffer kept in shared memory
-    float *med = bufA;
+    float *med = bufA;  // [C][MS] channel-major with an odd row stride: conflict-free for lanes across channels
+    const int MS = a.Lmax | 1;  // (median stores) and for lanes across time (section reads)
     float *colx = bufA, *coly = bufA + a.Lmax;  // column mode
     const int n_el = static_cast<int>(L0) * C;
     if (columns) {
@@ -565,10 +568,10 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
         for (int r = tid; r < n_runs; r += K4_THREADS) {
             const int tr = r / C, c = r - tr * C, t0 = tr * K4_RUN;
             switch (fp.filter_size) {
-                case 3: median_run<3>(src, Li, C, t0, c, med, C, c); break;
-                case 5: median_run<5>(src, Li, C, t0, c, med, C, c); break;
-                case 7: median_run<7>(src, Li, C, t0, c, med, C, c); break;
-                default: median_run<9>(src, Li, C, t0, c, med, C, c); break;
+                case 3: median_run<3>(src, Li, C, t0, c, med, 1, c * MS); break;
+                case 5: median_run<5>(src, Li, C, t0, c, med, 1, c * MS); break;
+                case 7: median_run<7>(src, Li, C, t0, c, med, 1, c * MS); break;
+                default: median_run<9>(src, Li, C, t0, c, med, 1, c * MS); break;
             }
         }
     } else {
@@ -579,7 +582,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
             const int c = c_el;
             t_el += dt_el; c_el += dc_el;
             if (c_el >= C) { c_el -= C; ++t_el; }
-            med[e] = fp.filter_size == 1 ? src[e] : median_window<0>(src, L0, C, t, c, fp.filter_size);
+            med[c * MS + static_cast<int>(t)] = fp.filter_size == 1 ? src[e] : median_window<0>(src, L0, C, t, c, fp.filter_size);
         }
     }
     const int64_t L = L0 - fp.d;
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(K4_THREADS, K4_MINCTA) k4_fix(const K4Args a) 
         float w[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            w[k] = k <= fp.d ? (columns ? (c == ref_ch ? colx : coly)[t + k] : med[(t + k) * C + c]) : 0.0f;
+            w[k] = k <= fp.d ? (columns ? (c == ref_ch ? colx : coly)[t + k] : med[c * MS + t + k]) : 0.0f;
         for (int rr = 0; rr < fp.d; ++rr)
 #pragma unroll
             for (int k = 0; k < 3; ++k) w[k] = __fsub_rn(w[k + 1], w[k]);
