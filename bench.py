@@ -50,6 +50,7 @@ def parse():
                     help="batch = configs[1] (headline); hits16 = configs[2] (16-channel hit mining, K4+K5); "
                          "realtime = configs[3] (4096 concurrent 128-sample block streams)")
     ap.add_argument("--windows", type=int, default=1000000, help="cnn: onset windows per GPU")
+    ap.add_argument("--network", default="cnn", choices=["cnn", "cccnn"], help="cnn workload: model.CNN or model.CCCNN")
     ap.add_argument("--hits", type=int, default=1000000, help="hits16: number of hits (over all GPUs)")
     ap.add_argument("--streams", type=int, default=4096, help="realtime: concurrent streams per GPU")
     ap.add_argument("--blocks", type=int, default=1000, help="realtime: consecutive blocks")
@@ -661,8 +662,9 @@ def run_cnn(args):
     from onset_fingerprinting_b200 import model
 
     torch.manual_seed(7)
-    m = model.CNN(256, 2).cuda()
-    n = args.windows
+    cc = args.network == "cccnn"
+    m = (model.CCCNN(256, 2) if cc else model.CNN(256, 2)).cuda()
+    n = args.windows if not cc else min(args.windows, 200000)
     g = torch.Generator(device="cuda"); g.manual_seed(100 + rank)
     x = torch.randn((n, 3, 256), device="cuda", generator=g) * 0.1
     for _ in range(args.warmup):
@@ -682,12 +684,14 @@ def run_cnn(args):
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     ms /= args.steps
     macs = 256 * (8 * 3 * 3 + 16 * 8 * 3) + 2 * 4096
+    if cc:  # per channel: conv 1->8->16, then 16 maps x V^2 / 2 products of the auto-correlation (lags >= 0)
+        macs = 3 * (256 * (8 * 3 + 16 * 8 * 3) + 16 * 256 * 257 // 2) + 2 * 3 * 511
     peak, src = _peak()
     alg_bytes = n * (3 * 256 * 4 + 2 * 4)
     cpu = e2e = None
-    if rank == 0 and not args.skip_cpu:
+    if rank == 0 and not args.skip_cpu and not cc:
         # the reference runs this network through stock torch modules; same modules on the host cores
-        mc = torch.nn.Sequential(m.conv_layers, torch.nn.Flatten(1), m.fc).cpu().eval()
+        mc = torch.nn.Sequential(m.conv_layers, torch.nn.Flatten(1), m.fc).cpu().eval() if not cc else None
         xs = x[:50000].cpu()
         with torch.no_grad():
             mc(xs[:1000])
@@ -709,13 +713,13 @@ def run_cnn(args):
         e2e = {"value": ne / dt, "unit": "windows/s", "h2d_bytes_per_step": int(xh.numel() * 4),
                "d2h_bytes_per_step": int(ne * 8), "windows": ne, "ms": dt * 1e3}
         print(json.dumps({
-            "metric": "onset windows/sec through model.CNN inference", "value": world * n / (ms / 1e3),
+            "metric": f"onset windows/sec through model.{'CCCNN' if cc else 'CNN'} inference", "value": world * n / (ms / 1e3),
             "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[4] (classifier): {n} windows x 3 ch x 256 samples per GPU, CNN [8, 16] k=3 SiLU "
                                    "+ Linear 4096->2, random-init weights", "l2": "inputs larger than L2"},
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg_bytes / (ms / 1e3) / 1e9 / peak, "traffic": None, "kernel": "k6_cnn",
+                         "frac": alg_bytes / (ms / 1e3) / 1e9 / peak, "traffic": None, "kernel": "k6_cccnn" if cc else "k6_cnn_tc",
                          "kernel_ms": ms, "peak_source": src,
                          "note": f"compute bound: {2 * macs * n / (ms / 1e3) / 1e12:.1f} TFLOP/s ({macs} MAC per window; conv2 as "
                                  "3xTF32 mma.sync on the tensor cores, conv1 / SiLU / Linear on the FP32 pipe)"},

@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 2) k6_cnn(const K6Args a) {
 
 }  // namespace ofp
 #include "cnn_infer_tc.cuh"
+#include "cnn_cc_infer.cuh"
 
 using namespace ofp;
 
@@ -314,6 +315,89 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
     const int64_t want = (n_windows + warps - 1) / warps;
     const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
     kern<<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_cccnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
+                          int32_t kernel_size, int32_t padding, int32_t out_size, int64_t *n_params_out,
+                          int32_t *n_lags_out) {
+    OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS && layer_sizes_host && n_params_out, "bad argument");
+    int64_t n = 0;
+    int cin = 1, len = input_size;
+    for (int l = 0; l < n_layers; ++l) {
+        const int cout = layer_sizes_host[l], cp = (cout + 7) & ~7;
+        n += static_cast<int64_t>(cin) * kernel_size * cp + cp;
+        len = len + 2 * padding - (kernel_size - 1);
+        OFP_REQUIRE(len >= 1, "layer %d has no output positions", l);
+        cin = cout;
+    }
+    n += static_cast<int64_t>(out_size) * channels * (2 * len - 1) + out_size;
+    *n_params_out = n;
+    if (n_lags_out) *n_lags_out = 2 * len - 1;
+    return OFP_OK;
+}
+
+int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
+                      int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
+                      int32_t activation, const float *params_dev, int32_t out_size, float *out_dev, void *stream) {
+    OFP_REQUIRE(x_dev && params_dev && out_dev && layer_sizes_host, "null argument");
+    OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS, "1..%d conv layers supported", K6_MAX_LAYERS);
+    OFP_REQUIRE(kernel_size == 1 || kernel_size == 3 || kernel_size == 5 || kernel_size == 7,
+                "kernel_size must be 1, 3, 5 or 7");
+    OFP_REQUIRE(padding >= 0 && padding <= 8 && channels >= 1 && channels <= 64 && out_size >= 1 && out_size <= 4,
+                "bad argument (out_size up to 4)");
+    OFP_REQUIRE(input_size >= 1 && input_size <= 256, "input_size up to 256 supported");
+    OFP_REQUIRE(activation >= 0 && activation <= 3, "activation: 0 SiLU, 1 ReLU, 2 tanh, 3 identity");
+    if (n_windows == 0) return OFP_OK;
+    K6Args a{};
+    a.x = x_dev; a.n = n_windows; a.win_stride = win_stride; a.C0 = 1; a.W = input_size; a.n_layers = n_layers;
+    a.ks = kernel_size; a.pad = padding; a.act = activation; a.out_size = out_size; a.params = params_dev;
+    a.out = out_dev;
+    int cin = 1, len = input_size, off = 0, max_len = input_size, rows_a = 1, rows_b = 1;
+    for (int l = 0; l < n_layers; ++l) {
+        const int cout = layer_sizes_host[l], cp = (cout + 7) & ~7;
+        OFP_REQUIRE(cout >= 1 && cout <= 64, "layer sizes 1..64 supported");
+        a.cin[l] = cin; a.cout[l] = cout; a.coutp[l] = cp; a.lin[l] = len;
+        a.w_off[l] = off; off += cin * kernel_size * cp;
+        a.b_off[l] = off; off += cp;
+        len = len + 2 * padding - (kernel_size - 1);
+        OFP_REQUIRE(len >= 1 && len <= 256, "layer %d output length %d outside 1..256", l, len);
+        a.lout[l] = len;
+        max_len = std::max(max_len, len);
+        (l % 2 == 0 ? rows_b : rows_a) = std::max(l % 2 == 0 ? rows_b : rows_a, cout);  // input in A, layer 0 -> B, ...
+        cin = cout;
+    }
+    OFP_REQUIRE(cin % 8 == 0, "the last layer size must be a multiple of 8 (tensor-core K dimension), got %d", cin);
+    rows_a = std::max(rows_a, cin); rows_b = std::max(rows_b, cin);  // the hi / lo planes of the feature maps
+    OFP_REQUIRE(len % 16 == 0, "the feature-map length must be a multiple of 16, got %d", len);
+    a.conv_params = off;
+    const int nb = 2 * len - 1;
+    a.fc_w_off = off; off += out_size * channels * nb;
+    a.fc_b_off = off; off += out_size;
+    a.n_params = off;
+    const int P = max_len <= 64 ? 2 : (max_len <= 128 ? 4 : 8);
+    a.row_stride = 32 * P + 2 * padding + kernel_size + 1;
+    const int warps = 3;
+    const size_t smem = sizeof(float) * (((a.conv_params + 3) & ~3) +
+                                         static_cast<size_t>(warps) * ((rows_a + rows_b) * a.row_stride + ((len + 3) & ~3) + 128));
+    OFP_REQUIRE(smem <= 227 * 1024, "network needs %zu bytes of shared memory per CTA", smem);
+    void (*kern)(const K6Args, int, int, int) = nullptr;
+#define K6C_PICK(KS_) kern = P == 2 ? k6_cccnn<KS_, 2> : (P == 4 ? k6_cccnn<KS_, 4> : k6_cccnn<KS_, 8>)
+    switch (kernel_size) {
+        case 1: K6C_PICK(1); break;
+        case 3: K6C_PICK(3); break;
+        case 5: K6C_PICK(5); break;
+        default: K6C_PICK(7); break;
+    }
+#undef K6C_PICK
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    OFP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    per_sm = std::max(per_sm, 1);
+    const int64_t want = (n_windows + warps - 1) / warps;
+    const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(sm_count()) * per_sm));
+    kern<<<grid, warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(a, channels, rows_a, rows_b);
     OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;
 }

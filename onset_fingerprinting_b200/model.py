@@ -101,3 +101,90 @@ class CNN(nn.Module):
     def call_np(self, x: np.ndarray) -> np.ndarray:
         """numpy in, numpy out (the shape FCNN.call_np has in the reference, calibration.py:463-560)."""
         return self.forward(x).cpu().numpy()
+
+
+class CCCNN(nn.Module):
+    """``model.CCCNN`` of the reference (model.py:443-538, ``group=False``) for inference: same constructor arguments
+    and parameter names (``conv_layers.conv1`` ..., ``fc``), fused forward in csrc/cnn_cc_infer.cuh -- per sensor
+    channel the shared conv stack, the summed auto-correlation of its feature maps as ``F^T F`` on the tensor
+    cores with the diagonal sums taken inside the accumulator fragments, softmax over the 2V-1 lags, Linear."""
+
+    def __init__(self, input_size: int, output_size: int, channels: int = 3, layer_sizes: list[int] = [8, 16],
+                 kernel_sizes=3, strides=1, dropout_rate: float = 0.5, batch_norm=False, pool=False, padding=1,
+                 dilation=1, group: bool = False, activation=nn.SiLU) -> None:
+        super().__init__()
+        if isinstance(kernel_sizes, (list, tuple)):
+            if len(set(kernel_sizes)) != 1:
+                raise NotImplementedError("one kernel size for all layers")
+            kernel_sizes = kernel_sizes[0]
+        if isinstance(strides, (list, tuple)):
+            strides = strides[0] if len(set(strides)) == 1 else None
+        if batch_norm or pool or dilation != 1 or group or strides != 1:
+            raise NotImplementedError("K6b covers the reference defaults: group=False, stride 1, no batch_norm / pool")
+        if activation not in _ACT:
+            raise NotImplementedError(f"activation {activation}")
+        self.input_size, self.output_size, self.channels = input_size, output_size, channels
+        self.layer_sizes, self.kernel_size, self.padding = list(layer_sizes), kernel_sizes, padding
+        self.act, self.group = _ACT[activation], False
+        self.conv_layers = nn.Sequential()
+        cur, length = 1, input_size
+        for i, size in enumerate(self.layer_sizes):
+            self.conv_layers.add_module(f"conv{i + 1}", nn.Conv1d(cur, size, kernel_sizes, padding=padding))
+            self.conv_layers.add_module(f"act{i + 1}", activation())
+            length = length + 2 * padding - (kernel_sizes - 1)
+            cur = size
+        self.dropout = nn.Dropout(dropout_rate)
+        self.n_lags = 2 * length - 1
+        self.fc = nn.Linear(channels * self.n_lags, output_size)
+        self._packed = None
+        self.eval()
+
+    def pack(self) -> torch.Tensor:
+        parts = []
+        for i in range(len(self.layer_sizes)):
+            conv = getattr(self.conv_layers, f"conv{i + 1}")
+            w = conv.weight.detach().float().cpu()
+            cout = w.shape[0]
+            cp = (cout + 7) // 8 * 8
+            wt = torch.zeros((w.shape[1], w.shape[2], cp))
+            wt[:, :, :cout] = w.permute(1, 2, 0)
+            bp = torch.zeros(cp)
+            bp[:cout] = conv.bias.detach().float().cpu()
+            parts += [wt.reshape(-1), bp]
+        parts += [self.fc.weight.detach().float().cpu().reshape(-1), self.fc.bias.detach().float().cpu()]
+        packed = torch.cat(parts).contiguous()
+        n = C.c_int64(0)
+        sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
+        check(_lib.lib().ofp_cccnn_param_count(C.c_int32(self.channels), C.c_int32(self.input_size),
+                                               C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
+                                               C.c_int32(self.padding), C.c_int32(self.output_size), C.byref(n), None))
+        assert n.value == packed.numel(), (n.value, packed.numel())
+        self._packed = packed.cuda()
+        return self._packed
+
+    def load_state_dict(self, *args, **kw):
+        out = super().load_state_dict(*args, **kw)
+        self._packed = None
+        return out
+
+    @torch.no_grad()
+    def forward(self, x) -> torch.Tensor:
+        """x [B, channels, input_size] float32 -> [B, output_size] device tensor."""
+        _lib.require_cuda()
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        x = x.cuda().float()
+        if x.dim() != 3 or x.shape[1] != self.channels or x.shape[2] != self.input_size:
+            raise ValueError(f"expected [B, {self.channels}, {self.input_size}], got {tuple(x.shape)}")
+        if x.stride(2) != 1 or x.stride(1) != self.input_size:
+            x = x.contiguous()
+        if self._packed is None:
+            self.pack()
+        out = torch.empty((x.shape[0], self.output_size), dtype=torch.float32, device="cuda")
+        sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
+        check(_lib.lib().ofp_cccnn_forward(ptr(x), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)),
+                                           C.c_int32(self.channels), C.c_int32(self.input_size),
+                                           C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
+                                           C.c_int32(self.padding), C.c_int32(self.act), ptr(self._packed),
+                                           C.c_int32(self.output_size), ptr(out), stream_ptr()))
+        return out

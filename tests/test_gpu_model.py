@@ -183,3 +183,50 @@ def test_chunked_host_pipeline_equals_direct_call():
     assert torch.equal(got, want)
     (again,) = hostpipe.run_chunked([xh], net, chunk=400, outs=(got,))
     assert again.data_ptr() == got.data_ptr() and torch.equal(again, want)
+
+
+def cccnn_reference(m, x):
+    """model.CCCNN.forward (model.py:512-538, group=False) with stock torch ops, TF32 off."""
+    import torch.nn.functional as F
+
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            B, Cn, W = x.shape
+            f = m.conv_layers(x.reshape(B * Cn, 1, W))  # the reference vmaps the same stack over the channels
+            K, V = f.shape[1:]
+            cc = F.conv1d(f.reshape(1, B * Cn * K, V), f.reshape(B * Cn * K, 1, V), groups=B * Cn * K, padding=V - 1)
+            cc = cc.view(B * Cn, K, -1).sum(1)
+            p = torch.softmax(cc, dim=-1).view(B, -1)
+            return m.fc(p)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(input_size=256, output_size=2),
+    dict(input_size=128, output_size=3, channels=4, layer_sizes=[8], kernel_sizes=5, padding=2),
+    dict(input_size=64, output_size=2, channels=2, layer_sizes=[6, 12, 8], activation=torch.nn.Tanh),
+])
+def test_cccnn_forward_matches_torch(cfg):
+    """The summed auto-correlation runs as F^T F on the tensor cores (3xTF32); softmax turns absolute errors of the
+    correlation into relative errors of the probabilities, so the bar is 1e-3 of the output scale (float32 on both
+    sides, different summation orders over V*K products).  Input scales from a near-uniform to a near-one-hot lag
+    distribution; at least one of them must make the output depend on the window (not a vacuous comparison)."""
+    from onset_fingerprinting_b200 import model
+
+    torch.manual_seed(3)
+    m = model.CCCNN(**cfg).cuda()
+    with torch.no_grad():
+        m.fc.weight.mul_(30.0)  # default init is 1/sqrt(fan_in): make the lag distribution visible in the output
+    spread = 0.0
+    for scale in (0.05, 0.15, 0.3, 0.6, 1.2, 2.5):
+        x = torch.randn(257, cfg.get("channels", 3), cfg["input_size"], device="cuda") * scale
+        got, want = m(x), cccnn_reference(m, x)
+        assert got.shape == want.shape
+        err = float((got - want).abs().max())
+        assert err <= 1e-3 * max(float(want.abs().max()), 1e-3), (scale, err)
+        spread = max(spread, float(want.std(0).max()))
+    assert spread > 1e-3, spread
