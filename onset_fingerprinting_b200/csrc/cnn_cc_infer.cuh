@@ -17,7 +17,7 @@
 
 namespace ofp {
 
-template <int KS, int P>
+template <int KS, int P, int ND>
 __global__ void __launch_bounds__(3 * 32, 2) k6_cccnn(const K6Args a, const int n_ch, const int rows_a, const int rows_b) {
     extern __shared__ __align__(16) float k6_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
@@ -99,45 +99,46 @@ __global__ void __launch_bounds__(3 * 32, 2) k6_cccnn(const K6Args a, const int 
             for (int i = lane; i < V; i += 32) cc[i] = 0.f;
             __syncwarp();
             // ---- cc[lag] = sum over the lag-th diagonal of F^T F, tile diagonal by tile diagonal ----
-            // two neighbouring tile diagonals per pass: they share the A fragments and give six independent HMMA
+            // ND neighbouring tile diagonals per pass: they share the A fragments and give 3 ND independent HMMA
             // chains (the kernel is latency bound at 6 warps per SM)
-            for (int d8 = 0; d8 < V / 8; d8 += 2) {
-                float e0[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
-                float f0[4] = {0.f, 0.f, 0.f, 0.f}, f1[4] = {0.f, 0.f, 0.f, 0.f}, f2[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int d8 = 0; d8 < V / 8; d8 += ND) {
+                float acc[ND][3][4];
+#pragma unroll
+                for (int n = 0; n < ND; ++n)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[n][t][e] = 0.f;
                 for (int mt = 0; 8 * (d8 + 2 * mt) < V; ++mt) {
                     const int i0 = 16 * mt + g, j0 = 8 * (d8 + 2 * mt) + g;
-                    const bool second = j0 - g + 8 < V;  // the d8 + 1 diagonal still has a tile in this tile row (uniform)
                     for (int ks = 0; ks < Kp; ks += 8) {
                         const int r0 = (ks + tg) * RS, r1 = r0 + 4 * RS;
                         const uint32_t ah[4] = {__float_as_uint(Fh[r0 + i0]), __float_as_uint(Fh[r0 + i0 + 8]),
                                                 __float_as_uint(Fh[r1 + i0]), __float_as_uint(Fh[r1 + i0 + 8])};
                         const uint32_t al[4] = {__float_as_uint(Fl[r0 + i0]), __float_as_uint(Fl[r0 + i0 + 8]),
                                                 __float_as_uint(Fl[r1 + i0]), __float_as_uint(Fl[r1 + i0 + 8])};
-                        const uint32_t bh[2] = {__float_as_uint(Fh[r0 + j0]), __float_as_uint(Fh[r1 + j0])};
-                        const uint32_t bl[2] = {__float_as_uint(Fl[r0 + j0]), __float_as_uint(Fl[r1 + j0])};
-                        mma_tf32(e1, al, bh);
-                        mma_tf32(e2, ah, bl);
-                        mma_tf32(e0, ah, bh);
-                        if (second) {
-                            const uint32_t ch[2] = {__float_as_uint(Fh[r0 + j0 + 8]), __float_as_uint(Fh[r1 + j0 + 8])};
-                            const uint32_t cl[2] = {__float_as_uint(Fl[r0 + j0 + 8]), __float_as_uint(Fl[r1 + j0 + 8])};
-                            mma_tf32(f1, al, ch);
-                            mma_tf32(f2, ah, cl);
-                            mma_tf32(f0, ah, ch);
+#pragma unroll
+                        for (int n = 0; n < ND; ++n) {
+                            if (j0 - g + 8 * n < V) {  // diagonal d8 + n still has a tile in this tile row (uniform)
+                                const uint32_t bh[2] = {__float_as_uint(Fh[r0 + j0 + 8 * n]), __float_as_uint(Fh[r1 + j0 + 8 * n])};
+                                const uint32_t bl[2] = {__float_as_uint(Fl[r0 + j0 + 8 * n]), __float_as_uint(Fl[r1 + j0 + 8 * n])};
+                                mma_tf32(acc[n][1], al, bh);
+                                mma_tf32(acc[n][2], ah, bl);
+                                mma_tf32(acc[n][0], ah, bh);
+                            }
                         }
                     }
                 }
                 // fragment -> 16 x 8 tile (rows g, g + 8; columns 2 tg, 2 tg + 1); lane l then owns the diagonal
-                // col - row = l - 15 of the tile, i.e. lag 8 d8 + l - 15: one owner per bin, no atomics
+                // col - row = l - 15 of the tile, i.e. lag 8 (d8 + n) + l - 15: one owner per bin, no atomics
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const float *x0 = half ? f0 : e0, *x1 = half ? f1 : e1, *x2 = half ? f2 : e2;
-                    tile[g * 8 + 2 * tg] = x0[0] + (x1[0] + x2[0]);
-                    tile[g * 8 + 2 * tg + 1] = x0[1] + (x1[1] + x2[1]);
-                    tile[(g + 8) * 8 + 2 * tg] = x0[2] + (x1[2] + x2[2]);
-                    tile[(g + 8) * 8 + 2 * tg + 1] = x0[3] + (x1[3] + x2[3]);
+                for (int n = 0; n < ND; ++n) {
+                    tile[g * 8 + 2 * tg] = acc[n][0][0] + (acc[n][1][0] + acc[n][2][0]);
+                    tile[g * 8 + 2 * tg + 1] = acc[n][0][1] + (acc[n][1][1] + acc[n][2][1]);
+                    tile[(g + 8) * 8 + 2 * tg] = acc[n][0][2] + (acc[n][1][2] + acc[n][2][2]);
+                    tile[(g + 8) * 8 + 2 * tg + 1] = acc[n][0][3] + (acc[n][1][3] + acc[n][2][3]);
                     __syncwarp();
-                    const int off = lane - 15, lagv = 8 * (d8 + half) + off;
+                    const int off = lane - 15, lagv = 8 * (d8 + n) + off;
                     if (lane < 23 && lagv >= 0 && lagv < V) {
                         float sdiag = 0.f;
                         for (int row = max(0, -off); row < 16 && row + off < 8; ++row) sdiag += tile[row * 8 + row + off];

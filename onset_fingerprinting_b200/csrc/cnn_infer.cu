@@ -383,7 +383,10 @@ int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride,
                                          static_cast<size_t>(warps) * ((rows_a + rows_b) * a.row_stride + ((len + 3) & ~3) + 128));
     OFP_REQUIRE(smem <= 227 * 1024, "network needs %zu bytes of shared memory per CTA", smem);
     void (*kern)(const K6Args, int, int, int) = nullptr;
-#define K6C_PICK(KS_) kern = P == 2 ? k6_cccnn<KS_, 2> : (P == 4 ? k6_cccnn<KS_, 4> : k6_cccnn<KS_, 8>)
+    // diagonals per pass: 4 when the number of tile diagonals (V / 8) allows, else 2 (V is a multiple of 16)
+#define K6C_PICK(KS_)                                                                                       \
+    kern = (len % 32 == 0) ? (P == 2 ? k6_cccnn<KS_, 2, 4> : (P == 4 ? k6_cccnn<KS_, 4, 4> : k6_cccnn<KS_, 8, 4>)) \
+                           : (P == 2 ? k6_cccnn<KS_, 2, 2> : (P == 4 ? k6_cccnn<KS_, 4, 2> : k6_cccnn<KS_, 8, 2>))
     switch (kernel_size) {
         case 1: K6C_PICK(1); break;
         case 3: K6C_PICK(3); break;

@@ -209,6 +209,7 @@ def cccnn_reference(m, x):
     dict(input_size=256, output_size=2),
     dict(input_size=128, output_size=3, channels=4, layer_sizes=[8], kernel_sizes=5, padding=2),
     dict(input_size=64, output_size=2, channels=2, layer_sizes=[6, 12, 8], activation=torch.nn.Tanh),
+    dict(input_size=48, output_size=1, channels=3, layer_sizes=[16], activation=torch.nn.ReLU),  # V / 8 not a multiple of 4
 ])
 def test_cccnn_forward_matches_torch(cfg):
     """The summed auto-correlation runs as F^T F on the tensor cores (3xTF32); softmax turns absolute errors of the
