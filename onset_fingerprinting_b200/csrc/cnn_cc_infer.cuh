@@ -185,3 +185,181 @@ __global__ void __launch_bounds__(3 * 32, 2) k6_cccnn(const K6Args a, const int 
 }
 
 }  // namespace ofp
+
+namespace ofp {
+
+// Same network, one CTA (4 warps) per window: the warp-per-window kernel above keeps 33 KB of hi / lo planes per
+// WARP, which caps an SM at 6 warps and leaves it latency bound (issue 28 % busy).  Here the four warps of a CTA
+// share one set of planes: every thread owns positions t = tid + 128 p of the conv layers, the tile diagonals of the
+// Gram matrix are dealt round-robin to the warps (lag bins through shared-memory atomics: neighbouring diagonals of
+// different warps overlap in 15 bins), warp 0 does the softmax and the Linear layer.  6 CTAs = 24 warps per SM.
+template <int KS, int PP, int ND>
+__global__ void __launch_bounds__(128, 6) k6_cccnn_cta(const K6Args a, const int n_ch, const int rows) {
+    extern __shared__ __align__(16) float k6_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int RS = a.row_stride, pad = a.pad;
+    const int Kp = a.coutp[a.n_layers - 1], V = a.lout[a.n_layers - 1], nb = 2 * V - 1;
+    float *prm = k6_smem;
+    const float *fcs = a.params + a.fc_w_off;
+    float *bufA = prm + ((a.conv_params + 3) & ~3);
+    float *bufB = bufA + rows * RS;
+    float *cc = bufB + rows * RS;
+    float *tile = cc + ((V + 3) & ~3) + warp * 128;
+    for (int i = tid; i < a.conv_params; i += 128) prm[i] = a.params[i];
+    for (int i = tid; i < 2 * rows * RS; i += 128) bufA[i] = 0.f;
+    __syncthreads();
+    const float *fcb = a.params + a.fc_b_off;
+    const int g = lane >> 2, tg = lane & 3;
+
+    for (int64_t wi = blockIdx.x; wi < a.n; wi += gridDim.x) {
+        float fcacc[4] = {0.f, 0.f, 0.f, 0.f};  // warp 0
+        for (int c = 0; c < n_ch; ++c) {
+            const float *xw = a.x + wi * a.win_stride + static_cast<int64_t>(c) * a.W;
+            for (int t = tid; t < a.W; t += 128) bufA[pad + t] = __ldg(xw + t);
+            for (int t = pad + a.W + tid; t < RS; t += 128) bufA[t] = 0.f;
+            __syncthreads();
+            float *in = bufA, *outb = bufB;
+            for (int l = 0; l < a.n_layers; ++l) {
+                const int Cin = a.cin[l], Cout = a.cout[l], CP = a.coutp[l], Lout = a.lout[l];
+                const float *wT = prm + a.w_off[l], *bias = prm + a.b_off[l];
+                for (int ob = 0; ob < CP; ob += 8) {
+                    float acc[8][PP];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const float b = bias[ob + o];
+#pragma unroll
+                        for (int p = 0; p < PP; ++p) acc[o][p] = b;
+                    }
+                    for (int ic = 0; ic < Cin; ++ic) {
+                        const float *row = in + ic * RS + tid;
+#pragma unroll
+                        for (int k = 0; k < KS; ++k) {
+                            const float4 w0 = *reinterpret_cast<const float4 *>(wT + (ic * KS + k) * CP + ob);
+                            const float4 w1 = *reinterpret_cast<const float4 *>(wT + (ic * KS + k) * CP + ob + 4);
+                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                            for (int p = 0; p < PP; ++p) {
+                                const float xin = row[128 * p + k];
+#pragma unroll
+                                for (int o = 0; o < 8; ++o) acc[o][p] = fmaf(wv[o], xin, acc[o][p]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const int oc = ob + o;
+                        if (oc < Cout) {
+#pragma unroll
+                            for (int p = 0; p < PP; ++p) {
+                                float h = acc[o][p];
+                                switch (a.act) {  // uniform
+                                    case 0: h = k6_act<0>(h); break;
+                                    case 1: h = k6_act<1>(h); break;
+                                    case 2: h = k6_act<2>(h); break;
+                                    default: break;
+                                }
+                                if (tid + 128 * p < Lout) outb[oc * RS + pad + tid + 128 * p] = h;
+                            }
+                        }
+                    }
+                }
+                for (int oc = 0; oc < Cout; ++oc)
+                    for (int t = pad + Lout + tid; t < RS; t += 128) outb[oc * RS + t] = 0.f;
+                __syncthreads();
+                float *t2 = in; in = outb; outb = t2;
+            }
+            float *Fh = in + pad, *Fl = outb + pad;
+            for (int e = tid; e < Kp * V; e += 128) {
+                const int k = e / V, i = e - k * V;
+                uint32_t hi, lo;
+                tf32_split(Fh[k * RS + i], hi, lo);
+                Fh[k * RS + i] = __uint_as_float(hi);
+                Fl[k * RS + i] = __uint_as_float(lo);
+            }
+            for (int i = tid; i < V; i += 128) cc[i] = 0.f;
+            __syncthreads();
+            for (int d8 = ND * warp; d8 < V / 8; d8 += 4 * ND) {
+                float acc[ND][3][4];
+#pragma unroll
+                for (int n = 0; n < ND; ++n)
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[n][t][e] = 0.f;
+                for (int mt = 0; 8 * (d8 + 2 * mt) < V; ++mt) {
+                    const int i0 = 16 * mt + g, j0 = 8 * (d8 + 2 * mt) + g;
+                    for (int ks = 0; ks < Kp; ks += 8) {
+                        const int r0 = (ks + tg) * RS, r1 = r0 + 4 * RS;
+                        const uint32_t ah[4] = {__float_as_uint(Fh[r0 + i0]), __float_as_uint(Fh[r0 + i0 + 8]),
+                                                __float_as_uint(Fh[r1 + i0]), __float_as_uint(Fh[r1 + i0 + 8])};
+                        const uint32_t al[4] = {__float_as_uint(Fl[r0 + i0]), __float_as_uint(Fl[r0 + i0 + 8]),
+                                                __float_as_uint(Fl[r1 + i0]), __float_as_uint(Fl[r1 + i0 + 8])};
+#pragma unroll
+                        for (int n = 0; n < ND; ++n) {
+                            if (j0 - g + 8 * n < V) {
+                                const uint32_t bh[2] = {__float_as_uint(Fh[r0 + j0 + 8 * n]), __float_as_uint(Fh[r1 + j0 + 8 * n])};
+                                const uint32_t bl[2] = {__float_as_uint(Fl[r0 + j0 + 8 * n]), __float_as_uint(Fl[r1 + j0 + 8 * n])};
+                                mma_tf32(acc[n][1], al, bh);
+                                mma_tf32(acc[n][2], ah, bl);
+                                mma_tf32(acc[n][0], ah, bh);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < ND; ++n) {
+                    tile[g * 8 + 2 * tg] = acc[n][0][0] + (acc[n][1][0] + acc[n][2][0]);
+                    tile[g * 8 + 2 * tg + 1] = acc[n][0][1] + (acc[n][1][1] + acc[n][2][1]);
+                    tile[(g + 8) * 8 + 2 * tg] = acc[n][0][2] + (acc[n][1][2] + acc[n][2][2]);
+                    tile[(g + 8) * 8 + 2 * tg + 1] = acc[n][0][3] + (acc[n][1][3] + acc[n][2][3]);
+                    __syncwarp();
+                    const int off = lane - 15, lagv = 8 * (d8 + n) + off;
+                    if (lane < 23 && lagv >= 0 && lagv < V) {
+                        float sdiag = 0.f;
+                        for (int row = max(0, -off); row < 16 && row + off < 8; ++row) sdiag += tile[row * 8 + row + off];
+                        atomicAdd(&cc[lagv], sdiag);
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                float mx = -INFINITY;
+                for (int i = lane; i < V; i += 32) mx = fmaxf(mx, cc[i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float sum = 0.f;
+                for (int i = lane; i < V; i += 32) {
+                    const float e = __expf(cc[i] - mx);
+                    cc[i] = e;
+                    sum += i == 0 ? e : 2.0f * e;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float inv = 1.0f / sum;
+                for (int i = lane; i < V; i += 32) {
+                    const float pr = cc[i] * inv;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q < a.out_size) {
+                            const float *wq = fcs + (q * n_ch + c) * nb + (V - 1);
+                            fcacc[q] = fmaf(pr, i == 0 ? wq[0] : wq[i] + wq[-i], fcacc[q]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v = fcacc[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && q < a.out_size) a.out[wi * a.out_size + q] = v + __ldg(fcb + q);
+            }
+        }
+    }
+}
+
+}  // namespace ofp

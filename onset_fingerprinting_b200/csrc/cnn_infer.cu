@@ -378,6 +378,30 @@ int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride,
     a.n_params = off;
     const int P = max_len <= 64 ? 2 : (max_len <= 128 ? 4 : 8);
     a.row_stride = 32 * P + 2 * padding + kernel_size + 1;
+    // CTA-per-window kernel (4 warps share one set of planes, 24 warps per SM) unless OFP_K6CC_WARP=1 (A/B)
+    if (getenv("OFP_K6CC_WARP") == nullptr && len <= 256) {
+        const int rows = std::max(rows_a, rows_b);
+        const size_t smem_c = sizeof(float) * (((a.conv_params + 3) & ~3) + 2 * static_cast<size_t>(rows) * a.row_stride +
+                                               ((len + 3) & ~3) + 4 * 128);
+        const int PP = max_len <= 128 ? 1 : 2;
+        void (*kc)(const K6Args, int, int) = nullptr;
+#define K6CC_PICK(KS_) kc = PP == 1 ? k6_cccnn_cta<KS_, 1, 2> : k6_cccnn_cta<KS_, 2, 2>
+        switch (kernel_size) {
+            case 1: K6CC_PICK(1); break;
+            case 3: K6CC_PICK(3); break;
+            case 5: K6CC_PICK(5); break;
+            default: K6CC_PICK(7); break;
+        }
+#undef K6CC_PICK
+        OFP_CUDA_CHECK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_c)));
+        int per_sm_c = 0;
+        OFP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, kc, 128, smem_c));
+        per_sm_c = std::max(per_sm_c, 1);
+        const int grid_c = static_cast<int>(std::min<int64_t>(n_windows, static_cast<int64_t>(sm_count()) * per_sm_c));
+        kc<<<grid_c, 128, smem_c, static_cast<cudaStream_t>(stream)>>>(a, channels, rows);
+        OFP_CUDA_CHECK(cudaGetLastError());
+        return OFP_OK;
+    }
     const int warps = 3;
     const size_t smem = sizeof(float) * (((a.conv_params + 3) & ~3) +
                                          static_cast<size_t>(warps) * ((rows_a + rows_b) * a.row_stride + ((len + 3) & ~3) + 128));
