@@ -193,8 +193,14 @@ namespace ofp {
 // share one set of planes: every thread owns positions t = tid + 128 p of the conv layers, the tile diagonals of the
 // Gram matrix are dealt round-robin to the warps (lag bins through shared-memory atomics: neighbouring diagonals of
 // different warps overlap in 15 bins), warp 0 does the softmax and the Linear layer.  6 CTAs = 24 warps per SM.
+#ifndef OFP_K6CC_ND
+#define OFP_K6CC_ND 4
+#endif
+#ifndef OFP_K6CC_MINCTA
+#define OFP_K6CC_MINCTA 5
+#endif
 template <int KS, int PP, int ND>
-__global__ void __launch_bounds__(128, 6) k6_cccnn_cta(const K6Args a, const int n_ch, const int rows) {
+__global__ void __launch_bounds__(128, OFP_K6CC_MINCTA) k6_cccnn_cta(const K6Args a, const int n_ch, const int rows) {
     extern __shared__ __align__(16) float k6_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int RS = a.row_stride, pad = a.pad;

@@ -385,7 +385,7 @@ int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride,
                                                ((len + 3) & ~3) + 4 * 128);
         const int PP = max_len <= 128 ? 1 : 2;
         void (*kc)(const K6Args, int, int) = nullptr;
-#define K6CC_PICK(KS_) kc = PP == 1 ? k6_cccnn_cta<KS_, 1, 2> : k6_cccnn_cta<KS_, 2, 2>
+#define K6CC_PICK(KS_) kc = PP == 1 ? k6_cccnn_cta<KS_, 1, OFP_K6CC_ND> : k6_cccnn_cta<KS_, 2, OFP_K6CC_ND>
         switch (kernel_size) {
             case 1: K6CC_PICK(1); break;
             case 3: K6CC_PICK(3); break;
