@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--e2e-recordings", type=int, default=3072)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--k1-only", action="store_true",
+                    help="time only the detector kernel (A/B runs and the speed-of-light ladder, scripts/k1_ladder.sh)")
     ap.add_argument("--workload", default="batch", choices=["batch", "hits16", "realtime", "spectral", "cnn"],
                     help="batch = configs[1] (headline); hits16 = configs[2] (16-channel hit mining, K4+K5); "
                          "realtime = configs[3] (4096 concurrent 128-sample block streams)")
@@ -804,10 +807,46 @@ def run_realtime(args):
         "cpu_baseline": None, "roofline": None}))
 
 
+def run_k1_only(args):
+    """Detector kernel alone at the headline shape (A/B runs of kernel variants, the speed-of-light ladder)."""
+    import torch
+
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    from onset_fingerprinting_b200 import detection, synth
+
+    R, N = args.recordings, int(args.seconds * SR)
+    nb = N // BLOCK
+    x = synth.drum_batch_device(R, N, seed=1234)
+    det = detection.BatchedOnsetDetector(R, N_CH, BLOCK, sr=SR)
+    cap = det.default_cap(N)
+    out = (torch.empty((R, cap), dtype=torch.int32, device="cuda"), torch.empty((R, cap), dtype=torch.int32, device="cuda"),
+           torch.empty((R,), dtype=torch.int32, device="cuda"),
+           None if args.no_rel else torch.empty((R, nb * BLOCK, N_CH), dtype=torch.float32, device="cuda"))
+    ms = []
+    for i in range(args.warmup + args.steps):
+        det.reset()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        det.detect_offline(x, int(0.5 * SR), out=out)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            ms.append(a.elapsed_time(b))
+    k1_ms = float(np.mean(ms))
+    peak, src = _peak()
+    alg = R * nb * BLOCK * N_CH * (4 if args.no_rel else 8)
+    print(json.dumps({"metric": "k1_detect alone", "value": R * nb * BLOCK * N_CH / (k1_ms / 1e3), "unit": "channel-samples/s",
+                      "onsets": int(out[2].sum().item()),
+                      "roofline": {"kernel_ms": k1_ms, "achieved": alg / (k1_ms / 1e3) / 1e9, "peak": peak,
+                                   "frac": alg / (k1_ms / 1e3) / 1e9 / peak, "peak_source": src}}))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.k1_only:
+        run_k1_only(args)
     elif args.workload == "hits16":
         run_hits16(args)
     elif args.workload == "realtime":

@@ -26,6 +26,13 @@
 #include <mutex>
 #include "k1_math.cuh"
 
+// Speed-of-light ladder for profiles/ (scripts/k1_ladder.sh): 0 = TMA in + rel out only, 1 = + high-pass,
+// 2 = + dB, 3 = + followers, 4 = + 10**x, 5.. = the full detector (default).  Anything below 5 computes
+// something else than the detector and only exists to time the stages.
+#ifndef OFP_K1_LADDER
+#define OFP_K1_LADDER 9
+#endif
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -402,8 +409,14 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float x = lds_f32(xs + u * step);
-            h[u] = USE_HP ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
+            h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
         }
+#if OFP_K1_LADDER <= 1  // speed-of-light ladder (profiles/): memory path only / + high-pass; results are NOT the detector's
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (store) sts_f32(rs + u * rstep, h[u]);
+        return false;
+#endif
         // exact short-cut (iv): a chunk whose samples all sit below the floor needs no logarithm
         float vmax = 0.0f;
 #pragma unroll
@@ -415,6 +428,12 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
             to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
         }
     }
+#if OFP_K1_LADDER == 2  // + dB
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (store) sts_f32(rs + u * rstep, db[u]);
+    return flags != 0;
+#endif
     bool sliver = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -427,12 +446,20 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
         L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
         dr[u] = __fsub_rn(L.yf, L.ys);
     }
+#if OFP_K1_LADDER == 3  // + followers
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (store) sts_f32(rs + u * rstep, dr[u]);
+    return sliver | (flags != 0);
+#endif
     to_amp_vec<U, false>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+#if OFP_K1_LADDER >= 5  // 4: + 10**x only; 5 and above: the full chunk
         if (DO_MM) minmax_step(L, k, amp[u]);
         L.bmax = fmaxf(L.bmax, amp[u]);
         L.bmin = fminf(L.bmin, amp[u]);
+#endif
         if (store) sts_f32(rs + u * rstep, amp[u]);
     }
     return sliver | (flags != 0);

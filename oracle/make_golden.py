@@ -477,6 +477,106 @@ def gen_stream_fsm(ml):
     print("stream_fsm: located", int(np.isfinite(res[..., 0]).sum()), "of", int((cnt == 3).sum()), "full blocks")
 
 
+CONFIG0 = dict(seconds=60.0, seed=101)
+
+
+def gen_config0(det, ml):
+    """BASELINE.json configs[0] at its stated size: one 3-mic 96 kHz recording of 60 s (~500 hits, ~1500 onsets)
+    through the whole reference chain: detect_onsets_amplitude -> find_onset_groups -> fix_onsets ->
+    Multilaterate3D.locate (streaming, hit by hit)."""
+    x, hits = synth.drum_recording(**CONFIG0)
+    ch, on, rel = det.detect_onsets_amplitude(x, sr=96000)
+    groups = det.find_onset_groups(on, ch, 1000, 3)
+    fixed = det.fix_onsets(x, groups)
+    m = ml.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+    xy = np.full((len(fixed), 2), np.nan)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for h, row in enumerate(fixed):
+            m.ongoing = []
+            r = None
+            for s_ in np.argsort(row, kind="stable"):
+                r = m.locate(int(s_), int(row[s_]))
+            if r is not None:
+                xy[h] = r
+    np.savez_compressed(OUT / "config0_60s.npz", channels=np.asarray(ch, np.int32), onsets=np.asarray(on, np.int64),
+                        rel_sub=rel[::64].astype(np.float32), rel_shape=np.asarray(rel.shape), groups=groups,
+                        fixed=fixed, xy=xy, x_sha=sha(x), env=env(), arrival=hits["arrival"])
+    print("config0: onsets", len(on), "groups", len(groups), "moved", int((fixed != groups).any(1).sum()), "located",
+          int(np.isfinite(xy[:, 0]).sum()))
+
+
+HITS16_OPTS = dict(filter_size=7, d=1, take_abs=True, normalization_cutoff=20, onset_tolerance=150)
+
+
+def hits16_sections(n_hits=240, seed=61, L=768):
+    """Host twin of bench.py's configs[2] input: one [L, 16] section per hit (a burst reaching the 16 mesh sensors
+    between look+4 and look+4+420 samples) and detected onsets = true arrival + jitter."""
+    rng = np.random.default_rng(seed)
+    look = HITS16_OPTS["onset_tolerance"] + HITS16_OPTS["normalization_cutoff"]
+    locs = synth.sensor_xyz(synth.SENSORS_16MESH)
+    c = synth.speed_cm_s("drumhead")
+    t = np.arange(4096) / 96000
+    burst = np.exp(-400.0 * t) * np.sin(2 * np.pi * 900.0 * t)
+    xs = (1e-4 * rng.standard_normal((n_hits, L, 16))).astype(np.float32)
+    on = np.zeros((n_hits, 16), np.int64)
+    for h in range(n_hits):
+        rr, ang = 0.85 * 17.78 * np.sqrt(rng.uniform()), rng.uniform(0, 2 * np.pi)
+        p = np.array([rr * np.cos(ang), rr * np.sin(ang), 0.0])
+        dist = np.sqrt(((locs - p) ** 2).sum(1))
+        delay = np.round(dist / c * 96000).astype(int)
+        for k in range(16):
+            a = look + 4 + delay[k]
+            xs[h, a:, k] += (0.5 * 10.0 / dist[k] * burst[: L - a]).astype(np.float32)
+            on[h, k] = min(max(a + int(rng.integers(-25, 40)), look + 1), L - look - 1)
+    return xs, on
+
+
+NO_SIMD_SORT = "AVX2 AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR"
+
+
+def _hits16_reference(det):
+    xs, on = hits16_sections()
+    fixed = np.zeros_like(on)
+    raised = np.zeros(len(on), np.int32)
+    for h in range(len(on)):
+        try:
+            fixed[h] = det.fix_onsets(xs[h], on[h:h + 1], **HITS16_OPTS)[0]
+        except ValueError:
+            raised[h] = 1
+            fixed[h] = on[h]
+    return xs, on, fixed, raised
+
+
+def gen_hits16(det):
+    """configs[2] with the exact option set the bench runs (tol 150, cutoff 20, d=1, abs, median 7; 16 channels,
+    section 768): the reference's fix_onsets per hit (it can raise).
+
+    H8 (found with this fixture): fix_onsets orders the channels with np.argsort(og) (detection.py:416), and the
+    order numpy gives EQUAL onsets depends on the build/CPU: the AVX2 / AVX-512 x86-simd-sort kernels are not
+    stable, the scalar introsort is (insertion sort for n <= 16).  Because the reference onset moves between
+    pairs (Q6), hits whose later channels hold tied onsets come out differently on the two.  Both are recorded:
+    `fixed` = the reference as numpy runs it on this host, `fixed_scalar` = the same reference in a subprocess
+    with NPY_DISABLE_CPU_FEATURES (scalar sort = stable order, which is what the oracle and the CUDA path pin)."""
+    import os
+    import subprocess
+    import tempfile
+
+    xs, on, fixed, raised = _hits16_reference(det)
+    with tempfile.TemporaryDirectory() as td:
+        tmp = os.path.join(td, "scalar.npz")
+        envv = dict(os.environ, NPY_DISABLE_CPU_FEATURES=NO_SIMD_SORT)
+        subprocess.run([sys.executable, "-m", "oracle.make_golden", "hits16_scalar", tmp], check=True, cwd=str(ROOT), env=envv)
+        sc = np.load(tmp)
+        fixed_scalar, raised_scalar = sc["fixed"], sc["raised"]
+    srt = np.sort(on, axis=1)
+    tied = (srt[:, 1:] == srt[:, :-1]).any(1)
+    differ = (fixed != fixed_scalar).any(1)
+    assert not (differ & ~tied).any(), "the two sort orders may only differ on hits with tied onsets"
+    np.savez_compressed(OUT / "hits16_bench_opts.npz", fixed=fixed, raised=raised, fixed_scalar=fixed_scalar,
+                        raised_scalar=raised_scalar, tied=tied, x_sha=sha(xs), on_sha=sha(on), env=env())
+    print("hits16: moved", float((fixed != on).mean()), "raised", int(raised.sum()), "of", len(on), "| tied hits",
+          int(tied.sum()), "of which the SIMD and scalar argsort orders give different results:", int(differ.sum()))
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     if "fsm" in sys.argv:
@@ -486,6 +586,14 @@ def main():
         gen_frames()
         return
     det, ml = rh.load_reference()
+    if "hits16_scalar" in sys.argv:  # child of gen_hits16, runs with numpy's SIMD sort kernels disabled
+        _, _, fixed, raised = _hits16_reference(det)
+        np.savez(sys.argv[-1], fixed=fixed, raised=raised)
+        return
+    if "sizes" in sys.argv:  # parity at the sizes BASELINE.json states
+        gen_config0(det, ml)
+        gen_hits16(det)
+        return
     if "tools" in sys.argv:  # only the helper-surface fixtures
         gen_tools(det, ml)
         gen_stream_cc(det, ml)
@@ -501,6 +609,8 @@ def main():
     gen_stream_cc(det, ml)
     gen_frames()
     gen_stream_fsm(ml)
+    gen_config0(det, ml)
+    gen_hits16(det)
 
 
 if __name__ == "__main__":

@@ -268,6 +268,11 @@ ORC_API void orc_backtrack(const float *buf, const int32_t *ch, int32_t *deltas,
 
 #define ORC_LAG_NONE INT32_MIN
 
+/* Margin audit (SURVEY.md H2 iii): when non-NULL, orc_cc_lag stores {top-1 value, best other value}
+ * in orc_audit[0..1] and orc_adjust_onset stores {da, db} in orc_audit[2..3].  Set per pair by
+ * orc_fix_group_audit; never set on the plain paths. */
+static __thread double *orc_audit = NULL;
+
 /* Python slice [s:e) on a sequence of length len */
 static inline void py_slice(int64_t *s, int64_t *e, int64_t len) {
     if (*s < 0) { *s += len; if (*s < 0) *s = 0; } else if (*s > len) *s = len;
@@ -295,6 +300,21 @@ ORC_API int32_t orc_cc_lag(const float *x, const float *y, int64_t stride, int64
         if (cnt < cutoff) cnt = cutoff;
         float v = (float)acc / (float)cnt;
         if (best_w < 0 || v > best) { best = v; best_w = k - s; } /* np.argmax: first max wins */
+    }
+    if (orc_audit) { /* second pass: the largest value at any other lag */
+        double second = -INFINITY;
+        for (int64_t k = s; k < e; ++k) {
+            if (k - s == best_w) continue;
+            int64_t m = k - (n - 1);
+            int64_t i0 = m < 0 ? -m : 0, i1 = m > 0 ? n - m : n;
+            double acc = 0.0;
+            for (int64_t i = i0; i < i1; ++i) acc += (double)x[(i + m) * stride] * (double)y[i * stride];
+            int64_t cnt = n - (m < 0 ? -m : m);
+            if (cnt < cutoff) cnt = cutoff;
+            float v = (float)acc / (float)cnt;
+            if (v > second) second = v;
+        }
+        orc_audit[0] = best; orc_audit[1] = second;
     }
     return (int32_t)(adj - best_w);                                 /* detection.py:268 */
 }
@@ -354,6 +374,7 @@ ORC_API void orc_adjust_onset(int32_t oa, int32_t ob, const float *x, const floa
         db = db / (double)ymax;
     }
 #undef EXPW
+    if (orc_audit) { orc_audit[2] = da; orc_audit[3] = db; }
     if (da > db && !(oa + ld < 0)) { out[0] = (int32_t)ld; out[1] = 0; }
     else { out[0] = 0; out[1] = (int32_t)(-ld); }             /* Q7: both else branches */
 }
@@ -390,6 +411,8 @@ ORC_API void orc_median_axis0(const float *in, float *out, int64_t L, int C, int
 #define ORC_FIX_OK 0
 #define ORC_FIX_DEGENERATE 1 /* a - look < 0 or section too short: reference raises / wraps (Q6) */
 #define ORC_FIX_REF_CRASH 2  /* reference raises ValueError in adjust_onset (Q10) */
+
+static __thread double *orc_audit_base = NULL;
 
 /* fix_onsets (detection.py:373-451) for ONE onset group.  audio [N, C]; og [C] in/out.
  * direction: 0 none, 1 "up", 2 "down".  lags_out [C] (optional): the lag returned by
@@ -442,6 +465,7 @@ ORC_API int orc_fix_group(const float *audio, int64_t N, int C, int64_t *og, int
             for (int64_t t = 0; t < z0; ++t) x[t * C] = 0.0f;
             for (int64_t t = 0; t < z1; ++t) y[t * C] = 0.0f;
         }
+        if (orc_audit_base) orc_audit = orc_audit_base + 4 * i;
         int32_t lag = orc_cc_lag(x, y, C, L, (int32_t)o0, (int32_t)o1, 0, 0, 0, cutoff, tol);
         if (lags_out) lags_out[i] = lag;
         if (lag == ORC_LAG_NONE) continue;
@@ -452,7 +476,20 @@ ORC_API int orc_fix_group(const float *audio, int64_t N, int C, int64_t *og, int
         so[r] += cab[0]; so[i] += cab[1];
     }
     free(m0); free(m1);
+    orc_audit = NULL;
     return status;
+}
+
+/* orc_fix_group + the margin audit: audit [C][4] = {cc top-1, cc best other lag, da, db} per later
+ * channel (NaN where the pair was not evaluated). */
+ORC_API int orc_fix_group_audit(const float *audio, int64_t N, int C, int64_t *og, int filter_size, int d,
+                                int direction, int take_abs, int zero_left, int cutoff, int tol,
+                                int32_t *lags_out, double *audit) {
+    for (int i = 0; i < 4 * C; ++i) audit[i] = NAN;
+    orc_audit_base = audit;
+    int st = orc_fix_group(audio, N, C, og, filter_size, d, direction, take_abs, zero_left, cutoff, tol, lags_out);
+    orc_audit_base = NULL; orc_audit = NULL;
+    return st;
 }
 
 /* ------------------------------------------------------------------------------------
