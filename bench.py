@@ -40,10 +40,12 @@ def parse():
     ap.add_argument("--recordings", type=int, default=10000, help="recordings per GPU")
     ap.add_argument("--seconds", type=float, default=5.0, help="length of each recording")
     ap.add_argument("--no-rel", action="store_true", help="onsets-only mode (4 B per channel-sample)")
-    ap.add_argument("--overlap", action="store_true",
-                    help="batch: run the detector of step s+1 next to the post-processing of step s (two streams); "
-                         "measured: no gain, k1_detect is issue-bound and slows by what the overlap hides")
-    ap.add_argument("--e2e-recordings", type=int, default=3072)
+    ap.add_argument("--e2e-recordings", type=int, default=0,
+                    help="recordings of the batch pushed through the host-buffer leg (0 = all that fit in host memory)")
+    ap.add_argument("--skip-hits16", action="store_true", help="batch: leave the configs[2] leg out of the line")
+    ap.add_argument("--hits16-per-gpu", type=int, default=200000, help="batch: hits per GPU of the configs[2] leg")
+    ap.add_argument("--parity-recordings", type=int, default=8,
+                    help="recordings of the timed batch checked against the CPU oracle after the timed region")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -117,29 +119,59 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arms
+# CPU arms: the reference's CPU implementation of the WHOLE chain on the host cores
+#   detector  = the reference's compiled DLL (oracle/_ref/envelope_follower.so) driven by a numpy block loop of the
+#               reference's granularity (oracle/ref_style.py; bit-identical to detection.detect_onsets_amplitude)
+#   later     = find_onset_groups -> fix_onsets -> Multilaterate3D.locate restated with the reference's own numpy /
+#               scipy calls per hit (oracle/ref_chain.py; checked against goldens of the unmodified reference)
+# The reference's .py files themselves live under /root/reference, which does not exist on the GPU box.
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(x):
-    from oracle import ref_style
-
-    ch, on, _ = ref_style.detect_onsets_amplitude(x, block_size=BLOCK, sr=SR)
-    return len(on)
+METRIC = "channel-samples/sec through the onset->lag->multilateration hot path (detect, group, lag-refine, locate)"
+_CPU = {}
 
 
-def cpu_reference_rate(xs: np.ndarray, cores: int):
-    """channel-samples/s of the reference-shaped CPU path (oracle/ref_style.py) over xs [R, N, C]
-    with `cores` worker processes; returns (rate, seconds)."""
-    import multiprocessing as mp
+def _chain_worker(i):
+    from oracle import ref_chain
 
+    if "loc" not in _CPU:
+        from onset_fingerprinting_b200 import synth
+
+        _CPU["loc"] = ref_chain.Locator(synth.SENSORS_3MIC, sr=SR, medium="air")
     t0 = time.perf_counter()
-    if cores > 1:
-        with mp.get_context("fork").Pool(cores) as pool:
-            pool.map(_cpu_worker, list(xs))
-    else:
-        for x in xs:
-            _cpu_worker(x)
-    dt = time.perf_counter() - t0
-    return xs.size / dt, dt
+    n_on, n_hit, n_loc = ref_chain.chain(_CPU["xs"][i], _CPU["loc"], block_size=BLOCK, sr=SR)
+    return n_on, n_hit, n_loc, time.perf_counter() - t0
+
+
+class CpuChain:
+    """Worker pool over recordings held by the parent before the fork (no per-step pickling of audio);
+    the pool and the DLL handle are created ONCE, outside any timed step."""
+
+    def __init__(self, xs: np.ndarray, cores: int):
+        import multiprocessing as mp
+
+        from oracle import ref_style
+
+        ref_style._dll()  # map oracle/_ref/envelope_follower.so in the parent as well (the driver lists loaded .so files)
+        self.kind = ref_style.kind()
+        _CPU["xs"] = xs
+        self.xs, self.cores = xs, cores
+        self.pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+        if self.pool is not None:
+            self.pool.map(_chain_worker, range(min(cores, len(xs))))  # start-up (imports, lag maps) outside the timing
+
+    def run(self):
+        t0 = time.perf_counter()
+        res = self.pool.map(_chain_worker, range(len(self.xs)), chunksize=1) if self.pool else \
+            [_chain_worker(i) for i in range(len(self.xs))]
+        dt = time.perf_counter() - t0
+        res = np.asarray(res, np.float64)
+        return {"seconds": dt, "rate": self.xs.size / dt, "onsets": int(res[:, 0].sum()), "hits": int(res[:, 1].sum()),
+                "located": int(res[:, 2].sum()), "hits_per_sec": float(res[:, 2].sum() / dt)}
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
 
 
 def host_cores():
@@ -149,36 +181,47 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_kind(chain: "CpuChain"):
+    return chain.kind if chain.kind == "reference" else "port"
+
+
+CPU_NOTE = ("detector: the reference's compiled envelope_follower.so under a numpy block loop (oracle/ref_style.py); "
+            "grouping / lag refinement / multilateration: the reference's numpy+scipy calls per hit restated in "
+            "oracle/ref_chain.py (np.correlate, median_filter, fsolve)")
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's CPU implementation of the whole path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from onset_fingerprinting_b200 import synth
-    from oracle import ref_style
 
     cores = host_cores()
     n = int(args.seconds * SR)
-    # one step = a bounded sample of the workload: `cores` recordings (one per worker)
+    # one step = a bounded sample of the workload: `cores` recordings (one per worker), whole chain each
     n_rec = max(cores, 1)
     xs = np.stack([synth.drum_recording(args.seconds, seed=1000 + r)[0][:n] for r in range(n_rec)])
-    times = []
-    for i in range(args.warmup + args.steps):
-        rate, dt = cpu_reference_rate(xs, cores)
-        if i >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
+    chain = CpuChain(xs, cores)
+    runs = [chain.run() for _ in range(args.warmup + args.steps)][args.warmup:]
+    chain.close()
+    ms = 1e3 * float(np.mean([r["seconds"] for r in runs]))
     value = xs.size / (ms / 1e3)
-    sample = f"{n_rec} recordings x {args.seconds:g} s x {N_CH} ch per step ({xs.size} channel-samples)"
+    sample = f"{n_rec} recordings x {args.seconds:g} s x {N_CH} ch per step ({xs.size} channel-samples), whole chain"
+    h16 = None
+    if args.workload in ("batch", "hits16") and not args.skip_hits16:
+        h16 = hits16_reference(cores, args.cpu_seconds)
     line = {
-        "impl": "reference", "metric": "channel-samples/sec through the onset->lag->multilateration hot path",
+        "impl": "reference", "metric": METRIC,
         "value": value, "unit": "channel-samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.recordings),
-        "cpu_baseline": {"value": value, "unit": "channel-samples/s", "cores": cores, "kind": ref_style.kind(),
-                         "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "channel-samples/s", "cores": cores, "kind": cpu_kind(chain),
+                         "sample": sample, "note": CPU_NOTE, "onsets": runs[-1]["onsets"], "hits": runs[-1]["hits"],
+                         "located": runs[-1]["located"], "localised_hits_per_sec": runs[-1]["hits_per_sec"]},
         "e2e": {"value": value, "unit": "channel-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "localised_hits_per_sec": runs[-1]["hits_per_sec"], "hits16": h16,
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -191,8 +234,7 @@ def workload_config(args, n_rec):
         "recordings_per_gpu": n_rec, "seconds": args.seconds, "channels": N_CH, "sr": SR, "block_size": BLOCK,
         "mode": "onsets_only" if args.no_rel else "drop_in (rel envelope written to HBM)",
         "l2": "inputs larger than L2 (no flush needed)",
-        "pipelining": "detector of step s+1 overlaps grouping/lag/multilateration of step s (two streams)"
-                      if getattr(args, "overlap", False) else "stages back to back",
+        "pipelining": "stages back to back on one stream",
     }
 
 
@@ -254,64 +296,21 @@ def run_ours(args):
         step()
     barrier()
     launches = 0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    # Default: the stages of a step run back to back on one stream.  --overlap pipelines consecutive steps
-    # (detector of step s+1 on s_det next to grouping / lag refinement / multilateration of step s on s_post,
-    # onset lists double buffered).  Measured on B200: 94.3 vs 95.0 ms per step -- k1_detect is instruction
-    # issue bound, the co-running kernels take the issue slots they were meant to fill (k1 85.2 -> 92.4 ms).
-    overlap = args.overlap
-    if hp._out is None:  # --warmup 0: the output buffers are allocated by the first pass
-        step()
-        torch.cuda.synchronize()
-    outs = [hp._out, tuple(torch.empty_like(t) if i < 3 else t for i, t in enumerate(hp._out))]
-    cur = torch.cuda.current_stream()
-    s_det, s_post = (torch.cuda.Stream(), torch.cuda.Stream()) if overlap else (cur, cur)
-    k1_done = [torch.cuda.Event() for _ in range(args.steps)]
-    post_done = [torch.cuda.Event() for _ in range(args.steps)]
-    k1_out = {}
-
-    def launch_k1(i):
-        with torch.cuda.stream(s_det):
-            if i >= 2:
-                s_det.wait_event(post_done[i - 2])  # its onset buffers are free again
-            ev[i][1].record()
-            det.reset()
-            k1_out[i] = det.detect_offline(x, warm_n, out=outs[i & 1])
-            ev[i][2].record()
-            k1_done[i].record()
-
-    def post(i):
-        with torch.cuda.stream(s_post):
-            s_post.wait_event(k1_done[i])
-            ch_, ix_, cnt_, rel_ = k1_out.pop(i)
-            hit_rec, hit_on, _ = detection.find_onset_groups_batch(ch_, ix_, cnt_, N_CH, **hp.group_kw)
-            fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on)
-            xy, lstat = hp.ml.locate_batch(fixed)
-            last["hits"] = pipeline.HitBatch(hit_rec, hit_on, fixed, lags, fstat, xy, lstat, cnt_, rel_)
-            gather(last["hits"])
-            post_done[i].record()
-
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
         t_wall = time.perf_counter()
-        ev[0][0].record()
-        s_det.wait_stream(cur)
-        s_post.wait_stream(cur)
-        launch_k1(0)
-        for i in range(args.steps):
-            if i + 1 < args.steps:
-                launch_k1(i + 1)
-            post(i)
+        start.record()
+        for i in range(args.steps):  # stages back to back on one stream
+            last["hits"] = hp.run(x, return_rel=not args.no_rel, warm_n=warm_n, k1_events=ev[i])
+            gather(last["hits"])
             launches += LAUNCHES_PER_STEP
-        cur.wait_stream(s_det)
-        cur.wait_stream(s_post)
-        end = torch.cuda.Event(enable_timing=True)
         end.record()
         barrier()
         t_wall = time.perf_counter() - t_wall
-    total_ms = ev[0][0].elapsed_time(end)
-    k1_ms = float(np.mean([k0.elapsed_time(k1) for _, k0, k1 in ev]))
+    total_ms = start.elapsed_time(end)
+    k1_ms = float(np.mean([k0.elapsed_time(k1) for k0, k1 in ev]))
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,33 +329,39 @@ def run_ours(args):
         n_onsets, n_hits, n_located = (int(v) for v in t.tolist())
     else:
         n_onsets, n_hits, n_located = n_onsets, n_hits, n_located
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak, peak_src = _peak()
     bytes_per_unit = 4 if args.no_rel else 8
     alg_bytes = R * nb * BLOCK * N_CH * bytes_per_unit
     achieved = alg_bytes / (k1_ms / 1e3) / 1e9
-    traffic = None
-    try:  # DRAM bytes per launch, scaled from the committed ncu --set full capture of this kernel
-        tj = json.loads((ROOT / "profiles" / "r01_k1_traffic.json").read_text())
-        traffic = (tj["dram_read_bytes_per_input_sample"] * R * N_CH * (nb * BLOCK + warm_n)
-                   + (0 if args.no_rel else tj["dram_write_bytes_per_output_sample"] * R * N_CH * nb * BLOCK))
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of one k1_detect launch from the committed ncu --set full capture of THIS build at THIS shape
+        tj = json.loads((ROOT / "profiles" / "r02_k1_traffic.json").read_text())
+        if tj.get("recordings") == R and abs(tj.get("seconds", 0) - args.seconds) < 1e-9 and bool(tj.get("rel")) != args.no_rel:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel": "k1_detect", "kernel_ms": k1_ms,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_channel_sample": bytes_per_unit}
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes, "kernel": "k1_detect",
+                "kernel_ms": k1_ms, "peak_source": peak_src, "algorithmic_bytes_per_channel_sample": bytes_per_unit}
 
+    parity = parity_sample(args, torch, x, hp, hb) if args.parity_recordings > 0 else None
+    e2e = None if args.skip_e2e else run_e2e(args, torch, hp, x, dist, world, rank)  # every rank feeds its own GPU
+    cpu = None
+    if rank == 0 and not args.skip_cpu:
+        cpu = run_cpu_baseline(args, x)
+    del hb
+    last.clear()
+    hp._out = None
+    hp._host = None
+    del x
+    torch.cuda.empty_cache()
+    h16 = None
+    if not args.skip_hits16:
+        h16 = hits16_leg(args, torch, dist, world, rank, local, args.hits16_per_gpu * world, steps=3, warmup=2)
     line = None
-    e2e = run_e2e(args, torch, detection, _lib, synth, dist, world, rank)  # every rank feeds its own GPU
     if rank == 0:
-        cpu = None if args.skip_cpu else run_cpu_baseline(args, x)
         line = {
-            "metric": "channel-samples/sec through the onset->lag->multilateration hot path",
+            "metric": METRIC,
             "value": value, "unit": "channel-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -364,7 +369,7 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clk.summary(), "onsets_per_step": n_onsets,
             "hits_per_step": n_hits, "located_hits_per_step": n_located,
             "localised_hits_per_sec": n_located / (ms_per_step / 1e3),
-            "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "wall_ms_per_step": 1e3 * t_wall / args.steps, "parity_sample": parity, "hits16": h16,
         }
     if dist is not None:
         dist.barrier()
@@ -373,61 +378,138 @@ def run_ours(args):
         print(json.dumps(line))
 
 
-def run_e2e(args, torch, detection, _lib, synth, dist=None, world=1, rank=0):
-    """Same metric through the C-ABI host entry point: pinned host audio in, onsets out.  With N ranks every
+def parity_sample(args, torch, x, hp, hb):
+    """Self-check of the timed batch: K randomly chosen recordings of the step that was just timed go back to the
+    host and through the CPU oracle (detector, grouping, lag refinement, multilateration); the device results of
+    those recordings must be identical (onsets, groups, refined onsets, lags, None set), the positions within
+    1e-4 relative and the envelope within 1e-5 relative (north_star)."""
+    from oracle import oracle as orc
+    from onset_fingerprinting_b200 import synth
+
+    R = x.shape[0]
+    rng = np.random.default_rng(12345)
+    recs = sorted(rng.choice(R, size=min(args.parity_recordings, R), replace=False).tolist())
+    ch_d, ix_d, cnt_d, rel_d = hp._out
+    rec_all = hb.rec.cpu().numpy()
+    out = {"recordings": len(recs), "onsets_equal": True, "groups_equal": True, "fixed_equal": True, "lags_equal": True,
+           "none_set_equal": True, "xy_max_rel_err": 0.0, "rel_max_rel_err": 0.0, "rel_bit_equal_frac": 1.0,
+           "onsets_checked": 0, "hits_checked": 0, "located_checked": 0, "checked_against": "oracle/oracle_c.c (CPU)"}
+    ml = orc.Multilaterate3D(synth.SENSORS_3MIC, sr=SR, medium="air")
+    biteq = []
+    for r in recs:
+        xr = x[r].cpu().numpy()
+        c_o, o_o, rel_o = orc.detect_onsets_amplitude(xr, block_size=BLOCK, sr=SR, return_rel=rel_d is not None)
+        k = int(cnt_d[r].item())
+        out["onsets_equal"] &= (ch_d[r, :k].cpu().tolist() == c_o) and (ix_d[r, :k].cpu().tolist() == o_o)
+        out["onsets_checked"] += len(o_o)
+        if rel_d is not None:
+            got = rel_d[r].cpu().numpy()
+            err = np.abs(got - rel_o) / np.maximum(np.abs(rel_o), 1e-6)
+            out["rel_max_rel_err"] = max(out["rel_max_rel_err"], float(err.max()))
+            biteq.append(float((got == rel_o).mean()))
+        groups = orc.find_onset_groups(o_o, c_o, 1000, N_CH)
+        sel = rec_all == r
+        g_d = hb.onsets.cpu().numpy()[sel]
+        if groups is None:
+            out["groups_equal"] &= len(g_d) == 0
+            continue
+        out["groups_equal"] &= np.array_equal(g_d, groups)
+        fixed, fstat, lags = orc.fix_onsets(xr, groups, return_status=True)
+        out["fixed_equal"] &= np.array_equal(hb.fixed.cpu().numpy()[sel], fixed)
+        out["lags_equal"] &= np.array_equal(hb.lags.cpu().numpy()[sel], lags)
+        out["hits_checked"] += len(fixed)
+        xy_d, st_d = hb.xy.cpu().numpy()[sel], hb.loc_status.cpu().numpy()[sel]
+        for h, row in enumerate(fixed):
+            got, st = ml.locate_hit([0, 1, 2], row[:3])
+            out["none_set_equal"] &= (got is None) == (st_d[h] != 0)
+            if got is not None and st_d[h] == 0:
+                out["located_checked"] += 1
+                e = np.abs(xy_d[h] - np.asarray(got)) / np.maximum(np.abs(np.asarray(got)), 1e-3)
+                out["xy_max_rel_err"] = max(out["xy_max_rel_err"], float(e.max()))
+    if biteq:
+        out["rel_bit_equal_frac"] = float(np.mean(biteq))
+    out["ok"] = bool(out["onsets_equal"] and out["groups_equal"] and out["fixed_equal"] and out["lags_equal"]
+                     and out["none_set_equal"] and out["xy_max_rel_err"] <= 1e-4 and out["rel_max_rel_err"] <= 1e-5)
+    for k_ in ("onsets_equal", "groups_equal", "fixed_equal", "lags_equal", "none_set_equal"):
+        out[k_] = bool(out[k_])
+    return out
+
+
+def run_e2e(args, torch, hp, x, dist=None, world=1, rank=0):
+    """Same metric end to end through the host-buffer entry of the public API (pipeline.HotPath.run_host): the
+    batch starts in pinned HOST memory, is uploaded in time segments while the detector runs, goes through
+    grouping, lag refinement and multilateration on the device, and the per-hit records (and, in drop-in mode,
+    the whole rel envelope) return to pinned host memory inside the timed region.  Both modes are reported;
+    `value` is the drop-in one (the mode `value` of the line is quoted in) unless --no-rel.  With N ranks every
     rank pushes its own recordings through its own GPU at the same time; value = all ranks' units over the
     slowest rank's wall time."""
-    import ctypes as C
+    import psutil
 
-    Re, N = min(args.e2e_recordings, args.recordings), int(args.seconds * SR)
-    xd = synth.drum_batch_device(Re, N, seed=99, rec_offset=rank * Re)
-    xh = torch.empty(xd.shape, dtype=torch.float32, pin_memory=True)
-    xh.copy_(xd)
+    R, N, Cn = x.shape
+    per_rec = N * Cn * 4
+    avail = psutil.virtual_memory().available / max(world, 1)
+    want = args.e2e_recordings if args.e2e_recordings > 0 else R
+    modes = ["onsets_only"] if args.no_rel else ["onsets_only", "drop_in"]
+    fit = int(0.55 * avail / (per_rec * (2 if "drop_in" in modes else 1)))
+    Re = max(1, min(want, R, fit))
+    xh = torch.empty((Re, N, Cn), dtype=torch.float32, pin_memory=True)
+    xh.copy_(x[:Re])
     torch.cuda.synchronize()
-    del xd
-    p = detection.make_params(N_CH, BLOCK, sr=SR)
-    cap = int(N_CH * (N // 1323 + 2))
-    ch = torch.empty((Re, cap), dtype=torch.int32, pin_memory=True)
-    ix = torch.empty((Re, cap), dtype=torch.int32, pin_memory=True)
-    cnt = torch.empty((Re,), dtype=torch.int32, pin_memory=True)
+    hp_e = hp if Re == R else None
+    if hp_e is None:
+        from onset_fingerprinting_b200 import pipeline, synth
 
-    def call():
-        _lib.check(_lib.lib().ofp_detect_offline_host(
-            C.byref(p), C.c_void_p(xh.data_ptr()), C.c_int64(Re), C.c_int64(N), C.c_int64(int(0.5 * SR)), None,
-            C.c_void_p(ch.data_ptr()), C.c_void_p(ix.data_ptr()), C.c_void_p(cnt.data_ptr()), C.c_int32(cap)))
-
-    for _ in range(2):
-        call()
-    reps = 3
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        call()
-    dt = (time.perf_counter() - t0) / reps
-    if dist is not None:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    units = world * Re * (N // BLOCK) * BLOCK * N_CH
-    return {"value": units / dt, "unit": "channel-samples/s", "h2d_bytes_per_step": int(world * xh.numel() * 4),
-            "d2h_bytes_per_step": int(world * (ch.numel() + ix.numel() + cnt.numel()) * 4),
-            "recordings": world * Re, "ms": dt * 1e3, "mode": "onsets_only (rel not copied back)",
-            "entry": "ofp_detect_offline_host (one call per rank, concurrently)"}
+        hp_e = pipeline.HotPath(Re, N_CH, synth.SENSORS_3MIC, medium="air", sr=SR, block_size=BLOCK)
+    xd = x[:Re]  # the resident device copy the upload lands in (lag refinement reads its sections from it)
+    res = {}
+    relh = None
+    for mode in modes:
+        if mode == "drop_in":
+            relh = torch.empty((Re, (N // BLOCK) * BLOCK, Cn), dtype=torch.float32, pin_memory=True)
+        out = hp_e.run_host(xh, rel_host=relh, x_dev=xd)  # warm (allocations, pinned result buffers)
+        reps = 2
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = hp_e.run_host(xh, rel_host=relh, x_dev=xd)
+        dt = (time.perf_counter() - t0) / reps
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        units = world * Re * (N // BLOCK) * BLOCK * N_CH
+        d2h = sum(int(v.numel() * v.element_size()) for v in out.values()) + (relh.numel() * 4 if relh is not None else 0)
+        res[mode] = {"value": units / dt, "ms": dt * 1e3, "h2d_bytes_per_step": int(world * xh.numel() * 4),
+                     "d2h_bytes_per_step": int(world * d2h), "h2d_gbs_per_rank": xh.numel() * 4 / dt / 1e9,
+                     "hits": int(out["rec"].shape[0]) * world, "located": int((out["loc_status"] == 0).sum()) * world,
+                     "localised_hits_per_sec": int((out["loc_status"] == 0).sum()) * world / dt}
+    head = res["onsets_only" if args.no_rel else "drop_in"]
+    del xh, relh
+    return {"value": head["value"], "unit": "channel-samples/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+            "d2h_bytes_per_step": head["d2h_bytes_per_step"], "ms": head["ms"], "recordings": world * Re,
+            "recordings_of_batch": f"{Re} of {R} per GPU" + ("" if Re == R else " (host memory bound)"),
+            "mode": "onsets_only" if args.no_rel else "drop_in (rel envelope copied back to the host)",
+            "modes": res, "stages": "upload + detector + grouping + lag refinement + multilateration + results to host",
+            "entry": "pipeline.HotPath.run_host (one call per rank, concurrently): ofp_copy2d_async + ofp_detect_offline / "
+                     "ofp_detect_continue per time segment, then ofp_group_onsets / ofp_fix_onsets_ex / ofp_locate_hits"}
 
 
 def run_cpu_baseline(args, x):
-    """The reference-shaped CPU path on a bounded sample of the SAME device-generated audio."""
-    from oracle import ref_style
-
+    """The reference's CPU path -- whole chain -- on a bounded sample of the SAME device-generated audio."""
     cores = host_cores()
-    # ~2.5e6 channel-samples/s/core: size the sample for about args.cpu_seconds of work
+    # ~2.3e6 channel-samples/s/core through the whole chain: size the sample for about args.cpu_seconds of work
     per_rec = x.shape[1] * x.shape[2]
-    n_rec = int(max(cores, min(x.shape[0], args.cpu_seconds * 2.5e6 * cores / per_rec)))
+    n_rec = int(max(cores, min(x.shape[0], args.cpu_seconds * 2.3e6 * cores / per_rec)))
+    n_rec = max(cores, n_rec // cores * cores)
     xs = x[:n_rec].cpu().numpy()
-    rate, dt = cpu_reference_rate(xs, cores)
-    return {"value": rate, "unit": "channel-samples/s", "cores": cores, "kind": ref_style.kind(),
-            "sample": f"{n_rec} of the step's recordings ({xs.size} channel-samples, {dt:.1f} s)"}
+    chain = CpuChain(xs, cores)
+    r = chain.run()
+    chain.close()
+    return {"value": r["rate"], "unit": "channel-samples/s", "cores": cores, "kind": cpu_kind(chain),
+            "sample": f"{n_rec} of the step's recordings ({xs.size} channel-samples, {r['seconds']:.1f} s), whole chain",
+            "note": CPU_NOTE, "onsets": r["onsets"], "hits": r["hits"], "located": r["located"],
+            "localised_hits_per_sec": r["hits_per_sec"]}
 
 
 def _peak():
@@ -437,9 +519,12 @@ def _peak():
         return 6650.0, "fallback 6.65 TB/s"
 
 
+HITS16 = dict(Cn=16, L=768, tol=150, cut=20)
+HITS16_KW = dict(filter_size=7, d=1, take_abs=True, normalization_cutoff=20, onset_tolerance=150)
+
+
 def run_hits16(args):
-    """configs[2]: 16-channel mesh hit mining -- K4 (lag refinement, tol 150 / cutoff 20 / d=1 / abs /
-    median 7 as in notebooks/refresh.org:1507-1509) + K5 on the first three arrivals; hits sharded by rank."""
+    """--workload hits16: configs[2] on its own (1 M hits sharded over the ranks, strong scaling)."""
     import torch
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
@@ -449,10 +534,23 @@ def run_hits16(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d = hits16_leg(args, torch, dist, world, rank, local, args.hits, args.steps, args.warmup)
+    if rank == 0:
+        d.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                  "scaling": "strong", "vs_baseline": None, "data": "synthetic"})
+        print(json.dumps(d))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def hits16_leg(args, torch, dist, world, rank, local, hits_total, steps, warmup):
+    """configs[2]: 16-channel mesh hit mining -- K4 (lag refinement, tol 150 / cutoff 20 / d=1 / abs /
+    median 7 as in notebooks/refresh.org:1507-1509) + K5 on the first three arrivals; hits sharded by rank.
+    Returns the leg's record (rank 0; None elsewhere): value, roofline of k4_fix, cpu_baseline, e2e."""
     from onset_fingerprinting_b200 import detection, multilateration, parallel, synth
 
-    Cn, L, tol, cut = 16, 768, 150, 20
-    lo, hi = parallel.shard_range(args.hits, rank, world)
+    Cn, L, tol, cut = HITS16["Cn"], HITS16["L"], HITS16["tol"], HITS16["cut"]
+    lo, hi = parallel.shard_range(hits_total, rank, world)
     H = hi - lo
     look = tol + cut
     # one section per hit: a burst whose wavefront reaches the 16 mesh sensors between look and look+420
@@ -461,16 +559,20 @@ def run_hits16(args):
     g = torch.Generator(device="cuda").manual_seed(rank)
     onsets = (look + 4 + torch.randint(0, 400, (H, Cn), generator=g, device="cuda")).to(torch.int32)
     ml = multilateration.Multilaterate3D(synth.SENSORS_16MESH, sr=SR, medium="drumhead")
-    kw = dict(filter_size=7, d=1, take_abs=True, normalization_cutoff=cut, onset_tolerance=tol, max_section=L)
+    kw = dict(max_section=L, **HITS16_KW)
 
-    def step():
+    def step(events=None):
+        if events:
+            events[0].record()
         fixed, lags, st = detection.fix_onsets_batch(x, None, onsets, **kw)
+        if events:
+            events[1].record()
         first3 = torch.argsort(fixed, dim=1, stable=True)[:, :3].to(torch.int32)
         on3 = torch.gather(fixed, 1, first3.long())
         xy, lst = ml.locate_batch(on3, first3)
-        return fixed, st, xy, lst
+        return fixed, lags, st, first3, xy, lst
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         out = step()
     torch.cuda.synchronize()
     if dist is not None:
@@ -478,82 +580,138 @@ def run_hits16(args):
     e0, e1, ek = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), []
     with ClockSampler(local) as clk:
         e0.record()
-        for _ in range(args.steps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fixed, lags, st = detection.fix_onsets_batch(x, None, onsets, **kw)
-            b.record()
-            ek.append((a, b))
-            first3 = torch.argsort(fixed, dim=1, stable=True)[:, :3].to(torch.int32)
-            xy, lst = ml.locate_batch(torch.gather(fixed, 1, first3.long()), first3)
+        for _ in range(steps):
+            ek.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            fixed, lags, st, first3, xy, lst = step(ek[-1])
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-    ms /= args.steps
+    ms /= steps
     k4_ms = float(np.mean([a.elapsed_time(b) for a, b in ek]))
     peak, src = _peak()
     bytes_per_hit = 4 * Cn * L + 16 * Cn + 48
     achieved = bytes_per_hit * H / (k4_ms / 1e3) / 1e9
     ok = int((st == 0).sum().item()); loc = int((lst == 0).sum().item())
+    if dist is not None:
+        t = torch.tensor([ok, loc], device="cuda"); dist.all_reduce(t); ok, loc = (int(v) for v in t.tolist())
     import ctypes as C
     from onset_fingerprinting_b200 import _lib
     cs = (C.c_uint64 * 4)()
     _lib.check(_lib.lib().ofp_cc_screen_stats(cs, 1))
     screen = {"pairs": int(cs[0]), "single_survivor": int(cs[1]), "few_survivors_exact": int(cs[2]),
               "exact_all_lags": int(cs[3])}
-    cpu = e2e = None
-    if rank == 0 and not args.skip_cpu:
-        cpu = hits16_cpu_baseline(x, onsets, kw, args.cpu_seconds)
+    cpu = e2e = parity = None
     if rank == 0:
-        e2e = hits16_e2e(torch, detection, ml, x, onsets, kw)
-    if rank == 0:
-        print(json.dumps({
-            "metric": "hits/sec through lag refinement + multilateration (16-channel hit mining)",
-            "value": args.hits / (ms / 1e3), "unit": "hits/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64 accumulate / f32 data", "data": "synthetic",
-            "config": {"workload": f"configs[2]: {args.hits} hits x 16 ch, section {L}, tol {tol}, cutoff {cut}, d=1, abs, "
-                                   "median 7; K5 on the first three arrivals", "l2": "48.6 GB of sections per 1M hits, larger than L2"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k4_fix", "kernel_ms": k4_ms, "peak_source": src,
-                         "algorithmic_bytes_per_hit": bytes_per_hit,
-                         "note": "K4 at 16 ch is instruction bound (median filter, section preparation, float32 "
-                                 "lag screening = 41 % of the instructions, reductions), not HBM bound"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clk.summary(),
-            "fix_ok": ok, "located": loc, "cc_screening": screen}))
-    if dist is not None:
-        dist.barrier(); dist.destroy_process_group()
+        parity = hits16_parity(x, onsets, fixed, lags, st, first3, xy, lst, min(args.parity_recordings * 8, H))
+        if not args.skip_cpu:
+            cpu = hits16_cpu_baseline(x, onsets, args.cpu_seconds)
+        if not args.skip_e2e:
+            e2e = hits16_e2e(torch, detection, ml, x, onsets, kw)
+    del x
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {
+        "metric": "hits/sec through lag refinement + multilateration (16-channel hit mining)",
+        "value": hits_total / (ms / 1e3), "unit": "hits/s", "ms_per_step": ms, "dtype": "f64 accumulate / f32 data",
+        "localised_hits_per_sec": loc / (ms / 1e3),
+        "config": {"workload": f"configs[2]: {hits_total} hits x 16 ch, section {L}, tol {tol}, cutoff {cut}, d=1, abs, "
+                               "median 7; K5 on the first three arrivals", "hits_per_gpu": H,
+                   "l2": "48.6 GB of sections per 1M hits, larger than L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k4_fix", "kernel_ms": k4_ms, "peak_source": src,
+                     "algorithmic_bytes_per_hit": bytes_per_hit,
+                     "note": "K4 at 16 ch is instruction bound (median filter, section preparation, float32 "
+                             "lag screening, reductions), not HBM bound"},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * steps, "clocks": clk.summary(),
+        "fix_ok": ok, "located": loc, "cc_screening": screen, "parity_sample": parity}
 
 
-def _fix_worker(job):
+def hits16_parity(x, onsets, fixed, lags, st, first3, xy, lst, n):
+    """Self-check of the timed hits: the first n hits of the step through the CPU oracle."""
     from oracle import oracle as orc
+    from onset_fingerprinting_b200 import synth
 
-    xs, on, kw = job
-    n = 0
-    for k in range(len(xs)):
-        orc.fix_onsets(xs[k], on[k:k + 1], filter_size=kw["filter_size"], d=kw["d"], take_abs=kw["take_abs"],
-                       normalization_cutoff=kw["normalization_cutoff"], onset_tolerance=kw["onset_tolerance"])
+    xs, on = x[:n].cpu().numpy(), onsets[:n].cpu().numpy().astype(np.int64)
+    fx, lg, ss = fixed[:n].cpu().numpy(), lags[:n].cpu().numpy(), st[:n].cpu().numpy()
+    f3, xyh, lsh = first3[:n].cpu().numpy(), xy[:n].cpu().numpy(), lst[:n].cpu().numpy()
+    ml = orc.Multilaterate3D(synth.SENSORS_16MESH, sr=SR, medium="drumhead")
+    eq_f = eq_l = eq_s = eq_n = True
+    err = 0.0
+    nloc = 0
+    for h in range(n):
+        f_o, s_o, l_o = orc.fix_onsets(xs[h], on[h:h + 1], return_status=True, **HITS16_KW)
+        eq_f &= np.array_equal(f_o[0], fx[h]); eq_l &= np.array_equal(l_o[0], lg[h]); eq_s &= int(s_o[0]) == int(ss[h])
+        got, stt = ml.locate_hit(f3[h], f_o[0][f3[h]])
+        eq_n &= (got is None) == (lsh[h] != 0)
+        if got is not None and lsh[h] == 0:
+            nloc += 1
+            err = max(err, float((np.abs(xyh[h] - np.asarray(got)) / np.maximum(np.abs(np.asarray(got)), 1e-3)).max()))
+    return {"hits": n, "fixed_equal": bool(eq_f), "lags_equal": bool(eq_l), "status_equal": bool(eq_s),
+            "none_set_equal": bool(eq_n), "located_checked": nloc, "xy_max_rel_err": err,
+            "ok": bool(eq_f and eq_l and eq_s and eq_n and err <= 1e-4), "checked_against": "oracle/oracle_c.c (CPU)"}
+
+
+def _h16_worker(i):
+    from oracle import ref_chain
+
+    if "loc16" not in _CPU:
+        from onset_fingerprinting_b200 import synth
+
+        _CPU["loc16"] = ref_chain.Locator(synth.SENSORS_16MESH, sr=SR, medium="drumhead")
+    xs, on, cores = _CPU["h16"]
+    n = loc = 0
+    for k in range(i, len(xs), cores):
+        try:
+            f = ref_chain.fix_onsets(xs[k], on[k:k + 1], **HITS16_KW)[0]
+        except ValueError:  # the reference raises on these hits (SURVEY Q10)
+            n += 1
+            continue
+        f3 = np.argsort(f, kind="stable")[:3]
+        loc += _CPU["loc16"].locate_hit(f[f3], f3) is not None
         n += 1
-    return n
+    return n, loc
 
 
-def hits16_cpu_baseline(x, onsets, kw, budget_s):
-    """The oracle's C port of fix_onsets (the reference's numpy fix_onsets runs ~0.3 ms/hit at 3 ch and
-    cannot be imported on the GPU box) over a bounded sample of the step's hits on all host cores."""
+def _hits16_cpu(xs, on, cores):
     import multiprocessing as mp
 
-    cores = host_cores()
-    n = int(min(x.shape[0], max(cores * 8, 400 * cores * budget_s / 15.0)))
-    xs, on = x[:n].cpu().numpy(), onsets[:n].cpu().numpy().astype(np.int64)
-    jobs = [(xs[i::cores], on[i::cores], kw) for i in range(cores)]
-    t0 = time.perf_counter()
+    _CPU["h16"] = (xs, on, cores)
     with mp.get_context("fork").Pool(cores) as pool:
-        done = sum(pool.map(_fix_worker, jobs))
-    dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": "hits/s", "cores": cores, "kind": "port",
-            "sample": f"{done} of the step's hits, lag refinement only (oracle_c.c:orc_fix_group), {dt:.1f} s"}
+        pool.map(_h16_worker, [len(xs)] * cores)  # start-up outside the timing (empty slices)
+        t0 = time.perf_counter()
+        res = pool.map(_h16_worker, range(cores))
+        dt = time.perf_counter() - t0
+    done, loc = sum(r[0] for r in res), sum(r[1] for r in res)
+    return done, loc, dt
+
+
+def hits16_cpu_baseline(x, onsets, budget_s):
+    """The reference's numpy/scipy calls per hit (oracle/ref_chain.py: median_filter + np.correlate per channel pair
+    + fsolve) over a bounded sample of the step's hits on all host cores."""
+    cores = host_cores()
+    n = int(min(x.shape[0], max(cores * 4, 4000 * cores * budget_s / 15.0)))  # ~9e3 hits/s on 16 cores
+    xs, on = x[:n].cpu().numpy(), onsets[:n].cpu().numpy().astype(np.int64)
+    done, loc, dt = _hits16_cpu(xs, on, cores)
+    return {"value": done / dt, "unit": "hits/s", "cores": cores, "kind": "port", "located": loc,
+            "sample": f"{done} of the step's hits, lag refinement + multilateration at the reference's granularity "
+                      f"(oracle/ref_chain.py), {dt:.1f} s"}
+
+
+def hits16_reference(cores, budget_s):
+    """--impl reference: the same CPU path on host-generated sections (oracle/make_golden.py:hits16_sections)."""
+    from oracle.make_golden import hits16_sections
+
+    uniq, reps = 100 * cores, max(1, int(40 * budget_s / 15.0))
+    xs, on = hits16_sections(n_hits=uniq, seed=62)
+    xs, on = np.concatenate([xs] * reps), np.concatenate([on] * reps)  # the per-hit cost does not depend on uniqueness
+    done, loc, dt = _hits16_cpu(xs, on, cores)
+    return {"metric": "hits/sec through lag refinement + multilateration (16-channel hit mining)", "value": done / dt,
+            "unit": "hits/s", "cores": cores, "kind": "port", "located": loc,
+            "sample": f"{done} synthetic 16-channel hits ({uniq} distinct, section 768, tol 150, cutoff 20, d=1, abs, "
+                      f"median 7), {dt:.1f} s"}
 
 
 def hits16_e2e(torch, detection, ml, x, onsets, kw, n=40000):

@@ -22,6 +22,7 @@
 #ifndef OFP_H
 #define OFP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -37,6 +38,12 @@ extern "C" {
 const char *ofp_last_error(void);
 /* "libofp <version> sm_100a" */
 const char *ofp_version(void);
+
+/* Strided host <-> device copy of `rows` rows of `width_bytes` (cudaMemcpy2DAsync on `stream`): a time segment
+ * of every recording of a [R, N, C] batch in one call.  The reference has no counterpart (its arrays never
+ * leave the host); used by the host-buffer entry points (pipeline.HotPath.run_host). */
+int ofp_copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes, size_t rows,
+                     int to_host, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * K1  amplitude onset detector
@@ -367,6 +374,9 @@ int ofp_rt_destroy(ofp_rt *rt);
  * -1 a group list overflowed); either may be NULL (read them through ofp_rt_results instead). */
 int ofp_rt_step(ofp_rt *rt, const float *blocks, int32_t blocks_on_host, int64_t stream_stride, double *xy_host,
                 int32_t *found_host);
+/* Device-resident blocks are read on the session's private stream: call this first with the stream that
+ * produced them (e.g. torch's current stream) so that the copy is ordered after the producer. */
+int ofp_rt_wait_stream(ofp_rt *rt, void *producer_stream);
 int ofp_rt_results(ofp_rt *rt, const double **xy_host, const int32_t **found_host);
 
 /* ---------------------------------------------------------------------------------------

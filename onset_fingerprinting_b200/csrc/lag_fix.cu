@@ -276,8 +276,15 @@ static int launch_pairs(bool adjust, const float *x, const float *y, int32_t P, 
     const int smem = 2 * (n + 16) * sizeof(double) + 2 * n * sizeof(float) +
                      (static_cast<size_t>(n) + 2 * XPAD + n + 16 + K4_MAX_THREADS * LPF) * sizeof(float) +
                      (CAND_CAP + 1) * sizeof(int);
-    if (adjust) t192::k4_adjust_pairs<<<P, K4_MAX_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
-    else t192::k4_cc_pairs<<<P, K4_MAX_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    // n above ~1300 needs more than the default 48 KB of dynamic shared memory: opt in (as k4_fix does)
+    OFP_REQUIRE(smem <= 220 * 1024, "signal length %d needs %d bytes of shared memory", n, smem);
+    if (adjust) {
+        OFP_CUDA_CHECK(cudaFuncSetAttribute(t192::k4_adjust_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        t192::k4_adjust_pairs<<<P, K4_MAX_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    } else {
+        OFP_CUDA_CHECK(cudaFuncSetAttribute(t192::k4_cc_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        t192::k4_cc_pairs<<<P, K4_MAX_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    }
     OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;
 }

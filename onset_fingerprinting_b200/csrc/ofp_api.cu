@@ -58,5 +58,15 @@ int encode_tmap_2d_f32(CUtensorMap *map, const void *base, uint64_t dim0, uint64
 
 extern "C" {
 const char *ofp_last_error(void) { return ofp::g_err; }
-const char *ofp_version(void) { return "libofp 0.1 sm_100a"; }
+const char *ofp_version(void) { return "libofp 0.2 sm_100a"; }
+
+int ofp_copy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes, size_t rows,
+                     int to_host, void *stream) {
+    OFP_REQUIRE(dst && src && dst_pitch >= width_bytes && src_pitch >= width_bytes, "bad argument");
+    if (width_bytes == 0 || rows == 0) return OFP_OK;
+    OFP_CUDA_CHECK(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows,
+                                     to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice,
+                                     static_cast<cudaStream_t>(stream)));
+    return OFP_OK;
+}
 }

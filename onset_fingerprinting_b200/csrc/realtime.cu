@@ -29,6 +29,7 @@ struct ofp_rt {
     double *xy_h = nullptr;                     // pinned mirrors
     int32_t *found_h = nullptr;
     cudaStream_t stream = nullptr;
+    cudaEvent_t producer_ev = nullptr;          // ofp_rt_wait_stream
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     // geometry (device pointers owned by the caller, must outlive the session)
@@ -58,6 +59,7 @@ extern "C" {
 int ofp_rt_destroy(ofp_rt *r) {
     if (!r) return OFP_OK;
     if (r->exec) cudaGraphExecDestroy(r->exec);
+    if (r->producer_ev) cudaEventDestroy(r->producer_ev);
     if (r->graph) cudaGraphDestroy(r->graph);
     if (r->stream) cudaStreamDestroy(r->stream);
     cudaFree(r->in); cudaFree(r->ch); cudaFree(r->dl); cudaFree(r->cnt); cudaFree(r->found); cudaFree(r->xy);
@@ -155,6 +157,16 @@ int ofp_rt_step(ofp_rt *r, const float *blocks, int32_t blocks_on_host, int64_t 
     OFP_CUDA_CHECK(cudaStreamSynchronize(r->stream));
     if (xy_host) memcpy(xy_host, r->xy_h, sizeof(double) * 2 * r->S);
     if (found_host) memcpy(found_host, r->found_h, sizeof(int32_t) * r->S);
+    return OFP_OK;
+}
+
+/* Order the session's private stream after everything queued so far on `producer_stream` (the stream that
+ * writes the device-resident blocks handed to the next ofp_rt_step): an event recorded there, waited on here. */
+int ofp_rt_wait_stream(ofp_rt *r, void *producer_stream) {
+    OFP_REQUIRE(r, "null session");
+    if (!r->producer_ev) OFP_CUDA_CHECK(cudaEventCreateWithFlags(&r->producer_ev, cudaEventDisableTiming));
+    OFP_CUDA_CHECK(cudaEventRecord(r->producer_ev, static_cast<cudaStream_t>(producer_stream)));
+    OFP_CUDA_CHECK(cudaStreamWaitEvent(r->stream, r->producer_ev, 0));
     return OFP_OK;
 }
 

@@ -210,6 +210,8 @@ class RealtimeSession:
             assert blocks.dtype == self.torch.float32 and tuple(blocks.shape) == (self.S, self.blocksize, self.C)
             assert blocks.stride(2) == 1 and blocks.stride(1) == self.C
             p, on_host, stride = C.c_void_p(blocks.data_ptr()), int(not blocks.is_cuda), blocks.stride(0)
+            if blocks.is_cuda:  # the session reads on its own stream: order it after the producer of `blocks`
+                _lib.check(_lib.lib().ofp_rt_wait_stream(self._h, _lib.stream_ptr()))
         _lib.check(_lib.lib().ofp_rt_step(self._h, p, C.c_int32(on_host), C.c_int64(stride),
                                           self.xy.ctypes.data_as(C.c_void_p), self.found.ctypes.data_as(C.c_void_p)))
         self.current_index += self.blocksize

@@ -112,18 +112,21 @@ class Locator:
     def __init__(self, sensor_locations, sr=96000, medium="air"):
         self.m = orc.Multilaterate3D(sensor_locations, sr=sr, medium=medium)
 
-    def locate_hit(self, onsets):
+    def locate_hit(self, onsets, sensors=None):
+        """onsets of three detections; sensors = their sensor indices (default 0, 1, 2)."""
         m = self.m
+        ids = list(range(len(onsets))) if sensors is None else [int(v) for v in sensors]
         order = np.argsort(onsets, kind="stable")
-        s0, t0 = int(order[0]), int(onsets[order[0]])
+        s0, t0 = ids[order[0]], int(onsets[order[0]])
         sens, ons = [s0], [t0]
-        for k in order[1:]:
-            lag = int(onsets[k]) - t0
+        for j in order[1:]:
+            k = ids[j]
+            lag = int(onsets[j]) - t0
             if lag > m.max_max_lags[s0]:
                 return None
             if not (m.min_lags[s0][k] < lag < m.max_lags[s0][k]):
                 return None
-            sens.append(int(k)); ons.append(int(onsets[k]))
+            sens.append(k); ons.append(int(onsets[j]))
         tol = m.samples_per_cm
         l1, l2 = ons[1] - ons[0], ons[2] - ons[0]
         m1, m2 = m.maps[sens[0], sens[1]], m.maps[sens[0], sens[2]]

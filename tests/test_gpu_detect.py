@@ -57,20 +57,6 @@ def test_offline_vs_golden_and_oracle(name, det, orc, golden_dir):
     assert float((rel == rel_o).mean()) > 0.9999
 
 
-@pytest.mark.parametrize("name", ["default3", "realtime3", "b256_partial", "mesh16"])
-def test_pipelined_kernel_variant(name, det, orc, monkeypatch):
-    """The software-pipelined K1 variant (OFP_K1_PIPE=1, csrc/onset_detect_pipe.cuh) is bit-identical too."""
-    from oracle.make_golden import DETECT_CASES
-
-    monkeypatch.setenv("OFP_K1_PIPE", "1")
-    skw, dkw = DETECT_CASES[name]
-    x, _ = synth.drum_recording(**skw)
-    ch, on, rel = det.detect_onsets_amplitude(x, sr=96000, **dkw)
-    ch_o, on_o, rel_o = orc.detect_onsets_amplitude(x, sr=96000, **dkw)
-    assert ch == ch_o and on == on_o
-    assert float((rel == rel_o).mean()) > 0.9999 and rel_err(rel, rel_o) <= 1e-5
-
-
 def test_streaming_blocks_vs_golden(det, golden_dir):
     g = np.load(golden_dir / "stream_realtime.npz")
     x, _ = synth.drum_recording(seconds=1.5, seed=7, first_hit=20000)

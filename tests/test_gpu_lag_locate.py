@@ -60,6 +60,23 @@ def test_known_lags_survey(det):
     assert det.cross_correlation_lag(imp(100, 5), imp(100, 90), onsets=(5, 90), onset_tolerance=50) is None
 
 
+def test_long_signals_need_opt_in_shared_memory(det, orc):
+    """n = 1536 (the documented maximum of the pair entry points) needs more than 48 KB of dynamic shared memory
+    per CTA (the launch must raise the kernel's limit)."""
+    rng = np.random.default_rng(5)
+    n = 1536
+    a = np.abs(rng.standard_normal(n)).astype(np.float32)
+    b = (np.roll(a, 37) + 0.2 * np.abs(rng.standard_normal(n))).astype(np.float32)
+    for o in ((700, 760), (100, 1400), (1500, 20)):
+        assert det.cross_correlation_lag(a, b, onsets=o, onset_tolerance=150, normalization_cutoff=20) == \
+            orc.cross_correlation_lag(a, b, onsets=o, onset_tolerance=150, normalization_cutoff=20)
+    lag = det.cross_correlation_lag(a, b, onsets=(700, 760), onset_tolerance=150)
+    if not orc.lib().orc_adjust_would_raise(700, 760, n, lag):
+        assert det.adjust_onset((700, 760), a, b, lag) == orc.adjust_onset((700, 760), a, b, lag)
+    with pytest.raises(Exception):
+        det.cross_correlation_lag(np.zeros(1537, np.float32), np.zeros(1537, np.float32), onsets=(5, 9))
+
+
 def test_adjust_onset_vs_oracle(det, orc):
     rng = np.random.default_rng(3)
     for _ in range(150):

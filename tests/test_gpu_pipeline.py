@@ -51,6 +51,30 @@ def test_pipeline_matches_oracle():
     assert n_loc > 40
 
 
+def test_host_buffer_entry_equals_device_entry():
+    """pipeline.HotPath.run_host (pinned host audio in, time-segmented upload under the detector, host records
+    out -- bench.py's e2e leg) returns exactly what run() returns on the resident batch, for segment lengths that
+    do and do not divide the recording, with and without the rel envelope."""
+    from onset_fingerprinting_b200 import pipeline
+
+    xs, _ = synth.drum_batch(5, seconds=2.0, seed=700)
+    xd = torch.from_numpy(xs).cuda()
+    hp = pipeline.HotPath(len(xs), 3, synth.SENSORS_3MIC, medium="air", sr=96000)
+    want = hp.run(xd, return_rel=True)
+    want = {k: getattr(want, k).cpu().numpy().copy() for k in ("rec", "onsets", "fixed", "lags", "fix_status", "xy",
+                                                               "loc_status", "onset_counts", "rel")}
+    xh = torch.from_numpy(xs).pin_memory()
+    for seg, with_rel in ((49152, True), (50000, False), (1 << 20, True)):
+        relh = torch.zeros((len(xs), (xs.shape[1] // 128) * 128, 3), dtype=torch.float32).pin_memory() if with_rel else None
+        got = hp.run_host(xh, rel_host=relh, segment=seg)
+        for k in ("rec", "onsets", "fixed", "lags", "fix_status", "loc_status", "onset_counts"):
+            assert np.array_equal(got[k].numpy(), want[k]), (seg, k)
+        assert np.array_equal(got["xy"].numpy(), want["xy"], equal_nan=True)
+        if with_rel:
+            assert np.array_equal(relh.numpy(), want["rel"])
+    assert len(want["rec"]) > 40
+
+
 def test_pipeline_properties_large():
     """Device-generated batch far larger than the oracle can check: results are deterministic, every
     hit has one onset per channel inside the recording, and shifting the audio by whole blocks shifts

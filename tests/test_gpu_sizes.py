@@ -48,7 +48,8 @@ def test_config0_60s_chain(golden_dir):
         if r is not None:
             assert np.allclose(r, want[h], rtol=1e-9, atol=1e-9)
     # the batched device pipeline on the same recording (R = 1): same groups, refined onsets and positions
-    hb = pipeline.HotPath(1, 3, synth.SENSORS_3MIC, medium="air", sr=96000).run(torch.from_numpy(x[None]).cuda())
+    hb = pipeline.HotPath(1, 3, synth.SENSORS_3MIC, medium="air", sr=96000).run(torch.from_numpy(x[None]).cuda(),
+                                                                                 return_rel=True)
     assert np.array_equal(hb.onsets.cpu().numpy(), g["groups"])
     assert np.array_equal(hb.fixed.cpu().numpy(), g["fixed"])
     xy, st = hb.xy.cpu().numpy(), hb.loc_status.cpu().numpy()
