@@ -358,14 +358,36 @@ int ofp_stream_locate_dev(const double *sensor_xyz_dev, int32_t n_sensors, const
                           int32_t *state_sensor_dev, int64_t *state_onset_dev, double *xy_dev, int32_t *found_dev,
                           void *stream);
 
+/* The same with the ring-buffer refinement of every new (group, detection) pair -- what PlayRec's callback runs
+ * (realtime/audio.py:69 passes self.rec_audio; multilateration.py:457-501: median 5 -> diff -> falling flanks ->
+ * cross_correlation_lag(tol, cutoff) -> adjust_onset).  ring_dev [n_streams, ring_rows, n_channels] float32 holds
+ * the most recent rows of every stream (row = sample index % ring_rows, zeros before the stream started) INCLUDING
+ * the current block: call ofp_ring_write first.  One warp per stream.  found_dev additionally reports -2 where the
+ * reference would have raised inside adjust_onset. */
+int ofp_stream_locate_ring_dev(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                               int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                               const float *max_max_dev, double radius_cm, double samples_per_cm, double sr,
+                               double c_cm_s, int32_t n_streams, int32_t n_channels, const int32_t *det_channel_dev,
+                               const int32_t *det_delta_dev, const int32_t *det_count_dev, int64_t *current_index_dev,
+                               int32_t advance, const float *ring_dev, int32_t ring_rows, int32_t block_size,
+                               int32_t onset_tolerance, int32_t normalization_cutoff, int32_t *state_count_dev,
+                               int32_t *state_len_dev, int32_t *state_sensor_dev, int64_t *state_onset_dev,
+                               double *xy_dev, int32_t *found_dev, void *stream);
+/* CircularArray.write for every stream (loopmate; realtime/audio.py callback): blocks_dev [S, B, C] (stream s at
+ * blocks_dev + s*stream_stride elements, 0 = dense) into ring rows (*current_index_dev + row) % ring_rows. */
+int ofp_ring_write(float *ring_dev, int32_t ring_rows, const float *blocks_dev, int64_t stream_stride,
+                   int32_t n_streams, int32_t block_size, int32_t n_channels, const int64_t *current_index_dev,
+                   void *stream);
+
 typedef struct ofp_rt ofp_rt;
 /* The session owns the detector, the locate state, a staging buffer and pinned result buffers; the geometry
  * arrays (as in ofp_locate_hits) stay owned by the caller and must outlive it.  use_graph = 0 issues the same
- * launches eagerly (A/B). */
+ * launches eagerly (A/B).  ring_rows > 0: the session also keeps a ring of the last ring_rows audio rows per stream
+ * and runs the ring-buffer refinement inside locate (rec_audio passed, as PlayRec does); 0 = locate(rec_audio=None). */
 int ofp_rt_create(ofp_rt **out, int32_t n_streams, const ofp_detector_params *p, const double *sensor_xyz_dev,
                   int32_t n_sensors, const float *lag_maps_dev, int32_t map_size, const float *max_lags_dev,
                   const float *min_lags_dev, const float *max_max_dev, double radius_cm, double samples_per_cm,
-                  double sr, double c_cm_s, int32_t use_graph);
+                  double sr, double c_cm_s, int32_t use_graph, int32_t ring_rows);
 int ofp_rt_reset(ofp_rt *rt);
 int ofp_rt_destroy(ofp_rt *rt);
 /* One block for every stream: blocks [S, B, C] float32 in host (blocks_on_host = 1, pinned for an asynchronous

@@ -10,6 +10,8 @@
 // The same restatement, written for the CPU, is oracle/oracle_c.c:orc_hybrj2.
 #include "ofp_common.cuh"
 
+#include <algorithm>
+
 namespace ofp {
 
 typedef struct { double xa, ya, za, xb, yb, zb, xo, yo, zo, da, db; } tri_problem;
@@ -387,7 +389,12 @@ struct SlArgs {
     int32_t *g_sensor;        // [S, GMAX, LEN]
     int64_t *g_onset;         // [S, GMAX, LEN]
     double *xy;               // [S, 2]
-    int32_t *found;           // [S]: 1 located, 0 nothing, -1 state overflow (groups or members dropped)
+    int32_t *found;           // [S]: 1 located, 0 nothing, -1 state overflow (groups or members dropped),
+                              //      -2 the reference would have raised inside adjust_onset
+    // ring-buffer refinement (multilateration.py:457-501), RING instantiation only
+    const float *ring = nullptr;  // [S, ring_rows, C] most recent audio rows of every stream (row = sample % ring_rows)
+    int32_t ring_rows = 0, block = 0;
+    int32_t tol = 50, cutoff = 10;  // ONSET_TOL, NORM_CUTOFF (multilateration.py:18-19); lookaround = their sum
 };
 
 struct SlGroup { int len; int s[SL_LEN]; long long o[SL_LEN]; };
@@ -397,16 +404,146 @@ __device__ __forceinline__ bool sl_is_legal(const K5Args &a, int first, int late
     return static_cast<double>(a.min_lags[first * a.S + later]) < l && l < static_cast<double>(a.max_lags[first * a.S + later]);
 }
 
+// ---- ring-buffer refinement of one (group, detection) pair by ONE WARP (multilateration.py:457-501) ----
+// section = ring rows [last_onset - lookaround - 1, counter) of the two sensors' columns -> median 5 (scipy
+// 'reflect') -> first difference -> rising flanks zeroed, abs -> cross_correlation_lag(onsets, d = 0, tol 50,
+// cutoff 10) (detection.py:195-268) -> adjust_onset (299-352).  Arithmetic as in oracle_c.c: products exact in
+// double, sums in double in index order per lag, one rounding to float32, float32 division by the count,
+// first maximum wins.
+constexpr int SL_LMAX = 1024;  // longest refinement section (samples); longer ones raise the overflow flag
+struct SlRefine { int has, err; long long lag, co, cn; };
+
+__device__ __forceinline__ void sl_py_slice(long long &s, long long &e, long long len) {
+    if (s < 0) { s += len; if (s < 0) s = 0; } else if (s > len) s = len;
+    if (e < 0) { e += len; if (e < 0) e = 0; } else if (e > len) e = len;
+}
+
+__device__ __forceinline__ float sl_med5(float a0, float a1, float a2, float a3, float a4) {
+    // median of five by an optimal 9-exchange network (values only; inputs are finite audio samples)
+#define SL_CS(x, y) { const float lo_ = fminf(x, y), hi_ = fmaxf(x, y); x = lo_; y = hi_; }
+    SL_CS(a0, a3); SL_CS(a1, a4); SL_CS(a0, a2); SL_CS(a1, a3); SL_CS(a0, a1); SL_CS(a2, a4); SL_CS(a1, a2);
+    SL_CS(a3, a4); SL_CS(a2, a3);
+#undef SL_CS
+    return a2;
+}
+
+__device__ SlRefine sl_refine_pair(const SlArgs &a, int st, int lane, double *xd, double *yd, int first_sensor,
+                                   int sensor, long long last_onset, long long onset, long long counter) {
+    SlRefine r;
+    r.has = 0; r.err = 0; r.lag = 0; r.co = 0; r.cn = 0;
+    const int C = a.C, NR = a.ring_rows, tol = a.tol, cutoff = a.cutoff, look = a.tol + a.cutoff;
+    long long rows = counter - last_onset + look + 1;  // rec_audio[-i - 1:], i = counter - last_onset + lookaround
+    if (rows > NR) rows = NR;                          // python slice past the start: the whole ring
+    if (rows < 2) return r;
+    if (rows - 1 > SL_LMAX) { r.err = 1; return r; }
+    const long long start = counter - rows;            // absolute sample index of section row 0
+    const int L0 = static_cast<int>(rows), n = L0 - 1;
+    const float *ring = a.ring + static_cast<int64_t>(st) * NR * C;
+    auto sample = [&](int t, int ch) -> float {         // section row t (reflected at the ends), channel ch
+        if (t < 0) t = -t - 1;
+        if (t >= L0) t = 2 * L0 - 1 - t;
+        t = min(max(t, 0), L0 - 1);
+        const long long sidx = start + t;
+        if (sidx < 0) return 0.0f;                      // before the stream started: the ring is zero-initialised
+        return ring[static_cast<int64_t>(sidx % NR) * C + ch];
+    };
+    auto med = [&](int t, int ch) -> float {
+        return sl_med5(sample(t - 2, ch), sample(t - 1, ch), sample(t, ch), sample(t + 1, ch), sample(t + 2, ch));
+    };
+    float xm = -INFINITY, ym = -INFINITY;
+    for (int t = lane; t < n; t += 32) {
+        float dx = __fsub_rn(med(t + 1, first_sensor), med(t, first_sensor));
+        float dy = __fsub_rn(med(t + 1, sensor), med(t, sensor));
+        dx = dx >= 0.0f ? 0.0f : fabsf(dx);             // section[section >= 0] = 0; abs
+        dy = dy >= 0.0f ? 0.0f : fabsf(dy);
+        xd[t] = static_cast<double>(dx);
+        yd[t] = static_cast<double>(dy);
+        xm = fmaxf(xm, dx); ym = fmaxf(ym, dy);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xm = fmaxf(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+        ym = fmaxf(ym, __shfl_xor_sync(0xffffffffu, ym, o));
+    }
+    __syncwarp();
+    // ---- cross_correlation_lag, window centred on the current lag (detection.py:259-268) ----
+    const long long cur = onset - last_onset;
+    long long ws = n - cur - tol, we = n - cur + tol;
+    sl_py_slice(ws, we, 2ll * n - 1);
+    if (we - ws <= 0) return r;                         // None: no adjustment
+    float best = 0.0f;
+    long long best_k = -1;
+    for (long long k = ws + lane; k < we; k += 32) {
+        const long long m = k - (n - 1);                // np.correlate(x, y, 'full')[k] = sum_i x[i + m] * y[i]
+        const int i0 = m < 0 ? static_cast<int>(-m) : 0, i1 = m > 0 ? static_cast<int>(n - m) : n;
+        double acc = 0.0;
+        for (int i = i0; i < i1; ++i) acc = fma(xd[i + m], yd[i], acc);  // products of two float32 are exact in double
+        long long cnt = n - (m < 0 ? -m : m);
+        if (cnt < cutoff) cnt = cutoff;
+        const float v = __fdiv_rn(static_cast<float>(acc), static_cast<float>(cnt));
+        if (best_k < 0 || v > best) { best = v; best_k = k; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {                  // first maximum over the lanes
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        if (ok >= 0 && (best_k < 0 || ov > best || (ov == best && ok < best_k))) { best = ov; best_k = ok; }
+    }
+    const long long lag = cur + tol - (best_k - ws);
+    // ---- adjust_onset on section-relative onsets (lookaround, lookaround + cur) ----
+    const long long oa = look, ob = look + cur, ld = (ob - oa) - lag, kk = ld < 0 ? -ld : ld;
+    long long xs, xe, ys, ye;
+    if (ld < 0) { xs = oa + ld > 0 ? oa + ld : 0; xe = oa < n ? oa : n; ys = ob < n ? ob : n; ye = ob - ld < n ? ob - ld : n; }
+    else { xs = oa; xe = oa + ld < n ? oa + ld : n; ys = ob - ld > 0 ? ob - ld : 0; ye = ob < n ? ob : n; }
+    const long long lx = xe - xs, ly = ye - ys;
+    {   // would the reference raise "operands could not be broadcast" (oracle_c.c:orc_adjust_would_raise)?
+        const long long nx = lx > 0 ? lx : 0, ex = lx > 0 ? lx : (lx == 0 ? kk : (kk + lx > 0 ? kk + lx : 0));
+        bool bad = nx != ex && nx != 1 && ex != 1;
+        if (ly != 0) {
+            const long long ny = ly > 0 ? ly : 0, ey = ly > 0 ? ly : (kk + ly > 0 ? kk + ly : 0);
+            bad = bad || (ny != ey && ny != 1 && ey != 1);
+        }
+        if (bad) { r.err = 2; return r; }
+    }
+    const double stop = -2.718281828459045, step = kk > 1 ? stop / static_cast<double>(kk - 1) : 0.0;
+    auto expw = [&](long long i) { return exp((i == kk - 1 && kk > 1) ? stop : static_cast<double>(i) * step); };
+    double da = 0.0, db = 0.0;
+    for (long long i = lane; i < lx; i += 32) da += xd[xs + i] * expw(kk - lx + i);
+    for (long long i = lane; i < ly; i += 32) db += yd[ys + i] * expw(kk - 1 - i);
+    for (int o = 16; o > 0; o >>= 1) {
+        da += __shfl_xor_sync(0xffffffffu, da, o);
+        db += __shfl_xor_sync(0xffffffffu, db, o);
+    }
+    da = da / static_cast<double>(xm);
+    if (ly != 0) db = db / static_cast<double>(ym); else db = 0.0;
+    r.has = 1; r.lag = lag;
+    if (da > db && !(oa + ld < 0)) { r.co = ld; r.cn = 0; }
+    else { r.co = 0; r.cn = -ld; }
+    __syncwarp();
+    return r;
+}
+
+// RING = false: one thread per stream.  RING = true: one WARP per stream -- every lane runs the (uniform) group
+// state machine, the refinement of a pair is shared by the 32 lanes, lane 0 writes the state back.
+// Group identity: the reference appends the SAME tuple twice when a pair is legal, and mutates group lists in
+// place (the swap at 443-449, `group[1][0] += co` at 497) -- the twin sees the mutation.  Stored groups carry a
+// uid (upper bits of g_len); an entry with the uid of the entry processed just before it inherits that entry's
+// (possibly mutated) first sensor / onset.
+template <bool RING>
 __global__ void k5_stream_locate(const SlArgs a) {
-    const int st = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int st = RING ? gtid >> 5 : gtid;
+    const int lane = RING ? (threadIdx.x & 31) : 0;
     if (st >= a.n_streams) return;
+    extern __shared__ __align__(16) double sl_smem[];
+    double *xd = RING ? sl_smem + static_cast<size_t>(threadIdx.x >> 5) * 2 * SL_LMAX : nullptr;
+    double *yd = RING ? xd + SL_LMAX : nullptr;
     const K5Args &geo = a.geo;
     const int S = geo.S, Hm = geo.Hm;
     const long long cur_index = a.current_index_dev ? *a.current_index_dev : a.current_index;
+    const long long counter = cur_index + a.block;  // rows written to the ring so far (incl. this block)
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     double out[2] = {nan, nan};
     int found = 0;
-    bool overflow = false;
+    bool overflow = false, raised = false;
     // detections of this block in sample order (np.argsort on <= C values: stable insertion sort)
     const int nd = min(a.det_cnt[st], a.C);
     int ord[32];
@@ -419,21 +556,35 @@ __global__ void k5_stream_locate(const SlArgs a) {
     int32_t *gl = a.g_len + static_cast<int64_t>(st) * SL_GMAX;
     int32_t *gs = a.g_sensor + static_cast<int64_t>(st) * SL_GMAX * SL_LEN;
     int64_t *go = a.g_onset + static_cast<int64_t>(st) * SL_GMAX * SL_LEN;
-    int ng = a.g_count[st];
+    int ng = a.g_count[st] & 0xff;
+    int next_uid = a.g_count[st] >> 8;
+    // the previous contents are read by every lane before lane 0 overwrites them below: work on a register copy
+    SlGroup cur_g[SL_GMAX];
+    int cur_uid[SL_GMAX];
+    for (int gi = 0; gi < ng; ++gi) {
+        cur_g[gi].len = gl[gi] & 0xff;
+        cur_uid[gi] = gl[gi] >> 8;
+        for (int k = 0; k < SL_LEN; ++k) { cur_g[gi].s[k] = gs[gi * SL_LEN + k]; cur_g[gi].o[k] = go[gi * SL_LEN + k]; }
+    }
     for (int di = 0; di < nd && !found; ++di) {
         int sensor = a.det_ch[static_cast<int64_t>(st) * a.C + ord[di]];
         long long onset = cur_index + a.det_delta[static_cast<int64_t>(st) * a.C + ord[di]];
         // ---- Multilaterate3D.locate(sensor, onset) ----
         SlGroup ngp[SL_GMAX];  // new_groups
+        int nuid[SL_GMAX];
         int nn = 0;
-        auto push = [&](const SlGroup &g) { if (nn < SL_GMAX) ngp[nn++] = g; else overflow = true; };
+        auto push = [&](const SlGroup &g, int uid) {
+            if (nn < SL_GMAX) { ngp[nn] = g; nuid[nn] = uid; ++nn; } else overflow = true;
+        };
         bool returned = false, broke = false;
+        int prev_uid = -1, prev_s0 = 0;
+        long long prev_o0 = 0;
         for (int gi = 0; gi < ng && !returned && !broke; ++gi) {
-            SlGroup g;
-            g.len = gl[gi];
-            for (int k = 0; k < SL_LEN; ++k) { g.s[k] = gs[gi * SL_LEN + k]; g.o[k] = go[gi * SL_LEN + k]; }
+            SlGroup g = cur_g[gi];
+            int uid = cur_uid[gi];
+            if (uid == prev_uid) { g.s[0] = prev_s0; g.o[0] = prev_o0; }  // the same tuple, already mutated
             long long lag = onset - g.o[0];
-            if (static_cast<double>(lag) > static_cast<double>(geo.max_max[g.s[0]])) continue;
+            if (static_cast<double>(lag) > static_cast<double>(geo.max_max[g.s[0]])) { prev_uid = uid; prev_s0 = g.s[0]; prev_o0 = g.o[0]; continue; }
             if (lag < 0) {  // multilateration.py:443-449
                 const int ts = g.s[0]; const long long to = g.o[0];
                 g.s[0] = sensor; g.o[0] = onset;
@@ -443,9 +594,17 @@ __global__ void k5_stream_locate(const SlArgs a) {
             bool member = false;
             for (int k = 0; k < g.len; ++k) member = member || g.s[k] == sensor;
             if (!member) {
+                if (RING) {  // multilateration.py:457-501
+                    const SlRefine rf = sl_refine_pair(a, st, lane, xd, yd, g.s[0], sensor, g.o[0], onset, counter);
+                    if (rf.err == 1) overflow = true;
+                    if (rf.err == 2) raised = true;
+                    if (rf.has) { lag = rf.lag; g.o[0] += rf.co; onset += rf.cn; }
+                }
+                prev_uid = uid; prev_s0 = g.s[0]; prev_o0 = g.o[0];  // what the shared lists hold from here on
                 if (sl_is_legal(geo, g.s[0], sensor, lag)) {
                     if (g.len < SL_LEN) { g.s[g.len] = sensor; g.o[g.len] = onset; ++g.len; }
                     else overflow = true;
+                    uid = next_uid++;  // group[0] + [..] builds a NEW tuple
                     if (g.len == 3) {
                         if (g.s[0] == g.s[1]) { broke = true; break; }
                         // is_legal_3d (multilateration.py:413-426)
@@ -478,35 +637,52 @@ __global__ void k5_stream_locate(const SlArgs a) {
                                 // remove_seed (multilateration.py:160-167): same first sensor and onset
                                 int w = 0;
                                 for (int r = 0; r < nn; ++r)
-                                    if (!(ngp[r].s[0] == g.s[0] && ngp[r].o[0] == g.o[0])) ngp[w++] = ngp[r];
+                                    if (!(ngp[r].s[0] == g.s[0] && ngp[r].o[0] == g.o[0])) { ngp[w] = ngp[r]; nuid[w] = nuid[r]; ++w; }
                                 nn = w;
                             }
                             returned = true;  // self.ongoing = new_groups; return res
                             break;
                         }
                     }
-                    push(g);
+                    push(g, uid);
                 }
+            } else {
+                prev_uid = uid; prev_s0 = g.s[0]; prev_o0 = g.o[0];
             }
-            if (static_cast<double>(lag) <= static_cast<double>(geo.max_max[g.s[0]])) push(g);
+            if (static_cast<double>(lag) <= static_cast<double>(geo.max_max[g.s[0]])) push(g, uid);
         }
         if (!returned) {
             SlGroup single;
             single.len = 1;
             for (int k = 0; k < SL_LEN; ++k) { single.s[k] = -1; single.o[k] = 0; }
             single.s[0] = sensor; single.o[0] = onset;
-            push(single);
+            push(single, next_uid++);
         }
         ng = nn;
-        for (int gi = 0; gi < ng; ++gi) {
-            gl[gi] = ngp[gi].len;
-            for (int k = 0; k < SL_LEN; ++k) { gs[gi * SL_LEN + k] = ngp[gi].s[k]; go[gi * SL_LEN + k] = ngp[gi].o[k]; }
-        }
+        for (int gi = 0; gi < ng; ++gi) { cur_g[gi] = ngp[gi]; cur_uid[gi] = nuid[gi]; }
     }
-    a.g_count[st] = ng;
-    a.xy[2 * static_cast<int64_t>(st)] = out[0];
-    a.xy[2 * static_cast<int64_t>(st) + 1] = out[1];
-    a.found[st] = found ? 1 : (overflow ? -1 : 0);
+    if (lane == 0) {
+        for (int gi = 0; gi < ng; ++gi) {
+            gl[gi] = cur_g[gi].len | (cur_uid[gi] << 8);
+            for (int k = 0; k < SL_LEN; ++k) { gs[gi * SL_LEN + k] = cur_g[gi].s[k]; go[gi * SL_LEN + k] = cur_g[gi].o[k]; }
+        }
+        a.g_count[st] = ng | ((next_uid & 0x7fffff) << 8);
+        a.xy[2 * static_cast<int64_t>(st)] = out[0];
+        a.xy[2 * static_cast<int64_t>(st) + 1] = out[1];
+        a.found[st] = found ? 1 : (raised ? -2 : (overflow ? -1 : 0));
+    }
+}
+
+// One block of every stream into its ring (row = sample index % ring_rows); blocks [S, B, C] at stream stride.
+__global__ void k_ring_write(float *ring, int32_t ring_rows, const float *blocks, int64_t stream_stride, int32_t S,
+                             int32_t B, int32_t C, const int64_t *current_index_dev, int64_t current_index) {
+    const int64_t base = current_index_dev ? *current_index_dev : current_index;
+    const int64_t per = static_cast<int64_t>(B) * C, total = per * S;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t s = i / per, e = i - s * per, row = e / C, c = e - row * C;
+        ring[(s * ring_rows + (base + row) % ring_rows) * C + c] = blocks[s * stream_stride + e];
+    }
 }
 
 // solve_trilateration / solve_trilateration_3d (multilateration.py:170-316) with an explicit seed, one
@@ -564,7 +740,7 @@ extern "C" int ofp_stream_locate(const double *sensor_xyz_dev, int32_t n_sensors
     a.det_cnt = det_count_dev; a.current_index = current_index; a.g_count = state_count_dev;
     a.g_len = state_len_dev; a.g_sensor = state_sensor_dev; a.g_onset = state_onset_dev; a.xy = xy_dev;
     a.found = found_dev;
-    k5_stream_locate<<<(n_streams + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    k5_stream_locate<false><<<(n_streams + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(a);
     OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;
 }
@@ -596,8 +772,70 @@ extern "C" int ofp_stream_locate_dev(const double *sensor_xyz_dev, int32_t n_sen
     a.det_cnt = det_count_dev; a.current_index = 0; a.current_index_dev = current_index_dev;
     a.g_count = state_count_dev; a.g_len = state_len_dev; a.g_sensor = state_sensor_dev; a.g_onset = state_onset_dev;
     a.xy = xy_dev; a.found = found_dev;
-    k5_stream_locate<<<(n_streams + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    k5_stream_locate<false><<<(n_streams + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(a);
     k_advance_index<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(current_index_dev, advance);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+// The same with the ring-buffer refinement of every new pair (multilateration.py:457-501, what PlayRec's callback
+// runs: realtime/audio.py:69 passes self.rec_audio): ring_dev [S, ring_rows, C] holds the most recent rows of every
+// stream INCLUDING the current block (ofp_ring_write first).  One warp per stream.
+extern "C" int ofp_stream_locate_ring_dev(const double *sensor_xyz_dev, int32_t n_sensors, const float *lag_maps_dev,
+                                          int32_t map_size, const float *max_lags_dev, const float *min_lags_dev,
+                                          const float *max_max_dev, double radius_cm, double samples_per_cm,
+                                          double sr, double c_cm_s, int32_t n_streams, int32_t n_channels,
+                                          const int32_t *det_channel_dev, const int32_t *det_delta_dev,
+                                          const int32_t *det_count_dev, int64_t *current_index_dev, int32_t advance,
+                                          const float *ring_dev, int32_t ring_rows, int32_t block_size,
+                                          int32_t onset_tolerance, int32_t normalization_cutoff,
+                                          int32_t *state_count_dev, int32_t *state_len_dev,
+                                          int32_t *state_sensor_dev, int64_t *state_onset_dev, double *xy_dev,
+                                          int32_t *found_dev, void *stream) {
+    OFP_REQUIRE(sensor_xyz_dev && lag_maps_dev && max_lags_dev && min_lags_dev && max_max_dev && det_channel_dev &&
+                    det_delta_dev && det_count_dev && state_count_dev && state_len_dev && state_sensor_dev &&
+                    state_onset_dev && xy_dev && found_dev && current_index_dev && ring_dev, "null argument");
+    OFP_REQUIRE(n_sensors >= 3 && n_channels >= 1 && n_channels <= 32, "bad sensor / channel count");
+    OFP_REQUIRE(ring_rows >= block_size && block_size >= 1 && onset_tolerance >= 1 && normalization_cutoff >= 1,
+                "bad ring / refinement parameters");
+    if (n_streams == 0) return OFP_OK;
+    SlArgs a;
+    a.geo.locs = sensor_xyz_dev; a.geo.maps = lag_maps_dev; a.geo.max_lags = max_lags_dev;
+    a.geo.min_lags = min_lags_dev; a.geo.max_max = max_max_dev; a.geo.S = n_sensors; a.geo.Hm = map_size;
+    a.geo.H = 0; a.geo.n_per_hit = 3; a.geo.radius = radius_cm; a.geo.samples_per_cm = samples_per_cm;
+    a.geo.sr = sr; a.geo.c_cm = c_cm_s; a.geo.sensors = nullptr; a.geo.onsets = nullptr; a.geo.onset_stride = 0;
+    a.geo.xy = nullptr; a.geo.status = nullptr;
+    a.n_streams = n_streams; a.C = n_channels; a.det_ch = det_channel_dev; a.det_delta = det_delta_dev;
+    a.det_cnt = det_count_dev; a.current_index = 0; a.current_index_dev = current_index_dev;
+    a.g_count = state_count_dev; a.g_len = state_len_dev; a.g_sensor = state_sensor_dev; a.g_onset = state_onset_dev;
+    a.xy = xy_dev; a.found = found_dev;
+    a.ring = ring_dev; a.ring_rows = ring_rows; a.block = block_size; a.tol = onset_tolerance; a.cutoff = normalization_cutoff;
+    constexpr int WARPS = 4;
+    const size_t smem = static_cast<size_t>(WARPS) * 2 * SL_LMAX * sizeof(double);
+    static bool attr_set = false;  // per process is enough: the attribute is per function and device-independent here
+    if (!attr_set) {
+        OFP_CUDA_CHECK(cudaFuncSetAttribute(k5_stream_locate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+        attr_set = true;
+    }
+    k5_stream_locate<true><<<(n_streams + WARPS - 1) / WARPS, 32 * WARPS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    k_advance_index<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(current_index_dev, advance);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+extern "C" int ofp_ring_write(float *ring_dev, int32_t ring_rows, const float *blocks_dev, int64_t stream_stride,
+                              int32_t n_streams, int32_t block_size, int32_t n_channels,
+                              const int64_t *current_index_dev, void *stream) {
+    OFP_REQUIRE(ring_dev && blocks_dev && current_index_dev, "null argument");
+    OFP_REQUIRE(ring_rows >= block_size && block_size >= 1 && n_channels >= 1, "bad ring shape");
+    if (n_streams == 0) return OFP_OK;
+    if (stream_stride <= 0) stream_stride = static_cast<int64_t>(block_size) * n_channels;
+    const int64_t total = static_cast<int64_t>(n_streams) * block_size * n_channels;
+    const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, 148 * 8));
+    k_ring_write<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ring_dev, ring_rows, blocks_dev, stream_stride,
+                                                                    n_streams, block_size, n_channels,
+                                                                    current_index_dev, 0);
     OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;
 }

@@ -34,6 +34,7 @@
 #endif
 
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 
@@ -81,7 +82,6 @@ struct K1Args {
     int32_t floor_skip;  // OFP_K1_FLOOR_SKIP=0 disables the below-floor short-cut (A/B runs)
     int32_t cnt_in;      // continue: the per-recording onset counts in on_cnt are the starting fill levels
     int64_t blk0;        // continue: global index of the first block of this call (x / rel start there)
-    int32_t role_swap, n_sm;  // k1_detect2: alternate which warp of a CTA takes the front role (A/B switch)
 };
 
 // Per-kernel constants held in registers for the whole launch (a one-warp CTA has registers to
@@ -229,6 +229,12 @@ __device__ __forceinline__ float to_amp_fast(float r, float ceil_amp, uint32_t e
     return amp_of(ad, ceil_amp);
 }
 
+// (double)k for |k| < 2^31 without the conversion unit (I2F.F64 is a quarter-rate XU instruction): the integer is
+// planted in the mantissa of 2^52 + 2^31 and the constant subtracted -- one LOP3 + one DADD, exact.
+__device__ __forceinline__ double int_to_double(int32_t k) {
+    return __dsub_rn(__hiloint2double(0x43300000, k ^ static_cast<int32_t>(0x80000000u)), 0x1.00000008p52);
+}
+
 // Step-major ("vertical") forms of to_db_fast / to_amp_fast for U independent samples: every
 // elementary operation is issued for all U samples before the next one, so the instruction stream
 // handed to ptxas is already interleaved.  (Written sample-major, ptxas keeps the U dependency
@@ -254,7 +260,7 @@ __device__ __forceinline__ void to_db_vec(const float (&h)[U], float floor_db, u
 #pragma unroll
     for (int u = 0; u < U; ++u) r[u] = __fma_rn(z[u], invc[u], -1.0);
 #pragma unroll
-    for (int u = 0; u < U; ++u) base[u] = __fma_rn(static_cast<double>(kexp[u]), mc.log10_2, logc[u]);
+    for (int u = 0; u < U; ++u) base[u] = __fma_rn(int_to_double(kexp[u]), mc.log10_2, logc[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) r2[u] = __dmul_rn(r[u], r[u]);
 #pragma unroll
@@ -336,10 +342,9 @@ __device__ __forceinline__ void minmax_step(Lane &L, const Coef &k, float r) {
 template <bool USE_HP, int U>
 __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
                                       bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
-                                      const MathConst &mc, uint32_t rstep = 0) {
+                                      const MathConst &mc) {
     float h[U], db[U], dr[U], amp[U], aux[U];
     bool redo[U], any = false;
-    if (rstep == 0) rstep = step;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const float x = lds_f32(xs + u * step);
@@ -380,7 +385,7 @@ __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint3
         if (do_minmax) minmax_step(L, k, amp[u]);
         L.bmax = fmaxf(L.bmax, amp[u]);
         L.bmin = fminf(L.bmin, amp[u]);
-        if (store) sts_f32(rs + u * rstep, amp[u]);
+        if (store) sts_f32(rs + u * step, amp[u]);
     }
 }
 
@@ -391,52 +396,58 @@ __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint3
 //   - follower steps in the sliver 0 < |t| < 2^-22 where the float32 shortcut is not proven exact.
 // Returns true when this lane hit a flag; the caller then restores the lane state and re-runs the
 // samples through chunk<> (exact, with branches).
-template <bool USE_HP, bool HP_SYM, int U, bool DO_MM, bool FROM_DB = false>
+template <bool USE_HP, bool HP_SYM, int U, bool DO_MM, bool SAFE_COEF>
 __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
-                                           bool store, uint32_t logtab, uint32_t exptab,
-                                           const MathConst &mc, uint32_t rstep = 0) {
+                                           bool store, uint32_t logtab, uint32_t exptab, const MathConst &mc) {
     float h[U], db[U], dr[U], amp[U], aux[U];
     uint32_t flags = 0;
-    if (rstep == 0) rstep = step;
-    if (FROM_DB) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) db[u] = lds_f32(xs + u * step);
-    } else {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float x = lds_f32(xs + u * step);
-            h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
-        }
+    for (int u = 0; u < U; ++u) {
+        const float x = lds_f32(xs + u * step);
+        h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
+    }
 #if OFP_K1_LADDER <= 1  // speed-of-light ladder (profiles/): memory path only / + high-pass; results are NOT the detector's
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (store) sts_f32(rs + u * rstep, h[u]);
-        return false;
+    for (int u = 0; u < U; ++u)
+        if (store) sts_f32(rs + u * step, h[u]);
+    return false;
 #endif
-        // exact short-cut (iv): a chunk whose samples all sit below the floor needs no logarithm
-        float vmax = 0.0f;
+    // exact short-cut (iv): a chunk whose samples all sit below the floor needs no logarithm
+    float vmax = 0.0f;
 #pragma unroll
-        for (int u = 0; u < U; ++u) vmax = fmaxf(vmax, fabsf(__fadd_rn(h[u], 1e-10f)));
-        if (__all_sync(0xffffffffu, vmax < k.vfloor)) {
+    for (int u = 0; u < U; ++u) vmax = fmaxf(vmax, fabsf(__fadd_rn(h[u], 1e-10f)));
+    const bool all_floor = __all_sync(0xffffffffu, vmax < k.vfloor);
+    if (all_floor) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) db[u] = k.floor_db;
-        } else {
-            to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
-        }
+        for (int u = 0; u < U; ++u) db[u] = k.floor_db;
+    } else {
+        to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
     }
 #if OFP_K1_LADDER == 2  // + dB
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * rstep, db[u]);
+        if (store) sts_f32(rs + u * step, db[u]);
     return flags != 0;
 #endif
+    // The float32 short-cut of the follower step is proven for t == 0 or |t| >= 2^-26 (ar_step); the sliver in
+    // between needs min(|x|, |y|) < 2 (a difference of floats is a multiple of the smaller ulp), so the chunk is
+    // flagged conservatively on the operands and re-run exactly.  With every coefficient in (0, 1] a follower
+    // stays between its old value and the input (+1e-10 drift), so ONE test on the largest operand of the chunk
+    // covers all U steps (operands are dB values, negative in all but the loudest passages); otherwise
+    // (realtime attack 1/0.3 > 1: the follower overshoots) every step is tested.
     bool sliver = false;
+    if (SAFE_COEF) {
+        float m = fmaxf(fmaxf(L.yf, L.ys), k.floor_db);
+        if (!all_floor) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) m = fmaxf(m, db[u]);
+        }
+        sliver = !(m < -2.5f);
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const float t1 = __fsub_rn(db[u], L.yf), t2 = __fsub_rn(db[u], L.ys);
-        // 0 < |x - y| < 2^-22 needs min(|x|, |y|) < 2 (a difference of floats is a multiple of the smaller
-        // ulp): flag conservatively on the operands, the exact test runs in the re-run path
-        sliver |= (fabsf(db[u]) < 2.0f) | (fabsf(L.yf) < 2.0f) | (fabsf(L.ys) < 2.0f);
+        if (!SAFE_COEF) sliver |= (fabsf(db[u]) < 2.0f) | (fabsf(L.yf) < 2.0f) | (fabsf(L.ys) < 2.0f);
         const float d1 = __fadd_rn(t1, 1e-10f), d2 = __fadd_rn(t2, 1e-10f);
         L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
         L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
@@ -445,18 +456,28 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
 #if OFP_K1_LADDER == 3  // + followers
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * rstep, dr[u]);
+        if (store) sts_f32(rs + u * step, dr[u]);
     return sliver | (flags != 0);
 #endif
     to_amp_vec<U, false>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
 #if OFP_K1_LADDER >= 5  // 4: + 10**x only; 5 and above: the full chunk
-        if (DO_MM) minmax_step(L, k, amp[u]);
-        L.bmax = fmaxf(L.bmax, amp[u]);
-        L.bmin = fminf(L.bmin, amp[u]);
+    if (DO_MM) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) minmax_step(L, k, amp[u]);
+    }
+    // block extrema as 3-input min/max trees (FMNMX3): U/2 + 1 instructions each instead of U
+    float hi = L.bmax, lo = L.bmin;
+#pragma unroll
+    for (int u = 0; u + 1 < U; u += 2) {
+        hi = fmaxf(fmaxf(hi, amp[u]), amp[u + 1]);
+        lo = fminf(fminf(lo, amp[u]), amp[u + 1]);
+    }
+    if (U & 1) { hi = fmaxf(hi, amp[U - 1]); lo = fminf(lo, amp[U - 1]); }
+    L.bmax = hi; L.bmin = lo;
 #endif
-        if (store) sts_f32(rs + u * rstep, amp[u]);
+    if (store) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) sts_f32(rs + u * step, amp[u]);
     }
     return sliver | (flags != 0);
 }
@@ -565,7 +586,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
 #endif
 constexpr int KU = OFP_K1_KU;  // samples per straight-line chunk of the single-warp kernel
 
-template <bool USE_HP, bool USE_TMA, bool HP_SYM>
+template <bool USE_HP, bool USE_TMA, bool HP_SYM, bool SAFE_COEF>
 __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -589,7 +610,8 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
 
     Coef kf = load_coef(a);
     const uint32_t logtab_s = smem_u32(logtab), exptab_s = smem_u32(exptab);
-    const uint32_t step = 4u * C;
+    uint32_t step = 4u * C;
+    asm volatile("mov.u32 %0, %0;" : "+r"(step));  // opaque: stays in a register across the shared-memory asm
     MathConst mc = math_const();
     launder(kf, mc, smem_u32(relbuf));
     Lane L;
@@ -676,10 +698,10 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                         const Lane saved = L;
                         // the min/max trackers only rest in the main phase of manual-threshold detectors
                         const bool bad = do_minmax
-                            ? chunk_fast<USE_HP, HP_SYM, KU, true>(L, kf, xp + i * step, rp + i * step, step, in_group,
-                                                                   logtab_s, exptab_s, mc)
-                            : chunk_fast<USE_HP, HP_SYM, KU, false>(L, kf, xp + i * step, rp + i * step, step, in_group,
-                                                                    logtab_s, exptab_s, mc);
+                            ? chunk_fast<USE_HP, HP_SYM, KU, true, SAFE_COEF>(L, kf, xp + i * step, rp + i * step, step,
+                                                                              in_group, logtab_s, exptab_s, mc)
+                            : chunk_fast<USE_HP, HP_SYM, KU, false, SAFE_COEF>(L, kf, xp + i * step, rp + i * step, step,
+                                                                               in_group, logtab_s, exptab_s, mc);
                         if (__any_sync(0xffffffffu, bad)) {  // rare: exact re-run of these samples
                             L = saved;
                             for (int e = 0; e < KU; ++e)
@@ -722,281 +744,6 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     }
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// k1_detect2: the same detector split over TWO warps per recording group (CTA = 64 threads).
-//
-// k1_detect keeps one warp per group of G recordings, so 10 000 3-channel recordings are 1000 warps = 1.7 per
-// scheduler, each of which issues one instruction every ~3 cycles (dependent FP32/FP64 chains; ncu: issue slots
-// 52-66 % busy, profiles/r02_k1_ladder*.txt).  Time cannot be cut (non-linear recurrences) and lanes cannot be
-// added (R*C of them), but the per-sample work is a chain of stages, so it is cut BETWEEN stages, into two halves
-// of about equal instruction count (warps of a CTA sit on different schedulers, and with one CTA shape per SM a
-// scheduler sees only ONE of the two roles -- an unbalanced cut leaves half the schedulers idle):
-//   warp 0 (front):  TMA tile -> high-pass (recurrence) -> dB (pointwise) -> fast/slow followers (recurrences)
-//                    -> yf - ys into a ring in shared memory                               (~33-63 instr/sample)
-//   warp 1 (back):   ring -> 10**x (pointwise) -> min/max trackers (recurrence) -> block FSM, onset compaction,
-//                    rel -> HBM                                                             (~50 instr/sample)
-// Both warps use the same lane <-> (recording, channel) mapping, so a ring row is 32 consecutive words (conflict
-// free).  Hand-over per chunk of KU samples through NS2 ring slots guarded by named barriers (bar.arrive by the
-// writer / bar.sync by the reader on "full", the reverse on "empty"): no polling, no mbarrier phase arithmetic.
-// The arithmetic is the same code as k1_detect (hp_step*, to_db_vec, to_amp_vec, minmax_step, block_end), with the
-// same flag-and-redo treatment of the rare cases, so the outputs are bit-identical.
-constexpr int NS2 = 4;  // ring slots (chunks in flight between the two warps)
-
-// Barrier ids must be IMMEDIATES: with a register operand ptxas reserves all 16 hardware barriers for the CTA and
-// an SM (64 barriers) then holds only 4 CTAs (ncu launch__occupancy_limit_barriers; measured 115 instead of 86 ms).
-// With ids 1 .. 2*NS2 a CTA uses 9 barriers -> 7 CTAs per SM.
-template <int BASE>
-__device__ __forceinline__ void nbar_sync(int slot) {
-    switch (slot) {
-        case 0: asm volatile("bar.sync %0, 64;" ::"n"(BASE + 0) : "memory"); break;
-        case 1: asm volatile("bar.sync %0, 64;" ::"n"(BASE + 1) : "memory"); break;
-        case 2: asm volatile("bar.sync %0, 64;" ::"n"(BASE + 2) : "memory"); break;
-        default: asm volatile("bar.sync %0, 64;" ::"n"(BASE + 3) : "memory"); break;
-    }
-}
-template <int BASE>
-__device__ __forceinline__ void nbar_arrive(int slot) {
-    switch (slot) {
-        case 0: asm volatile("bar.arrive %0, 64;" ::"n"(BASE + 0) : "memory"); break;
-        case 1: asm volatile("bar.arrive %0, 64;" ::"n"(BASE + 1) : "memory"); break;
-        case 2: asm volatile("bar.arrive %0, 64;" ::"n"(BASE + 2) : "memory"); break;
-        default: asm volatile("bar.arrive %0, 64;" ::"n"(BASE + 3) : "memory"); break;
-    }
-}
-static_assert(NS2 == 4, "nbar_sync / nbar_arrive enumerate four slots");
-
-// front warp: U samples -> follower differences yf - ys in registers
-template <bool USE_HP, bool HP_SYM, int U, bool SAFE_COEF>
-__device__ __forceinline__ void front_chunk(Lane &L, const Coef &k, uint32_t xs, uint32_t step, uint32_t logtab,
-                                            const MathConst &mc, float (&dr)[U]) {
-    float h[U], db[U], aux[U];
-    uint32_t flags = 0;
-    const float z0 = L.z0, z1 = L.z1, z2 = L.z2, z3 = L.z3, yf0 = L.yf, ys0 = L.ys;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float x = lds_f32(xs + u * step);
-        h[u] = USE_HP ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
-    }
-    // exact short-cut (iv): a chunk whose samples all sit below the floor needs no logarithm
-    float vmax = 0.0f;
-#pragma unroll
-    for (int u = 0; u < U; ++u) vmax = fmaxf(vmax, fabsf(__fadd_rn(h[u], 1e-10f)));
-    const bool all_floor = __all_sync(0xffffffffu, vmax < k.vfloor);
-    if (all_floor) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) db[u] = k.floor_db;
-    } else {
-        to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
-    }
-    bool sliver = false;
-    if (SAFE_COEF) {
-        // 0 < |x - y| < 2^-22 needs min(|x|, |y|) < 2.  With every coefficient in (0, 1] a follower stays between
-        // its old value and the input (+1e-10), so ONE test on the chunk's largest operand covers all U steps.
-        float m = fmaxf(fmaxf(L.yf, L.ys), k.floor_db);
-        if (!all_floor) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) m = fmaxf(m, db[u]);
-        }
-        sliver = !(m < -2.5f);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float t1 = __fsub_rn(db[u], L.yf), t2 = __fsub_rn(db[u], L.ys);
-        if (!SAFE_COEF) sliver |= (fabsf(db[u]) < 2.0f) | (fabsf(L.yf) < 2.0f) | (fabsf(L.ys) < 2.0f);
-        const float d1 = __fadd_rn(t1, 1e-10f), d2 = __fadd_rn(t2, 1e-10f);
-        L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
-        L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
-        dr[u] = __fsub_rn(L.yf, L.ys);
-    }
-    if (__any_sync(0xffffffffu, sliver | (flags != 0))) {  // rare: exact re-run of these samples (all lanes)
-        L.z0 = z0; L.z1 = z1; L.z2 = z2; L.z3 = z3; L.yf = yf0; L.ys = ys0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float x = lds_f32(xs + u * step);
-            const float hh = USE_HP ? hp_step(L, k, x) : x;
-            float v; bool redo;
-            float d = to_db_fast(hh, k.floor_db, logtab, mc, v, redo);
-            if (redo) d = db_of(slow_log10(v), k.floor_db);
-            L.yf = ar_step(L.yf, d, k.fa, k.fr);
-            L.ys = ar_step(L.ys, d, k.sa, k.sr);
-            dr[u] = __fsub_rn(L.yf, L.ys);
-        }
-    }
-}
-
-// back warp: U follower differences -> 10**x, min/max, rel into the block buffer
-template <int U, bool DO_MM>
-__device__ __forceinline__ void back_chunk(Lane &L, const Coef &k, const float (&dr)[U], uint32_t rs, uint32_t rstep,
-                                           bool store, uint32_t exptab, const MathConst &mc) {
-    float amp[U];
-    uint32_t flags = 0;
-    to_amp_vec<U, false>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
-    if (__any_sync(0xffffffffu, flags != 0)) {  // rare: exact evaluation of this lane's samples (pointwise, no state)
-        if (flags) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                float q; bool redo;
-                amp[u] = to_amp_fast(dr[u], k.ceil_amp, exptab, mc, q, redo);
-                if (redo) amp[u] = amp_of(slow_exp10(fabsf(q) < 30.0f ? q : __fdiv_rn(dr[u], 20.0f)), k.ceil_amp);
-            }
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        if (DO_MM) minmax_step(L, k, amp[u]);
-        L.bmax = fmaxf(L.bmax, amp[u]);
-        L.bmin = fminf(L.bmin, amp[u]);
-        if (store) sts_f32(rs + u * rstep, amp[u]);
-    }
-}
-
-template <bool USE_HP, bool HP_SYM, bool SAFE_COEF>
-__global__ void __launch_bounds__(64, 7) k1_detect2(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    double *logtab = reinterpret_cast<double *>(smem + 128);
-    double *exptab = logtab + (2 << OFP_LOG_N);
-    float *stages = reinterpret_cast<float *>(smem + K1_SMEM_HEADER);
-    float *relbuf = stages + static_cast<size_t>(a.nst) * a.stage_floats;
-    float *ring = relbuf + static_cast<size_t>(a.G) * a.stride_rel;  // [NS2][KU][32]
-
-    // CTAs reach an SM in blockIdx order s, s + n_sm, ...: with role_swap every other CTA of an SM swaps its warps' roles
-    const int warp = (threadIdx.x >> 5) ^ (a.role_swap ? ((blockIdx.x / a.n_sm) & 1) : 0), lane = threadIdx.x & 31;
-    const int C = a.p.n_channels, B = a.p.block_size, G = a.G, T = a.T, TC = a.TC;
-    const int g_raw = lane / C;
-    const bool in_group = g_raw < G;
-    const int g = in_group ? g_raw : 0;
-    const int c = in_group ? lane - g_raw * C : 0;
-    const int rec0 = blockIdx.x * G;
-    const int rec = rec0 + g;
-    const bool active = in_group && rec < a.R;
-    const int64_t lid = static_cast<int64_t>(rec) * C + c;
-
-    Coef kf = load_coef(a);
-    MathConst mc = math_const();
-    for (int i = threadIdx.x; i < (2 << OFP_LOG_N); i += 64) logtab[i] = g_logtab[i];
-    if (threadIdx.x < 32) exptab[threadIdx.x] = g_exptab[threadIdx.x];
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < a.nst; ++s) mbar_init(&bars[s], 1);
-        fence_mbar_init();
-        tma_prefetch_desc(&tmap);
-    }
-    launder(kf, mc, smem_u32(ring) + 256u * warp);
-    __syncthreads();
-    const uint32_t logtab_s = smem_u32(logtab), exptab_s = smem_u32(exptab);
-    const uint32_t ring_s = smem_u32(ring) + 4u * lane;
-    const int64_t env_warm = (a.warm_n / B) * B;
-
-    if (warp == 0) {
-        // ========================= front: TMA -> high-pass -> dB -> followers =========================
-        Lane L;
-        L.z0 = L.z1 = L.z2 = L.z3 = 0.f; L.yf = L.ys = a.p.floor_db;
-        if (active) {
-            L.z0 = a.st.z0[lid]; L.z1 = a.st.z1[lid]; L.z2 = a.st.z2[lid]; L.z3 = a.st.z3[lid];
-            L.yf = a.st.yf[lid]; L.ys = a.st.ys[lid];
-        }
-        const uint32_t step = 4u * C;
-        const uint32_t box_bytes = static_cast<uint32_t>(G) * TC * 4u;
-        const uint32_t stage0_s = smem_u32(stages) + 4u * (g * TC + c);
-        uint32_t it = 0;
-        int64_t q = 0;  // chunks handed over so far
-        for (int phase = 0; phase < 2; ++phase) {
-            const int64_t len = phase == 0 ? a.warm_n : a.n_main;
-            if (len <= 0) continue;
-            const int64_t env_len = phase == 0 ? env_warm : len;
-            const int64_t ntiles = (len + T - 1) / T;
-            if (lane == 0) {
-                for (int p = 0; p < a.nst - 1 && p < ntiles; ++p) {
-                    const int s = (it + p) % a.nst;
-                    mbar_expect_tx(&bars[s], box_bytes);
-                    tma_load_2d(stages + static_cast<size_t>(s) * a.stage_floats, &tmap, &bars[s], p * TC, rec0);
-                }
-            }
-            for (int64_t ti = 0; ti < ntiles; ++ti, ++it) {
-                const int s = it % a.nst;
-                const int64_t t0 = ti * T;
-                const int64_t nx = ti + a.nst - 1;
-                if (lane == 0 && nx < ntiles) {
-                    const int sn = (it + a.nst - 1) % a.nst;
-                    mbar_expect_tx(&bars[sn], box_bytes);
-                    tma_load_2d(stages + static_cast<size_t>(sn) * a.stage_floats, &tmap, &bars[sn],
-                                static_cast<int32_t>(nx * TC), rec0);
-                }
-                mbar_wait(&bars[s], (it / a.nst) & 1u);
-                const uint32_t sp = stage0_s + 4u * static_cast<uint32_t>(s) * a.stage_floats;
-                const int tl = static_cast<int>(min(static_cast<int64_t>(T), len - t0));
-                int j = 0;
-                for (; j + KU <= tl && t0 + j < env_len; j += KU, ++q) {
-                    const int slot = static_cast<int>(q % NS2);
-                    float dr[KU];
-                    front_chunk<USE_HP, HP_SYM, KU, SAFE_COEF>(L, kf, sp + j * step, step, logtab_s, mc, dr);
-                    if (q >= NS2) nbar_sync<1 + NS2>(slot);  // the back warp has released this slot
-                    const uint32_t dst = ring_s + static_cast<uint32_t>(slot * KU) * 128u;
-#pragma unroll
-                    for (int u = 0; u < KU; ++u) sts_f32(dst + u * 128u, dr[u]);
-                    nbar_arrive<1>(slot);
-                }
-                // warm-up tail beyond the last full block: only the high-pass advances (detection.py:828-829)
-                if (USE_HP)
-                    for (; j < tl; ++j) hp_step(L, kf, lds_f32(sp + j * step));
-                __syncwarp();  // every lane is done with stage s before lane 0 refills it
-            }
-        }
-        if (active) {
-            a.st.z0[lid] = L.z0; a.st.z1[lid] = L.z1; a.st.z2[lid] = L.z2; a.st.z3[lid] = L.z3;
-            a.st.yf[lid] = L.yf; a.st.ys[lid] = L.ys;
-        }
-    } else {
-        // ========================= back: 10**x -> min/max -> block FSM, outputs =========================
-        Lane L;
-        L.z0 = L.z1 = L.z2 = L.z3 = 0.f; L.yf = L.ys = a.p.floor_db;
-        if (active) {
-            L.mn = a.st.mn[lid]; L.mx = a.st.mx[lid];
-            L.prev = a.st.prev[lid]; L.state = a.st.state[lid]; L.deb = a.st.deb[lid];
-        } else {
-            L.mn = 0.f; L.mx = 10.f; L.prev = 0.f; L.state = 0; L.deb = 0;
-        }
-        L.bmax = -INFINITY; L.bmin = INFINITY;
-        const unsigned rec_mask = (C == 32 ? 0xffffffffu : ((1u << C) - 1u)) << (g * C);
-        const unsigned lower_mask = rec_mask & ((1u << lane) - 1u);
-        const uint32_t rstep = 4u * C;
-        float *rcol = relbuf + g * a.stride_rel + c;
-        const uint32_t rcol_s = smem_u32(rcol);
-        int32_t cnt = (a.cnt_in && active) ? a.on_cnt[rec] : 0;
-        int64_t blk = a.blk0;
-        const int64_t Qw = env_warm / KU, Q = Qw + a.n_main / KU;
-        int kpos = 0;
-        for (int64_t q = 0; q < Q; ++q) {
-            const int slot = static_cast<int>(q % NS2);
-            const bool main_phase = q >= Qw;
-            const bool do_minmax = !main_phase || !a.p.manual;
-            nbar_sync<1>(slot);  // the front warp has filled this slot
-            float dr[KU];
-            const uint32_t src = ring_s + static_cast<uint32_t>(slot * KU) * 128u;
-#pragma unroll
-            for (int u = 0; u < KU; ++u) dr[u] = lds_f32(src + u * 128u);
-            if (q + NS2 < Q) nbar_arrive<1 + NS2>(slot);  // values are in registers: hand the slot back
-            const uint32_t rp = rcol_s + kpos * rstep;
-            if (do_minmax) back_chunk<KU, true>(L, kf, dr, rp, rstep, in_group, exptab_s, mc);
-            else back_chunk<KU, false>(L, kf, dr, rp, rstep, in_group, exptab_s, mc);
-            kpos += KU;
-            if (kpos == B) {
-                kpos = 0;
-                if (main_phase) {
-                    block_end(L, a, rcol, relbuf, lane, g, c, rec, rec0, active, rec_mask, lower_mask, cnt, blk, 0, B);
-                    ++blk;
-                }
-                L.bmax = -INFINITY; L.bmin = INFINITY;
-            }
-        }
-        if (active) {
-            a.st.mn[lid] = L.mn; a.st.mx[lid] = L.mx;
-            a.st.prev[lid] = L.prev; a.st.state[lid] = L.state; a.st.deb[lid] = L.deb;
-            if (c == 0 && a.on_cnt != nullptr) a.on_cnt[rec] = cnt;
-        }
-    }
-}
 
 __global__ void k1_reset(DetState st, int64_t n, float floor_db) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -1167,25 +914,18 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     { int rc = upload_tables(); if (rc != OFP_OK) return rc; }
     const int grid = (a.R + a.G - 1) / a.G;
     const bool sym = p.use_hp && memcmp(&p.b[0], &p.b[4], 4) == 0 && memcmp(&p.b[1], &p.b[3], 4) == 0;
-    // two-warp split (default whenever the input can be tiled by TMA and blocks are whole chunks)
-    if (tma_ok && B % KU == 0 && a.T % KU == 0 && env_int("OFP_K1_SPLIT", 1)) {
-        const bool safe = p.fast_att <= 1.0f && p.fast_rel <= 1.0f && p.slow_att <= 1.0f && p.slow_rel <= 1.0f &&
-                          p.fast_att > 0.0f && p.fast_rel > 0.0f && p.slow_att > 0.0f && p.slow_rel > 0.0f;
-        auto k2 = p.use_hp ? (sym ? (safe ? k1_detect2<true, true, true> : k1_detect2<true, true, false>)
-                                  : (safe ? k1_detect2<true, false, true> : k1_detect2<true, false, false>))
-                           : (safe ? k1_detect2<false, false, true> : k1_detect2<false, false, false>);
-        a.role_swap = env_int("OFP_K1_ROLESWAP", 0); a.n_sm = sm_count();
-        const size_t smem2 = smem + static_cast<size_t>(NS2) * KU * 32 * 4;
-        OFP_REQUIRE(smem2 <= 227 * 1024, "block_size %d x %d channels needs %zu bytes of shared memory", B, C, smem2);
-        OFP_CUDA_CHECK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
-        OFP_CUDA_CHECK(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        k2<<<grid, 64, smem2, stream>>>(tmap, a);
-        OFP_CUDA_CHECK(cudaGetLastError());
-        return OFP_OK;
-    }
-    auto kern = p.use_hp ? (tma_ok ? (sym ? k1_detect<true, true, true> : k1_detect<true, true, false>)
-                                   : (sym ? k1_detect<true, false, true> : k1_detect<true, false, false>))
-                         : (tma_ok ? k1_detect<false, true, false> : k1_detect<false, false, false>);
+    // every follower coefficient in (0, 1]: the per-chunk form of the sliver test is valid (chunk_fast)
+    const bool safe = p.fast_att <= 1.0f && p.fast_rel <= 1.0f && p.slow_att <= 1.0f && p.slow_rel <= 1.0f &&
+                      p.fast_att > 0.0f && p.fast_rel > 0.0f && p.slow_att > 0.0f && p.slow_rel > 0.0f &&
+                      p.floor_db < -3.0f && !env_int("OFP_K1_NO_SAFE", 0);
+    auto pick = [&](auto hp, auto tma, auto sy) {
+        return safe ? k1_detect<decltype(hp)::value, decltype(tma)::value, decltype(sy)::value, true>
+                    : k1_detect<decltype(hp)::value, decltype(tma)::value, decltype(sy)::value, false>;
+    };
+    using T_ = std::true_type; using F_ = std::false_type;
+    auto kern = p.use_hp ? (tma_ok ? (sym ? pick(T_{}, T_{}, T_{}) : pick(T_{}, T_{}, F_{}))
+                                   : (sym ? pick(T_{}, F_{}, T_{}) : pick(T_{}, F_{}, F_{})))
+                         : (tma_ok ? pick(F_{}, T_{}, F_{}) : pick(F_{}, F_{}, F_{}));
     OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, 32, smem, stream>>>(tmap, a);
     OFP_CUDA_CHECK(cudaGetLastError());

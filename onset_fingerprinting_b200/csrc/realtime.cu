@@ -12,6 +12,12 @@
 
 #include <cstring>
 
+extern "C" int ofp_stream_locate_ring_dev(const double *, int32_t, const float *, int32_t, const float *, const float *,
+                                          const float *, double, double, double, double, int32_t, int32_t,
+                                          const int32_t *, const int32_t *, const int32_t *, int64_t *, int32_t,
+                                          const float *, int32_t, int32_t, int32_t, int32_t, int32_t *, int32_t *,
+                                          int32_t *, int64_t *, double *, int32_t *, void *);
+extern "C" int ofp_ring_write(float *, int32_t, const float *, int64_t, int32_t, int32_t, int32_t, const int64_t *, void *);
 extern "C" int ofp_stream_locate_dev(const double *, int32_t, const float *, int32_t, const float *, const float *,
                                      const float *, double, double, double, double, int32_t, int32_t, const int32_t *,
                                      const int32_t *, const int32_t *, int64_t *, int32_t, int32_t *, int32_t *,
@@ -21,6 +27,8 @@ struct ofp_rt {
     int32_t S = 0, C = 0, B = 0;
     ofp_detector *det = nullptr;
     float *in = nullptr;                        // [S, B, C] staging
+    float *ring = nullptr;                      // [S, ring_rows, C] most recent audio rows (ring_rows = 0: no refinement)
+    int32_t ring_rows = 0, ring_tol = 50, ring_cutoff = 10;
     int32_t *ch = nullptr, *dl = nullptr, *cnt = nullptr, *found = nullptr;
     double *xy = nullptr;
     int64_t *cur = nullptr;                     // device: start index of the next block
@@ -42,11 +50,22 @@ namespace {
 int rt_enqueue(ofp_rt *r) {
     int rc = ofp_detect_block(r->det, r->in, static_cast<int64_t>(r->B) * r->C, nullptr, r->ch, r->dl, r->cnt, r->stream);
     if (rc != OFP_OK) return rc;
-    rc = ofp_stream_locate_dev(r->locs, r->n_sensors, r->maps, r->map_size, r->mx, r->mn, r->mm, r->radius, r->spcm,
-                               r->sr, r->c, r->S, r->C, r->ch, r->dl, r->cnt, r->cur, r->B,
-                               static_cast<int32_t *>(r->state[0]), static_cast<int32_t *>(r->state[1]),
-                               static_cast<int32_t *>(r->state[2]), static_cast<int64_t *>(r->state[3]), r->xy, r->found,
-                               r->stream);
+    if (r->ring) {  // PlayRec.callback: rec_audio.write(block) -> detect_hits -> locate(..., rec_audio)
+        rc = ofp_ring_write(r->ring, r->ring_rows, r->in, 0, r->S, r->B, r->C, r->cur, r->stream);
+        if (rc != OFP_OK) return rc;
+        rc = ofp_stream_locate_ring_dev(r->locs, r->n_sensors, r->maps, r->map_size, r->mx, r->mn, r->mm, r->radius,
+                                        r->spcm, r->sr, r->c, r->S, r->C, r->ch, r->dl, r->cnt, r->cur, r->B, r->ring,
+                                        r->ring_rows, r->B, r->ring_tol, r->ring_cutoff,
+                                        static_cast<int32_t *>(r->state[0]), static_cast<int32_t *>(r->state[1]),
+                                        static_cast<int32_t *>(r->state[2]), static_cast<int64_t *>(r->state[3]), r->xy,
+                                        r->found, r->stream);
+    } else {
+        rc = ofp_stream_locate_dev(r->locs, r->n_sensors, r->maps, r->map_size, r->mx, r->mn, r->mm, r->radius, r->spcm,
+                                   r->sr, r->c, r->S, r->C, r->ch, r->dl, r->cnt, r->cur, r->B,
+                                   static_cast<int32_t *>(r->state[0]), static_cast<int32_t *>(r->state[1]),
+                                   static_cast<int32_t *>(r->state[2]), static_cast<int64_t *>(r->state[3]), r->xy,
+                                   r->found, r->stream);
+    }
     if (rc != OFP_OK) return rc;
     OFP_CUDA_CHECK(cudaMemcpyAsync(r->xy_h, r->xy, sizeof(double) * 2 * r->S, cudaMemcpyDeviceToHost, r->stream));
     OFP_CUDA_CHECK(cudaMemcpyAsync(r->found_h, r->found, sizeof(int32_t) * r->S, cudaMemcpyDeviceToHost, r->stream));
@@ -63,7 +82,7 @@ int ofp_rt_destroy(ofp_rt *r) {
     if (r->graph) cudaGraphDestroy(r->graph);
     if (r->stream) cudaStreamDestroy(r->stream);
     cudaFree(r->in); cudaFree(r->ch); cudaFree(r->dl); cudaFree(r->cnt); cudaFree(r->found); cudaFree(r->xy);
-    cudaFree(r->cur);
+    cudaFree(r->cur); cudaFree(r->ring);
     for (void *p : r->state) cudaFree(p);
     cudaFreeHost(r->xy_h); cudaFreeHost(r->found_h);
     ofp_detector_destroy(r->det);
@@ -77,6 +96,8 @@ int ofp_rt_reset(ofp_rt *r) {
     if (rc != OFP_OK) return rc;
     for (int i = 0; i < 4; ++i) OFP_CUDA_CHECK(cudaMemsetAsync(r->state[i], 0, r->state_bytes[i], r->stream));
     OFP_CUDA_CHECK(cudaMemsetAsync(r->cur, 0, sizeof(int64_t), r->stream));
+    if (r->ring)
+        OFP_CUDA_CHECK(cudaMemsetAsync(r->ring, 0, sizeof(float) * static_cast<size_t>(r->S) * r->C * r->ring_rows, r->stream));
     OFP_CUDA_CHECK(cudaStreamSynchronize(r->stream));
     return OFP_OK;
 }
@@ -84,11 +105,12 @@ int ofp_rt_reset(ofp_rt *r) {
 int ofp_rt_create(ofp_rt **out, int32_t n_streams, const ofp_detector_params *p, const double *sensor_xyz_dev,
                   int32_t n_sensors, const float *lag_maps_dev, int32_t map_size, const float *max_lags_dev,
                   const float *min_lags_dev, const float *max_max_dev, double radius_cm, double samples_per_cm,
-                  double sr, double c_cm_s, int32_t use_graph) {
+                  double sr, double c_cm_s, int32_t use_graph, int32_t ring_rows) {
     OFP_REQUIRE(out && p && sensor_xyz_dev && lag_maps_dev && max_lags_dev && min_lags_dev && max_max_dev, "null argument");
     OFP_REQUIRE(n_streams > 0, "n_streams must be positive");
+    OFP_REQUIRE(ring_rows == 0 || ring_rows >= p->block_size, "ring_rows must be 0 (no refinement) or >= block_size");
     ofp_rt *r = new ofp_rt;
-    r->S = n_streams; r->C = p->n_channels; r->B = p->block_size;
+    r->S = n_streams; r->C = p->n_channels; r->B = p->block_size; r->ring_rows = ring_rows;
     r->locs = sensor_xyz_dev; r->maps = lag_maps_dev; r->mx = max_lags_dev; r->mn = min_lags_dev; r->mm = max_max_dev;
     r->n_sensors = n_sensors; r->map_size = map_size; r->radius = radius_cm; r->spcm = samples_per_cm; r->sr = sr;
     r->c = c_cm_s;
@@ -109,6 +131,10 @@ int ofp_rt_create(ofp_rt **out, int32_t n_streams, const ofp_detector_params *p,
     const size_t SC = static_cast<size_t>(r->S) * r->C;
     RT_CHECK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     RT_CHECK(cudaMalloc(&r->in, sizeof(float) * SC * r->B));
+    if (ring_rows > 0) {
+        RT_CHECK(cudaMalloc(&r->ring, sizeof(float) * SC * ring_rows));
+        RT_CHECK(cudaMemset(r->ring, 0, sizeof(float) * SC * ring_rows));
+    }
     RT_CHECK(cudaMalloc(&r->ch, sizeof(int32_t) * SC));
     RT_CHECK(cudaMalloc(&r->dl, sizeof(int32_t) * SC));
     RT_CHECK(cudaMalloc(&r->cnt, sizeof(int32_t) * r->S));

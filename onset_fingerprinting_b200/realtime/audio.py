@@ -168,7 +168,12 @@ class RealtimeSession:
     ``StreamLocatorBatch`` block by block (tests/test_gpu_stream_locate.py)."""
 
     def __init__(self, n_streams: int, ml_conf: dict, n_channels: int = config.N_CHANNELS,
-                 blocksize: int = config.BLOCKSIZE, detector_kw: dict | None = None, use_graph: bool = True):
+                 blocksize: int = config.BLOCKSIZE, detector_kw: dict | None = None, use_graph: bool = True,
+                 ring_rows: int = 0):
+        """ring_rows > 0: every stream keeps a ring of its last ring_rows audio rows on the device and each new
+        (group, detection) pair goes through the cross-correlation refinement of ``locate(..., rec_audio)``
+        (multilateration.py:457-501) -- what PlayRec's callback runs (realtime/audio.py:69, 102).
+        ring_rows = 0 is ``locate(..., rec_audio=None)``."""
         import ctypes as C
 
         from .. import _lib
@@ -185,7 +190,9 @@ class RealtimeSession:
         _lib.check(_lib.lib().ofp_rt_create(C.byref(self._h), C.c_int32(n_streams), C.byref(self._params), ptr(m._locs),
                                             C.c_int32(m._S), ptr(m._maps), C.c_int32(m._M), ptr(m._mx), ptr(m._mn),
                                             ptr(m._mm), C.c_double(m.radius), C.c_double(m.samples_per_cm),
-                                            C.c_double(m.sr), C.c_double(m.c), C.c_int32(int(use_graph))))
+                                            C.c_double(m.sr), C.c_double(m.c), C.c_int32(int(use_graph)),
+                                            C.c_int32(int(ring_rows))))
+        self.ring_rows = int(ring_rows)
         self.xy = np.empty((n_streams, 2), np.float64)
         self.found = np.empty((n_streams,), np.int32)
         self.current_index = 0

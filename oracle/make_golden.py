@@ -576,6 +576,52 @@ def gen_hits16(det):
                         raised_scalar=raised_scalar, tied=tied, x_sha=sha(xs), on_sha=sha(on), env=env())
     print("hits16: moved", float((fixed != on).mean()), "raised", int(raised.sum()), "of", len(on), "| tied hits",
           int(tied.sum()), "of which the SIMD and scalar argsort orders give different results:", int(differ.sum()))
+STREAM_RING = dict(n_streams=48, seconds=1.2, seed0=300, ring_rows=4096)
+
+
+def stream_ring_input(s):
+    """Recording of stream s of the ring-refinement fixture: hits every 0.118 s from a stream-dependent start."""
+    return synth.drum_recording(seconds=STREAM_RING["seconds"], seed=STREAM_RING["seed0"] + s,
+                                first_hit=6000 + 997 * (s % 11))[0]
+
+
+def gen_stream_ring(det, ml):
+    """PlayRec.detect_hits with rec_audio for 48 independent streams (realtime/audio.py:62-74, 102;
+    multilateration.py:428-534 incl. the ring-buffer refinement 457-501), block by block: the golden for the
+    batched device session (csrc/realtime.cu with ring_rows > 0).  Per stream: the blocks in which a hit was
+    located and its position; `raised` = block at which the reference itself raised, -1 = never."""
+    S = STREAM_RING["n_streams"]
+    rows, raised, ndet = [], np.full(S, -1, np.int64), np.zeros(S, np.int64)
+    for s in range(S):
+        x = stream_ring_input(s)
+        od = det.AmplitudeOnsetDetector(3, 128, hipass_freq=0, fast_ar=(0.3, 800), slow_ar=(8000, 8000),
+                                        on_threshold=0.45, off_threshold=0.45, cooldown=1323, sr=96000)
+        m = ml.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+        ring = rh.RingStub(np.zeros((STREAM_RING["ring_rows"], 3), np.float32))
+        cur = 0
+        with contextlib.redirect_stdout(io.StringIO()):
+            for b, i in enumerate(range(0, len(x) - 127, 128)):
+                blk = x[i:i + 128]
+                ring.write(blk)
+                c, dl, _ = od(blk)
+                if len(c) > 0:
+                    dd = [cur + int(v) for v in dl]
+                    ndet[s] += len(c)
+                    try:
+                        for k in np.argsort(dd):
+                            res = m.locate(int(c[k]), dd[k], ring)
+                            if res is not None:
+                                rows.append((s, b, res[0], res[1]))
+                                break
+                    except ValueError:
+                        raised[s] = b
+                        break
+                cur += 128
+    rows = np.asarray(rows, np.float64).reshape(-1, 4)
+    np.savez_compressed(OUT / "stream_ring.npz", rows=rows, raised=raised, n_detections=ndet, env=env())
+    print("stream_ring: streams", S, "detections", int(ndet.sum()), "located", len(rows), "raised", int((raised >= 0).sum()))
+
+
 
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
@@ -589,6 +635,9 @@ def main():
     if "hits16_scalar" in sys.argv:  # child of gen_hits16, runs with numpy's SIMD sort kernels disabled
         _, _, fixed, raised = _hits16_reference(det)
         np.savez(sys.argv[-1], fixed=fixed, raised=raised)
+        return
+    if "ring" in sys.argv:
+        gen_stream_ring(det, ml)
         return
     if "sizes" in sys.argv:  # parity at the sizes BASELINE.json states
         gen_config0(det, ml)
@@ -611,6 +660,7 @@ def main():
     gen_stream_fsm(ml)
     gen_config0(det, ml)
     gen_hits16(det)
+    gen_stream_ring(det, ml)
 
 
 if __name__ == "__main__":

@@ -34,7 +34,7 @@ def test_group_state_machine_vs_reference(golden_dir):
         assert np.array_equal(found == 1, ok), b
         assert (found >= 0).all()
         assert np.allclose(xy[ok], want[ok], rtol=1e-9, atol=1e-9)
-        n_groups = sl._state[0].view(torch.int32).cpu().numpy()
+        n_groups = sl._state[0].view(torch.int32).cpu().numpy() & 0xff  # upper bits: the group-identity counter
         assert np.array_equal(n_groups, g["n_groups"][:, b]), b
         n_loc += int(ok.sum())
     assert n_loc > 900
@@ -91,3 +91,40 @@ def test_realtime_session_graph_equals_python_path(use_graph):
             n_loc += int((f == 1).sum())
         assert n_loc >= S  # every stream locates at least one hit on average
         sl.reset(); rs.reset()
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_ring_refinement_session_vs_reference(use_graph, golden_dir):
+    """The realtime path as PlayRec runs it -- locate(sensor, onset, rec_audio), i.e. WITH the ring-buffer
+    cross-correlation refinement of every new pair (multilateration.py:457-501) -- for 48 concurrent streams in the
+    native session (one warp per stream, per-stream device ring): block by block the same hits at the same
+    positions as the unmodified reference run stream by stream (tests/golden/stream_ring.npz)."""
+    from oracle.make_golden import STREAM_RING, stream_ring_input
+    from onset_fingerprinting_b200.realtime.audio import RealtimeSession
+
+    g = np.load(golden_dir / "stream_ring.npz")
+    S = STREAM_RING["n_streams"]
+    xs = np.stack([stream_ring_input(s) for s in range(S)])
+    nblk = xs.shape[1] // 128
+    want = {(int(r[0]), int(r[1])): r[2:] for r in g["rows"]}
+    assert len(want) == 289 and (g["raised"] < 0).all()
+    rs = RealtimeSession(S, ML_CONF, use_graph=use_graph, ring_rows=STREAM_RING["ring_rows"])
+    xd = torch.from_numpy(xs).cuda()
+    for attempt in range(2):
+        got = {}
+        for b in range(nblk):
+            xy, f = rs.detect_hits(xd[:, b * 128:(b + 1) * 128])
+            assert (f >= 0).all(), (b, f.min())
+            for s in np.nonzero(f == 1)[0]:
+                got[(int(s), b)] = xy[s].copy()
+        assert set(got) == set(want)
+        err = max(float(np.abs(got[k] - want[k]).max()) for k in want)
+        assert err <= 1e-9 * 20, err
+        rs.reset()
+    # the refinement changes results: without the ring the same streams locate a different set of hits
+    plain = RealtimeSession(S, ML_CONF, use_graph=use_graph)
+    got0 = set()
+    for b in range(nblk):
+        xy, f = plain.detect_hits(xd[:, b * 128:(b + 1) * 128])
+        got0 |= {(int(s), b) for s in np.nonzero(f == 1)[0]}
+    assert got0 != set(want)
