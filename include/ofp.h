@@ -294,6 +294,17 @@ int ofp_filter_data(const float *x_dev, float *out_dev, int64_t n_samples, int32
 int ofp_detect_onset_region(const float *audio_dev, int32_t n_signals, int64_t len, const int32_t *onsets_dev,
                             int32_t n, int32_t median_filter_size, float threshold_factor, int32_t *out_dev,
                             void *stream);
+/* Peak refinement of the dataset builder (notebooks/refresh.org:262-279): out[h, c] = onsets[h, c] +
+ * argmax(audio[onsets[h, c] : onsets[h, c] + tolerance, c]) (first maximum; -1 = missing channel stays -1).
+ * audio_dev [R, n_samples, C], hit h in recording hit_rec_dev[h] (NULL: hit h in recording h). */
+int ofp_window_argmax(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                      const int32_t *hit_rec_dev, const int32_t *onsets_dev, int32_t n_hits, int32_t tolerance,
+                      int32_t *out_dev, void *stream);
+/* RecAnalysis.tempogram (realtime/recording.py:313-327) for the frames first_frame + k*every (k < n_selected) of
+ * every row of oe_dev [n_rec, n_frames]: tg_dev [n_rec, n_selected, win_length] = autocorrelation of
+ * window * oe[j - win_length + 1 .. j] (zeros before frame 0) divided by (its maximum + 1e-10). */
+int ofp_tempogram(const float *oe_dev, int32_t n_rec, int64_t n_frames, const float *window_dev, int32_t win_length,
+                  int64_t first_frame, int64_t every, int64_t n_selected, float *tg_dev, void *stream);
 /* np.correlate(x, y, "full") as find_lag / find_lag_multi use it (multilateration.py:878-899):
  * x_dev, y_dev [P, n] -> out_dev [P, 2n-1] (double accumulation, rounded once). */
 int ofp_correlate_full(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, float *out_dev,

@@ -304,3 +304,102 @@ extern "C" int ofp_extract_frames(const float *audio_dev, int64_t n_samples, int
     OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Peak refinement of the notebooks' dataset builder (notebooks/refresh.org:262-279):
+//     onsets[h, c] + np.argmax(audio[onsets[h, c] : onsets[h, c] + tolerance, c])
+// One warp per (hit, channel): strided window read, first maximum wins (np.argmax).
+// ---------------------------------------------------------------------------------------------
+namespace ofp {
+__global__ void k_window_argmax(const float *audio, int64_t n_samples, int64_t rec_stride, int C, const int32_t *hit_rec,
+                                const int32_t *onsets, int64_t n_pairs, int tol, int32_t *out) {
+    const int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_pairs) return;
+    const int64_t h = w / C;
+    const int c = static_cast<int>(w - h * C);
+    const int64_t on = onsets[w];
+    if (on < 0) { if (lane == 0) out[w] = static_cast<int32_t>(on); return; }  // missing channel stays missing
+    const float *col = audio + (hit_rec ? hit_rec[h] : h) * rec_stride + c;
+    const int64_t end = (on + tol < n_samples) ? on + tol : n_samples;  // python slice clips at the end of the recording
+    float best = -INFINITY;
+    int64_t best_i = INT64_MAX;
+    for (int64_t i = on + lane; i < end; i += 32) {
+        const float v = col[i * C];
+        if (v > best || (best_i == INT64_MAX && !(v < best))) { best = v; best_i = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane == 0) out[w] = static_cast<int32_t>(best_i == INT64_MAX ? on : best_i);  // empty window: argmax raises; keep
+}
+
+// ---------------------------------------------------------------------------------------------
+// RecAnalysis.tempogram (realtime/recording.py:313-327): for frame j the autocorrelation of the Hann-windowed
+// last W onset-envelope values, irfft(|rfft(w * oe[j-W+1 .. j], n = 2W-1)|^2)[:W] (no circular wrap at that
+// padding => the plain linear autocorrelation), normalised by (max + 1e-10).  Values before the first frame
+// read 0 (the reference's ring is zero-initialised).  One CTA per (recording, selected frame).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tempogram(const float *oe, int64_t n_frames, const float *window, int W, int64_t first, int64_t every,
+                            int64_t n_sel, float *tg) {
+    extern __shared__ float tgs[];  // [W] windowed envelope, then [W] raw autocorrelation
+    float *x = tgs, *ac = tgs + W;
+    const int64_t r = blockIdx.y, j = first + static_cast<int64_t>(blockIdx.x) * every;
+    const float *row = oe + r * n_frames;
+    for (int t = threadIdx.x; t < W; t += blockDim.x) {
+        const int64_t f = j - W + 1 + t;
+        x[t] = __fmul_rn(window[t], f >= 0 && f < n_frames ? row[f] : 0.0f);
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int l = threadIdx.x; l < W; l += blockDim.x) {
+        double acc = 0.0;
+        for (int t = 0; t + l < W; ++t) acc = fma(static_cast<double>(x[t]), static_cast<double>(x[t + l]), acc);
+        const float v = static_cast<float>(acc);
+        ac[l] = v;
+        mx = fmaxf(mx, v);
+    }
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int k = 1; k < (blockDim.x + 31) / 32; ++k) mx = fmaxf(mx, red[k]);
+    const float inv = __fadd_rn(mx, 1e-10f);
+    float *dst = tg + (r * n_sel + blockIdx.x) * W;
+    for (int l = threadIdx.x; l < W; l += blockDim.x) dst[l] = __fdiv_rn(ac[l], inv);
+}
+}  // namespace ofp
+
+extern "C" int ofp_window_argmax(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
+                                 const int32_t *hit_rec_dev, const int32_t *onsets_dev, int32_t n_hits,
+                                 int32_t tolerance, int32_t *out_dev, void *stream) {
+    OFP_REQUIRE(audio_dev && onsets_dev && out_dev, "null argument");
+    OFP_REQUIRE(n_channels >= 1 && tolerance >= 1, "bad size");
+    if (n_hits == 0) return OFP_OK;
+    const int64_t pairs = static_cast<int64_t>(n_hits) * n_channels;
+    ofp::k_window_argmax<<<static_cast<unsigned>((pairs * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        audio_dev, n_samples, rec_stride, n_channels, hit_rec_dev, onsets_dev, pairs, tolerance, out_dev);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+extern "C" int ofp_tempogram(const float *oe_dev, int32_t n_rec, int64_t n_frames, const float *window_dev,
+                             int32_t win_length, int64_t first_frame, int64_t every, int64_t n_selected, float *tg_dev,
+                             void *stream) {
+    OFP_REQUIRE(oe_dev && window_dev && tg_dev, "null argument");
+    OFP_REQUIRE(win_length >= 1 && win_length <= 8192 && every >= 1 && first_frame >= 0, "bad tempogram shape");
+    OFP_REQUIRE(n_selected >= 0 && (n_selected == 0 || first_frame + (n_selected - 1) * every < n_frames),
+                "selected frames exceed the envelope");
+    if (n_rec == 0 || n_selected == 0) return OFP_OK;
+    OFP_REQUIRE(n_selected < (1ll << 31) && n_rec <= 65535, "grid too large: select fewer frames or recordings per call");
+    const size_t smem = 2 * static_cast<size_t>(win_length) * sizeof(float);
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(ofp::k_tempogram, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid(static_cast<unsigned>(n_selected), static_cast<unsigned>(n_rec));
+    ofp::k_tempogram<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(oe_dev, n_frames, window_dev, win_length,
+                                                                           first_frame, every, n_selected, tg_dev);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}

@@ -187,9 +187,11 @@ __global__ void __launch_bounds__(K2_THREADS) k2_flux(const K2Args a) {
 #include "spectral_flux_warp.cuh"
 namespace ofp {
 
-// librosa.util.peak_pick restated (greedy, sequential; one thread per recording):
-// x[n] is a peak if x[n] == max(x[n-pre_max : n+post_max+1]) and x[n] >= mean(x[n-pre_avg : n+post_avg+1]) + delta
-// and n - last_peak > wait.
+// librosa.util.peak_pick restated (greedy, sequential; one thread per recording): x[n] is a peak iff
+//   x[n] == max(x[n-pre_max : n+post_max])  and  x[n] >= mean(x[n-pre_avg : n+post_avg]) + delta  and  n - last > wait
+// with HALF-OPEN windows clipped at the ends (librosa's documented conditions; its 0.9 implementation builds them
+// from maximum_filter1d / uniform_filter1d of length pre+post with a shifted origin -- oracle/librosa_standin.py).
+// A zero-valued sample is never a peak (librosa multiplies the detections into x).  The mean is accumulated in double.
 __global__ void k2_peak_pick(const float *oe, int n_frames, int R, int pre_max, int post_max, int pre_avg,
                              int post_avg, float delta, int wait, int32_t *peaks, int32_t *n_peaks, int cap) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,15 +200,16 @@ __global__ void k2_peak_pick(const float *oe, int n_frames, int R, int pre_max, 
     int cnt = 0;
     int last = -(1 << 30);
     for (int n = 0; n < n_frames; ++n) {
-        const int a0 = max(0, n - pre_max), a1 = min(n_frames, n + post_max + 1);
+        if (n - last <= wait) continue;
+        const int a0 = max(0, n - pre_max), a1 = min(n_frames, max(n + post_max, n + 1));
         float mx = -INFINITY;
         for (int i = a0; i < a1; ++i) mx = fmaxf(mx, x[i]);
-        if (x[n] != mx) continue;
-        const int b0 = max(0, n - pre_avg), b1 = min(n_frames, n + post_avg + 1);
-        float s = 0.f;
-        for (int i = b0; i < b1; ++i) s += x[i];
-        if (x[n] < s / static_cast<float>(b1 - b0) + delta) continue;
-        if (n - last <= wait) continue;
+        if (x[n] != mx || x[n] == 0.0f) continue;
+        const int b0 = max(0, n - pre_avg), b1 = min(n_frames, max(n + post_avg, n + 1));
+        double s = 0.0;
+        for (int i = b0; i < b1; ++i) s += static_cast<double>(x[i]);
+        const float avg = static_cast<float>(s / static_cast<double>(b1 - b0));
+        if (x[n] < __fadd_rn(avg, delta)) continue;
         if (cnt < cap) peaks[static_cast<int64_t>(r) * cap + cnt] = n;
         ++cnt;
         last = n;

@@ -500,6 +500,23 @@ def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 
     return out, lags, status
 
 
+def max_onsets_batch(audio, hit_rec, hit_onsets, tolerance: int):
+    """The peak refinement of the notebooks' dataset builder (notebooks/refresh.org:262-279):
+    ``og[i] + np.argmax(audio[og[i] : og[i] + tolerance, i])`` for every hit and channel in one launch.
+    audio [R, N, C] (device or numpy), hit_rec [H] or None (hit h in recording h), hit_onsets [H, C] int32."""
+    torch = _lib.require_cuda()
+    audio = _to_dev(audio, torch)
+    R, N, Cn = audio.shape
+    hit_onsets = hit_onsets.to(device="cuda", dtype=torch.int32).contiguous()
+    if hit_rec is not None:
+        hit_rec = hit_rec.to(device="cuda", dtype=torch.int32).contiguous()
+    out = torch.empty_like(hit_onsets)
+    check(_lib.lib().ofp_window_argmax(ptr(audio), C.c_int64(N), C.c_int64(audio.stride(0)), C.c_int32(Cn), ptr(hit_rec),
+                                       ptr(hit_onsets), C.c_int32(hit_onsets.shape[0]), C.c_int32(int(tolerance)),
+                                       ptr(out), stream_ptr()))
+    return out
+
+
 def fix_onsets(audio: np.ndarray, onsets: np.ndarray, filter_size: int = 5, d: int = 0, onset_direction=None,
                take_abs: bool = False, zero_left: bool = False, normalization_cutoff: int = 10,
                onset_tolerance: int = 30, shift_onsets: int = 0, return_status: bool = False):

@@ -21,6 +21,22 @@ from ._lib import check, ptr, stream_ptr
 _ACT = {nn.SiLU: 0, nn.ReLU: 1, nn.Tanh: 2, nn.Identity: 3}
 
 
+def paired_xcorr(x: torch.Tensor, C: int, K: int) -> torch.Tensor:
+    """model.paired_xcorr (model.py:12-45): full cross-correlation of every adjacent channel pair (1&2, 2&3, ...) of
+    each feature map, averaged over the K maps.  x [B, C*K, V] -> [B, C-1, 2V-1].  The grouped ``F.conv1d`` of the
+    reference is one np.correlate(a, b, "full") per (batch, pair, map) row: those rows go through
+    ofp_correlate_full (csrc/onset_tools.cu, double accumulation) in one launch; the mean over K is a reshape."""
+    from .multilateration import correlate_full
+
+    B, CK, V = x.shape
+    assert CK == C * K
+    xv = x.reshape(B, C, K, V)
+    a = xv[:, :-1].reshape(B * (C - 1) * K, V).float().contiguous()
+    b = xv[:, 1:].reshape(B * (C - 1) * K, V).float().contiguous()
+    cc = correlate_full(a.cuda(), b.cuda())  # [B*(C-1)*K, 2V-1]
+    return cc.view(B, C - 1, K, 2 * V - 1).mean(dim=2)
+
+
 class CNN(nn.Module):
     def __init__(self, input_size: int, output_size: int, channels: int = 3, layer_sizes: list[int] = [8, 16],
                  kernel_size: int = 3, dropout_rate: float = 0.5, loss=None, batch_norm=False, pool=False,

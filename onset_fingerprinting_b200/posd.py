@@ -107,6 +107,23 @@ def write_session(folder, name: str, audio: np.ndarray, sr: int, onsets, locatio
     return d
 
 
+def onsets_to_hits(onsets, zone: str = "center") -> dict:
+    """notebooks/refresh.org:243-249: the `combined.json` table -- {"hits": [{"i", "zone", "onset_start"}]}."""
+    return {"hits": [{"i": i, "zone": zone, "onset_start": [int(v) for v in np.atleast_1d(row)]}
+                     for i, row in enumerate(np.asarray(onsets))]}
+
+
+def write_combined(folder, audio: np.ndarray, sr: int, onsets, name: str = "combined", zone: str = "center") -> dict:
+    """notebooks/refresh.org:281-287: <folder>/combined.wav + combined.json (sf.write + json.dump(onsets_to_hits))."""
+    folder = Path(folder)
+    folder.mkdir(parents=True, exist_ok=True)
+    write_wav(folder / f"{name}.wav", audio, sr)
+    d = onsets_to_hits(onsets, zone)
+    with open(folder / f"{name}.json", "w") as f:
+        json.dump(d, f)
+    return d
+
+
 def read_json(file) -> dict:
     """data.read_json (data.py:31-38)."""
     with open(file, "r") as f:

@@ -100,3 +100,22 @@ def detect_onsets_spectral(x: np.ndarray, n_fft: int = 256, hop: int = 32, sr: i
                                  int(0.01 * sr // hop + 1), 0.1, int(sr * 0.07 // hop))
     p = peaks[0, : int(cnt[0].item())].cpu().numpy().astype(np.int64) * hop
     return (p, oe[0].cpu().numpy()) if return_oe else p
+
+
+def tempogram_batch(oe, win_length: int = 384, first_frame: int = 0, every: int = 1, window: np.ndarray | None = None):
+    """RecAnalysis.tempogram (realtime/recording.py:313-327) for frames first_frame, first_frame + every, ... of every
+    row of the onset envelope oe [R, F]: the autocorrelation of the Hann-windowed (symmetric window, recording.py:244)
+    last win_length envelope values, normalised by (max + 1e-10).  Returns [R, n_selected, win_length] float32."""
+    torch = _lib.require_cuda()
+    oe = _to_dev(oe, torch)
+    if oe.dim() == 1:
+        oe = oe[None]
+    R, F = oe.shape
+    n_sel = 0 if first_frame >= F else (F - 1 - first_frame) // every + 1
+    if window is None:
+        window = hann(win_length, periodic=False)
+    wd = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float32)).cuda()
+    tg = torch.empty((R, n_sel, win_length), dtype=torch.float32, device="cuda")
+    check(_lib.lib().ofp_tempogram(ptr(oe.contiguous()), C.c_int32(R), C.c_int64(F), ptr(wd), C.c_int32(win_length),
+                                   C.c_int64(first_frame), C.c_int64(every), C.c_int64(n_sel), ptr(tg), stream_ptr()))
+    return tg

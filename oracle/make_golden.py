@@ -622,6 +622,25 @@ def gen_stream_ring(det, ml):
     print("stream_ring: streams", S, "detections", int(ndet.sum()), "located", len(rows), "raised", int((raised >= 0).sum()))
 
 
+SPECTRAL = dict(seconds=2.0, seed=15)
+
+
+def gen_spectral(det):
+    """Spectral-flux row (a6).  librosa / loopmate are absent, so the pin is (a) the UNMODIFIED reference's
+    detect_onsets_spectral run on top of oracle/librosa_standin.py (scipy.signal.ShortTimeFFT, librosa 0.9's
+    filter-based peak picker) on the channel mean of a synthetic recording, and (b) the realtime onset strength
+    (recording.py:273-296, un-normalised) through scipy.signal.ShortTimeFFT."""
+    from oracle import librosa_standin as ls
+
+    x, _ = synth.drum_recording(**SPECTRAL)
+    mono = np.ascontiguousarray(x.mean(1), np.float32)
+    peaks, oe = det.detect_onsets_spectral(mono, return_oe=True)
+    flux = ls.onset_strength_shorttimefft(x, 2048, 128)
+    np.savez_compressed(OUT / "spectral.npz", peaks=np.asarray(peaks, np.int64), oe=np.asarray(oe, np.float32),
+                        flux2048=flux, x_sha=sha(x), env=env())
+    print("spectral: frames", len(oe), "peaks", len(peaks), "flux frames", len(flux))
+
+
 
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
@@ -635,6 +654,9 @@ def main():
     if "hits16_scalar" in sys.argv:  # child of gen_hits16, runs with numpy's SIMD sort kernels disabled
         _, _, fixed, raised = _hits16_reference(det)
         np.savez(sys.argv[-1], fixed=fixed, raised=raised)
+        return
+    if "spectral" in sys.argv:
+        gen_spectral(det)
         return
     if "ring" in sys.argv:
         gen_stream_ring(det, ml)
@@ -661,6 +683,7 @@ def main():
     gen_config0(det, ml)
     gen_hits16(det)
     gen_stream_ring(det, ml)
+    gen_spectral(det)
 
 
 if __name__ == "__main__":

@@ -1,7 +1,9 @@
 """numpy restatement of the spectral-flux path (TEST INFRASTRUCTURE).
 
-recording.py:273-311 (realtime) and detection.py:89-128 (offline).  librosa / loopmate are absent from
-the reference tree, so this restates their documented behaviour; "parity unpinned" for this row."""
+recording.py:273-311 (realtime) and detection.py:89-128 (offline).  librosa / loopmate are absent from the
+reference tree, so this restates their documented behaviour.  Pin: tests/golden/spectral.npz = the unmodified
+reference's detect_onsets_spectral run over an INDEPENDENT scipy implementation of the three librosa calls
+(oracle/librosa_standin.py: ShortTimeFFT, filter-based peak picker) -- tests/test_spectral_cpu.py."""
 import numpy as np
 
 
@@ -40,13 +42,15 @@ def stft_mag(x, n_fft, hop):
 
 
 def peak_pick(x, pre_max, post_max, pre_avg, post_avg, delta, wait):
+    """librosa.util.peak_pick's documented conditions, half-open windows: x[n] == max(x[n-pre_max : n+post_max]),
+    x[n] >= mean(x[n-pre_avg : n+post_avg]) + delta, n - previous > wait; zero-valued samples are never peaks."""
     peaks, last = [], -(1 << 30)
     for n in range(len(x)):
-        if x[n] != x[max(0, n - pre_max):n + post_max + 1].max():
-            continue
-        if x[n] < x[max(0, n - pre_avg):n + post_avg + 1].mean() + delta:
-            continue
         if n - last <= wait:
+            continue
+        if x[n] != x[max(0, n - pre_max):max(n + post_max, n + 1)].max() or x[n] == 0:
+            continue
+        if x[n] < np.float32(x[max(0, n - pre_avg):max(n + post_avg, n + 1)].astype(np.float64).mean()) + np.float32(delta):
             continue
         peaks.append(n)
         last = n
@@ -60,3 +64,12 @@ def detect_onsets_spectral(x, weight, n_fft=256, hop=32, sr=96000):
     p = peak_pick(oe, int(0.12 * sr // hop), int(0.01 * sr // hop), int(0.12 * sr // hop), int(0.01 * sr // hop + 1),
                   0.1, int(sr * 0.07 // hop))
     return p * hop, oe
+
+
+def tempogram_frame(oe_last, window):
+    """recording.py:313-327 for one frame: oe_last = the last W onset-envelope values (zeros before the start)."""
+    W = len(window)
+    pad = 2 * W - 1
+    spec = np.fft.rfft(window.astype(np.float64) * oe_last.astype(np.float64), n=pad)
+    tg = np.fft.irfft(spec.real ** 2 + spec.imag ** 2, n=pad)[:W]
+    return (tg / (tg.max() + 1e-10)).astype(np.float32)

@@ -26,13 +26,6 @@
 #include <mutex>
 #include "k1_math.cuh"
 
-// Speed-of-light ladder for profiles/ (scripts/k1_ladder.sh): 0 = TMA in + rel out only, 1 = + high-pass,
-// 2 = + dB, 3 = + followers, 4 = + 10**x, 5.. = the full detector (default).  Anything below 5 computes
-// something else than the detector and only exists to time the stages.
-#ifndef OFP_K1_LADDER
-#define OFP_K1_LADDER 9
-#endif
-
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -332,27 +325,32 @@ __device__ __forceinline__ void minmax_step(Lane &L, const Coef &k, float r) {
 // U samples are independent instruction streams between the short sequential recurrences.  The rare
 // slow paths are taken after a warp vote, outside the straight-line code.
 //   xs: shared address of the lane's first input sample, rs: of its first rel slot; step = 4*C bytes.
-template <bool USE_HP, int U>
+template <bool USE_HP, int U, bool FROM_DB = false>
 __device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
                                       bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
                                       const MathConst &mc, uint32_t rstep = 0) {
     float h[U], db[U], dr[U], amp[U], aux[U];
     bool redo[U], any = false;
     if (rstep == 0) rstep = step;
+    if (FROM_DB) {  // warp-specialised consumer: dB values come from the producer warp's ring
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float x = lds_f32(xs + u * step);
-        h[u] = USE_HP ? hp_step(L, k, x) : x;
-    }
+        for (int u = 0; u < U; ++u) db[u] = lds_f32(xs + u * step);
+    } else {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        db[u] = to_db_fast(h[u], k.floor_db, logtab, mc, aux[u], redo[u]);
-        any |= redo[u];
-    }
-    if (__any_sync(0xffffffffu, any)) {
+        for (int u = 0; u < U; ++u) {
+            const float x = lds_f32(xs + u * step);
+            h[u] = USE_HP ? hp_step(L, k, x) : x;
+        }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (redo[u]) db[u] = db_of(slow_log10(aux[u]), k.floor_db);
+        for (int u = 0; u < U; ++u) {
+            db[u] = to_db_fast(h[u], k.floor_db, logtab, mc, aux[u], redo[u]);
+            any |= redo[u];
+        }
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (redo[u]) db[u] = db_of(slow_log10(aux[u]), k.floor_db);
+        }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {  // detection.py:751 (envelope_follower.c:6-25 twice)
@@ -404,14 +402,8 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float x = lds_f32(xs + u * step);
-            h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
+            h[u] = USE_HP ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
         }
-#if OFP_K1_LADDER <= 1  // speed-of-light ladder (profiles/): memory path only / + high-pass; results are NOT the detector's
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (store) sts_f32(rs + u * rstep, h[u]);
-        return false;
-#endif
         // exact short-cut (iv): a chunk whose samples all sit below the floor needs no logarithm
         float vmax = 0.0f;
 #pragma unroll
@@ -423,12 +415,6 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
             to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
         }
     }
-#if OFP_K1_LADDER == 2  // + dB
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * rstep, db[u]);
-    return flags != 0;
-#endif
     bool sliver = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -441,20 +427,12 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
         L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
         dr[u] = __fsub_rn(L.yf, L.ys);
     }
-#if OFP_K1_LADDER == 3  // + followers
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * rstep, dr[u]);
-    return sliver | (flags != 0);
-#endif
     to_amp_vec<U, false>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-#if OFP_K1_LADDER >= 5  // 4: + 10**x only; 5 and above: the full chunk
         if (DO_MM) minmax_step(L, k, amp[u]);
         L.bmax = fmaxf(L.bmax, amp[u]);
         L.bmin = fminf(L.bmin, amp[u]);
-#endif
         if (store) sts_f32(rs + u * rstep, amp[u]);
     }
     return sliver | (flags != 0);
@@ -675,10 +653,10 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                         const Lane saved = L;
                         // the min/max trackers only rest in the main phase of manual-threshold detectors
                         const bool bad = do_minmax
-                            ? chunk_fast<USE_HP, HP_SYM, KU, true>(L, kf, xp + i * step, rp + i * step, step,
-                                                                              in_group, logtab_s, exptab_s, mc)
-                            : chunk_fast<USE_HP, HP_SYM, KU, false>(L, kf, xp + i * step, rp + i * step, step,
-                                                                               in_group, logtab_s, exptab_s, mc);
+                            ? chunk_fast<USE_HP, HP_SYM, KU, true>(L, kf, xp + i * step, rp + i * step, step, in_group,
+                                                                   logtab_s, exptab_s, mc)
+                            : chunk_fast<USE_HP, HP_SYM, KU, false>(L, kf, xp + i * step, rp + i * step, step, in_group,
+                                                                    logtab_s, exptab_s, mc);
                         if (__any_sync(0xffffffffu, bad)) {  // rare: exact re-run of these samples
                             L = saved;
                             for (int e = 0; e < KU; ++e)
@@ -721,6 +699,10 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     }
 }
 
+}  // namespace ofp
+#include "onset_detect_ws.cuh"
+#include "onset_detect_pipe.cuh"
+namespace ofp {
 
 __global__ void k1_reset(DetState st, int64_t n, float floor_db) {
     const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -822,23 +804,12 @@ static int pick_tile(int C, int tcap = 64, int multiple = 1) {
     return best;
 }
 
-constexpr int MAX_DEVICES = 64;
-static int current_device() {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    return dev >= 0 && dev < MAX_DEVICES ? dev : 0;
-}
-
-// __device__ tables exist once per device: upload on first use of EACH device (a process may drive several)
 static int upload_tables() {
-    static std::mutex mu;
-    static bool done[MAX_DEVICES] = {false};
-    std::lock_guard<std::mutex> lock(mu);
-    const int dev = current_device();
-    if (done[dev]) return OFP_OK;
+    static bool done = false;
+    if (done) return OFP_OK;
     OFP_CUDA_CHECK(cudaMemcpyToSymbol(g_logtab, OFP_LOGTAB_H, sizeof(OFP_LOGTAB_H)));
     OFP_CUDA_CHECK(cudaMemcpyToSymbol(g_exptab, OFP_EXPTAB_H, sizeof(OFP_EXPTAB_H)));
-    done[dev] = true;
+    done = true;
     return OFP_OK;
 }
 
@@ -854,6 +825,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.ia_max = static_cast<float>(1.0 - static_cast<double>(p.alpha_max));
     a.floor_skip = env_int("OFP_K1_FLOOR_SKIP", 1);
     a.blk0 = blk0; a.cnt_in = cnt_in ? 1 : 0;
+    const bool plain = blk0 == 0 && !cnt_in;  // the opt-in experimental kernels only know whole recordings
     a.st = state_of(det);
     a.x = x; a.n_samples = n_samples; a.rec_stride = rec_stride;
     a.warm_n = std::min(warm_n, n_samples);
@@ -868,9 +840,13 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.nst = std::max(2, std::min(8, env_int("OFP_K1_STAGES", 2)));
     const int stage_bytes = (a.G * a.TC * 4 + 127) / 128 * 128;
     a.stage_floats = stage_bytes / 4;
+    // software-pipelined kernel (opt-in, OFP_K1_PIPE=1; measured 8 % slower than k1_detect at the same
+    // issue rate, DESIGN.md "K1 experiments"): needs TMA-able input and whole chunks per block and tile;
+    // its envelope buffer is a ring of B + PU rows
     const bool tma_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (a.R == 1 || rec_stride % 4 == 0) &&
                         (n_samples * C < (1ll << 31)) && !env_int("OFP_K1_NO_TMA", 0);
-    const int NR = B;
+    const bool pipe = plain && tma_ok && B % PU == 0 && a.T % PU == 0 && env_int("OFP_K1_PIPE", 0) && !env_int("OFP_K1_WS", 0);
+    const int NR = pipe ? B + PU : B;
     const int want = ((C + 3) / 4 * 4) % 32;
     const int bc4 = (NR * C + 3) / 4 * 4;
     a.stride_rel = bc4 + ((want - bc4 % 32) + 32) % 32;
@@ -890,7 +866,50 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     }
     { int rc = upload_tables(); if (rc != OFP_OK) return rc; }
     const int grid = (a.R + a.G - 1) / a.G;
+    // ---- warp-specialised kernel (default): needs TMA-able input and a block size divisible by 4 ----
+    if (plain && tma_ok && B % 4 == 0 && env_int("OFP_K1_WS", 0)) {
+        WsCfg w;
+        w.CH = B % 16 == 0 ? 16 : (B % 8 == 0 ? 8 : 4);
+        w.NDB = std::max(2, std::min(WS_MAX_NDB, env_int("OFP_K1_NDB", 3)));
+        w.NRS = B / w.CH + std::max(1, env_int("OFP_K1_SLACK", 1));
+        w.row = a.G * C;
+        K1Args b = a;
+        b.T = pick_tile(C, env_int("OFP_K1_WS_TILECAP", 16), 4);
+        if (b.T > 0 && w.NRS <= WS_MAX_NRS) {
+            b.TC = b.T * C;
+            b.nst = std::max(2, std::min(4, env_int("OFP_K1_STAGES", 2)));
+            const int sb = (b.G * b.TC * 4 + 127) / 128 * 128;
+            b.stage_floats = sb / 4;
+            w.off_x = WS_OFF_DATA;
+            w.off_db = w.off_x + b.nst * sb;
+            w.off_rel = (w.off_db + w.NDB * w.CH * w.row * 4 + 15) / 16 * 16;
+            const size_t smem_ws = static_cast<size_t>(w.off_rel) + static_cast<size_t>(w.NRS) * w.CH * w.row * 4;
+            if (smem_ws <= 227 * 1024 && smem_ws >= static_cast<size_t>(w.off_rel) + 3 * 512) {
+                CUtensorMap tm2;
+                const uint64_t stride1 = a.R == 1 ? static_cast<uint64_t>((n_samples * C * 4 + 15) / 16 * 16)
+                                                  : static_cast<uint64_t>(rec_stride) * 4;
+                int rc = encode_tmap_2d_f32(&tm2, x, static_cast<uint64_t>(n_samples) * C, static_cast<uint64_t>(a.R),
+                                            stride1, static_cast<uint32_t>(b.TC), static_cast<uint32_t>(b.G));
+                if (rc != OFP_OK) return rc;
+                auto kws = p.use_hp ? k1_detect_ws<true> : k1_detect_ws<false>;
+                OFP_CUDA_CHECK(cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    static_cast<int>(smem_ws)));
+                kws<<<grid, WS_THREADS, smem_ws, stream>>>(tm2, b, w);
+                OFP_CUDA_CHECK(cudaGetLastError());
+                return OFP_OK;
+            }
+        }
+    }
     const bool sym = p.use_hp && memcmp(&p.b[0], &p.b[4], 4) == 0 && memcmp(&p.b[1], &p.b[3], 4) == 0;
+    if (pipe) {
+        auto kp = p.use_hp ? (sym ? (p.manual ? k1_pipe<true, true, true> : k1_pipe<true, true, false>)
+                                  : (p.manual ? k1_pipe<true, false, true> : k1_pipe<true, false, false>))
+                           : (p.manual ? k1_pipe<false, false, true> : k1_pipe<false, false, false>);
+        OFP_CUDA_CHECK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kp<<<grid, 32, smem, stream>>>(tmap, a, NR);
+        OFP_CUDA_CHECK(cudaGetLastError());
+        return OFP_OK;
+    }
     auto kern = p.use_hp ? (tma_ok ? (sym ? k1_detect<true, true, true> : k1_detect<true, true, false>)
                                    : (sym ? k1_detect<true, false, true> : k1_detect<true, false, false>))
                          : (tma_ok ? k1_detect<false, true, false> : k1_detect<false, false, false>);
@@ -908,7 +927,7 @@ struct HostCache {
     cudaStream_t copy = nullptr, comp = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
 };
-static HostCache g_host_cache[MAX_DEVICES];  // staging buffers, streams and events live on ONE device each
+static HostCache g_host_cache;
 
 }  // namespace ofp
 
@@ -917,7 +936,7 @@ using namespace ofp;
 extern "C" {
 
 int ofp_host_release(void) {
-    HostCache &c = g_host_cache[current_device()];
+    HostCache &c = g_host_cache;
     for (int i = 0; i < 2; ++i) {
         cudaFree(c.x[i]); cudaFree(c.rel[i]);
         if (c.copied[i]) cudaEventDestroy(c.copied[i]);
@@ -1045,7 +1064,7 @@ int ofp_detect_offline_host(const ofp_detector_params *p, const float *x_host, i
     // cost more than the whole pipeline); ofp_host_release() frees them.  One call at a time.
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    HostCache &cx = g_host_cache[current_device()];
+    HostCache &cx = g_host_cache;
     ofp_detector *det = nullptr;
     auto cleanup = [&]() { ofp_detector_destroy(det); };
 #define HOST_CHECK(expr)                                                                  \

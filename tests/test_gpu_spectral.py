@@ -59,6 +59,49 @@ def test_detect_onsets_spectral_restatement():
     assert peaks.tolist() == peaks_o.tolist()
 
 
+def test_spectral_golden_reference_over_scipy_standin(golden_dir):
+    """Pin of row a6: the unmodified reference's detect_onsets_spectral run on top of an independent scipy
+    implementation of the three librosa calls (oracle/librosa_standin.py: scipy.signal.ShortTimeFFT, librosa 0.9's
+    filter-based peak_pick), and the realtime onset strength through ShortTimeFFT (tests/golden/spectral.npz).
+    Bars: envelope 2e-4 of its maximum (float32 FFT both sides), identical peak indices."""
+    import hashlib
+
+    from onset_fingerprinting_b200 import spectral
+    from oracle.make_golden import SPECTRAL
+
+    g = np.load(golden_dir / "spectral.npz")
+    x, _ = synth.drum_recording(**SPECTRAL)
+    assert hashlib.sha1(np.ascontiguousarray(x).tobytes()).hexdigest() == str(g["x_sha"])
+    mono = np.ascontiguousarray(x.mean(1), np.float32)
+    peaks, oe = spectral.detect_onsets_spectral(mono, return_oe=True)
+    assert oe.shape == g["oe"].shape
+    assert np.abs(oe - g["oe"]).max() <= 2e-4 * np.abs(g["oe"]).max()
+    assert peaks.tolist() == g["peaks"].tolist() and len(peaks) == 9
+    flux = spectral.onset_strength(x, 2048, 128)
+    assert flux.shape == g["flux2048"].shape
+    assert np.abs(flux - g["flux2048"]).max() <= 3e-3 + 2e-3 * np.abs(g["flux2048"]).max()
+
+
+def test_peak_pick_kernel_vs_filter_formulation():
+    """ofp_peak_pick against librosa 0.9's filter formulation (oracle/librosa_standin.py) on random envelopes."""
+    from onset_fingerprinting_b200 import spectral
+    from oracle import librosa_standin as ls
+
+    rng = np.random.default_rng(4)
+    for trial in range(40):
+        n = int(rng.integers(5, 900))
+        x = np.abs(rng.standard_normal(n)).astype(np.float32)
+        if trial % 3 == 0:
+            x[rng.integers(0, n, n // 4)] = 0.0
+        if trial % 4 == 0:
+            x = (np.round(x * 4) / 4).astype(np.float32)
+        a = dict(pre_max=int(rng.integers(1, 40)), post_max=int(rng.integers(1, 40)), pre_avg=int(rng.integers(1, 60)),
+                 post_avg=int(rng.integers(1, 60)), delta=float(rng.uniform(0, 0.5)), wait=int(rng.integers(0, 30)))
+        pk, cnt = spectral.peak_pick_batch(torch.from_numpy(x[None]).cuda(), a["pre_max"], a["post_max"], a["pre_avg"],
+                                           a["post_avg"], a["delta"], a["wait"], cap=n + 1)
+        assert pk[0, : int(cnt[0])].cpu().tolist() == ls.peak_pick(x, **a).tolist(), (trial, a)
+
+
 def test_flux_properties_large_batch():
     """BASELINE-size properties the numpy restatement is too slow to check: per-recording independence of the
     batch, determinism, hop-shift equivariance (delaying a recording by k hops delays its flux by k frames

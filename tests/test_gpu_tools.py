@@ -187,3 +187,68 @@ def test_streaming_locate_with_ring_refinement(golden_dir):
     assert np.array_equal(np.isfinite(rows[:, 3]), np.isfinite(g[:, 3]))
     ok = np.isfinite(g[:, 3])
     assert np.allclose(rows[ok, 3:], g[ok, 3:], rtol=1e-9, atol=1e-9)
+
+
+def test_window_argmax_dataset_builder():
+    """notebooks/refresh.org:262-279: og[i] + argmax(audio[og[i] : og[i] + tol, i]) per hit and channel."""
+    from onset_fingerprinting_b200 import detection as det
+
+    rng = np.random.default_rng(8)
+    R, N, Cn, H = 3, 5000, 4, 40
+    x = rng.standard_normal((R, N, Cn)).astype(np.float32)
+    x[:, 100:110, 1] = 7.0  # a plateau: the FIRST maximum wins
+    rec = rng.integers(0, R, H).astype(np.int32)
+    on = rng.integers(0, N - 10, (H, Cn)).astype(np.int32)
+    on[0] = [95, 95, 95, 4995]
+    on[1, 2] = -1
+    got = det.max_onsets_batch(x, torch.from_numpy(rec), torch.from_numpy(on), 300).cpu().numpy()
+    for h in range(H):
+        for c in range(Cn):
+            if on[h, c] < 0:
+                assert got[h, c] == -1
+            else:
+                assert got[h, c] == on[h, c] + int(np.argmax(x[rec[h], on[h, c]:on[h, c] + 300, c])), (h, c)
+
+
+def test_tempogram_vs_fft_formula():
+    """RecAnalysis.tempogram (recording.py:313-327): irfft(|rfft(w * oe[-W:], n=2W-1)|^2)[:W] / (max + 1e-10); the
+    kernel evaluates the same autocorrelation directly."""
+    from onset_fingerprinting_b200 import spectral
+    from oracle import spectral_np
+
+    rng = np.random.default_rng(9)
+    W, F = 384, 900
+    oe = np.abs(rng.standard_normal((2, F))).astype(np.float32)
+    oe[:, ::40] += 3.0
+    tg = spectral.tempogram_batch(oe, W, first_frame=10, every=37).cpu().numpy()
+    win = spectral.hann(W, periodic=False)
+    frames = list(range(10, F, 37))
+    assert tg.shape == (2, len(frames), W)
+    for r in range(2):
+        for k, j in enumerate(frames):
+            last = np.zeros(W, np.float32)
+            lo = max(0, j - W + 1)
+            last[W - (j + 1 - lo):] = oe[r, lo:j + 1]
+            want = spectral_np.tempogram_frame(last, win)
+            assert np.abs(tg[r, k] - want).max() <= 2e-5, (r, j)
+            assert abs(tg[r, k].max() - 1.0) < 1e-6
+
+
+def test_paired_xcorr_vs_torch():
+    """model.paired_xcorr (model.py:12-45) against the reference's own formulation (grouped F.conv1d) in torch."""
+    import torch.nn.functional as F
+
+    from onset_fingerprinting_b200 import model
+
+    torch.manual_seed(3)
+    B, Cc, K, V = 5, 3, 4, 64
+    x = torch.randn(B, Cc * K, V)
+    got = model.paired_xcorr(x.cuda(), Cc, K).cpu()
+    xv = x.view(B, Cc, K, V)
+    a = xv[:, :-1].reshape(B, (Cc - 1) * K, V)
+    b = xv[:, 1:].reshape(B, (Cc - 1) * K, V)
+    M = B * (Cc - 1) * K
+    a_pad = F.pad(a, (V - 1, V - 1)).view(1, M, 3 * V - 2)
+    want = F.conv1d(a_pad, b.reshape(M, 1, V), groups=M).view(B, Cc - 1, K, 2 * V - 1).mean(dim=2)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max())

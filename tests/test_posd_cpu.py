@@ -86,3 +86,21 @@ def test_spec_example_session(tmp_path):
     audio, sr, onsets, loc, meta = posd.read_session(tmp_path, "session1")
     assert sr == 48000 and audio.shape == (100, 3) and onsets.tolist() == [h["onset_start"] for h in example["hits"]]
     assert np.isnan(loc).all() and meta["channels"]["OP"]["location"] == [0.95, 30]
+
+
+def test_combined_json_writer(tmp_path):
+    """notebooks/refresh.org:243-287: combined.wav + combined.json = {"hits": [{"i", "zone": "center", "onset_start"}]}."""
+    import json
+
+    from onset_fingerprinting_b200 import posd
+
+    rng = np.random.default_rng(0)
+    audio = rng.standard_normal((4000, 3)).astype(np.float32) * 0.1
+    onsets = np.array([[100, 120, 90], [2000, 2010, 2020]])
+    d = posd.write_combined(tmp_path / "Setup 1", audio, 96000, onsets)
+    want = {"hits": [{"i": i, "zone": "center", "onset_start": o.tolist()} for i, o in enumerate(onsets)]}
+    assert d == want
+    assert json.load(open(tmp_path / "Setup 1" / "combined.json")) == want
+    back, sr = posd.read_wav(tmp_path / "Setup 1" / "combined.wav")
+    assert sr == 96000 and np.array_equal(back, audio)
+    assert posd.parse_hits(d["hits"])["onset_start"].tolist() == onsets.tolist()
