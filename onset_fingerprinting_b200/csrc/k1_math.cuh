@@ -58,57 +58,25 @@ OFP_HD bool near_f32_midpoint(double d, uint32_t win) {
 // Polynomial / scaling constants.  The kernel keeps one copy in registers for its whole lifetime
 // (a warp-per-CTA kernel has registers to spare) instead of re-materialising 64-bit immediates.
 struct MathConst {
-    double a1, a2, a3, a4, a5, log10_2;      // log10(1+r)
-    double e1, e2, e3, e4, e5, log2_10;      // 2^r
-    double shift;                            // 1.5 * 2^52
+    double a1, a2, a3, a4, a5;    // log10(1+r) = r (a1 + a2 r + ... + a5 r^4), |r| <= 2^-8
+    double log10_2s, kmagic;      // log10(2) * 2^-23 and 2^52 + 2^31 (exponent word -> double without I2F)
+    double e1, e2, e3, e4;        // 2^r = 1 + r (e1 + e2 r + e3 r^2 + e4 r^3), |r| <= 2^-8
+    double log2_10, shift;        // shift = 1.5 * 2^(52 - OFP_EXP_N): kd0 = q log2(10) + shift has spacing 2^-OFP_EXP_N
 };
 OFP_HD MathConst math_const() {
     MathConst c;
     c.a1 = OFP_LOG_A1; c.a2 = OFP_LOG_A2; c.a3 = OFP_LOG_A3; c.a4 = OFP_LOG_A4; c.a5 = OFP_LOG_A5;
-    c.log10_2 = OFP_LOG10_2;
-    c.e1 = OFP_EXP_E1; c.e2 = OFP_EXP_E2; c.e3 = OFP_EXP_E3; c.e4 = OFP_EXP_E4; c.e5 = OFP_EXP_E5;
+    c.log10_2s = OFP_LOG10_2 * 0x1p-23;
+    c.kmagic = 0x1p52 + 0x1p31;
+    c.e1 = OFP_EXP_E1; c.e2 = OFP_EXP_E2; c.e3 = OFP_EXP_E3; c.e4 = OFP_EXP_E4;
     c.log2_10 = OFP_LOG2_10;
-    c.shift = 0x1.8p52;
+    c.shift = 0x1.8p52 / static_cast<double>(1 << OFP_EXP_N);
     return c;
 }
 
-// log10 of a positive normal float32 (bit pattern ix), double result with relative error < 2^-41.
-// tab: {invc, logc} pairs (OFP_LOGTAB_H) in whatever memory the caller staged them.
-OFP_HD double log10_core(uint32_t ix, const double *tab, const MathConst &mc) {
-    const uint32_t tmp = ix - OFP_LOG_OFF;
-    const int32_t k = static_cast<int32_t>(tmp) >> 23;
-    const uint32_t i = (tmp >> (23 - OFP_LOG_N)) & ((1u << OFP_LOG_N) - 1u);
-    const uint32_t iz = ix - (tmp & 0xff800000u);  // z in [OFF, 2*OFF)
-    // float32 bits -> double bits (z is normal): exponent rebias 127 -> 1023
-    const uint64_t zb = (static_cast<uint64_t>((iz >> 3) + 0x38000000u) << 32) | (static_cast<uint64_t>(iz) << 61 >> 32);
-    const double z = bits2d(zb);
-    const double invc = tab[2 * i], logc = tab[2 * i + 1];
-    const double r = fma_d(z, invc, -1.0);
-    const double r2 = r * r;
-    // r * (A1 + A2 r + A3 r^2 + A4 r^3 + A5 r^4), Estrin
-    const double p01 = fma_d(r, mc.a2, mc.a1);
-    const double p23 = fma_d(r, mc.a4, mc.a3);
-    const double p = fma_d(r2, fma_d(r2, mc.a5, p23), p01);
-    const double base = fma_d(static_cast<double>(k), mc.log10_2, logc);
-    return fma_d(r, p, base);
-}
-
-// 10**q for |q| < 30, double result with relative error < 2^-46.  tab: OFP_EXPTAB_H (2^(j/32)).
-OFP_HD double exp10_core(float q, const double *tab, const MathConst &mc) {
-    const double t = static_cast<double>(q) * mc.log2_10;
-    const double shift = mc.shift;  // round-to-nearest-integer magic number
-    const double kd0 = fma_d(t, 32.0, shift);
-    const int32_t ki = static_cast<int32_t>(static_cast<uint32_t>(d2bits(kd0)));
-    const double kd = kd0 - shift;
-    const double r = fma_d(kd, -0.03125, t);  // |r| <= 1/64
-    const double r2 = r * r;
-    const double p01 = fma_d(r, mc.e2, mc.e1);
-    const double p23 = fma_d(r, mc.e4, mc.e3);
-    const double p = fma_d(r2, fma_d(r2, mc.e5, p23), p01);
-    const double s = tab[ki & 31];
-    const double y = fma_d(s * r, p, s);
-    // scale by 2^(ki >> 5): add to the exponent field (results here are far from over/underflow)
-    return bits2d(d2bits(y) + (static_cast<uint64_t>(static_cast<int64_t>(ki >> 5)) << 52));
-}
+// Rounding windows of the fast paths, in units of 2^-52 relative (double ulps of the result):
+// log10: |error| < 2^-41 (2^11 ulps), 10**x: |error| < 2^-47.5 (2^4.5 ulps); windows leave a factor >= 4.
+constexpr uint32_t OFP_LOG_WIN = 1u << 13;
+constexpr uint32_t OFP_EXP_WIN = 1u << 8;
 
 }  // namespace ofp

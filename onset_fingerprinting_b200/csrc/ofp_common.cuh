@@ -74,6 +74,19 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// Bulk copy shared -> global (one contiguous run, 16-byte aligned on both sides, size a multiple of 16) in the
+// issuing thread's bulk async-group; bulk_wait_read<N>() returns once all but the N newest groups have finished
+// READING their shared-memory source (the buffer may then be overwritten).
+__device__ __forceinline__ void bulk_store(void *dst_global, const void *src_shared, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst_global)),
+                 "r"(smem_u32(src_shared)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

@@ -32,6 +32,21 @@
 #ifndef OFP_K1_LADDER
 #define OFP_K1_LADDER 9
 #endif
+#ifndef OFP_K1_SPARSE  // short-cut (v) of chunk_fast, switchable for A/B builds
+#define OFP_K1_SPARSE 1
+#endif
+#ifndef OFP_K1_ICVT  // 10**x: double(q) and the float32 rounding of the result by integer operations instead of F2F
+#define OFP_K1_ICVT 0  // measured slower (79.8 vs 76.7 ms): the XU conversions cost one issue slot each, the integer forms 4-5
+#endif
+#ifndef OFP_K1_KMAGIC  // log10: exponent -> double by a magic-constant subtraction instead of I2F
+#define OFP_K1_KMAGIC 1
+#endif
+#ifndef OFP_K1_FOLMAX  // followers: coef * d as max(att * d, rel * d) instead of a select
+#define OFP_K1_FOLMAX 1
+#endif
+#ifndef OFP_K1_MNVOTE  // short-cut (vi)
+#define OFP_K1_MNVOTE 1
+#endif
 
 #include <algorithm>
 #include <cstdlib>
@@ -47,7 +62,7 @@ struct ofp_detector {
 namespace ofp {
 
 // shared memory header: 128 B of mbarriers, then the log10 / 10**x tables
-constexpr int K1_SMEM_HEADER = 128 + (2 << OFP_LOG_N) * 8 + 32 * 8;
+constexpr int K1_SMEM_HEADER = 128 + (2 << OFP_LOG_N) * 8 + (1 << OFP_EXP_N) * 8;
 
 struct DetState {
     float *z0, *z1, *z2, *z3, *yf, *ys, *mn, *mx, *prev;
@@ -79,6 +94,7 @@ struct K1Args {
     int32_t cap;
     int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
     int32_t floor_skip;  // OFP_K1_FLOOR_SKIP=0 disables the below-floor short-cut (A/B runs)
+    int32_t fast_ok;     // follower coefficients in (0, 1]: the straight-line chunk's short-cuts are proven for those
     int32_t cnt_in;      // continue: the per-recording onset counts in on_cnt are the starting fill levels
     int64_t blk0;        // continue: global index of the first block of this call (x / rel start there)
 };
@@ -88,6 +104,7 @@ struct K1Args {
 struct Coef {
     float b0, b1, b2, b3, b4, a1, a2, a3, a4;
     float fa, fr, sa, sr;
+    float fA, fR, fS, sA, sR, sS;  // followers of the straight-line chunk: (s att, s rel, s), s = att >= rel ? 1 : -1
     float floor_db, ceil_amp, vfloor;
     float amin, amax, iamin, iamax, minmin;
 };
@@ -96,6 +113,8 @@ __device__ __forceinline__ Coef load_coef(const K1Args &a) {
     k.b0 = a.p.b[0]; k.b1 = a.p.b[1]; k.b2 = a.p.b[2]; k.b3 = a.p.b[3]; k.b4 = a.p.b[4];
     k.a1 = a.p.a[1]; k.a2 = a.p.a[2]; k.a3 = a.p.a[3]; k.a4 = a.p.a[4];
     k.fa = a.p.fast_att; k.fr = a.p.fast_rel; k.sa = a.p.slow_att; k.sr = a.p.slow_rel;
+    k.fS = k.fa >= k.fr ? 1.0f : -1.0f; k.fA = k.fS * k.fa; k.fR = k.fS * k.fr;
+    k.sS = k.sa >= k.sr ? 1.0f : -1.0f; k.sA = k.sS * k.sa; k.sR = k.sS * k.sr;
     k.floor_db = a.p.floor_db; k.ceil_amp = -a.p.floor_db;
     // |h + 1e-10| below vfloor => 20*log10(.) rounds below the floor => the clipped dB value IS the floor
     // (4e-6 relative margin = 4.5 float32 ulps of the floor in dB, DESIGN.md "K1 arithmetic" (iv))
@@ -176,84 +195,50 @@ __device__ __forceinline__ float hp_step(Lane &L, const Coef &k, float x) {
 __device__ __forceinline__ float db_of(double ld, float floor_db) {
     return fmaxf(__fmul_rn(20.0f, __double2float_rn(ld)), floor_db);
 }
-// Fast path of k1_math.cuh:log10_core with the table in shared memory; `redo` is set when the value
-// must be recomputed by slow_log10 (special input, or too close to a float32 rounding boundary).
-__device__ __forceinline__ float to_db_fast(float h, float floor_db, uint32_t logtab, const MathConst &mc,
-                                            float &v_out, bool &redo) {
-    const float v = fabsf(__fadd_rn(h, 1e-10f));
-    const uint32_t ix = __float_as_uint(v);
-    const uint32_t tmp = ix - OFP_LOG_OFF;
-    const int32_t kexp = static_cast<int32_t>(tmp) >> 23;
-    const uint32_t ti = (tmp >> (23 - OFP_LOG_N - 4)) & (((1u << OFP_LOG_N) - 1u) << 4);  // byte offset
-    const uint32_t iz = ix - (tmp & 0xff800000u);
-    const double z = __hiloint2double(static_cast<int>((iz >> 3) + 0x38000000u), static_cast<int>(iz << 29));
-    double invc, logc;
-    lds_2f64(logtab + ti, invc, logc);
-    const double r = __fma_rn(z, invc, -1.0);
-    const double r2 = __dmul_rn(r, r);
-    const double p01 = __fma_rn(r, mc.a2, mc.a1);
-    const double p23 = __fma_rn(r, mc.a4, mc.a3);
-    const double pp = __fma_rn(r2, __fma_rn(r2, mc.a5, p23), p01);
-    const double base = __fma_rn(static_cast<double>(kexp), mc.log10_2, logc);
-    const double ld = __fma_rn(r, pp, base);
-    redo = ((ix - 0x00800000u) >= 0x7f000000u) | near_f32_midpoint(ld, 1u << 13);
-    v_out = v;
-    return db_of(ld, floor_db);
-}
-
 // detection.py:753-754: clip(10**(r/20) - 1e-10, 0, -floor) in float32; 10**x correctly rounded.
 __device__ __forceinline__ float amp_of(double ad, float ceil_amp) {
     const float amp = __fsub_rn(__double2float_rn(ad), 1e-10f);
     return fminf(fmaxf(amp, 0.0f), ceil_amp);
 }
-__device__ __forceinline__ float to_amp_fast(float r, float ceil_amp, uint32_t exptab, const MathConst &mc,
-                                             float &q_out, bool &redo) {
-    // r / 20 correctly rounded without a division (exact: host harness over 4e8 values)
-    const float q0 = __fmul_rn(r, 0.05f);
-    const float q = __fmaf_rn(__fmaf_rn(-20.0f, q0, r), 0.05f, q0);
-    const double t = __dmul_rn(static_cast<double>(q), mc.log2_10);
-    const double kd0 = __fma_rn(t, 32.0, mc.shift);
-    const int32_t ki = __double2loint(kd0);
-    const double kd = __dsub_rn(kd0, mc.shift);
-    const double rr = __fma_rn(kd, -0.03125, t);
-    const double r2 = __dmul_rn(rr, rr);
-    const double p01 = __fma_rn(rr, mc.e2, mc.e1);
-    const double p23 = __fma_rn(rr, mc.e4, mc.e3);
-    const double pp = __fma_rn(r2, __fma_rn(r2, mc.e5, p23), p01);
-    const double sc = lds_f64(exptab + ((ki & 31) << 3));
-    const double y = __fma_rn(__dmul_rn(sc, rr), pp, sc);
-    const double ad = __hiloint2double(__double2hiint(y) + ((ki >> 5) << 20), __double2loint(y));
-    redo = !(fabsf(q) < 30.0f) | near_f32_midpoint(ad, 1u << 8);
-    q_out = q;
-    return amp_of(ad, ceil_amp);
-}
 
-// Step-major ("vertical") forms of to_db_fast / to_amp_fast for U independent samples: every
-// elementary operation is issued for all U samples before the next one, so the instruction stream
-// handed to ptxas is already interleaved.  (Written sample-major, ptxas keeps the U dependency
-// chains mostly back to back and the warp stalls on every dependent FP64 op -- ncu, profiles/.)
-template <int U, bool MASK = true>
-__device__ __forceinline__ void to_db_vec(const float (&h)[U], float floor_db, uint32_t logtab, const MathConst &mc,
-                                          float (&db)[U], float (&v_out)[U], uint32_t &redo_mask, int bit0) {
-    uint32_t ix[U], tmp[U], iz[U];
-    int32_t kexp[U];
-    double z[U], invc[U], logc[U], r[U], r2[U], p01[U], p23[U], pp[U], base[U], ld[U];
+// Issue costs on B200 (profiles/r02_ubench_op_rates.txt, SMSP cycles per warp instruction): FP32 1, LOP3 / IADD3 /
+// FMNMX 1, SHF / IMAD / FSEL / SEL / ISETP / FMNMX3 2, FP64 2, F2F / I2F conversions 8.5 -- and no dual issue: the
+// costs add up.  The two pointwise stages below are therefore written to avoid conversions (integer constructions
+// of the doubles, integer rounding of the result), per-sample predicate logic (the rare-case tests are ACCUMULATED
+// as unsigned min / max words and examined once per chunk) and selects.
+
+// log10 of U samples, step-major (every elementary operation is issued for all U samples before the next one, so
+// the instruction stream handed to ptxas is already interleaved).  v = |h + 1e-10|.  Table-driven double
+// evaluation, relative error < 2^-41.  Rare cases are accumulated, not branched on:
+//   spec = max (bits(v) - 0x00800000): >= 0x7f000000 for zero / denormal / inf / nan inputs;
+//   mid  = min distance word of the double result to a float32 rounding boundary: < 2 * OFP_LOG_WIN when the
+//          double cannot be trusted to round correctly (the caller then uses slow_log10).
+template <int U>
+__device__ __forceinline__ void to_db_vec(const float (&v)[U], float floor_db, uint32_t logtab, const MathConst &mc,
+                                          float (&db)[U], uint32_t &spec, uint32_t &mid) {
+    uint32_t ix[U], tmp[U], kw[U], iz[U];
+    double z[U], kd[U], invc[U], logc[U], r[U], r2[U], p01[U], p23[U], pp[U], base[U], ld[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) { v_out[u] = fabsf(__fadd_rn(h[u], 1e-10f)); ix[u] = __float_as_uint(v_out[u]); }
-#pragma unroll
-    for (int u = 0; u < U; ++u) tmp[u] = ix[u] - OFP_LOG_OFF;
+    for (int u = 0; u < U; ++u) { ix[u] = __float_as_uint(v[u]); tmp[u] = ix[u] - OFP_LOG_OFF; }
 #pragma unroll
     for (int u = 0; u < U; ++u)
         lds_2f64(logtab + ((tmp[u] >> (23 - OFP_LOG_N - 4)) & (((1u << OFP_LOG_N) - 1u) << 4)), invc[u], logc[u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) { kexp[u] = static_cast<int32_t>(tmp[u]) >> 23; iz[u] = ix[u] - (tmp[u] & 0xff800000u); }
+    for (int u = 0; u < U; ++u) { kw[u] = tmp[u] & 0xff800000u; iz[u] = ix[u] - kw[u]; }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u)  // z in [OFF, 2 OFF) as a double: exponent rebias 127 -> 1023
         z[u] = __hiloint2double(static_cast<int>((iz[u] >> 3) + 0x38000000u), static_cast<int>(iz[u] << 29));
+#pragma unroll
+    for (int u = 0; u < U; ++u)  // exponent * 2^23 as a double: 2^52 + (kw ^ 2^31) minus the magic constant, exact
+#if OFP_K1_KMAGIC
+        kd[u] = __dsub_rn(__hiloint2double(0x43300000, static_cast<int>(kw[u] ^ 0x80000000u)), mc.kmagic);
+#else
+        kd[u] = static_cast<double>(static_cast<int32_t>(kw[u]));
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u) r[u] = __fma_rn(z[u], invc[u], -1.0);
 #pragma unroll
-    for (int u = 0; u < U; ++u) base[u] = __fma_rn(static_cast<double>(kexp[u]), mc.log10_2, logc[u]);
+    for (int u = 0; u < U; ++u) base[u] = __fma_rn(kd[u], mc.log10_2s, logc[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) r2[u] = __dmul_rn(r[u], r[u]);
 #pragma unroll
@@ -268,56 +253,98 @@ __device__ __forceinline__ void to_db_vec(const float (&h)[U], float floor_db, u
     for (int u = 0; u < U; ++u) ld[u] = __fma_rn(r[u], pp[u], base[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const bool redo = ((ix[u] - 0x00800000u) >= 0x7f000000u) | near_f32_midpoint(ld[u], 1u << 13);
-        if (MASK) redo_mask |= (redo ? 1u : 0u) << (bit0 + u);
-        else redo_mask |= redo;  // only "any sample flagged" is needed
+        spec = max(spec, ix[u] - 0x00800000u);
+        mid = min(mid, (static_cast<uint32_t>(__double2loint(ld[u])) & 0x1fffffffu) - (0x10000000u - OFP_LOG_WIN));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) db[u] = db_of(ld[u], floor_db);
 }
+__device__ __forceinline__ bool db_flagged(uint32_t spec, uint32_t mid) {
+    return (spec >= 0x7f000000u) | (mid < 2u * OFP_LOG_WIN);
+}
 
-template <int U, bool MASK = true>
+// 10**(dr/20) - 1e-10 clipped to the ceiling for U samples, step-major.  q = dr / 20 correctly rounded without a
+// division (exact: host harness over 4e8 values); double(q) by integer operations (zero / denormal q
+// become 2^-127-sized doubles: harmless); k = rint(q log2(10) 2^N) from the low word of q log2(10) + 1.5 2^(52-N),
+// reduced argument by one FMA against that same sum, 2^(j / 2^N) from the table, degree-4 polynomial, relative
+// error < 2^-47.5; the result is rounded to float32 by integer operations (add half a float32 ulp to the low word,
+// carry, funnel shift -- equal to round-to-nearest-even except on exact ties, which the window below excludes)
+// and scaled by 2^(k >> N) in the float32 exponent field.  Accumulated rare cases:
+//   qmax = max |q|: the fast path needs |q| < 9.5 (10**q - 1e-10 > 0, no overflow of the exponent arithmetic);
+//   mid  = min distance word to a float32 rounding boundary: < 2 * OFP_EXP_WIN => slow_exp10.
+template <int U>
 __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp, uint32_t exptab, const MathConst &mc,
-                                           float (&amp)[U], uint32_t &redo_mask, int bit0) {
-    float q0[U], q[U];
-    double t[U], kd0[U], kd[U], rr[U], r2[U], p01[U], p23[U], pp[U], sc[U], y[U], ad[U];
-    int32_t ki[U];
+                                           float (&amp)[U], float (&q)[U], float &qmax, uint32_t &mid) {
+    float q0[U];
+    uint32_t qb[U], ki[U], lo2[U], hi2[U], fb[U];
+    double qd[U], kd0[U], kq[U], rr[U], sc[U], pp[U], s1[U], y[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) q0[u] = __fmul_rn(dr[u], 0.05f);
 #pragma unroll
     for (int u = 0; u < U; ++u) q[u] = __fmaf_rn(__fmaf_rn(-20.0f, q0[u], dr[u]), 0.05f, q0[u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) t[u] = __dmul_rn(static_cast<double>(q[u]), mc.log2_10);
-#pragma unroll
-    for (int u = 0; u < U; ++u) kd0[u] = __fma_rn(t[u], 32.0, mc.shift);
-#pragma unroll
-    for (int u = 0; u < U; ++u) { ki[u] = __double2loint(kd0[u]); kd[u] = __dsub_rn(kd0[u], mc.shift); }
-#pragma unroll
-    for (int u = 0; u < U; ++u) sc[u] = lds_f64(exptab + ((ki[u] & 31) << 3));
-#pragma unroll
-    for (int u = 0; u < U; ++u) rr[u] = __fma_rn(kd[u], -0.03125, t[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) r2[u] = __dmul_rn(rr[u], rr[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) p01[u] = __fma_rn(rr[u], mc.e2, mc.e1);
-#pragma unroll
-    for (int u = 0; u < U; ++u) p23[u] = __fma_rn(rr[u], mc.e4, mc.e3);
-#pragma unroll
-    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(r2[u], mc.e5, p23[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(r2[u], pp[u], p01[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) y[u] = __fma_rn(__dmul_rn(sc[u], rr[u]), pp[u], sc[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) ad[u] = __hiloint2double(__double2hiint(y[u]) + ((ki[u] >> 5) << 20), __double2loint(y[u]));
-#pragma unroll
     for (int u = 0; u < U; ++u) {
-        const bool redo = !(fabsf(q[u]) < 30.0f) | near_f32_midpoint(ad[u], 1u << 8);
-        if (MASK) redo_mask |= (redo ? 1u : 0u) << (bit0 + u);
-        else redo_mask |= redo;
+        qb[u] = __float_as_uint(q[u]);
+#if OFP_K1_ICVT
+        const uint32_t hi = (((qb[u] & 0x7fffffffu) >> 3) + 0x38000000u) | (qb[u] & 0x80000000u);
+        qd[u] = __hiloint2double(static_cast<int>(hi), static_cast<int>(qb[u] << 29));
+#else
+        qd[u] = static_cast<double>(q[u]);
+#endif
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) amp[u] = amp_of(ad[u], ceil_amp);
+    for (int u = 0; u < U; ++u) kd0[u] = __fma_rn(qd[u], mc.log2_10, mc.shift);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { ki[u] = static_cast<uint32_t>(__double2loint(kd0[u])); kq[u] = __dsub_rn(kd0[u], mc.shift); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) sc[u] = lds_f64(exptab + ((ki[u] & ((1u << OFP_EXP_N) - 1u)) << 3));
+#pragma unroll
+    for (int u = 0; u < U; ++u) rr[u] = __fma_rn(qd[u], mc.log2_10, -kq[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(rr[u], mc.e4, mc.e3);
+#pragma unroll
+    for (int u = 0; u < U; ++u) s1[u] = __dmul_rn(sc[u], rr[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(rr[u], pp[u], mc.e2);
+#pragma unroll
+    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(rr[u], pp[u], mc.e1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) y[u] = __fma_rn(s1[u], pp[u], sc[u]);  // in (0.99, 2.01)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t yl = static_cast<uint32_t>(__double2loint(y[u])), yh = static_cast<uint32_t>(__double2hiint(y[u]));
+        // + 2^28 in the low word (half a float32 ulp), carry into the high word together with the exponent
+        // rebias 1023 -> 127 (0x08000000 << 3 == 0x40000000 == -896 << 23 mod 2^32)
+#if OFP_K1_ICVT
+        asm("add.cc.u32 %0, %2, 0x10000000;\n\taddc.u32 %1, %3, 0x08000000;" : "=r"(lo2[u]), "=r"(hi2[u]) : "r"(yl), "r"(yh));
+#else
+        lo2[u] = yl; hi2[u] = yh;
+#endif
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#if OFP_K1_ICVT
+        fb[u] = __funnelshift_l(lo2[u], hi2[u], 3) + ((ki[u] & ~((1u << OFP_EXP_N) - 1u)) << (23 - OFP_EXP_N));
+#else
+        fb[u] = __float_as_uint(__double2float_rn(y[u])) + ((ki[u] & ~((1u << OFP_EXP_N) - 1u)) << (23 - OFP_EXP_N));
+#endif
+#if OFP_K1_ICVT
+        mid = min(mid, (lo2[u] + OFP_EXP_WIN) & 0x1fffffffu);
+#else
+        mid = min(mid, (static_cast<uint32_t>(__double2loint(y[u])) + (0x10000000u + OFP_EXP_WIN)) & 0x1fffffffu);
+#endif
+        qmax = fmaxf(qmax, fabsf(q[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) amp[u] = fminf(__fsub_rn(__uint_as_float(fb[u]), 1e-10f), ceil_amp);
+}
+__device__ __forceinline__ bool amp_flagged(float qmax, uint32_t mid) {
+    return !(qmax < 9.5f) | (mid < 2u * OFP_EXP_WIN);
+}
+
+// The previous block's bulk copy (block_end) must have read the block buffer before it is overwritten.
+__device__ __forceinline__ void wait_rel(bool &rel_pending) {
+    if (rel_pending) { bulk_wait_read<0>(); __syncwarp(); rel_pending = false; }
 }
 
 // envelope_follower.c:38-52
@@ -328,140 +355,175 @@ __device__ __forceinline__ void minmax_step(Lane &L, const Coef &k, float r) {
     L.mx = r > L.mx ? r : nx;
 }
 
-// U consecutive samples of one lane, stage by stage so that the pointwise stages (dB, 10**x) of the
-// U samples are independent instruction streams between the short sequential recurrences.  The rare
-// slow paths are taken after a warp vote, outside the straight-line code.
-//   xs: shared address of the lane's first input sample, rs: of its first rel slot; step = 4*C bytes.
-template <bool USE_HP, int U>
-__device__ __forceinline__ void chunk(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
-                                      bool do_minmax, bool store, uint32_t logtab, uint32_t exptab,
-                                      const MathConst &mc, uint32_t rstep = 0) {
-    float h[U], db[U], dr[U], amp[U], aux[U];
-    bool redo[U], any = false;
-    if (rstep == 0) rstep = step;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float x = lds_f32(xs + u * step);
-        h[u] = USE_HP ? hp_step(L, k, x) : x;
+// ONE sample of one lane, exact in every case (branches, slow paths after a warp vote): the reference semantics
+// the straight-line chunk below falls back to, and the path of block tails.
+//   xs: shared address of the lane's input sample, rs: of its rel slot.
+template <bool USE_HP>
+__device__ __forceinline__ void sample_exact(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, bool do_minmax,
+                                             bool store, uint32_t logtab, uint32_t exptab, const MathConst &mc,
+                                             bool &rel_pending) {
+    const float x = lds_f32(xs);
+    const float h = USE_HP ? hp_step(L, k, x) : x;
+    float v[1] = {fabsf(__fadd_rn(h, 1e-10f))}, db[1], dr[1], amp[1], q[1];
+    uint32_t spec = 0, mid = 0xffffffffu;
+    to_db_vec<1>(v, k.floor_db, logtab, mc, db, spec, mid);
+    const bool redo_db = db_flagged(spec, mid);
+    if (__any_sync(0xffffffffu, redo_db)) {
+        if (redo_db) db[0] = db_of(slow_log10(v[0]), k.floor_db);
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        db[u] = to_db_fast(h[u], k.floor_db, logtab, mc, aux[u], redo[u]);
-        any |= redo[u];
+    // detection.py:751 (envelope_follower.c:6-25 twice)
+    L.yf = ar_step(L.yf, db[0], k.fa, k.fr);
+    L.ys = ar_step(L.ys, db[0], k.sa, k.sr);
+    dr[0] = __fsub_rn(L.yf, L.ys);
+    float qmax = 0.0f;
+    mid = 0xffffffffu;
+    to_amp_vec<1>(dr, k.ceil_amp, exptab, mc, amp, q, qmax, mid);
+    const bool redo_amp = amp_flagged(qmax, mid);
+    if (__any_sync(0xffffffffu, redo_amp)) {
+        if (redo_amp) {
+            const float qq = fabsf(q[0]) < 30.0f ? q[0] : __fdiv_rn(dr[0], 20.0f);
+            amp[0] = amp_of(slow_exp10(qq), k.ceil_amp);
+        }
     }
-    if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (redo[u]) db[u] = db_of(slow_log10(aux[u]), k.floor_db);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {  // detection.py:751 (envelope_follower.c:6-25 twice)
-        L.yf = ar_step(L.yf, db[u], k.fa, k.fr);
-        L.ys = ar_step(L.ys, db[u], k.sa, k.sr);
-        dr[u] = __fsub_rn(L.yf, L.ys);
-    }
-    any = false;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        amp[u] = to_amp_fast(dr[u], k.ceil_amp, exptab, mc, aux[u], redo[u]);
-        any |= redo[u];
-    }
-    if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (redo[u]) {
-                const float q = fabsf(aux[u]) < 30.0f ? aux[u] : __fdiv_rn(dr[u], 20.0f);
-                amp[u] = amp_of(slow_exp10(q), k.ceil_amp);
-            }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        if (do_minmax) minmax_step(L, k, amp[u]);
-        L.bmax = fmaxf(L.bmax, amp[u]);
-        L.bmin = fminf(L.bmin, amp[u]);
-        if (store) sts_f32(rs + u * rstep, amp[u]);
-    }
+    if (do_minmax) minmax_step(L, k, amp[0]);
+    L.bmax = fmaxf(L.bmax, amp[0]);
+    L.bmin = fminf(L.bmin, amp[0]);
+    wait_rel(rel_pending);
+    if (store) sts_f32(rs, amp[0]);
 }
 
-// Straight-line, branch-free form of chunk<> for U samples: one large basic block that ptxas can
-// software-pipeline (needs __launch_bounds__(32, 1): with a higher occupancy target ptxas keeps
-// the dependency chains back to back to save registers).  Every rare case is only FLAGGED:
-//   - dB / 10**x results that need the exact slow path (special input, float32 rounding boundary),
-//   - follower steps in the sliver 0 < |t| < 2^-22 where the float32 shortcut is not proven exact.
-// Returns true when this lane hit a flag; the caller then restores the lane state and re-runs the
-// samples through chunk<> (exact, with branches).
-template <bool USE_HP, bool HP_SYM, int U, bool DO_MM, bool FROM_DB = false>
+// Straight-line form for U samples: one large basic block per path that ptxas can software-pipeline (needs
+// __launch_bounds__(32, 1): with a higher occupancy target ptxas keeps the dependency chains back to back to
+// save registers).  Every rare case is only FLAGGED (see to_db_vec / to_amp_vec, plus follower steps that could
+// fall into the sliver 0 < |x - y| < 2^-22 where the float32 short-cut of ar_step is not proven exact).  Returns
+// true when this lane hit a flag; the caller then restores the lane state and re-runs the samples through
+// sample_exact.  CT: compile-time channel count (0 = use `step`), so that the shared-memory accesses of a chunk
+// are one base register plus immediates.
+//
+// Data-dependent exact short-cuts, all decided by warp votes (DESIGN.md "K1"):
+//  (iv)  no sample of the warp above the floor -> the dB values are the floor, no logarithm;
+//  (v)   at most ONE sample per lane above the floor (noise peaks: one value in a few hundred) -> one logarithm
+//        per lane (of the lane's maximum) instead of U;
+//  (vi)  the last rel value of every lane below `minmin` -> the min tracker ends at `minmin` whatever came
+//        before (envelope_follower.c:42-43), its recurrence is skipped.
+template <bool USE_HP, bool HP_SYM, int U, bool DO_MM, int CT>
 __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
-                                           bool store, uint32_t logtab, uint32_t exptab,
-                                           const MathConst &mc, uint32_t rstep = 0) {
-    float h[U], db[U], dr[U], amp[U], aux[U];
-    uint32_t flags = 0;
-    if (rstep == 0) rstep = step;
-    if (FROM_DB) {
+                                           bool store, uint32_t logtab, uint32_t exptab, const MathConst &mc,
+                                           bool &rel_pending) {
+    const uint32_t st = CT ? 4u * CT : step;
+    float h[U], v[U], db[U], dr[U], amp[U], q[U];
+    uint32_t spec = 0, mid = 0xffffffffu;
+    bool bad = false;
 #pragma unroll
-        for (int u = 0; u < U; ++u) db[u] = lds_f32(xs + u * step);
-    } else {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float x = lds_f32(xs + u * step);
-            h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
-        }
+    for (int u = 0; u < U; ++u) {
+        const float x = lds_f32(xs + u * st);
+        h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
+    }
 #if OFP_K1_LADDER <= 1  // speed-of-light ladder (profiles/): memory path only / + high-pass; results are NOT the detector's
+    wait_rel(rel_pending);
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (store) sts_f32(rs + u * rstep, h[u]);
-        return false;
+    for (int u = 0; u < U; ++u)
+        if (store) sts_f32(rs + u * st, h[u]);
+    return false;
 #endif
-        // exact short-cut (iv): a chunk whose samples all sit below the floor needs no logarithm
-        float vmax = 0.0f;
+    float vmax = 0.0f;
 #pragma unroll
-        for (int u = 0; u < U; ++u) vmax = fmaxf(vmax, fabsf(__fadd_rn(h[u], 1e-10f)));
-        if (__all_sync(0xffffffffu, vmax < k.vfloor)) {
+    for (int u = 0; u < U; ++u) { v[u] = fabsf(__fadd_rn(h[u], 1e-10f)); vmax = fmaxf(vmax, v[u]); }
+    float dbmax = k.floor_db;  // largest dB value of the chunk (sliver test below)
+    if (__all_sync(0xffffffffu, vmax < k.vfloor)) {  // (iv)
 #pragma unroll
-            for (int u = 0; u < U; ++u) db[u] = k.floor_db;
+        for (int u = 0; u < U; ++u) db[u] = k.floor_db;
+    } else {
+        float m1 = v[0], m2 = 0.0f;  // largest and second largest of the lane
+#pragma unroll
+        for (int u = 1; u < U; ++u) { m2 = fmaxf(m2, fminf(m1, v[u])); m1 = fmaxf(m1, v[u]); }
+        if (OFP_K1_SPARSE && __all_sync(0xffffffffu, m2 < k.vfloor)) {  // (v)
+            // the lane's other samples are below the floor; if its maximum is too, db1 comes out as the floor
+            float v1[1] = {m1}, db1[1];
+            to_db_vec<1>(v1, k.floor_db, logtab, mc, db1, spec, mid);
+            bad = db_flagged(spec, mid) & (m1 >= k.vfloor);
+            dbmax = m1 >= k.vfloor ? db1[0] : k.floor_db;  // (a special value below the floor must not leak through)
+#pragma unroll
+            for (int u = 0; u < U; ++u) db[u] = v[u] == m1 ? dbmax : k.floor_db;
         } else {
-            to_db_vec<U, false>(h, k.floor_db, logtab, mc, db, aux, flags, 0);
+            to_db_vec<U>(v, k.floor_db, logtab, mc, db, spec, mid);
+            bad = db_flagged(spec, mid);
+#pragma unroll
+            for (int u = 0; u < U; ++u) dbmax = fmaxf(dbmax, db[u]);
         }
     }
 #if OFP_K1_LADDER == 2  // + dB
+    wait_rel(rel_pending);
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * rstep, db[u]);
-    return flags != 0;
+        if (store) sts_f32(rs + u * st, db[u]);
+    return bad;
 #endif
-    bool sliver = false;
+    // Followers (envelope_follower.c:15-22).  0 < |x - y| < 2^-22 (the sliver in which float(double(t) + 1e-10)
+    // differs from t + 1e-10f) needs min(|x|, |y|) < 2.  With every dB value of the chunk and both envelopes at
+    // its start <= -4, the envelopes stay <= -3.99 throughout (a step moves y towards x by a factor <= 1 up to
+    // rounding), so one test per chunk is enough; anything else re-runs exactly.
+    bad |= !((dbmax <= -4.0f) & (L.yf <= -4.0f) & (L.ys <= -4.0f));
+    // coef * d with coef = d > 0 ? att : rel is max(att * d, rel * d) for att >= rel >= 0 (rounding is monotone)
+    // and -max(-att * d, -rel * d) for rel > att >= 0: the host passes (A, R, s) = (s att, s rel, s = +-1).
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const float t1 = __fsub_rn(db[u], L.yf), t2 = __fsub_rn(db[u], L.ys);
-        // 0 < |x - y| < 2^-22 needs min(|x|, |y|) < 2 (a difference of floats is a multiple of the smaller
-        // ulp): flag conservatively on the operands, the exact test runs in the re-run path
-        sliver |= (fabsf(db[u]) < 2.0f) | (fabsf(L.yf) < 2.0f) | (fabsf(L.ys) < 2.0f);
-        const float d1 = __fadd_rn(t1, 1e-10f), d2 = __fadd_rn(t2, 1e-10f);
+        const float d1 = __fadd_rn(__fsub_rn(db[u], L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(db[u], L.ys), 1e-10f);
+#if OFP_K1_FOLMAX
+        L.yf = __fmaf_rn(k.fS, fmaxf(__fmul_rn(k.fA, d1), __fmul_rn(k.fR, d1)), L.yf);
+        L.ys = __fmaf_rn(k.sS, fmaxf(__fmul_rn(k.sA, d2), __fmul_rn(k.sR, d2)), L.ys);
+#else
         L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
         L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
+#endif
         dr[u] = __fsub_rn(L.yf, L.ys);
     }
 #if OFP_K1_LADDER == 3  // + followers
+    wait_rel(rel_pending);
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * rstep, dr[u]);
-    return sliver | (flags != 0);
+        if (store) sts_f32(rs + u * st, dr[u]);
+    return bad;
 #endif
-    to_amp_vec<U, false>(dr, k.ceil_amp, exptab, mc, amp, flags, 0);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
+    float qmax = 0.0f;
+    mid = 0xffffffffu;
+    to_amp_vec<U>(dr, k.ceil_amp, exptab, mc, amp, q, qmax, mid);
+    bad |= amp_flagged(qmax, mid);
 #if OFP_K1_LADDER >= 5  // 4: + 10**x only; 5 and above: the full chunk
-        if (DO_MM) minmax_step(L, k, amp[u]);
-        L.bmax = fmaxf(L.bmax, amp[u]);
-        L.bmin = fminf(L.bmin, amp[u]);
-#endif
-        if (store) sts_f32(rs + u * rstep, amp[u]);
+    // max tracker, block extrema and the stores first: they overlap the drain of the 10**x pipeline that the
+    // vote of short-cut (vi) has to wait for
+    if (DO_MM) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float nx = __fadd_rn(__fmul_rn(L.mx, k.iamax), __fmul_rn(amp[u], k.amax));
+            L.mx = amp[u] > L.mx ? amp[u] : nx;
+        }
     }
-    return sliver | (flags != 0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { L.bmax = fmaxf(L.bmax, amp[u]); L.bmin = fminf(L.bmin, amp[u]); }
+#endif
+    wait_rel(rel_pending);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (store) sts_f32(rs + u * st, amp[u]);
+#if OFP_K1_LADDER >= 5
+    if (DO_MM) {
+        if (OFP_K1_MNVOTE && __all_sync(0xffffffffu, amp[U - 1] < k.minmin)) {  // (vi)
+            L.mn = k.minmin;
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float nm = __fadd_rn(__fmul_rn(L.mn, k.iamin), __fmul_rn(amp[u], k.amin));
+                L.mn = amp[u] < k.minmin ? k.minmin : (amp[u] < L.mn ? amp[u] : nm);
+            }
+        }
+    }
+#endif
+    return bad;
 }
 
 __device__ double g_logtab[2 << OFP_LOG_N];
-__device__ double g_exptab[32];
+__device__ double g_exptab[1 << OFP_EXP_N];
 
 // Round-trip the launch constants through shared memory with volatile loads.  To nvcc/ptxas the
 // reloaded values are opaque, so they stay in registers; otherwise they are re-materialised inside
@@ -488,17 +550,17 @@ __device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch
     __syncwarp();
 }
 
-// End of a block (main phase): the reference's threshold FSM (detection.py:759-792) on the block held
-// in shared memory, onset compaction in the reference's order, and the coalesced copy of the block's
-// rel envelope to HBM.  The block lives in a ring of NR rows per recording starting at row r0
-// (rcol = this lane's column of row 0; NR == B, r0 == 0 for a plain block buffer).
+// End of a block (main phase): the reference's threshold FSM (detection.py:759-792) on the block held in shared
+// memory, onset compaction in the reference's order, and the copy of the block's rel envelope to HBM
+// (rcol = this lane's column of row 0).  With 16-byte aligned rows the copy is one bulk async copy per recording
+// (cp.async.bulk shared -> global, issued by lane g for recording g): the warp does not touch the data again, and
+// `rel_pending` tells the next writer of the block buffer to wait until the copy engine has read it.
 __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float *rcol, const float *relbuf, int lane,
                                           int g, int c, int rec, int rec0, bool active, unsigned rec_mask,
-                                          unsigned lower_mask, int32_t &cnt, int64_t blk, int r0, int NR) {
+                                          unsigned lower_mask, int32_t &cnt, int64_t blk, bool &rel_pending) {
     const int C = a.p.n_channels, B = a.p.block_size, G = a.G;
-    auto row = [&](int k) { const int i = r0 + k; return (i >= NR ? i - NR : i) * C; };
     // ---- block FSM, detection.py:759-792 ----
-    const float last = rcol[row(B - 1)];
+    const float last = rcol[(B - 1) * C];
     const float thr_on = a.p.manual ? a.p.on_thr
                                     : __fadd_rn(__fmul_rn(L.mx, a.p.on_thr), L.mn);
     const float thr_off = a.p.manual ? a.p.off_thr
@@ -508,7 +570,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     if (!L.state && L.deb < 1 && L.bmax > thr_on) {
         float before = L.prev;
         for (int k = 0; k < B; ++k) {
-            const float r = rcol[row(k)];
+            const float r = rcol[k * C];
             if (r > thr_on && before < thr_on) { oi = k; hit = true; break; }
             before = r;
         }
@@ -524,7 +586,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     if (M == 0) off = L.bmin < thr_off;
     else {
         for (int k = M; k < B; ++k)
-            if (rcol[row(k)] < thr_off) { off = true; break; }
+            if (rcol[k * C] < thr_off) { off = true; break; }
     }
     if (off) L.state = 0;
     L.prev = last;
@@ -538,24 +600,25 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
         cnt += __popc(hits & rec_mask);
     }
     if (a.rel != nullptr) {
-        __syncwarp();
         const int nBC = B * C;
-        const int n1 = min(B, NR - r0) * C;  // elements before the ring wraps
-        for (int gi = 0; gi < G; ++gi) {
-            if (rec0 + gi >= a.R) break;
-            float *dst = a.rel + (rec0 + gi) * a.rel_stride + (blk - a.blk0) * nBC;
-            const float *src = relbuf + gi * a.stride_rel;
-            if (a.rel_vec_ok) {
-                // n1 and r0 * C are multiples of 4 whenever the ring is used (chunks of 8 rows)
-                const float4 *s4 = reinterpret_cast<const float4 *>(src);
-                float4 *d4 = reinterpret_cast<float4 *>(dst);
-                const int q1 = n1 / 4, q0 = r0 * C / 4;
-                for (int i = lane; i < nBC / 4; i += 32) __stcs(d4 + i, s4[i < q1 ? q0 + i : i - q1]);
-            } else {
-                for (int i = lane; i < nBC; i += 32) __stcs(dst + i, src[i < n1 ? r0 * C + i : i - n1]);
+        if (a.rel_vec_ok) {
+            fence_proxy_async();  // this lane's st.shared of the block -> visible to the async proxy
+            __syncwarp();
+            if (lane < G && rec0 + lane < a.R)
+                bulk_store(a.rel + (rec0 + lane) * a.rel_stride + (blk - a.blk0) * nBC, relbuf + lane * a.stride_rel,
+                           static_cast<uint32_t>(nBC) * 4u);
+            bulk_commit();
+            rel_pending = true;
+        } else {
+            __syncwarp();
+            for (int gi = 0; gi < G; ++gi) {
+                if (rec0 + gi >= a.R) break;
+                float *dst = a.rel + (rec0 + gi) * a.rel_stride + (blk - a.blk0) * nBC;
+                const float *src = relbuf + gi * a.stride_rel;
+                for (int i = lane; i < nBC; i += 32) __stcs(dst + i, src[i]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -564,7 +627,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
 #endif
 constexpr int KU = OFP_K1_KU;  // samples per straight-line chunk of the single-warp kernel
 
-template <bool USE_HP, bool USE_TMA, bool HP_SYM>
+template <bool USE_HP, bool USE_TMA, bool HP_SYM, int CT>
 __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUtensorMap tmap, const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -574,7 +637,7 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     float *relbuf = stages + static_cast<size_t>(a.nst) * a.stage_floats;
 
     const int lane = threadIdx.x;
-    const int C = a.p.n_channels, B = a.p.block_size, G = a.G, T = a.T, TC = a.TC;
+    const int C = CT ? CT : a.p.n_channels, B = a.p.block_size, G = a.G, T = a.T, TC = a.TC;
     const int g_raw = lane / C;
     const bool in_group = g_raw < G;
     const int g = in_group ? g_raw : 0;
@@ -603,7 +666,7 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     L.bmax = -INFINITY; L.bmin = INFINITY;
 
     for (int i = lane; i < (2 << OFP_LOG_N); i += 32) logtab[i] = g_logtab[i];
-    exptab[lane] = g_exptab[lane];
+    for (int i = lane; i < (1 << OFP_EXP_N); i += 32) exptab[i] = g_exptab[i];
     __syncwarp();
     if (USE_TMA) {
         if (lane == 0) {
@@ -614,7 +677,6 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
         __syncwarp();
     }
     const uint32_t box_bytes = static_cast<uint32_t>(G) * TC * 4u;
-    uint32_t it = 0;      // tiles consumed so far (ring position / parity)
     int32_t cnt = (a.cnt_in && active) ? a.on_cnt[rec] : 0;  // onsets emitted for this lane's recording
     int64_t blk = a.blk0;  // main-phase block index (global; a.blk0 != 0 when a recording is fed in segments)
 
@@ -622,79 +684,85 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     const uint32_t rcol_s = smem_u32(rcol);
     const uint32_t stage0_s = smem_u32(stages) + 4u * (g * TC + c);
 
+    bool rel_pending = false;  // a bulk copy of the block buffer to HBM is in flight (block_end)
+    int s_cur = 0;             // ring position of the tile being consumed
+    uint32_t par = 0;          // its mbarrier phase parity
+    const int nst = a.nst;
+    const uint32_t stage_bytes = 4u * static_cast<uint32_t>(a.stage_floats);
     for (int phase = 0; phase < 2; ++phase) {
-        const int64_t len = phase == 0 ? a.warm_n : a.n_main;
+        // both lengths fit 32 bits (int32 sample indices, ofp_detect_offline)
+        const int len = static_cast<int>(phase == 0 ? a.warm_n : a.n_main);
         if (len <= 0) continue;
-        const int64_t env_len = phase == 0 ? (len / B) * B : len;
+        const int env_len = phase == 0 ? (len / B) * B : len;
         const bool do_minmax = phase == 0 || !a.p.manual;
-        const int64_t ntiles = (len + T - 1) / T;
+        const int ntiles = (len + T - 1) / T;
         int kpos = 0;
         if (USE_TMA && lane == 0) {
-            for (int p = 0; p < a.nst - 1 && p < ntiles; ++p) {
-                const int s = (it + p) % a.nst;
-                mbar_expect_tx(&bars[s], box_bytes);
-                tma_load_2d(stages + static_cast<size_t>(s) * a.stage_floats, &tmap, &bars[s], p * TC, rec0);
+            int sp = s_cur;
+            for (int p = 0; p < nst - 1 && p < ntiles; ++p) {
+                mbar_expect_tx(&bars[sp], box_bytes);
+                tma_load_2d(stages + static_cast<size_t>(sp) * a.stage_floats, &tmap, &bars[sp], p * TC, rec0);
+                sp = sp + 1 == nst ? 0 : sp + 1;
             }
         }
-        for (int64_t ti = 0; ti < ntiles; ++ti, ++it) {
-            int s = it % a.nst;
-            const int64_t t0 = ti * T;
+        int t0 = 0;
+        for (int ti = 0; ti < ntiles; ++ti, t0 += T) {
+            int s = s_cur;
             if (USE_TMA) {
-                const int64_t nx = ti + a.nst - 1;
+                const int nx = ti + nst - 1;
                 if (lane == 0 && nx < ntiles) {
-                    const int sn = (it + a.nst - 1) % a.nst;
+                    const int sn = s_cur == 0 ? nst - 1 : s_cur - 1;  // the stage consumed last
                     mbar_expect_tx(&bars[sn], box_bytes);
-                    tma_load_2d(stages + static_cast<size_t>(sn) * a.stage_floats, &tmap, &bars[sn],
-                                static_cast<int32_t>(nx * TC), rec0);
+                    tma_load_2d(stages + static_cast<size_t>(sn) * a.stage_floats, &tmap, &bars[sn], nx * TC, rec0);
                 }
-                mbar_wait(&bars[s], (it / a.nst) & 1u);
+                mbar_wait(&bars[s], par);
+                if (++s_cur == nst) { s_cur = 0; par ^= 1u; }
             } else {
                 // generic path (unaligned input): cooperative copy of the tile into stage 0
                 s = 0;
                 const int64_t row_elems = a.n_samples * C;
                 for (int idx = lane; idx < G * TC; idx += 32) {
                     const int gi = idx / TC, e = idx - gi * TC;
-                    const int64_t col = t0 * C + e;
+                    const int64_t col = static_cast<int64_t>(t0) * C + e;
                     float v = 0.f;
                     if (rec0 + gi < a.R && col < row_elems) v = a.x[(rec0 + gi) * a.rec_stride + col];
                     stages[idx] = v;
                 }
                 __syncwarp();
             }
-            const uint32_t sp = stage0_s + 4u * static_cast<uint32_t>(s) * a.stage_floats;
-            const int tl = static_cast<int>(min(static_cast<int64_t>(T), len - t0));
+            const uint32_t sp = stage0_s + static_cast<uint32_t>(s) * stage_bytes;
+            const int tl = min(T, len - t0);
             int j = 0;
             while (j < tl) {
-                const int64_t t = t0 + j;
-                if (t < env_len) {
+                if (t0 + j < env_len) {
                     const int seg = min(tl - j, B - kpos);
-                    const uint32_t xp = sp + j * step;
-                    const uint32_t rp = rcol_s + kpos * step;
+                    uint32_t xp = sp + j * step;
+                    uint32_t rp = rcol_s + kpos * step;
                     int i = 0;
-                    for (; i + KU <= seg; i += KU) {
+                    for (; i + KU <= seg; i += KU, xp += KU * step, rp += KU * step) {
                         const Lane saved = L;
                         // the min/max trackers only rest in the main phase of manual-threshold detectors
                         const bool bad = do_minmax
-                            ? chunk_fast<USE_HP, HP_SYM, KU, true>(L, kf, xp + i * step, rp + i * step, step,
-                                                                              in_group, logtab_s, exptab_s, mc)
-                            : chunk_fast<USE_HP, HP_SYM, KU, false>(L, kf, xp + i * step, rp + i * step, step,
-                                                                               in_group, logtab_s, exptab_s, mc);
-                        if (__any_sync(0xffffffffu, bad)) {  // rare: exact re-run of these samples
+                            ? chunk_fast<USE_HP, HP_SYM, KU, true, CT>(L, kf, xp, rp, step, in_group, logtab_s, exptab_s,
+                                                                                  mc, rel_pending)
+                            : chunk_fast<USE_HP, HP_SYM, KU, false, CT>(L, kf, xp, rp, step, in_group, logtab_s, exptab_s,
+                                                                                   mc, rel_pending);
+                        if (__any_sync(0xffffffffu, bad | !a.fast_ok)) {  // rare: exact re-run of these samples
                             L = saved;
                             for (int e = 0; e < KU; ++e)
-                                chunk<USE_HP, 1>(L, kf, xp + (i + e) * step, rp + (i + e) * step, step, do_minmax,
-                                                 in_group, logtab_s, exptab_s, mc);
+                                sample_exact<USE_HP>(L, kf, xp + e * step, rp + e * step, do_minmax, in_group, logtab_s,
+                                                     exptab_s, mc, rel_pending);
                         }
                     }
-                    for (; i < seg; ++i)
-                        chunk<USE_HP, 1>(L, kf, xp + i * step, rp + i * step, step, do_minmax, in_group, logtab_s,
-                                         exptab_s, mc);
+                    for (; i < seg; ++i, xp += step, rp += step)
+                        sample_exact<USE_HP>(L, kf, xp, rp, do_minmax, in_group, logtab_s, exptab_s, mc, rel_pending);
                     j += seg;
                     kpos += seg;
                     if (kpos == B) {
                         kpos = 0;
                         if (phase == 1) {
-                            block_end(L, a, rcol, relbuf, lane, g, c, rec, rec0, active, rec_mask, lower_mask, cnt, blk, 0, B);
+                            block_end(L, a, rcol, relbuf, lane, g, c, rec, rec0, active, rec_mask, lower_mask, cnt, blk,
+                                      rel_pending);
                             ++blk;
                         }
                         L.bmax = -INFINITY; L.bmin = INFINITY;
@@ -712,6 +780,7 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
             __syncwarp();  // every lane is done with stage s before the producer refills it
         }
     }
+    if (rel_pending) bulk_wait_read<0>();  // the block buffer must outlive the copy engine's reads
 
     if (active) {
         a.st.z0[lid] = L.z0; a.st.z1[lid] = L.z1; a.st.z2[lid] = L.z2; a.st.z3[lid] = L.z3;
@@ -853,6 +922,11 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.ia_min = static_cast<float>(1.0 - static_cast<double>(p.alpha_min));
     a.ia_max = static_cast<float>(1.0 - static_cast<double>(p.alpha_max));
     a.floor_skip = env_int("OFP_K1_FLOOR_SKIP", 1);
+    {
+        const float cf[4] = {p.fast_att, p.fast_rel, p.slow_att, p.slow_rel};
+        a.fast_ok = 1;
+        for (float c : cf) a.fast_ok &= (c > 0.0f && c <= 1.0f) ? 1 : 0;
+    }
     a.blk0 = blk0; a.cnt_in = cnt_in ? 1 : 0;
     a.st = state_of(det);
     a.x = x; a.n_samples = n_samples; a.rec_stride = rec_stride;
@@ -891,9 +965,13 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     { int rc = upload_tables(); if (rc != OFP_OK) return rc; }
     const int grid = (a.R + a.G - 1) / a.G;
     const bool sym = p.use_hp && memcmp(&p.b[0], &p.b[4], 4) == 0 && memcmp(&p.b[1], &p.b[3], 4) == 0;
-    auto kern = p.use_hp ? (tma_ok ? (sym ? k1_detect<true, true, true> : k1_detect<true, true, false>)
-                                   : (sym ? k1_detect<true, false, true> : k1_detect<true, false, false>))
-                         : (tma_ok ? k1_detect<false, true, false> : k1_detect<false, false, false>);
+    // channel count as a compile-time constant for the common 3-microphone layout (immediate shared-memory offsets)
+    auto kern = C == 3 ? (p.use_hp ? (tma_ok ? (sym ? k1_detect<true, true, true, 3> : k1_detect<true, true, false, 3>)
+                                             : (sym ? k1_detect<true, false, true, 3> : k1_detect<true, false, false, 3>))
+                                   : (tma_ok ? k1_detect<false, true, false, 3> : k1_detect<false, false, false, 3>))
+                       : (p.use_hp ? (tma_ok ? (sym ? k1_detect<true, true, true, 0> : k1_detect<true, true, false, 0>)
+                                             : (sym ? k1_detect<true, false, true, 0> : k1_detect<true, false, false, 0>))
+                                   : (tma_ok ? k1_detect<false, true, false, 0> : k1_detect<false, false, false, 0>));
     OFP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, 32, smem, stream>>>(tmap, a);
     OFP_CUDA_CHECK(cudaGetLastError());

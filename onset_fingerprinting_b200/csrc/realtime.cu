@@ -147,8 +147,13 @@ int ofp_rt_create(ofp_rt **out, int32_t n_streams, const ofp_detector_params *p,
     RT_CHECK(cudaMemset(r->in, 0, sizeof(float) * SC * r->B));
     RT_CHECK(cudaDeviceSynchronize());
     // one eager pass uploads the detector's tables and sets the kernel attributes (not capturable), then the
-    // state is reset and the same sequence is captured
-    rc = rt_enqueue(r);
+    // state is reset and the same sequence is captured.  The pass must already see defined state: the group
+    // tables and counters come from cudaMalloc and the locate kernel indexes with them.
+    RT_CHECK(cudaMemset(r->ch, 0, sizeof(int32_t) * SC));
+    RT_CHECK(cudaMemset(r->dl, 0, sizeof(int32_t) * SC));
+    RT_CHECK(cudaMemset(r->cnt, 0, sizeof(int32_t) * r->S));
+    rc = ofp_rt_reset(r);
+    if (rc == OFP_OK) rc = rt_enqueue(r);
     if (rc == OFP_OK) rc = ofp_rt_reset(r);
     if (rc != OFP_OK) { ofp_rt_destroy(r); return rc; }
     if (use_graph) {
