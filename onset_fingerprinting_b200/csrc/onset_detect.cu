@@ -47,9 +47,16 @@
 #ifndef OFP_K1_MNVOTE  // short-cut (vi)
 #define OFP_K1_MNVOTE 1
 #endif
+#ifndef OFP_K1_SKIPFOL  // followers of below-floor chunks without the coefficient choice
+#define OFP_K1_SKIPFOL 1
+#endif
+#ifndef OFP_K1_MXSPEC  // max tracker without the select (speculating that no sample exceeds it)
+#define OFP_K1_MXSPEC 1
+#endif
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 
 struct ofp_detector {
@@ -106,6 +113,7 @@ struct Coef {
     float fa, fr, sa, sr;
     float fA, fR, fS, sA, sR, sS;  // followers of the straight-line chunk: (s att, s rel, s), s = att >= rel ? 1 : -1
     float floor_db, ceil_amp, vfloor;
+    float sliver_thr;  // -4, or -inf when the straight-line chunk must not be trusted (every chunk re-runs exactly)
     float amin, amax, iamin, iamax, minmin;
 };
 __device__ __forceinline__ Coef load_coef(const K1Args &a) {
@@ -119,6 +127,7 @@ __device__ __forceinline__ Coef load_coef(const K1Args &a) {
     // |h + 1e-10| below vfloor => 20*log10(.) rounds below the floor => the clipped dB value IS the floor
     // (4e-6 relative margin = 4.5 float32 ulps of the floor in dB, DESIGN.md "K1 arithmetic" (iv))
     k.vfloor = a.floor_skip ? static_cast<float>(exp10(static_cast<double>(a.p.floor_db) / 20.0) * (1.0 - 4e-6)) : 0.0f;
+    k.sliver_thr = a.fast_ok ? -4.0f : -INFINITY;
     k.amin = a.p.alpha_min; k.amax = a.p.alpha_max; k.iamin = a.ia_min; k.iamax = a.ia_max;
     k.minmin = a.p.minmin;
     return k;
@@ -211,8 +220,9 @@ __device__ __forceinline__ float amp_of(double ad, float ceil_amp) {
 // the instruction stream handed to ptxas is already interleaved).  v = |h + 1e-10|.  Table-driven double
 // evaluation, relative error < 2^-41.  Rare cases are accumulated, not branched on:
 //   spec = max (bits(v) - 0x00800000): >= 0x7f000000 for zero / denormal / inf / nan inputs;
-//   mid  = min distance word of the double result to a float32 rounding boundary: < 2 * OFP_LOG_WIN when the
-//          double cannot be trusted to round correctly (the caller then uses slow_log10).
+//   mid  = min distance word of the double result to a float32 rounding boundary (the 29 dropped bits shifted to
+//          the top of the word, minus the lower edge of the window): < 2 * OFP_LOG_WIN << 3 when the double cannot
+//          be trusted to round correctly (the caller then uses slow_log10).
 template <int U>
 __device__ __forceinline__ void to_db_vec(const float (&v)[U], float floor_db, uint32_t logtab, const MathConst &mc,
                                           float (&db)[U], uint32_t &spec, uint32_t &mid) {
@@ -254,13 +264,13 @@ __device__ __forceinline__ void to_db_vec(const float (&v)[U], float floor_db, u
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         spec = max(spec, ix[u] - 0x00800000u);
-        mid = min(mid, (static_cast<uint32_t>(__double2loint(ld[u])) & 0x1fffffffu) - (0x10000000u - OFP_LOG_WIN));
+        mid = min(mid, (static_cast<uint32_t>(__double2loint(ld[u])) << 3) - ((0x10000000u - OFP_LOG_WIN) << 3));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) db[u] = db_of(ld[u], floor_db);
 }
 __device__ __forceinline__ bool db_flagged(uint32_t spec, uint32_t mid) {
-    return (spec >= 0x7f000000u) | (mid < 2u * OFP_LOG_WIN);
+    return (spec >= 0x7f000000u) | (mid < ((2u * OFP_LOG_WIN) << 3));
 }
 
 // 10**(dr/20) - 1e-10 clipped to the ceiling for U samples, step-major.  q = dr / 20 correctly rounded without a
@@ -301,11 +311,9 @@ __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp,
 #pragma unroll
     for (int u = 0; u < U; ++u) rr[u] = __fma_rn(qd[u], mc.log2_10, -kq[u]);
 #pragma unroll
-    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(rr[u], mc.e4, mc.e3);
+    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(rr[u], mc.e3, mc.e2);
 #pragma unroll
     for (int u = 0; u < U; ++u) s1[u] = __dmul_rn(sc[u], rr[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) pp[u] = __fma_rn(rr[u], pp[u], mc.e2);
 #pragma unroll
     for (int u = 0; u < U; ++u) pp[u] = __fma_rn(rr[u], pp[u], mc.e1);
 #pragma unroll
@@ -329,9 +337,9 @@ __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp,
         fb[u] = __float_as_uint(__double2float_rn(y[u])) + ((ki[u] & ~((1u << OFP_EXP_N) - 1u)) << (23 - OFP_EXP_N));
 #endif
 #if OFP_K1_ICVT
-        mid = min(mid, (lo2[u] + OFP_EXP_WIN) & 0x1fffffffu);
+        mid = min(mid, (lo2[u] << 3) + (OFP_EXP_WIN << 3));
 #else
-        mid = min(mid, (static_cast<uint32_t>(__double2loint(y[u])) + (0x10000000u + OFP_EXP_WIN)) & 0x1fffffffu);
+        mid = min(mid, (static_cast<uint32_t>(__double2loint(y[u])) << 3) + ((0x10000000u + OFP_EXP_WIN) << 3));
 #endif
         qmax = fmaxf(qmax, fabsf(q[u]));
     }
@@ -339,7 +347,7 @@ __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp,
     for (int u = 0; u < U; ++u) amp[u] = fminf(__fsub_rn(__uint_as_float(fb[u]), 1e-10f), ceil_amp);
 }
 __device__ __forceinline__ bool amp_flagged(float qmax, uint32_t mid) {
-    return !(qmax < 9.5f) | (mid < 2u * OFP_EXP_WIN);
+    return !(qmax < 9.5f) | (mid < ((2u * OFP_EXP_WIN) << 3));
 }
 
 // The previous block's bulk copy (block_end) must have read the block buffer before it is overwritten.
@@ -430,7 +438,8 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
 #pragma unroll
     for (int u = 0; u < U; ++u) { v[u] = fabsf(__fadd_rn(h[u], 1e-10f)); vmax = fmaxf(vmax, v[u]); }
     float dbmax = k.floor_db;  // largest dB value of the chunk (sliver test below)
-    if (__all_sync(0xffffffffu, vmax < k.vfloor)) {  // (iv)
+    const bool skip = __all_sync(0xffffffffu, vmax < k.vfloor);
+    if (skip) {  // (iv)
 #pragma unroll
         for (int u = 0; u < U; ++u) db[u] = k.floor_db;
     } else {
@@ -463,20 +472,37 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
     // differs from t + 1e-10f) needs min(|x|, |y|) < 2.  With every dB value of the chunk and both envelopes at
     // its start <= -4, the envelopes stay <= -3.99 throughout (a step moves y towards x by a factor <= 1 up to
     // rounding), so one test per chunk is enough; anything else re-runs exactly.
-    bad |= !((dbmax <= -4.0f) & (L.yf <= -4.0f) & (L.ys <= -4.0f));
+    bad |= !((dbmax <= k.sliver_thr) & (L.yf <= k.sliver_thr) & (L.ys <= k.sliver_thr));
     // coef * d with coef = d > 0 ? att : rel is max(att * d, rel * d) for att >= rel >= 0 (rounding is monotone)
     // and -max(-att * d, -rel * d) for rel > att >= 0: the host passes (A, R, s) = (s att, s rel, s = +-1).
+    // Below-floor chunks (iv) know more: x is the floor and y >= floor, so d = (floor - y) + 1e-10 <= 1e-10 and the
+    // release coefficient applies; for 0 < d <= 1e-7 either coefficient (both <= 1) leaves y <= -3.99 unchanged
+    // (|coef d| < half an ulp), so y + rel * d is the reference's value unless d > 1e-7 -- flagged (an envelope one
+    // rounding below the floor).
+    if (OFP_K1_SKIPFOL && skip) {
+        bool rising = false;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float d1 = __fadd_rn(__fsub_rn(db[u], L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(db[u], L.ys), 1e-10f);
+        for (int u = 0; u < U; ++u) {
+            const float d1 = __fadd_rn(__fsub_rn(k.floor_db, L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(k.floor_db, L.ys), 1e-10f);
+            rising |= (d1 > 1e-7f) | (d2 > 1e-7f);
+            L.yf = __fadd_rn(L.yf, __fmul_rn(k.fr, d1));
+            L.ys = __fadd_rn(L.ys, __fmul_rn(k.sr, d2));
+            dr[u] = __fsub_rn(L.yf, L.ys);
+        }
+        bad |= rising;
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float d1 = __fadd_rn(__fsub_rn(db[u], L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(db[u], L.ys), 1e-10f);
 #if OFP_K1_FOLMAX
-        L.yf = __fmaf_rn(k.fS, fmaxf(__fmul_rn(k.fA, d1), __fmul_rn(k.fR, d1)), L.yf);
-        L.ys = __fmaf_rn(k.sS, fmaxf(__fmul_rn(k.sA, d2), __fmul_rn(k.sR, d2)), L.ys);
+            L.yf = __fmaf_rn(k.fS, fmaxf(__fmul_rn(k.fA, d1), __fmul_rn(k.fR, d1)), L.yf);
+            L.ys = __fmaf_rn(k.sS, fmaxf(__fmul_rn(k.sA, d2), __fmul_rn(k.sR, d2)), L.ys);
 #else
-        L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
-        L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
+            L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
+            L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
 #endif
-        dr[u] = __fsub_rn(L.yf, L.ys);
+            dr[u] = __fsub_rn(L.yf, L.ys);
+        }
     }
 #if OFP_K1_LADDER == 3  // + followers
     wait_rel(rel_pending);
@@ -493,11 +519,23 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
     // max tracker, block extrema and the stores first: they overlap the drain of the 10**x pipeline that the
     // vote of short-cut (vi) has to wait for
     if (DO_MM) {
+#if OFP_K1_MXSPEC
+        // max tracker (envelope_follower.c:48-51) on the assumption that no sample exceeds it (then every step is the
+        // decay branch: no select in the recurrence); a sample that does flags the chunk
+        bool exceeds = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            exceeds |= amp[u] > L.mx;
+            L.mx = __fadd_rn(__fmul_rn(L.mx, k.iamax), __fmul_rn(amp[u], k.amax));
+        }
+        bad |= exceeds;
+#else
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float nx = __fadd_rn(__fmul_rn(L.mx, k.iamax), __fmul_rn(amp[u], k.amax));
             L.mx = amp[u] > L.mx ? amp[u] : nx;
         }
+#endif
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) { L.bmax = fmaxf(L.bmax, amp[u]); L.bmin = fminf(L.bmin, amp[u]); }
@@ -739,18 +777,27 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                     uint32_t xp = sp + j * step;
                     uint32_t rp = rcol_s + kpos * step;
                     int i = 0;
-                    for (; i + KU <= seg; i += KU, xp += KU * step, rp += KU * step) {
+                    // Straight-line chunks.  Their rare-case flags are collected over the whole segment (<= one tile,
+                    // inside one block) and voted on once: a flagged segment is re-run sample by sample on the exact
+                    // path from the state saved at its start (0.2 % of the segments of the benchmark signal).  The
+                    // min/max trackers only rest in the main phase of manual-threshold detectors: that choice is made
+                    // outside the chunk loop (inside it costs a constant-bank load and a dependent branch per chunk).
+                    const int nfast = seg - seg % KU;
+                    if (nfast > 0) {
                         const Lane saved = L;
-                        // the min/max trackers only rest in the main phase of manual-threshold detectors
-                        const bool bad = do_minmax
-                            ? chunk_fast<USE_HP, HP_SYM, KU, true, CT>(L, kf, xp, rp, step, in_group, logtab_s, exptab_s,
-                                                                                  mc, rel_pending)
-                            : chunk_fast<USE_HP, HP_SYM, KU, false, CT>(L, kf, xp, rp, step, in_group, logtab_s, exptab_s,
-                                                                                   mc, rel_pending);
-                        if (__any_sync(0xffffffffu, bad | !a.fast_ok)) {  // rare: exact re-run of these samples
+                        const uint32_t xp0 = xp, rp0 = rp;
+                        bool bad = false;
+                        auto chunks = [&](auto mm) {
+                            for (; i < nfast; i += KU, xp += KU * step, rp += KU * step)
+                                bad |= chunk_fast<USE_HP, HP_SYM, KU, decltype(mm)::value, CT>(
+                                    L, kf, xp, rp, step, in_group, logtab_s, exptab_s, mc, rel_pending);
+                        };
+                        if (do_minmax) chunks(std::true_type{});
+                        else chunks(std::false_type{});
+                        if (__any_sync(0xffffffffu, bad)) {
                             L = saved;
-                            for (int e = 0; e < KU; ++e)
-                                sample_exact<USE_HP>(L, kf, xp + e * step, rp + e * step, do_minmax, in_group, logtab_s,
+                            for (int e = 0; e < nfast; ++e)
+                                sample_exact<USE_HP>(L, kf, xp0 + e * step, rp0 + e * step, do_minmax, in_group, logtab_s,
                                                      exptab_s, mc, rel_pending);
                         }
                     }
