@@ -61,7 +61,7 @@ struct MathConst {
     double a1, a2, a3, a4, a5;    // log10(1+r) = r (a1 + a2 r + ... + a5 r^4), |r| <= 2^-8
     double log10_2s, kmagic;      // log10(2) * 2^-23 and 2^52 + 2^31 (exponent word -> double without I2F)
     double e1, e2, e3;            // 2^r = 1 + r (e1 + e2 r + e3 r^2), |r| <= 2^-10
-    double log2_10, shift;        // shift = 1.5 * 2^(52 - OFP_EXP_N): kd0 = q log2(10) + shift has spacing 2^-OFP_EXP_N
+    double log2_10;
 };
 OFP_HD MathConst math_const() {
     MathConst c;
@@ -70,13 +70,14 @@ OFP_HD MathConst math_const() {
     c.kmagic = 0x1p52 + 0x1p31;
     c.e1 = OFP_EXP_E1; c.e2 = OFP_EXP_E2; c.e3 = OFP_EXP_E3;
     c.log2_10 = OFP_LOG2_10;
-    c.shift = 0x1.8p52 / static_cast<double>(1 << OFP_EXP_N);
     return c;
 }
 
 // Rounding windows of the fast paths, in units of 2^-52 relative (double ulps of the result):
 // log10: |error| < 2^-41 (2^11 ulps), 10**x: |error| < 2^-46.1 (2^5.9 ulps: truncation 2^-46.7, q log2(10) 2^-48,
 // roundings 2^-51.4); the windows leave a factor >= 4.
+constexpr float OFP_LOG2_10_F = 3.3219280948873623f;                                   // float32(log2(10))
+constexpr float OFP_EXP_MAGIC_F = 1.5f * static_cast<float>(1 << (23 - OFP_EXP_N));   // spacing 2^-OFP_EXP_N
 constexpr uint32_t OFP_LOG_WIN = 1u << 13;
 constexpr uint32_t OFP_EXP_WIN = 1u << 8;
 

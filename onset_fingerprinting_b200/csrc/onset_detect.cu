@@ -32,6 +32,9 @@
 #ifndef OFP_K1_LADDER
 #define OFP_K1_LADDER 9
 #endif
+#ifndef OFP_K1_KU
+#define OFP_K1_KU 8
+#endif
 #ifndef OFP_K1_SPARSE  // short-cut (v) of chunk_fast, switchable for A/B builds
 #define OFP_K1_SPARSE 1
 #endif
@@ -101,7 +104,7 @@ struct K1Args {
     int32_t cap;
     int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
     int32_t floor_skip;  // OFP_K1_FLOOR_SKIP=0 disables the below-floor short-cut (A/B runs)
-    int32_t fast_ok;     // follower coefficients in (0, 1]: the straight-line chunk's short-cuts are proven for those
+    int32_t fast_ok;     // follower coefficients in (0, 1/2]: the straight-line chunk's short-cuts are proven for those
     int32_t cnt_in;      // continue: the per-recording onset counts in on_cnt are the starting fill levels
     int64_t blk0;        // continue: global index of the first block of this call (x / rel start there)
 };
@@ -112,7 +115,8 @@ struct Coef {
     float b0, b1, b2, b3, b4, a1, a2, a3, a4;
     float fa, fr, sa, sr;
     float fA, fR, fS, sA, sR, sS;  // followers of the straight-line chunk: (s att, s rel, s), s = att >= rel ? 1 : -1
-    float floor_db, ceil_amp, vfloor;
+    float floor_db, ceil_amp, vfloor, vfloor_h;
+    float mxfac;       // chunk maximum < mxfac x max tracker => no sample of the chunk exceeds the tracker
     float sliver_thr;  // -4, or -inf when the straight-line chunk must not be trusted (every chunk re-runs exactly)
     float amin, amax, iamin, iamax, minmin;
 };
@@ -127,6 +131,11 @@ __device__ __forceinline__ Coef load_coef(const K1Args &a) {
     // |h + 1e-10| below vfloor => 20*log10(.) rounds below the floor => the clipped dB value IS the floor
     // (4e-6 relative margin = 4.5 float32 ulps of the floor in dB, DESIGN.md "K1 arithmetic" (iv))
     k.vfloor = a.floor_skip ? static_cast<float>(exp10(static_cast<double>(a.p.floor_db) / 20.0) * (1.0 - 4e-6)) : 0.0f;
+    k.vfloor_h = k.vfloor > 0.0f ? nextafterf(static_cast<float>(static_cast<double>(k.vfloor) * (1.0 - 0x1p-23) - 1e-10), 0.0f) : 0.0f;
+    {
+        const double ia = static_cast<double>(a.ia_max);
+        k.mxfac = (ia > 0.0 && ia < 1.0) ? static_cast<float>(pow(ia, OFP_K1_KU) * (1.0 - 4e-6)) : 0.0f;
+    }
     k.sliver_thr = a.fast_ok ? -4.0f : -INFINITY;
     k.amin = a.p.alpha_min; k.amax = a.p.alpha_max; k.iamin = a.ia_min; k.iamax = a.ia_max;
     k.minmin = a.p.minmin;
@@ -287,7 +296,8 @@ __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp,
                                            float (&amp)[U], float (&q)[U], float &qmax, uint32_t &mid) {
     float q0[U];
     uint32_t qb[U], ki[U], lo2[U], hi2[U], fb[U];
-    double qd[U], kd0[U], kq[U], rr[U], sc[U], pp[U], s1[U], y[U];
+    float kf0[U];
+    double qd[U], kq[U], rr[U], sc[U], pp[U], s1[U], y[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) q0[u] = __fmul_rn(dr[u], 0.05f);
 #pragma unroll
@@ -302,10 +312,12 @@ __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp,
         qd[u] = static_cast<double>(q[u]);
 #endif
     }
+    // k / 2^N = q log2(10) rounded to N fractional bits in float32 (magic-constant add: the integer k sits in the low
+    // mantissa bits of the sum); a k that is off by one near a tie only makes |rr| 2^-19 larger
 #pragma unroll
-    for (int u = 0; u < U; ++u) kd0[u] = __fma_rn(qd[u], mc.log2_10, mc.shift);
+    for (int u = 0; u < U; ++u) kf0[u] = __fmaf_rn(q[u], OFP_LOG2_10_F, OFP_EXP_MAGIC_F);
 #pragma unroll
-    for (int u = 0; u < U; ++u) { ki[u] = static_cast<uint32_t>(__double2loint(kd0[u])); kq[u] = __dsub_rn(kd0[u], mc.shift); }
+    for (int u = 0; u < U; ++u) { ki[u] = __float_as_uint(kf0[u]); kq[u] = static_cast<double>(__fsub_rn(kf0[u], OFP_EXP_MAGIC_F)); }
 #pragma unroll
     for (int u = 0; u < U; ++u) sc[u] = lds_f64(exptab + ((ki[u] & ((1u << OFP_EXP_N) - 1u)) << 3));
 #pragma unroll
@@ -415,18 +427,20 @@ __device__ __forceinline__ void sample_exact(Lane &L, const Coef &k, uint32_t xs
 //  (vi)  the last rel value of every lane below `minmin` -> the min tracker ends at `minmin` whatever came
 //        before (envelope_follower.c:42-43), its recurrence is skipped.
 template <bool USE_HP, bool HP_SYM, int U, bool DO_MM, int CT>
-__device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, uint32_t rs, uint32_t step,
-                                           bool store, uint32_t logtab, uint32_t exptab, const MathConst &mc,
-                                           bool &rel_pending) {
+__device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[U], uint32_t xs_next, uint32_t rs,
+                                           uint32_t step, bool store, uint32_t logtab, uint32_t exptab,
+                                           const MathConst &mc, bool &rel_pending) {
     const uint32_t st = CT ? 4u * CT : step;
     float h[U], v[U], db[U], dr[U], amp[U], q[U];
     uint32_t spec = 0, mid = 0xffffffffu;
     bool bad = false;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const float x = lds_f32(xs + u * st);
-        h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, x) : hp_step(L, k, x)) : x;
-    }
+    for (int u = 0; u < U; ++u)
+        h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, xin[u]) : hp_step(L, k, xin[u])) : xin[u];
+    // the NEXT chunk's input is fetched now (its shared-memory latency hides behind this chunk); past the end of a
+    // tile this reads the neighbouring stage / the block buffer -- defined addresses, values never used
+#pragma unroll
+    for (int u = 0; u < U; ++u) xin[u] = lds_f32(xs_next + u * st);
 #if OFP_K1_LADDER <= 1  // speed-of-light ladder (profiles/): memory path only / + high-pass; results are NOT the detector's
     wait_rel(rel_pending);
 #pragma unroll
@@ -434,15 +448,18 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
         if (store) sts_f32(rs + u * st, h[u]);
     return false;
 #endif
-    float vmax = 0.0f;
+    // |h| < vfloor_h implies |h + 1e-10| < vfloor (vfloor_h = vfloor (1 - 2^-23) - 1e-10, rounded down)
+    float hmax = 0.0f;
 #pragma unroll
-    for (int u = 0; u < U; ++u) { v[u] = fabsf(__fadd_rn(h[u], 1e-10f)); vmax = fmaxf(vmax, v[u]); }
+    for (int u = 0; u < U; ++u) hmax = fmaxf(hmax, fabsf(h[u]));
     float dbmax = k.floor_db;  // largest dB value of the chunk (sliver test below)
-    const bool skip = __all_sync(0xffffffffu, vmax < k.vfloor);
+    const bool skip = __all_sync(0xffffffffu, hmax < k.vfloor_h);
     if (skip) {  // (iv)
 #pragma unroll
         for (int u = 0; u < U; ++u) db[u] = k.floor_db;
     } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = fabsf(__fadd_rn(h[u], 1e-10f));
         float m1 = v[0], m2 = 0.0f;  // largest and second largest of the lane
 #pragma unroll
         for (int u = 1; u < U; ++u) { m2 = fmaxf(m2, fminf(m1, v[u])); m1 = fmaxf(m1, v[u]); }
@@ -480,16 +497,16 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
     // (|coef d| < half an ulp), so y + rel * d is the reference's value unless d > 1e-7 -- flagged (an envelope one
     // rounding below the floor).
     if (OFP_K1_SKIPFOL && skip) {
-        bool rising = false;
+        // y >= floor at the start keeps y >= floor through the chunk (coefficients <= 1/2: a step covers at most
+        // half the distance, rounding is monotone and the floor is a float), so every d is <= 1e-10
+        bad |= !((L.yf >= k.floor_db) & (L.ys >= k.floor_db));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float d1 = __fadd_rn(__fsub_rn(k.floor_db, L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(k.floor_db, L.ys), 1e-10f);
-            rising |= (d1 > 1e-7f) | (d2 > 1e-7f);
             L.yf = __fadd_rn(L.yf, __fmul_rn(k.fr, d1));
             L.ys = __fadd_rn(L.ys, __fmul_rn(k.sr, d2));
             dr[u] = __fsub_rn(L.yf, L.ys);
         }
-        bad |= rising;
     } else {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -518,27 +535,26 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
 #if OFP_K1_LADDER >= 5  // 4: + 10**x only; 5 and above: the full chunk
     // max tracker, block extrema and the stores first: they overlap the drain of the 10**x pipeline that the
     // vote of short-cut (vi) has to wait for
-    if (DO_MM) {
-#if OFP_K1_MXSPEC
-        // max tracker (envelope_follower.c:48-51) on the assumption that no sample exceeds it (then every step is the
-        // decay branch: no select in the recurrence); a sample that does flags the chunk
-        bool exceeds = false;
+    float cmax = amp[0], cmin = amp[0];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            exceeds |= amp[u] > L.mx;
-            L.mx = __fadd_rn(__fmul_rn(L.mx, k.iamax), __fmul_rn(amp[u], k.amax));
-        }
-        bad |= exceeds;
-#else
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float nx = __fadd_rn(__fmul_rn(L.mx, k.iamax), __fmul_rn(amp[u], k.amax));
-            L.mx = amp[u] > L.mx ? amp[u] : nx;
-        }
-#endif
+    for (int u = 1; u + 1 < U; u += 2) {
+        cmax = fmaxf(fmaxf(cmax, amp[u]), amp[u + 1]);
+        cmin = fminf(fminf(cmin, amp[u]), amp[u + 1]);
     }
+    if (U % 2 == 0) { cmax = fmaxf(cmax, amp[U - 1]); cmin = fminf(cmin, amp[U - 1]); }
+    // The max tracker (envelope_follower.c:48-51) runs on the assumption that no sample exceeds it: every step is
+    // then the decay branch, no select in the recurrence.  The assumption holds when the chunk maximum is below
+    // mxfac = (1 - alpha_max)^U (1 - 4e-6) x the tracker's start value (the decay steps of a chunk cannot take it
+    // lower: the samples are >= 0, roundings cost < 2^-23 per step); it is checked together with
+    // short-cut (vi) by the one vote below, after the stores, so that the recurrence overlaps the 10**x pipeline.
+    const float mx0 = L.mx;
+    float mx_spec = mx0;
+    if (DO_MM && OFP_K1_MXSPEC) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) { L.bmax = fmaxf(L.bmax, amp[u]); L.bmin = fminf(L.bmin, amp[u]); }
+        for (int u = 0; u < U; ++u) mx_spec = __fadd_rn(__fmul_rn(mx_spec, k.iamax), __fmul_rn(amp[u], k.amax));
+    }
+    L.bmax = fmaxf(L.bmax, cmax);
+    L.bmin = fminf(L.bmin, cmin);
 #endif
     wait_rel(rel_pending);
 #pragma unroll
@@ -546,14 +562,13 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, uint32_t xs, 
         if (store) sts_f32(rs + u * st, amp[u]);
 #if OFP_K1_LADDER >= 5
     if (DO_MM) {
-        if (OFP_K1_MNVOTE && __all_sync(0xffffffffu, amp[U - 1] < k.minmin)) {  // (vi)
+        const bool quiet = (amp[U - 1] < k.minmin) & (cmax < __fmul_rn(mx0, k.mxfac));
+        if (OFP_K1_MNVOTE && OFP_K1_MXSPEC && __all_sync(0xffffffffu, quiet)) {  // (vi) + the max tracker's assumption
             L.mn = k.minmin;
+            L.mx = mx_spec;
         } else {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float nm = __fadd_rn(__fmul_rn(L.mn, k.iamin), __fmul_rn(amp[u], k.amin));
-                L.mn = amp[u] < k.minmin ? k.minmin : (amp[u] < L.mn ? amp[u] : nm);
-            }
+            for (int u = 0; u < U; ++u) minmax_step(L, k, amp[u]);
         }
     }
 #endif
@@ -660,9 +675,6 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     }
 }
 
-#ifndef OFP_K1_KU
-#define OFP_K1_KU 8
-#endif
 constexpr int KU = OFP_K1_KU;  // samples per straight-line chunk of the single-warp kernel
 
 template <bool USE_HP, bool USE_TMA, bool HP_SYM, int CT>
@@ -787,10 +799,13 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                         const Lane saved = L;
                         const uint32_t xp0 = xp, rp0 = rp;
                         bool bad = false;
+                        float xin[KU];  // the chunk's input samples, fetched one chunk ahead
+#pragma unroll
+                        for (int u = 0; u < KU; ++u) xin[u] = lds_f32(xp + u * step);
                         auto chunks = [&](auto mm) {
                             for (; i < nfast; i += KU, xp += KU * step, rp += KU * step)
                                 bad |= chunk_fast<USE_HP, HP_SYM, KU, decltype(mm)::value, CT>(
-                                    L, kf, xp, rp, step, in_group, logtab_s, exptab_s, mc, rel_pending);
+                                    L, kf, xin, xp + KU * step, rp, step, in_group, logtab_s, exptab_s, mc, rel_pending);
                         };
                         if (do_minmax) chunks(std::true_type{});
                         else chunks(std::false_type{});
@@ -972,7 +987,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     {
         const float cf[4] = {p.fast_att, p.fast_rel, p.slow_att, p.slow_rel};
         a.fast_ok = 1;
-        for (float c : cf) a.fast_ok &= (c > 0.0f && c <= 1.0f) ? 1 : 0;
+        for (float c : cf) a.fast_ok &= (c > 0.0f && c <= 0.5f) ? 1 : 0;
     }
     a.blk0 = blk0; a.cnt_in = cnt_in ? 1 : 0;
     a.st = state_of(det);
