@@ -38,9 +38,6 @@
 #ifndef OFP_K1_SPARSE  // short-cut (v) of chunk_fast, switchable for A/B builds
 #define OFP_K1_SPARSE 1
 #endif
-#ifndef OFP_K1_ICVT  // 10**x: double(q) and the float32 rounding of the result by integer operations instead of F2F
-#define OFP_K1_ICVT 0  // measured slower (79.8 vs 76.7 ms): the XU conversions cost one issue slot each, the integer forms 4-5
-#endif
 #ifndef OFP_K1_KMAGIC  // log10: exponent -> double by a magic-constant subtraction instead of I2F
 #define OFP_K1_KMAGIC 1
 #endif
@@ -103,6 +100,7 @@ struct K1Args {
     int32_t *on_ch, *on_idx, *on_cnt;
     int32_t cap;
     int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
+    int32_t P;  // row pitch of a stage in floats: TC + padding columns (the TMA box is P wide, tiles advance by TC)
     int32_t floor_skip;  // OFP_K1_FLOOR_SKIP=0 disables the below-floor short-cut (A/B runs)
     int32_t fast_ok;     // follower coefficients in (0, 1/2]: the straight-line chunk's short-cuts are proven for those
     int32_t cnt_in;      // continue: the per-recording onset counts in on_cnt are the starting fill levels
@@ -282,46 +280,42 @@ __device__ __forceinline__ bool db_flagged(uint32_t spec, uint32_t mid) {
     return (spec >= 0x7f000000u) | (mid < ((2u * OFP_LOG_WIN) << 3));
 }
 
-// 10**(dr/20) - 1e-10 clipped to the ceiling for U samples, step-major.  q = dr / 20 correctly rounded without a
-// division (exact: host harness over 4e8 values); double(q) by integer operations (zero / denormal q
-// become 2^-127-sized doubles: harmless); k = rint(q log2(10) 2^N) from the low word of q log2(10) + 1.5 2^(52-N),
-// reduced argument by one FMA against that same sum, 2^(j / 2^N) from the table, degree-4 polynomial, relative
-// error < 2^-47.5; the result is rounded to float32 by integer operations (add half a float32 ulp to the low word,
-// carry, funnel shift -- equal to round-to-nearest-even except on exact ties, which the window below excludes)
-// and scaled by 2^(k >> N) in the float32 exponent field.  Accumulated rare cases:
-//   qmax = max |q|: the fast path needs |q| < 9.5 (10**q - 1e-10 > 0, no overflow of the exponent arithmetic);
-//   mid  = min distance word to a float32 rounding boundary: < 2 * OFP_EXP_WIN => slow_exp10.
+// 10**(dr/20) - 1e-10 clipped to the ceiling.  q = dr / 20 correctly rounded without a division (exact: host harness
+// over 4e8 values); k = rint(q log2(10) 2^N) by a float32 magic-constant add, reduced argument
+// rr = q log2(10) - k / 2^N by one double FMA, 2^(j / 2^N) from the table, degree-3 polynomial, relative error
+// < 2^-46.1; the result is rounded to float32 and scaled by 2^(k >> N) in the exponent field.  Rare cases:
+//   |q| >= 9.5 (the fast path needs 10**q - 1e-10 > 0 and no overflow of the exponent arithmetic);
+//   mid = min distance word of the double result to a float32 rounding boundary: < 2 * OFP_EXP_WIN << 3 => slow_exp10.
+// Front of the evaluation for ONE sample (float32 work + two conversions; depends only on dr): a separate piece so
+// that the straight-line chunk can issue it between the dependent steps of the follower recurrences.
+struct AmpFront {
+    float q;        // dr / 20, correctly rounded
+    uint32_t ki;    // low mantissa bits: k = rint(q log2(10) 2^N)
+    double qd, kq;  // q and k / 2^N as doubles
+};
+__device__ __forceinline__ AmpFront amp_front(float dr) {
+    AmpFront f;
+    const float q0 = __fmul_rn(dr, 0.05f);
+    f.q = __fmaf_rn(__fmaf_rn(-20.0f, q0, dr), 0.05f, q0);
+    f.qd = static_cast<double>(f.q);
+    // the integer k sits in the low mantissa bits of the sum; a k that is off by one near a tie only makes |rr|
+    // 2^-19 larger
+    const float kf0 = __fmaf_rn(f.q, OFP_LOG2_10_F, OFP_EXP_MAGIC_F);
+    f.ki = __float_as_uint(kf0);
+    f.kq = static_cast<double>(__fsub_rn(kf0, OFP_EXP_MAGIC_F));
+    return f;
+}
+// Back of the evaluation for U samples, step-major (every elementary operation is issued for all U samples before
+// the next one): table, reduced argument, polynomial, rounding, scaling.
 template <int U>
-__device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp, uint32_t exptab, const MathConst &mc,
-                                           float (&amp)[U], float (&q)[U], float &qmax, uint32_t &mid) {
-    float q0[U];
-    uint32_t qb[U], ki[U], lo2[U], hi2[U], fb[U];
-    float kf0[U];
-    double qd[U], kq[U], rr[U], sc[U], pp[U], s1[U], y[U];
+__device__ __forceinline__ void amp_back(const AmpFront (&f)[U], float ceil_amp, uint32_t exptab, const MathConst &mc,
+                                         float (&amp)[U], uint32_t &mid) {
+    uint32_t fb[U];
+    double rr[U], sc[U], pp[U], s1[U], y[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) q0[u] = __fmul_rn(dr[u], 0.05f);
+    for (int u = 0; u < U; ++u) sc[u] = lds_f64(exptab + ((f[u].ki & ((1u << OFP_EXP_N) - 1u)) << 3));
 #pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = __fmaf_rn(__fmaf_rn(-20.0f, q0[u], dr[u]), 0.05f, q0[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        qb[u] = __float_as_uint(q[u]);
-#if OFP_K1_ICVT
-        const uint32_t hi = (((qb[u] & 0x7fffffffu) >> 3) + 0x38000000u) | (qb[u] & 0x80000000u);
-        qd[u] = __hiloint2double(static_cast<int>(hi), static_cast<int>(qb[u] << 29));
-#else
-        qd[u] = static_cast<double>(q[u]);
-#endif
-    }
-    // k / 2^N = q log2(10) rounded to N fractional bits in float32 (magic-constant add: the integer k sits in the low
-    // mantissa bits of the sum); a k that is off by one near a tie only makes |rr| 2^-19 larger
-#pragma unroll
-    for (int u = 0; u < U; ++u) kf0[u] = __fmaf_rn(q[u], OFP_LOG2_10_F, OFP_EXP_MAGIC_F);
-#pragma unroll
-    for (int u = 0; u < U; ++u) { ki[u] = __float_as_uint(kf0[u]); kq[u] = static_cast<double>(__fsub_rn(kf0[u], OFP_EXP_MAGIC_F)); }
-#pragma unroll
-    for (int u = 0; u < U; ++u) sc[u] = lds_f64(exptab + ((ki[u] & ((1u << OFP_EXP_N) - 1u)) << 3));
-#pragma unroll
-    for (int u = 0; u < U; ++u) rr[u] = __fma_rn(qd[u], mc.log2_10, -kq[u]);
+    for (int u = 0; u < U; ++u) rr[u] = __fma_rn(f[u].qd, mc.log2_10, -f[u].kq);
 #pragma unroll
     for (int u = 0; u < U; ++u) pp[u] = __fma_rn(rr[u], mc.e3, mc.e2);
 #pragma unroll
@@ -332,28 +326,8 @@ __device__ __forceinline__ void to_amp_vec(const float (&dr)[U], float ceil_amp,
     for (int u = 0; u < U; ++u) y[u] = __fma_rn(s1[u], pp[u], sc[u]);  // in (0.99, 2.01)
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const uint32_t yl = static_cast<uint32_t>(__double2loint(y[u])), yh = static_cast<uint32_t>(__double2hiint(y[u]));
-        // + 2^28 in the low word (half a float32 ulp), carry into the high word together with the exponent
-        // rebias 1023 -> 127 (0x08000000 << 3 == 0x40000000 == -896 << 23 mod 2^32)
-#if OFP_K1_ICVT
-        asm("add.cc.u32 %0, %2, 0x10000000;\n\taddc.u32 %1, %3, 0x08000000;" : "=r"(lo2[u]), "=r"(hi2[u]) : "r"(yl), "r"(yh));
-#else
-        lo2[u] = yl; hi2[u] = yh;
-#endif
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-#if OFP_K1_ICVT
-        fb[u] = __funnelshift_l(lo2[u], hi2[u], 3) + ((ki[u] & ~((1u << OFP_EXP_N) - 1u)) << (23 - OFP_EXP_N));
-#else
-        fb[u] = __float_as_uint(__double2float_rn(y[u])) + ((ki[u] & ~((1u << OFP_EXP_N) - 1u)) << (23 - OFP_EXP_N));
-#endif
-#if OFP_K1_ICVT
-        mid = min(mid, (lo2[u] << 3) + (OFP_EXP_WIN << 3));
-#else
+        fb[u] = __float_as_uint(__double2float_rn(y[u])) + ((f[u].ki & ~((1u << OFP_EXP_N) - 1u)) << (23 - OFP_EXP_N));
         mid = min(mid, (static_cast<uint32_t>(__double2loint(y[u])) << 3) + ((0x10000000u + OFP_EXP_WIN) << 3));
-#endif
-        qmax = fmaxf(qmax, fabsf(q[u]));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) amp[u] = fminf(__fsub_rn(__uint_as_float(fb[u]), 1e-10f), ceil_amp);
@@ -395,10 +369,11 @@ __device__ __forceinline__ void sample_exact(Lane &L, const Coef &k, uint32_t xs
     L.yf = ar_step(L.yf, db[0], k.fa, k.fr);
     L.ys = ar_step(L.ys, db[0], k.sa, k.sr);
     dr[0] = __fsub_rn(L.yf, L.ys);
-    float qmax = 0.0f;
     mid = 0xffffffffu;
-    to_amp_vec<1>(dr, k.ceil_amp, exptab, mc, amp, q, qmax, mid);
-    const bool redo_amp = amp_flagged(qmax, mid);
+    AmpFront af[1] = {amp_front(dr[0])};
+    q[0] = af[0].q;
+    amp_back<1>(af, k.ceil_amp, exptab, mc, amp, mid);
+    const bool redo_amp = amp_flagged(fabsf(q[0]), mid);
     if (__any_sync(0xffffffffu, redo_amp)) {
         if (redo_amp) {
             const float qq = fabsf(q[0]) < 30.0f ? q[0] : __fdiv_rn(dr[0], 20.0f);
@@ -431,7 +406,8 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
                                            uint32_t step, bool store, uint32_t logtab, uint32_t exptab,
                                            const MathConst &mc, bool &rel_pending) {
     const uint32_t st = CT ? 4u * CT : step;
-    float h[U], v[U], db[U], dr[U], amp[U], q[U];
+    float h[U], v[U], db[U], dr[U], amp[U];
+    AmpFront af[U];  // fronts of the 10**x evaluations, issued inside the follower loops
     uint32_t spec = 0, mid = 0xffffffffu;
     bool bad = false;
 #pragma unroll
@@ -490,6 +466,9 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
     // its start <= -4, the envelopes stay <= -3.99 throughout (a step moves y towards x by a factor <= 1 up to
     // rounding), so one test per chunk is enough; anything else re-runs exactly.
     bad |= !((dbmax <= k.sliver_thr) & (L.yf <= k.sliver_thr) & (L.ys <= k.sliver_thr));
+    // floor invariant of the envelopes (every dB value is >= floor, a step moves y towards x): holds from the reset
+    // on, but a state injected through ofp_detector_set_state may violate it
+    bad |= !((L.yf >= k.floor_db) & (L.ys >= k.floor_db));
     // coef * d with coef = d > 0 ? att : rel is max(att * d, rel * d) for att >= rel >= 0 (rounding is monotone)
     // and -max(-att * d, -rel * d) for rel > att >= 0: the host passes (A, R, s) = (s att, s rel, s = +-1).
     // Below-floor chunks (iv) know more: x is the floor and y >= floor, so d = (floor - y) + 1e-10 <= 1e-10 and the
@@ -497,15 +476,15 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
     // (|coef d| < half an ulp), so y + rel * d is the reference's value unless d > 1e-7 -- flagged (an envelope one
     // rounding below the floor).
     if (OFP_K1_SKIPFOL && skip) {
-        // y >= floor at the start keeps y >= floor through the chunk (coefficients <= 1/2: a step covers at most
-        // half the distance, rounding is monotone and the floor is a float), so every d is <= 1e-10
-        bad |= !((L.yf >= k.floor_db) & (L.ys >= k.floor_db));
+        // y >= floor at the start (tested above) keeps y >= floor through the chunk (coefficients <= 1/2: a step
+        // covers at most half the distance, rounding is monotone and the floor is a float), so every d is <= 1e-10
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float d1 = __fadd_rn(__fsub_rn(k.floor_db, L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(k.floor_db, L.ys), 1e-10f);
             L.yf = __fadd_rn(L.yf, __fmul_rn(k.fr, d1));
             L.ys = __fadd_rn(L.ys, __fmul_rn(k.sr, d2));
             dr[u] = __fsub_rn(L.yf, L.ys);
+            af[u] = amp_front(dr[u]);
         }
     } else {
 #pragma unroll
@@ -519,6 +498,7 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
             L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
 #endif
             dr[u] = __fsub_rn(L.yf, L.ys);
+            af[u] = amp_front(dr[u]);
         }
     }
 #if OFP_K1_LADDER == 3  // + followers
@@ -528,10 +508,11 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
         if (store) sts_f32(rs + u * st, dr[u]);
     return bad;
 #endif
-    float qmax = 0.0f;
+    // |q| < 9.5 needs no test here: both envelopes stay within [floor, -3.99] through the chunk (floor invariant and
+    // sliver test above; the host only enables this path for floor >= -180 dB), so |dr| < 190
     mid = 0xffffffffu;
-    to_amp_vec<U>(dr, k.ceil_amp, exptab, mc, amp, q, qmax, mid);
-    bad |= amp_flagged(qmax, mid);
+    amp_back<U>(af, k.ceil_amp, exptab, mc, amp, mid);
+    bad |= amp_flagged(0.0f, mid);
 #if OFP_K1_LADDER >= 5  // 4: + 10**x only; 5 and above: the full chunk
     // max tracker, block extrema and the stores first: they overlap the drain of the 10**x pipeline that the
     // vote of short-cut (vi) has to wait for
@@ -726,13 +707,14 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
         }
         __syncwarp();
     }
-    const uint32_t box_bytes = static_cast<uint32_t>(G) * TC * 4u;
+    const int P = a.P;
+    const uint32_t box_bytes = static_cast<uint32_t>(G) * P * 4u;
     int32_t cnt = (a.cnt_in && active) ? a.on_cnt[rec] : 0;  // onsets emitted for this lane's recording
     int64_t blk = a.blk0;  // main-phase block index (global; a.blk0 != 0 when a recording is fed in segments)
 
     float *rcol = relbuf + g * a.stride_rel + c;  // this lane's column of the block buffer
     const uint32_t rcol_s = smem_u32(rcol);
-    const uint32_t stage0_s = smem_u32(stages) + 4u * (g * TC + c);
+    const uint32_t stage0_s = smem_u32(stages) + 4u * (g * P + c);
 
     bool rel_pending = false;  // a bulk copy of the block buffer to HBM is in flight (block_end)
     int s_cur = 0;             // ring position of the tile being consumed
@@ -771,8 +753,8 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                 // generic path (unaligned input): cooperative copy of the tile into stage 0
                 s = 0;
                 const int64_t row_elems = a.n_samples * C;
-                for (int idx = lane; idx < G * TC; idx += 32) {
-                    const int gi = idx / TC, e = idx - gi * TC;
+                for (int idx = lane; idx < G * P; idx += 32) {
+                    const int gi = idx / P, e = idx - gi * P;
                     const int64_t col = static_cast<int64_t>(t0) * C + e;
                     float v = 0.f;
                     if (rec0 + gi < a.R && col < row_elems) v = a.x[(rec0 + gi) * a.rec_stride + col];
@@ -988,6 +970,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
         const float cf[4] = {p.fast_att, p.fast_rel, p.slow_att, p.slow_rel};
         a.fast_ok = 1;
         for (float c : cf) a.fast_ok &= (c > 0.0f && c <= 0.5f) ? 1 : 0;
+        a.fast_ok &= (p.floor_db >= -180.0f && p.floor_db <= -4.0f) ? 1 : 0;
     }
     a.blk0 = blk0; a.cnt_in = cnt_in ? 1 : 0;
     a.st = state_of(det);
@@ -1001,8 +984,18 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.T = pick_tile(C, env_int("OFP_K1_TILECAP", 48), (B % KU == 0) ? KU : 1);
     OFP_REQUIRE(a.T > 0, "no valid tile length for %d channels", C);
     a.TC = a.T * C;
+    {
+        // pad the rows of a stage so that the G rows start 4 banks apart (the per-sample LDS of a warp touches one
+        // word per lane: rows starting in the same bank conflict); the TMA box simply reads the extra columns
+        const int want = ((C + 3) / 4 * 4) % 32;
+        int pad = ((want - a.TC % 32) + 32) % 32;
+        // off by default: at T = 40 the padded stages cost the seventh resident CTA per SM (84 vs 59 ms) and the
+        // 3-way conflicts of the unpadded rows are not visible in the kernel time; T = 32 padded is equally fast
+        if (!env_int("OFP_K1_PAD", 0) || a.TC + pad > 256 || (a.TC + pad) % 4 != 0) pad = 0;
+        a.P = a.TC + pad;
+    }
     a.nst = std::max(2, std::min(8, env_int("OFP_K1_STAGES", 2)));
-    const int stage_bytes = (a.G * a.TC * 4 + 127) / 128 * 128;
+    const int stage_bytes = (a.G * a.P * 4 + 127) / 128 * 128;
     a.stage_floats = stage_bytes / 4;
     const bool tma_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (a.R == 1 || rec_stride % 4 == 0) &&
                         (n_samples * C < (1ll << 31)) && !env_int("OFP_K1_NO_TMA", 0);
@@ -1021,7 +1014,7 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
         const uint64_t stride1 = a.R == 1 ? static_cast<uint64_t>((n_samples * C * 4 + 15) / 16 * 16)
                                           : static_cast<uint64_t>(rec_stride) * 4;
         int rc = encode_tmap_2d_f32(&tmap, x, static_cast<uint64_t>(n_samples) * C, static_cast<uint64_t>(a.R),
-                                    stride1, static_cast<uint32_t>(a.TC), static_cast<uint32_t>(a.G));
+                                    stride1, static_cast<uint32_t>(a.P), static_cast<uint32_t>(a.G));
         if (rc != OFP_OK) return rc;
     }
     { int rc = upload_tables(); if (rc != OFP_OK) return rc; }
