@@ -452,9 +452,38 @@ def run_e2e(args, torch, hp, x, dist=None, world=1, rank=0):
     modes = ["onsets_only"] if args.no_rel else ["onsets_only", "drop_in"]
     fit = int(0.55 * avail / (per_rec * (2 if "drop_in" in modes else 1)))
     Re = max(1, min(want, R, fit))
+    from onset_fingerprinting_b200 import parallel
+
+    numa = parallel.bind_to_gpu_numa(torch.cuda.current_device())  # before the pinned buffers are first touched
     xh = torch.empty((Re, N, Cn), dtype=torch.float32, pin_memory=True)
     xh.copy_(x[:Re])
     torch.cuda.synchronize()
+    # Denominator of the end-to-end figure: a plain pinned cudaMemcpyAsync of the same bytes, every rank at the same
+    # time (what the host side and the PCIe links sustain with N uploads in flight), H2D alone and H2D + D2H together.
+    ceil = {}
+    scratch = xd_like = x[:Re]  # the upload lands in the resident device copy itself (same bytes): no extra HBM
+    side = torch.cuda.Stream()
+    for name, both in (("h2d", False), ("h2d_d2h", True)):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        scratch.copy_(xh, non_blocking=True)
+        if both:
+            with torch.cuda.stream(side):
+                xh2 = ceil.setdefault("_buf", torch.empty((min(Re, 1024), N, Cn), dtype=torch.float32, pin_memory=True))
+                for lo in range(0, Re, xh2.shape[0]):  # the D2H stream lands in a small pinned buffer (host memory)
+                    n = min(xh2.shape[0], Re - lo)
+                    xh2[:n].copy_(xd_like[lo:lo + n], non_blocking=True)
+        torch.cuda.synchronize()
+        dtc = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dtc], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtc = float(t.item())
+        ceil[name + "_gbs_per_rank"] = xh.numel() * 4 / dtc / 1e9
+        ceil[name + "_ms"] = dtc * 1e3
+    ceil.pop("_buf", None)
     hp_e = hp if Re == R else None
     if hp_e is None:
         from onset_fingerprinting_b200 import pipeline, synth
@@ -490,7 +519,10 @@ def run_e2e(args, torch, hp, x, dist=None, world=1, rank=0):
             "d2h_bytes_per_step": head["d2h_bytes_per_step"], "ms": head["ms"], "recordings": world * Re,
             "recordings_of_batch": f"{Re} of {R} per GPU" + ("" if Re == R else " (host memory bound)"),
             "mode": "onsets_only" if args.no_rel else "drop_in (rel envelope copied back to the host)",
-            "modes": res, "stages": "upload + detector + grouping + lag refinement + multilateration + results to host",
+            "modes": res, "numa": numa, "plain_copy_ceiling": ceil,
+            "vs_plain_copy": {m: r["h2d_gbs_per_rank"] / ceil["h2d_d2h_gbs_per_rank" if m == "drop_in" else "h2d_gbs_per_rank"]
+                              for m, r in res.items()},
+            "stages": "upload + detector + grouping + lag refinement + multilateration + results to host",
             "entry": "pipeline.HotPath.run_host (one call per rank, concurrently): ofp_copy2d_async + ofp_detect_offline / "
                      "ofp_detect_continue per time segment, then ofp_group_onsets / ofp_fix_onsets_ex / ofp_locate_hits"}
 

@@ -38,6 +38,15 @@
 #ifndef OFP_K1_SPARSE  // short-cut (v) of chunk_fast, switchable for A/B builds
 #define OFP_K1_SPARSE 1
 #endif
+#ifndef OFP_K1_KQF  // 10**x: k by a float32 magic-constant add (+ one conversion) instead of a double one
+#define OFP_K1_KQF 0  // measured: 59.1 ms with the conversion, 57.9 ms without (the XU pipe is the busier resource)
+#endif
+#ifndef OFP_K1_ICVT_IN  // 10**x: double(q) by integer operations instead of F2F
+#define OFP_K1_ICVT_IN 0
+#endif
+#ifndef OFP_K1_ICVT_OUT  // 10**x: float32 rounding of the result by integer operations instead of F2F
+#define OFP_K1_ICVT_OUT 0
+#endif
 #ifndef OFP_K1_KMAGIC  // log10: exponent -> double by a magic-constant subtraction instead of I2F
 #define OFP_K1_KMAGIC 1
 #endif
@@ -297,12 +306,26 @@ __device__ __forceinline__ AmpFront amp_front(float dr) {
     AmpFront f;
     const float q0 = __fmul_rn(dr, 0.05f);
     f.q = __fmaf_rn(__fmaf_rn(-20.0f, q0, dr), 0.05f, q0);
+#if OFP_K1_ICVT_IN
+    {   // zero / denormal q become 2^-127-sized doubles: harmless; inf / nan are excluded by the |q| bound
+        const uint32_t qb = __float_as_uint(f.q);
+        const uint32_t hi = (((qb & 0x7fffffffu) >> 3) + 0x38000000u) | (qb & 0x80000000u);
+        f.qd = __hiloint2double(static_cast<int>(hi), static_cast<int>(qb << 29));
+    }
+#else
     f.qd = static_cast<double>(f.q);
+#endif
     // the integer k sits in the low mantissa bits of the sum; a k that is off by one near a tie only makes |rr|
     // 2^-19 larger
+#if OFP_K1_KQF
     const float kf0 = __fmaf_rn(f.q, OFP_LOG2_10_F, OFP_EXP_MAGIC_F);
     f.ki = __float_as_uint(kf0);
     f.kq = static_cast<double>(__fsub_rn(kf0, OFP_EXP_MAGIC_F));
+#else  // the same in double: one conversion less, one more FP64 issue slot
+    const double kd0 = __fma_rn(f.qd, OFP_LOG2_10, 0x1.8p52 / static_cast<double>(1 << OFP_EXP_N));
+    f.ki = static_cast<uint32_t>(__double2loint(kd0));
+    f.kq = __dsub_rn(kd0, 0x1.8p52 / static_cast<double>(1 << OFP_EXP_N));
+#endif
     return f;
 }
 // Back of the evaluation for U samples, step-major (every elementary operation is issued for all U samples before
@@ -326,8 +349,20 @@ __device__ __forceinline__ void amp_back(const AmpFront (&f)[U], float ceil_amp,
     for (int u = 0; u < U; ++u) y[u] = __fma_rn(s1[u], pp[u], sc[u]);  // in (0.99, 2.01)
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+#if OFP_K1_ICVT_OUT
+        // + 2^28 in the low word (half a float32 ulp), carry into the high word together with the exponent rebias
+        // 1023 -> 127 (0x08000000 << 3 == -896 << 23 mod 2^32), funnel shift: round-to-nearest-even except on exact
+        // ties, which the window excludes
+        uint32_t lo2, hi2;
+        asm("add.cc.u32 %0, %2, 0x10000000;\n\taddc.u32 %1, %3, 0x08000000;"
+            : "=r"(lo2), "=r"(hi2)
+            : "r"(static_cast<uint32_t>(__double2loint(y[u]))), "r"(static_cast<uint32_t>(__double2hiint(y[u]))));
+        fb[u] = __funnelshift_l(lo2, hi2, 3) + ((f[u].ki & ~((1u << OFP_EXP_N) - 1u)) << (23 - OFP_EXP_N));
+        mid = min(mid, (lo2 << 3) + (OFP_EXP_WIN << 3));
+#else
         fb[u] = __float_as_uint(__double2float_rn(y[u])) + ((f[u].ki & ~((1u << OFP_EXP_N) - 1u)) << (23 - OFP_EXP_N));
         mid = min(mid, (static_cast<uint32_t>(__double2loint(y[u])) << 3) + ((0x10000000u + OFP_EXP_WIN) << 3));
+#endif
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) amp[u] = fminf(__fsub_rn(__uint_as_float(fb[u]), 1e-10f), ceil_amp);
