@@ -65,8 +65,14 @@ struct K4Args {
 // v32 + delta >= max_w (v32 - delta).  The true first maximum is always among them.  One survivor
 // (the usual case) IS the answer; a handful are recomputed exactly, one thread each, and compared
 // with np.argmax's tie rule; more than CAND_CAP, or non-finite data, falls back to cc_argmax.
-constexpr int LPF = 9;       // lags per thread (odd: conflict-free x reads across lanes)
-constexpr int CCF_UN = 8;    // time steps per unrolled iteration
+#ifndef OFP_K4_LPF
+#define OFP_K4_LPF 9
+#endif
+#ifndef OFP_K4_CCF_UN
+#define OFP_K4_CCF_UN 8
+#endif
+constexpr int LPF = OFP_K4_LPF;        // lags per thread (odd: conflict-free x reads across lanes)
+constexpr int CCF_UN = OFP_K4_CCF_UN;  // time steps per unrolled iteration
 constexpr int XPAD = 16;     // zeros on both sides of the float copy of x
 constexpr int CAND_CAP = 32;
 

@@ -812,12 +812,9 @@ extern "C" int ofp_stream_locate_ring_dev(const double *sensor_xyz_dev, int32_t 
     a.ring = ring_dev; a.ring_rows = ring_rows; a.block = block_size; a.tol = onset_tolerance; a.cutoff = normalization_cutoff;
     constexpr int WARPS = 4;
     const size_t smem = static_cast<size_t>(WARPS) * 2 * SL_LMAX * sizeof(double);
-    static bool attr_set = false;  // per process is enough: the attribute is per function and device-independent here
-    if (!attr_set) {
-        OFP_CUDA_CHECK(cudaFuncSetAttribute(k5_stream_locate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(smem)));
-        attr_set = true;
-    }
+    // (set on every launch: the attribute belongs to the function ON THE CURRENT DEVICE, and a process may drive several)
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(k5_stream_locate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
     k5_stream_locate<true><<<(n_streams + WARPS - 1) / WARPS, 32 * WARPS, smem, static_cast<cudaStream_t>(stream)>>>(a);
     k_advance_index<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(current_index_dev, advance);
     OFP_CUDA_CHECK(cudaGetLastError());

@@ -434,11 +434,13 @@ _DIRECTION = {None: 0, "up": 1, "down": 2}
 
 def find_onset_groups_batch(channels, onsets, counts, n_channels: int, max_distance: int = 1000,
                             min_channels: int = 3, close_channel: Optional[int] = None,
-                            max_groups: Optional[int] = None):
+                            max_groups: Optional[int] = None, with_span: bool = False):
     """find_onset_groups for every recording of a batch on the device.
     channels/onsets [R, cap] int32 and counts [R] int32 as returned by detect_onsets_amplitude_batch.
     Returns (hit_rec [H] int32, hit_onsets [H, C] int32, n_groups [R] int32): the groups of all
-    recordings concatenated in recording order (rows may contain -1 for a missing channel)."""
+    recordings concatenated in recording order (rows may contain -1 for a missing channel).
+    with_span: also return the largest onset spread over the complete groups (what sizes the sections of
+    fix_onsets_batch) -- it rides on the same host round trip as the hit count, so a pass has ONE."""
     torch = _lib.require_cuda()
     R, cap = channels.shape
     if max_groups is None:
@@ -451,13 +453,29 @@ def find_onset_groups_batch(channels, onsets, counts, n_channels: int, max_dista
                                       C.c_int32(max_groups), ptr(groups), ptr(ng), stream_ptr()))
     kept = torch.clamp(ng, max=max_groups).to(torch.int64)
     offsets = torch.cumsum(kept, 0) - kept
-    H = int(kept.sum().item())
+    span = 0
+    if with_span:
+        valid = torch.arange(max_groups, device="cuda")[None, :] < kept[:, None]
+        mn, mx = groups.min(2).values, groups.max(2).values
+        spread = torch.where(valid & (mn >= 0), mx - mn, torch.zeros_like(mx)).max().to(torch.int64)
+        H, span = (int(v) for v in torch.stack([kept.sum(), spread]).tolist())
+    else:
+        H = int(kept.sum().item())
     hit_rec = torch.empty((H,), dtype=torch.int32, device="cuda")
     hit_on = torch.empty((H, n_channels), dtype=torch.int32, device="cuda")
     if H:
         check(_lib.lib().ofp_compact_groups(ptr(groups), ptr(ng), ptr(offsets), C.c_int32(R), C.c_int32(max_groups),
                                             C.c_int32(n_channels), ptr(hit_rec), ptr(hit_on), stream_ptr()))
+    if with_span:
+        return hit_rec, hit_on, ng, span
     return hit_rec, hit_on, ng
+
+
+def section_budget(max_section: int, n_channels: int) -> int:
+    """Section length a K4 CTA can hold: longer sections are flagged OFP_FIX_TOO_LONG.  When the [L, C] section does
+    not fit, the kernel keeps two channel columns instead (column mode): 16 + 8 + 8 + 8 B per sample."""
+    budget = max((200 * 1024 - 128) // (16 + 8 * n_channels), (200 * 1024 - 16 * 1024) // 40)
+    return min(int(max_section), budget)
 
 
 def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 0, onset_direction=None,
@@ -482,11 +500,7 @@ def fix_onsets_batch(audio, hit_rec, hit_onsets, filter_size: int = 5, d: int = 
         if H:  # largest onset spread over the complete groups: one small reduction, one host round trip
             mn, mx = hit_onsets.min(1).values, hit_onsets.max(1).values
             span = int(torch.where(mn >= 0, mx - mn, torch.zeros_like(mx)).max().item())
-        max_section = N if to_end else span + 2 * look + 1
-        # shared-memory budget of one CTA; longer sections are flagged OFP_FIX_TOO_LONG.  When the [L, C] section
-        # does not fit, the kernel keeps two channel columns instead (column mode): 16 + 8 + 8 + 8 B per sample.
-        budget = max((200 * 1024 - 128) // (16 + 8 * Cn), (200 * 1024 - 16 * 1024) // 40)
-        max_section = min(max_section, budget)
+        max_section = section_budget(N if to_end else span + 2 * look + 1, Cn)
     out = torch.empty_like(hit_onsets)
     lags = torch.empty_like(hit_onsets)
     status = torch.empty((H,), dtype=torch.int32, device="cuda")

@@ -259,7 +259,6 @@ class Multilaterate3D:
                 self.max_lags[i][j] = np.nanmax(lm)
                 self.min_lags[i][j] = np.nanmin(lm)
         self.max_max_lags = [np.nanmax(list(d.values())) for d in self.max_lags]
-        self.ongoing = []
         # device copies for K5
         M = self.lag_maps[0][1].shape[0]
         maps = np.full((S, S, M, M), np.nan, np.float32)
@@ -344,77 +343,135 @@ class Multilaterate3D:
                                       self.sensor_locs[sensors[0]], d_a1 / self.sr * self.c, d_b1 / self.sr * self.c,
                                       initial_guess)
 
-    def _refine_pair(self, rec_audio, first_sensor, sensor_index, last_onset, onset_index):
-        """The ring-buffer refinement of locate (multilateration.py:457-501): median 5 -> first
-        difference -> falling flanks only -> bounded-lag cross-correlation (tol 50, cutoff 10) ->
-        adjust_onset, on the section from lookaround + 1 samples before the group's first onset to the
-        newest sample.  One K4 launch on the two columns.  Returns (new_lag | None, change_first, change_new)."""
-        from . import detection
+    # -- streaming form: the group state machine lives on the device ------------------------------------
+    _SL_GMAX, _SL_LEN = 16, 4  # csrc/multilaterate.cu: groups kept per stream, members kept per group
 
+    def _stream(self):
+        """Device state of the streaming contract for ONE stream (the realtime sessions hold S of them):
+        the `ongoing` group lists (csrc/multilaterate.cu:k5_stream_locate), one detection slot, the results."""
+        st = getattr(self, "_sl", None)
+        if st is None:
+            torch = self.torch
+            sizes = [C.c_int64() for _ in range(4)]
+            check(_lib.lib().ofp_stream_locate_state_bytes(C.c_int32(1), *[C.byref(v) for v in sizes]))
+            st = self._sl = {
+                "state": [torch.zeros((v.value,), dtype=torch.uint8, device="cuda") for v in sizes],
+                "det": torch.zeros((3, 32), dtype=torch.int32, device="cuda"),  # channel / delta / count rows
+                "det_h": torch.zeros((3, 32), dtype=torch.int32).pin_memory(),
+                "cur": torch.zeros((1,), dtype=torch.int64, device="cuda"),
+                "xy": torch.empty((1, 2), dtype=torch.float64, device="cuda"),
+                "found": torch.empty((1,), dtype=torch.int32, device="cuda"),
+                "ring": None, "ring_count": 0, "ring_src": None,
+            }
+        return st
+
+    @property
+    def ongoing(self):
+        """The reference's list of (sensors, onsets) groups, decoded from the device state."""
+        st = getattr(self, "_sl", None)
+        if st is None:
+            return []
+        cnt, ln, sen, ons = (t.cpu().numpy() for t in st["state"])
+        ng = int(cnt.view(np.int32)[0]) & 0xff
+        ln, sen, ons = ln.view(np.int32), sen.view(np.int32), ons.view(np.int64)
+        out = []
+        for g in range(ng):
+            k = int(ln[g]) & 0xff
+            out.append(([int(v) for v in sen[g * self._SL_LEN:g * self._SL_LEN + k]],
+                        [int(v) for v in ons[g * self._SL_LEN:g * self._SL_LEN + k]]))
+        return out
+
+    @ongoing.setter
+    def ongoing(self, groups):
+        """``m.ongoing = []`` (the reference's reset) or an explicit list of (sensors, onsets) groups; equal
+        neighbouring groups are taken to be the same tuple, as the reference's own lists hold them."""
+        groups = list(groups)
+        if not groups and getattr(self, "_sl", None) is None:
+            return
+        if len(groups) > self._SL_GMAX or any(len(g[0]) > self._SL_LEN for g in groups):
+            raise ValueError(f"at most {self._SL_GMAX} groups of {self._SL_LEN} members")
+        st = self._stream()
+        ln = np.zeros(self._SL_GMAX, np.int32)
+        sen = np.full(self._SL_GMAX * self._SL_LEN, -1, np.int32)
+        ons = np.zeros(self._SL_GMAX * self._SL_LEN, np.int64)
+        uid = 0
+        for g, (ss, oo) in enumerate(groups):
+            if g and (list(ss), list(oo)) != (list(groups[g - 1][0]), list(groups[g - 1][1])):
+                uid += 1
+            ln[g] = len(ss) | (uid << 8)
+            sen[g * self._SL_LEN:g * self._SL_LEN + len(ss)] = ss
+            ons[g * self._SL_LEN:g * self._SL_LEN + len(oo)] = oo
+        cnt = np.asarray([len(groups) | ((uid + 1) << 8)], np.int32)
+        for t, v in zip(st["state"], (cnt, ln, sen, ons)):
+            t.copy_(self.torch.from_numpy(v.view(np.uint8)))
+
+    def _mirror_ring(self, st, rec_audio):
+        """Keep a device copy of rec_audio in the layout the kernel reads (row = sample index % rows): only the
+        rows written since the last call are copied."""
         torch = self.torch
-        i = rec_audio.counter - last_onset + lookaround
-        section = rec_audio[-i - 1:]
-        if isinstance(section, np.ndarray):
-            section = torch.from_numpy(np.ascontiguousarray(section[:, [first_sensor, sensor_index]], np.float32)).cuda()
-        else:
-            section = section[:, [first_sensor, sensor_index]].to(device="cuda", dtype=torch.float32)
-        section = section.contiguous()[None]
-        on = torch.tensor([[lookaround, lookaround + (onset_index - last_onset)]], dtype=torch.int32)
-        out, lags, st = detection.fix_onsets_batch(section, None, on, filter_size=5, d=1, onset_direction="down",
-                                                   take_abs=True, normalization_cutoff=NORM_CUTOFF,
-                                                   onset_tolerance=ONSET_TOL, to_end=True)
-        code = int(st[0].item())
-        if code == 2:
-            raise ValueError("operands could not be broadcast together (adjust_onset, detection.py:335)")
-        if code != 0:
-            return None, 0, 0
-        lag = int(lags[0, 1].item())
-        if lag == detection.LAG_NONE:
-            return None, 0, 0
-        o = out[0].cpu().tolist()
-        return lag, o[0] - lookaround, o[1] - (lookaround + (onset_index - last_onset))
+        NR = int(rec_audio.N)
+        probe = rec_audio[-1:]
+        Cn = int(probe.shape[1])
+        if st["ring"] is None or st["ring_src"] is not rec_audio or tuple(st["ring"].shape) != (1, NR, Cn) \
+                or rec_audio.counter < st["ring_count"]:
+            st["ring"] = torch.zeros((1, NR, Cn), dtype=torch.float32, device="cuda")
+            st["ring_count"], st["ring_src"] = 0, rec_audio
+        k = min(int(rec_audio.counter) - st["ring_count"], NR)
+        if k > 0:
+            new = rec_audio[-k:]
+            new = torch.from_numpy(np.ascontiguousarray(new, np.float32)).cuda() if isinstance(new, np.ndarray) \
+                else new.to(device="cuda", dtype=torch.float32)
+            rows = (torch.arange(int(rec_audio.counter) - k, int(rec_audio.counter), device="cuda") % NR)
+            st["ring"][0, rows] = new
+        st["ring_count"] = int(rec_audio.counter)
+        return NR, Cn
 
     def locate(self, sensor_index: int, onset_index: int, rec_audio=None):
         """multilateration.py:428-534, streaming contract: feed detections one at a time, get (x, y)
         in cm when a third legal sensor completes a group, else None.  rec_audio: a ring of the most
-        recent audio rows (``counter`` = rows written so far, ``ring[-k:]`` = last k rows in time
+        recent audio rows (``counter`` = rows written so far, ``N`` rows, ``ring[-k:]`` = last k rows in time
         order; realtime.audio.DeviceRing or loopmate's CircularArray) enables the cross-correlation
-        refinement of each new pair."""
-        new_groups = []
-        for group in self.ongoing:
-            lag = onset_index - group[1][0]
-            if lag > self.max_max_lags[group[0][0]]:
-                continue
-            if lag < 0:  # an adjustment moved an onset behind the next one (multilateration.py:443-449)
-                inter = (group[0][0], group[1][0])
-                group[0][0], group[1][0] = sensor_index, onset_index
-                sensor_index, onset_index = inter
-                lag = -lag
-            if sensor_index not in group[0]:
-                if rec_audio is not None:
-                    new_lag, co, cn = self._refine_pair(rec_audio, group[0][0], sensor_index, group[1][0], onset_index)
-                    if new_lag is not None:
-                        lag = new_lag
-                        group[1][0] += co
-                        onset_index += cn
-                if self.is_legal(group[0][0], sensor_index, lag):
-                    group = (group[0] + [sensor_index], group[1] + [onset_index])
-                    if len(group[0]) == 3:
-                        if group[0][0] == group[0][1]:
-                            break
-                        res = self.is_legal_3d(group)
-                        if res != (0, 0):
-                            res = self.trilaterate(group, initial_guess=np.array(res) - self.radius)
-                            if res is not None:
-                                new_groups = remove_seed(new_groups, group)
-                            self.ongoing = new_groups
-                            return res
-                    new_groups.append(group)
-            if lag <= self.max_max_lags[group[0][0]]:
-                new_groups.append(group)
-        new_groups.append(([sensor_index], [onset_index]))
-        self.ongoing = new_groups
-        return None
+        refinement of each new pair (multilateration.py:457-501).
+
+        One launch of the device state machine that the realtime sessions run for thousands of streams
+        (ofp_stream_locate / ofp_stream_locate_ring_dev with one stream and one detection); the group lists
+        stay on the device (`ongoing` decodes them)."""
+        if self.model is not None:
+            raise NotImplementedError("streaming locate with a model: use locate_batch / trilaterate (the model "
+                                      "bypass of multilateration.py:553-557 is built for complete groups)")
+        st = self._stream()
+        L = _lib.lib()
+        h = st["det_h"]
+        h[0, 0], h[1, 0], h[2, 0] = int(sensor_index), 0, 1
+        st["det"].copy_(h, non_blocking=True)
+        geo = (ptr(self._locs), C.c_int32(self._S), ptr(self._maps), C.c_int32(self._M), ptr(self._mx), ptr(self._mn),
+               ptr(self._mm), C.c_double(self.radius), C.c_double(self.samples_per_cm), C.c_double(self.sr),
+               C.c_double(self.c))
+        state = [ptr(t) for t in st["state"]]
+        if rec_audio is None:
+            check(L.ofp_stream_locate(*geo, C.c_int32(1), C.c_int32(32), ptr(st["det"][0]), ptr(st["det"][1]),
+                                      ptr(st["det"][2]), C.c_int64(int(onset_index)), *state, ptr(st["xy"]),
+                                      ptr(st["found"]), stream_ptr()))
+        else:
+            NR, Cn = self._mirror_ring(st, rec_audio)
+            written = int(rec_audio.counter) - int(onset_index)  # rows of the ring after the detection's own
+            if not 1 <= written <= NR:
+                raise ValueError("the detection lies outside the ring buffer")
+            st["cur"].fill_(int(onset_index))
+            check(L.ofp_stream_locate_ring_dev(*geo, C.c_int32(1), C.c_int32(Cn), ptr(st["det"][0]), ptr(st["det"][1]),
+                                               ptr(st["det"][2]), ptr(st["cur"]), C.c_int32(0), ptr(st["ring"]),
+                                               C.c_int32(NR), C.c_int32(written), C.c_int32(ONSET_TOL),
+                                               C.c_int32(NORM_CUTOFF), *state, ptr(st["xy"]), ptr(st["found"]),
+                                               stream_ptr()))
+        found = int(st["found"].item())
+        if found == -2:
+            raise ValueError("operands could not be broadcast together (adjust_onset, detection.py:335)")
+        if found == -1:
+            raise RuntimeError("streaming locate: more than 16 ongoing groups / 4 members, or a refinement section "
+                               "longer than 1024 samples")
+        if found != 1:
+            return None
+        return tuple(st["xy"][0].cpu().tolist())
 
 
 class Multilaterate:

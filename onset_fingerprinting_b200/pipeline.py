@@ -4,7 +4,8 @@
 
 which is what the reference's notebooks run per recording in Python (notebooks/refresh.org:149-172,
 1507-1509) and what PlayRec.detect_hits runs per block (realtime/audio.py:62-74).  Everything stays
-on the device; the only host round trip is the hit count (one integer) that sizes the K4/K5 launches.
+on the device; the only host round trip is ONE pair of integers (hit count and largest onset spread) that
+sizes the K4/K5 launches.
 """
 from __future__ import annotations
 
@@ -74,12 +75,19 @@ class HotPath:
         ch, ix, cnt, rel = self.det.detect_offline(x, warm_n, out=self._out)
         if k1_events is not None:
             k1_events[1].record()
-        hit_rec, hit_on, _ = detection.find_onset_groups_batch(ch, ix, cnt, C, **self.group_kw)
-        # sections are sized by the largest onset spread actually present (one tiny reduction + host round
-        # trip): the shared memory of a K4 CTA -- and with it how many hits an SM works on -- follows it
-        fixed, lags, fstat = detection.fix_onsets_batch(x, hit_rec, hit_on, **self.fix_kw)
+        hit_rec, hit_on, _, span = detection.find_onset_groups_batch(ch, ix, cnt, C, with_span=True, **self.group_kw)
+        # sections are sized by the largest onset spread actually present (the shared memory of a K4 CTA -- and
+        # with it how many hits an SM works on -- follows it); the spread comes back with the hit count
+        fixed, lags, fstat = self._fix(x, hit_rec, hit_on, span)
         xy, lstat = self.ml.locate_batch(fixed)
         return HitBatch(hit_rec, hit_on, fixed, lags, fstat, xy, lstat, cnt, rel)
+
+    def _fix(self, x, hit_rec, hit_on, span):
+        kw = dict(self.fix_kw)
+        if "max_section" not in kw and not kw.get("to_end", False):
+            look = kw.get("normalization_cutoff", 10) + kw.get("onset_tolerance", 30)
+            kw["max_section"] = detection.section_budget(span + 2 * look + 1, x.shape[2])
+        return detection.fix_onsets_batch(x, hit_rec, hit_on, **kw)
 
     # -- host buffers in, host results out -------------------------------------------------------------
     def run_host(self, x_host, rel_host=None, x_dev=None, warm_n: Optional[int] = None, segment: int = 49152):
@@ -151,8 +159,8 @@ class HotPath:
                                                   C.c_void_p(rel.data_ptr() + 4 * t0 * Cn), C.c_size_t(4 * rel.stride(0)),
                                                   C.c_size_t(4 * blocks * B * Cn), C.c_size_t(R), C.c_int(1), _lib.stream_ptr()))
             t0 += ln
-        hit_rec, hit_on, _ = detection.find_onset_groups_batch(ch, ix, cnt, Cn, **self.group_kw)
-        fixed, lags, fstat = detection.fix_onsets_batch(x_dev, hit_rec, hit_on, **self.fix_kw)
+        hit_rec, hit_on, _, span = detection.find_onset_groups_batch(ch, ix, cnt, Cn, with_span=True, **self.group_kw)
+        fixed, lags, fstat = self._fix(x_dev, hit_rec, hit_on, span)
         xy, lstat = self.ml.locate_batch(fixed)
         out = {}
         for name, t in (("rec", hit_rec), ("onsets", hit_on), ("fixed", fixed), ("lags", lags), ("fix_status", fstat),
