@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--hits", type=int, default=1000000, help="hits16: number of hits (over all GPUs)")
     ap.add_argument("--streams", type=int, default=4096, help="realtime: concurrent streams per GPU")
     ap.add_argument("--blocks", type=int, default=1000, help="realtime: consecutive blocks")
+    ap.add_argument("--ring-rows", type=int, default=2048, help="realtime: rows of recent audio kept per stream for the "
+                                                                "ring-buffer refinement leg")
     return ap.parse_args()
 
 
@@ -628,6 +630,12 @@ def hits16_leg(args, torch, dist, world, rank, local, hits_total, steps, warmup)
     ok = int((st == 0).sum().item()); loc = int((lst == 0).sum().item())
     if dist is not None:
         t = torch.tensor([ok, loc], device="cuda"); dist.all_reduce(t); ok, loc = (int(v) for v in t.tolist())
+    # How far fix_onsets moves the REFERENCE (first-arriving) channel's onset over the 15 pairs of a hit:
+    # the reason the pairs of a hit cannot share one lag window, i.e. one batched (tensor-core) contraction.
+    ref = torch.argmin(onsets, dim=1, keepdim=True)
+    dr = (torch.gather(fixed, 1, ref) - torch.gather(onsets, 1, ref)).abs().float().flatten()[st == 0]
+    drift = {"mean_abs": float(dr.mean()), "p50": float(dr.median()), "p90": float(dr.quantile(0.9)),
+             "max": float(dr.max()), "frac_above_tol": float((dr > tol).float().mean())} if dr.numel() else None
     import ctypes as C
     from onset_fingerprinting_b200 import _lib
     cs = (C.c_uint64 * 4)()
@@ -658,7 +666,8 @@ def hits16_leg(args, torch, dist, world, rank, local, hits_total, steps, warmup)
                      "note": "K4 at 16 ch is instruction bound (median filter, section preparation, float32 "
                              "lag screening, reductions), not HBM bound"},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * steps, "clocks": clk.summary(),
-        "fix_ok": ok, "located": loc, "cc_screening": screen, "parity_sample": parity}
+        "fix_ok": ok, "located": loc, "cc_screening": screen, "parity_sample": parity,
+        "ref_onset_drift": drift}
 
 
 def hits16_parity(x, onsets, fixed, lags, st, first3, xy, lst, n):
@@ -979,6 +988,21 @@ def run_realtime(args):
 
     ho = drive(host_step, rs.reset)
     assert py["located"] == gr["located"] == ho["located"], (py["located"], gr["located"], ho["located"])
+    # (d) what the reference's callback actually runs (realtime/audio.py:69 passes rec_audio): every new pair is
+    # refined by cross-correlation on the stream's ring of recent audio (multilateration.py:457-501)
+    rr = rt.RealtimeSession(S, conf, ring_rows=args.ring_rows)
+
+    def ring_step(b):
+        xy, found = rr.detect_hits(x[:, b * BLOCK:(b + 1) * BLOCK])
+        return int((found == 1).sum())
+
+    rg = drive(ring_step, rr.reset)
+
+    def ring_host_step(b):
+        xy, found = rr.detect_hits(xh[b])
+        return int((found == 1).sum())
+
+    rh = drive(ring_host_step, rr.reset)
     units = S * nblk * BLOCK * N_CH
     print(json.dumps({
         "metric": "channel-samples/sec, realtime block streams", "value": units / gr["total_s"],
@@ -987,6 +1011,11 @@ def run_realtime(args):
         "config": {"workload": f"configs[3]: {S} concurrent 3-mic streams, {BLOCK}-sample blocks, realtime detector "
                                "settings, detector + streaming locate per block, one replayed CUDA graph per block"},
         "latency_us": {"p50": gr["p50"], "p99": gr["p99"], "budget_us": 1e6 * BLOCK / SR},
+        "with_ring_refinement": {"note": "locate(..., rec_audio): per-stream device ring of %d rows, bounded-lag CC + "
+                                         "adjust_onset for every new pair, one warp per stream" % args.ring_rows,
+                                 "value": units / rg["total_s"], "ms_per_step": rg["ms_per_block"],
+                                 "latency_us": {"p50": rg["p50"], "p99": rg["p99"]}, "located_hits": rg["located"],
+                                 "e2e": {"value": units / rh["total_s"], "latency_us": {"p50": rh["p50"], "p99": rh["p99"]}}},
         "python_driven": {"value": units / py["total_s"], "latency_us": {"p50": py["p50"], "p99": py["p99"]},
                           "ms_per_step": py["ms_per_block"]},
         "located_hits": gr["located"], "localised_hits_per_sec": gr["located"] / gr["total_s"],

@@ -111,7 +111,7 @@ struct K1Args {
     int32_t R, G, T, TC, nst, stage_floats, stride_rel, rel_vec_ok;
     int32_t P;  // row pitch of a stage in floats: TC + padding columns (the TMA box is P wide, tiles advance by TC)
     int32_t floor_skip;  // OFP_K1_FLOOR_SKIP=0 disables the below-floor short-cut (A/B runs)
-    int32_t fast_ok;     // follower coefficients in (0, 1/2]: the straight-line chunk's short-cuts are proven for those
+    int32_t fast_ok;     // follower coefficients in range: the straight-line chunk's short-cuts are proven for those
     int32_t cnt_in;      // continue: the per-recording onset counts in on_cnt are the starting fill levels
     int64_t blk0;        // continue: global index of the first block of this call (x / rel start there)
 };
@@ -507,12 +507,11 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
     // coef * d with coef = d > 0 ? att : rel is max(att * d, rel * d) for att >= rel >= 0 (rounding is monotone)
     // and -max(-att * d, -rel * d) for rel > att >= 0: the host passes (A, R, s) = (s att, s rel, s = +-1).
     // Below-floor chunks (iv) know more: x is the floor and y >= floor, so d = (floor - y) + 1e-10 <= 1e-10 and the
-    // release coefficient applies; for 0 < d <= 1e-7 either coefficient (both <= 1) leaves y <= -3.99 unchanged
-    // (|coef d| < half an ulp), so y + rel * d is the reference's value unless d > 1e-7 -- flagged (an envelope one
-    // rounding below the floor).
+    // release coefficient applies; d > 0 only for y == floor, where either coefficient (<= 16) leaves y unchanged
+    // (|coef d| <= 1.6e-9, far below half an ulp of y <= -3.99), so y + rel * d is the reference's value.
     if (OFP_K1_SKIPFOL && skip) {
-        // y >= floor at the start (tested above) keeps y >= floor through the chunk (coefficients <= 1/2: a step
-        // covers at most half the distance, rounding is monotone and the floor is a float), so every d is <= 1e-10
+        // y >= floor at the start (tested above) keeps y >= floor through the chunk (release coefficients <= 1/2: a
+        // step covers at most half the distance, rounding is monotone and the floor is a float): every d <= 1e-10
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float d1 = __fadd_rn(__fsub_rn(k.floor_db, L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(k.floor_db, L.ys), 1e-10f);
@@ -522,6 +521,9 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
             af[u] = amp_front(dr[u]);
         }
     } else {
+        // an attack coefficient above 1 (the reference's realtime settings use 1 / 0.3) overshoots its input: the
+        // envelopes are followed through the chunk and must stay <= -4 for the sliver argument above
+        float ytop = -INFINITY;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float d1 = __fadd_rn(__fsub_rn(db[u], L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(db[u], L.ys), 1e-10f);
@@ -532,9 +534,11 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
             L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
             L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
 #endif
+            ytop = fmaxf(fmaxf(ytop, L.yf), L.ys);
             dr[u] = __fsub_rn(L.yf, L.ys);
             af[u] = amp_front(dr[u]);
         }
+        bad |= !(ytop <= k.sliver_thr);
     }
 #if OFP_K1_LADDER == 3  // + followers
     wait_rel(rel_pending);
@@ -591,8 +595,8 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
     return bad;
 }
 
-__device__ double g_logtab[2 << OFP_LOG_N];
-__device__ double g_exptab[1 << OFP_EXP_N];
+__device__ __align__(16) double g_logtab[2 << OFP_LOG_N];
+__device__ __align__(16) double g_exptab[1 << OFP_EXP_N];
 
 // Round-trip the launch constants through shared memory with volatile loads.  To nvcc/ptxas the
 // reloaded values are opaque, so they stay in registers; otherwise they are re-materialised inside
@@ -731,8 +735,19 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     }
     L.bmax = -INFINITY; L.bmin = INFINITY;
 
-    for (int i = lane; i < (2 << OFP_LOG_N); i += 32) logtab[i] = g_logtab[i];
-    for (int i = lane; i < (1 << OFP_EXP_N); i += 32) exptab[i] = g_exptab[i];
+    {   // tables -> shared memory: all loads of a lane in flight together (a dependent load / store loop costs one L2
+        // round trip per iteration -- 10 us of a 25 us single-block launch of the realtime path)
+        constexpr int NL = (2 << OFP_LOG_N) / 64, NE = (1 << OFP_EXP_N) / 64;  // double2 per lane
+        double2 tl[NL], te[NE];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) tl[i] = reinterpret_cast<const double2 *>(g_logtab)[lane + 32 * i];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) te[i] = reinterpret_cast<const double2 *>(g_exptab)[lane + 32 * i];
+#pragma unroll
+        for (int i = 0; i < NL; ++i) reinterpret_cast<double2 *>(logtab)[lane + 32 * i] = tl[i];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) reinterpret_cast<double2 *>(exptab)[lane + 32 * i] = te[i];
+    }
     __syncwarp();
     if (USE_TMA) {
         if (lane == 0) {
@@ -1002,9 +1017,10 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.ia_max = static_cast<float>(1.0 - static_cast<double>(p.alpha_max));
     a.floor_skip = env_int("OFP_K1_FLOOR_SKIP", 1);
     {
-        const float cf[4] = {p.fast_att, p.fast_rel, p.slow_att, p.slow_rel};
-        a.fast_ok = 1;
-        for (float c : cf) a.fast_ok &= (c > 0.0f && c <= 0.5f) ? 1 : 0;
+        // release coefficients in (0, 1/2] (a release step covers at most half the distance to its input: the floor
+        // invariant), attack coefficients in (0, 16] (att * 1e-10 stays far below half an ulp of the floor)
+        a.fast_ok = (p.fast_rel > 0.0f && p.fast_rel <= 0.5f && p.slow_rel > 0.0f && p.slow_rel <= 0.5f &&
+                     p.fast_att > 0.0f && p.fast_att <= 16.0f && p.slow_att > 0.0f && p.slow_att <= 16.0f) ? 1 : 0;
         a.fast_ok &= (p.floor_db >= -180.0f && p.floor_db <= -4.0f) ? 1 : 0;
     }
     a.blk0 = blk0; a.cnt_in = cnt_in ? 1 : 0;
