@@ -437,6 +437,23 @@ def parity_sample(args, torch, x, hp, hb):
     return out
 
 
+def host_memory_available() -> float:
+    """Bytes this job may still take from host memory: what the kernel reports as available, capped by the container's
+    cgroup limit minus its current usage (pinned staging buffers beyond that get the job killed, not an exception)."""
+    import psutil
+
+    avail = float(psutil.virtual_memory().available)
+    for lim, use in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            limit = open(lim).read().strip()
+            if limit != "max":
+                avail = min(avail, float(limit) - float(open(use).read().strip()))
+        except Exception:
+            pass
+    return max(avail, 0.0)
+
+
 def run_e2e(args, torch, hp, x, dist=None, world=1, rank=0):
     """Same metric end to end through the host-buffer entry of the public API (pipeline.HotPath.run_host): the
     batch starts in pinned HOST memory, is uploaded in time segments while the detector runs, goes through
@@ -449,10 +466,10 @@ def run_e2e(args, torch, hp, x, dist=None, world=1, rank=0):
 
     R, N, Cn = x.shape
     per_rec = N * Cn * 4
-    avail = psutil.virtual_memory().available / max(world, 1)
+    avail = host_memory_available() / max(world, 1)
     want = args.e2e_recordings if args.e2e_recordings > 0 else R
     modes = ["onsets_only"] if args.no_rel else ["onsets_only", "drop_in"]
-    fit = int(0.55 * avail / (per_rec * (2 if "drop_in" in modes else 1)))
+    fit = int(0.4 * avail / (per_rec * (2 if "drop_in" in modes else 1)))  # pinned memory is locked: stay well inside
     Re = max(1, min(want, R, fit))
     from onset_fingerprinting_b200 import parallel
 
@@ -465,6 +482,7 @@ def run_e2e(args, torch, hp, x, dist=None, world=1, rank=0):
     ceil = {}
     scratch = xd_like = x[:Re]  # the upload lands in the resident device copy itself (same bytes): no extra HBM
     side = torch.cuda.Stream()
+    ceil["_buf"] = torch.empty((min(Re, 256), N, Cn), dtype=torch.float32, pin_memory=True)  # allocated outside the timing
     for name, both in (("h2d", False), ("h2d_d2h", True)):
         if dist is not None:
             dist.barrier()
@@ -473,7 +491,7 @@ def run_e2e(args, torch, hp, x, dist=None, world=1, rank=0):
         scratch.copy_(xh, non_blocking=True)
         if both:
             with torch.cuda.stream(side):
-                xh2 = ceil.setdefault("_buf", torch.empty((min(Re, 1024), N, Cn), dtype=torch.float32, pin_memory=True))
+                xh2 = ceil["_buf"]
                 for lo in range(0, Re, xh2.shape[0]):  # the D2H stream lands in a small pinned buffer (host memory)
                     n = min(xh2.shape[0], Re - lo)
                     xh2[:n].copy_(xd_like[lo:lo + n], non_blocking=True)

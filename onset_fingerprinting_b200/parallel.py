@@ -28,7 +28,8 @@ def bind_to_gpu_numa(device_index: int) -> dict:
     found and done; a box that exposes one node (or hides sysfs) is reported as such, not treated as an error."""
     info = {"device": device_index, "bound": False}
     try:
-        bdf = torch.cuda.get_device_properties(device_index).pci_bus_id  # torch >= 2.4
+        pr = torch.cuda.get_device_properties(device_index)  # torch >= 2.4: integer domain / bus / device ids
+        bdf = f"{int(pr.pci_domain_id):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
     except Exception:
         try:
             import pynvml
