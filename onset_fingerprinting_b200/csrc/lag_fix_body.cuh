@@ -300,8 +300,10 @@ __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double 
     if (x_fresh) sx_cache = sx; else sx = sx_cache;
     // ||x|| ||y|| as ONE square root (two double square roots per thread per pair were 2.5 % of the kernel's
     // samples); it only enters the error bound, where the 1.0001 factor below covers its rounding
-    const double S = sqrt(sx * sy);
     if (!(sx < 1e30 && sy < 1e30)) return false;  // inf / NaN in the section: exact path
+    // ||x|| ||y|| only enters the error bound: a float32 square root rounded up (of the product rounded up) is an
+    // upper bound and costs a fraction of the double one (3.9 % of the kernel's samples sat on its result)
+    const float S = __fsqrt_ru(__double2float_ru(sx * sy));
     if (sx == 0.0 || sy == 0.0) {   // one signal is all zero: every sum is 0, np.argmax returns index 0
         if (tid == 0) *s_lag = static_cast<int>(adj);
         __syncthreads();
@@ -361,7 +363,7 @@ __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double 
     }
     __syncthreads();
     // pass 2: v32, bounds, candidates
-    const float Ef = static_cast<float>(S * (static_cast<double>(L + 8) * 5.9604644775390625e-08) * 1.0001);
+    const float Ef = S * (static_cast<float>(L + 8) * 5.9604644775390625e-08f) * 1.0002f;
     const int m_first = static_cast<int>(ws - (L - 1)), Lw = static_cast<int>(L), nlw = static_cast<int>(nl);
     auto eval = [&](int w, float &v, float &d) {
         const int gg = w / K4_LPF, u = w - gg * K4_LPF;
@@ -375,19 +377,41 @@ __device__ __forceinline__ bool cc_argmax_screen(const double *xd, const double 
         d = Ef / c * 1.0001f + fabsf(v) * 4.76837158203125e-07f;
     };
     float lowmax = -INFINITY;
-    for (int w = tid; w < nlw; w += K4_THREADS) {
-        float v, d;
-        eval(w, v, d);
-        lowmax = fmaxf(lowmax, v - d);
+    constexpr int EV = 2;  // values per thread kept in registers between the two sweeps (nl <= EV * threads: always
+    float ev[EV], ed[EV];  // for the windows of fix_onsets; longer windows re-evaluate)
+    const bool keep = nlw <= EV * K4_THREADS;
+#pragma unroll
+    for (int q = 0; q < EV; ++q) {
+        const int w = tid + q * K4_THREADS;
+        ev[q] = -INFINITY; ed[q] = 0.f;
+        if (keep && w < nlw) { eval(w, ev[q], ed[q]); lowmax = fmaxf(lowmax, ev[q] - ed[q]); }
+    }
+    if (!keep) {
+        for (int w = tid; w < nlw; w += K4_THREADS) {
+            float v, d;
+            eval(w, v, d);
+            lowmax = fmaxf(lowmax, v - d);
+        }
     }
     lowmax = block_max(lowmax, sc.red_f);
     __syncthreads();
-    for (int w = tid; w < nlw; w += K4_THREADS) {
-        float v, d;
-        eval(w, v, d);
-        if (v + d >= lowmax) {
-            const int k = atomicAdd(&sc.cand[0], 1);
-            if (k < CAND_CAP) sc.cand[1 + k] = static_cast<int>(w);
+    if (keep) {
+#pragma unroll
+        for (int q = 0; q < EV; ++q) {
+            const int w = tid + q * K4_THREADS;
+            if (w < nlw && ev[q] + ed[q] >= lowmax) {
+                const int k = atomicAdd(&sc.cand[0], 1);
+                if (k < CAND_CAP) sc.cand[1 + k] = w;
+            }
+        }
+    } else {
+        for (int w = tid; w < nlw; w += K4_THREADS) {
+            float v, d;
+            eval(w, v, d);
+            if (v + d >= lowmax) {
+                const int k = atomicAdd(&sc.cand[0], 1);
+                if (k < CAND_CAP) sc.cand[1 + k] = static_cast<int>(w);
+            }
         }
     }
     __syncthreads();

@@ -373,7 +373,7 @@ __device__ __forceinline__ bool amp_flagged(float qmax, uint32_t mid) {
 
 // The previous block's bulk copy (block_end) must have read the block buffer before it is overwritten.
 __device__ __forceinline__ void wait_rel(bool &rel_pending) {
-    if (rel_pending) { bulk_wait_read<0>(); __syncwarp(); rel_pending = false; }
+    if (__builtin_expect(rel_pending, 0)) { bulk_wait_read<0>(); __syncwarp(); rel_pending = false; }
 }
 
 // envelope_follower.c:38-52
@@ -465,7 +465,7 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
     for (int u = 0; u < U; ++u) hmax = fmaxf(hmax, fabsf(h[u]));
     float dbmax = k.floor_db;  // largest dB value of the chunk (sliver test below)
     const bool skip = __all_sync(0xffffffffu, hmax < k.vfloor_h);
-    if (skip) {  // (iv)
+    if (__builtin_expect(skip, 1)) {  // (iv)
 #pragma unroll
         for (int u = 0; u < U; ++u) db[u] = k.floor_db;
     } else {
@@ -509,7 +509,7 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
     // Below-floor chunks (iv) know more: x is the floor and y >= floor, so d = (floor - y) + 1e-10 <= 1e-10 and the
     // release coefficient applies; d > 0 only for y == floor, where either coefficient (<= 16) leaves y unchanged
     // (|coef d| <= 1.6e-9, far below half an ulp of y <= -3.99), so y + rel * d is the reference's value.
-    if (OFP_K1_SKIPFOL && skip) {
+    if (OFP_K1_SKIPFOL && __builtin_expect(skip, 1)) {
         // y >= floor at the start (tested above) keeps y >= floor through the chunk (release coefficients <= 1/2: a
         // step covers at most half the distance, rounding is monotone and the floor is a float): every d <= 1e-10
 #pragma unroll
@@ -583,7 +583,7 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
 #if OFP_K1_LADDER >= 5
     if (DO_MM) {
         const bool quiet = (amp[U - 1] < k.minmin) & (cmax < __fmul_rn(mx0, k.mxfac));
-        if (OFP_K1_MNVOTE && OFP_K1_MXSPEC && __all_sync(0xffffffffu, quiet)) {  // (vi) + the max tracker's assumption
+        if (OFP_K1_MNVOTE && OFP_K1_MXSPEC && __builtin_expect(__all_sync(0xffffffffu, quiet), 1)) {  // (vi) + (vii)
             L.mn = k.minmin;
             L.mx = mx_spec;
         } else {
@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                         };
                         if (do_minmax) chunks(std::true_type{});
                         else chunks(std::false_type{});
-                        if (__any_sync(0xffffffffu, bad)) {
+                        if (__builtin_expect(__any_sync(0xffffffffu, bad), 0)) {
                             L = saved;
                             for (int e = 0; e < nfast; ++e)
                                 sample_exact<USE_HP>(L, kf, xp0 + e * step, rp0 + e * step, do_minmax, in_group, logtab_s,
