@@ -217,3 +217,22 @@ def test_loud_clipped_signal_exercises_exact_paths(det, orc):
         assert ch == ch_o and on == on_o
         assert rel_err(rel, rel_o) <= 1e-5
         assert float((rel == rel_o).mean()) > 0.9999
+
+
+@pytest.mark.parametrize("kw", [
+    dict(fast_ar=(1.0, 1.5), slow_ar=(1.2, 1.8)),            # release coefficients above 1/2: every chunk on the exact path
+    dict(fast_ar=(0.05, 300.0)),                              # attack coefficient 20 (> 16): exact path
+    dict(floor=-3.0),                                         # floor above the sliver threshold: exact path
+    dict(fast_ar=(0.3, 800), slow_ar=(500.0, 8000.0)),        # attack above 1 on the straight-line path, att != rel slow
+    dict(fast_ar=(400.0, 3.0), slow_ar=(2205.0, 100.0)),      # release faster than attack (the sign-flipped max form)
+])
+def test_follower_coefficient_ranges(kw, det, orc):
+    """The straight-line chunk is only enabled for release coefficients in (0, 1/2], attack coefficients in
+    (0, 16] and floors in [-180, -4] dB (csrc/onset_detect.cu: fast_ok); outside, and on the boundary cases inside,
+    the kernel must still equal the oracle bit for bit."""
+    x, _ = synth.drum_recording(seconds=1.5, seed=5)
+    ch, on, rel = det.detect_onsets_amplitude(x, sr=96000, **kw)
+    ch_o, on_o, rel_o = orc.detect_onsets_amplitude(x, sr=96000, **kw)
+    assert ch == ch_o and on == on_o
+    assert rel_err(rel, rel_o) <= 1e-5
+    assert float((rel == rel_o).mean()) > 0.9999

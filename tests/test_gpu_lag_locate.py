@@ -225,3 +225,30 @@ def test_locate_streaming_matches_batch(golden_dir):
             assert res is None
         else:
             assert res is not None and np.allclose(res, want, rtol=1e-9)
+
+
+def test_streaming_locate_state_on_device():
+    """Multilaterate3D.locate runs the device state machine; `ongoing` decodes its group lists, `m.ongoing = []` is the
+    reference's reset, and an explicit list can be written back."""
+    from onset_fingerprinting_b200 import multilateration as ml
+
+    m = ml.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+    assert m.ongoing == []
+    assert m.locate(0, 1000) is None
+    assert m.ongoing == [([0], [1000])]
+    assert m.locate(1, 1003) is None
+    g = m.ongoing
+    assert ([0, 1], [1000, 1003]) in g and ([1], [1003]) in g
+    saved = list(g)
+    m.ongoing = []
+    assert m.ongoing == []
+    m.ongoing = saved
+    assert m.ongoing == saved
+    a = m.locate(2, 1010)
+    m2 = ml.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+    for s, o in ((0, 1000), (1, 1003)):
+        m2.locate(s, o)
+    b = m2.locate(2, 1010)
+    assert (a is None) == (b is None) and (a is None or np.array_equal(a, b))
+    with pytest.raises(ValueError):
+        m.ongoing = [([0], [1])] * 17

@@ -53,3 +53,13 @@ def test_gather_records_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, 29611, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def test_bind_to_gpu_numa_reports_instead_of_failing():
+    """Without a GPU (or with a box that hides NUMA locality) the helper says why it did nothing."""
+    from onset_fingerprinting_b200 import parallel
+
+    info = parallel.bind_to_gpu_numa(0)
+    assert info["device"] == 0 and isinstance(info["bound"], bool)
+    assert info["bound"] or "reason" in info
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
