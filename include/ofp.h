@@ -431,18 +431,22 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
                     int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
                     int32_t activation, const float *params_dev, int32_t out_size, float *out_dev, void *stream);
 
-/* model.CCCNN.forward in eval mode (model.py:443-538, group = False): the conv stack (as above, but with ONE input
+/* model.CCCNN.forward in eval mode (model.py:443-538): the conv stack (as above, but with ONE input
  * channel) runs on every sensor channel separately, the K feature maps of a channel are auto-correlated over all
  * 2V-1 lags and summed, soft-maxed over the lags, and the [channels x (2V-1)] probabilities feed Linear.
  * x_dev [n_windows, channels, input_size]; params_dev: conv layers packed as for ofp_cnn_forward (first layer
  * c_in = 1), then fc.weight [out_size][channels * (2V-1)] and fc.bias.  out_size <= 4, the last layer size a
- * multiple of 8 and V a multiple of 16 (the auto-correlation runs as F^T F on the tensor cores). */
+ * multiple of 8 and V a multiple of 16 (the auto-correlation runs as F^T F on the tensor cores).
+ * group != 0 is CCCNN(group=True) (model.py:470-484: every conv layer with groups = channels, i.e. each sensor channel
+ * runs its own copy of the stack): the packed conv parameters are then `channels` blocks of the layout above, channel
+ * 0 first, followed by fc. */
 int ofp_cccnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
-                          int32_t kernel_size, int32_t padding, int32_t out_size, int64_t *n_params_out,
+                          int32_t kernel_size, int32_t padding, int32_t out_size, int32_t group, int64_t *n_params_out,
                           int32_t *n_lags_out);
 int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
                       int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
-                      int32_t activation, const float *params_dev, int32_t out_size, float *out_dev, void *stream);
+                      int32_t activation, int32_t group, const float *params_dev, int32_t out_size, float *out_dev,
+                      void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Benchmark input: seeded synthetic multi-mic drum audio generated on the device

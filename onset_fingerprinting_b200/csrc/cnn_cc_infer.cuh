@@ -49,7 +49,8 @@ __global__ void __launch_bounds__(3 * 32, 2) k6_cccnn(const K6Args a, const int 
             // ---- conv stack, every layer stored ----
             for (int l = 0; l < a.n_layers; ++l) {
                 const int Cin = a.cin[l], Cout = a.cout[l], CP = a.coutp[l], Lout = a.lout[l];
-                const float *wT = prm + a.w_off[l], *bias = prm + a.b_off[l];
+                // group = True (model.py:512-538: groups = channels): channel c runs its OWN copy of the stack
+                const float *wT = prm + c * a.group_stride + a.w_off[l], *bias = prm + c * a.group_stride + a.b_off[l];
                 for (int ob = 0; ob < CP; ob += 8) {
                     float acc[8][P];
 #pragma unroll
@@ -227,7 +228,8 @@ __global__ void __launch_bounds__(128, OFP_K6CC_MINCTA) k6_cccnn_cta(const K6Arg
             float *in = bufA, *outb = bufB;
             for (int l = 0; l < a.n_layers; ++l) {
                 const int Cin = a.cin[l], Cout = a.cout[l], CP = a.coutp[l], Lout = a.lout[l];
-                const float *wT = prm + a.w_off[l], *bias = prm + a.b_off[l];
+                // group = True (model.py:512-538: groups = channels): channel c runs its OWN copy of the stack
+                const float *wT = prm + c * a.group_stride + a.w_off[l], *bias = prm + c * a.group_stride + a.b_off[l];
                 for (int ob = 0; ob < CP; ob += 8) {
                     float acc[8][PP];
 #pragma unroll

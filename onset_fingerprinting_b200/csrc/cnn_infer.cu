@@ -31,6 +31,7 @@ struct K6Args {
     int32_t w_off[K6_MAX_LAYERS], b_off[K6_MAX_LAYERS];  // float offsets into params
     int32_t fc_w_off, fc_b_off, n_params, conv_params;   // conv_params: floats staged in shared memory always
     int32_t fc_in_smem;
+    int32_t group_stride;    // CCCNN(group=True): floats between the conv parameter blocks of two channels (0 = shared stack)
     int32_t row_stride;      // floats per activation row (>= 32 P + ks, multiple of 4... plus halo)
     int32_t buf_rows;        // rows per activation buffer
     const float *params;     // packed: per layer wT[ic][k][coutp] + bias[coutp]; fc w[out][flat] + bias[out]
@@ -320,8 +321,8 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
 }
 
 int ofp_cccnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
-                          int32_t kernel_size, int32_t padding, int32_t out_size, int64_t *n_params_out,
-                          int32_t *n_lags_out) {
+                          int32_t kernel_size, int32_t padding, int32_t out_size, int32_t group,
+                          int64_t *n_params_out, int32_t *n_lags_out) {
     OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS && layer_sizes_host && n_params_out, "bad argument");
     int64_t n = 0;
     int cin = 1, len = input_size;
@@ -332,6 +333,7 @@ int ofp_cccnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers
         OFP_REQUIRE(len >= 1, "layer %d has no output positions", l);
         cin = cout;
     }
+    if (group) n *= channels;  // one copy of the stack per sensor channel (groups = channels)
     n += static_cast<int64_t>(out_size) * channels * (2 * len - 1) + out_size;
     *n_params_out = n;
     if (n_lags_out) *n_lags_out = 2 * len - 1;
@@ -340,7 +342,8 @@ int ofp_cccnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers
 
 int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
                       int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
-                      int32_t activation, const float *params_dev, int32_t out_size, float *out_dev, void *stream) {
+                      int32_t activation, int32_t group, const float *params_dev, int32_t out_size, float *out_dev,
+                      void *stream) {
     OFP_REQUIRE(x_dev && params_dev && out_dev && layer_sizes_host, "null argument");
     OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS, "1..%d conv layers supported", K6_MAX_LAYERS);
     OFP_REQUIRE(kernel_size == 1 || kernel_size == 3 || kernel_size == 5 || kernel_size == 7,
@@ -371,7 +374,11 @@ int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride,
     OFP_REQUIRE(cin % 8 == 0, "the last layer size must be a multiple of 8 (tensor-core K dimension), got %d", cin);
     rows_a = std::max(rows_a, cin); rows_b = std::max(rows_b, cin);  // the hi / lo planes of the feature maps
     OFP_REQUIRE(len % 16 == 0, "the feature-map length must be a multiple of 16, got %d", len);
+    // group = True: `channels` copies of the stack one after the other, channel c at c * group_stride
+    a.group_stride = group ? off : 0;
+    if (group) off *= channels;
     a.conv_params = off;
+    OFP_REQUIRE(off <= 16384, "conv stack too large for shared memory (%d floats)", off);
     const int nb = 2 * len - 1;
     a.fc_w_off = off; off += out_size * channels * nb;
     a.fc_b_off = off; off += out_size;

@@ -120,7 +120,7 @@ class CNN(nn.Module):
 
 
 class CCCNN(nn.Module):
-    """``model.CCCNN`` of the reference (model.py:443-538, ``group=False``) for inference: same constructor arguments
+    """``model.CCCNN`` of the reference (model.py:443-538, ``group`` False or True) for inference: same constructor arguments
     and parameter names (``conv_layers.conv1`` ..., ``fc``), fused forward in csrc/cnn_cc_infer.cuh -- per sensor
     channel the shared conv stack, the summed auto-correlation of its feature maps as ``F^T F`` on the tensor
     cores with the diagonal sums taken inside the accumulator fragments, softmax over the 2V-1 lags, Linear."""
@@ -135,20 +135,21 @@ class CCCNN(nn.Module):
             kernel_sizes = kernel_sizes[0]
         if isinstance(strides, (list, tuple)):
             strides = strides[0] if len(set(strides)) == 1 else None
-        if batch_norm or pool or dilation != 1 or group or strides != 1:
-            raise NotImplementedError("K6b covers the reference defaults: group=False, stride 1, no batch_norm / pool")
+        if batch_norm or pool or dilation != 1 or strides != 1:
+            raise NotImplementedError("K6b covers stride 1, dilation 1, no batch_norm / pool (group either way)")
         if activation not in _ACT:
             raise NotImplementedError(f"activation {activation}")
         self.input_size, self.output_size, self.channels = input_size, output_size, channels
         self.layer_sizes, self.kernel_size, self.padding = list(layer_sizes), kernel_sizes, padding
-        self.act, self.group = _ACT[activation], False
+        self.act, self.group = _ACT[activation], bool(group)
         self.conv_layers = nn.Sequential()
-        cur, length = 1, input_size
+        g = channels if group else 1  # model.py:470-484: in / out channels times `channels`, groups = channels
+        cur, length = g, input_size
         for i, size in enumerate(self.layer_sizes):
-            self.conv_layers.add_module(f"conv{i + 1}", nn.Conv1d(cur, size, kernel_sizes, padding=padding))
+            self.conv_layers.add_module(f"conv{i + 1}", nn.Conv1d(cur, size * g, kernel_sizes, padding=padding, groups=g))
             self.conv_layers.add_module(f"act{i + 1}", activation())
             length = length + 2 * padding - (kernel_sizes - 1)
-            cur = size
+            cur = size * g
         self.dropout = nn.Dropout(dropout_rate)
         self.n_lags = 2 * length - 1
         self.fc = nn.Linear(channels * self.n_lags, output_size)
@@ -157,23 +158,25 @@ class CCCNN(nn.Module):
 
     def pack(self) -> torch.Tensor:
         parts = []
-        for i in range(len(self.layer_sizes)):
-            conv = getattr(self.conv_layers, f"conv{i + 1}")
-            w = conv.weight.detach().float().cpu()
-            cout = w.shape[0]
-            cp = (cout + 7) // 8 * 8
-            wt = torch.zeros((w.shape[1], w.shape[2], cp))
-            wt[:, :, :cout] = w.permute(1, 2, 0)
-            bp = torch.zeros(cp)
-            bp[:cout] = conv.bias.detach().float().cpu()
-            parts += [wt.reshape(-1), bp]
+        for c in range(self.channels if self.group else 1):  # group: one block per sensor channel, channel 0 first
+            for i, size in enumerate(self.layer_sizes):
+                conv = getattr(self.conv_layers, f"conv{i + 1}")
+                w = conv.weight.detach().float().cpu()[c * size:(c + 1) * size]  # [size, c_in per group, k]
+                b = conv.bias.detach().float().cpu()[c * size:(c + 1) * size]
+                cp = (size + 7) // 8 * 8
+                wt = torch.zeros((w.shape[1], w.shape[2], cp))
+                wt[:, :, :size] = w.permute(1, 2, 0)
+                bp = torch.zeros(cp)
+                bp[:size] = b
+                parts += [wt.reshape(-1), bp]
         parts += [self.fc.weight.detach().float().cpu().reshape(-1), self.fc.bias.detach().float().cpu()]
         packed = torch.cat(parts).contiguous()
         n = C.c_int64(0)
         sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
         check(_lib.lib().ofp_cccnn_param_count(C.c_int32(self.channels), C.c_int32(self.input_size),
                                                C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
-                                               C.c_int32(self.padding), C.c_int32(self.output_size), C.byref(n), None))
+                                               C.c_int32(self.padding), C.c_int32(self.output_size),
+                                               C.c_int32(int(self.group)), C.byref(n), None))
         assert n.value == packed.numel(), (n.value, packed.numel())
         self._packed = packed.cuda()
         return self._packed
@@ -201,6 +204,6 @@ class CCCNN(nn.Module):
         check(_lib.lib().ofp_cccnn_forward(ptr(x), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)),
                                            C.c_int32(self.channels), C.c_int32(self.input_size),
                                            C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
-                                           C.c_int32(self.padding), C.c_int32(self.act), ptr(self._packed),
-                                           C.c_int32(self.output_size), ptr(out), stream_ptr()))
+                                           C.c_int32(self.padding), C.c_int32(self.act), C.c_int32(int(self.group)),
+                                           ptr(self._packed), C.c_int32(self.output_size), ptr(out), stream_ptr()))
         return out

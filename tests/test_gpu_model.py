@@ -195,7 +195,11 @@ def cccnn_reference(m, x):
     try:
         with torch.no_grad():
             B, Cn, W = x.shape
-            f = m.conv_layers(x.reshape(B * Cn, 1, W))  # the reference vmaps the same stack over the channels
+            if m.group:  # model.py:512-513: grouped convolutions over the C input channels -> (B, C*K, V)
+                f = m.conv_layers(x)
+                f = f.reshape(B * Cn, f.shape[1] // Cn, f.shape[2])
+            else:
+                f = m.conv_layers(x.reshape(B * Cn, 1, W))  # the reference vmaps the same stack over the channels
             K, V = f.shape[1:]
             cc = F.conv1d(f.reshape(1, B * Cn * K, V), f.reshape(B * Cn * K, 1, V), groups=B * Cn * K, padding=V - 1)
             cc = cc.view(B * Cn, K, -1).sum(1)
@@ -210,6 +214,8 @@ def cccnn_reference(m, x):
     dict(input_size=128, output_size=3, channels=4, layer_sizes=[8], kernel_sizes=5, padding=2),
     dict(input_size=64, output_size=2, channels=2, layer_sizes=[6, 12, 8], activation=torch.nn.Tanh),
     dict(input_size=48, output_size=1, channels=3, layer_sizes=[16], activation=torch.nn.ReLU),  # V / 8 not a multiple of 4
+    dict(input_size=256, output_size=2, group=True),                                              # own stack per sensor
+    dict(input_size=64, output_size=2, channels=4, layer_sizes=[6, 8], group=True, activation=torch.nn.Tanh),
 ])
 def test_cccnn_forward_matches_torch(cfg):
     """The summed auto-correlation runs as F^T F on the tensor cores (3xTF32); softmax turns absolute errors of the
