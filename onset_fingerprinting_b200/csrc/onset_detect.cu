@@ -124,6 +124,7 @@ struct Coef {
     float fA, fR, fS, sA, sR, sS;  // followers of the straight-line chunk: (s att, s rel, s), s = att >= rel ? 1 : -1
     float floor_db, ceil_amp, vfloor, vfloor_h;
     float mxfac;       // chunk maximum < mxfac x max tracker => no sample of the chunk exceeds the tracker
+    float overshoot;   // != 0: an attack coefficient above 1 (envelopes are followed through non-skip chunks)
     float sliver_thr;  // -4, or -inf when the straight-line chunk must not be trusted (every chunk re-runs exactly)
     float amin, amax, iamin, iamax, minmin;
 };
@@ -143,6 +144,7 @@ __device__ __forceinline__ Coef load_coef(const K1Args &a) {
         const double ia = static_cast<double>(a.ia_max);
         k.mxfac = (ia > 0.0 && ia < 1.0) ? static_cast<float>(pow(ia, OFP_K1_KU) * (1.0 - 4e-6)) : 0.0f;
     }
+    k.overshoot = (k.fa > 1.0f || k.fr > 1.0f || k.sa > 1.0f || k.sr > 1.0f) ? 1.0f : 0.0f;
     k.sliver_thr = a.fast_ok ? -4.0f : -INFINITY;
     k.amin = a.p.alpha_min; k.amax = a.p.alpha_max; k.iamin = a.ia_min; k.iamax = a.ia_max;
     k.minmin = a.p.minmin;
@@ -523,22 +525,26 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
     } else {
         // an attack coefficient above 1 (the reference's realtime settings use 1 / 0.3) overshoots its input: the
         // envelopes are followed through the chunk and must stay <= -4 for the sliver argument above
+        // (attack coefficients <= 1 cannot overshoot: the chunk-start test above covers them, no per-step tracking)
         float ytop = -INFINITY;
+        auto steps = [&](auto track) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float d1 = __fadd_rn(__fsub_rn(db[u], L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(db[u], L.ys), 1e-10f);
+            for (int u = 0; u < U; ++u) {
+                const float d1 = __fadd_rn(__fsub_rn(db[u], L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(db[u], L.ys), 1e-10f);
 #if OFP_K1_FOLMAX
-            L.yf = __fmaf_rn(k.fS, fmaxf(__fmul_rn(k.fA, d1), __fmul_rn(k.fR, d1)), L.yf);
-            L.ys = __fmaf_rn(k.sS, fmaxf(__fmul_rn(k.sA, d2), __fmul_rn(k.sR, d2)), L.ys);
+                L.yf = __fmaf_rn(k.fS, fmaxf(__fmul_rn(k.fA, d1), __fmul_rn(k.fR, d1)), L.yf);
+                L.ys = __fmaf_rn(k.sS, fmaxf(__fmul_rn(k.sA, d2), __fmul_rn(k.sR, d2)), L.ys);
 #else
-            L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
-            L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
+                L.yf = __fadd_rn(L.yf, __fmul_rn(d1 > 0.0f ? k.fa : k.fr, d1));
+                L.ys = __fadd_rn(L.ys, __fmul_rn(d2 > 0.0f ? k.sa : k.sr, d2));
 #endif
-            ytop = fmaxf(fmaxf(ytop, L.yf), L.ys);
-            dr[u] = __fsub_rn(L.yf, L.ys);
-            af[u] = amp_front(dr[u]);
-        }
-        bad |= !(ytop <= k.sliver_thr);
+                if (decltype(track)::value) ytop = fmaxf(fmaxf(ytop, L.yf), L.ys);
+                dr[u] = __fsub_rn(L.yf, L.ys);
+                af[u] = amp_front(dr[u]);
+            }
+        };
+        if (k.overshoot != 0.0f) { steps(std::true_type{}); bad |= !(ytop <= k.sliver_thr); }
+        else steps(std::false_type{});
     }
 #if OFP_K1_LADDER == 3  // + followers
     wait_rel(rel_pending);
@@ -626,7 +632,7 @@ __device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch
 // End of a block (main phase): the reference's threshold FSM (detection.py:759-792) on the block held in shared
 // memory, onset compaction in the reference's order, and the copy of the block's rel envelope to HBM
 // (rcol = this lane's column of row 0).  With 16-byte aligned rows the copy is one bulk async copy per recording
-// (cp.async.bulk shared -> global, issued by lane g for recording g): the warp does not touch the data again, and
+// (cp.async.bulk shared -> global, issued by lane 0): the warp does not touch the data again, and
 // `rel_pending` tells the next writer of the block buffer to wait until the copy engine has read it.
 __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float *rcol, const float *relbuf, int lane,
                                           int g, int c, int rec, int rec0, bool active, unsigned rec_mask,
@@ -677,9 +683,15 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
         if (a.rel_vec_ok) {
             fence_proxy_async();  // this lane's st.shared of the block -> visible to the async proxy
             __syncwarp();
-            if (lane < G && rec0 + lane < a.R)
-                bulk_store(a.rel + (rec0 + lane) * a.rel_stride + (blk - a.blk0) * nBC, relbuf + lane * a.stride_rel,
-                           static_cast<uint32_t>(nBC) * 4u);
+            // lane 0 issues the G copies one after the other: the copy instruction takes uniform operands, so G
+            // lanes issuing one copy each become a divergence loop of G iterations anyway, with more bookkeeping
+            if (lane == 0) {
+                float *dst = a.rel + static_cast<int64_t>(rec0) * a.rel_stride + (blk - a.blk0) * nBC;
+                const float *src = relbuf;
+                const int ng = min(G, a.R - rec0);
+                for (int gi = 0; gi < ng; ++gi, dst += a.rel_stride, src += a.stride_rel)
+                    bulk_store(dst, src, static_cast<uint32_t>(nBC) * 4u);
+            }
             bulk_commit();
             rel_pending = true;
         } else {

@@ -455,8 +455,12 @@ def find_onset_groups_batch(channels, onsets, counts, n_channels: int, max_dista
     offsets = torch.cumsum(kept, 0) - kept
     span = 0
     if with_span:
+        # element-wise min / max over the channel columns (a torch reduction over a trailing dimension of 3 costs
+        # milliseconds on 10^7 elements; C - 1 strided maximum / minimum kernels cost microseconds)
+        mn = mx = groups[:, :, 0]
+        for c in range(1, n_channels):
+            mn, mx = torch.minimum(mn, groups[:, :, c]), torch.maximum(mx, groups[:, :, c])
         valid = torch.arange(max_groups, device="cuda")[None, :] < kept[:, None]
-        mn, mx = groups.min(2).values, groups.max(2).values
         spread = torch.where(valid & (mn >= 0), mx - mn, torch.zeros_like(mx)).max().to(torch.int64)
         H, span = (int(v) for v in torch.stack([kept.sum(), spread]).tolist())
     else:
