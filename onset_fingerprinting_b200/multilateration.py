@@ -505,24 +505,36 @@ class Multilaterate:
     is_legal_3d = Multilaterate3D.is_legal_3d
 
     def locate(self, sensor_index: int, onset_index: int):
-        """multilateration.py:679-713."""
-        new_groups = []
-        for group in self.ongoing:
-            lag = onset_index - group[1][0]
-            if sensor_index not in group[0]:
-                if self.is_legal(group[0][0], sensor_index, lag):
-                    group = (group[0] + [sensor_index], group[1] + [onset_index])
-                    if len(group[0]) == 3:
-                        res = self.is_legal_3d(group)
-                        if res != (0, 0):
-                            res = self.trilaterate(group, np.array(res) - self.radius)
-                            self.ongoing = new_groups
-                            return res
-                    new_groups.append(group)
-            if lag <= self.max_max_lags[group[0][0]]:
-                new_groups.append(group)
-        new_groups.append(([sensor_index], [onset_index]))
-        self.ongoing = new_groups
+        """multilateration.py:679-713: the 2-D streaming contract.  Every ongoing group that the detection legally
+        extends is tried; the first group it completes to three sensors with a legal lag-map cell is solved and
+        ends the call (the groups visited so far stay, the rest are dropped -- as the reference does).  Quirk kept:
+        an extended group is listed twice (the reference's loop variable is rebound to the extended tuple before the
+        keep-alive test), the un-extended one is not kept."""
+        kept = []
+
+        def solved(group):
+            """(done, result): a complete group with a legal seed cell goes to the solver."""
+            if len(group[0]) != 3:
+                return False, None
+            cell = self.is_legal_3d(group)
+            if cell == (0, 0):
+                return False, None
+            return True, self.trilaterate(group, np.array(cell) - self.radius)
+
+        for sensors, onsets in self.ongoing:
+            lag = onset_index - onsets[0]
+            current = (sensors, onsets)
+            if sensor_index not in sensors and self.is_legal(sensors[0], sensor_index, lag):
+                current = (sensors + [sensor_index], onsets + [onset_index])
+                done, res = solved(current)
+                if done:
+                    self.ongoing = kept
+                    return res
+                kept.append(current)
+            if lag <= self.max_max_lags[current[0][0]]:
+                kept.append(current)
+        kept.append(([sensor_index], [onset_index]))
+        self.ongoing = kept
         return None
 
     def trilaterate(self, group, initial_guess):
