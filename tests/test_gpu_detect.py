@@ -148,6 +148,8 @@ def test_host_buffer_entry_point(det, orc):
         c_o, o_o, rel_o = orc.detect_onsets_amplitude(xs[r], sr=96000)
         assert ch[r, :cnt[r]].tolist() == c_o and ix[r, :cnt[r]].tolist() == o_o
         assert rel_err(rel[r], rel_o) <= 1e-5
+    _lib.check(_lib.lib().ofp_host_release())  # the staging buffers the call keeps for its next use
+    _lib.check(_lib.lib().ofp_host_release())  # idempotent
 
 
 def test_host_entry_time_segments_equal_one_shot(det, monkeypatch):
@@ -181,6 +183,7 @@ def test_host_entry_time_segments_equal_one_shot(det, monkeypatch):
             assert np.array_equal(ch[r, :cnt[r]], ch0[r, :cnt[r]]) and np.array_equal(ix[r, :cnt[r]], ix0[r, :cnt[r]])
         assert np.array_equal(rel, rel0), (seg, chunk)
     assert int(cnt0.sum()) >= 5 * 6  # the batch does contain hits
+    _lib.check(_lib.lib().ofp_host_release())
 
 
 def test_backtrack_offline_and_streaming(det, golden_dir):
