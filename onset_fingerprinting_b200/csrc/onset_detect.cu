@@ -374,8 +374,12 @@ __device__ __forceinline__ bool amp_flagged(float qmax, uint32_t mid) {
 }
 
 // The previous block's bulk copy (block_end) must have read the block buffer before it is overwritten.
+// (Unconditional: with nothing in flight the wait is a scoreboard test that falls through; a branch around it was
+// one more taken branch in every chunk.)
 __device__ __forceinline__ void wait_rel(bool &rel_pending) {
-    if (__builtin_expect(rel_pending, 0)) { bulk_wait_read<0>(); __syncwarp(); rel_pending = false; }
+    bulk_wait_read<0>();
+    __syncwarp();
+    rel_pending = false;
 }
 
 // envelope_follower.c:38-52
