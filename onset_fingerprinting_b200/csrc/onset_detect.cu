@@ -35,7 +35,7 @@
 #ifndef OFP_K1_KU
 #define OFP_K1_KU 8
 #endif
-#ifndef OFP_K1_SPARSE  // short-cut (v) of chunk_fast, switchable for A/B builds
+#ifndef OFP_K1_SPARSE  // short-cut (v) of chunk_loop, switchable for A/B builds
 #define OFP_K1_SPARSE 1
 #endif
 #ifndef OFP_K1_KQF  // 10**x: k by a float32 magic-constant add (+ one conversion) instead of a double one
@@ -52,15 +52,6 @@
 #endif
 #ifndef OFP_K1_FOLMAX  // followers: coef * d as max(att * d, rel * d) instead of a select
 #define OFP_K1_FOLMAX 1
-#endif
-#ifndef OFP_K1_MNVOTE  // short-cut (vi)
-#define OFP_K1_MNVOTE 1
-#endif
-#ifndef OFP_K1_SKIPFOL  // followers of below-floor chunks without the coefficient choice
-#define OFP_K1_SKIPFOL 1
-#endif
-#ifndef OFP_K1_MXSPEC  // max tracker without the select (speculating that no sample exceeds it)
-#define OFP_K1_MXSPEC 1
 #endif
 
 #include <algorithm>
@@ -428,109 +419,195 @@ __device__ __forceinline__ void sample_exact(Lane &L, const Coef &k, uint32_t xs
     if (store) sts_f32(rs, amp[0]);
 }
 
-// Straight-line form for U samples: one large basic block per path that ptxas can software-pipeline (needs
-// __launch_bounds__(32, 1): with a higher occupancy target ptxas keeps the dependency chains back to back to
-// save registers).  Every rare case is only FLAGGED (see to_db_vec / to_amp_vec, plus follower steps that could
-// fall into the sliver 0 < |x - y| < 2^-22 where the float32 short-cut of ar_step is not proven exact).  Returns
-// true when this lane hit a flag; the caller then restores the lane state and re-runs the samples through
-// sample_exact.  CT: compile-time channel count (0 = use `step`), so that the shared-memory accesses of a chunk
-// are one base register plus immediates.
+// Back half of a chunk (see chunk_loop): 10**x, block extrema, stores of rel into the block buffer, and the vote
+// on short-cuts (vi) + (vii).  Returns true when the vote passed (the caller then sets L.mn / L.mx from minmin /
+// mx_spec), false when the trackers have to be stepped sample by sample over amp[].
+template <int U, bool DO_MM>
+__device__ __forceinline__ bool chunk_tail(Lane &L, const Coef &k, const AmpFront (&af)[U], const float (&dr)[U],
+                                           float (&amp)[U], float &mx_spec, uint32_t rp, uint32_t st, bool store,
+                                           uint32_t exptab, const MathConst &mc, bool &rel_pending, bool &bad) {
+    if (OFP_K1_LADDER == 3) {  // speed-of-light ladder: + followers
+        wait_rel(rel_pending);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (store) sts_f32(rp + u * st, dr[u]);
+        return true;
+    }
+    // |q| < 9.5 needs no test here: both envelopes stay within [floor, -3.99] through the chunk (floor invariant and
+    // sliver test in chunk_loop; the host only enables this path for floor >= -180 dB), so |dr| < 190
+    uint32_t mid = 0xffffffffu;
+    amp_back<U>(af, k.ceil_amp, exptab, mc, amp, mid);
+    bad |= amp_flagged(0.0f, mid);
+    float cmax = amp[0], cmin = amp[0];
+    const float mx0 = L.mx;
+    if (OFP_K1_LADDER >= 5) {  // 4: + 10**x only; 5 and above: the full chunk
+        // max tracker, block extrema and the stores first: they overlap the drain of the 10**x pipeline that the
+        // vote has to wait for
+#pragma unroll
+        for (int u = 1; u + 1 < U; u += 2) {
+            cmax = fmaxf(fmaxf(cmax, amp[u]), amp[u + 1]);
+            cmin = fminf(fminf(cmin, amp[u]), amp[u + 1]);
+        }
+        if (U % 2 == 0) { cmax = fmaxf(cmax, amp[U - 1]); cmin = fminf(cmin, amp[U - 1]); }
+        // (vii) The max tracker (envelope_follower.c:48-51) runs on the assumption that no sample exceeds it: every
+        // step is then the decay branch, no select in the recurrence.  The assumption holds when the chunk maximum is
+        // below mxfac = (1 - alpha_max)^U (1 - 4e-6) x the tracker's start value (the decay steps of a chunk cannot
+        // take it lower: the samples are >= 0, roundings cost < 2^-23 per step); it is checked together with
+        // short-cut (vi) by the one vote below, after the stores, so that the recurrence overlaps the 10**x pipeline.
+        mx_spec = mx0;
+        if (DO_MM) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) mx_spec = __fadd_rn(__fmul_rn(mx_spec, k.iamax), __fmul_rn(amp[u], k.amax));
+        }
+        L.bmax = fmaxf(L.bmax, cmax);
+        L.bmin = fminf(L.bmin, cmin);
+    }
+    wait_rel(rel_pending);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (store) sts_f32(rp + u * st, amp[u]);
+    if (!DO_MM || OFP_K1_LADDER < 5) return true;
+    return __all_sync(0xffffffffu, (amp[U - 1] < k.minmin) & (cmax < __fmul_rn(mx0, k.mxfac)));
+}
+
+// The chunk loop: U samples per iteration in straight-line form, one large basic block per path that ptxas can
+// software-pipeline (needs __launch_bounds__(32, 1): with a higher occupancy target ptxas keeps the dependency
+// chains back to back to save registers).  Every rare case is only FLAGGED (see to_db_vec / amp_back, plus follower
+// steps that could fall into the sliver 0 < |x - y| < 2^-22 where the float32 short-cut of ar_step is not proven
+// exact).  Returns true when this lane hit a flag; the caller then restores the lane state and re-runs the samples
+// through sample_exact.  CT: compile-time channel count (0 = use `step`), so that the shared-memory accesses of a
+// chunk are one base register plus immediates.
 //
 // Data-dependent exact short-cuts, all decided by warp votes (DESIGN.md "K1"):
-//  (iv)  no sample of the warp above the floor -> the dB values are the floor, no logarithm;
+//  (iv)  no sample of the warp above the floor -> the dB values are the floor, no logarithm, and the followers
+//        only release;
 //  (v)   at most ONE sample per lane above the floor (noise peaks: one value in a few hundred) -> one logarithm
 //        per lane (of the lane's maximum) instead of U;
 //  (vi)  the last rel value of every lane below `minmin` -> the min tracker ends at `minmin` whatever came
-//        before (envelope_follower.c:42-43), its recurrence is skipped.
+//        before (envelope_follower.c:42-43), its recurrence is skipped;
+//  (vii) no sample above the decayed max tracker -> its recurrence has no select.
+//
+// Layout.  A taken branch costs this kernel about 2.5 % of its time (one or two warps per scheduler: nothing
+// hides the refetch).  ptxas orders basic blocks topologically (every forward predecessor of a block before it), so
+// an if/else or an if around a slow path always costs the common path one taken branch, whatever __builtin_expect
+// says.  The loop is therefore written as two nested loops with gotos: the inner one is the common path -- (iv),
+// (vi) and (vii) all hold -- in one straight line from `top` to its back edge; every other case LEAVES the inner
+// loop, finishes its chunk behind it (with its own copy of chunk_tail) and re-enters through `outer`.  Every local
+// is declared before the first label (a goto must not cross an initialisation).
 template <bool USE_HP, bool HP_SYM, int U, bool DO_MM, int CT>
-__device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[U], uint32_t xs_next, uint32_t rs,
-                                           uint32_t step, bool store, uint32_t logtab, uint32_t exptab,
-                                           const MathConst &mc, bool &rel_pending) {
+__device__ __forceinline__ bool chunk_loop(Lane &L, const Coef &k, float (&xin)[U], int &i_io, const int nfast,
+                                           uint32_t &xp_io, uint32_t &rp_io, uint32_t step, bool store,
+                                           uint32_t logtab, uint32_t exptab, const MathConst &mc, bool &rel_pending) {
     const uint32_t st = CT ? 4u * CT : step;
+    constexpr bool TRACK = DO_MM && OFP_K1_LADDER >= 5;
     float h[U], v[U], db[U], dr[U], amp[U];
     AmpFront af[U];  // fronts of the 10**x evaluations, issued inside the follower loops
-    uint32_t spec = 0, mid = 0xffffffffu;
-    bool bad = false;
+    uint32_t spec, mid, xp, rp;
+    float hmax, dbmax, m1, m2, mx_spec, ytop;
+    bool bad, skip;
+    int i;
+    i = i_io; xp = xp_io; rp = rp_io;
+    bad = false;
+outer:
+    if (i >= nfast) goto done;
+top:
 #pragma unroll
     for (int u = 0; u < U; ++u)
         h[u] = (USE_HP && OFP_K1_LADDER >= 1) ? (HP_SYM ? hp_step_sym(L, k, xin[u]) : hp_step(L, k, xin[u])) : xin[u];
     // the NEXT chunk's input is fetched now (its shared-memory latency hides behind this chunk); past the end of a
     // tile this reads the neighbouring stage / the block buffer -- defined addresses, values never used
 #pragma unroll
-    for (int u = 0; u < U; ++u) xin[u] = lds_f32(xs_next + u * st);
-#if OFP_K1_LADDER <= 1  // speed-of-light ladder (profiles/): memory path only / + high-pass; results are NOT the detector's
-    wait_rel(rel_pending);
+    for (int u = 0; u < U; ++u) xin[u] = lds_f32(xp + (U + u) * st);
+    if (OFP_K1_LADDER <= 1) {  // speed-of-light ladder (profiles/): memory path only / + high-pass
+        wait_rel(rel_pending);
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * st, h[u]);
-    return false;
-#endif
+        for (int u = 0; u < U; ++u)
+            if (store) sts_f32(rp + u * st, h[u]);
+        goto next;
+    }
     // |h| < vfloor_h implies |h + 1e-10| < vfloor (vfloor_h = vfloor (1 - 2^-23) - 1e-10, rounded down)
-    float hmax = 0.0f;
+    hmax = 0.0f;
 #pragma unroll
     for (int u = 0; u < U; ++u) hmax = fmaxf(hmax, fabsf(h[u]));
-    float dbmax = k.floor_db;  // largest dB value of the chunk (sliver test below)
-    const bool skip = __all_sync(0xffffffffu, hmax < k.vfloor_h);
-    if (__builtin_expect(skip, 1)) {  // (iv)
-#pragma unroll
-        for (int u = 0; u < U; ++u) db[u] = k.floor_db;
-    } else {
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = fabsf(__fadd_rn(h[u], 1e-10f));
-        float m1 = v[0], m2 = 0.0f;  // largest and second largest of the lane
-#pragma unroll
-        for (int u = 1; u < U; ++u) { m2 = fmaxf(m2, fminf(m1, v[u])); m1 = fmaxf(m1, v[u]); }
-        if (OFP_K1_SPARSE && __all_sync(0xffffffffu, m2 < k.vfloor)) {  // (v)
-            // the lane's other samples are below the floor; if its maximum is too, db1 comes out as the floor
-            float v1[1] = {m1}, db1[1];
-            to_db_vec<1>(v1, k.floor_db, logtab, mc, db1, spec, mid);
-            bad = db_flagged(spec, mid) & (m1 >= k.vfloor);
-            dbmax = m1 >= k.vfloor ? db1[0] : k.floor_db;  // (a special value below the floor must not leak through)
-#pragma unroll
-            for (int u = 0; u < U; ++u) db[u] = v[u] == m1 ? dbmax : k.floor_db;
-        } else {
-            to_db_vec<U>(v, k.floor_db, logtab, mc, db, spec, mid);
-            bad = db_flagged(spec, mid);
-#pragma unroll
-            for (int u = 0; u < U; ++u) dbmax = fmaxf(dbmax, db[u]);
-        }
-    }
-#if OFP_K1_LADDER == 2  // + dB
-    wait_rel(rel_pending);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * st, db[u]);
-    return bad;
-#endif
+    skip = __all_sync(0xffffffffu, hmax < k.vfloor_h);
     // Followers (envelope_follower.c:15-22).  0 < |x - y| < 2^-22 (the sliver in which float(double(t) + 1e-10)
     // differs from t + 1e-10f) needs min(|x|, |y|) < 2.  With every dB value of the chunk and both envelopes at
     // its start <= -4, the envelopes stay <= -3.99 throughout (a step moves y towards x by a factor <= 1 up to
     // rounding), so one test per chunk is enough; anything else re-runs exactly.
-    bad |= !((dbmax <= k.sliver_thr) & (L.yf <= k.sliver_thr) & (L.ys <= k.sliver_thr));
+    bad |= !((k.floor_db <= k.sliver_thr) & (L.yf <= k.sliver_thr) & (L.ys <= k.sliver_thr));
     // floor invariant of the envelopes (every dB value is >= floor, a step moves y towards x): holds from the reset
     // on, but a state injected through ofp_detector_set_state may violate it
     bad |= !((L.yf >= k.floor_db) & (L.ys >= k.floor_db));
+    if (!skip) goto general;
+    // (iv): x is the floor and y >= floor (tested above, and kept through the chunk: release coefficients <= 1/2, a
+    // step covers at most half the distance, rounding is monotone and the floor is a float), so
+    // d = (floor - y) + 1e-10 <= 1e-10 and the release coefficient applies; d > 0 only for y == floor, where either
+    // coefficient (<= 16) leaves y unchanged (|coef d| <= 1.6e-9, far below half an ulp of y <= -3.99), so
+    // y + rel * d is the reference's value.
+    if (OFP_K1_LADDER == 2) {
+        wait_rel(rel_pending);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (store) sts_f32(rp + u * st, k.floor_db);
+        goto next;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float d1 = __fadd_rn(__fsub_rn(k.floor_db, L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(k.floor_db, L.ys), 1e-10f);
+        L.yf = __fadd_rn(L.yf, __fmul_rn(k.fr, d1));
+        L.ys = __fadd_rn(L.ys, __fmul_rn(k.sr, d2));
+        dr[u] = __fsub_rn(L.yf, L.ys);
+        af[u] = amp_front(dr[u]);
+    }
+    if (!chunk_tail<U, DO_MM>(L, k, af, dr, amp, mx_spec, rp, st, store, exptab, mc, rel_pending, bad)) goto trackers;
+    if (TRACK) { L.mn = k.minmin; L.mx = mx_spec; }  // (vi), (vii)
+next:
+    i += U; xp += U * st; rp += U * st;
+    if (i < nfast) goto top;
+done:
+    i_io = i; xp_io = xp; rp_io = rp;
+    return bad;
+
+    // ---- behind the inner loop: a chunk with samples above the floor ----
+general:
+    spec = 0; mid = 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = fabsf(__fadd_rn(h[u], 1e-10f));
+    m1 = v[0]; m2 = 0.0f;  // largest and second largest of the lane
+#pragma unroll
+    for (int u = 1; u < U; ++u) { m2 = fmaxf(m2, fminf(m1, v[u])); m1 = fmaxf(m1, v[u]); }
+    if (OFP_K1_SPARSE && __all_sync(0xffffffffu, m2 < k.vfloor)) {  // (v)
+        // the lane's other samples are below the floor; if its maximum is too, db1 comes out as the floor
+        float v1[1], db1[1];
+        v1[0] = m1;
+        to_db_vec<1>(v1, k.floor_db, logtab, mc, db1, spec, mid);
+        bad |= db_flagged(spec, mid) & (m1 >= k.vfloor);
+        dbmax = m1 >= k.vfloor ? db1[0] : k.floor_db;  // (a special value below the floor must not leak through)
+#pragma unroll
+        for (int u = 0; u < U; ++u) db[u] = v[u] == m1 ? dbmax : k.floor_db;
+    } else {
+        to_db_vec<U>(v, k.floor_db, logtab, mc, db, spec, mid);
+        bad |= db_flagged(spec, mid);
+        dbmax = k.floor_db;
+#pragma unroll
+        for (int u = 0; u < U; ++u) dbmax = fmaxf(dbmax, db[u]);
+    }
+    if (OFP_K1_LADDER == 2) {  // + dB
+        wait_rel(rel_pending);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (store) sts_f32(rp + u * st, db[u]);
+        i += U; xp += U * st; rp += U * st;
+        goto outer;
+    }
+    bad |= !(dbmax <= k.sliver_thr);  // largest dB value of the chunk: the sliver test above
     // coef * d with coef = d > 0 ? att : rel is max(att * d, rel * d) for att >= rel >= 0 (rounding is monotone)
     // and -max(-att * d, -rel * d) for rel > att >= 0: the host passes (A, R, s) = (s att, s rel, s = +-1).
-    // Below-floor chunks (iv) know more: x is the floor and y >= floor, so d = (floor - y) + 1e-10 <= 1e-10 and the
-    // release coefficient applies; d > 0 only for y == floor, where either coefficient (<= 16) leaves y unchanged
-    // (|coef d| <= 1.6e-9, far below half an ulp of y <= -3.99), so y + rel * d is the reference's value.
-    if (OFP_K1_SKIPFOL && __builtin_expect(skip, 1)) {
-        // y >= floor at the start (tested above) keeps y >= floor through the chunk (release coefficients <= 1/2: a
-        // step covers at most half the distance, rounding is monotone and the floor is a float): every d <= 1e-10
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float d1 = __fadd_rn(__fsub_rn(k.floor_db, L.yf), 1e-10f), d2 = __fadd_rn(__fsub_rn(k.floor_db, L.ys), 1e-10f);
-            L.yf = __fadd_rn(L.yf, __fmul_rn(k.fr, d1));
-            L.ys = __fadd_rn(L.ys, __fmul_rn(k.sr, d2));
-            dr[u] = __fsub_rn(L.yf, L.ys);
-            af[u] = amp_front(dr[u]);
-        }
-    } else {
-        // an attack coefficient above 1 (the reference's realtime settings use 1 / 0.3) overshoots its input: the
-        // envelopes are followed through the chunk and must stay <= -4 for the sliver argument above
-        // (attack coefficients <= 1 cannot overshoot: the chunk-start test above covers them, no per-step tracking)
-        float ytop = -INFINITY;
+    // An attack coefficient above 1 (the reference's realtime settings use 1 / 0.3) overshoots its input: the
+    // envelopes are then followed through the chunk and must stay <= -4 for the sliver argument above (attack
+    // coefficients <= 1 cannot overshoot: the chunk-start test covers them, no per-step tracking).
+    {
+        ytop = -INFINITY;
         auto steps = [&](auto track) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -550,59 +627,16 @@ __device__ __forceinline__ bool chunk_fast(Lane &L, const Coef &k, float (&xin)[
         if (k.overshoot != 0.0f) { steps(std::true_type{}); bad |= !(ytop <= k.sliver_thr); }
         else steps(std::false_type{});
     }
-#if OFP_K1_LADDER == 3  // + followers
-    wait_rel(rel_pending);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * st, dr[u]);
-    return bad;
-#endif
-    // |q| < 9.5 needs no test here: both envelopes stay within [floor, -3.99] through the chunk (floor invariant and
-    // sliver test above; the host only enables this path for floor >= -180 dB), so |dr| < 190
-    mid = 0xffffffffu;
-    amp_back<U>(af, k.ceil_amp, exptab, mc, amp, mid);
-    bad |= amp_flagged(0.0f, mid);
-#if OFP_K1_LADDER >= 5  // 4: + 10**x only; 5 and above: the full chunk
-    // max tracker, block extrema and the stores first: they overlap the drain of the 10**x pipeline that the
-    // vote of short-cut (vi) has to wait for
-    float cmax = amp[0], cmin = amp[0];
-#pragma unroll
-    for (int u = 1; u + 1 < U; u += 2) {
-        cmax = fmaxf(fmaxf(cmax, amp[u]), amp[u + 1]);
-        cmin = fminf(fminf(cmin, amp[u]), amp[u + 1]);
+    if (chunk_tail<U, DO_MM>(L, k, af, dr, amp, mx_spec, rp, st, store, exptab, mc, rel_pending, bad)) {
+        if (TRACK) { L.mn = k.minmin; L.mx = mx_spec; }
+        i += U; xp += U * st; rp += U * st;
+        goto outer;
     }
-    if (U % 2 == 0) { cmax = fmaxf(cmax, amp[U - 1]); cmin = fminf(cmin, amp[U - 1]); }
-    // The max tracker (envelope_follower.c:48-51) runs on the assumption that no sample exceeds it: every step is
-    // then the decay branch, no select in the recurrence.  The assumption holds when the chunk maximum is below
-    // mxfac = (1 - alpha_max)^U (1 - 4e-6) x the tracker's start value (the decay steps of a chunk cannot take it
-    // lower: the samples are >= 0, roundings cost < 2^-23 per step); it is checked together with
-    // short-cut (vi) by the one vote below, after the stores, so that the recurrence overlaps the 10**x pipeline.
-    const float mx0 = L.mx;
-    float mx_spec = mx0;
-    if (DO_MM && OFP_K1_MXSPEC) {
+trackers:  // (vi) or (vii) failed: the reference's recurrences, sample by sample
 #pragma unroll
-        for (int u = 0; u < U; ++u) mx_spec = __fadd_rn(__fmul_rn(mx_spec, k.iamax), __fmul_rn(amp[u], k.amax));
-    }
-    L.bmax = fmaxf(L.bmax, cmax);
-    L.bmin = fminf(L.bmin, cmin);
-#endif
-    wait_rel(rel_pending);
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (store) sts_f32(rs + u * st, amp[u]);
-#if OFP_K1_LADDER >= 5
-    if (DO_MM) {
-        const bool quiet = (amp[U - 1] < k.minmin) & (cmax < __fmul_rn(mx0, k.mxfac));
-        if (OFP_K1_MNVOTE && OFP_K1_MXSPEC && __builtin_expect(__all_sync(0xffffffffu, quiet), 1)) {  // (vi) + (vii)
-            L.mn = k.minmin;
-            L.mx = mx_spec;
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; ++u) minmax_step(L, k, amp[u]);
-        }
-    }
-#endif
-    return bad;
+    for (int u = 0; u < U; ++u) minmax_step(L, k, amp[u]);
+    i += U; xp += U * st; rp += U * st;
+    goto outer;
 }
 
 __device__ __align__(16) double g_logtab[2 << OFP_LOG_N];
@@ -850,13 +884,12 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                         float xin[KU];  // the chunk's input samples, fetched one chunk ahead
 #pragma unroll
                         for (int u = 0; u < KU; ++u) xin[u] = lds_f32(xp + u * step);
-                        auto chunks = [&](auto mm) {
-                            for (; i < nfast; i += KU, xp += KU * step, rp += KU * step)
-                                bad |= chunk_fast<USE_HP, HP_SYM, KU, decltype(mm)::value, CT>(
-                                    L, kf, xin, xp + KU * step, rp, step, in_group, logtab_s, exptab_s, mc, rel_pending);
-                        };
-                        if (do_minmax) chunks(std::true_type{});
-                        else chunks(std::false_type{});
+                        if (do_minmax)
+                            bad = chunk_loop<USE_HP, HP_SYM, KU, true, CT>(L, kf, xin, i, nfast, xp, rp, step, in_group,
+                                                                           logtab_s, exptab_s, mc, rel_pending);
+                        else
+                            bad = chunk_loop<USE_HP, HP_SYM, KU, false, CT>(L, kf, xin, i, nfast, xp, rp, step, in_group,
+                                                                            logtab_s, exptab_s, mc, rel_pending);
                         if (__builtin_expect(__any_sync(0xffffffffu, bad), 0)) {
                             L = saved;
                             for (int e = 0; e < nfast; ++e)
