@@ -67,6 +67,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
+// the same three operations on 32-bit shared-window addresses (a kernel that keeps its base address in a register
+// saves the generic -> shared conversion, which ptxas rebuilds from SR_CgaCtaId at every use)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_s, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(bar_s), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_s, const CUtensorMap *map, uint32_t bar_s, int32_t c0,
+                                            int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst_s), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar_s)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t c0,
                                             int32_t c1) {
     asm volatile(
@@ -77,6 +103,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 // Bulk copy shared -> global (one contiguous run, 16-byte aligned on both sides, size a multiple of 16) in the
 // issuing thread's bulk async-group; bulk_wait_read<N>() returns once all but the N newest groups have finished
 // READING their shared-memory source (the buffer may then be overwritten).
+__device__ __forceinline__ void bulk_store(void *dst_global, uint32_t src_s, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst_global)),
+                 "r"(src_s), "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_store(void *dst_global, const void *src_shared, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst_global)),
                  "r"(smem_u32(src_shared)), "r"(bytes)

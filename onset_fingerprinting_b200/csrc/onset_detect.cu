@@ -50,6 +50,9 @@
 #ifndef OFP_K1_KMAGIC  // log10: exponent -> double by a magic-constant subtraction instead of I2F
 #define OFP_K1_KMAGIC 1
 #endif
+#ifndef OFP_K1_LAUNDER_TAB
+#define OFP_K1_LAUNDER_TAB 1  // measured: 55.0 ms with the opaque base, 56.4 ms without
+#endif
 #ifndef OFP_K1_FOLMAX  // followers: coef * d as max(att * d, rel * d) instead of a select
 #define OFP_K1_FOLMAX 1
 #endif
@@ -669,15 +672,16 @@ __device__ __forceinline__ void launder(Coef &k, MathConst &mc, uint32_t scratch
 
 // End of a block (main phase): the reference's threshold FSM (detection.py:759-792) on the block held in shared
 // memory, onset compaction in the reference's order, and the copy of the block's rel envelope to HBM
-// (rcol = this lane's column of row 0).  With 16-byte aligned rows the copy is one bulk async copy per recording
+// (rcol_s = shared address of this lane's column of row 0).  With 16-byte aligned rows the copy is one bulk async copy per recording
 // (cp.async.bulk shared -> global, issued by lane 0): the warp does not touch the data again, and
 // `rel_pending` tells the next writer of the block buffer to wait until the copy engine has read it.
-__device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float *rcol, const float *relbuf, int lane,
+__device__ __forceinline__ void block_end(Lane &L, const K1Args &a, uint32_t rcol_s, const float *relbuf,
+                                          uint32_t relbuf_s, int lane,
                                           int g, int c, int rec, int rec0, bool active, unsigned rec_mask,
                                           unsigned lower_mask, int32_t &cnt, int64_t blk, bool &rel_pending) {
     const int C = a.p.n_channels, B = a.p.block_size, G = a.G;
     // ---- block FSM, detection.py:759-792 ----
-    const float last = rcol[(B - 1) * C];
+    const float last = lds_f32(rcol_s + 4u * ((B - 1) * C));
     const float thr_on = a.p.manual ? a.p.on_thr
                                     : __fadd_rn(__fmul_rn(L.mx, a.p.on_thr), L.mn);
     const float thr_off = a.p.manual ? a.p.off_thr
@@ -687,7 +691,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     if (!L.state && L.deb < 1 && L.bmax > thr_on) {
         float before = L.prev;
         for (int k = 0; k < B; ++k) {
-            const float r = rcol[k * C];
+            const float r = lds_f32(rcol_s + 4u * (k * C));
             if (r > thr_on && before < thr_on) { oi = k; hit = true; break; }
             before = r;
         }
@@ -703,7 +707,7 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
     if (M == 0) off = L.bmin < thr_off;
     else {
         for (int k = M; k < B; ++k)
-            if (rcol[k * C] < thr_off) { off = true; break; }
+            if (lds_f32(rcol_s + 4u * (k * C)) < thr_off) { off = true; break; }
     }
     if (off) L.state = 0;
     L.prev = last;
@@ -725,9 +729,9 @@ __device__ __forceinline__ void block_end(Lane &L, const K1Args &a, const float 
             // lanes issuing one copy each become a divergence loop of G iterations anyway, with more bookkeeping
             if (lane == 0) {
                 float *dst = a.rel + static_cast<int64_t>(rec0) * a.rel_stride + (blk - a.blk0) * nBC;
-                const float *src = relbuf;
+                uint32_t src = relbuf_s;
                 const int ng = min(G, a.R - rec0);
-                for (int gi = 0; gi < ng; ++gi, dst += a.rel_stride, src += a.stride_rel)
+                for (int gi = 0; gi < ng; ++gi, dst += a.rel_stride, src += 4u * a.stride_rel)
                     bulk_store(dst, src, static_cast<uint32_t>(nBC) * 4u);
             }
             bulk_commit();
@@ -770,10 +774,26 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     const unsigned lower_mask = rec_mask & ((1u << lane) - 1u);
 
     Coef kf = load_coef(a);
-    const uint32_t logtab_s = smem_u32(logtab), exptab_s = smem_u32(exptab);
     const uint32_t step = 4u * C;
     MathConst mc = math_const();
     launder(kf, mc, smem_u32(relbuf));
+#if OFP_K1_LAUNDER_TAB
+    // The base of the shared-memory window as an opaque register: ptxas otherwise rebuilds every shared address in
+    // the uniform datapath at its use (S2UR of the CTA's rank in the cluster + ULEA, a 20-cycle chain in front of
+    // the table loads of every chunk and of the barrier / TMA operations of every tile).
+    uint32_t smem_s = smem_u32(smem);
+    {
+        const uint32_t scratch = smem_u32(relbuf) + 512;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(scratch), "r"(smem_s) : "memory");
+        __syncwarp();
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(smem_s) : "r"(scratch) : "memory");
+        __syncwarp();
+    }
+#else
+    const uint32_t smem_s = smem_u32(smem);
+#endif
+    const uint32_t bars_s = smem_s, logtab_s = smem_s + 128, exptab_s = logtab_s + (2 << OFP_LOG_N) * 8;
+    const uint32_t stages_s = smem_s + K1_SMEM_HEADER;
     Lane L;
     if (active) {
         L.z0 = a.st.z0[lid]; L.z1 = a.st.z1[lid]; L.z2 = a.st.z2[lid]; L.z3 = a.st.z3[lid];
@@ -812,9 +832,9 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
     int32_t cnt = (a.cnt_in && active) ? a.on_cnt[rec] : 0;  // onsets emitted for this lane's recording
     int64_t blk = a.blk0;  // main-phase block index (global; a.blk0 != 0 when a recording is fed in segments)
 
-    float *rcol = relbuf + g * a.stride_rel + c;  // this lane's column of the block buffer
-    const uint32_t rcol_s = smem_u32(rcol);
-    const uint32_t stage0_s = smem_u32(stages) + 4u * (g * P + c);
+    const uint32_t relbuf_s = stages_s + static_cast<uint32_t>(a.nst) * 4u * static_cast<uint32_t>(a.stage_floats);
+    const uint32_t rcol_s = relbuf_s + 4u * static_cast<uint32_t>(g * a.stride_rel + c);
+    const uint32_t stage0_s = stages_s + 4u * (g * P + c);
 
     bool rel_pending = false;  // a bulk copy of the block buffer to HBM is in flight (block_end)
     int s_cur = 0;             // ring position of the tile being consumed
@@ -832,8 +852,8 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
         if (USE_TMA && lane == 0) {
             int sp = s_cur;
             for (int p = 0; p < nst - 1 && p < ntiles; ++p) {
-                mbar_expect_tx(&bars[sp], box_bytes);
-                tma_load_2d(stages + static_cast<size_t>(sp) * a.stage_floats, &tmap, &bars[sp], p * TC, rec0);
+                mbar_expect_tx(bars_s + 8u * sp, box_bytes);
+                tma_load_2d(stages_s + static_cast<uint32_t>(sp) * stage_bytes, &tmap, bars_s + 8u * sp, p * TC, rec0);
                 sp = sp + 1 == nst ? 0 : sp + 1;
             }
         }
@@ -844,10 +864,10 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                 const int nx = ti + nst - 1;
                 if (lane == 0 && nx < ntiles) {
                     const int sn = s_cur == 0 ? nst - 1 : s_cur - 1;  // the stage consumed last
-                    mbar_expect_tx(&bars[sn], box_bytes);
-                    tma_load_2d(stages + static_cast<size_t>(sn) * a.stage_floats, &tmap, &bars[sn], nx * TC, rec0);
+                    mbar_expect_tx(bars_s + 8u * sn, box_bytes);
+                    tma_load_2d(stages_s + static_cast<uint32_t>(sn) * stage_bytes, &tmap, bars_s + 8u * sn, nx * TC, rec0);
                 }
-                mbar_wait(&bars[s], par);
+                mbar_wait(bars_s + 8u * s, par);
                 if (++s_cur == nst) { s_cur = 0; par ^= 1u; }
             } else {
                 // generic path (unaligned input): cooperative copy of the tile into stage 0
@@ -904,8 +924,8 @@ __global__ void __launch_bounds__(32, 1) k1_detect(const __grid_constant__ CUten
                     if (kpos == B) {
                         kpos = 0;
                         if (phase == 1) {
-                            block_end(L, a, rcol, relbuf, lane, g, c, rec, rec0, active, rec_mask, lower_mask, cnt, blk,
-                                      rel_pending);
+                            block_end(L, a, rcol_s, relbuf, relbuf_s, lane, g, c, rec, rec0, active, rec_mask, lower_mask,
+                                      cnt, blk, rel_pending);
                             ++blk;
                         }
                         L.bmax = -INFINITY; L.bmin = INFINITY;
@@ -1088,7 +1108,8 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
         // pad the rows of a stage so that the G rows start 4 banks apart (the per-sample LDS of a warp touches one
         // word per lane: rows starting in the same bank conflict); the TMA box simply reads the extra columns
         const int want = ((C + 3) / 4 * 4) % 32;
-        int pad = ((want - a.TC % 32) + 32) % 32;
+        // rows `want` banks apart in either direction are equally good: take the smaller pad
+        int pad = std::min(((want - a.TC % 32) + 32) % 32, ((32 - want - a.TC % 32) + 64) % 32);
         // off by default: at T = 40 the padded stages cost the seventh resident CTA per SM (84 vs 59 ms) and the
         // 3-way conflicts of the unpadded rows are not visible in the kernel time; T = 32 padded is equally fast
         if (!env_int("OFP_K1_PAD", 0) || a.TC + pad > 256 || (a.TC + pad) % 4 != 0) pad = 0;
