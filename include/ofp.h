@@ -414,7 +414,7 @@ int ofp_rt_results(ofp_rt *rt, const double **xy_host, const int32_t **found_hos
 
 /* ---------------------------------------------------------------------------------------
  * K6  onset-window network inference -- replaces model.CNN.forward in eval mode (model.py:52-120):
- *     n_layers x [Conv1d(kernel_size, padding; stride 1, dilation 1, groups 1) + activation],
+ *     n_layers x [Conv1d(kernel_size, padding, dilation, groups; stride 1) + activation (+ BatchNorm1d) (+ MaxPool1d(2))],
  *     flatten (channel-major), Dropout = identity, Linear(flat, out_size).
  * ------------------------------------------------------------------------------------- */
 
@@ -430,6 +430,20 @@ int ofp_cnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers, 
 int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
                     int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
                     int32_t activation, const float *params_dev, int32_t out_size, float *out_dev, void *stream);
+
+/* The same network with the constructor options the reference's CNN also has (model.py:62-66, 91-108):
+ * dilation >= 1; pool != 0: MaxPool1d(kernel_size=2, stride=2) after every layer's activation (and norm);
+ * batch_norm != 0: eval-mode BatchNorm1d behind every activation, passed as scale = weight / sqrt(running_var + eps)
+ * and shift = bias - running_mean * scale, [c_out_padded] floats each, packed right behind the layer's bias.
+ * `groups` needs no argument: pack the grouped weight as a dense [c_in][k][c_out_padded] block with zeros between the
+ * groups.  (dilation, pool, batch_norm) = (1, 0, 0) is ofp_cnn_forward / ofp_cnn_param_count. */
+int ofp_cnn_param_count_ex(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
+                           int32_t kernel_size, int32_t padding, int32_t dilation, int32_t pool, int32_t batch_norm,
+                           int32_t out_size, int64_t *n_params_out, int32_t *flat_out);
+int ofp_cnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
+                       int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
+                       int32_t dilation, int32_t pool, int32_t batch_norm, int32_t activation, const float *params_dev,
+                       int32_t out_size, float *out_dev, void *stream);
 
 /* model.CCCNN.forward in eval mode (model.py:443-538): the conv stack (as above, but with ONE input
  * channel) runs on every sensor channel separately, the K feature maps of a channel are auto-correlated over all

@@ -28,6 +28,8 @@ struct K6Args {
     int64_t n, win_stride;
     int32_t C0, W, n_layers, ks, pad, act, out_size;
     int32_t cin[K6_MAX_LAYERS], cout[K6_MAX_LAYERS], coutp[K6_MAX_LAYERS], lin[K6_MAX_LAYERS], lout[K6_MAX_LAYERS];
+    int32_t dil, pool, bn;   // k6_cnn only: dilation (>= 1), MaxPool1d(2, 2) after every layer, eval-mode BatchNorm1d as
+                             // scale[coutp] + shift[coutp] behind every layer's bias; lout is the length AFTER pooling
     int32_t w_off[K6_MAX_LAYERS], b_off[K6_MAX_LAYERS];  // float offsets into params
     int32_t fc_w_off, fc_b_off, n_params, conv_params;   // conv_params: floats staged in shared memory always
     int32_t fc_in_smem;
@@ -61,6 +63,25 @@ __device__ __forceinline__ void k6_activate(float (&acc)[8][P]) {
 
 // Epilogue of one activated 8-channel x P tile: the next layer's input rows (OUT = 0) or the Linear layer
 // with OUT <= 4 outputs accumulated straight from the registers against fc weights in shared memory.
+// MaxPool1d(2, 2) (model.py:104-107) of one activated tile into the next layer's input rows: neighbouring positions
+// sit in neighbouring lanes, the even lane of a pair writes max(y[2j], y[2j+1]) to position j < Lout = floor(L / 2).
+template <int P>
+__device__ __forceinline__ void k6_epilogue_pool(const float (&acc)[8][P], int ob, int Cout, int Lout, int lane,
+                                                 float *outb, int RS, int pad) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        if (ob + o < Cout) {  // uniform
+            float *orow = outb + (ob + o) * RS + pad;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float m = fmaxf(acc[o][p], __shfl_xor_sync(0xffffffffu, acc[o][p], 1));
+                const int j = (lane + 32 * p) >> 1;
+                if (!(lane & 1) && j < Lout) orow[j] = m;
+            }
+        }
+    }
+}
+
 template <int P, int OUT>
 __device__ __forceinline__ void k6_epilogue(const float (&acc)[8][P], int ob, int Cout, int Lout, int lane,
                                             float *outb, int RS, int pad, const float *fcw, float (&fcacc)[4]) {
@@ -108,7 +129,7 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 2) k6_cnn(const K6Args a) {
     const bool fuse_fc = a.fc_in_smem != 0;
     const float *fcw = prm + a.fc_w_off;                  // shared (only dereferenced when fuse_fc)
     const float *fcw_g = a.params + a.fc_w_off, *fcb = a.params + a.fc_b_off;
-    const int RS = a.row_stride, pad = a.pad;
+    const int RS = a.row_stride, pad = a.pad, dil = a.dil;
 
     for (int64_t wi = static_cast<int64_t>(blockIdx.x) * NW + warp; wi < a.n;
          wi += static_cast<int64_t>(gridDim.x) * NW) {
@@ -142,7 +163,7 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 2) k6_cnn(const K6Args a) {
                         const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
                         for (int p = 0; p < P; ++p) {
-                            const float xin = row[32 * p + k];
+                            const float xin = row[32 * p + k * dil];
 #pragma unroll
                             for (int o = 0; o < 8; ++o) acc[o][p] = fmaf(wv[o], xin, acc[o][p]);
                         }
@@ -154,6 +175,18 @@ __global__ void __launch_bounds__(K6_WARPS * 32, 2) k6_cnn(const K6Args a) {
                     case 1: k6_activate<1, P>(acc); break;
                     case 2: k6_activate<2, P>(acc); break;
                     default: break;
+                }
+                if (a.bn) {  // eval-mode BatchNorm1d behind the activation (model.py:100-103): y * scale + shift
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        const float sc = bias[CP + ob + o], sh = bias[2 * CP + ob + o];
+#pragma unroll
+                        for (int p = 0; p < P; ++p) acc[o][p] = fmaf(acc[o][p], sc, sh);
+                    }
+                }
+                if (a.pool) {  // uniform; never together with the fused Linear layer
+                    k6_epilogue_pool<P>(acc, ob, Cout, Lout, lane, outb, RS, pad);
+                    continue;
                 }
                 switch ((last && fuse_fc) ? a.out_size : 0) {  // uniform
                     case 0: k6_epilogue<P, 0>(acc, ob, Cout, Lout, lane, outb, RS, pad, fcw, fcacc); break;
@@ -212,14 +245,24 @@ extern "C" {
 int ofp_cnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
                         int32_t kernel_size, int32_t padding, int32_t out_size, int64_t *n_params_out,
                         int32_t *flat_out) {
+    return ofp_cnn_param_count_ex(channels, input_size, n_layers, layer_sizes_host, kernel_size, padding, 1, 0, 0,
+                                  out_size, n_params_out, flat_out);
+}
+
+int ofp_cnn_param_count_ex(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
+                           int32_t kernel_size, int32_t padding, int32_t dilation, int32_t pool, int32_t batch_norm,
+                           int32_t out_size, int64_t *n_params_out, int32_t *flat_out) {
     OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS && layer_sizes_host && n_params_out, "bad argument");
+    OFP_REQUIRE(dilation >= 1, "dilation must be >= 1");
     int64_t n = 0;
     int cin = channels, len = input_size;
     for (int l = 0; l < n_layers; ++l) {
         const int cout = layer_sizes_host[l], cp = (cout + 7) & ~7;
-        n += static_cast<int64_t>(cin) * kernel_size * cp + cp;
-        len = len + 2 * padding - (kernel_size - 1);
+        n += static_cast<int64_t>(cin) * kernel_size * cp + cp + (batch_norm ? 2 * cp : 0);
+        len = len + 2 * padding - dilation * (kernel_size - 1);
         OFP_REQUIRE(len >= 1, "layer %d has no output positions", l);
+        if (pool) len /= 2;
+        OFP_REQUIRE(len >= 1, "layer %d has no output positions after pooling", l);
         cin = cout;
     }
     n += static_cast<int64_t>(out_size) * cin * len + out_size;
@@ -231,7 +274,18 @@ int ofp_cnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers, 
 int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
                     int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
                     int32_t activation, const float *params_dev, int32_t out_size, float *out_dev, void *stream) {
+    return ofp_cnn_forward_ex(x_dev, n_windows, win_stride, channels, input_size, n_layers, layer_sizes_host, kernel_size,
+                              padding, 1, 0, 0, activation, params_dev, out_size, out_dev, stream);
+}
+
+int ofp_cnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
+                       int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
+                       int32_t dilation, int32_t pool, int32_t batch_norm, int32_t activation, const float *params_dev,
+                       int32_t out_size, float *out_dev, void *stream) {
     OFP_REQUIRE(x_dev && params_dev && out_dev && layer_sizes_host, "null argument");
+    OFP_REQUIRE(dilation >= 1 && dilation <= 16, "dilation 1..16 supported");
+    pool = pool != 0; batch_norm = batch_norm != 0;
+    const bool plain = dilation == 1 && !pool && !batch_norm;
     OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS, "1..%d conv layers supported", K6_MAX_LAYERS);
     OFP_REQUIRE(kernel_size == 1 || kernel_size == 3 || kernel_size == 5 || kernel_size == 7,
                 "kernel_size must be 1, 3, 5 or 7");
@@ -243,18 +297,20 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
     K6Args a{};
     a.x = x_dev; a.n = n_windows; a.win_stride = win_stride; a.C0 = channels; a.W = input_size; a.n_layers = n_layers;
     a.ks = kernel_size; a.pad = padding; a.act = activation; a.out_size = out_size; a.params = params_dev;
-    a.out = out_dev;
+    a.out = out_dev; a.dil = dilation; a.pool = pool; a.bn = batch_norm;
     int cin = channels, len = input_size, off = 0, max_len = input_size, max_rows = channels, max_rows_all = channels;
     for (int l = 0; l < n_layers; ++l) {
         const int cout = layer_sizes_host[l], cp = (cout + 7) & ~7;
         OFP_REQUIRE(cout >= 1 && cout <= 64, "layer sizes 1..64 supported");
         a.cin[l] = cin; a.cout[l] = cout; a.coutp[l] = cp; a.lin[l] = len;
         a.w_off[l] = off; off += cin * kernel_size * cp;
-        a.b_off[l] = off; off += cp;
-        len = len + 2 * padding - (kernel_size - 1);
+        a.b_off[l] = off; off += cp + (batch_norm ? 2 * cp : 0);
+        len = len + 2 * padding - dilation * (kernel_size - 1);
         OFP_REQUIRE(len >= 1 && len <= 256, "layer %d output length %d outside 1..256", l, len);
+        max_len = std::max(max_len, len);  // the register tile covers the positions BEFORE pooling
+        if (pool) len /= 2;
+        OFP_REQUIRE(len >= 1, "layer %d has no output positions after pooling", l);
         a.lout[l] = len;
-        max_len = std::max(max_len, len);
         max_rows_all = std::max(max_rows_all, cout);
         if (l + 1 < n_layers) max_rows = std::max(max_rows, cout);  // a fused last layer stays in registers
         cin = cout;
@@ -266,10 +322,10 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
     a.n_params = off;
     const int P = max_len <= 64 ? 2 : (max_len <= 128 ? 4 : 8);
     // odd multiple-of-nothing row stride is fine (all accesses are 32 consecutive words); room for the halo
-    a.row_stride = 32 * P + 2 * padding + kernel_size + 1;
+    a.row_stride = 32 * P + 2 * padding + dilation * (kernel_size - 1) + 2;
     // Tensor-core path for the reference's default shape: [C0 -> 8 -> 16], k = 3, padding 1, SiLU, <= 4 outputs
     const bool no_tc = getenv("OFP_K6_NO_TC") != nullptr;  // read per call: tests compare both kernels in one process
-    if (!no_tc && n_layers == 2 && kernel_size == 3 && padding == 1 && activation == 0 && out_size <= 4 &&
+    if (!no_tc && plain && n_layers == 2 && kernel_size == 3 && padding == 1 && activation == 0 && out_size <= 4 &&
         layer_sizes_host[0] == K6T_C1 && layer_sizes_host[1] == K6T_C2 && input_size % 16 == 0 && channels <= 8) {
         const int n_w1 = channels * 24 + 8;
         const size_t smem_tc = sizeof(float) * (((n_w1 + 3) & ~3) + static_cast<size_t>(out_size) * K6T_C2 * K6T_FCS +
@@ -291,7 +347,7 @@ int ofp_cnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride, i
     // staged and fused (2 CTAs per SM) when that fits, else 4 / 2 / 1 warps and the Linear read through L1.
     int warps = K6_WARPS;
     auto act_bytes_of = [&](int w, int rows) { return sizeof(float) * w * 2 * static_cast<size_t>(rows) * a.row_stride; };
-    a.fc_in_smem = out_size <= 4 && (((a.n_params + 3) & ~3) * sizeof(float) + act_bytes_of(warps, max_rows)) <= 112 * 1024;
+    a.fc_in_smem = !pool && out_size <= 4 && (((a.n_params + 3) & ~3) * sizeof(float) + act_bytes_of(warps, max_rows)) <= 112 * 1024;
     a.buf_rows = a.fc_in_smem ? max_rows : max_rows_all;  // a fused last layer stays in registers
     if (!a.fc_in_smem)
         while (warps > 1 && ((a.conv_params + 3) & ~3) * sizeof(float) + act_bytes_of(warps, a.buf_rows) > 112 * 1024)

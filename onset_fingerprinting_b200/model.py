@@ -4,8 +4,10 @@ Mirrors ``model.CNN`` of the reference (model.py:52-120) for inference: the cons
 arguments and builds the same ``conv_layers`` / ``fc`` parameter containers, so a checkpoint of the
 reference model loads with ``load_state_dict`` unchanged; ``forward`` runs the fused CUDA kernel
 (Conv1d + activation stack -> flatten -> Linear, one warp per window) instead of cuDNN/cuBLAS calls.
-Training (LightningModule hooks, optimisers, plots; model.py:122-165) is out of scope, and so are the
-options the reference leaves off by default (batch_norm, pool, dilation != 1, groups != 1): they raise.
+The constructor options the reference leaves off by default -- ``batch_norm`` (BatchNorm1d behind every activation,
+eval mode), ``pool`` (MaxPool1d(2, 2)), ``dilation``, ``groups`` (model.py:62-66, 91-108) -- run on the generic
+kernel; the reference defaults take the tensor-core kernel.  Training (LightningModule hooks, optimisers, plots;
+model.py:122-165) is out of scope.
 """
 from __future__ import annotations
 
@@ -42,19 +44,24 @@ class CNN(nn.Module):
                  kernel_size: int = 3, dropout_rate: float = 0.5, loss=None, batch_norm=False, pool=False,
                  padding=1, dilation=1, groups=1, lr=1e-3, activation=nn.SiLU) -> None:
         super().__init__()
-        if batch_norm or pool or dilation != 1 or groups != 1:
-            raise NotImplementedError("K6 covers the reference defaults: no batch_norm / pool, dilation = groups = 1")
         if activation not in _ACT:
             raise NotImplementedError(f"activation {activation} (supported: {[a.__name__ for a in _ACT]})")
         self.input_size, self.output_size, self.channels = input_size, output_size, channels
         self.layer_sizes, self.kernel_size, self.padding = list(layer_sizes), kernel_size, padding
+        self.dilation, self.groups, self.batch_norm, self.pool = int(dilation), int(groups), bool(batch_norm), bool(pool)
         self.act = _ACT[activation]
-        self.conv_layers = nn.Sequential()  # same names as the reference: conv1, act1, conv2, ...
+        self.conv_layers = nn.Sequential()  # same names as the reference: conv1, act1, (bn1,) (pool1,) conv2, ...
         cur, length = channels, input_size
         for i, size in enumerate(self.layer_sizes):
-            self.conv_layers.add_module(f"conv{i + 1}", nn.Conv1d(cur, size, kernel_size, padding=padding))
+            self.conv_layers.add_module(f"conv{i + 1}", nn.Conv1d(cur, size, kernel_size, padding=padding,
+                                                                 dilation=dilation, groups=groups))
             self.conv_layers.add_module(f"act{i + 1}", activation())
-            length = length + 2 * padding - (kernel_size - 1)
+            length = length + 2 * padding - dilation * (kernel_size - 1)
+            if batch_norm:
+                self.conv_layers.add_module(f"bn{i + 1}", nn.BatchNorm1d(size))
+            if pool:
+                self.conv_layers.add_module(f"pool{i + 1}", nn.MaxPool1d(kernel_size=2, stride=2))
+                length //= 2
             cur = size
         self.dropout = nn.Dropout(dropout_rate)
         self.fc = nn.Linear(cur * length, output_size)
@@ -67,22 +74,37 @@ class CNN(nn.Module):
         parts = []
         for i in range(len(self.layer_sizes)):
             conv = getattr(self.conv_layers, f"conv{i + 1}")
-            w = conv.weight.detach().float().cpu()  # [cout, cin, ks]
+            w = conv.weight.detach().float().cpu()  # [cout, cin / groups, ks]
             b = conv.bias.detach().float().cpu() if conv.bias is not None else torch.zeros(w.shape[0])
             cout = w.shape[0]
+            if self.groups != 1:  # dense [cout, cin, ks] with zeros between the groups (0 * x adds nothing)
+                cin_g, cout_g = w.shape[1], cout // self.groups
+                dense = torch.zeros((cout, cin_g * self.groups, w.shape[2]))
+                for g in range(self.groups):
+                    dense[g * cout_g:(g + 1) * cout_g, g * cin_g:(g + 1) * cin_g] = w[g * cout_g:(g + 1) * cout_g]
+                w = dense
             cp = (cout + 7) // 8 * 8
             wt = torch.zeros((w.shape[1], w.shape[2], cp))
             wt[:, :, :cout] = w.permute(1, 2, 0)
             bp = torch.zeros(cp)
             bp[:cout] = b
             parts += [wt.reshape(-1), bp]
+            if self.batch_norm:  # eval mode: (y - mean) / sqrt(var + eps) * weight + bias = y * scale + shift
+                bn = getattr(self.conv_layers, f"bn{i + 1}")
+                scale = (bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)).cpu()
+                shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
+                sp, tp = torch.zeros(cp), torch.zeros(cp)
+                sp[:cout], tp[:cout] = scale.float(), shift.float()
+                parts += [sp, tp]
         parts += [self.fc.weight.detach().float().cpu().reshape(-1), self.fc.bias.detach().float().cpu()]
         packed = torch.cat(parts).contiguous()
         n = C.c_int64(0)
         sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
-        check(_lib.lib().ofp_cnn_param_count(C.c_int32(self.channels), C.c_int32(self.input_size),
-                                             C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
-                                             C.c_int32(self.padding), C.c_int32(self.output_size), C.byref(n), None))
+        check(_lib.lib().ofp_cnn_param_count_ex(C.c_int32(self.channels), C.c_int32(self.input_size),
+                                                C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
+                                                C.c_int32(self.padding), C.c_int32(self.dilation),
+                                                C.c_int32(self.pool), C.c_int32(self.batch_norm),
+                                                C.c_int32(self.output_size), C.byref(n), None))
         assert n.value == packed.numel(), (n.value, packed.numel())
         self._packed = packed.cuda()
         return self._packed
@@ -107,11 +129,12 @@ class CNN(nn.Module):
             self.pack()
         out = torch.empty((x.shape[0], self.output_size), dtype=torch.float32, device="cuda")
         sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
-        check(_lib.lib().ofp_cnn_forward(ptr(x), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)),
-                                         C.c_int32(self.channels), C.c_int32(self.input_size),
-                                         C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
-                                         C.c_int32(self.padding), C.c_int32(self.act), ptr(self._packed),
-                                         C.c_int32(self.output_size), ptr(out), stream_ptr()))
+        check(_lib.lib().ofp_cnn_forward_ex(ptr(x), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)),
+                                            C.c_int32(self.channels), C.c_int32(self.input_size),
+                                            C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
+                                            C.c_int32(self.padding), C.c_int32(self.dilation), C.c_int32(self.pool),
+                                            C.c_int32(self.batch_norm), C.c_int32(self.act), ptr(self._packed),
+                                            C.c_int32(self.output_size), ptr(out), stream_ptr()))
         return out
 
     def call_np(self, x: np.ndarray) -> np.ndarray:

@@ -60,13 +60,43 @@ def test_state_dict_round_trip_and_views():
     assert np.array_equal(a.call_np(x.cpu().numpy()), ya.cpu().numpy())
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(input_size=256, output_size=2, batch_norm=True),
+    dict(input_size=256, output_size=2, pool=True),
+    dict(input_size=256, output_size=2, batch_norm=True, pool=True, layer_sizes=[8, 16, 24]),
+    dict(input_size=250, output_size=3, channels=4, layer_sizes=[8, 12], kernel_size=5, padding=2, dilation=3),
+    dict(input_size=128, output_size=2, channels=4, layer_sizes=[8, 16], groups=2, pool=True),
+    dict(input_size=255, output_size=5, layer_sizes=[6, 9], kernel_size=3, padding=0, dilation=2, pool=True,
+         batch_norm=True, activation=torch.nn.ReLU),                                # odd lengths: pooling drops the last
+])
+def test_cnn_constructor_options_match_torch(cfg):
+    """batch_norm / pool / dilation / groups of the reference's CNN (model.py:62-66, 91-108), eval mode, with
+    non-trivial BatchNorm running statistics and affine parameters."""
+    from onset_fingerprinting_b200 import model
+
+    torch.manual_seed(3)
+    m = model.CNN(**cfg).cuda()
+    for mod in m.conv_layers:
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.uniform_(-0.3, 0.3)
+            mod.running_var.uniform_(0.5, 2.0)
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.uniform_(-0.2, 0.2)
+    x = torch.randn(515, cfg.get("channels", 3), cfg["input_size"], device="cuda")
+    got = m(x)
+    want = torch_reference(m, x)
+    scale = float(want.abs().max())
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-4 * scale, float((got - want).abs().max()) / scale
+
+
 def test_unsupported_options_raise():
     from onset_fingerprinting_b200 import model
 
     with pytest.raises(NotImplementedError):
-        model.CNN(256, 2, batch_norm=True)
+        model.CNN(256, 2, activation=torch.nn.GELU)
     with pytest.raises(NotImplementedError):
-        model.CNN(256, 2, pool=True)
+        model.CCCNN(256, 2, pool=True)
 
 
 def _fcnn_reference(m, x):
