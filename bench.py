@@ -1081,8 +1081,18 @@ def run_k1_only(args):
                                    "frac": alg / (k1_ms / 1e3) / 1e9 / peak, "peak_source": src}}))
 
 
+def _quiet_stdout():
+    """stdout carries exactly one JSON line: libraries that write to file descriptor 1 themselves (NCCL prints its
+    version there when NCCL_DEBUG is set in the environment) are pointed at stderr, print() keeps the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.k1_only:
