@@ -462,6 +462,22 @@ int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride,
                       int32_t activation, int32_t group, const float *params_dev, int32_t out_size, float *out_dev,
                       void *stream);
 
+/* The same network with the constructor options the reference's CCCNN leaves off by default (model.py:451-457,
+ * 485-503): one kernel size and one stride per layer, dilation, pool != 0: MaxPool1d(2, 2) after every layer,
+ * group_norm != 0: the GroupNorm(1, K) that `batch_norm=True` builds (model.py:494-498; statistics over the K x L values
+ * of one sensor channel's feature maps, eps 1e-5), packed as gamma[c_out_padded] + beta[c_out_padded] right behind each
+ * layer's bias.  group together with group_norm is refused (that norm spans all sensor channels of a window).  The
+ * last layer size must be a multiple of 8 and the final feature-map length a multiple of 16, as above. */
+int ofp_cccnn_param_count_ex(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
+                             const int32_t *kernel_sizes_host, const int32_t *strides_host, int32_t padding,
+                             int32_t dilation, int32_t pool, int32_t group_norm, int32_t out_size, int32_t group,
+                             int64_t *n_params_out, int32_t *n_lags_out);
+int ofp_cccnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
+                         int32_t n_layers, const int32_t *layer_sizes_host, const int32_t *kernel_sizes_host,
+                         const int32_t *strides_host, int32_t padding, int32_t dilation, int32_t pool, int32_t group_norm,
+                         int32_t activation, int32_t group, const float *params_dev, int32_t out_size, float *out_dev,
+                         void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Benchmark input: seeded synthetic multi-mic drum audio generated on the device
  * (SURVEY.md section 8d signal model; not a reference function).  x_dev [R, N, C] float32;

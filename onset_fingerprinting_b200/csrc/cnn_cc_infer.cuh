@@ -194,13 +194,28 @@ namespace ofp {
 // share one set of planes: every thread owns positions t = tid + 128 p of the conv layers, the tile diagonals of the
 // Gram matrix are dealt round-robin to the warps (lag bins through shared-memory atomics: neighbouring diagonals of
 // different warps overlap in 15 bins), warp 0 does the softmax and the Linear layer.  6 CTAs = 24 warps per SM.
+// sum over the 128 threads of a CTA, returned to all of them (scratch: 8 floats of shared memory)
+__device__ __forceinline__ float block_sum_128(float v, float *scratch, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // scratch free again
+    if ((tid & 31) == 0) scratch[tid >> 5] = v;
+    __syncthreads();
+    return (scratch[0] + scratch[1]) + (scratch[2] + scratch[3]);
+}
+
 #ifndef OFP_K6CC_ND
 #define OFP_K6CC_ND 4
 #endif
 #ifndef OFP_K6CC_MINCTA
 #define OFP_K6CC_MINCTA 5
 #endif
-template <int KS, int PP, int ND>
+// GEN = true: the constructor options the reference leaves off by default (model.py:451-457, 485-503) -- per-layer
+// kernel sizes and strides, dilation, GroupNorm(1, K) behind every activation (`batch_norm=True` builds a GroupNorm,
+// model.py:494-498: statistics over all K x L values of ONE sensor channel's feature maps, biased variance, eps 1e-5)
+// and MaxPool1d(2, 2) -- with run-time loop bounds; KS is ignored.  Parameters per layer: wT[cin][ks_l][coutp],
+// bias[coutp], then gamma[coutp], beta[coutp] when a.bn.
+template <int KS, int PP, int ND, bool GEN>
 __global__ void __launch_bounds__(128, OFP_K6CC_MINCTA) k6_cccnn_cta(const K6Args a, const int n_ch, const int rows) {
     extern __shared__ __align__(16) float k6_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -212,6 +227,7 @@ __global__ void __launch_bounds__(128, OFP_K6CC_MINCTA) k6_cccnn_cta(const K6Arg
     float *bufB = bufA + rows * RS;
     float *cc = bufB + rows * RS;
     float *tile = cc + ((V + 3) & ~3) + warp * 128;
+    float *red = cc + ((V + 3) & ~3);  // the staging tiles double as reduction scratch of the norm (GEN)
     for (int i = tid; i < a.conv_params; i += 128) prm[i] = a.params[i];
     for (int i = tid; i < 2 * rows * RS; i += 128) bufA[i] = 0.f;
     __syncthreads();
@@ -228,6 +244,7 @@ __global__ void __launch_bounds__(128, OFP_K6CC_MINCTA) k6_cccnn_cta(const K6Arg
             float *in = bufA, *outb = bufB;
             for (int l = 0; l < a.n_layers; ++l) {
                 const int Cin = a.cin[l], Cout = a.cout[l], CP = a.coutp[l], Lout = a.lout[l];
+                const int Lc = GEN ? a.lconv[l] : Lout;  // length before pooling
                 // group = True (model.py:512-538: groups = channels): channel c runs its OWN copy of the stack
                 const float *wT = prm + c * a.group_stride + a.w_off[l], *bias = prm + c * a.group_stride + a.b_off[l];
                 for (int ob = 0; ob < CP; ob += 8) {
@@ -238,6 +255,25 @@ __global__ void __launch_bounds__(128, OFP_K6CC_MINCTA) k6_cccnn_cta(const K6Arg
 #pragma unroll
                         for (int p = 0; p < PP; ++p) acc[o][p] = b;
                     }
+                    if (GEN) {
+                        const int ksl = a.ksl[l], strl = a.strl[l], dil = a.dil;
+                        for (int ic = 0; ic < Cin; ++ic) {
+                            const float *row = in + ic * RS;
+                            for (int k = 0; k < ksl; ++k) {
+                                const float4 w0 = *reinterpret_cast<const float4 *>(wT + (ic * ksl + k) * CP + ob);
+                                const float4 w1 = *reinterpret_cast<const float4 *>(wT + (ic * ksl + k) * CP + ob + 4);
+                                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                                for (int p = 0; p < PP; ++p) {
+                                    // positions past the layer's output would read past the row: clamp the index (the
+                                    // value is never stored)
+                                    const float xin = row[min((tid + 128 * p) * strl + k * dil, RS - 1)];
+#pragma unroll
+                                    for (int o = 0; o < 8; ++o) acc[o][p] = fmaf(wv[o], xin, acc[o][p]);
+                                }
+                            }
+                        }
+                    } else
                     for (int ic = 0; ic < Cin; ++ic) {
                         const float *row = in + ic * RS + tid;
 #pragma unroll
@@ -266,9 +302,38 @@ __global__ void __launch_bounds__(128, OFP_K6CC_MINCTA) k6_cccnn_cta(const K6Arg
                                     case 2: h = k6_act<2>(h); break;
                                     default: break;
                                 }
-                                if (tid + 128 * p < Lout) outb[oc * RS + pad + tid + 128 * p] = h;
+                                if (tid + 128 * p < Lc) outb[oc * RS + pad + tid + 128 * p] = h;
                             }
                         }
+                    }
+                }
+                if (GEN && a.bn) {  // GroupNorm(1, Cout) over the Cout x Lc values just stored
+                    __syncthreads();
+                    const int nel = Cout * Lc;
+                    float s1 = 0.f;
+                    for (int e = tid; e < nel; e += 128) s1 += outb[(e / Lc) * RS + pad + e % Lc];
+                    const float mean = block_sum_128(s1, red, tid) / nel;
+                    float s2 = 0.f;
+                    for (int e = tid; e < nel; e += 128) {
+                        const float dv = outb[(e / Lc) * RS + pad + e % Lc] - mean;
+                        s2 = fmaf(dv, dv, s2);
+                    }
+                    const float rstd = rsqrtf(block_sum_128(s2, red, tid) / nel + 1e-5f);
+                    for (int e = tid; e < nel; e += 128) {
+                        const int oc = e / Lc;
+                        float *q = outb + oc * RS + pad + e % Lc;
+                        *q = fmaf((*q - mean) * rstd, bias[CP + oc], bias[2 * CP + oc]);
+                    }
+                }
+                if (GEN && a.pool) {  // MaxPool1d(2, 2) in place: all reads of a pass before its writes
+                    __syncthreads();
+                    for (int base = 0; base < Cout * Lout; base += 128) {
+                        const int e = base + tid, oc = e / Lout, j = e - oc * Lout;
+                        float m = 0.f;
+                        if (e < Cout * Lout) m = fmaxf(outb[oc * RS + pad + 2 * j], outb[oc * RS + pad + 2 * j + 1]);
+                        __syncthreads();
+                        if (e < Cout * Lout) outb[oc * RS + pad + j] = m;
+                        __syncthreads();
                     }
                 }
                 for (int oc = 0; oc < Cout; ++oc)

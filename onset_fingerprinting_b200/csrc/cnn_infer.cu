@@ -28,7 +28,9 @@ struct K6Args {
     int64_t n, win_stride;
     int32_t C0, W, n_layers, ks, pad, act, out_size;
     int32_t cin[K6_MAX_LAYERS], cout[K6_MAX_LAYERS], coutp[K6_MAX_LAYERS], lin[K6_MAX_LAYERS], lout[K6_MAX_LAYERS];
-    int32_t dil, pool, bn;   // k6_cnn only: dilation (>= 1), MaxPool1d(2, 2) after every layer, eval-mode BatchNorm1d as
+    int32_t ksl[K6_MAX_LAYERS], strl[K6_MAX_LAYERS], lconv[K6_MAX_LAYERS];  // k6_cccnn_cta<GEN>: per-layer kernel size,
+                                                                            // stride, output length before pooling
+    int32_t dil, pool, bn;   // k6_cnn / k6_cccnn_cta<GEN>: dilation (>= 1), MaxPool1d(2, 2) after every layer, eval-mode BatchNorm1d as
                              // scale[coutp] + shift[coutp] behind every layer's bias; lout is the length AFTER pooling
     int32_t w_off[K6_MAX_LAYERS], b_off[K6_MAX_LAYERS];  // float offsets into params
     int32_t fc_w_off, fc_b_off, n_params, conv_params;   // conv_params: floats staged in shared memory always
@@ -376,6 +378,101 @@ int ofp_cnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stride
     return OFP_OK;
 }
 
+// Output length of one CCCNN layer with the options of model.py:485-503 (Conv1d, then MaxPool1d(2, 2) when pool).
+static int cccnn_layer_len(int len, int ks, int stride, int padding, int dilation, int pool, int *conv_len) {
+    const int span = len + 2 * padding - dilation * (ks - 1) - 1;
+    const int lc = span < 0 ? 0 : span / stride + 1;
+    if (conv_len) *conv_len = lc;
+    return pool ? lc / 2 : lc;
+}
+
+int ofp_cccnn_param_count_ex(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
+                             const int32_t *kernel_sizes_host, const int32_t *strides_host, int32_t padding,
+                             int32_t dilation, int32_t pool, int32_t group_norm, int32_t out_size, int32_t group,
+                             int64_t *n_params_out, int32_t *n_lags_out) {
+    OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS && layer_sizes_host && kernel_sizes_host && strides_host &&
+                    n_params_out, "bad argument");
+    OFP_REQUIRE(dilation >= 1, "dilation must be >= 1");
+    int64_t n = 0;
+    int cin = 1, len = input_size;
+    for (int l = 0; l < n_layers; ++l) {
+        const int cout = layer_sizes_host[l], cp = (cout + 7) & ~7;
+        OFP_REQUIRE(kernel_sizes_host[l] >= 1 && strides_host[l] >= 1, "layer %d: kernel size and stride must be >= 1", l);
+        n += static_cast<int64_t>(cin) * kernel_sizes_host[l] * cp + cp + (group_norm ? 2 * cp : 0);
+        len = cccnn_layer_len(len, kernel_sizes_host[l], strides_host[l], padding, dilation, pool, nullptr);
+        OFP_REQUIRE(len >= 1, "layer %d has no output positions", l);
+        cin = cout;
+    }
+    if (group) n *= channels;
+    n += static_cast<int64_t>(out_size) * channels * (2 * len - 1) + out_size;
+    *n_params_out = n;
+    if (n_lags_out) *n_lags_out = 2 * len - 1;
+    return OFP_OK;
+}
+
+int ofp_cccnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stride, int32_t channels, int32_t input_size,
+                         int32_t n_layers, const int32_t *layer_sizes_host, const int32_t *kernel_sizes_host,
+                         const int32_t *strides_host, int32_t padding, int32_t dilation, int32_t pool, int32_t group_norm,
+                         int32_t activation, int32_t group, const float *params_dev, int32_t out_size, float *out_dev,
+                         void *stream) {
+    OFP_REQUIRE(x_dev && params_dev && out_dev && layer_sizes_host && kernel_sizes_host && strides_host, "null argument");
+    OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS, "1..%d conv layers supported", K6_MAX_LAYERS);
+    OFP_REQUIRE(padding >= 0 && padding <= 8 && channels >= 1 && channels <= 64 && out_size >= 1 && out_size <= 4,
+                "bad argument (out_size up to 4)");
+    OFP_REQUIRE(input_size >= 1 && input_size <= 256, "input_size up to 256 supported");
+    OFP_REQUIRE(dilation >= 1 && dilation <= 16, "dilation 1..16 supported");
+    OFP_REQUIRE(activation >= 0 && activation <= 3, "activation: 0 SiLU, 1 ReLU, 2 tanh, 3 identity");
+    // GroupNorm(1, K * channels) of the grouped stack (model.py:494-498 with group = True) takes its statistics over
+    // ALL sensor channels of a window at once; the kernel runs the channels one after the other
+    OFP_REQUIRE(!(group && group_norm), "group = True together with the norm layer is not supported");
+    pool = pool != 0; group_norm = group_norm != 0;
+    if (n_windows == 0) return OFP_OK;
+    K6Args a{};
+    a.x = x_dev; a.n = n_windows; a.win_stride = win_stride; a.C0 = 1; a.W = input_size; a.n_layers = n_layers;
+    a.ks = 0; a.pad = padding; a.act = activation; a.out_size = out_size; a.params = params_dev; a.out = out_dev;
+    a.dil = dilation; a.pool = pool; a.bn = group_norm;
+    int cin = 1, len = input_size, off = 0, max_conv = 1, max_in = input_size, rows = 1;
+    for (int l = 0; l < n_layers; ++l) {
+        const int cout = layer_sizes_host[l], cp = (cout + 7) & ~7, ks = kernel_sizes_host[l], st = strides_host[l];
+        OFP_REQUIRE(cout >= 1 && cout <= 64, "layer sizes 1..64 supported");
+        OFP_REQUIRE(ks >= 1 && ks <= 15 && st >= 1 && st <= 8, "layer %d: kernel size 1..15, stride 1..8 supported", l);
+        a.cin[l] = cin; a.cout[l] = cout; a.coutp[l] = cp; a.lin[l] = len; a.ksl[l] = ks; a.strl[l] = st;
+        a.w_off[l] = off; off += cin * ks * cp;
+        a.b_off[l] = off; off += cp + (group_norm ? 2 * cp : 0);
+        int lc = 0;
+        len = cccnn_layer_len(len, ks, st, padding, dilation, pool, &lc);
+        OFP_REQUIRE(len >= 1 && lc <= 256, "layer %d output length %d outside 1..256", l, lc);
+        a.lconv[l] = lc; a.lout[l] = len;
+        max_conv = std::max(max_conv, lc);
+        max_in = std::max(max_in, len);
+        rows = std::max(rows, cout);
+        cin = cout;
+    }
+    OFP_REQUIRE(cin % 8 == 0, "the last layer size must be a multiple of 8 (tensor-core K dimension), got %d", cin);
+    OFP_REQUIRE(len % 16 == 0, "the feature-map length must be a multiple of 16, got %d", len);
+    a.group_stride = group ? off : 0;
+    if (group) off *= channels;
+    a.conv_params = off;
+    OFP_REQUIRE(off <= 16384, "conv stack too large for shared memory (%d floats)", off);
+    const int nb = 2 * len - 1;
+    a.fc_w_off = off; off += out_size * channels * nb;
+    a.fc_b_off = off; off += out_size;
+    a.n_params = off;
+    a.row_stride = ((std::max(max_in, max_conv) + 2 * padding + 4) | 1);  // odd: rows start in different banks
+    const size_t smem_c = sizeof(float) * (((a.conv_params + 3) & ~3) + 2 * static_cast<size_t>(rows) * a.row_stride +
+                                           ((len + 3) & ~3) + 4 * 128);
+    OFP_REQUIRE(smem_c <= 227 * 1024, "network needs %zu bytes of shared memory per CTA", smem_c);
+    auto kc = max_conv <= 128 ? k6_cccnn_cta<0, 1, OFP_K6CC_ND, true> : k6_cccnn_cta<0, 2, OFP_K6CC_ND, true>;
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_c)));
+    int per_sm_c = 0;
+    OFP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, kc, 128, smem_c));
+    per_sm_c = std::max(per_sm_c, 1);
+    const int grid_c = static_cast<int>(std::min<int64_t>(n_windows, static_cast<int64_t>(sm_count()) * per_sm_c));
+    kc<<<grid_c, 128, smem_c, static_cast<cudaStream_t>(stream)>>>(a, channels, rows);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
 int ofp_cccnn_param_count(int32_t channels, int32_t input_size, int32_t n_layers, const int32_t *layer_sizes_host,
                           int32_t kernel_size, int32_t padding, int32_t out_size, int32_t group,
                           int64_t *n_params_out, int32_t *n_lags_out) {
@@ -448,7 +545,7 @@ int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride,
                                                ((len + 3) & ~3) + 4 * 128);
         const int PP = max_len <= 128 ? 1 : 2;
         void (*kc)(const K6Args, int, int) = nullptr;
-#define K6CC_PICK(KS_) kc = PP == 1 ? k6_cccnn_cta<KS_, 1, OFP_K6CC_ND> : k6_cccnn_cta<KS_, 2, OFP_K6CC_ND>
+#define K6CC_PICK(KS_) kc = PP == 1 ? k6_cccnn_cta<KS_, 1, OFP_K6CC_ND, false> : k6_cccnn_cta<KS_, 2, OFP_K6CC_ND, false>
         switch (kernel_size) {
             case 1: K6CC_PICK(1); break;
             case 3: K6CC_PICK(3); break;

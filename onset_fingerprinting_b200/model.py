@@ -143,7 +143,8 @@ class CNN(nn.Module):
 
 
 class CCCNN(nn.Module):
-    """``model.CCCNN`` of the reference (model.py:443-538, ``group`` False or True) for inference: same constructor arguments
+    """``model.CCCNN`` of the reference (model.py:443-538, every constructor option except ``batch_norm`` together with
+    ``group=True``) for inference: same constructor arguments
     and parameter names (``conv_layers.conv1`` ..., ``fc``), fused forward in csrc/cnn_cc_infer.cuh -- per sensor
     channel the shared conv stack, the summed auto-correlation of its feature maps as ``F^T F`` on the tensor
     cores with the diagonal sums taken inside the accumulator fragments, softmax over the 2V-1 lags, Linear."""
@@ -152,26 +153,38 @@ class CCCNN(nn.Module):
                  kernel_sizes=3, strides=1, dropout_rate: float = 0.5, batch_norm=False, pool=False, padding=1,
                  dilation=1, group: bool = False, activation=nn.SiLU) -> None:
         super().__init__()
-        if isinstance(kernel_sizes, (list, tuple)):
-            if len(set(kernel_sizes)) != 1:
-                raise NotImplementedError("one kernel size for all layers")
-            kernel_sizes = kernel_sizes[0]
-        if isinstance(strides, (list, tuple)):
-            strides = strides[0] if len(set(strides)) == 1 else None
-        if batch_norm or pool or dilation != 1 or strides != 1:
-            raise NotImplementedError("K6b covers stride 1, dilation 1, no batch_norm / pool (group either way)")
+        self.layer_sizes = list(layer_sizes)
+        if isinstance(kernel_sizes, int):  # model.py:476-479
+            kernel_sizes = [kernel_sizes] * len(self.layer_sizes)
+        if isinstance(strides, int):
+            strides = [strides] * len(self.layer_sizes)
+        self.kernel_sizes, self.strides = [int(k) for k in kernel_sizes], [int(t) for t in strides]
+        if batch_norm and group:
+            # GroupNorm(1, K * channels) of the grouped stack takes its statistics over all sensor channels of a window;
+            # the kernel runs the channels one after the other
+            raise NotImplementedError("batch_norm together with group=True")
         if activation not in _ACT:
             raise NotImplementedError(f"activation {activation}")
         self.input_size, self.output_size, self.channels = input_size, output_size, channels
-        self.layer_sizes, self.kernel_size, self.padding = list(layer_sizes), kernel_sizes, padding
+        self.padding, self.dilation, self.batch_norm, self.pool = padding, int(dilation), bool(batch_norm), bool(pool)
+        # the reference defaults (one kernel size, stride 1, dilation 1, no norm / pool) take the specialised kernels
+        self.plain = (len(set(self.kernel_sizes)) == 1 and set(self.strides) == {1} and self.dilation == 1 and
+                      not self.batch_norm and not self.pool and self.kernel_sizes[0] in (1, 3, 5, 7))
+        self.kernel_size = self.kernel_sizes[0]
         self.act, self.group = _ACT[activation], bool(group)
         self.conv_layers = nn.Sequential()
         g = channels if group else 1  # model.py:470-484: in / out channels times `channels`, groups = channels
         cur, length = g, input_size
-        for i, size in enumerate(self.layer_sizes):
-            self.conv_layers.add_module(f"conv{i + 1}", nn.Conv1d(cur, size * g, kernel_sizes, padding=padding, groups=g))
+        for i, (size, ks, st) in enumerate(zip(self.layer_sizes, self.kernel_sizes, self.strides)):
+            self.conv_layers.add_module(f"conv{i + 1}", nn.Conv1d(cur, size * g, ks, padding=padding, dilation=dilation,
+                                                                 stride=st, groups=g))
             self.conv_layers.add_module(f"act{i + 1}", activation())
-            length = length + 2 * padding - (kernel_sizes - 1)
+            length = (length + 2 * padding - dilation * (ks - 1) - 1) // st + 1
+            if batch_norm:  # model.py:494-498: the `batch_norm` option builds a GroupNorm with one group
+                self.conv_layers.add_module(f"bn{i + 1}", nn.GroupNorm(1, size * g))
+            if pool:
+                self.conv_layers.add_module(f"pool{i + 1}", nn.MaxPool1d(kernel_size=2, stride=2))
+                length //= 2
             cur = size * g
         self.dropout = nn.Dropout(dropout_rate)
         self.n_lags = 2 * length - 1
@@ -192,14 +205,26 @@ class CCCNN(nn.Module):
                 bp = torch.zeros(cp)
                 bp[:size] = b
                 parts += [wt.reshape(-1), bp]
+                if self.batch_norm:
+                    gn = getattr(self.conv_layers, f"bn{i + 1}")
+                    gp, tp = torch.zeros(cp), torch.zeros(cp)
+                    gp[:size], tp[:size] = gn.weight.detach().float().cpu(), gn.bias.detach().float().cpu()
+                    parts += [gp, tp]
         parts += [self.fc.weight.detach().float().cpu().reshape(-1), self.fc.bias.detach().float().cpu()]
         packed = torch.cat(parts).contiguous()
         n = C.c_int64(0)
         sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
-        check(_lib.lib().ofp_cccnn_param_count(C.c_int32(self.channels), C.c_int32(self.input_size),
-                                               C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
-                                               C.c_int32(self.padding), C.c_int32(self.output_size),
-                                               C.c_int32(int(self.group)), C.byref(n), None))
+        if self.plain:
+            check(_lib.lib().ofp_cccnn_param_count(C.c_int32(self.channels), C.c_int32(self.input_size),
+                                                   C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
+                                                   C.c_int32(self.padding), C.c_int32(self.output_size),
+                                                   C.c_int32(int(self.group)), C.byref(n), None))
+        else:
+            check(_lib.lib().ofp_cccnn_param_count_ex(
+                C.c_int32(self.channels), C.c_int32(self.input_size), C.c_int32(len(self.layer_sizes)), sizes,
+                (C.c_int32 * len(self.layer_sizes))(*self.kernel_sizes), (C.c_int32 * len(self.layer_sizes))(*self.strides),
+                C.c_int32(self.padding), C.c_int32(self.dilation), C.c_int32(self.pool), C.c_int32(self.batch_norm),
+                C.c_int32(self.output_size), C.c_int32(int(self.group)), C.byref(n), None))
         assert n.value == packed.numel(), (n.value, packed.numel())
         self._packed = packed.cuda()
         return self._packed
@@ -224,9 +249,18 @@ class CCCNN(nn.Module):
             self.pack()
         out = torch.empty((x.shape[0], self.output_size), dtype=torch.float32, device="cuda")
         sizes = (C.c_int32 * len(self.layer_sizes))(*self.layer_sizes)
-        check(_lib.lib().ofp_cccnn_forward(ptr(x), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)),
-                                           C.c_int32(self.channels), C.c_int32(self.input_size),
-                                           C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
-                                           C.c_int32(self.padding), C.c_int32(self.act), C.c_int32(int(self.group)),
-                                           ptr(self._packed), C.c_int32(self.output_size), ptr(out), stream_ptr()))
+        if self.plain:
+            check(_lib.lib().ofp_cccnn_forward(ptr(x), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)),
+                                               C.c_int32(self.channels), C.c_int32(self.input_size),
+                                               C.c_int32(len(self.layer_sizes)), sizes, C.c_int32(self.kernel_size),
+                                               C.c_int32(self.padding), C.c_int32(self.act), C.c_int32(int(self.group)),
+                                               ptr(self._packed), C.c_int32(self.output_size), ptr(out), stream_ptr()))
+        else:
+            check(_lib.lib().ofp_cccnn_forward_ex(
+                ptr(x), C.c_int64(x.shape[0]), C.c_int64(x.stride(0)), C.c_int32(self.channels),
+                C.c_int32(self.input_size), C.c_int32(len(self.layer_sizes)), sizes,
+                (C.c_int32 * len(self.layer_sizes))(*self.kernel_sizes), (C.c_int32 * len(self.layer_sizes))(*self.strides),
+                C.c_int32(self.padding), C.c_int32(self.dilation), C.c_int32(self.pool), C.c_int32(self.batch_norm),
+                C.c_int32(self.act), C.c_int32(int(self.group)), ptr(self._packed), C.c_int32(self.output_size), ptr(out),
+                stream_ptr()))
         return out
