@@ -12,12 +12,15 @@
 //     them 6/7 per SM instead of 4/8.
 //   * input [R, N, C] is staged by TMA: a 2-D tensor map over (N*C, R) with box (T*C, G) brings the
 //     next T samples of all G recordings of the warp with ONE cp.async.bulk.tensor per tile into a
-//     warp-private mbarrier ring.  T is chosen so that the row pitch T*C is 4 (mod 32) floats:
-//     the per-sample LDS of the 32 lanes is then (almost) bank-conflict free.
+//     warp-private mbarrier ring.  T = 40: the longest tile that keeps 7 warps resident per SM; its row pitch
+//     (120 words) leaves the per-sample LDS of the 32 lanes with 3-way bank conflicts -- measured harmless (rows
+//     padded to 124 words are conflict-free and equally fast, DESIGN.md "K1"), the LSU is 11 % busy.
 //   * the rel envelope of the current block stays in shared memory: the thresholds of a block
 //     depend on the END-of-block min/max, so crossings are found by a second pass that
-//     only runs when the block maximum exceeded the on-threshold (once per hit).  rel is written to
-//     HBM from that buffer with coalesced 16-byte streaming stores.
+//     only runs when the block maximum exceeded the on-threshold (once per hit).  rel leaves for HBM from
+//     that buffer as one bulk async copy per recording and block (cp.async.bulk shared -> global).
+//   * the chunk loop is laid out by hand (nested goto loops: the common path is one straight line) and the
+//     shared-window base is an opaque register (no S2UR + ULEA rebuild of shared addresses inside loops).
 //   * arithmetic follows SURVEY Appendix A op for op: explicit __f*_rn intrinsics (never contracted
 //     to FMA), one double add inside the follower, log10/10**x evaluated in double and rounded once.
 #include "ofp_common.cuh"
