@@ -1,10 +1,10 @@
 #!/bin/bash
 # 2-GPU run of the default bench line (torchrun, NCCL) -- validates the multi-rank path of this build
 free -g; cat /sys/fs/cgroup/memory.max 2>/dev/null; cat /sys/fs/cgroup/memory/memory.limit_in_bytes 2>/dev/null; nproc
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --cpu-seconds 5 > gpurun_out/r02_bench_2gpu.json 2> gpurun_out/r02_bench_2gpu.err; tail -c 600 gpurun_out/r02_bench_2gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 3 --warmup 3 --cpu-seconds 5 > gpurun_out/r02_bench_4gpu.json 2> gpurun_out/r02_bench_4gpu.err; tail -c 600 gpurun_out/r02_bench_4gpu.err
 python - <<'PY'
 import json
-d=json.loads([l for l in open('gpurun_out/r02_bench_2gpu.json') if l.startswith('{')][-1])
+d=json.loads([l for l in open('gpurun_out/r02_bench_4gpu.json') if l.startswith('{')][-1])
 print('value',d['value'],'ms',d['ms_per_step'],'frac',d['roofline']['frac'],'ngpu',d['n_gpus'])
 e=d['e2e']; print('e2e',e['value'],{k:(v['value'],v['ms'],v['h2d_gbs_per_rank']) for k,v in e['modes'].items()}); print(e['plain_copy_ceiling'], e['vs_plain_copy'], e['numa'])
 print('h16',d['hits16']['value'])
