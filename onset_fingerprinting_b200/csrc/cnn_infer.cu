@@ -284,6 +284,7 @@ int ofp_cnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stride
                        int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
                        int32_t dilation, int32_t pool, int32_t batch_norm, int32_t activation, const float *params_dev,
                        int32_t out_size, float *out_dev, void *stream) {
+    if (n_windows == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(x_dev && params_dev && out_dev && layer_sizes_host, "null argument");
     OFP_REQUIRE(dilation >= 1 && dilation <= 16, "dilation 1..16 supported");
     pool = pool != 0; batch_norm = batch_norm != 0;
@@ -295,7 +296,6 @@ int ofp_cnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stride
                 "bad argument");
     OFP_REQUIRE(input_size >= 1 && input_size <= 256, "input_size up to 256 supported");
     OFP_REQUIRE(activation >= 0 && activation <= 3, "activation: 0 SiLU, 1 ReLU, 2 tanh, 3 identity");
-    if (n_windows == 0) return OFP_OK;
     K6Args a{};
     a.x = x_dev; a.n = n_windows; a.win_stride = win_stride; a.C0 = channels; a.W = input_size; a.n_layers = n_layers;
     a.ks = kernel_size; a.pad = padding; a.act = activation; a.out_size = out_size; a.params = params_dev;
@@ -415,6 +415,7 @@ int ofp_cccnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stri
                          const int32_t *strides_host, int32_t padding, int32_t dilation, int32_t pool, int32_t group_norm,
                          int32_t activation, int32_t group, const float *params_dev, int32_t out_size, float *out_dev,
                          void *stream) {
+    if (n_windows == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(x_dev && params_dev && out_dev && layer_sizes_host && kernel_sizes_host && strides_host, "null argument");
     OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS, "1..%d conv layers supported", K6_MAX_LAYERS);
     OFP_REQUIRE(padding >= 0 && padding <= 8 && channels >= 1 && channels <= 64 && out_size >= 1 && out_size <= 4,
@@ -426,7 +427,6 @@ int ofp_cccnn_forward_ex(const float *x_dev, int64_t n_windows, int64_t win_stri
     // ALL sensor channels of a window at once; the kernel runs the channels one after the other
     OFP_REQUIRE(!(group && group_norm), "group = True together with the norm layer is not supported");
     pool = pool != 0; group_norm = group_norm != 0;
-    if (n_windows == 0) return OFP_OK;
     K6Args a{};
     a.x = x_dev; a.n = n_windows; a.win_stride = win_stride; a.C0 = 1; a.W = input_size; a.n_layers = n_layers;
     a.ks = 0; a.pad = padding; a.act = activation; a.out_size = out_size; a.params = params_dev; a.out = out_dev;
@@ -497,6 +497,7 @@ int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride,
                       int32_t n_layers, const int32_t *layer_sizes_host, int32_t kernel_size, int32_t padding,
                       int32_t activation, int32_t group, const float *params_dev, int32_t out_size, float *out_dev,
                       void *stream) {
+    if (n_windows == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(x_dev && params_dev && out_dev && layer_sizes_host, "null argument");
     OFP_REQUIRE(n_layers >= 1 && n_layers <= K6_MAX_LAYERS, "1..%d conv layers supported", K6_MAX_LAYERS);
     OFP_REQUIRE(kernel_size == 1 || kernel_size == 3 || kernel_size == 5 || kernel_size == 7,
@@ -505,7 +506,6 @@ int ofp_cccnn_forward(const float *x_dev, int64_t n_windows, int64_t win_stride,
                 "bad argument (out_size up to 4)");
     OFP_REQUIRE(input_size >= 1 && input_size <= 256, "input_size up to 256 supported");
     OFP_REQUIRE(activation >= 0 && activation <= 3, "activation: 0 SiLU, 1 ReLU, 2 tanh, 3 identity");
-    if (n_windows == 0) return OFP_OK;
     K6Args a{};
     a.x = x_dev; a.n = n_windows; a.win_stride = win_stride; a.C0 = 1; a.W = input_size; a.n_layers = n_layers;
     a.ks = kernel_size; a.pad = padding; a.act = activation; a.out_size = out_size; a.params = params_dev;

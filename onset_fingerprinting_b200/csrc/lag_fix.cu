@@ -227,12 +227,12 @@ int ofp_fix_onsets_ex(const float *audio_dev, int64_t n_samples, int64_t rec_str
                       int32_t d, int32_t direction, int32_t take_abs, int32_t zero_left, int32_t cutoff,
                       int32_t tol, int32_t shift, int32_t max_section, int32_t flags, int32_t *out_onsets_dev,
                       int32_t *out_lags_dev, int32_t *out_status_dev, void *stream) {
+    if (n_hits == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(audio_dev && onsets_dev && out_onsets_dev && out_status_dev, "null argument");
     OFP_REQUIRE(n_channels >= 2 && n_channels <= 32, "n_channels must be in 2..32");
     OFP_REQUIRE(filter_size >= 1 && filter_size <= 15, "filter_size must be in 1..15");
     OFP_REQUIRE(d >= 0 && d <= 3 && cutoff >= 0 && tol >= 0 && direction >= 0 && direction <= 2,
                 "bad option (difference order d must be 0..3)");
-    if (n_hits == 0) return OFP_OK;
     K4Args a;
     a.audio = audio_dev; a.rec_stride = rec_stride; a.n_samples = n_samples; a.C = n_channels; a.H = n_hits;
     a.Lmax = max_section; a.hit_rec = hit_rec_dev; a.onsets = onsets_dev;

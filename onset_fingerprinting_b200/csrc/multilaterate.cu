@@ -854,10 +854,10 @@ extern "C" int ofp_locate_hits(const double *sensor_xyz_dev, int32_t n_sensors, 
                                double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
                                int32_t onset_stride, int32_t n_hits, double *xy_dev, int32_t *status_dev,
                                void *stream) {
+    if (n_hits == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(sensor_xyz_dev && lag_maps_dev && max_lags_dev && min_lags_dev && max_max_dev && hit_onsets_dev &&
                     xy_dev && status_dev, "null argument");
     OFP_REQUIRE(n_sensors >= 3 && onset_stride >= 3, "need at least three sensors / onsets per hit");
-    if (n_hits == 0) return OFP_OK;
     K5Args a;
     a.locs = sensor_xyz_dev; a.maps = lag_maps_dev; a.max_lags = max_lags_dev; a.min_lags = min_lags_dev;
     a.max_max = max_max_dev; a.S = n_sensors; a.Hm = map_size; a.H = n_hits; a.n_per_hit = 3;
@@ -942,10 +942,10 @@ __global__ void __launch_bounds__(128) k5_fcnn(const FcArgs a) {
 extern "C" int ofp_fcnn_forward(const float *x_dev, int64_t n_rows, int32_t n_layers, const int32_t *widths_host,
                                 int32_t activation, const float *params_dev, const int32_t *status_dev,
                                 float out_scale, float *out_f32_dev, double *out_f64_dev, void *stream) {
+    if (n_rows == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(x_dev && widths_host && params_dev && (out_f32_dev || out_f64_dev), "null argument");
     OFP_REQUIRE(n_layers >= 1 && n_layers <= FC_MAXL, "1..%d layers supported", FC_MAXL);
     OFP_REQUIRE(activation >= 0 && activation <= 4, "activation: 0 ReLU, 1 tanh, 2 sigmoid, 3 SiLU, 4 identity");
-    if (n_rows == 0) return OFP_OK;
     FcArgs a{};
     a.x = x_dev; a.n = n_rows; a.n_layers = n_layers; a.act = activation; a.params = params_dev;
     a.status = status_dev; a.out_scale = out_scale; a.out_f32 = out_f32_dev; a.out_f64 = out_f64_dev;
@@ -967,10 +967,10 @@ extern "C" int ofp_locate_hits_lags(const double *sensor_xyz_dev, int32_t n_sens
                                     double c_cm_s, const int32_t *hit_sensors_dev, const int32_t *hit_onsets_dev,
                                     int32_t onset_stride, int32_t n_hits, float *pair_lags_dev, double *xy_dev,
                                     int32_t *status_dev, void *stream) {
+    if (n_hits == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(sensor_xyz_dev && lag_maps_dev && max_lags_dev && min_lags_dev && max_max_dev && hit_onsets_dev &&
                     xy_dev && status_dev && pair_lags_dev, "null argument");
     OFP_REQUIRE(n_sensors >= 3 && onset_stride >= 3, "need at least three sensors / onsets per hit");
-    if (n_hits == 0) return OFP_OK;
     K5Args a;
     a.locs = sensor_xyz_dev; a.maps = lag_maps_dev; a.max_lags = max_lags_dev; a.min_lags = min_lags_dev;
     a.max_max = max_max_dev; a.S = n_sensors; a.Hm = map_size; a.H = n_hits; a.n_per_hit = 3;

@@ -187,11 +187,11 @@ int ofp_filter_data(const float *x_dev, float *out_dev, int64_t n_samples, int32
 int ofp_detect_onset_region(const float *audio_dev, int32_t n_signals, int64_t len, const int32_t *onsets_dev,
                             int32_t n, int32_t median_filter_size, float threshold_factor, int32_t *out_dev,
                             void *stream) {
+    if (n_signals == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(audio_dev && onsets_dev && out_dev, "null argument");
     OFP_REQUIRE(n >= 0 && n <= 8192, "n must be in 0..8192");
     OFP_REQUIRE(median_filter_size >= 1 && median_filter_size % 2 == 1 && median_filter_size <= 31,
                 "kernel_size must be odd and <= 31");
-    if (n_signals == 0) return OFP_OK;
     const int m = n + 2;
     const size_t smem = static_cast<size_t>(m) * (2 * sizeof(float) + 2);
     k_onset_region<<<n_signals, 128, smem, static_cast<cudaStream_t>(stream)>>>(
@@ -202,9 +202,9 @@ int ofp_detect_onset_region(const float *audio_dev, int32_t n_signals, int64_t l
 
 int ofp_correlate_full(const float *x_dev, const float *y_dev, int32_t n_pairs, int32_t n, float *out_dev,
                        void *stream) {
+    if (n_pairs == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(x_dev && y_dev && out_dev, "null argument");
     OFP_REQUIRE(n >= 1 && n <= 24 * 1024, "signal length must be in 1..24576");
-    if (n_pairs == 0) return OFP_OK;
     const size_t smem = 2 * static_cast<size_t>(n) * sizeof(float);
     OFP_CUDA_CHECK(cudaFuncSetAttribute(k_correlate_full, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
@@ -290,10 +290,10 @@ extern "C" int ofp_extract_frames(const float *audio_dev, int64_t n_samples, int
                                   const int32_t *hit_rec_dev, const int32_t *onsets_dev, const int32_t *shifts_dev,
                                   int32_t n_hits, int32_t frame_length, int32_t pre_samples, int32_t use_min_onset,
                                   float *frames_dev, int32_t *status_dev, void *stream) {
+    if (n_hits == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(audio_dev && onsets_dev && frames_dev && status_dev, "null argument");
     OFP_REQUIRE(n_channels >= 1 && n_channels <= 32, "n_channels must be in 1..32");
     OFP_REQUIRE(frame_length >= 1 && frame_length <= n_samples, "frame_length must be in 1..n_samples");
-    if (n_hits == 0) return OFP_OK;
     const size_t smem = static_cast<size_t>(n_channels) * (frame_length + 1) * sizeof(float);
     OFP_REQUIRE(smem <= 200 * 1024, "frame of %d x %d samples does not fit shared memory", frame_length, n_channels);
     ofp::FrameArgs a{audio_dev, n_samples, rec_stride, n_channels, n_hits, frame_length, pre_samples, use_min_onset,
@@ -376,9 +376,9 @@ __global__ void k_tempogram(const float *oe, int64_t n_frames, const float *wind
 extern "C" int ofp_window_argmax(const float *audio_dev, int64_t n_samples, int64_t rec_stride, int32_t n_channels,
                                  const int32_t *hit_rec_dev, const int32_t *onsets_dev, int32_t n_hits,
                                  int32_t tolerance, int32_t *out_dev, void *stream) {
+    if (n_hits == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(audio_dev && onsets_dev && out_dev, "null argument");
     OFP_REQUIRE(n_channels >= 1 && tolerance >= 1, "bad size");
-    if (n_hits == 0) return OFP_OK;
     const int64_t pairs = static_cast<int64_t>(n_hits) * n_channels;
     ofp::k_window_argmax<<<static_cast<unsigned>((pairs * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         audio_dev, n_samples, rec_stride, n_channels, hit_rec_dev, onsets_dev, pairs, tolerance, out_dev);

@@ -239,3 +239,31 @@ def test_follower_coefficient_ranges(kw, det, orc):
     assert ch == ch_o and on == on_o
     assert rel_err(rel, rel_o) <= 1e-5
     assert float((rel == rel_o).mean()) > 0.9999
+
+
+def test_detector_edge_cases(det, orc):
+    """Inputs at the edges of the offline driver (detection.py:55-86): silence (no onset at all), a recording shorter
+    than the 0.5 s warm-up, one shorter than a block (no block processed: empty outputs), exactly one block, and a
+    batch of one recording; every case equals the oracle's answer, empty lists included."""
+    rng = np.random.default_rng(7)
+    sr, B = 96000, 128
+    full, _ = synth.drum_recording(seconds=1.0, seed=21)
+    cases = {
+        "silence": np.zeros((sr, 3), np.float32),
+        "short_of_warmup": full[48000 + 900:48000 + 900 + 10 * B + 17].copy(),  # a burst inside, < 0.5 s
+        "less_than_a_block": (1e-3 * rng.standard_normal((B - 1, 3))).astype(np.float32),
+        "one_block": (1e-3 * rng.standard_normal((B, 3))).astype(np.float32),
+        "one_recording": full,
+    }
+    for name, x in cases.items():
+        c_o, o_o, rel_o = orc.detect_onsets_amplitude(x, sr=sr)
+        ch, ix, cnt, rel = det.detect_onsets_amplitude_batch(x[None], sr=sr)
+        k = int(cnt[0])
+        assert ch[0, :k].tolist() == list(c_o) and ix[0, :k].tolist() == list(o_o), name
+        rel = rel[0].cpu().numpy()
+        assert rel.shape == np.asarray(rel_o).shape, (name, rel.shape, np.asarray(rel_o).shape)
+        if rel.size:
+            assert rel_err(rel, rel_o) <= 1e-5, name
+        # the reference's own entry point (lists + ndarray)
+        c1, o1, rel1 = det.detect_onsets_amplitude(x, sr=sr)
+        assert list(c1) == list(c_o) and list(o1) == list(o_o), name

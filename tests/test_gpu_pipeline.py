@@ -147,3 +147,24 @@ def test_stream_batch_equals_independent_detectors():
             c, d, r = ods[s](xs[s, i:i + 128])
             assert ch[s, :cnt[s]].tolist() == c.tolist() and dl[s, :cnt[s]].tolist() == d.tolist()
             assert np.array_equal(rel[s], r)
+
+
+def test_pipeline_without_any_hit():
+    """A batch in which nothing crosses the threshold (noise only) and one in which a single recording has hits:
+    K3 / K4 / K5 run on zero hits (empty tensors of the right shapes), and the empty recordings of a mixed batch
+    contribute nothing -- through both entry points."""
+    from onset_fingerprinting_b200 import pipeline
+
+    rng = np.random.default_rng(3)
+    quiet = (1e-4 * rng.standard_normal((4, 96000, 3))).astype(np.float32)
+    hp = pipeline.HotPath(4, 3, synth.SENSORS_3MIC, medium="air", sr=96000)
+    hb = hp.run(torch.from_numpy(quiet).cuda(), return_rel=True)
+    assert hb.rec.numel() == 0 and hb.onsets.shape == (0, 3) and hb.fixed.shape == (0, 3) and hb.xy.shape == (0, 2)
+    assert hb.rel is not None and tuple(hb.rel.shape) == (4, 96000 // 128 * 128, 3)
+    hh = hp.run_host(torch.from_numpy(quiet).pin_memory())
+    assert len(hh["rec"]) == 0 and tuple(hh["xy"].shape) == (0, 2) and int(hh["onset_counts"].sum()) == 0
+    mixed = quiet.copy()
+    mixed[2], _ = synth.drum_recording(seconds=1.0, seed=77)
+    hb = hp.run(torch.from_numpy(mixed).cuda(), return_rel=False)
+    rec = hb.rec.cpu().numpy()
+    assert len(rec) > 0 and set(rec.tolist()) == {2}
