@@ -840,8 +840,8 @@ extern "C" int ofp_ring_write(float *ring_dev, int32_t ring_rows, const float *b
 extern "C" int ofp_solve_trilateration(const double *problems_dev, const double *seeds_dev, int32_t n_problems,
                                        double xtol, int32_t maxfev, double *xy_dev, int32_t *ier_dev,
                                        int32_t *nfev_dev, void *stream) {
+    if (n_problems == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(problems_dev && seeds_dev && xy_dev && ier_dev, "null argument");
-    if (n_problems == 0) return OFP_OK;
     k5_solve<<<(n_problems + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         problems_dev, seeds_dev, n_problems, xtol, maxfev, xy_dev, ier_dev, nfev_dev);
     OFP_CUDA_CHECK(cudaGetLastError());

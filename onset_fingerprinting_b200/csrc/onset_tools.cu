@@ -389,6 +389,7 @@ extern "C" int ofp_window_argmax(const float *audio_dev, int64_t n_samples, int6
 extern "C" int ofp_tempogram(const float *oe_dev, int32_t n_rec, int64_t n_frames, const float *window_dev,
                              int32_t win_length, int64_t first_frame, int64_t every, int64_t n_selected, float *tg_dev,
                              void *stream) {
+    if (n_rec == 0 || n_selected == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(oe_dev && window_dev && tg_dev, "null argument");
     OFP_REQUIRE(win_length >= 1 && win_length <= 8192 && every >= 1 && first_frame >= 0, "bad tempogram shape");
     OFP_REQUIRE(n_selected >= 0 && (n_selected == 0 || first_frame + (n_selected - 1) * every < n_frames),

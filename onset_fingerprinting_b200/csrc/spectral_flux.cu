@@ -227,10 +227,10 @@ int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int6
                       int32_t n_fft, int32_t hop, int32_t center, int32_t reflect, int32_t mode, float top_db,
                       const float *window_dev, const float *weight_dev, int32_t n_frames, float *flux_dev,
                       void *stream) {
+    if (n_frames <= 0 || n_rec == 0) return OFP_OK;  // nothing to compute: the buffers may be null
     OFP_REQUIRE(x_dev && window_dev && flux_dev, "null argument");
     OFP_REQUIRE(n_fft >= 64 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0, "n_fft must be a power of two in 64..8192");
     OFP_REQUIRE(hop >= 1 && n_channels >= 1 && n_rec <= 65535, "bad argument");
-    if (n_frames <= 0 || n_rec == 0) return OFP_OK;
     K2Args a;
     a.x = x_dev; a.rec_stride = rec_stride; a.n_samples = n_samples; a.C = n_channels; a.n_fft = n_fft; a.hop = hop;
     a.n_frames = n_frames; a.center = center; a.reflect = reflect; a.mode = mode;
@@ -266,8 +266,8 @@ int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int6
 int ofp_peak_pick(const float *oe_dev, int32_t n_rec, int32_t n_frames, int32_t pre_max, int32_t post_max,
                   int32_t pre_avg, int32_t post_avg, float delta, int32_t wait, int32_t *peaks_dev,
                   int32_t *n_peaks_dev, int32_t cap, void *stream) {
+    if (n_rec == 0) return OFP_OK;  // an empty batch may come with null buffers
     OFP_REQUIRE(oe_dev && peaks_dev && n_peaks_dev, "null argument");
-    if (n_rec == 0) return OFP_OK;
     k2_peak_pick<<<(n_rec + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
         oe_dev, n_frames, n_rec, pre_max, post_max, pre_avg, post_avg, delta, wait, peaks_dev, n_peaks_dev, cap);
     OFP_CUDA_CHECK(cudaGetLastError());

@@ -163,6 +163,12 @@ def detect_onsets_amplitude_batch(x, block_size: int = 128, floor: float = -70.0
     counts[r] entries of row r are recording r's onsets in the reference's order."""
     torch = _lib.require_cuda()
     x = _to_dev(x, torch)
+    if x.shape[0] == 0:  # an empty batch: empty results of the usual shapes
+        nb = x.shape[1] // block_size
+        k = cap if cap is not None else 1
+        e = torch.empty((0, k), dtype=torch.int32, device="cuda")
+        rel = torch.empty((0, nb * block_size, x.shape[2]), dtype=torch.float32, device="cuda") if return_rel else None
+        return e, e.clone(), torch.empty((0,), dtype=torch.int32, device="cuda"), rel
     det = BatchedOnsetDetector(x.shape[0], x.shape[2], block_size, floor=floor, hipass_freq=hipass_freq,
                                fast_ar=fast_ar, slow_ar=slow_ar, on_threshold=on_threshold,
                                off_threshold=off_threshold, cooldown=cooldown, sr=sr)
@@ -560,6 +566,8 @@ def cross_correlation_lag(x: np.ndarray, y: np.ndarray, onsets=None, legal_lags=
                           normalization_cutoff: int = 10, onset_tolerance: int = 50, take_abs: bool = False):
     """Drop-in for detection.cross_correlation_lag (detection.py:195-268) -> int or None."""
     torch = _lib.require_cuda()
+    if len(x) - d < 1 or len(y) - d < 1:  # np.correlate refuses empty operands (detection.py:232)
+        raise ValueError("first array argument cannot be empty")
     xd = _to_dev(np.ascontiguousarray(x, dtype=np.float32)[None], torch)
     yd = _to_dev(np.ascontiguousarray(y, dtype=np.float32)[None], torch)
     use_legal = legal_lags is not None

@@ -252,3 +252,46 @@ def test_paired_xcorr_vs_torch():
     want = F.conv1d(a_pad, b.reshape(M, 1, V), groups=M).view(B, Cc - 1, K, 2 * V - 1).mean(dim=2)
     assert got.shape == want.shape
     assert float((got - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
+def test_empty_batches_everywhere():
+    """Every batch entry point on an EMPTY batch (zero hits / windows / pairs / recordings / frames): results of the
+    usual shapes with a zero leading dimension, no error (torch's empty tensors carry null data pointers, which the
+    C ABI must not reject when the count is zero).  Empty operands of cross_correlation_lag raise as np.correlate does."""
+    import numpy as np
+    from onset_fingerprinting_b200 import calibration, data, detection as det, model, multilateration as ml, spectral, synth
+
+    audio = torch.randn(2, 4096, 3, device="cuda")
+
+    def i32(*s):
+        return torch.zeros(s, dtype=torch.int32, device="cuda")
+
+    M = ml.Multilaterate3D(synth.SENSORS_3MIC, sr=96000, medium="air")
+    xy, st = M.locate_batch(i32(0, 3))
+    assert tuple(xy.shape) == (0, 2) and tuple(st.shape) == (0,)
+    fixed, lags, fstat = det.fix_onsets_batch(audio, i32(0), i32(0, 3))
+    assert tuple(fixed.shape) == (0, 3) and tuple(fstat.shape) == (0,)
+    assert tuple(det.max_onsets_batch(audio, i32(0), i32(0, 3), 8).shape) == (0, 3)
+    assert tuple(data.extract_frames_batch(audio, i32(0), i32(0, 3), 256).shape) == (0, 3, 256)
+    z = torch.zeros(0, 64, device="cuda")
+    assert tuple(ml.correlate_full(z, z).shape) == (0, 127)
+    xy, ier = ml.solve_trilateration_batch(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0), np.zeros(0),
+                                           np.zeros((0, 2)))
+    assert tuple(xy.shape) == (0, 2) and tuple(ier.shape) == (0,)
+    assert len(det.detect_onset_region_batch(np.zeros((0, 512), np.float32), np.zeros(0, np.int64))) == 0
+    hit_rec, hit_on, n_groups = det.find_onset_groups_batch(i32(2, 16), i32(2, 16), i32(2), 3)
+    assert hit_rec.numel() == 0 and tuple(hit_on.shape) == (0, 3) and n_groups.tolist() == [0, 0]
+    assert tuple(model.CNN(256, 2).cuda()(torch.zeros(0, 3, 256, device="cuda")).shape) == (0, 2)
+    assert tuple(model.CCCNN(256, 2).cuda()(torch.zeros(0, 3, 256, device="cuda")).shape) == (0, 2)
+    assert tuple(calibration.FCNN(2, 2).cuda()(torch.zeros(0, 2, device="cuda")).shape) == (0, 2)
+    assert tuple(spectral.spectral_flux_batch(torch.zeros(0, 8192, device="cuda")).shape) == (0, 64)
+    assert tuple(spectral.spectral_flux_batch(torch.zeros(2, 100, device="cuda")).shape) == (2, 0)  # shorter than a hop
+    peaks, n_peaks = spectral.peak_pick_batch(torch.zeros(0, 100, device="cuda"), 3, 3, 3, 3, 0.1, 2)
+    assert peaks.shape[0] == 0 and tuple(n_peaks.shape) == (0,)
+    assert spectral.tempogram_batch(torch.zeros(0, 1000, device="cuda")).shape[0] == 0
+    ch, ix, cnt, rel = det.detect_onsets_amplitude_batch(np.zeros((0, 4096, 3), np.float32), sr=96000)
+    assert ch.shape[0] == 0 and tuple(cnt.shape) == (0,) and tuple(rel.shape) == (0, 4096, 3)
+    assert tuple(np.asarray(det.fix_onsets(np.zeros((4096, 3), np.float32), np.zeros((0, 3), np.int64))).shape) == (0, 3)
+    with pytest.raises(ValueError):
+        det.cross_correlation_lag(np.zeros(0, np.float32), np.zeros(0, np.float32), onsets=(0, 0))
+    torch.cuda.synchronize()
