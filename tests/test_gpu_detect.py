@@ -267,3 +267,33 @@ def test_detector_edge_cases(det, orc):
         # the reference's own entry point (lists + ndarray)
         c1, o1, rel1 = det.detect_onsets_amplitude(x, sr=sr)
         assert list(c1) == list(c_o) and list(o1) == list(o_o), name
+
+
+@pytest.mark.parametrize("n_ch,block", [(1, 128), (2, 64), (5, 128), (7, 96), (32, 32)])
+def test_channel_counts_and_lane_packing(n_ch, block, det, orc):
+    """Channel counts that pack the warp differently (G = 32, 16, 6, 4, 1 recordings per warp; 32, 32, 30, 28, 32
+    active lanes) on a ragged batch of R = 2 G + 1 recordings: onsets identical to the oracle per recording,
+    envelope <= 1e-5 relative.  Bursts reach the channels with different delays and gains, so the cross-channel
+    off-threshold coupling is exercised for every packing."""
+    rng = np.random.default_rng(100 + n_ch)
+    sr, n = 96000, 96000 + 4 * block + 5
+    R = 2 * (32 // n_ch) + 1 if n_ch < 32 else 3
+    R = min(R, 9)
+    t = np.arange(3000) / sr
+    burst = np.exp(-400 * t) * np.sin(2 * np.pi * 900 * t)
+    xs = (1e-4 * rng.standard_normal((R, n, n_ch))).astype(np.float32)
+    for r in range(R):
+        for s in range(50000 + 37 * r, n - 4000, 11000 + 501 * r):
+            for c in range(n_ch):
+                a = s + int(rng.integers(0, 60))
+                xs[r, a:a + 3000, c] += (rng.uniform(0.05, 0.5) * burst).astype(np.float32)
+    ch, ix, cnt, rel = det.detect_onsets_amplitude_batch(xs, block_size=block, sr=sr)
+    ch, ix, cnt, rel = ch.cpu().numpy(), ix.cpu().numpy(), cnt.cpu().numpy(), rel.cpu().numpy()
+    total = 0
+    for r in range(R):
+        c_o, o_o, rel_o = orc.detect_onsets_amplitude(xs[r], block_size=block, sr=sr)
+        k = int(cnt[r])
+        assert ch[r, :k].tolist() == list(c_o) and ix[r, :k].tolist() == list(o_o), (n_ch, r)
+        assert rel_err(rel[r], rel_o) <= 1e-5, (n_ch, r)
+        total += k
+    assert total >= R * n_ch  # every channel of every recording fired at least once
