@@ -347,6 +347,13 @@ int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int6
                       int32_t n_fft, int32_t hop, int32_t center, int32_t reflect, int32_t mode, float top_db,
                       const float *window_dev, const float *weight_dev, int32_t n_frames, float *flux_dev,
                       void *stream);
+/* Complex short-time spectra of frames that are already cut -- replaces the per-frame `np.fft.rfft(window * x)` of
+ * data.stft / data.stft_frame (data.py:581-654).  frames_dev [n_frames, frame_length] float32; every frame is centred
+ * in n_fft points (librosa.util.pad_center, data.py:589-590), multiplied by window_dev [n_fft] float64 and transformed
+ * in double; out_dev [n_frames, n_fft/2 + 1] complex64 (interleaved re, im).  n_fft: a power of two up to 4096. */
+int ofp_stft_frames(const float *frames_dev, int64_t n_frames, int32_t frame_length, int32_t n_fft,
+                    const double *window_dev, float *out_dev, void *stream);
+
 /* librosa.util.peak_pick (detection.py:113-121) per row of oe_dev [R, n_frames]: peaks_dev [R, cap],
  * n_peaks_dev [R]. */
 int ofp_peak_pick(const float *oe_dev, int32_t n_rec, int32_t n_frames, int32_t pre_max, int32_t post_max,

@@ -183,6 +183,44 @@ __global__ void __launch_bounds__(K2_THREADS) k2_flux(const K2Args a) {
     }
 }
 
+// Complex short-time spectra of already cut frames -- data.stft / stft_frame (data.py:581-654): frame f of
+// `frame_length` samples is centred in n_fft points (librosa.util.pad_center), multiplied by the window and
+// transformed; numpy computes `np.fft.rfft(window * x)` in double (the window is float64) and the caller stores
+// complex64, so the transform runs in double here too (radix-2 Stockham over n_fft complex points in shared memory,
+// one CTA per frame -- a handful of 512-point frames per onset, nowhere near a hot loop) and rounds once at the end.
+__global__ void __launch_bounds__(128) k2_stft_frames(const float *frames, int64_t n_frames, int frame_length, int n_fft,
+                                                      const double *window, float2 *out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *bufA = reinterpret_cast<double2 *>(smem_raw), *bufB = bufA + n_fft;
+    const int tid = threadIdx.x, N = n_fft, lpad = (n_fft - frame_length) / 2;
+    const int64_t f = blockIdx.x;
+    const float *x = frames + f * frame_length;
+    for (int n = tid; n < N; n += 128) {
+        const int i = n - lpad;
+        const double v = (i >= 0 && i < frame_length) ? static_cast<double>(x[i]) * window[n] : 0.0;
+        bufA[n] = make_double2(v, 0.0);
+    }
+    __syncthreads();
+    double2 *src = bufA, *dst = bufB;
+    for (int L = 1; L < N; L *= 2) {  // Stockham autosort, radix 2: after the pass sub-transforms have length 2 L
+        for (int i = tid; i < N / 2; i += 128) {
+            const int k = i & (L - 1);
+            double sn, cs;
+            sincospi(-static_cast<double>(k) / static_cast<double>(L), &sn, &cs);
+            const double2 u = src[i], v = src[i + N / 2];
+            const double2 t = make_double2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+            const int o = ((i - k) << 1) + k;
+            dst[o] = make_double2(u.x + t.x, u.y + t.y);
+            dst[o + L] = make_double2(u.x - t.x, u.y - t.y);
+        }
+        __syncthreads();
+        double2 *tmp = src; src = dst; dst = tmp;
+    }
+    float2 *o = out + f * (N / 2 + 1);
+    for (int k = tid; k <= N / 2; k += 128)
+        o[k] = make_float2(static_cast<float>(src[k].x), static_cast<float>(src[k].y));
+}
+
 }  // namespace ofp
 #include "spectral_flux_warp.cuh"
 namespace ofp {
@@ -259,6 +297,21 @@ int ofp_spectral_flux(const float *x_dev, int64_t n_rec, int64_t n_samples, int6
     OFP_CUDA_CHECK(cudaFuncSetAttribute(k2_flux, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     dim3 grid((n_frames + a.frames_per_cta - 1) / a.frames_per_cta, static_cast<unsigned>(n_rec));
     k2_flux<<<grid, K2_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    OFP_CUDA_CHECK(cudaGetLastError());
+    return OFP_OK;
+}
+
+int ofp_stft_frames(const float *frames_dev, int64_t n_frames, int32_t frame_length, int32_t n_fft,
+                    const double *window_dev, float *out_dev, void *stream) {
+    if (n_frames == 0) return OFP_OK;  // an empty batch may come with null buffers
+    OFP_REQUIRE(frames_dev && window_dev && out_dev, "null argument");
+    OFP_REQUIRE(n_fft >= 2 && n_fft <= 4096 && (n_fft & (n_fft - 1)) == 0, "n_fft must be a power of two in 2..4096");
+    OFP_REQUIRE(frame_length >= 1 && frame_length <= n_fft, "frame_length must be in 1..n_fft");
+    OFP_REQUIRE(n_frames < (1ll << 31), "too many frames for one launch");
+    const size_t smem = 2 * static_cast<size_t>(n_fft) * sizeof(double2);
+    OFP_CUDA_CHECK(cudaFuncSetAttribute(k2_stft_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k2_stft_frames<<<static_cast<unsigned>(n_frames), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+        frames_dev, n_frames, frame_length, n_fft, window_dev, reinterpret_cast<float2 *>(out_dev));
     OFP_CUDA_CHECK(cudaGetLastError());
     return OFP_OK;
 }

@@ -7,6 +7,9 @@ windows are gathered by ``ofp_extract_frames`` straight from recordings resident
 ``[R, N, C]`` batch K1/K4 just processed (``extract_frames_batch``) -- so the offline dataset build
 (BASELINE config 2, "data.py path") never copies audio back to the host.
 
+``stft`` / ``stft_frame`` / ``window_contribution_weights`` (data.py:560-654), the complex short-time spectra around an
+onset that feed the MFCC features, run on ``ofp_stft_frames`` (``stft_batch``: many onsets per launch).
+
 The wav + json session files are read and written by ``posd.py`` (``MCPOSD.from_file`` goes through it);
 the augmentation pipeline is host-side and out of scope.
 """
@@ -109,6 +112,102 @@ def batch_cc(a, b):
     from .multilateration import correlate_full
 
     return correlate_full(a, b)
+
+
+def window_contribution_weights(window: np.ndarray, hop_length: int, hop_edge_padding: bool = False) -> np.ndarray:
+    """data.py:560-577: how much of the signal of interest each STFT frame of ``stft`` saw through the window --
+    the trapezoid integral of the window's first i samples for i = start, start + hop, ... (start = half a window,
+    or one hop with ``hop_edge_padding``), mirrored for the trailing frames and scaled to a maximum of 1.  Host
+    arithmetic on a handful of numbers."""
+    window = np.asarray(window)
+    first = hop_length if hop_edge_padding else len(window) // 2
+    rising = [float(np.trapezoid(window[:i])) for i in range(first, len(window) + hop_length, hop_length)]
+    w = np.array(rising + rising[-2::-1])
+    return w / w.max()
+
+
+def _hann_periodic(n: int) -> np.ndarray:
+    # librosa.filters.get_window("hann", n, fftbins=True) = scipy's periodic Hann, float64 (data.py:624)
+    return 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)
+
+
+def _pad_center(v: np.ndarray, size: int) -> np.ndarray:
+    # librosa.util.pad_center along the last axis: zeros, the odd one on the right (data.py:589, 626)
+    lpad = (size - v.shape[-1]) // 2
+    width = [(0, 0)] * (v.ndim - 1) + [(lpad, size - v.shape[-1] - lpad)]
+    return np.pad(v, width)
+
+
+def stft_frames_dev(frames, n_fft: int, window: np.ndarray):
+    """np.fft.rfft(window * pad_center(frame, n_fft)) for every row of frames [F, frame_length] (device tensor or
+    numpy) on ofp_stft_frames -> complex64 device tensor [F, n_fft/2 + 1]."""
+    torch = _lib.require_cuda()
+    fr = _to_dev(np.ascontiguousarray(frames, dtype=np.float32) if isinstance(frames, np.ndarray) else frames, torch)
+    fr = fr.float().contiguous()
+    F, flen = fr.shape
+    wd = torch.from_numpy(np.ascontiguousarray(window, dtype=np.float64)).cuda()
+    if wd.numel() != n_fft:
+        raise ValueError(f"window of {wd.numel()} samples for n_fft = {n_fft}")
+    out = torch.empty((F, n_fft // 2 + 1, 2), dtype=torch.float32, device="cuda")
+    check(_lib.lib().ofp_stft_frames(ptr(fr), C.c_int64(F), C.c_int32(flen), C.c_int32(n_fft), ptr(wd), ptr(out),
+                                     stream_ptr()))
+    return torch.view_as_complex(out)
+
+
+def stft_frame(x: np.ndarray, n_fft: int, window: np.ndarray) -> np.ndarray:
+    """Drop-in for data.stft_frame (data.py:580-590): one frame (or [C, frame] rows) -> rfft(window * x), with x
+    centred in n_fft points when it is shorter.  The reference returns numpy's complex128; the transform here runs in
+    double on the device and returns complex64, the precision ``stft`` stores it in."""
+    x = np.asarray(x)
+    rows = x.reshape(-1, x.shape[-1])
+    if rows.shape[-1] > n_fft:
+        raise ValueError("operands could not be broadcast together")  # what window * x raises in the reference
+    S = stft_frames_dev(rows, n_fft, window).cpu().numpy()
+    return S.reshape(x.shape[:-1] + (n_fft // 2 + 1,))
+
+
+def stft_batch(audio, onsets, frame_length: int = 256, hop_length: int = 64, n_fft: int = 512,
+               hop_edge_padding: bool = False, method: str = "zerozero"):
+    """``stft`` (data.py:593-654) around MANY onsets of one recording in one launch: audio [N] or [C, N], onsets [H]
+    -> complex64 device tensor [H, (C,) n_fft/2 + 1, n_frames].  The padded excerpts are assembled on the device
+    (zeros / preceding audio in front, zeros or nothing behind, per ``method``) and cut into hop-spaced frames."""
+    torch = _lib.require_cuda()
+    a = _to_dev(np.ascontiguousarray(audio, dtype=np.float32) if isinstance(audio, np.ndarray) else audio, torch).float()
+    mono = a.dim() == 1
+    if mono:
+        a = a[None]
+    Cn, N = a.shape
+    on = torch.as_tensor(np.asarray(onsets, dtype=np.int64)).cuda().reshape(-1)
+    H = on.numel()
+    pad = frame_length - hop_length if hop_edge_padding else frame_length // 2
+    if method not in ("zerozero", "prezero", "pre"):
+        raise ValueError(f"method {method!r}")
+    if H and (int(on.min()) < (0 if method == "zerozero" else pad) or int(on.max()) + frame_length > N):
+        raise IndexError("stft excerpt outside the recording")
+    body = a[:, (on[:, None] + torch.arange(frame_length, device="cuda")[None]).reshape(-1)]
+    body = body.reshape(Cn, H, frame_length).permute(1, 0, 2)                       # [H, C, frame_length]
+    zeros = torch.zeros((H, Cn, pad), dtype=torch.float32, device="cuda")
+    if method == "zerozero":
+        front = zeros
+    else:
+        pre = a[:, (on[:, None] - pad + torch.arange(pad, device="cuda")[None]).reshape(-1)]
+        front = pre.reshape(Cn, H, pad).permute(1, 0, 2)
+    y = torch.cat([front, body] + ([] if method == "pre" else [zeros]), dim=-1)     # [H, C, Ly]
+    n_frames = 1 + (y.shape[-1] - frame_length) // hop_length
+    frames = y.unfold(-1, frame_length, hop_length)[..., :n_frames, :].contiguous()  # [H, C, n_frames, frame_length]
+    window = _hann_periodic(frame_length)
+    if n_fft > frame_length:
+        window = _pad_center(window, n_fft)
+    S = stft_frames_dev(frames.reshape(-1, frame_length), n_fft, window)
+    S = S.reshape(H, Cn, n_frames, n_fft // 2 + 1).permute(0, 1, 3, 2)               # [H, C, bins, n_frames]
+    return S[:, 0] if mono else S
+
+
+def stft(audio: np.ndarray, onset: int, frame_length: int = 256, hop_length: int = 64, n_fft: int = 512,
+         hop_edge_padding: bool = False, method: str = "zerozero") -> np.ndarray:
+    """Drop-in for data.stft (data.py:593-654): complex64 [(C,) n_fft/2 + 1, n_frames] around one onset."""
+    S = stft_batch(audio, [int(onset)], frame_length, hop_length, n_fft, hop_edge_padding, method)[0]
+    return S.cpu().numpy()
 
 
 class MCPOSD:

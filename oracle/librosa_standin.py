@@ -70,11 +70,30 @@ def peak_pick(x, *, pre_max, post_max, pre_avg, post_avg, delta, wait):
     return np.array(peaks, dtype=int)
 
 
+def get_window(window, Nx, *, fftbins=True):
+    """librosa.filters.get_window for a window given by name: scipy.signal.get_window (periodic for fftbins)."""
+    return scipy.signal.get_window(window, Nx, fftbins=fftbins)
+
+
+def pad_center(data, *, size, axis=-1, **kw):
+    """librosa.util.pad_center: zeros on both sides, the left pad is (size - n) // 2."""
+    n = data.shape[axis]
+    lpad = int((size - n) // 2)
+    widths = [(0, 0)] * data.ndim
+    widths[axis] = (lpad, int(size - n - lpad))
+    if lpad < 0:
+        raise ValueError(f"Target size ({size}) must be at least input size ({n})")
+    return np.pad(data, widths, **kw)
+
+
 def module() -> types.ModuleType:
     m = types.ModuleType("librosa")
     m.stft, m.A_weighting = stft, A_weighting
     m.util = types.ModuleType("librosa.util")
     m.util.peak_pick = peak_pick
+    m.util.pad_center = pad_center
+    m.filters = types.ModuleType("librosa.filters")
+    m.filters.get_window = get_window
     m.__standin__ = True
     return m
 

@@ -642,8 +642,42 @@ def gen_spectral(det):
 
 
 
+STFT_CASES = [
+    dict(),
+    dict(method="prezero"),
+    dict(method="pre", hop_edge_padding=True),
+    dict(frame_length=128, hop_length=32, n_fft=128, method="prezero"),
+    dict(frame_length=200, hop_length=50, n_fft=256, hop_edge_padding=True),
+]
+STFT_ONSETS = [49100, 60391, 71700]
+
+
+def stft_inputs():
+    x, _ = synth.drum_recording(seconds=1.0, seed=14)
+    return np.ascontiguousarray(x.T)  # [C, N], the layout data.stft indexes (audio[..., onset:...])
+
+
+def gen_stft():
+    """data.stft / window_contribution_weights (data.py:560-654) of the unmodified reference; librosa's get_window /
+    pad_center come from oracle/librosa_standin.py (scipy.signal.get_window, zero padding)."""
+    data = rh.load_reference_data()
+    a = stft_inputs()
+    out = {"env": env(), "x_sha": sha(a)}
+    for i, kw in enumerate(STFT_CASES):
+        out[f"S{i}"] = np.stack([data.stft(a, o, **kw) for o in STFT_ONSETS])
+        out[f"M{i}"] = data.stft(a[1].copy(), STFT_ONSETS[0], **kw)
+    w = np.hanning(256)
+    out["wcw"] = data.window_contribution_weights(w, 64)
+    out["wcw_edge"] = data.window_contribution_weights(w, 64, True)
+    np.savez_compressed(OUT / "stft.npz", **out)
+    print("stft ok", [out[f"S{i}"].shape for i in range(len(STFT_CASES))])
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    if "stft" in sys.argv:
+        gen_stft()
+        return
     if "fsm" in sys.argv:
         gen_stream_fsm(rh.load_reference()[1])
         return
@@ -684,6 +718,7 @@ def main():
     gen_hits16(det)
     gen_stream_ring(det, ml)
     gen_spectral(det)
+    gen_stft()
 
 
 if __name__ == "__main__":

@@ -78,6 +78,7 @@ def load_reference():
 
         sys.modules["librosa"] = librosa_standin.module()
         sys.modules["librosa.util"] = sys.modules["librosa"].util
+        sys.modules["librosa.filters"] = sys.modules["librosa"].filters
     sys.modules["loopmate.circular_array"].CircularArray = RingStub
     sys.modules["loopmate"].circular_array = sys.modules["loopmate.circular_array"]
 

@@ -73,3 +73,35 @@ def tempogram_frame(oe_last, window):
     spec = np.fft.rfft(window.astype(np.float64) * oe_last.astype(np.float64), n=pad)
     tg = np.fft.irfft(spec.real ** 2 + spec.imag ** 2, n=pad)[:W]
     return (tg / (tg.max() + 1e-10)).astype(np.float32)
+
+
+def stft_around_onset(audio, onset, frame_length=256, hop_length=64, n_fft=512, hop_edge_padding=False,
+                      method="zerozero"):
+    """data.stft (data.py:593-654) restated: the excerpt after the onset, padded in front with zeros or the
+    preceding audio and behind with zeros or nothing, cut into hop-spaced frames; every frame centred in n_fft
+    points, multiplied by the (pad-centred) periodic Hann window of frame_length and transformed with numpy's
+    double-precision rfft; stored as complex64 [(C,) n_fft/2 + 1, n_frames]."""
+    audio = np.asarray(audio)
+    pad = frame_length - hop_length if hop_edge_padding else frame_length // 2
+    y = audio[..., onset:onset + frame_length]
+    z = np.zeros(y.shape[:-1] + (pad,), np.float32)
+    pre = audio[..., onset - pad:onset]
+    y = np.concatenate({"zerozero": (z, y, z), "prezero": (pre, y, z), "pre": (pre, y)}[method], axis=-1)
+    window = hann(frame_length, periodic=True).astype(np.float64)
+    lw = (n_fft - frame_length) // 2
+    window = np.pad(window, (lw, n_fft - frame_length - lw))
+    n_frames = 1 + (y.shape[-1] - frame_length) // hop_length
+    out = np.empty(y.shape[:-1] + (n_fft // 2 + 1, n_frames), np.complex64)
+    for i in range(n_frames):
+        fr = y[..., hop_length * i:hop_length * i + frame_length]
+        fr = np.pad(fr, [(0, 0)] * (fr.ndim - 1) + [(lw, n_fft - frame_length - lw)])
+        out[..., i] = np.fft.rfft(window * fr)
+    return out
+
+
+def window_contribution_weights(window, hop_length, hop_edge_padding=False):
+    """data.py:560-577."""
+    start = hop_length if hop_edge_padding else len(window) // 2
+    w = [np.trapezoid(window[:i]) for i in range(start, len(window) + hop_length, hop_length)]
+    w = w + w[-2::-1]
+    return np.array(w) / max(w)

@@ -154,3 +154,36 @@ def test_warp_kernel_equals_generic_kernel_2048(channels, monkeypatch):
     # a batch that is a strided view (every other recording of a larger buffer)
     big = torch.from_numpy((rng.standard_normal((6, N, channels)) * 0.05).astype(np.float32)).cuda()
     assert torch.equal(spectral.spectral_flux_batch(big[::2], 2048, 128), spectral.spectral_flux_batch(big[::2].contiguous(), 2048, 128))
+
+
+def test_stft_around_onsets_vs_reference_golden(golden_dir):
+    """data.stft / stft_frame / window_contribution_weights (data.py:560-654) on ofp_stft_frames against the unmodified
+    reference's output (tests/golden/stft.npz).  Floating-point bar: numpy transforms `window * x` in double and the
+    result is stored as complex64; the kernel transforms in double as well (radix-2 Stockham) and rounds once, so
+    the two agree to 1e-6 of the largest bin (an ulp or two of complex64)."""
+    from onset_fingerprinting_b200 import data
+    from oracle.make_golden import STFT_CASES, STFT_ONSETS, stft_inputs
+
+    g = np.load(golden_dir / "stft.npz")
+    a = stft_inputs()
+    for i, kw in enumerate(STFT_CASES):
+        want, mono = g[f"S{i}"], g[f"M{i}"]
+        got = data.stft_batch(a, STFT_ONSETS, **kw).cpu().numpy()              # all onsets in one launch
+        assert got.shape == want.shape and got.dtype == np.complex64
+        assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max(), (i, float(np.abs(got - want).max()))
+        one = data.stft(a, STFT_ONSETS[1], **kw)                                # the reference's call
+        assert np.abs(one - want[1]).max() <= 1e-6 * np.abs(want).max()
+        got1 = data.stft(a[1].copy(), STFT_ONSETS[0], **kw)                     # mono audio
+        assert got1.shape == mono.shape and np.abs(got1 - mono).max() <= 1e-6 * np.abs(mono).max()
+    # stft_frame: one frame, shorter than n_fft -> centred
+    fr = a[:, 50000:50200]
+    win = np.pad(np.hanning(200), (28, 28))
+    lw = (256 - 200) // 2
+    want = np.fft.rfft(win * np.pad(fr, [(0, 0), (lw, 256 - 200 - lw)])).astype(np.complex64)
+    got = data.stft_frame(fr, 256, win)
+    assert got.shape == want.shape and np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+    w = np.hanning(256)
+    assert np.allclose(data.window_contribution_weights(w, 64), g["wcw"], rtol=1e-14, atol=0)
+    assert np.allclose(data.window_contribution_weights(w, 64, True), g["wcw_edge"], rtol=1e-14, atol=0)
+    with pytest.raises(IndexError):
+        data.stft(a, a.shape[1] - 10)

@@ -49,3 +49,24 @@ def test_peak_pick_loop_equals_filter_formulation():
         want = ls.peak_pick(x, **args)
         got = spectral_np.peak_pick(x, **args)
         assert got.tolist() == want.tolist(), (trial, args)
+
+
+def test_stft_around_onset_and_contribution_weights(golden_dir):
+    """oracle/spectral_np.stft_around_onset against data.stft of the unmodified reference (tests/golden/stft.npz,
+    generated over the stand-in for librosa's get_window / pad_center): both transform in double and round once to
+    complex64, so they agree to an ulp of the largest bin."""
+    from oracle.make_golden import STFT_CASES, STFT_ONSETS, stft_inputs
+
+    g = np.load(golden_dir / "stft.npz")
+    a = stft_inputs()
+    assert hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest() == str(g["x_sha"])
+    for i, kw in enumerate(STFT_CASES):
+        want, mono = g[f"S{i}"], g[f"M{i}"]
+        got = np.stack([spectral_np.stft_around_onset(a, o, **kw) for o in STFT_ONSETS])
+        assert got.shape == want.shape and got.dtype == want.dtype == np.complex64
+        assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
+        got1 = spectral_np.stft_around_onset(a[1].copy(), STFT_ONSETS[0], **kw)
+        assert got1.shape == mono.shape and np.abs(got1 - mono).max() <= 1e-6 * np.abs(mono).max()
+    w = np.hanning(256)
+    assert np.array_equal(spectral_np.window_contribution_weights(w, 64), g["wcw"])
+    assert np.array_equal(spectral_np.window_contribution_weights(w, 64, True), g["wcw_edge"])
