@@ -1104,8 +1104,29 @@ static int launch_k1(ofp_detector *det, const float *x, int64_t n_samples, int64
     a.on_ch = on_ch; a.on_idx = on_idx; a.on_cnt = on_cnt; a.cap = cap;
     a.R = static_cast<int32_t>(det->n_streams);
     a.G = 32 / C;
-    a.T = pick_tile(C, env_int("OFP_K1_TILECAP", 48), (B % KU == 0) ? KU : 1);
+    const int tile_mult = (B % KU == 0) ? KU : 1;
+    a.T = pick_tile(C, env_int("OFP_K1_TILECAP", 48), tile_mult);
     OFP_REQUIRE(a.T > 0, "no valid tile length for %d channels", C);
+    if (env_int("OFP_K1_TILE", 0) <= 0) {
+        // The tile length also decides how many one-warp CTAs an SM holds (stages + block buffer + tables).  A grid
+        // that needs k CTAs per SM to be resident at once should get them: with one fewer the launch runs in two
+        // waves (2 and 4 channels: 72-74 ms instead of ~52 for the 10 000 x 5 s batch).  Among the valid tiles take
+        // the one with the highest useful residency, longer tiles first.
+        const int grid_ctas = (a.R + a.G - 1) / a.G, need = (grid_ctas + sm_count() - 1) / sm_count();
+        const int want_rel = ((C + 3) / 4 * 4) % 32, bc4r = (B * C + 3) / 4 * 4;
+        const size_t fixed = K1_SMEM_HEADER + static_cast<size_t>(a.G) * (bc4r + ((want_rel - bc4r % 32) + 32) % 32) * 4;
+        const int nst_env = std::max(2, std::min(8, env_int("OFP_K1_STAGES", 2)));
+        int best_t = a.T, best_r = -1;
+        for (int cap_t = env_int("OFP_K1_TILECAP", 48); cap_t >= tile_mult; cap_t -= tile_mult) {
+            const int t = pick_tile(C, cap_t, tile_mult);
+            if (t <= 0) continue;
+            const size_t stage = (static_cast<size_t>(a.G) * t * C * 4 + 127) / 128 * 128;
+            const int resident = static_cast<int>((227 * 1024) / (fixed + nst_env * stage + 1024));
+            const int useful = std::min(resident, need);
+            if (useful > best_r) { best_r = useful; best_t = t; }
+        }
+        a.T = best_t;
+    }
     a.TC = a.T * C;
     {
         // pad the rows of a stage so that the G rows start 4 banks apart (the per-sample LDS of a warp touches one
